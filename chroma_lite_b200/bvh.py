@@ -1,0 +1,90 @@
+"""BVH data model in the reference node format plus the builder entry point.
+
+Node packing (chroma/bvh/bvh.py:8-41, chroma/cuda/geometry_types.h:86-96):
+uint4 {x,y,z = lo16 | hi16<<16 ; w = nchild<<28 | child}; leaf <=> nchild == 0 and
+child is the triangle id; world = origin + q*scale.  The build itself runs in
+libchroma_b200.so (cb_bvh_build: Morton sort on the GPU, layer grouping in C++).
+"""
+import ctypes as C
+import numpy as np
+
+from . import _lib
+from .gpuarray import vec
+
+uint4 = vec.uint4
+CHILD_BITS = 28
+NCHILD_MASK = np.uint32(0xF0000000)
+
+
+def unpack_nodes(nodes):
+    out = np.empty(len(nodes), dtype=[('xlo', np.uint16), ('xhi', np.uint16), ('ylo', np.uint16),
+                                      ('yhi', np.uint16), ('zlo', np.uint16), ('zhi', np.uint16),
+                                      ('child', np.uint64), ('nchild', np.uint16)])
+    for axis in 'xyz':
+        out[axis + 'lo'] = nodes[axis] & 0xFFFF
+        out[axis + 'hi'] = nodes[axis] >> 16
+    out['child'] = nodes['w'] & ~NCHILD_MASK
+    out['nchild'] = nodes['w'] >> CHILD_BITS
+    return out
+
+
+class WorldCoords(object):
+    """world = world_origin + fixed * world_scale (chroma/bvh/bvh.py:44-94)."""
+
+    MAX_INT = 2 ** 16 - 1
+
+    def __init__(self, world_origin, world_scale):
+        self.world_origin = np.array(world_origin, dtype=np.float32)
+        self.world_scale = np.float32(world_scale)
+
+    def world_to_fixed(self, world):
+        fixed = ((np.asarray(world) - self.world_origin) / self.world_scale).round()
+        if int(fixed.max()) > self.MAX_INT or fixed.min() < 0:
+            raise ValueError('world coordinates outside the 16-bit fixed point range')
+        return fixed.astype(np.uint16)
+
+    def fixed_to_world(self, fixed):
+        return np.asarray(fixed) * self.world_scale + self.world_origin
+
+
+class BVH(object):
+    def __init__(self, world_coords, nodes, layer_offsets):
+        self.world_coords = world_coords
+        self.nodes = nodes
+        self.layer_offsets = list(layer_offsets)
+        layer = np.zeros(len(nodes), dtype=np.uint32)
+        for i, start in enumerate(self.layer_offsets):
+            layer[start:] = i
+        self.layer_lookup = layer
+
+    def get_layer(self, layer_number):
+        start = self.layer_offsets[layer_number]
+        end = self.layer_offsets[layer_number + 1] if layer_number + 1 < len(self.layer_offsets) else len(self.nodes)
+        return self.nodes[start:end]
+
+    def layer_count(self):
+        return len(self.layer_offsets)
+
+    def __len__(self):
+        return len(self.nodes)
+
+
+def make_recursive_grid_bvh(mesh, target_degree=3):
+    """Recursive-grid BVH (behaviour of chroma/bvh/grid.py:11-95): one leaf per
+    triangle, Morton-ordered, parents formed by dropping low Morton bits until the
+    mean fan-out reaches target_degree, <= 15 children, single-child chains collapsed."""
+    lib = _lib.lib()
+    v = np.ascontiguousarray(mesh.vertices, dtype=np.float32)
+    t = np.ascontiguousarray(mesh.triangles, dtype=np.uint32)
+    origin = (C.c_float * 3)()
+    scale = C.c_float()
+    nnodes = C.c_uint64()
+    nlayers = C.c_int32()
+    _lib.check(lib.cb_bvh_build(v.ctypes.data, len(v), t.ctypes.data, len(t), int(target_degree),
+                                C.byref(origin), C.byref(scale), None, C.byref(nnodes), None, C.byref(nlayers)))
+    nodes = np.empty(nnodes.value, dtype=uint4)
+    layers = np.empty(nlayers.value, dtype=np.uint64)
+    _lib.check(lib.cb_bvh_build(v.ctypes.data, len(v), t.ctypes.data, len(t), int(target_degree),
+                                C.byref(origin), C.byref(scale), nodes.ctypes.data, C.byref(nnodes),
+                                layers.ctypes.data, C.byref(nlayers)))
+    return BVH(WorldCoords(np.array(list(origin), dtype=np.float32), scale.value), nodes, layers.astype(np.int64))

@@ -1,0 +1,917 @@
+// engine.cuh -- device-side building blocks of the B200 photon transport engine:
+// vector helpers, XORWOW, the BVH traversal and the optical physics.
+//
+// Reference behaviour followed (NOT its code structure): chroma/cuda/mesh.h,
+// intersect.h, geometry.h, photon.h, random.h, interpolate.h, rotate.h.  The
+// arithmetic expression shapes deliberately match the reference's so that, built
+// with the same nvcc flags (--use_fast_math, default -fmad), decisions replay.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuComplex.h>
+#include <stdint.h>
+#include <float.h>
+#include "../../include/chroma_b200.h"
+
+namespace cb {
+
+// ------------------------------------------------------------------ vectors
+__device__ __forceinline__ float3 f3(float x, float y, float z) { return make_float3(x, y, z); }
+__device__ __forceinline__ float3 operator-(const float3& a) { return f3(-a.x, -a.y, -a.z); }
+__device__ __forceinline__ float3 operator+(const float3& a, const float3& b) { return f3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ float3 operator-(const float3& a, const float3& b) { return f3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ float3 operator*(const float3& a, float c) { return f3(a.x * c, a.y * c, a.z * c); }
+__device__ __forceinline__ float3 operator*(float c, const float3& a) { return f3(c * a.x, c * a.y, c * a.z); }
+__device__ __forceinline__ float3 operator/(const float3& a, float c) { return f3(a.x / c, a.y / c, a.z / c); }
+__device__ __forceinline__ float dot(const float3& a, const float3& b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ float3 cross(const float3& a, const float3& b)
+{
+    return f3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+__device__ __forceinline__ float norm(const float3& a) { return sqrtf(dot(a, a)); }
+__device__ __forceinline__ float3 normalize(const float3& a) { return a / norm(a); }
+
+#define CB_SPEED_OF_LIGHT 299.792458f
+#define CB_PI 3.141592653589793f
+#define CB_WEIGHT_LOWER_THRESHOLD 0.0001f
+#define CB_TERMINAL (CB_NO_HIT | CB_BULK_ABSORB | CB_SURFACE_DETECT | CB_SURFACE_ABSORB | CB_NAN_ABORT)
+
+// rotate `a` through phi about axis n (behaviour of chroma/cuda/rotate.h:22-28)
+__device__ __forceinline__ float3 rotate(const float3& a, float phi, const float3& n)
+{
+    float cos_phi = cosf(phi);
+    float sin_phi = sinf(phi);
+    return a * cos_phi + n * dot(a, n) * (1.0f - cos_phi) + cross(a, n) * sin_phi;
+}
+
+// ------------------------------------------------------------------ XORWOW
+// Compact 24-byte state {d, v[5]}: bit-compatible stream with cuRAND's
+// curandStateXORWOW (curand_kernel.h:863-874); Box-Muller cache kept separately
+// by the one caller that needs normals (run_daq_many).
+struct Rng {
+    uint32_t d, v0, v1, v2, v3, v4;
+};
+
+__device__ __forceinline__ uint32_t rng_next(Rng& s)
+{
+    uint32_t t = s.v0 ^ (s.v0 >> 2);
+    s.v0 = s.v1; s.v1 = s.v2; s.v2 = s.v3; s.v3 = s.v4;
+    s.v4 = (s.v4 ^ (s.v4 << 4)) ^ (t ^ (t << 1));
+    s.d += 362437u;
+    return s.v4 + s.d;
+}
+// curand_uniform: (0, 1]  (curand_uniform.h:69-72)
+__device__ __forceinline__ float rng_uniform(Rng& s)
+{
+    return rng_next(s) * 2.3283064e-10f + (2.3283064e-10f / 2.0f);
+}
+__device__ __forceinline__ float rng_range(Rng& s, float low, float high)
+{
+    return low + rng_uniform(s) * (high - low);
+}
+__device__ __forceinline__ Rng rng_load(const uint32_t* __restrict__ states, uint64_t i)
+{
+    const uint2* p = reinterpret_cast<const uint2*>(states + 6 * i);
+    uint2 a = p[0], b = p[1], c = p[2];
+    Rng r = {a.x, a.y, b.x, b.y, c.x, c.y};
+    return r;
+}
+__device__ __forceinline__ void rng_store(uint32_t* __restrict__ states, uint64_t i, const Rng& r)
+{
+    uint2* p = reinterpret_cast<uint2*>(states + 6 * i);
+    p[0] = make_uint2(r.d, r.v0); p[1] = make_uint2(r.v1, r.v2); p[2] = make_uint2(r.v3, r.v4);
+}
+// isotropic direction: theta first, then u (random.h:15-23)
+__device__ __forceinline__ float3 rng_sphere(Rng& s)
+{
+    float theta = rng_range(s, 0.0f, 2 * CB_PI);
+    float u = rng_range(s, -1.0f, 1.0f);
+    float c = sqrtf(1.0f - u * u);
+    return f3(c * cosf(theta), c * sinf(theta), u);
+}
+
+// ------------------------------------------------------------------ geometry view
+struct DevGeometry {
+    const uint4*  nodes;      // reference packing, children of a node contiguous
+    const float4* tri48;      // 3 x float4 per triangle: v0.xyz v1.x | v1.yz v2.xy | v2.z rank code pad
+    const float*  tables;     // global table pool
+    const CbMaterial* materials;
+    const CbSurface*  surfaces;
+    float3 world_origin;
+    float  world_scale;
+    int32_t wavelength_n; float wavelength_start, wavelength_step;
+    int32_t time_n;       float time_start, time_step;
+    uint32_t root_w;          // root node's child word
+    uint32_t root_x, root_y, root_z;  // root node's packed box
+    uint32_t smem_floats;     // leading floats of the pool staged into shared memory
+    uint32_t nmaterials, nsurfaces;
+};
+
+// shared-memory view handed to the physics (tables staged by the kernel prologue)
+struct Tables {
+    const float* smem;        // may be nullptr when nothing is staged
+    const float* gmem;
+    uint32_t smem_floats;
+    __device__ __forceinline__ const float* at(int32_t off) const
+    {
+        return ((uint32_t)off < smem_floats) ? (smem + off) : (gmem + off);
+    }
+};
+
+struct TraverseCounters { uint32_t nodes, tris; };
+
+// ------------------------------------------------------------------ triangle test
+// Moller-Trumbore with the reference's tolerances and mixed precision
+// (behaviour of chroma/cuda/intersect.h:26-101): reject
+// |a| < FLT_EPSILON, reciprocal in double, u/v bounds +-1e-6 compared in
+// double, accept 1e-6 < t < inf.
+__device__ __forceinline__ bool hit_triangle(const float3& origin, const float3& direction,
+                                             const float3& v0, const float3& v1, const float3& v2,
+                                             float& distance)
+{
+    float3 edge1 = v1 - v0;
+    float3 edge2 = v2 - v0;
+    float3 h = cross(direction, edge2);
+    float a = dot(edge1, h);
+    if (a > -FLT_EPSILON && a < FLT_EPSILON) return false;
+    float f = 1.0 / a;
+    float3 s = origin - v0;
+    float u = f * dot(s, h);
+    if (u < -1e-6 || u > 1.0 + 1e-6) return false;
+    float3 q = cross(s, edge1);
+    float v = f * dot(direction, q);
+    if (v < -1e-6 || u + v > 1.0 + 1e-6) return false;
+    float t = f * dot(edge2, q);
+    if (t > 1e-6 && t < __int_as_float(0x7f800000)) {
+        distance = t;
+        return true;
+    }
+    return false;
+}
+
+// exact uint16 -> float without the (quarter-rate) I2F unit
+__device__ __forceinline__ float u16f_lo(uint32_t w) { return __uint_as_float((w & 0xFFFFu) | 0x4B000000u) - 8388608.0f; }
+__device__ __forceinline__ float u16f_hi(uint32_t w) { return __uint_as_float((w >> 16) | 0x4B000000u) - 8388608.0f; }
+
+struct RaySetup {
+    float3 inv, noid;          // 1/d and -o/d  (mesh.h:57-58)
+    bool fx, fy, fz;           // isfinite(inv.*)  (intersect.h:120-146)
+};
+
+// slab test on a packed node, same dequantisation and arithmetic as
+// geometry.h:31-47 + intersect.h:112-157.  Returns tmin through `tnear`.
+__device__ __forceinline__ bool hit_box(const DevGeometry& g, const RaySetup& r, uint32_t px,
+                                        uint32_t py, uint32_t pz, float& tnear)
+{
+    const float INF = __int_as_float(0x7f800000);
+    float tmin = 0.0f, tmax = INF;
+    if (r.fx) {
+        float lo = g.world_origin.x + u16f_lo(px) * g.world_scale;
+        float hi = g.world_origin.x + u16f_hi(px) * g.world_scale;
+        float t0 = lo * r.inv.x + r.noid.x;
+        float t1 = hi * r.inv.x + r.noid.x;
+        tmin = fmaxf(tmin, fminf(t0, t1));
+        tmax = fminf(tmax, fmaxf(t0, t1));
+    }
+    if (r.fy) {
+        float lo = g.world_origin.y + u16f_lo(py) * g.world_scale;
+        float hi = g.world_origin.y + u16f_hi(py) * g.world_scale;
+        float t0 = lo * r.inv.y + r.noid.y;
+        float t1 = hi * r.inv.y + r.noid.y;
+        tmin = fmaxf(tmin, fminf(t0, t1));
+        tmax = fminf(tmax, fmaxf(t0, t1));
+    }
+    if (r.fz) {
+        float lo = g.world_origin.z + u16f_lo(pz) * g.world_scale;
+        float hi = g.world_origin.z + u16f_hi(pz) * g.world_scale;
+        float t0 = lo * r.inv.z + r.noid.z;
+        float t1 = hi * r.inv.z + r.noid.z;
+        tmin = fmaxf(tmin, fminf(t0, t1));
+        tmax = fminf(tmax, fmaxf(t0, t1));
+    }
+    tnear = tmin;
+    return !(tmin > tmax);
+}
+
+// ------------------------------------------------------------------ traversal
+// Nearest-hit search over the reference tree topology with
+//   * near-child-first ordering and cull-at-pop (the reference does neither),
+//   * batched 128-bit node fetches (4 siblings in flight),
+//   * a lane-interleaved shared-memory short stack (conflict-free: entry e of
+//     lane l lives at stack[e*blockDim + l]) with a local-memory overflow area,
+//   * (distance, reference-test-rank) lexicographic minimum, which reproduces the
+//     reference's first-tested-wins tie rule under ANY visit order (SURVEY A-1).
+// Returns the triangle index or -1; `best_t` is the hit distance.
+constexpr int CB_SSTACK = 12;   // entries per lane in shared memory
+constexpr int CB_LSTACK = 52;   // overflow entries in local memory
+
+template <bool COUNT>
+__device__ __forceinline__ int traverse(const DevGeometry& g, const float3& origin,
+                                        const float3& direction, int last_hit, float& best_t,
+                                        uint2* sstack, int sstride, uint32_t* overflow_flag,
+                                        TraverseCounters* cnt)
+{
+    const float INF = __int_as_float(0x7f800000);
+    RaySetup r;
+    r.noid = f3(-origin.x / direction.x, -origin.y / direction.y, -origin.z / direction.z);
+    r.inv = f3(1.0f / direction.x, 1.0f / direction.y, 1.0f / direction.z);
+    r.fx = isfinite(r.inv.x); r.fy = isfinite(r.inv.y); r.fz = isfinite(r.inv.z);
+
+    int best_tri = -1;
+    uint32_t best_rank = 0xFFFFFFFFu;
+    best_t = INF;
+
+    float tn;
+    if (!hit_box(g, r, g.root_x, g.root_y, g.root_z, tn)) { best_t = -1.0f; return -1; }
+
+    uint2 lstack[CB_LSTACK];
+    int sp = 0;
+    uint32_t cur = g.root_w;     // node group being expanded: nchild<<28 | first
+    float top_t = INF;           // tmin of the entry on top of the stack (valid when sp > 0)
+
+    while (true) {
+        const uint32_t first = cur & 0x0FFFFFFFu;
+        const uint32_t n = cur >> 28;
+        for (uint32_t i = 0; i < n; i += 4) {
+            uint4 nd[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                uint32_t idx = first + min(i + k, n - 1);
+                nd[k] = __ldg(&g.nodes[idx]);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (i + k < n) {
+                    if (COUNT) cnt->nodes++;
+                    float tmin;
+                    if (hit_box(g, r, nd[k].x, nd[k].y, nd[k].z, tmin) && !(tmin > best_t)) {
+                        const uint32_t w = nd[k].w;
+                        if ((w >> 28) == 0) {
+                            if ((int)w != last_hit) {
+                                if (COUNT) cnt->tris++;
+                                const float4* tp = g.tri48 + 3ull * w;
+                                float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+                                float t;
+                                if (hit_triangle(origin, direction, f3(a.x, a.y, a.z), f3(a.w, b.x, b.y),
+                                                 f3(b.z, b.w, c.x), t)) {
+                                    uint32_t rank = __float_as_uint(c.y);
+                                    if (t < best_t || (t == best_t && rank < best_rank)) {
+                                        best_t = t; best_tri = (int)w; best_rank = rank;
+                                    }
+                                }
+                            }
+                        } else {
+                            // push, keeping the nearest entry on top
+                            uint2 e = make_uint2(w, __float_as_uint(tmin));
+                            if (sp > 0 && tmin > top_t) {
+                                // new entry goes below the current top
+                                uint2 top = (sp - 1 < CB_SSTACK) ? sstack[(sp - 1) * sstride] : lstack[sp - 1 - CB_SSTACK];
+                                if (sp - 1 < CB_SSTACK) sstack[(sp - 1) * sstride] = e; else lstack[sp - 1 - CB_SSTACK] = e;
+                                e = top;
+                            } else {
+                                top_t = tmin;
+                            }
+                            if (sp < CB_SSTACK) sstack[sp * sstride] = e;
+                            else if (sp < CB_SSTACK + CB_LSTACK) lstack[sp - CB_SSTACK] = e;
+                            else { atomicOr(overflow_flag, 1u); sp--; }
+                            sp++;
+                        }
+                    }
+                }
+            }
+        }
+        // pop the next group whose box can still contain a nearer hit
+        bool found = false;
+        while (sp > 0) {
+            sp--;
+            uint2 e = (sp < CB_SSTACK) ? sstack[sp * sstride] : lstack[sp - CB_SSTACK];
+            if (sp > 0) {
+                uint2 nt = (sp - 1 < CB_SSTACK) ? sstack[(sp - 1) * sstride] : lstack[sp - 1 - CB_SSTACK];
+                top_t = __uint_as_float(nt.y);
+            }
+            if (!(__uint_as_float(e.y) > best_t)) { cur = e.x; found = true; break; }
+        }
+        if (!found) break;
+    }
+    if (best_tri == -1) best_t = -1.0f;
+    return best_tri;
+}
+
+// ------------------------------------------------------------------ physics
+struct Photon {
+    float3 pos, dir, pol;
+    float wavelength, time, weight;
+    uint32_t history;        // 16 significant bits (photon.h:29)
+    int last_hit_triangle;
+};
+
+struct StepState {
+    float3 normal;
+    float n1, n2, absorption_length, scattering_length;
+    const CbMaterial* material1;
+    int surface_index;
+    float distance;
+};
+
+enum { CMD_BREAK = 0, CMD_CONTINUE = 1, CMD_PASS = 2 };
+
+// clamp-then-linear table lookup on the uniform wavelength grid (geometry.h:61-74)
+__device__ __forceinline__ float interp_property(const DevGeometry& g, float x, const float* fp)
+{
+    if (x < g.wavelength_start) return fp[0];
+    if (x > (g.wavelength_start + (g.wavelength_n - 1) * g.wavelength_step)) return fp[g.wavelength_n - 1];
+    int jl = (x - g.wavelength_start) / g.wavelength_step;
+    return fp[jl] + (x - (g.wavelength_start + jl * g.wavelength_step)) * (fp[jl + 1] - fp[jl]) / g.wavelength_step;
+}
+
+// inverse-CDF sampling on a uniform x grid (random.h:33-55)
+__device__ __forceinline__ float sample_cdf_uniform(Rng& rng, int ncdf, float x0, float delta, const float* cdf_y)
+{
+    float u = rng_uniform(rng);
+    int lower = 0, upper = ncdf - 1;
+    while (lower < upper - 1) {
+        int half = (lower + upper) / 2;
+        if (u < cdf_y[half]) upper = half; else lower = half;
+    }
+    float delta_cdf_y = cdf_y[upper] - cdf_y[lower];
+    return x0 + delta * lower + delta * (u - cdf_y[lower]) / delta_cdf_y;
+}
+
+// piecewise-linear interpolation by bisection (interpolate.h:33-58)
+__device__ __forceinline__ float interp_xy(float x, int n, const float* xp, const float* fp)
+{
+    int lower = 0, upper = n - 1;
+    if (x <= xp[lower]) return fp[lower];
+    if (x >= xp[upper]) return fp[upper];
+    while (lower < upper - 1) {
+        int half = (lower + upper) / 2;
+        if (x < xp[half]) upper = half; else lower = half;
+    }
+    float df = fp[upper] - fp[lower];
+    float dx = xp[upper] - xp[lower];
+    return fp[lower] + df * (x - xp[lower]) / dx;
+}
+
+// fractional index of x in xp (interpolate.h:5-29)
+__device__ __forceinline__ float interp_idx(float x, int n, const float* xp)
+{
+    int lower = 0, upper = n - 1;
+    if (x <= xp[lower]) return lower;
+    if (x >= xp[upper]) return upper;
+    while (lower < upper - 1) {
+        int half = (lower + upper) / 2;
+        if (x < xp[half]) upper = half; else lower = half;
+    }
+    float dx = xp[upper] - xp[lower];
+    return lower + 1.0 * (x - xp[lower]) / dx;
+}
+
+__device__ __forceinline__ int sext8(int c) { return (c & 0x80) ? (0xFFFFFF00 | c) : c; }
+__device__ __forceinline__ float get_theta(const float3& a, const float3& b)
+{
+    return acosf(fmaxf(-1.0f, fminf(1.0f, dot(a, b))));
+}
+
+// Classify the boundary found by the traversal (mesh branch of fill_state,
+// photon.h:355-394).  `tri` >= 0.
+__device__ __forceinline__ void classify_hit(const DevGeometry& g, const Tables& T, Photon& p,
+                                             StepState& s, int tri)
+{
+    p.last_hit_triangle = tri;
+    const float4* tp = g.tri48 + 3ull * (uint32_t)tri;
+    float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+    float3 v0 = f3(a.x, a.y, a.z), v1 = f3(a.w, b.x, b.y), v2 = f3(b.z, b.w, c.x);
+    uint32_t material_code = __float_as_uint(c.z);
+    int inner = sext8(0xFF & (material_code >> 24));
+    int outer = sext8(0xFF & (material_code >> 16));
+    s.surface_index = sext8(0xFF & (material_code >> 8));
+
+    float3 v01 = v1 - v0;
+    float3 v12 = v2 - v1;
+    s.normal = normalize(cross(v01, v12));
+
+    const CbMaterial *m1, *m2;
+    if (dot(s.normal, -p.dir) > 0.0f) {
+        m1 = &g.materials[outer]; m2 = &g.materials[inner];
+    } else {
+        m1 = &g.materials[inner]; m2 = &g.materials[outer];
+        s.normal = -s.normal;
+    }
+    s.n1 = interp_property(g, p.wavelength, T.at(m1->refractive_index));
+    s.n2 = interp_property(g, p.wavelength, T.at(m2->refractive_index));
+    s.absorption_length = interp_property(g, p.wavelength, T.at(m1->absorption_length));
+    s.scattering_length = interp_property(g, p.wavelength, T.at(m1->scattering_length));
+    s.material1 = m1;
+}
+
+// new direction at polar angle theta / azimuth phi about `axis` (photon.h:399-424)
+__device__ __forceinline__ float3 pick_new_direction(float3 axis, float theta, float phi)
+{
+    float cos_theta, sin_theta;
+    sincosf(theta, &sin_theta, &cos_theta);
+    float cos_phi, sin_phi;
+    sincosf(phi, &sin_phi, &cos_phi);
+    float sin_axis_theta = sqrt(1.0f - axis.z * axis.z);
+    float cos_axis_phi, sin_axis_phi;
+    if (isnan(sin_axis_theta) || sin_axis_theta < 0.00001f) {
+        cos_axis_phi = 1.0f;
+        sin_axis_phi = 0.0f;
+    } else {
+        cos_axis_phi = axis.x / sin_axis_theta;
+        sin_axis_phi = axis.y / sin_axis_theta;
+    }
+    float dirx = cos_theta * axis.x + sin_theta * (axis.z * cos_phi * cos_axis_phi - sin_phi * sin_axis_phi);
+    float diry = cos_theta * axis.y + sin_theta * (cos_phi * axis.z * sin_axis_phi + sin_phi * cos_axis_phi);
+    float dirz = cos_theta * axis.z - sin_theta * cos_phi * sin_axis_theta;
+    return f3(dirx, diry, dirz);
+}
+
+// Rayleigh scattering about the polarisation axis (photon.h:426-453)
+__device__ __forceinline__ void rayleigh_scatter(Photon& p, Rng& rng)
+{
+    float cos_theta = 2.0f * cosf((acosf(1.0f - 2.0f * rng_uniform(rng)) - 2 * CB_PI) / 3.0f);
+    if (cos_theta > 1.0f) cos_theta = 1.0f;
+    else if (cos_theta < -1.0f) cos_theta = -1.0f;
+    float theta = acosf(cos_theta);
+    float phi = rng_range(rng, 0.0f, 2.0f * CB_PI);
+    p.dir = pick_new_direction(p.pol, theta, phi);
+    if (1.0f - fabsf(cos_theta) < 1e-6f) p.pol = pick_new_direction(p.pol, CB_PI / 2.0f, phi);
+    else p.pol = p.pol - cos_theta * p.dir;
+    p.dir = p.dir / norm(p.dir);
+    p.pol = p.pol / norm(p.pol);
+}
+
+// bulk step: absorption / re-emission / Rayleigh / reach boundary (photon.h:455-570)
+static __device__ __noinline__ int to_boundary(const DevGeometry& g, const Tables& T, Photon& p, StepState& s,
+                                        Rng& rng, bool use_weights, int scatter_first)
+{
+    float absorption_distance = -s.absorption_length * logf(rng_uniform(rng));
+    float scattering_distance = -s.scattering_length * logf(rng_uniform(rng));
+
+    if (use_weights && p.weight > CB_WEIGHT_LOWER_THRESHOLD) absorption_distance = 1e30;
+    else use_weights = false;
+
+    if (scatter_first == 1) {
+        float scatter_prob = 1.0f - expf(-s.distance / s.scattering_length);
+        if (scatter_prob > CB_WEIGHT_LOWER_THRESHOLD) {
+            int i = 0;
+            while (i < 1000 && scattering_distance > s.distance) {
+                scattering_distance = -s.scattering_length * logf(rng_uniform(rng));
+                i++;
+            }
+            p.weight *= scatter_prob;
+        }
+    } else if (scatter_first == -1) {
+        float no_scatter_prob = expf(-s.distance / s.scattering_length);
+        if (no_scatter_prob > CB_WEIGHT_LOWER_THRESHOLD) {
+            int i = 0;
+            while (i < 1000 && scattering_distance <= s.distance) {
+                scattering_distance = -s.scattering_length * logf(rng_uniform(rng));
+                i++;
+            }
+            p.weight *= no_scatter_prob;
+        }
+    }
+
+    if (absorption_distance <= scattering_distance) {
+        if (absorption_distance <= s.distance) {
+            p.time += absorption_distance / (CB_SPEED_OF_LIGHT / s.n1);
+            p.pos = p.pos + absorption_distance * p.dir;
+            const CbMaterial* m = s.material1;
+            if (m->num_comp == 0) {
+                p.last_hit_triangle = -1;
+                p.history |= CB_BULK_ABSORB;
+                return CMD_BREAK;
+            }
+            float uniform_sample_comp = rng_uniform(rng);
+            float prob = 0.0f;
+            int comp;
+            for (comp = 0;; comp++) {
+                float comp_abs = interp_property(g, p.wavelength, T.at(m->comp_absorption_length + comp * g.wavelength_n));
+                prob += s.absorption_length / comp_abs;
+                if (uniform_sample_comp < prob || comp + 1 == m->num_comp) break;
+            }
+            float uniform_sample_reemit = rng_uniform(rng);
+            float comp_reemit_prob = interp_property(g, p.wavelength, T.at(m->comp_reemission_prob + comp * g.wavelength_n));
+            if (uniform_sample_reemit < comp_reemit_prob) {
+                p.wavelength = sample_cdf_uniform(rng, g.wavelength_n, g.wavelength_start, g.wavelength_step,
+                                                  T.at(m->comp_reemission_wvl_cdf + comp * g.wavelength_n));
+                p.time += sample_cdf_uniform(rng, g.time_n, g.time_start, g.time_step,
+                                             T.at(m->comp_reemission_time_cdf + comp * g.time_n));
+                p.dir = rng_sphere(rng);
+                p.pol = cross(rng_sphere(rng), p.dir);
+                p.pol = p.pol / norm(p.pol);
+                p.last_hit_triangle = -1;
+                p.history |= CB_BULK_REEMIT;
+                return CMD_CONTINUE;
+            }
+            p.last_hit_triangle = -1;
+            p.history |= CB_BULK_ABSORB;
+            return CMD_BREAK;
+        }
+    } else {
+        if (scattering_distance <= s.distance) {
+            if (use_weights) p.weight *= expf(-scattering_distance / s.absorption_length);
+            p.time += scattering_distance / (CB_SPEED_OF_LIGHT / s.n1);
+            p.pos = p.pos + scattering_distance * p.dir;
+            rayleigh_scatter(p, rng);
+            p.history |= CB_RAYLEIGH_SCATTER;
+            p.last_hit_triangle = -1;
+            return CMD_CONTINUE;
+        }
+    }
+    if (use_weights) p.weight *= expf(-s.distance / s.absorption_length);
+    p.pos = p.pos + s.distance * p.dir;
+    p.time += s.distance / (CB_SPEED_OF_LIGHT / s.n1);
+    return CMD_PASS;
+}
+
+// Fresnel reflection / refraction (photon.h:572-632)
+static __device__ __noinline__ void at_boundary(Photon& p, StepState& s, Rng& rng)
+{
+    float incident_angle = get_theta(s.normal, -p.dir);
+    float refracted_angle = asinf(sinf(incident_angle) * s.n1 / s.n2);
+
+    float3 incident_plane_normal = cross(p.dir, s.normal);
+    float incident_plane_normal_length = norm(incident_plane_normal);
+    if (incident_plane_normal_length < 1e-6f) incident_plane_normal = p.pol;
+    else incident_plane_normal = incident_plane_normal / incident_plane_normal_length;
+
+    float normal_coefficient = dot(p.pol, incident_plane_normal);
+    float normal_probability = normal_coefficient * normal_coefficient;
+
+    float reflection_coefficient;
+    if (rng_uniform(rng) < normal_probability) {
+        reflection_coefficient = -sinf(incident_angle - refracted_angle) / sinf(incident_angle + refracted_angle);
+        if ((rng_uniform(rng) < reflection_coefficient * reflection_coefficient) || isnan(refracted_angle)) {
+            p.dir = rotate(s.normal, incident_angle, incident_plane_normal);
+            p.history |= CB_REFLECT_SPECULAR;
+        } else {
+            p.dir = rotate(s.normal, CB_PI - refracted_angle, incident_plane_normal);
+        }
+        p.pol = incident_plane_normal;
+    } else {
+        reflection_coefficient = tanf(incident_angle - refracted_angle) / tanf(incident_angle + refracted_angle);
+        if ((rng_uniform(rng) < reflection_coefficient * reflection_coefficient) || isnan(refracted_angle)) {
+            p.dir = rotate(s.normal, incident_angle, incident_plane_normal);
+            p.history |= CB_REFLECT_SPECULAR;
+        } else {
+            p.dir = rotate(s.normal, CB_PI - refracted_angle, incident_plane_normal);
+        }
+        p.pol = cross(incident_plane_normal, p.dir);
+        p.pol = p.pol / norm(p.pol);
+    }
+}
+
+// mirror reflection (photon.h:634-646)
+__device__ __forceinline__ int specular_reflect(Photon& p, const StepState& s)
+{
+    float incident_angle = get_theta(s.normal, -p.dir);
+    float3 incident_plane_normal = cross(p.dir, s.normal);
+    incident_plane_normal = incident_plane_normal / norm(incident_plane_normal);
+    p.dir = rotate(s.normal, incident_angle, incident_plane_normal);
+    p.history |= CB_REFLECT_SPECULAR;
+    return CMD_CONTINUE;
+}
+
+// Lambertian reflection by rejection (photon.h:648-667)
+__device__ __forceinline__ int diffuse_reflect(Photon& p, const StepState& s, Rng& rng)
+{
+    float ndotv;
+    do {
+        p.dir = rng_sphere(rng);
+        ndotv = dot(p.dir, s.normal);
+        if (ndotv < 0.0f) {
+            p.dir = -p.dir;
+            ndotv = -ndotv;
+        }
+    } while (!(rng_uniform(rng) < ndotv));
+    p.pol = cross(rng_sphere(rng), p.dir);
+    p.pol = p.pol / norm(p.pol);
+    p.history |= CB_REFLECT_DIFFUSE;
+    return CMD_CONTINUE;
+}
+
+// complex helpers the reference adds to cuComplex.h (cx.h:29-35)
+__device__ __forceinline__ float cx_arg(cuFloatComplex x) { return atan2f(x.y, x.x); }
+__device__ __forceinline__ cuFloatComplex cx_sqrt(cuFloatComplex x)
+{
+    float r = sqrtf(cuCabsf(x));
+    float t = cx_arg(x) / 2.0f;
+    return make_cuFloatComplex(r * cosf(t), r * sinf(t));
+}
+
+// thin-film surface (n1 | eta+ik, thickness | n3), photon.h:669-827
+static __device__ __noinline__ int surface_complex(const DevGeometry& g, const Tables& T, Photon& p, StepState& s,
+                                            Rng& rng, const CbSurface* surface, bool use_weights)
+{
+    float detect = interp_property(g, p.wavelength, T.at(surface->detect));
+    float reflect_diffuse = interp_property(g, p.wavelength, T.at(surface->reflect_diffuse));
+    float n2_eta = interp_property(g, p.wavelength, T.at(surface->eta));
+    float n2_k = interp_property(g, p.wavelength, T.at(surface->k));
+
+    cuFloatComplex n1 = make_cuFloatComplex(s.n1, 0.0f);
+    cuFloatComplex n2 = make_cuFloatComplex(n2_eta, n2_k);
+    cuFloatComplex n3 = make_cuFloatComplex(s.n2, 0.0f);
+
+    float cos_t1 = dot(p.dir, s.normal);
+    if (cos_t1 < 0.0f) cos_t1 = -cos_t1;
+    float theta = acosf(cos_t1);
+
+    cuFloatComplex cos1 = make_cuFloatComplex(cosf(theta), 0.0f);
+    cuFloatComplex sin1 = make_cuFloatComplex(sinf(theta), 0.0f);
+
+    float e = 2.0f * CB_PI * surface->thickness / p.wavelength;
+    cuFloatComplex ratio13sin = cuCmulf(cuCmulf(cuCdivf(n1, n3), cuCdivf(n1, n3)), cuCmulf(sin1, sin1));
+    cuFloatComplex cos3 = cx_sqrt(cuCsubf(make_cuFloatComplex(1.0f, 0.0f), ratio13sin));
+    cuFloatComplex ratio12sin = cuCmulf(cuCmulf(cuCdivf(n1, n2), cuCdivf(n1, n2)), cuCmulf(sin1, sin1));
+    cuFloatComplex cos2 = cx_sqrt(cuCsubf(make_cuFloatComplex(1.0f, 0.0f), ratio12sin));
+    float u = cuCrealf(cuCmulf(n2, cos2));
+    float v = cuCimagf(cuCmulf(n2, cos2));
+
+    // s polarisation
+    cuFloatComplex s_n1c1 = cuCmulf(n1, cos1);
+    cuFloatComplex s_n2c2 = cuCmulf(n2, cos2);
+    cuFloatComplex s_n3c3 = cuCmulf(n3, cos3);
+    cuFloatComplex s_r12 = cuCdivf(cuCsubf(s_n1c1, s_n2c2), cuCaddf(s_n1c1, s_n2c2));
+    cuFloatComplex s_r23 = cuCdivf(cuCsubf(s_n2c2, s_n3c3), cuCaddf(s_n2c2, s_n3c3));
+    cuFloatComplex s_t12 = cuCdivf(cuCmulf(make_cuFloatComplex(2.0f, 0.0f), s_n1c1), cuCaddf(s_n1c1, s_n2c2));
+    cuFloatComplex s_t23 = cuCdivf(cuCmulf(make_cuFloatComplex(2.0f, 0.0f), s_n2c2), cuCaddf(s_n2c2, s_n3c3));
+    cuFloatComplex s_g = cuCdivf(s_n3c3, s_n1c1);
+
+    float s_abs_r12 = cuCabsf(s_r12);
+    float s_abs_r23 = cuCabsf(s_r23);
+    float s_abs_t12 = cuCabsf(s_t12);
+    float s_abs_t23 = cuCabsf(s_t23);
+    float s_arg_r12 = cx_arg(s_r12);
+    float s_arg_r23 = cx_arg(s_r23);
+    float s_exp1 = exp(2.0f * v * e);
+    float s_exp2 = 1.0f / s_exp1;
+    float s_denom = s_exp1 + s_abs_r12 * s_abs_r12 * s_abs_r23 * s_abs_r23 * s_exp2 +
+                    2.0f * s_abs_r12 * s_abs_r23 * cosf(s_arg_r23 + s_arg_r12 + 2.0f * u * e);
+    float s_r = s_abs_r12 * s_abs_r12 * s_exp1 + s_abs_r23 * s_abs_r23 * s_exp2 +
+                2.0f * s_abs_r12 * s_abs_r23 * cosf(s_arg_r23 - s_arg_r12 + 2.0f * u * e);
+    s_r /= s_denom;
+    float s_t = cuCrealf(s_g) * s_abs_t12 * s_abs_t12 * s_abs_t23 * s_abs_t23;
+    s_t /= s_denom;
+
+    // p polarisation
+    cuFloatComplex p_n2c1 = cuCmulf(n2, cos1);
+    cuFloatComplex p_n3c2 = cuCmulf(n3, cos2);
+    cuFloatComplex p_n2c3 = cuCmulf(n2, cos3);
+    cuFloatComplex p_n1c2 = cuCmulf(n1, cos2);
+    cuFloatComplex p_r12 = cuCdivf(cuCsubf(p_n2c1, p_n1c2), cuCaddf(p_n2c1, p_n1c2));
+    cuFloatComplex p_r23 = cuCdivf(cuCsubf(p_n3c2, p_n2c3), cuCaddf(p_n3c2, p_n2c3));
+    cuFloatComplex p_t12 = cuCdivf(cuCmulf(cuCmulf(make_cuFloatComplex(2.0f, 0.0f), n1), cos1), cuCaddf(p_n2c1, p_n1c2));
+    cuFloatComplex p_t23 = cuCdivf(cuCmulf(cuCmulf(make_cuFloatComplex(2.0f, 0.0f), n2), cos2), cuCaddf(p_n3c2, p_n2c3));
+    cuFloatComplex p_g = cuCdivf(cuCmulf(n3, cos3), cuCmulf(n1, cos1));
+
+    float p_abs_r12 = cuCabsf(p_r12);
+    float p_abs_r23 = cuCabsf(p_r23);
+    float p_abs_t12 = cuCabsf(p_t12);
+    float p_abs_t23 = cuCabsf(p_t23);
+    float p_arg_r12 = cx_arg(p_r12);
+    float p_arg_r23 = cx_arg(p_r23);
+    float p_exp1 = exp(2.0f * v * e);
+    float p_exp2 = 1.0f / p_exp1;
+    float p_denom = p_exp1 + p_abs_r12 * p_abs_r12 * p_abs_r23 * p_abs_r23 * p_exp2 +
+                    2.0f * p_abs_r12 * p_abs_r23 * cosf(p_arg_r23 + p_arg_r12 + 2.0f * u * e);
+    float p_r = p_abs_r12 * p_abs_r12 * p_exp1 + p_abs_r23 * p_abs_r23 * p_exp2 +
+                2.0f * p_abs_r12 * p_abs_r23 * cosf(p_arg_r23 - p_arg_r12 + 2.0f * u * e);
+    p_r /= p_denom;
+    float p_t = cuCrealf(p_g) * p_abs_t12 * p_abs_t12 * p_abs_t23 * p_abs_t23;
+    p_t /= p_denom;
+
+    // s-polarisation fraction, as in at_boundary
+    float incident_angle = get_theta(s.normal, -p.dir);
+    float refracted_angle = asinf(sinf(incident_angle) * s.n1 / s.n2);
+    float3 incident_plane_normal = cross(p.dir, s.normal);
+    float incident_plane_normal_length = norm(incident_plane_normal);
+    if (incident_plane_normal_length < 1e-6f) incident_plane_normal = p.pol;
+    else incident_plane_normal = incident_plane_normal / incident_plane_normal_length;
+    float normal_coefficient = dot(p.pol, incident_plane_normal);
+    float normal_probability = normal_coefficient * normal_coefficient;
+
+    float transmit = normal_probability * s_t + (1.0f - normal_probability) * p_t;
+    if (!surface->transmissive) transmit = 0.0f;
+    float reflect = normal_probability * s_r + (1.0f - normal_probability) * p_r;
+    float absorb = 1.0f - transmit - reflect;
+
+    if (use_weights && p.weight > CB_WEIGHT_LOWER_THRESHOLD && absorb < (1.0f - CB_WEIGHT_LOWER_THRESHOLD)) {
+        float survive = 1.0f - absorb;
+        absorb = 0.0f;
+        p.weight *= survive;
+        detect /= survive;
+        reflect /= survive;
+        transmit /= survive;
+    }
+    if (use_weights && detect > 0.0f) {
+        p.history |= CB_SURFACE_DETECT;
+        p.weight *= detect;
+        return CMD_BREAK;
+    }
+
+    float uniform_sample = rng_uniform(rng);
+    if (uniform_sample < absorb) {
+        float uniform_sample_detect = rng_uniform(rng);
+        if (uniform_sample_detect < detect) p.history |= CB_SURFACE_DETECT;
+        else p.history |= CB_SURFACE_ABSORB;
+        return CMD_BREAK;
+    } else if (uniform_sample < absorb + reflect || !surface->transmissive) {
+        float uniform_sample_reflect = rng_uniform(rng);
+        if (uniform_sample_reflect < reflect_diffuse) return diffuse_reflect(p, s, rng);
+        return specular_reflect(p, s);
+    } else {
+        p.dir = rotate(s.normal, CB_PI - refracted_angle, incident_plane_normal);
+        p.pol = cross(incident_plane_normal, p.dir);
+        p.pol = p.pol / norm(p.pol);
+        p.history |= CB_SURFACE_TRANSMIT;
+        return CMD_CONTINUE;
+    }
+}
+
+// wavelength-shifting surface (photon.h:829-874)
+__device__ __forceinline__ int surface_wls(const DevGeometry& g, const Tables& T, Photon& p, StepState& s,
+                                           Rng& rng, const CbSurface* surface, bool use_weights)
+{
+    float absorb = interp_property(g, p.wavelength, T.at(surface->absorb));
+    float reflect_specular = interp_property(g, p.wavelength, T.at(surface->reflect_specular));
+    float reflect_diffuse = interp_property(g, p.wavelength, T.at(surface->reflect_diffuse));
+    float reemit = interp_property(g, p.wavelength, T.at(surface->reemit));
+
+    float uniform_sample = rng_uniform(rng);
+    if (use_weights && p.weight > CB_WEIGHT_LOWER_THRESHOLD && absorb < (1.0f - CB_WEIGHT_LOWER_THRESHOLD)) {
+        float survive = 1.0f - absorb;
+        absorb = 0.0f;
+        p.weight *= survive;
+        reflect_diffuse /= survive;
+        reflect_specular /= survive;
+    }
+    if (uniform_sample < absorb) {
+        float uniform_sample_reemit = rng_uniform(rng);
+        if (uniform_sample_reemit < reemit) {
+            p.history |= CB_SURFACE_REEMIT;
+            p.wavelength = sample_cdf_uniform(rng, g.wavelength_n, g.wavelength_start, g.wavelength_step,
+                                              T.at(surface->reemission_cdf));
+            p.dir = rng_sphere(rng);
+            p.pol = cross(rng_sphere(rng), p.dir);
+            p.pol = p.pol / norm(p.pol);
+            return CMD_CONTINUE;
+        }
+        p.history |= CB_SURFACE_ABSORB;
+        return CMD_BREAK;
+    } else if (uniform_sample < absorb + reflect_specular + reflect_diffuse) {
+        float uniform_sample_reflect = rng_uniform(rng) * (reflect_specular + reflect_diffuse);
+        if (uniform_sample_reflect < reflect_specular) return specular_reflect(p, s);
+        return diffuse_reflect(p, s, rng);
+    }
+    p.history |= CB_SURFACE_TRANSMIT;
+    return CMD_PASS;
+}
+
+// dichroic filter: angle-of-incidence blended reflect/transmit tables (photon.h:877-907)
+__device__ __forceinline__ int surface_dichroic(const DevGeometry& g, const Tables& T, Photon& p, StepState& s,
+                                                Rng& rng, const CbSurface* surface)
+{
+    float incident_angle = get_theta(s.normal, -p.dir);
+    float idx = interp_idx(incident_angle, surface->dichroic_nangles, T.at(surface->dichroic_angles));
+    unsigned int iidx = (int)idx;
+    const int W = g.wavelength_n;
+    float reflect_prob_low = interp_property(g, p.wavelength, T.at(surface->dichroic_reflect + iidx * W));
+    float reflect_prob_high = interp_property(g, p.wavelength, T.at(surface->dichroic_reflect + (iidx + 1) * W));
+    float transmit_prob_low = interp_property(g, p.wavelength, T.at(surface->dichroic_transmit + iidx * W));
+    float transmit_prob_high = interp_property(g, p.wavelength, T.at(surface->dichroic_transmit + (iidx + 1) * W));
+    float reflect_prob = reflect_prob_low + (reflect_prob_high - reflect_prob_low) * (idx - iidx);
+    float transmit_prob = transmit_prob_low + (transmit_prob_high - transmit_prob_low) * (idx - iidx);
+
+    float uniform_sample = rng_uniform(rng);
+    if (uniform_sample < reflect_prob) return specular_reflect(p, s);
+    if (uniform_sample < transmit_prob + reflect_prob) {
+        p.history |= CB_SURFACE_TRANSMIT;
+        return CMD_PASS;
+    }
+    p.history |= CB_SURFACE_ABSORB;
+    return CMD_BREAK;
+}
+
+// angle-tabulated surface (photon.h:909-951)
+__device__ __forceinline__ int surface_angular(const DevGeometry& g, const Tables& T, Photon& p, StepState& s,
+                                               Rng& rng, const CbSurface* surface, bool use_weights)
+{
+    float incident_angle = get_theta(s.normal, -p.dir);
+    float idx = interp_idx(incident_angle, surface->angular_nangles, T.at(surface->angular_angles));
+    unsigned int iidx = (int)idx;
+    float t = idx - iidx;
+    const float* tr = T.at(surface->angular_transmit);
+    const float* rs = T.at(surface->angular_reflect_specular);
+    const float* rd = T.at(surface->angular_reflect_diffuse);
+    float transmit_prob = tr[iidx] + t * (tr[iidx + 1] - tr[iidx]);
+    float reflect_spec_prob = rs[iidx] + t * (rs[iidx + 1] - rs[iidx]);
+    float reflect_diff_prob = rd[iidx] + t * (rd[iidx + 1] - rd[iidx]);
+    float absorb_prob = 1.0f - transmit_prob - reflect_spec_prob - reflect_diff_prob;
+
+    if (use_weights && p.weight > CB_WEIGHT_LOWER_THRESHOLD && absorb_prob < (1.0f - CB_WEIGHT_LOWER_THRESHOLD)) {
+        float survive = 1.0f - absorb_prob;
+        absorb_prob = 0.0f;
+        p.weight *= survive;
+        transmit_prob /= survive;
+        reflect_spec_prob /= survive;
+        reflect_diff_prob /= survive;
+    }
+    float uniform_sample = rng_uniform(rng);
+    if (uniform_sample < absorb_prob) {
+        p.history |= CB_SURFACE_ABSORB;
+        return CMD_BREAK;
+    }
+    if (uniform_sample < absorb_prob + transmit_prob) {
+        p.history |= CB_SURFACE_TRANSMIT;
+        return CMD_PASS;
+    }
+    if (uniform_sample < absorb_prob + transmit_prob + reflect_spec_prob) return specular_reflect(p, s);
+    return diffuse_reflect(p, s, rng);
+}
+
+// surface dispatch + default model (photon.h:953-1037; the reference's
+// effective default is CHROMA_FORCE_SCATTER_AT_PASS == 0)
+__device__ __forceinline__ int at_surface(const DevGeometry& g, const Tables& T, Photon& p, StepState& s,
+                                          Rng& rng, bool use_weights)
+{
+    const CbSurface* surface = &g.surfaces[s.surface_index];
+    const int model = surface->model;
+    if (model == CB_SURFACE_COMPLEX) return surface_complex(g, T, p, s, rng, surface, use_weights);
+    if (model == CB_SURFACE_WLS) return surface_wls(g, T, p, s, rng, surface, use_weights);
+    if (model == CB_SURFACE_DICHROIC) return surface_dichroic(g, T, p, s, rng, surface);
+    if (model == CB_SURFACE_ANGULAR) return surface_angular(g, T, p, s, rng, surface, use_weights);
+
+    float detect = interp_property(g, p.wavelength, T.at(surface->detect));
+    float absorb = interp_property(g, p.wavelength, T.at(surface->absorb));
+    float reflect_diffuse = interp_property(g, p.wavelength, T.at(surface->reflect_diffuse));
+    float reflect_specular = interp_property(g, p.wavelength, T.at(surface->reflect_specular));
+
+    float uniform_sample = rng_uniform(rng);
+    if (use_weights && p.weight > CB_WEIGHT_LOWER_THRESHOLD && absorb < (1.0f - CB_WEIGHT_LOWER_THRESHOLD)) {
+        float survive = 1.0f - absorb;
+        absorb = 0.0f;
+        p.weight *= survive;
+        detect /= survive;
+        reflect_diffuse /= survive;
+        reflect_specular /= survive;
+    }
+    if (use_weights && detect > 0.0f) {
+        p.history |= CB_SURFACE_DETECT;
+        p.weight *= detect;
+        return CMD_BREAK;
+    }
+    if (uniform_sample < absorb) {
+        p.history |= CB_SURFACE_ABSORB;
+        return CMD_BREAK;
+    } else if (uniform_sample < absorb + detect) {
+        p.history |= CB_SURFACE_DETECT;
+        return CMD_BREAK;
+    } else if (uniform_sample < absorb + detect + reflect_diffuse)
+        return diffuse_reflect(p, s, rng);
+    else if (uniform_sample < absorb + detect + reflect_diffuse + reflect_specular)
+        return specular_reflect(p, s);
+    return CMD_PASS;
+}
+
+// everything after the intersection for one step (propagate.cu:312-336).
+// Returns true when the photon continues to another step.
+__device__ __forceinline__ bool physics_step(const DevGeometry& g, const Tables& T, Photon& p, Rng& rng,
+                                             int tri, float distance, bool use_weights, int scatter_first)
+{
+    if (tri == -1) {
+        p.last_hit_triangle = -1;
+        p.history |= CB_NO_HIT;
+        return false;
+    }
+    StepState s;
+    s.distance = distance;
+    classify_hit(g, T, p, s, tri);
+    int command = to_boundary(g, T, p, s, rng, use_weights, scatter_first);
+    if (command == CMD_BREAK) return false;
+    if (command == CMD_CONTINUE) return true;
+    if (s.surface_index != -1) {
+        command = at_surface(g, T, p, s, rng, use_weights);
+        if (command == CMD_BREAK) return false;
+        if (command == CMD_CONTINUE) return true;
+    }
+    at_boundary(p, s, rng);
+    return true;
+}
+
+__device__ __forceinline__ bool photon_is_nan(const Photon& p)
+{
+    return isnan(p.dir.x * p.dir.y * p.dir.z * p.pos.x * p.pos.y * p.pos.z);
+}
+
+// ------------------------------------------------------------------ bank I/O
+__device__ __forceinline__ float3 ld3(const float* __restrict__ a, uint64_t i)
+{
+    return f3(a[3 * i], a[3 * i + 1], a[3 * i + 2]);
+}
+__device__ __forceinline__ void st3(float* __restrict__ a, uint64_t i, const float3& v)
+{
+    a[3 * i] = v.x; a[3 * i + 1] = v.y; a[3 * i + 2] = v.z;
+}
+
+} // namespace cb

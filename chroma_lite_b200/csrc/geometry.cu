@@ -1,0 +1,461 @@
+// geometry.cu -- geometry / detector upload into the engine's native layout and
+// the recursive-grid BVH builder in the reference node format.
+#include "host.h"
+#include <cub/device/device_radix_sort.cuh>
+#include <algorithm>
+#include <string.h>
+#include <thread>
+
+namespace cb {
+
+// Pack triangles for the traversal: 48 B = 3 x float4 per triangle holding the
+// three world-space vertices, the reference test rank (tie-break, SURVEY A-1)
+// and the material code, so a leaf test is three coalescable 128-bit loads
+// instead of an index fetch + three scattered 12-byte gathers.
+__global__ void __launch_bounds__(256)
+pack_triangles_kernel(const float* __restrict__ vertices, const uint32_t* __restrict__ triangles,
+                      const uint32_t* __restrict__ material_codes, const uint32_t* __restrict__ rank,
+                      uint64_t ntriangles, float4* __restrict__ tri48)
+{
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ntriangles) return;
+    uint32_t i0 = triangles[3 * t], i1 = triangles[3 * t + 1], i2 = triangles[3 * t + 2];
+    float3 v0 = ld3(vertices, i0), v1 = ld3(vertices, i1), v2 = ld3(vertices, i2);
+    tri48[3 * t + 0] = make_float4(v0.x, v0.y, v0.z, v1.x);
+    tri48[3 * t + 1] = make_float4(v1.y, v1.z, v2.x, v2.y);
+    tri48[3 * t + 2] = make_float4(v2.z, __uint_as_float(rank[t]), __uint_as_float(material_codes[t]), 0.0f);
+}
+
+// Position at which the reference traversal (mesh.h:75-117) would test each
+// triangle if nothing were pruned: leaf children of a group in ascending index,
+// then internal children in LIFO order.  Ray independent.
+static void reference_test_rank(const uint32_t* nodes, uint64_t nnodes, uint64_t ntriangles,
+                                std::vector<uint32_t>& rank)
+{
+    rank.assign(ntriangles, 0xFFFFFFFFu);
+    std::vector<uint32_t> stack;
+    stack.reserve(4096);
+    uint32_t r = 0;
+    stack.push_back(nodes[3]);
+    while (!stack.empty()) {
+        uint32_t w = stack.back();
+        stack.pop_back();
+        uint32_t first = w & 0x0FFFFFFFu, n = w >> 28;
+        for (uint32_t i = first; i < first + n && i < nnodes; i++) {
+            uint32_t cw = nodes[4ull * i + 3];
+            if ((cw >> 28) == 0) {
+                uint32_t tri = cw & 0x0FFFFFFFu;
+                if (tri < ntriangles && rank[tri] == 0xFFFFFFFFu) rank[tri] = r++;
+            } else {
+                stack.push_back(cw);
+            }
+        }
+    }
+}
+
+template <typename T>
+static int upload(T** dst, const T* src, uint64_t count, uint64_t& total)
+{
+    *dst = nullptr;
+    uint64_t bytes = std::max<uint64_t>(count, 1) * sizeof(T);
+    CB_CUDA(cudaMalloc((void**)dst, bytes));
+    if (count && src) CB_CUDA(cudaMemcpy(*dst, src, count * sizeof(T), cudaMemcpyHostToDevice));
+    total += bytes;
+    return CB_OK;
+}
+
+static void free_geometry(Geometry* g)
+{
+    cudaFree(g->vertices); cudaFree(g->triangles); cudaFree(g->material_codes); cudaFree(g->colors);
+    cudaFree(g->solid_id); cudaFree(g->nodes); cudaFree(g->tri48); cudaFree(g->tables);
+    cudaFree(g->materials); cudaFree(g->surfaces); cudaFree(g->solid_to_channel);
+    cudaFree(g->time_cdf_x); cudaFree(g->time_cdf_y); cudaFree(g->charge_cdf_x); cudaFree(g->charge_cdf_y);
+    delete g;
+}
+
+} // namespace cb
+
+using namespace cb;
+
+extern "C" {
+
+int cb_geometry_create(const CbGeometryDesc* d, cb_geom_t* out)
+{
+    CB_REQUIRE_INIT();
+    if (!d || !out) return fail(CB_ERR_INVALID, "cb_geometry_create: null argument");
+    if (d->nwireplanes != 0) return fail(CB_ERR_UNSUPPORTED, "analytic wire planes are not supported");
+    if (!d->vertices || !d->triangles || !d->material_codes || !d->nodes || d->nnodes == 0)
+        return fail(CB_ERR_INVALID, "cb_geometry_create: vertices/triangles/material_codes/nodes are required");
+    if (d->nmaterials <= 0 || d->nmaterials > 127 || d->nsurfaces < 0 || d->nsurfaces > 127)
+        return fail(CB_ERR_INVALID, "material/surface count out of range (8-bit signed codes, SURVEY App. A-7)");
+    if (d->ntriangles >= (1ull << 28)) return fail(CB_ERR_INVALID, "too many triangles for 28-bit child ids");
+    for (uint64_t t = 0; t < 3 * d->ntriangles; t++)
+        if (d->triangles[t] >= d->nvertices) return fail(CB_ERR_INVALID, "triangle %llu references a vertex out of range", (unsigned long long)(t / 3));
+    for (uint64_t i = 0; i < d->nnodes; i++) {
+        uint32_t w = d->nodes[4 * i + 3];
+        uint32_t n = w >> 28, c = w & 0x0FFFFFFFu;
+        if (n == 0) { if (c >= d->ntriangles && i != 0) return fail(CB_ERR_INVALID, "BVH leaf %llu references triangle %u out of range", (unsigned long long)i, c); }
+        else if ((uint64_t)c + n > d->nnodes) return fail(CB_ERR_INVALID, "BVH node %llu children out of range", (unsigned long long)i);
+    }
+
+    Geometry* g = new Geometry();
+    int rc;
+    uint64_t total = 0;
+#define UP(field, src, count) if ((rc = upload(&g->field, src, count, total)) != CB_OK) { free_geometry(g); return rc; }
+    g->nvertices = d->nvertices; g->ntriangles = d->ntriangles; g->nnodes = d->nnodes; g->table_floats = d->table_floats;
+    UP(vertices, d->vertices, 3 * d->nvertices);
+    UP(triangles, d->triangles, 3 * d->ntriangles);
+    UP(material_codes, d->material_codes, d->ntriangles);
+    UP(colors, d->colors, d->colors ? d->ntriangles : 0);
+    UP(solid_id, d->solid_id, d->solid_id ? d->ntriangles : 0);
+    // node array padded so the batched sibling fetch never leaves the allocation
+    {
+        uint64_t bytes = (d->nnodes + 16) * sizeof(uint4);
+        cudaError_t e = cudaMalloc((void**)&g->nodes, bytes);
+        if (e != cudaSuccess) { free_geometry(g); return cuda_fail(e, "cudaMalloc(nodes)"); }
+        cudaMemset(g->nodes, 0, bytes);
+        cudaMemcpy(g->nodes, d->nodes, d->nnodes * sizeof(uint4), cudaMemcpyHostToDevice);
+        total += bytes;
+    }
+    // table pool padded by 4 floats: interp_property may read fp[n] at the exact
+    // upper edge; pool size rounded up to 16 B for the bulk copy
+    {
+        uint64_t nf = ((d->table_floats + 4 + 3) / 4) * 4;
+        std::vector<float> pool(nf, 0.0f);
+        if (d->table_floats) memcpy(pool.data(), d->table_pool, d->table_floats * sizeof(float));
+        UP(tables, pool.data(), nf);
+    }
+    UP(materials, d->materials, (uint64_t)d->nmaterials);
+    UP(surfaces, d->surfaces, (uint64_t)d->nsurfaces);
+#undef UP
+
+    std::vector<uint32_t> rank;
+    reference_test_rank(d->nodes, d->nnodes, d->ntriangles, rank);
+    uint32_t* d_rank = nullptr;
+    uint64_t scratch = 0;
+    if ((rc = upload(&d_rank, rank.data(), d->ntriangles, scratch)) != CB_OK) { free_geometry(g); return rc; }
+    {
+        cudaError_t e = cudaMalloc((void**)&g->tri48, std::max<uint64_t>(d->ntriangles, 1) * 48);
+        if (e != cudaSuccess) { cudaFree(d_rank); free_geometry(g); return cuda_fail(e, "cudaMalloc(tri48)"); }
+        total += d->ntriangles * 48;
+        if (d->ntriangles) {
+            pack_triangles_kernel<<<(unsigned)((d->ntriangles + 255) / 256), 256, 0, ctx().stream>>>(
+                g->vertices, g->triangles, g->material_codes, d_rank, d->ntriangles, g->tri48);
+            e = cudaStreamSynchronize(ctx().stream);
+            if (e != cudaSuccess) { cudaFree(d_rank); free_geometry(g); return cuda_fail(e, "pack_triangles"); }
+        }
+        cudaFree(d_rank);
+    }
+
+    DevGeometry& v = g->dev;
+    v.nodes = g->nodes; v.tri48 = g->tri48; v.tables = g->tables;
+    v.materials = g->materials; v.surfaces = g->surfaces;
+    v.world_origin = make_float3(d->world_origin[0], d->world_origin[1], d->world_origin[2]);
+    v.world_scale = d->world_scale;
+    v.wavelength_n = d->wavelength_n; v.wavelength_start = d->wavelength_start; v.wavelength_step = d->wavelength_step;
+    v.time_n = d->time_n; v.time_start = d->time_start; v.time_step = d->time_step;
+    v.root_x = d->nodes[0]; v.root_y = d->nodes[1]; v.root_z = d->nodes[2]; v.root_w = d->nodes[3];
+    v.nmaterials = d->nmaterials; v.nsurfaces = d->nsurfaces;
+    // stage the leading part of the pool (the wavelength tables; the host lays
+    // the long time CDFs out last) into shared memory, up to 48 KB
+    uint64_t stage = std::min<uint64_t>(d->table_floats, 12288);
+    if (d->time_n > 0) {
+        // never split a table: only whole leading region before the first time CDF
+        int32_t first_time = INT32_MAX;
+        for (int i = 0; i < d->nmaterials; i++)
+            if (d->materials[i].num_comp > 0 && d->materials[i].comp_reemission_time_cdf >= 0)
+                first_time = std::min(first_time, d->materials[i].comp_reemission_time_cdf);
+        if (first_time != INT32_MAX) stage = std::min<uint64_t>(stage, (uint64_t)first_time);
+    }
+    stage = (stage / 4) * 4;
+    v.smem_floats = (uint32_t)stage;
+    g->smem_table_bytes = (uint32_t)(stage * 4);
+    g->device_bytes = total;
+    *out = geoms().add(g);
+    return CB_OK;
+}
+
+int cb_geometry_destroy(cb_geom_t h)
+{
+    Geometry* g = geoms().take(h);
+    if (!g) return fail(CB_ERR_INVALID, "cb_geometry_destroy: bad handle");
+    cudaStreamSynchronize(ctx().stream);
+    free_geometry(g);
+    return CB_OK;
+}
+
+int cb_geometry_info(cb_geom_t h, CbGeometryInfo* info)
+{
+    Geometry* g = geoms().get(h);
+    if (!g || !info) return fail(CB_ERR_INVALID, "cb_geometry_info: bad handle");
+    memset(info, 0, sizeof(*info));
+    info->vertices = g->vertices; info->triangles = g->triangles; info->material_codes = g->material_codes;
+    info->colors = g->colors; info->solid_id_map = g->solid_id; info->nodes = g->nodes;
+    info->solid_id_to_channel_index = g->solid_to_channel;
+    info->time_cdf_x = g->time_cdf_x; info->time_cdf_y = g->time_cdf_y;
+    info->charge_cdf_x = g->charge_cdf_x; info->charge_cdf_y = g->charge_cdf_y;
+    info->nvertices = g->nvertices; info->ntriangles = g->ntriangles; info->nnodes = g->nnodes;
+    info->nchannels = g->nchannels; info->device_bytes = g->device_bytes;
+    info->max_stack_depth = CB_SSTACK + CB_LSTACK;
+    return CB_OK;
+}
+
+int cb_detector_attach(cb_geom_t h, const int32_t* solid_id_to_channel_index, uint64_t nsolids,
+                       int32_t nchannels, const float* time_cdf_x, const float* time_cdf_y,
+                       int32_t time_cdf_len, const float* charge_cdf_x, const float* charge_cdf_y,
+                       int32_t charge_cdf_len, float charge_unit)
+{
+    Geometry* g = geoms().get(h);
+    if (!g) return fail(CB_ERR_INVALID, "cb_detector_attach: bad handle");
+    if (!solid_id_to_channel_index || time_cdf_len < 2 || charge_cdf_len < 2)
+        return fail(CB_ERR_INVALID, "cb_detector_attach: channel map and CDFs (len >= 2) required");
+    if (!g->solid_id && g->ntriangles) return fail(CB_ERR_INVALID, "cb_detector_attach: geometry has no solid_id map");
+    int rc;
+    uint64_t total = 0;
+    cudaFree(g->solid_to_channel); cudaFree(g->time_cdf_x); cudaFree(g->time_cdf_y);
+    cudaFree(g->charge_cdf_x); cudaFree(g->charge_cdf_y);
+    if ((rc = upload(&g->solid_to_channel, solid_id_to_channel_index, nsolids, total))) return rc;
+    if ((rc = upload(&g->time_cdf_x, time_cdf_x, (uint64_t)time_cdf_len, total))) return rc;
+    if ((rc = upload(&g->time_cdf_y, time_cdf_y, (uint64_t)time_cdf_len, total))) return rc;
+    if ((rc = upload(&g->charge_cdf_x, charge_cdf_x, (uint64_t)charge_cdf_len, total))) return rc;
+    if ((rc = upload(&g->charge_cdf_y, charge_cdf_y, (uint64_t)charge_cdf_len, total))) return rc;
+    g->nsolids = nsolids; g->nchannels = nchannels;
+    g->time_cdf_len = time_cdf_len; g->charge_cdf_len = charge_cdf_len; g->charge_unit = charge_unit;
+    g->device_bytes += total;
+    return CB_OK;
+}
+
+} // extern "C"
+
+// =====================================================================
+// BVH construction in the reference node format
+// =====================================================================
+namespace cb {
+
+__device__ __forceinline__ unsigned long long spread3_16(uint32_t input)
+{
+    unsigned long long x = input;
+    x = (x | (x << 16)) & 0x00000000FF0000FFull;
+    x = (x | (x << 8)) & 0x000000F00F00F00Full;
+    x = (x | (x << 4)) & 0x00000C30C30C30C3ull;
+    x = (x | (x << 2)) & 0x0000249249249249ull;
+    return x;
+}
+__device__ __forceinline__ uint32_t quantize(float v, float origin, float scale)
+{
+    return (uint32_t)((v - origin) / scale);   // truncation
+}
+
+// per triangle: 16-bit quantised AABB padded by one quantum and the 48-bit
+// Morton code of the centroid (behaviour of bvh.cu:148-203)
+__global__ void __launch_bounds__(256)
+make_leaves_kernel(const float* __restrict__ vertices, const uint32_t* __restrict__ triangles,
+                   uint64_t ntriangles, float3 origin, float scale, uint4* __restrict__ leaves,
+                   unsigned long long* __restrict__ codes, uint32_t* __restrict__ ids)
+{
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ntriangles) return;
+    float3 a = ld3(vertices, triangles[3 * t]);
+    float3 b = ld3(vertices, triangles[3 * t + 1]);
+    float3 c = ld3(vertices, triangles[3 * t + 2]);
+    float3 lo = f3(fminf(fminf(a.x, b.x), c.x), fminf(fminf(a.y, b.y), c.y), fminf(fminf(a.z, b.z), c.z));
+    float3 hi = f3(fmaxf(fmaxf(a.x, b.x), c.x), fmaxf(fmaxf(a.y, b.y), c.y), fmaxf(fmaxf(a.z, b.z), c.z));
+    float3 ce = (a + b + c) / 3.0f;
+    uint32_t lx = quantize(lo.x, origin.x, scale), ly = quantize(lo.y, origin.y, scale), lz = quantize(lo.z, origin.z, scale);
+    if (lx > 0) lx--;
+    if (ly > 0) ly--;
+    if (lz > 0) lz--;
+    uint32_t ux = quantize(hi.x, origin.x, scale) + 1, uy = quantize(hi.y, origin.y, scale) + 1, uz = quantize(hi.z, origin.z, scale) + 1;
+    uint32_t cx = quantize(ce.x, origin.x, scale), cy = quantize(ce.y, origin.y, scale), cz = quantize(ce.z, origin.z, scale);
+    codes[t] = spread3_16(cx) | (spread3_16(cy) << 1) | (spread3_16(cz) << 2);
+    ids[t] = (uint32_t)t;
+    leaves[t] = make_uint4(lx | (ux << 16), ly | (uy << 16), lz | (uz << 16), (uint32_t)t);
+}
+
+struct BvhResult {
+    std::vector<uint32_t> nodes;      // 4 words per node
+    std::vector<uint64_t> layer_offsets;
+    float origin[3]; float scale;
+    bool valid = false;
+};
+static BvhResult g_bvh;
+
+static inline void node_union(const uint32_t* child, uint32_t n, uint32_t* lo, uint32_t* hi)
+{
+    for (int a = 0; a < 3; a++) { lo[a] = 0xFFFF; hi[a] = 0; }
+    for (uint32_t i = 0; i < n; i++)
+        for (int a = 0; a < 3; a++) {
+            uint32_t w = child[4 * i + a];
+            lo[a] = std::min(lo[a], w & 0xFFFFu);
+            hi[a] = std::max(hi[a], w >> 16);
+        }
+}
+
+static uint64_t count_unique_sorted(const std::vector<uint64_t>& a)
+{
+    if (a.empty()) return 0;
+    uint64_t n = 1;
+    for (size_t i = 1; i < a.size(); i++) n += (a[i] != a[i - 1]);
+    return n;
+}
+
+// Host part of the recursive-grid builder (behaviour of bvh/grid.py:11-95 with
+// the layer merge / concatenate / collapse kernels of bvh.cu folded in).
+static void build_layers(std::vector<uint32_t>& leaf_nodes, std::vector<uint64_t>& codes,
+                         int target_degree, BvhResult& out)
+{
+    const uint32_t MAX_CHILD = 15;
+    std::vector<std::vector<uint32_t>> layers;   // root-first at the end; built leaf-first
+    layers.push_back(std::move(leaf_nodes));
+    while (layers.back().size() / 4 > 1) {
+        const std::vector<uint32_t>& top = layers.back();
+        const uint64_t nnodes = top.size() / 4;
+        uint64_t nunique = count_unique_sorted(codes);
+        while ((double)nnodes / (double)nunique < (double)target_degree && nunique > 1) {
+            for (auto& c : codes) c >>= 1;
+            nunique = count_unique_sorted(codes);
+        }
+        std::vector<uint32_t> first_child;
+        std::vector<uint64_t> parent_codes;
+        for (uint64_t i = 0; i < nnodes; i++) {
+            if (i == 0 || codes[i] != codes[i - 1]) {
+                first_child.push_back((uint32_t)i);
+                parent_codes.push_back(codes[i]);
+            }
+        }
+        // split groups with more than MAX_CHILD children into runs of MAX_CHILD
+        std::vector<uint32_t> fc2;
+        std::vector<uint64_t> pc2;
+        fc2.reserve(first_child.size()); pc2.reserve(first_child.size());
+        for (size_t k = 0; k < first_child.size(); k++) {
+            uint64_t end = (k + 1 < first_child.size()) ? first_child[k + 1] : nnodes;
+            for (uint64_t s = first_child[k]; s < end; s += MAX_CHILD) {
+                fc2.push_back((uint32_t)s);
+                pc2.push_back(parent_codes[k]);
+            }
+        }
+        std::vector<uint32_t> parents(fc2.size() * 4);
+        for (size_t k = 0; k < fc2.size(); k++) {
+            uint64_t end = (k + 1 < fc2.size()) ? fc2[k + 1] : nnodes;
+            uint32_t n = (uint32_t)(end - fc2[k]);
+            uint32_t lo[3], hi[3];
+            node_union(&top[4ull * fc2[k]], n, lo, hi);
+            parents[4 * k + 0] = (hi[0] << 16) | lo[0];
+            parents[4 * k + 1] = (hi[1] << 16) | lo[1];
+            parents[4 * k + 2] = (hi[2] << 16) | lo[2];
+            parents[4 * k + 3] = (n << 28) | fc2[k];
+        }
+        layers.push_back(std::move(parents));
+        codes = std::move(pc2);
+    }
+    // concatenate root-first; rebase child ids of every non-leaf layer
+    const size_t nl = layers.size();
+    std::vector<uint64_t> bounds(nl + 1, 0);
+    for (size_t l = 0; l < nl; l++) bounds[l + 1] = bounds[l] + layers[nl - 1 - l].size() / 4;
+    out.nodes.resize(bounds[nl] * 4);
+    for (size_t l = 0; l < nl; l++) {
+        const std::vector<uint32_t>& src = layers[nl - 1 - l];
+        uint32_t* dst = &out.nodes[bounds[l] * 4];
+        memcpy(dst, src.data(), src.size() * 4);
+        if (l + 1 < nl) {
+            uint32_t off = (uint32_t)bounds[l + 1];
+            for (size_t i = 0; i < src.size() / 4; i++) {
+                uint32_t w = dst[4 * i + 3];
+                dst[4 * i + 3] = (w & 0xF0000000u) | ((w & 0x0FFFFFFFu) + off);
+            }
+        }
+    }
+    // collapse single-child chains bottom-up (leaf layer excluded)
+    for (size_t l = nl - 1; l-- > 0;) {
+        for (uint64_t i = bounds[l]; i < bounds[l + 1]; i++) {
+            uint32_t w = out.nodes[4 * i + 3];
+            if ((w >> 28) == 1) {
+                uint32_t c = w & 0x0FFFFFFFu;
+                memcpy(&out.nodes[4 * i], &out.nodes[4ull * c], 16);
+            }
+        }
+    }
+    out.layer_offsets.assign(bounds.begin(), bounds.end() - 1);
+}
+
+} // namespace cb
+
+extern "C" int cb_bvh_build(const float* vertices, uint64_t nvertices, const uint32_t* triangles,
+                            uint64_t ntriangles, int32_t target_degree, float world_origin_out[3],
+                            float* world_scale_out, uint32_t* nodes_out, uint64_t* nnodes_out,
+                            uint64_t* layer_offsets_out, int32_t* nlayers_out)
+{
+    CB_REQUIRE_INIT();
+    if (!vertices || !triangles || nvertices == 0 || ntriangles == 0)
+        return fail(CB_ERR_INVALID, "cb_bvh_build: empty mesh");
+    if (ntriangles >= (1ull << 28)) return fail(CB_ERR_INVALID, "cb_bvh_build: too many triangles");
+    if (target_degree < 2) target_degree = 3;
+    if (nodes_out && g_bvh.valid) {
+        // second call of the two-call protocol: hand over the cached result
+        memcpy(nodes_out, g_bvh.nodes.data(), g_bvh.nodes.size() * 4);
+        if (layer_offsets_out) memcpy(layer_offsets_out, g_bvh.layer_offsets.data(), g_bvh.layer_offsets.size() * 8);
+        if (nnodes_out) *nnodes_out = g_bvh.nodes.size() / 4;
+        if (nlayers_out) *nlayers_out = (int32_t)g_bvh.layer_offsets.size();
+        if (world_origin_out) memcpy(world_origin_out, g_bvh.origin, 12);
+        if (world_scale_out) *world_scale_out = g_bvh.scale;
+        g_bvh = BvhResult();
+        return CB_OK;
+    }
+    // world coordinates (behaviour of gpu/bvh.py:42-47)
+    float lo[3] = {vertices[0], vertices[1], vertices[2]}, hi[3] = {vertices[0], vertices[1], vertices[2]};
+    for (uint64_t i = 1; i < nvertices; i++)
+        for (int a = 0; a < 3; a++) {
+            lo[a] = std::min(lo[a], vertices[3 * i + a]);
+            hi[a] = std::max(hi[a], vertices[3 * i + a]);
+        }
+    float extent = std::max(std::max(hi[0] - lo[0], hi[1] - lo[1]), hi[2] - lo[2]);
+    float scale = (float)((double)extent / 65534.0);
+
+    Context& c = ctx();
+    float* d_v = nullptr; uint32_t* d_t = nullptr; uint4* d_leaves = nullptr; uint4* d_sorted = nullptr;
+    unsigned long long *d_codes = nullptr, *d_codes2 = nullptr; uint32_t *d_ids = nullptr, *d_ids2 = nullptr;
+    void* d_tmp = nullptr; size_t tmp_bytes = 0;
+    auto cleanup = [&]() {
+        cudaFree(d_v); cudaFree(d_t); cudaFree(d_leaves); cudaFree(d_sorted); cudaFree(d_codes);
+        cudaFree(d_codes2); cudaFree(d_ids); cudaFree(d_ids2); cudaFree(d_tmp);
+    };
+#define BV(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { cleanup(); return cuda_fail(_e, #call); } } while (0)
+    BV(cudaMalloc(&d_v, nvertices * 12)); BV(cudaMalloc(&d_t, ntriangles * 12));
+    BV(cudaMalloc(&d_leaves, ntriangles * 16)); BV(cudaMalloc(&d_codes, ntriangles * 8));
+    BV(cudaMalloc(&d_codes2, ntriangles * 8)); BV(cudaMalloc(&d_ids, ntriangles * 4)); BV(cudaMalloc(&d_ids2, ntriangles * 4));
+    BV(cudaMemcpyAsync(d_v, vertices, nvertices * 12, cudaMemcpyHostToDevice, c.stream));
+    BV(cudaMemcpyAsync(d_t, triangles, ntriangles * 12, cudaMemcpyHostToDevice, c.stream));
+    make_leaves_kernel<<<(unsigned)((ntriangles + 255) / 256), 256, 0, c.stream>>>(
+        d_v, d_t, ntriangles, make_float3(lo[0], lo[1], lo[2]), scale, d_leaves, d_codes, d_ids);
+    BV(cudaGetLastError());
+    // stable LSD radix sort of (morton, triangle id): ties keep ascending triangle order
+    BV(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_codes, d_codes2, d_ids, d_ids2, (int)ntriangles, 0, 48, c.stream));
+    BV(cudaMalloc(&d_tmp, tmp_bytes));
+    BV(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_codes, d_codes2, d_ids, d_ids2, (int)ntriangles, 0, 48, c.stream));
+    std::vector<uint64_t> codes(ntriangles);
+    std::vector<uint32_t> ids(ntriangles), leaves(ntriangles * 4), sorted(ntriangles * 4);
+    BV(cudaMemcpyAsync(codes.data(), d_codes2, ntriangles * 8, cudaMemcpyDeviceToHost, c.stream));
+    BV(cudaMemcpyAsync(ids.data(), d_ids2, ntriangles * 4, cudaMemcpyDeviceToHost, c.stream));
+    BV(cudaMemcpyAsync(leaves.data(), d_leaves, ntriangles * 16, cudaMemcpyDeviceToHost, c.stream));
+    BV(cudaStreamSynchronize(c.stream));
+#undef BV
+    cleanup();
+    for (uint64_t i = 0; i < ntriangles; i++) memcpy(&sorted[4 * i], &leaves[4ull * ids[i]], 16);
+    leaves.clear(); leaves.shrink_to_fit();
+
+    g_bvh = BvhResult();
+    build_layers(sorted, codes, target_degree, g_bvh);
+    memcpy(g_bvh.origin, lo, 12);
+    g_bvh.scale = scale;
+    g_bvh.valid = true;
+    if (nnodes_out) *nnodes_out = g_bvh.nodes.size() / 4;
+    if (nlayers_out) *nlayers_out = (int32_t)g_bvh.layer_offsets.size();
+    if (world_origin_out) memcpy(world_origin_out, lo, 12);
+    if (world_scale_out) *world_scale_out = scale;
+    if (nodes_out) {
+        memcpy(nodes_out, g_bvh.nodes.data(), g_bvh.nodes.size() * 4);
+        if (layer_offsets_out) memcpy(layer_offsets_out, g_bvh.layer_offsets.data(), g_bvh.layer_offsets.size() * 8);
+        g_bvh = BvhResult();
+    }
+    return CB_OK;
+}

@@ -1,0 +1,87 @@
+// host.h -- library-internal host state shared by the translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <string>
+#include <vector>
+#include <mutex>
+#include <unordered_map>
+#include "../../include/chroma_b200.h"
+#include "engine.cuh"
+
+namespace cb {
+
+struct Context {
+    int device = -1;
+    int sm_count = 0;
+    size_t l2_bytes = 0;
+    int max_smem_optin = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;      // cb_timer_*
+    cudaEvent_t kev0 = nullptr, kev1 = nullptr;    // per-call kernel timing
+    void* flush_buf = nullptr; size_t flush_bytes = 0;
+    unsigned long long* d_counters = nullptr;      // 16 x u64 scratch (work counter, stats, flags)
+    unsigned long long* h_counters = nullptr;      // pinned mirror
+    uint32_t* d_block_counts = nullptr; size_t block_counts_cap = 0;   // compaction scratch
+};
+
+Context& ctx();
+int fail(int code, const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define CB_CUDA(call)                                                         \
+    do {                                                                      \
+        cudaError_t _e = (call);                                              \
+        if (_e != cudaSuccess) return cb::cuda_fail(_e, #call);               \
+    } while (0)
+
+#define CB_REQUIRE_INIT()                                                     \
+    do {                                                                      \
+        if (cb::ctx().device < 0) return cb::fail(CB_ERR_INVALID, "cb_init() has not been called"); \
+    } while (0)
+
+struct Geometry {
+    DevGeometry dev;                 // kernel-side view (pointers below)
+    // reference-layout copies (API mirror + bank utilities)
+    float* vertices = nullptr; uint32_t* triangles = nullptr; uint32_t* material_codes = nullptr;
+    uint32_t* colors = nullptr; uint32_t* solid_id = nullptr; uint4* nodes = nullptr;
+    // native
+    float4* tri48 = nullptr; float* tables = nullptr; CbMaterial* materials = nullptr; CbSurface* surfaces = nullptr;
+    uint64_t nvertices = 0, ntriangles = 0, nnodes = 0, table_floats = 0;
+    // detector
+    int32_t* solid_to_channel = nullptr; uint64_t nsolids = 0; int32_t nchannels = 0;
+    float *time_cdf_x = nullptr, *time_cdf_y = nullptr, *charge_cdf_x = nullptr, *charge_cdf_y = nullptr;
+    int32_t time_cdf_len = 0, charge_cdf_len = 0; float charge_unit = 0.f;
+    uint64_t device_bytes = 0;
+    uint32_t smem_table_bytes = 0;   // bytes of the table pool staged in shared memory
+};
+
+struct RngPool {
+    uint32_t* states = nullptr;      // 6 words per state {d, v0..v4}
+    float* bm_extra = nullptr;       // Box-Muller cache (allocated lazily for run_daq_many)
+    uint32_t* bm_flag = nullptr;
+    uint64_t n = 0;
+};
+
+struct Daq {
+    Geometry* geom = nullptr;
+    int32_t ndaq = 1; uint64_t count = 0;
+    float* earliest_time = nullptr; uint32_t* earliest_time_int = nullptr;
+    uint32_t* channel_history = nullptr; uint32_t* channel_q_int = nullptr; float* channel_q = nullptr;
+};
+
+// handle registries (opaque 64-bit ids -> objects)
+template <typename T>
+struct Registry {
+    std::mutex mu; std::unordered_map<uint64_t, T*> map; uint64_t next = 1;
+    uint64_t add(T* p) { std::lock_guard<std::mutex> l(mu); uint64_t id = next++; map[id] = p; return id; }
+    T* get(uint64_t id) { std::lock_guard<std::mutex> l(mu); auto it = map.find(id); return it == map.end() ? nullptr : it->second; }
+    T* take(uint64_t id) { std::lock_guard<std::mutex> l(mu); auto it = map.find(id); if (it == map.end()) return nullptr; T* p = it->second; map.erase(it); return p; }
+};
+Registry<Geometry>& geoms();
+Registry<RngPool>& rngs();
+Registry<Daq>& daqs();
+
+} // namespace cb

@@ -1,0 +1,768 @@
+// kernels.cu -- the hot path: ray intersection, photon propagation, photon-bank
+// utilities and the DAQ, plus their C-ABI entry points.
+#include "host.h"
+#include <algorithm>
+#include <string.h>
+#include <stdlib.h>
+
+namespace cb {
+
+constexpr int PROP_THREADS = 256;
+
+// ---------------------------------------------------------------- smem staging
+// The wavelength tables (a few KB .. 48 KB) are staged once per CTA with the bulk
+// async-copy engine (TMA 1-D: cp.async.bulk -> SASS UBLKCP) completing on an
+// mbarrier, instead of 188-float tables being chased through three levels of
+// global pointers per lookup as in the reference (photon.h:386-393).
+__device__ __forceinline__ void stage_tables(float* smem_dst, const float* gsrc, uint32_t bytes,
+                                             unsigned long long* mbar)
+{
+    if (bytes == 0) return;   // uniform across the CTA
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(mbar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem_dst);
+        const char* src = reinterpret_cast<const char*>(gsrc);
+        for (uint32_t off = 0; off < bytes; off += 16384) {
+            uint32_t chunk = min(bytes - off, 16384u);
+            asm volatile(
+                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                ::"r"(dst + off), "l"(src + off), "r"(chunk), "r"(bar)
+                : "memory");
+        }
+    }
+    // every thread waits for phase 0 to complete
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------- intersection
+template <bool COUNT>
+__global__ void __launch_bounds__(PROP_THREADS)
+intersect_kernel(DevGeometry g, const float* __restrict__ origins, const float* __restrict__ directions,
+                 const int32_t* __restrict__ last_hit, uint64_t n, int32_t* __restrict__ tri_out,
+                 float* __restrict__ dist_out, unsigned long long* counters)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint2* sstack = reinterpret_cast<uint2*>(smem_raw) + threadIdx.x;
+    TraverseCounters cnt = {0, 0};
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        float3 o = ld3(origins, i);
+        float3 d = ld3(directions, i);
+        d = d / norm(d);
+        float dist;
+        int tri = traverse<COUNT>(g, o, d, last_hit ? last_hit[i] : -1, dist, sstack, PROP_THREADS,
+                                  (uint32_t*)(counters + 3), &cnt);
+        tri_out[i] = tri;
+        if (tri != -1) dist_out[i] = dist;
+    }
+    if (COUNT) {
+        atomicAdd(counters + 1, (unsigned long long)cnt.nodes);
+        atomicAdd(counters + 2, (unsigned long long)cnt.tris);
+    }
+}
+
+// ---------------------------------------------------------------- propagation
+struct PropParams {
+    CbPhotonBank bank;
+    uint32_t* rng;            // state of photon (first + k) is rng[k]
+    uint64_t first, count;
+    int32_t max_steps, use_weights, scatter_first;
+    unsigned long long* counters;   // [0] work cursor, [1] nodes, [2] tris, [3] overflow flag, [4] steps
+};
+
+// Persistent-thread propagation: every lane owns one photon at a time and runs
+// it to termination (all steps in ONE launch, no host round trips); a lane whose
+// photon finished refills from a global cursor with one warp-aggregated atomic
+// (ballot + popc prefix), so warps stay populated without the reference's
+// per-step relaunch, 108 B/photon state reload and host-side queue swap
+// (gpu/photon.py:259-286).  RNG state k belongs to photon first+k (replay
+// contract), so results do not depend on scheduling.
+template <bool COUNT>
+__global__ void __launch_bounds__(PROP_THREADS, 2)
+propagate_kernel(DevGeometry g, PropParams P)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ unsigned long long mbar;
+    float* stab = reinterpret_cast<float*>(smem_raw);
+    const uint32_t tab_bytes = g.smem_floats * 4u;
+    uint2* sstack = reinterpret_cast<uint2*>(smem_raw + ((tab_bytes + 127u) & ~127u)) + threadIdx.x;
+    stage_tables(stab, g.tables, tab_bytes, &mbar);
+    Tables T = {stab, g.tables, g.smem_floats};
+
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    long long my = -1;        // index within the chunk, -1 = lane is empty
+    bool exhausted = false;
+    Photon p;
+    Rng rng;
+    int steps = 0, sf = 0;
+    TraverseCounters cnt = {0, 0};
+    unsigned long long nsteps_total = 0;
+
+    while (true) {
+        // ---- refill empty lanes
+        const bool need = (my < 0) && !exhausted;
+        const unsigned need_mask = __ballot_sync(0xffffffffu, need);
+        if (need_mask) {
+            unsigned long long base = 0;
+            if (lane == (unsigned)(__ffs(need_mask) - 1))
+                base = atomicAdd(P.counters, (unsigned long long)__popc(need_mask));
+            base = __shfl_sync(0xffffffffu, base, __ffs(need_mask) - 1);
+            if (need) {
+                unsigned long long k = base + __popc(need_mask & lt_mask);
+                if (k < P.count) {
+                    const uint64_t id = P.first + k;
+                    uint32_t hist = P.bank.flags[id] & 0xFFFFu;
+                    if (!(hist & CB_TERMINAL)) {
+                        my = (long long)k;
+                        p.pos = ld3(P.bank.pos, id);
+                        p.dir = ld3(P.bank.dir, id);
+                        p.dir = p.dir / norm(p.dir);
+                        p.pol = ld3(P.bank.pol, id);
+                        p.pol = p.pol / norm(p.pol);
+                        p.wavelength = P.bank.wavelengths[id];
+                        p.time = P.bank.t[id];
+                        p.last_hit_triangle = P.bank.last_hit_triangles[id];
+                        p.history = hist;
+                        p.weight = P.bank.weights[id];
+                        rng = rng_load(P.rng, k);
+                        steps = 0;
+                        sf = P.scatter_first;
+                    }
+                } else {
+                    exhausted = true;
+                }
+            }
+        }
+        if (__all_sync(0xffffffffu, my < 0)) {
+            if (__any_sync(0xffffffffu, exhausted)) break;
+            continue;
+        }
+        // ---- one step for every populated lane
+        if (my >= 0) {
+            bool alive;
+            steps++;
+            if (photon_is_nan(p)) {
+                p.history |= CB_NO_HIT | CB_NAN_ABORT;
+                alive = false;
+            } else {
+                float dist;
+                int tri = traverse<COUNT>(g, p.pos, p.dir, p.last_hit_triangle, dist, sstack, PROP_THREADS,
+                                          (uint32_t*)(P.counters + 3), &cnt);
+                alive = physics_step(g, T, p, rng, tri, dist, P.use_weights != 0, sf);
+                sf = 0;
+            }
+            if (!alive || steps >= P.max_steps) {
+                const uint64_t id = P.first + (uint64_t)my;
+                rng_store(P.rng, (uint64_t)my, rng);
+                st3(P.bank.pos, id, p.pos);
+                st3(P.bank.dir, id, p.dir);
+                st3(P.bank.pol, id, p.pol);
+                P.bank.wavelengths[id] = p.wavelength;
+                P.bank.t[id] = p.time;
+                P.bank.flags[id] = p.history;
+                P.bank.last_hit_triangles[id] = p.last_hit_triangle;
+                P.bank.weights[id] = p.weight;
+                nsteps_total += (unsigned long long)steps;
+                my = -1;
+            }
+        }
+    }
+    // per-warp reduction of the statistics, one atomic per warp
+    for (int o = 16; o > 0; o >>= 1) nsteps_total += __shfl_down_sync(0xffffffffu, nsteps_total, o);
+    if (lane == 0 && nsteps_total) atomicAdd(P.counters + 4, nsteps_total);
+    if (COUNT) {
+        atomicAdd(P.counters + 1, (unsigned long long)cnt.nodes);
+        atomicAdd(P.counters + 2, (unsigned long long)cnt.tris);
+    }
+}
+
+// ---------------------------------------------------------------- bank utilities
+struct BankPtrs { CbPhotonBank b; };
+
+__device__ __forceinline__ void copy_photon(const CbPhotonBank& s, uint64_t i, const CbPhotonBank& d, uint64_t o)
+{
+    st3(d.pos, o, ld3(s.pos, i));
+    st3(d.dir, o, ld3(s.dir, i));
+    st3(d.pol, o, ld3(s.pol, i));
+    d.wavelengths[o] = s.wavelengths[i];
+    d.t[o] = s.t[i];
+    d.flags[o] = s.flags[i];
+    d.last_hit_triangles[o] = s.last_hit_triangles[i];
+    d.weights[o] = s.weights[i];
+    if (d.evidx && s.evidx) d.evidx[o] = s.evidx[i];
+}
+
+// replicate the first n photons `copies` more times at stride n (propagate.cu:29-68)
+__global__ void duplicate_kernel(CbPhotonBank b, uint64_t n, int copies)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (int c = 1; c <= copies; c++) copy_photon(b, i, b, i + n * (uint64_t)c);
+}
+
+__device__ __forceinline__ int photon_channel(const CbPhotonBank& b, uint64_t id, uint32_t flag,
+                                              const uint32_t* solid_map, const int32_t* solid_to_channel)
+{
+    int tri = b.last_hit_triangles[id];
+    if ((b.flags[id] & flag) && tri > -1) return solid_to_channel[solid_map[tri]];
+    return -1;
+}
+
+// Stable two-pass compaction (count per 1024-photon tile -> exclusive scan ->
+// ordered scatter).  The reference appends in atomicAdd arrival order
+// (propagate.cu:97-139, 201-251), which is run-to-run nondeterministic; keeping
+// photon order makes hit lists reproducible at the same cost.
+constexpr int TILE = 1024;
+template <bool HITS>
+__global__ void __launch_bounds__(256)
+tile_count_kernel(CbPhotonBank b, uint64_t first, uint64_t n, uint32_t flag, const uint32_t* solid_map,
+                  const int32_t* solid_to_channel, uint32_t* tile_counts)
+{
+    __shared__ uint32_t total;
+    if (threadIdx.x == 0) total = 0;
+    __syncthreads();
+    uint32_t c = 0;
+    uint64_t base = (uint64_t)blockIdx.x * TILE;
+    for (int k = threadIdx.x; k < TILE; k += 256) {
+        uint64_t i = base + k;
+        if (i < n) {
+            bool sel = HITS ? (photon_channel(b, first + i, flag, solid_map, solid_to_channel) >= 0)
+                            : ((b.flags[first + i] & flag) != 0);
+            c += sel;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&total, c);
+    __syncthreads();
+    if (threadIdx.x == 0) tile_counts[blockIdx.x] = total;
+}
+
+// single-CTA exclusive scan of the tile counts; total -> counts[ntiles]
+__global__ void __launch_bounds__(1024)
+tile_scan_kernel(uint32_t* counts, uint32_t ntiles)
+{
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < ntiles; base += 1024) {
+        uint32_t i = base + threadIdx.x;
+        uint32_t v = (i < ntiles) ? counts[i] : 0;
+        uint32_t x = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if ((threadIdx.x & 31) >= o) x += y;
+        }
+        if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            uint32_t w = warp_sums[threadIdx.x], s = w;
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t y = __shfl_up_sync(0xffffffffu, s, o);
+                if (threadIdx.x >= o) s += y;
+            }
+            warp_sums[threadIdx.x] = s - w;
+        }
+        __syncthreads();
+        uint32_t excl = carry + warp_sums[threadIdx.x >> 5] + x - v;
+        if (i < ntiles) counts[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) counts[ntiles] = carry;
+}
+
+template <bool HITS>
+__global__ void __launch_bounds__(256)
+tile_scatter_kernel(CbPhotonBank src, uint64_t first, uint64_t n, uint32_t flag, const uint32_t* solid_map,
+                    const int32_t* solid_to_channel, const uint32_t* tile_offsets, CbPhotonBank dst,
+                    int32_t* channels_out)
+{
+    __shared__ uint32_t warp_base[8];
+    __shared__ uint32_t running;
+    if (threadIdx.x == 0) running = tile_offsets[blockIdx.x];
+    __syncthreads();
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint64_t base = (uint64_t)blockIdx.x * TILE;
+    for (int k0 = 0; k0 < TILE; k0 += 256) {
+        uint64_t i = base + k0 + threadIdx.x;
+        int ch = -1;
+        bool sel = false;
+        if (i < n) {
+            if (HITS) { ch = photon_channel(src, first + i, flag, solid_map, solid_to_channel); sel = ch >= 0; }
+            else sel = (src.flags[first + i] & flag) != 0;
+        }
+        unsigned m = __ballot_sync(0xffffffffu, sel);
+        if (lane == 0) warp_base[warp] = __popc(m);
+        __syncthreads();
+        uint32_t off = running;
+        for (unsigned w = 0; w < warp; w++) off += warp_base[w];
+        if (sel) {
+            uint64_t o = off + __popc(m & ((1u << lane) - 1u));
+            copy_photon(src, first + i, dst, o);
+            if (HITS) channels_out[o] = ch;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t t = 0;
+            for (int w = 0; w < 8; w++) t += warp_base[w];
+            running += t;
+        }
+        __syncthreads();
+    }
+}
+
+// gather by queue (propagate.cu:141-169)
+__global__ void gather_queue_kernel(CbPhotonBank src, const uint32_t* queue, uint64_t n, CbPhotonBank dst)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    copy_photon(src, queue[i], dst, i);
+}
+
+// ---------------------------------------------------------------- DAQ
+// one photon per thread: weight test, smeared time, charge -> per-channel
+// atomicMin / atomicAdd / atomicOr (behaviour of daq.cu:35-86; time ordering on
+// raw float bits, valid for t >= 0)
+__global__ void __launch_bounds__(256)
+daq_kernel(uint32_t* __restrict__ rng_states, uint32_t detection_state, uint64_t first_photon, uint64_t nphotons,
+           CbPhotonBank b, const uint32_t* __restrict__ solid_map, const int32_t* __restrict__ solid_to_channel,
+           const float* __restrict__ time_cdf_x, const float* __restrict__ time_cdf_y, int time_cdf_len,
+           const float* __restrict__ charge_cdf_x, const float* __restrict__ charge_cdf_y, int charge_cdf_len,
+           float charge_unit, uint32_t* earliest_time_int, uint32_t* channel_q_int, uint32_t* channel_histories,
+           float global_weight)
+{
+    uint64_t id = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= nphotons) return;
+    uint64_t photon_id = id + first_photon;
+    int triangle_id = b.last_hit_triangles[photon_id];
+    if (triangle_id > -1) {
+        int solid_id = solid_map[triangle_id];
+        uint32_t history = b.flags[photon_id];
+        int channel_index = solid_to_channel[solid_id];
+        if (channel_index >= 0 && (history & detection_state)) {
+            Rng rng = rng_load(rng_states, id);
+            float weight = b.weights[photon_id] * global_weight;
+            if (rng_uniform(rng) < weight) {
+                float time = b.t[photon_id] + interp_xy(rng_uniform(rng), time_cdf_len, time_cdf_y, time_cdf_x);
+                uint32_t time_int = __float_as_uint(time);
+                float charge = interp_xy(rng_uniform(rng), charge_cdf_len, charge_cdf_y, charge_cdf_x);
+                uint32_t charge_int = roundf(charge / charge_unit);
+                atomicMin(earliest_time_int + channel_index, time_int);
+                atomicAdd(channel_q_int + channel_index, charge_int);
+                atomicOr(channel_histories + channel_index, history);
+            }
+            rng_store(rng_states, id, rng);
+        }
+    }
+}
+
+// cuRAND's Box-Muller normal on the XORWOW stream (curand_normal.h: two 32-bit
+// draws -> two normals, second one cached in the state)
+__device__ __forceinline__ float rng_normal(Rng& s, uint32_t& flag, float& extra)
+{
+    if (flag) { flag = 0; return extra; }
+    uint32_t x = rng_next(s), y = rng_next(s);
+    float u = x * 2.3283064e-10f + (2.3283064e-10f / 2.0f);
+    float v = y * (2.3283064e-10f * 6.2831855f) + (2.3283064e-10f * 6.2831855f / 2.0f);
+    float r = sqrtf(-2.0f * logf(u));
+    float sv, cv;
+    __sincosf(v, &sv, &cv);
+    extra = r * cv;
+    flag = 1;
+    return r * sv;
+}
+
+// one CTA per photon, threads stride over the ndaq virtual DAQ copies (daq.cu:88-150)
+__global__ void daq_many_kernel(uint32_t* __restrict__ rng_states, float* bm_extra, uint32_t* bm_flag,
+                                uint32_t detection_state, uint64_t first_photon, CbPhotonBank b,
+                                const uint32_t* __restrict__ solid_map, const int32_t* __restrict__ solid_to_channel,
+                                const float* __restrict__ time_cdf_x, const float* __restrict__ time_cdf_y, int time_cdf_len,
+                                const float* __restrict__ charge_cdf_x, const float* __restrict__ charge_cdf_y, int charge_cdf_len,
+                                float charge_unit, uint32_t* earliest_time_int, uint32_t* channel_q_int,
+                                uint32_t* channel_histories, int ndaq, int channel_stride, float global_weight)
+{
+    uint64_t photon_id = first_photon + blockIdx.x;
+    int triangle_id = b.last_hit_triangles[photon_id];
+    if (triangle_id == -1) return;
+    int channel_index = (triangle_id > -1) ? solid_to_channel[solid_map[triangle_id]] : -1;
+    uint32_t history = b.flags[photon_id];
+    if (channel_index < 0 || !(history & detection_state)) return;
+    float photon_time = b.t[photon_id];
+    float weight = b.weights[photon_id] * global_weight;
+    uint64_t id = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    Rng rng = rng_load(rng_states, id);
+    uint32_t flag = bm_flag[id];
+    float extra = bm_extra[id];
+    for (int i = threadIdx.x; i < ndaq; i += blockDim.x) {
+        int channel_offset = channel_index + i * channel_stride;
+        if (rng_uniform(rng) < weight) {
+            float time = photon_time + rng_normal(rng, flag, extra) +
+                         interp_xy(rng_uniform(rng), time_cdf_len, time_cdf_y, time_cdf_x);
+            uint32_t time_int = __float_as_uint(time);
+            float charge = interp_xy(rng_uniform(rng), charge_cdf_len, charge_cdf_y, charge_cdf_x);
+            uint32_t charge_int = roundf(charge / charge_unit);
+            atomicMin(earliest_time_int + channel_offset, time_int);
+            atomicAdd(channel_q_int + channel_offset, charge_int);
+            atomicOr(channel_histories + channel_offset, history);
+        }
+    }
+    rng_store(rng_states, id, rng);
+    bm_flag[id] = flag;
+    bm_extra[id] = extra;
+}
+
+// fused finaliser: time bits -> float, integer charge -> float (daq.cu:152-173)
+__global__ void daq_finalize_kernel(uint64_t n, const uint32_t* time_int, const uint32_t* q_int, float charge_unit,
+                                    float* t_out, float* q_out)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    t_out[i] = __uint_as_float(time_int[i]);
+    q_out[i] = q_int[i] * charge_unit;
+}
+
+static int check_bank(const CbPhotonBank* b, const char* who)
+{
+    if (!b) return fail(CB_ERR_INVALID, "%s: null photon bank", who);
+    if (b->n && (!b->pos || !b->dir || !b->pol || !b->wavelengths || !b->t || !b->last_hit_triangles || !b->flags || !b->weights))
+        return fail(CB_ERR_INVALID, "%s: photon bank has null arrays", who);
+    return CB_OK;
+}
+
+static size_t stack_smem_bytes() { return (size_t)CB_SSTACK * PROP_THREADS * sizeof(uint2); }
+
+static int ensure_tile_scratch(uint64_t ntiles)
+{
+    Context& c = ctx();
+    if (c.block_counts_cap < ntiles + 1) {
+        cudaFree(c.d_block_counts);
+        c.d_block_counts = nullptr;
+        c.block_counts_cap = 0;
+        CB_CUDA(cudaMalloc(&c.d_block_counts, (ntiles + 1) * sizeof(uint32_t)));
+        c.block_counts_cap = ntiles + 1;
+    }
+    return CB_OK;
+}
+
+template <bool HITS>
+static int compact(const CbPhotonBank* src, uint64_t first, uint64_t n, uint32_t flag, Geometry* g,
+                   const CbPhotonBank* dst, int32_t* d_channels, uint32_t* count_out)
+{
+    Context& c = ctx();
+    if (count_out) *count_out = 0;
+    if (n == 0) return CB_OK;
+    if (first + n > src->n) return fail(CB_ERR_INVALID, "compaction range exceeds the photon bank");
+    const uint64_t ntiles = (n + TILE - 1) / TILE;
+    int rc = ensure_tile_scratch(ntiles);
+    if (rc) return rc;
+    const uint32_t* solid_map = g ? g->solid_id : nullptr;
+    const int32_t* s2c = g ? g->solid_to_channel : nullptr;
+    tile_count_kernel<HITS><<<(unsigned)ntiles, 256, 0, c.stream>>>(*src, first, n, flag, solid_map, s2c, c.d_block_counts);
+    tile_scan_kernel<<<1, 1024, 0, c.stream>>>(c.d_block_counts, (uint32_t)ntiles);
+    CB_CUDA(cudaGetLastError());
+    uint32_t total = 0;
+    CB_CUDA(cudaMemcpyAsync(&total, c.d_block_counts + ntiles, 4, cudaMemcpyDeviceToHost, c.stream));
+    CB_CUDA(cudaStreamSynchronize(c.stream));
+    if (count_out) *count_out = total;
+    if (dst && total) {
+        if (dst->n < total) return fail(CB_ERR_INVALID, "destination bank too small (%llu < %u)", (unsigned long long)dst->n, total);
+        tile_scatter_kernel<HITS><<<(unsigned)ntiles, 256, 0, c.stream>>>(*src, first, n, flag, solid_map, s2c,
+                                                                         c.d_block_counts, *dst, d_channels);
+        CB_CUDA(cudaGetLastError());
+        CB_CUDA(cudaStreamSynchronize(c.stream));
+    }
+    return CB_OK;
+}
+
+} // namespace cb
+
+using namespace cb;
+
+extern "C" {
+
+int cb_intersect(cb_geom_t gh, const float* d_origins, const float* d_directions, const int32_t* d_last_hit,
+                 uint64_t n, int32_t* d_triangle_out, float* d_distance_out)
+{
+    CB_REQUIRE_INIT();
+    Geometry* g = geoms().get(gh);
+    if (!g) return fail(CB_ERR_INVALID, "cb_intersect: bad geometry handle");
+    if (n == 0) return CB_OK;
+    if (!d_origins || !d_directions || !d_triangle_out || !d_distance_out)
+        return fail(CB_ERR_INVALID, "cb_intersect: null array");
+    Context& c = ctx();
+    CB_CUDA(cudaMemsetAsync(c.d_counters, 0, 16 * sizeof(unsigned long long), c.stream));
+    size_t smem = stack_smem_bytes();
+    CB_CUDA(cudaFuncSetAttribute(intersect_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, intersect_kernel<false>, PROP_THREADS, smem));
+    if (per_sm < 1) per_sm = 1;
+    unsigned blocks = (unsigned)std::min<uint64_t>((n + PROP_THREADS - 1) / PROP_THREADS, (uint64_t)c.sm_count * per_sm * 4);
+    intersect_kernel<false><<<blocks, PROP_THREADS, smem, c.stream>>>(g->dev, d_origins, d_directions, d_last_hit, n,
+                                                                     d_triangle_out, d_distance_out, c.d_counters);
+    CB_CUDA(cudaGetLastError());
+    CB_CUDA(cudaMemcpyAsync(c.h_counters, c.d_counters, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c.stream));
+    CB_CUDA(cudaStreamSynchronize(c.stream));
+    if (c.h_counters[3]) return fail(CB_ERR_CUDA, "cb_intersect: traversal stack overflow");
+    return CB_OK;
+}
+
+int cb_propagate(const CbPhotonBank* bank, cb_geom_t gh, cb_rng_t rh, int32_t nthreads_per_block,
+                 int32_t max_blocks, int32_t max_steps, int32_t use_weights, int32_t scatter_first,
+                 CbPropagateStats* stats)
+{
+    CB_REQUIRE_INIT();
+    int rc = check_bank(bank, "cb_propagate");
+    if (rc) return rc;
+    Geometry* g = geoms().get(gh);
+    RngPool* r = rngs().get(rh);
+    if (!g) return fail(CB_ERR_INVALID, "cb_propagate: bad geometry handle");
+    if (!r) return fail(CB_ERR_INVALID, "cb_propagate: bad rng handle");
+    if (nthreads_per_block <= 0 || max_blocks <= 0) return fail(CB_ERR_INVALID, "cb_propagate: bad launch parameters");
+    const uint64_t pool = std::min<uint64_t>((uint64_t)nthreads_per_block * (uint64_t)max_blocks, r->n);
+    if (pool == 0) return fail(CB_ERR_INVALID, "cb_propagate: empty rng pool");
+    if (stats) { memset(stats, 0, sizeof(*stats)); }
+    if (bank->n == 0 || max_steps <= 0) return CB_OK;
+    Context& c = ctx();
+    const bool count = getenv("CHROMA_B200_STATS") != nullptr;
+    auto kern = count ? propagate_kernel<true> : propagate_kernel<false>;
+    size_t smem = ((g->smem_table_bytes + 127u) & ~127u) + stack_smem_bytes();
+    CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, PROP_THREADS, smem));
+    if (per_sm < 1) return fail(CB_ERR_CUDA, "cb_propagate: kernel does not fit on an SM (smem %zu B)", smem);
+
+    unsigned long long tot[16] = {0};
+    uint32_t launches = 0;
+    CB_CUDA(cudaEventRecord(c.kev0, c.stream));
+    // photons beyond the pool reuse states chunk by chunk, in order, exactly as
+    // the reference's chunk_iterator does for one step (gpu/photon.py:266-268)
+    for (uint64_t first = 0; first < bank->n; first += pool) {
+        uint64_t cnt = std::min<uint64_t>(pool, bank->n - first);
+        CB_CUDA(cudaMemsetAsync(c.d_counters, 0, 16 * sizeof(unsigned long long), c.stream));
+        PropParams P;
+        P.bank = *bank; P.rng = r->states; P.first = first; P.count = cnt;
+        P.max_steps = max_steps; P.use_weights = use_weights; P.scatter_first = scatter_first;
+        P.counters = c.d_counters;
+        unsigned blocks = (unsigned)std::min<uint64_t>((cnt + PROP_THREADS - 1) / PROP_THREADS, (uint64_t)c.sm_count * per_sm);
+        kern<<<blocks, PROP_THREADS, smem, c.stream>>>(g->dev, P);
+        CB_CUDA(cudaGetLastError());
+        launches++;
+        CB_CUDA(cudaMemcpyAsync(c.h_counters, c.d_counters, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c.stream));
+        CB_CUDA(cudaStreamSynchronize(c.stream));
+        for (int i = 1; i < 5; i++) tot[i] += c.h_counters[i];
+    }
+    CB_CUDA(cudaEventRecord(c.kev1, c.stream));
+    CB_CUDA(cudaEventSynchronize(c.kev1));
+    if (stats) {
+        stats->photons = bank->n; stats->steps = tot[4]; stats->nodes_visited = tot[1]; stats->tris_tested = tot[2];
+        stats->launches = launches;
+        cudaEventElapsedTime(&stats->kernel_ms, c.kev0, c.kev1);
+    }
+    if (tot[3]) return fail(CB_ERR_CUDA, "cb_propagate: traversal stack overflow");
+    return CB_OK;
+}
+
+int cb_photon_duplicate(const CbPhotonBank* bank, uint64_t nphotons, int32_t ncopies)
+{
+    CB_REQUIRE_INIT();
+    int rc = check_bank(bank, "cb_photon_duplicate");
+    if (rc) return rc;
+    if (ncopies <= 1 || nphotons == 0) return CB_OK;
+    if (nphotons * (uint64_t)ncopies > bank->n) return fail(CB_ERR_INVALID, "cb_photon_duplicate: bank too small");
+    duplicate_kernel<<<(unsigned)((nphotons + 255) / 256), 256, 0, ctx().stream>>>(*bank, nphotons, ncopies - 1);
+    CB_CUDA(cudaGetLastError());
+    CB_CUDA(cudaStreamSynchronize(ctx().stream));
+    return CB_OK;
+}
+
+int cb_count_photons(const CbPhotonBank* bank, uint64_t first, uint64_t n, uint32_t flag, uint32_t* count_out)
+{
+    CB_REQUIRE_INIT();
+    int rc = check_bank(bank, "cb_count_photons");
+    if (rc) return rc;
+    return compact<false>(bank, first, n, flag, nullptr, nullptr, nullptr, count_out);
+}
+int cb_copy_photons(const CbPhotonBank* src, uint64_t first, uint64_t n, uint32_t flag, const CbPhotonBank* dst,
+                    uint32_t* count_out)
+{
+    CB_REQUIRE_INIT();
+    int rc = check_bank(src, "cb_copy_photons");
+    if (rc) return rc;
+    if ((rc = check_bank(dst, "cb_copy_photons(dst)"))) return rc;
+    return compact<false>(src, first, n, flag, nullptr, dst, nullptr, count_out);
+}
+int cb_count_photon_hits(const CbPhotonBank* bank, uint64_t first, uint64_t n, uint32_t flag, cb_geom_t gh,
+                         uint32_t* count_out)
+{
+    CB_REQUIRE_INIT();
+    int rc = check_bank(bank, "cb_count_photon_hits");
+    if (rc) return rc;
+    Geometry* g = geoms().get(gh);
+    if (!g || !g->solid_to_channel) return fail(CB_ERR_INVALID, "cb_count_photon_hits: geometry has no detector attached");
+    return compact<true>(bank, first, n, flag, g, nullptr, nullptr, count_out);
+}
+int cb_copy_photon_hits(const CbPhotonBank* src, uint64_t first, uint64_t n, uint32_t flag, cb_geom_t gh,
+                        const CbPhotonBank* dst, int32_t* d_channels_out, uint32_t* count_out)
+{
+    CB_REQUIRE_INIT();
+    int rc = check_bank(src, "cb_copy_photon_hits");
+    if (rc) return rc;
+    if ((rc = check_bank(dst, "cb_copy_photon_hits(dst)"))) return rc;
+    Geometry* g = geoms().get(gh);
+    if (!g || !g->solid_to_channel) return fail(CB_ERR_INVALID, "cb_copy_photon_hits: geometry has no detector attached");
+    if (!d_channels_out) return fail(CB_ERR_INVALID, "cb_copy_photon_hits: null channel array");
+    return compact<true>(src, first, n, flag, g, dst, d_channels_out, count_out);
+}
+int cb_copy_photon_queue(const CbPhotonBank* src, const uint32_t* d_queue, uint64_t n, const CbPhotonBank* dst)
+{
+    CB_REQUIRE_INIT();
+    int rc = check_bank(src, "cb_copy_photon_queue");
+    if (rc) return rc;
+    if ((rc = check_bank(dst, "cb_copy_photon_queue(dst)"))) return rc;
+    if (n == 0) return CB_OK;
+    if (dst->n < n) return fail(CB_ERR_INVALID, "cb_copy_photon_queue: destination too small");
+    gather_queue_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx().stream>>>(*src, d_queue, n, *dst);
+    CB_CUDA(cudaGetLastError());
+    CB_CUDA(cudaStreamSynchronize(ctx().stream));
+    return CB_OK;
+}
+
+// ---------------------------------------------------------------- DAQ
+int cb_daq_create(cb_geom_t gh, int32_t ndaq, cb_daq_t* out)
+{
+    CB_REQUIRE_INIT();
+    Geometry* g = geoms().get(gh);
+    if (!g || !out) return fail(CB_ERR_INVALID, "cb_daq_create: bad argument");
+    if (g->nchannels <= 0 || !g->solid_to_channel)
+        return fail(CB_ERR_INVALID, "Geometry has no detectors, DAQ can't be initialized.");
+    if (ndaq < 1) return fail(CB_ERR_INVALID, "cb_daq_create: ndaq must be >= 1");
+    Daq* d = new Daq();
+    d->geom = g; d->ndaq = ndaq; d->count = (uint64_t)g->nchannels * ndaq;
+    cudaError_t e;
+    if ((e = cudaMalloc(&d->earliest_time, d->count * 4)) || (e = cudaMalloc(&d->earliest_time_int, d->count * 4)) ||
+        (e = cudaMalloc(&d->channel_history, d->count * 4)) || (e = cudaMalloc(&d->channel_q_int, d->count * 4)) ||
+        (e = cudaMalloc(&d->channel_q, d->count * 4))) {
+        delete d;
+        return cuda_fail(e, "cudaMalloc(daq)");
+    }
+    cudaMemset(d->channel_history, 0, d->count * 4);
+    cudaMemset(d->channel_q_int, 0, d->count * 4);
+    cudaMemset(d->channel_q, 0, d->count * 4);
+    *out = daqs().add(d);
+    return CB_OK;
+}
+int cb_daq_destroy(cb_daq_t h)
+{
+    Daq* d = daqs().take(h);
+    if (!d) return fail(CB_ERR_INVALID, "cb_daq_destroy: bad handle");
+    cudaStreamSynchronize(ctx().stream);
+    cudaFree(d->earliest_time); cudaFree(d->earliest_time_int); cudaFree(d->channel_history);
+    cudaFree(d->channel_q_int); cudaFree(d->channel_q);
+    delete d;
+    return CB_OK;
+}
+int cb_daq_begin_acquire(cb_daq_t h)
+{
+    Daq* d = daqs().get(h);
+    if (!d) return fail(CB_ERR_INVALID, "cb_daq_begin_acquire: bad handle");
+    Context& c = ctx();
+    const float maxtime = 1e9f;   // gpu/daq.py:56
+    uint32_t bits;
+    memcpy(&bits, &maxtime, 4);
+    CB_CUDA(cudaMemsetAsync(d->channel_q_int, 0, d->count * 4, c.stream));
+    CB_CUDA(cudaMemsetAsync(d->channel_q, 0, d->count * 4, c.stream));
+    CB_CUDA(cudaMemsetAsync(d->channel_history, 0, d->count * 4, c.stream));
+    CB_CUDA(cudaStreamSynchronize(c.stream));
+    return cb_memset32(d->earliest_time_int, bits, d->count);
+}
+int cb_daq_acquire(cb_daq_t h, const CbPhotonBank* bank, cb_rng_t rh, int32_t nthreads_per_block,
+                   int32_t max_blocks, uint64_t start_photon, uint64_t nphotons, float weight)
+{
+    CB_REQUIRE_INIT();
+    Daq* d = daqs().get(h);
+    RngPool* r = rngs().get(rh);
+    if (!d) return fail(CB_ERR_INVALID, "cb_daq_acquire: bad daq handle");
+    if (!r) return fail(CB_ERR_INVALID, "cb_daq_acquire: bad rng handle");
+    int rc = check_bank(bank, "cb_daq_acquire");
+    if (rc) return rc;
+    if (start_photon + nphotons > bank->n) return fail(CB_ERR_INVALID, "cb_daq_acquire: photon range exceeds bank");
+    if (nthreads_per_block <= 0 || max_blocks <= 0) return fail(CB_ERR_INVALID, "cb_daq_acquire: bad launch parameters");
+    Geometry* g = d->geom;
+    Context& c = ctx();
+    if (d->ndaq == 1) {
+        // chunks reuse rng states [0, chunk) in order, as chunk_iterator does (gpu/daq.py:68-78)
+        uint64_t chunk = std::min<uint64_t>((uint64_t)nthreads_per_block * (uint64_t)max_blocks, r->n);
+        if (chunk == 0) return fail(CB_ERR_INVALID, "cb_daq_acquire: empty rng pool");
+        for (uint64_t first = 0; first < nphotons; first += chunk) {
+            uint64_t cnt = std::min<uint64_t>(chunk, nphotons - first);
+            daq_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, c.stream>>>(
+                r->states, CB_SURFACE_DETECT, start_photon + first, cnt, *bank, g->solid_id, g->solid_to_channel,
+                g->time_cdf_x, g->time_cdf_y, g->time_cdf_len, g->charge_cdf_x, g->charge_cdf_y, g->charge_cdf_len,
+                g->charge_unit, d->earliest_time_int, d->channel_q_int, d->channel_history, weight);
+            CB_CUDA(cudaGetLastError());
+        }
+    } else {
+        // one CTA per photon (chunk_iterator(nphotons, 1, max_blocks), gpu/daq.py:80-91)
+        if (!r->bm_flag) {
+            CB_CUDA(cudaMalloc(&r->bm_flag, std::max<uint64_t>(r->n, 1) * 4));
+            CB_CUDA(cudaMalloc(&r->bm_extra, std::max<uint64_t>(r->n, 1) * 4));
+            CB_CUDA(cudaMemsetAsync(r->bm_flag, 0, r->n * 4, c.stream));
+            CB_CUDA(cudaMemsetAsync(r->bm_extra, 0, r->n * 4, c.stream));
+        }
+        uint64_t max_ctas = std::min<uint64_t>((uint64_t)max_blocks, r->n / (uint64_t)nthreads_per_block);
+        if (max_ctas == 0) return fail(CB_ERR_INVALID, "cb_daq_acquire: rng pool smaller than one block");
+        for (uint64_t first = 0; first < nphotons; first += max_ctas) {
+            uint64_t cnt = std::min<uint64_t>(max_ctas, nphotons - first);
+            daq_many_kernel<<<(unsigned)cnt, nthreads_per_block, 0, c.stream>>>(
+                r->states, r->bm_extra, r->bm_flag, CB_SURFACE_DETECT, start_photon + first, *bank, g->solid_id,
+                g->solid_to_channel, g->time_cdf_x, g->time_cdf_y, g->time_cdf_len, g->charge_cdf_x, g->charge_cdf_y,
+                g->charge_cdf_len, g->charge_unit, d->earliest_time_int, d->channel_q_int, d->channel_history,
+                d->ndaq, g->nchannels, weight);
+            CB_CUDA(cudaGetLastError());
+        }
+    }
+    CB_CUDA(cudaStreamSynchronize(c.stream));
+    return CB_OK;
+}
+int cb_daq_finalize(cb_daq_t h)
+{
+    Daq* d = daqs().get(h);
+    if (!d) return fail(CB_ERR_INVALID, "cb_daq_finalize: bad handle");
+    Context& c = ctx();
+    daq_finalize_kernel<<<(unsigned)((d->count + 255) / 256), 256, 0, c.stream>>>(
+        d->count, d->earliest_time_int, d->channel_q_int, d->geom->charge_unit, d->earliest_time, d->channel_q);
+    CB_CUDA(cudaGetLastError());
+    CB_CUDA(cudaStreamSynchronize(c.stream));
+    return CB_OK;
+}
+int cb_daq_end_acquire(cb_daq_t h) { return cb_daq_finalize(h); }
+int cb_daq_pointers(cb_daq_t h, void** t, void** q, void** flags, void** time_int, void** q_int, uint64_t* count)
+{
+    Daq* d = daqs().get(h);
+    if (!d) return fail(CB_ERR_INVALID, "cb_daq_pointers: bad handle");
+    if (t) *t = d->earliest_time;
+    if (q) *q = d->channel_q;
+    if (flags) *flags = d->channel_history;
+    if (time_int) *time_int = d->earliest_time_int;
+    if (q_int) *q_int = d->channel_q_int;
+    if (count) *count = d->count;
+    return CB_OK;
+}
+
+} // extern "C"

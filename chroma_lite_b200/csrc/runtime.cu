@@ -1,0 +1,366 @@
+// runtime.cu -- context, memory, timers and the XORWOW state pool.
+#include "host.h"
+#include <string.h>
+
+namespace cb {
+
+static Context g_ctx;
+static thread_local char g_err[1024] = "";
+static char g_err_global[1024] = "";
+
+Context& ctx() { return g_ctx; }
+
+int fail(int code, const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    strncpy(g_err_global, g_err, sizeof(g_err_global) - 1);
+    return code;
+}
+int cuda_fail(cudaError_t e, const char* what)
+{
+    int code = (e == cudaErrorMemoryAllocation) ? CB_ERR_NOMEM : CB_ERR_CUDA;
+    return fail(code, "CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+}
+
+static Registry<Geometry> g_geoms;
+static Registry<RngPool> g_rngs;
+static Registry<Daq> g_daqs;
+Registry<Geometry>& geoms() { return g_geoms; }
+Registry<RngPool>& rngs() { return g_rngs; }
+Registry<Daq>& daqs() { return g_daqs; }
+
+// ---------------------------------------------------------------- XORWOW skip matrices
+// 160x160 GF(2) matrices in cuRAND's row layout (row i = image of state bit i,
+// 5 words), generated here by repeated squaring of the one-step matrix instead
+// of shipping curand_precalc.h: seq[k] = M^(2^67 * 2^k), off[k] = M^(2^k).
+struct XwMat { uint32_t r[160][5]; };
+
+static void xw_step(uint32_t v[5])
+{
+    uint32_t t = v[0] ^ (v[0] >> 2);
+    v[0] = v[1]; v[1] = v[2]; v[2] = v[3]; v[3] = v[4];
+    v[4] = (v[4] ^ (v[4] << 4)) ^ (t ^ (t << 1));
+}
+static void xw_matvec(const XwMat& m, const uint32_t* v, uint32_t* out)
+{
+    uint32_t acc[5] = {0, 0, 0, 0, 0};
+    for (int i = 0; i < 160; i++)
+        if (v[i >> 5] & (1u << (i & 31)))
+            for (int j = 0; j < 5; j++) acc[j] ^= m.r[i][j];
+    memcpy(out, acc, sizeof(acc));
+}
+static void xw_square(const XwMat& a, XwMat& out)
+{
+    XwMat tmp;
+    for (int i = 0; i < 160; i++) xw_matvec(a, a.r[i], tmp.r[i]);
+    out = tmp;
+}
+
+constexpr int XW_NMAT = 64;
+static uint32_t* d_xw_seq = nullptr;   // [64][800]
+static uint32_t* d_xw_off = nullptr;   // [64][800]
+
+static int xw_upload_tables()
+{
+    if (d_xw_seq) return CB_OK;
+    std::vector<XwMat> off(XW_NMAT), seq(XW_NMAT);
+    for (int i = 0; i < 160; i++) {
+        uint32_t v[5] = {0, 0, 0, 0, 0};
+        v[i >> 5] = 1u << (i & 31);
+        xw_step(v);
+        memcpy(off[0].r[i], v, 20);
+    }
+    for (int k = 1; k < XW_NMAT; k++) xw_square(off[k - 1], off[k]);
+    XwMat m = off[63];
+    for (int k = 64; k <= 67; k++) xw_square(m, m);
+    seq[0] = m;
+    for (int k = 1; k < XW_NMAT; k++) xw_square(seq[k - 1], seq[k]);
+    CB_CUDA(cudaMalloc(&d_xw_seq, sizeof(XwMat) * XW_NMAT));
+    CB_CUDA(cudaMalloc(&d_xw_off, sizeof(XwMat) * XW_NMAT));
+    CB_CUDA(cudaMemcpy(d_xw_seq, seq.data(), sizeof(XwMat) * XW_NMAT, cudaMemcpyHostToDevice));
+    CB_CUDA(cudaMemcpy(d_xw_off, off.data(), sizeof(XwMat) * XW_NMAT, cudaMemcpyHostToDevice));
+    return CB_OK;
+}
+
+__device__ __forceinline__ void xw_apply(const uint32_t* __restrict__ mat, uint32_t v[5])
+{
+    uint32_t acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0, acc4 = 0;
+#pragma unroll
+    for (int w = 0; w < 5; w++) {
+        uint32_t bits = v[w];
+#pragma unroll 4
+        for (int b = 0; b < 32; b++) {
+            const uint32_t* row = mat + (w * 32 + b) * 5;
+            uint32_t mask = 0u - ((bits >> b) & 1u);
+            acc0 ^= __ldg(row + 0) & mask; acc1 ^= __ldg(row + 1) & mask; acc2 ^= __ldg(row + 2) & mask;
+            acc3 ^= __ldg(row + 3) & mask; acc4 ^= __ldg(row + 4) & mask;
+        }
+    }
+    v[0] = acc0; v[1] = acc1; v[2] = acc2; v[3] = acc3; v[4] = acc4;
+}
+
+// state[i] = curand_init(seed, first_stream + i, offset)  (curand_kernel.h:772-800)
+__global__ void __launch_bounds__(256)
+rng_init_kernel(uint32_t* __restrict__ states, uint64_t n, uint64_t seed, uint64_t first_stream,
+                uint64_t offset, const uint32_t* __restrict__ seq, const uint32_t* __restrict__ off)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t s0 = ((uint32_t)seed) ^ 0xaad26b49u;
+    uint32_t s1 = (uint32_t)(seed >> 32) ^ 0xf7dcefddu;
+    uint32_t t0 = 1099087573u * s0;
+    uint32_t t1 = 2591861531u * s1;
+    uint32_t d = 6615241u + t1 + t0;
+    uint32_t v[5];
+    v[0] = 123456789u + t0;
+    v[1] = 362436069u ^ t0;
+    v[2] = 521288629u + t1;
+    v[3] = 88675123u ^ t1;
+    v[4] = 5783321u + t0;
+    uint64_t stream = first_stream + i;
+    for (int k = 0; stream; k++, stream >>= 1)
+        if (stream & 1) xw_apply(seq + k * 800, v);
+    uint64_t o = offset;
+    for (int k = 0; o; k++, o >>= 1)
+        if (o & 1) xw_apply(off + k * 800, v);
+    d += 362437u * (uint32_t)offset;
+    Rng r = {d, v[0], v[1], v[2], v[3], v[4]};
+    rng_store(states, i, r);
+}
+
+__global__ void rng_fill_uniform_kernel(uint32_t* __restrict__ states, uint64_t n, float low, float high,
+                                        float* __restrict__ out)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Rng r = rng_load(states, i);
+    out[i] = rng_range(r, low, high);
+    rng_store(states, i, r);
+}
+
+__global__ void fill32_kernel(uint32_t* p, uint32_t v, uint64_t n)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) p[i] = v;
+}
+
+} // namespace cb
+
+using namespace cb;
+
+extern "C" {
+
+int cb_abi_version(void) { return CB_ABI_VERSION; }
+const char* cb_last_error(void) { return g_err[0] ? g_err : g_err_global; }
+
+int cb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int cb_init(int device)
+{
+    Context& c = ctx();
+    if (c.device == device && c.stream) return CB_OK;
+    if (c.device >= 0 && c.device != device)
+        return fail(CB_ERR_INVALID, "library already bound to device %d (one process per GPU)", c.device);
+    int n = 0;
+    CB_CUDA(cudaGetDeviceCount(&n));
+    if (device < 0 || device >= n) return fail(CB_ERR_INVALID, "device %d out of range (%d visible)", device, n);
+    CB_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CB_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(CB_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    c.sm_count = prop.multiProcessorCount;
+    c.l2_bytes = (size_t)prop.l2CacheSize;
+    c.max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    CB_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    CB_CUDA(cudaEventCreate(&c.ev0)); CB_CUDA(cudaEventCreate(&c.ev1));
+    CB_CUDA(cudaEventCreate(&c.kev0)); CB_CUDA(cudaEventCreate(&c.kev1));
+    CB_CUDA(cudaMalloc(&c.d_counters, 16 * sizeof(unsigned long long)));
+    CB_CUDA(cudaMemset(c.d_counters, 0, 16 * sizeof(unsigned long long)));
+    CB_CUDA(cudaMallocHost(&c.h_counters, 16 * sizeof(unsigned long long)));
+    // keep the hot top of the BVH resident: let persisting lines use most of L2
+    if (prop.persistingL2CacheMaxSize > 0)
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)prop.persistingL2CacheMaxSize);
+    cudaGetLastError();
+    c.device = device;
+    return CB_OK;
+}
+
+int cb_sm_count(void) { return ctx().sm_count; }
+
+int cb_synchronize(void)
+{
+    CB_REQUIRE_INIT();
+    CB_CUDA(cudaStreamSynchronize(ctx().stream));
+    CB_CUDA(cudaDeviceSynchronize());
+    return CB_OK;
+}
+
+int cb_malloc(uint64_t bytes, void** dptr)
+{
+    CB_REQUIRE_INIT();
+    if (!dptr) return fail(CB_ERR_INVALID, "cb_malloc: null out pointer");
+    *dptr = nullptr;
+    if (bytes == 0) bytes = 16;
+    CB_CUDA(cudaMalloc(dptr, bytes));
+    return CB_OK;
+}
+int cb_free(void* dptr)
+{
+    if (!dptr) return CB_OK;
+    CB_REQUIRE_INIT();
+    CB_CUDA(cudaStreamSynchronize(ctx().stream));
+    CB_CUDA(cudaFree(dptr));
+    return CB_OK;
+}
+int cb_memcpy_h2d(void* d, const void* h, uint64_t bytes)
+{
+    CB_REQUIRE_INIT();
+    if (bytes == 0) return CB_OK;
+    CB_CUDA(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, ctx().stream));
+    CB_CUDA(cudaStreamSynchronize(ctx().stream));
+    return CB_OK;
+}
+int cb_memcpy_d2h(void* h, const void* d, uint64_t bytes)
+{
+    CB_REQUIRE_INIT();
+    if (bytes == 0) return CB_OK;
+    CB_CUDA(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, ctx().stream));
+    CB_CUDA(cudaStreamSynchronize(ctx().stream));
+    return CB_OK;
+}
+int cb_memcpy_d2d(void* dst, const void* src, uint64_t bytes)
+{
+    CB_REQUIRE_INIT();
+    if (bytes == 0) return CB_OK;
+    CB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx().stream));
+    CB_CUDA(cudaStreamSynchronize(ctx().stream));
+    return CB_OK;
+}
+int cb_memset32(void* dptr, uint32_t value, uint64_t count)
+{
+    CB_REQUIRE_INIT();
+    if (count == 0) return CB_OK;
+    int blocks = (int)std::min<uint64_t>((count + 255) / 256, (uint64_t)ctx().sm_count * 16);
+    fill32_kernel<<<blocks, 256, 0, ctx().stream>>>((uint32_t*)dptr, value, count);
+    CB_CUDA(cudaGetLastError());
+    CB_CUDA(cudaStreamSynchronize(ctx().stream));
+    return CB_OK;
+}
+int cb_host_alloc(uint64_t bytes, void** hptr)
+{
+    CB_REQUIRE_INIT();
+    CB_CUDA(cudaMallocHost(hptr, bytes ? bytes : 16));
+    return CB_OK;
+}
+int cb_host_free(void* hptr)
+{
+    if (!hptr) return CB_OK;
+    CB_CUDA(cudaFreeHost(hptr));
+    return CB_OK;
+}
+int cb_mem_info(uint64_t* free_bytes, uint64_t* total_bytes)
+{
+    CB_REQUIRE_INIT();
+    size_t f = 0, t = 0;
+    CB_CUDA(cudaMemGetInfo(&f, &t));
+    if (free_bytes) *free_bytes = f;
+    if (total_bytes) *total_bytes = t;
+    return CB_OK;
+}
+
+int cb_timer_start(void)
+{
+    CB_REQUIRE_INIT();
+    CB_CUDA(cudaEventRecord(ctx().ev0, ctx().stream));
+    return CB_OK;
+}
+int cb_timer_stop(float* ms)
+{
+    CB_REQUIRE_INIT();
+    CB_CUDA(cudaEventRecord(ctx().ev1, ctx().stream));
+    CB_CUDA(cudaEventSynchronize(ctx().ev1));
+    float t = 0.f;
+    CB_CUDA(cudaEventElapsedTime(&t, ctx().ev0, ctx().ev1));
+    if (ms) *ms = t;
+    return CB_OK;
+}
+int cb_flush_l2(void)
+{
+    CB_REQUIRE_INIT();
+    Context& c = ctx();
+    if (!c.flush_buf) {
+        c.flush_bytes = std::max<size_t>(c.l2_bytes * 2, (size_t)256 << 20);
+        CB_CUDA(cudaMalloc(&c.flush_buf, c.flush_bytes));
+    }
+    static uint32_t tick = 0;
+    fill32_kernel<<<c.sm_count * 8, 256, 0, c.stream>>>((uint32_t*)c.flush_buf, ++tick, c.flush_bytes / 4);
+    CB_CUDA(cudaGetLastError());
+    return CB_OK;
+}
+
+// ---------------------------------------------------------------- RNG pool
+int cb_rng_create(uint64_t n, uint64_t seed, uint64_t offset, cb_rng_t* out)
+{
+    CB_REQUIRE_INIT();
+    if (!out) return fail(CB_ERR_INVALID, "cb_rng_create: null out pointer");
+    int rc = xw_upload_tables();
+    if (rc) return rc;
+    RngPool* r = new RngPool();
+    r->n = n;
+    cudaError_t e = cudaMalloc(&r->states, std::max<uint64_t>(n, 1) * 24);
+    if (e != cudaSuccess) { delete r; return cuda_fail(e, "cudaMalloc(rng states)"); }
+    if (n) {
+        unsigned blocks = (unsigned)((n + 255) / 256);
+        rng_init_kernel<<<blocks, 256, 0, ctx().stream>>>(r->states, n, seed, 0, offset, d_xw_seq, d_xw_off);
+        CB_CUDA(cudaGetLastError());
+        CB_CUDA(cudaStreamSynchronize(ctx().stream));
+    }
+    *out = rngs().add(r);
+    return CB_OK;
+}
+int cb_rng_destroy(cb_rng_t h)
+{
+    RngPool* r = rngs().take(h);
+    if (!r) return fail(CB_ERR_INVALID, "cb_rng_destroy: bad handle");
+    cudaStreamSynchronize(ctx().stream);
+    cudaFree(r->states); cudaFree(r->bm_extra); cudaFree(r->bm_flag);
+    delete r;
+    return CB_OK;
+}
+int cb_rng_size(cb_rng_t h, uint64_t* n)
+{
+    RngPool* r = rngs().get(h);
+    if (!r) return fail(CB_ERR_INVALID, "cb_rng_size: bad handle");
+    *n = r->n;
+    return CB_OK;
+}
+int cb_rng_download(cb_rng_t h, uint64_t first, uint64_t count, uint32_t* out6)
+{
+    RngPool* r = rngs().get(h);
+    if (!r) return fail(CB_ERR_INVALID, "cb_rng_download: bad handle");
+    if (first + count > r->n) return fail(CB_ERR_INVALID, "cb_rng_download: range exceeds pool");
+    return cb_memcpy_d2h(out6, r->states + 6 * first, count * 24);
+}
+int cb_rng_fill_uniform(cb_rng_t h, uint64_t n, float low, float high, float* d_out)
+{
+    RngPool* r = rngs().get(h);
+    if (!r) return fail(CB_ERR_INVALID, "cb_rng_fill_uniform: bad handle");
+    if (n > r->n) return fail(CB_ERR_INVALID, "cb_rng_fill_uniform: n exceeds pool");
+    if (!n) return CB_OK;
+    rng_fill_uniform_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx().stream>>>(r->states, n, low, high, d_out);
+    CB_CUDA(cudaGetLastError());
+    CB_CUDA(cudaStreamSynchronize(ctx().stream));
+    return CB_OK;
+}
+
+} // extern "C"

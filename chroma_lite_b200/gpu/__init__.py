@@ -1,0 +1,8 @@
+"""GPU host wrappers with the names of chroma.gpu (chroma/gpu/__init__.py)."""
+from .tools import (create_cuda_context, get_rng_states, chunk_iterator, to_float3, to_uint3,  # noqa: F401
+                    format_size, format_array, RNGStates)
+from .geometry import GPUGeometry  # noqa: F401
+from .detector import GPUDetector  # noqa: F401
+from .photon import GPUPhotons, GPUPhotonsSlice  # noqa: F401
+from .daq import GPUDaq, GPUChannels  # noqa: F401
+from .intersect import intersect_mesh  # noqa: F401

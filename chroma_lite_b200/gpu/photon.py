@@ -1,0 +1,230 @@
+"""GPUPhotons / GPUPhotonsSlice: device photon bank and its operations
+(role of chroma/gpu/photon.py:13-415), implemented on the C ABI."""
+import ctypes as C
+import sys
+import numpy as np
+
+from .. import _lib, event
+from .. import gpuarray as ga
+from .tools import to_float3
+
+_FIELDS = ('pos', 'dir', 'pol', 'wavelengths', 't', 'last_hit_triangles', 'flags', 'weights', 'evidx')
+
+
+def _resolve_nphotons(ph):
+    try:
+        return len(ph)
+    except TypeError:
+        pass
+    true_n = getattr(ph, 'true_nphotons', None)
+    if true_n is not None:
+        return int(true_n)
+    pos = getattr(ph, 'pos', None)
+    if pos is not None:
+        return len(pos)
+    raise TypeError('Cannot determine photon count from object of type %r' % type(ph))
+
+
+def _alloc_bank(n):
+    return dict(pos=ga.empty(n, ga.vec.float3), dir=ga.empty(n, ga.vec.float3), pol=ga.empty(n, ga.vec.float3),
+                wavelengths=ga.empty(n, np.float32), t=ga.empty(n, np.float32),
+                last_hit_triangles=ga.empty(n, np.int32), flags=ga.empty(n, np.uint32),
+                weights=ga.empty(n, np.float32), evidx=ga.empty(n, np.uint32))
+
+
+class GPUPhotons(object):
+    def __init__(self, photons, ncopies=1, copy_flags=True, copy_triangles=True, copy_weights=True):
+        """Load ``photons`` onto the GPU, replicating ``ncopies`` times
+        (chroma/gpu/photon.py:14-116)."""
+        nphotons = _resolve_nphotons(photons)
+        total = nphotons * ncopies
+        self.pos = ga.empty(total, ga.vec.float3)
+        self.dir = ga.empty(total, ga.vec.float3)
+        self.pol = ga.empty(total, ga.vec.float3)
+        self.wavelengths = ga.empty(total, np.float32)
+        self.t = ga.empty(total, np.float32)
+        self.last_hit_triangles = ga.empty(total, np.int32)
+        if not copy_triangles:
+            self.last_hit_triangles.fill(-1)
+        self.flags = ga.empty(total, np.uint32) if copy_flags else ga.zeros(total, np.uint32)
+        self.weights = ga.empty(total, np.float32)
+        if not copy_weights:
+            self.weights.fill(1.0)
+        # the reference allocates evidx for nphotons only although photon_duplicate
+        # writes all copies; allocate the full size
+        self.evidx = ga.empty(total, np.uint32)
+
+        def put_vec(dest, source):
+            if isinstance(source, ga.DeviceArray):
+                dest[:nphotons].copy_from_device(source, min(len(source), nphotons) * 12)
+            else:
+                dest[:nphotons].set(to_float3(np.asarray(source)))
+
+        def put(dest, source, dtype):
+            if isinstance(source, ga.DeviceArray):
+                dest[:nphotons].copy_from_device(source, min(len(source), nphotons) * 4)
+            else:
+                dest[:nphotons].set(np.asarray(source, dtype=dtype))
+
+        if nphotons:
+            put_vec(self.pos, photons.pos)
+            put_vec(self.dir, photons.dir)
+            put_vec(self.pol, photons.pol)
+            put(self.wavelengths, photons.wavelengths, np.float32)
+            put(self.t, photons.t, np.float32)
+            if copy_triangles:
+                put(self.last_hit_triangles, photons.last_hit_triangles, np.int32)
+            if copy_flags:
+                put(self.flags, photons.flags, np.uint32)
+            if copy_weights:
+                put(self.weights, photons.weights, np.float32)
+            put(self.evidx, photons.evidx, np.uint32)
+
+        self.true_nphotons = getattr(photons, 'true_nphotons', nphotons)
+        self.ncopies = ncopies
+        if ncopies > 1 and nphotons:
+            bank = self._bank()
+            _lib.check(_lib.lib().cb_photon_duplicate(C.byref(bank), int(nphotons), int(ncopies)))
+
+    # ------------------------------------------------------------------
+    def _bank(self, start=0, count=None):
+        n = len(self.pos) - start if count is None else count
+        b = _lib.CbPhotonBank()
+        for f in _FIELDS:
+            arr = getattr(self, f)
+            setattr(b, f, arr.ptr + start * arr.dtype.itemsize if arr is not None else None)
+        b.n = int(n)
+        return b
+
+    def get(self):
+        n = len(self.pos)
+        pos = self.pos.get().view(np.float32).reshape((n, 3))
+        dir = self.dir.get().view(np.float32).reshape((n, 3))
+        pol = self.pol.get().view(np.float32).reshape((n, 3))
+        return event.Photons(pos, dir, pol, self.wavelengths.get(), self.t.get(), self.last_hit_triangles.get(),
+                             self.flags.get(), self.weights.get(), self.evidx.get())
+
+    def get_hits(self, *args, **kwargs):
+        """dict channel -> Photons detected by that channel."""
+        flat_hits = self.get_flat_hits(*args, **kwargs)
+        return {int(chan): flat_hits[flat_hits.channel == chan] for chan in np.unique(flat_hits.channel)}
+
+    def get_flat_hits(self, gpu_detector, target_flag=(0x1 << 2), nthreads_per_block=256, max_blocks=1024,
+                      start_photon=None, nphotons=None, no_map=False):
+        """Photons with ``target_flag`` set that ended on a triangle of a solid mapped
+        to a channel; ``.channel`` holds the channel index (gpu/photon.py:141-209)."""
+        lib = _lib.lib()
+        start_photon = 0 if start_photon is None else start_photon
+        nphotons = self.pos.size - start_photon if nphotons is None else nphotons
+        src = self._bank()
+        count = C.c_uint32()
+        _lib.check(lib.cb_count_photon_hits(C.byref(src), int(start_photon), int(nphotons), int(target_flag),
+                                            gpu_detector.handle, C.byref(count)))
+        n = count.value
+        out = _alloc_bank(n)
+        channels = ga.empty(n, np.int32)
+        if n:
+            dst = _lib.CbPhotonBank()
+            for f in _FIELDS:
+                setattr(dst, f, out[f].ptr)
+            dst.n = n
+            c2 = C.c_uint32()
+            _lib.check(lib.cb_copy_photon_hits(C.byref(src), int(start_photon), int(nphotons), int(target_flag),
+                                               gpu_detector.handle, C.byref(dst), channels.ptr, C.byref(c2)))
+            assert c2.value == n
+        g = lambda a: a.get()
+        return event.Photons(g(out['pos']).view(np.float32).reshape((n, 3)), g(out['dir']).view(np.float32).reshape((n, 3)),
+                             g(out['pol']).view(np.float32).reshape((n, 3)), g(out['wavelengths']), g(out['t']),
+                             g(out['last_hit_triangles']), g(out['flags']), g(out['weights']), g(out['evidx']),
+                             g(channels))
+
+    def iterate_copies(self):
+        for i in range(self.ncopies):
+            w = slice(self.true_nphotons * i, self.true_nphotons * (i + 1))
+            yield GPUPhotonsSlice(pos=self.pos[w], dir=self.dir[w], pol=self.pol[w], wavelengths=self.wavelengths[w],
+                                  t=self.t[w], last_hit_triangles=self.last_hit_triangles[w], flags=self.flags[w],
+                                  weights=self.weights[w], evidx=self.evidx[w])
+
+    def propagate(self, gpu_geometry, rng_states, nthreads_per_block=256, max_blocks=1024, max_steps=10,
+                  use_weights=False, scatter_first=0, track=False):
+        """Propagate photons to termination or ``max_steps`` (gpu/photon.py:227-290).
+
+        The whole step loop runs on the device in one call.  ``rng_states`` needs
+        ``nthreads_per_block*max_blocks`` states; with a pool >= len(self) photon i
+        uses stream i (replay contract); larger banks reuse the pool chunk by chunk.
+        With ``track=True`` returns (step_photon_ids, step_photons) like the reference.
+        """
+        lib = _lib.lib()
+        bank = self._bank()
+        self.last_stats = _lib.CbPropagateStats()
+        if not track:
+            _lib.check(lib.cb_propagate(C.byref(bank), gpu_geometry.handle, rng_states.handle,
+                                        int(nthreads_per_block), int(max_blocks), int(max_steps),
+                                        int(bool(use_weights)), int(scatter_first), C.byref(self.last_stats)))
+            return None
+        # tracking: one step per call, snapshotting the still-alive photons
+        n = self.pos.size
+        ids = np.arange(n, dtype=np.uint32)
+        step_photon_ids, step_photons = [ids], [self.copy_queue(ga.to_gpu(ids), n).get()]
+        for step in range(max_steps):
+            _lib.check(lib.cb_propagate(C.byref(bank), gpu_geometry.handle, rng_states.handle,
+                                        int(nthreads_per_block), int(max_blocks), 1, int(bool(use_weights)),
+                                        int(scatter_first), None))
+            scatter_first = 0
+            flags = self.flags.get()
+            alive_prev = ids
+            step_photon_ids.append(alive_prev)
+            step_photons.append(self.copy_queue(ga.to_gpu(alive_prev), len(alive_prev)).get())
+            ids = alive_prev[(flags[alive_prev] & event.TERMINAL_MASK) == 0]
+            if len(ids) == 0:
+                break
+        return step_photon_ids, step_photons
+
+    def copy_queue(self, queue_gpu, nphotons, nthreads_per_block=256, max_blocks=1024, start_photon=0):
+        out = _alloc_bank(nphotons)
+        if nphotons:
+            src = self._bank()
+            dst = _lib.CbPhotonBank()
+            for f in _FIELDS:
+                setattr(dst, f, out[f].ptr)
+            dst.n = nphotons
+            _lib.check(_lib.lib().cb_copy_photon_queue(C.byref(src), queue_gpu.ptr + 4 * start_photon,
+                                                       int(nphotons), C.byref(dst)))
+        return GPUPhotonsSlice(**out)
+
+    def select(self, target_flag, nthreads_per_block=256, max_blocks=1024, start_photon=None, nphotons=None):
+        """New bank with only the photons that have ``target_flag`` set
+        (gpu/photon.py:321-371); photon order is preserved."""
+        lib = _lib.lib()
+        start_photon = 0 if start_photon is None else start_photon
+        nphotons = self.pos.size - start_photon if nphotons is None else nphotons
+        src = self._bank()
+        count = C.c_uint32()
+        _lib.check(lib.cb_count_photons(C.byref(src), int(start_photon), int(nphotons), int(target_flag), C.byref(count)))
+        n = count.value
+        out = _alloc_bank(n)
+        if n:
+            dst = _lib.CbPhotonBank()
+            for f in _FIELDS:
+                setattr(dst, f, out[f].ptr)
+            dst.n = n
+            c2 = C.c_uint32()
+            _lib.check(lib.cb_copy_photons(C.byref(src), int(start_photon), int(nphotons), int(target_flag),
+                                           C.byref(dst), C.byref(c2)))
+            assert c2.value == n
+        return GPUPhotonsSlice(**out)
+
+    def __len__(self):
+        return self.pos.size
+
+
+class GPUPhotonsSlice(GPUPhotons):
+    """A view (or freshly compacted bank) that behaves like GPUPhotons
+    (gpu/photon.py:388-415)."""
+
+    def __init__(self, pos, dir, pol, wavelengths, t, last_hit_triangles, flags, weights, evidx):
+        self.pos, self.dir, self.pol = pos, dir, pol
+        self.wavelengths, self.t = wavelengths, t
+        self.last_hit_triangles, self.flags, self.weights, self.evidx = last_hit_triangles, flags, weights, evidx
+        self.true_nphotons = len(pos)
+        self.ncopies = 1

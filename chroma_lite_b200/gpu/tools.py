@@ -1,0 +1,101 @@
+"""Boundary utilities (role of chroma/gpu/tools.py): context creation, RNG
+pool, launch chunking helpers, float3/uint3 views."""
+import ctypes as C
+import numpy as np
+
+from .. import _lib
+from ..gpuarray import vec
+
+
+def create_cuda_context(device_id=None):
+    """Bind this process to one GPU (chroma/gpu/tools.py:182-203).  Returns a
+    small object with pop()/synchronize() so Simulation's lifecycle code works."""
+    dev = _lib.init(device_id)
+    return _Context(dev)
+
+
+class _Context(object):
+    def __init__(self, device):
+        self.device = device
+
+    def synchronize(self):
+        _lib.check(_lib.lib().cb_synchronize())
+
+    def pop(self):
+        pass
+
+    def push(self):
+        pass
+
+
+class RNGStates(object):
+    """Pool of XORWOW states; state i == curand_init(seed, i, 0)
+    (get_rng_states, chroma/gpu/tools.py:136-145)."""
+
+    def __init__(self, size, seed=1, offset=0):
+        h = C.c_uint64()
+        _lib.check(_lib.lib().cb_rng_create(int(size), int(seed) & 0xFFFFFFFFFFFFFFFF, int(offset), C.byref(h)))
+        self.handle = h.value
+        self.size = int(size)
+        self.seed = seed
+
+    def __len__(self):
+        return self.size
+
+    def get(self, first=0, count=None):
+        """State words {d, v0..v4} as uint32 (count, 6)."""
+        count = self.size - first if count is None else count
+        out = np.empty((count, 6), dtype=np.uint32)
+        _lib.check(_lib.lib().cb_rng_download(self.handle, int(first), int(count), out.ctypes.data))
+        return out
+
+    def __del__(self):
+        try:
+            if self.handle and _lib._lib is not None:
+                _lib._lib.cb_rng_destroy(self.handle)
+        except Exception:
+            pass
+        self.handle = 0
+
+
+def get_rng_states(size, seed=1):
+    "Return `size` number of CUDA random number generator states."
+    return RNGStates(size, seed=seed)
+
+
+def to_float3(arr):
+    "(N,3) array -> float3 structured array (chroma/gpu/tools.py:147-151)."
+    arr = np.ascontiguousarray(arr, dtype=np.float32)
+    return arr.view(vec.float3)[:, 0]
+
+
+def to_uint3(arr):
+    arr = np.ascontiguousarray(arr, dtype=np.uint32)
+    return arr.view(vec.uint3)[:, 0]
+
+
+def chunk_iterator(nelements, nthreads_per_block=64, max_blocks=1024):
+    """(first_index, elements_this_iteration, nblocks_this_iteration) tuples
+    (chroma/gpu/tools.py:159-180).
+
+    >>> list(chunk_iterator(300, 32, 2))
+    [(0, 64, 2), (64, 64, 2), (128, 64, 2), (192, 64, 2), (256, 44, 2)]
+    """
+    first = 0
+    while first < nelements:
+        left = nelements - first
+        blocks = min(max_blocks, -(-left // nthreads_per_block))
+        n = min(left, blocks * nthreads_per_block)
+        yield (first, n, blocks)
+        first += n
+
+
+def format_size(size):
+    for lim, div, suf in ((1e3, 1, ' '), (1e6, 1e3, 'K'), (1e9, 1e6, 'M')):
+        if size < lim:
+            return '%.1f%s' % (size / div, suf)
+    return '%.1f%s' % (size / 1e9, 'G')
+
+
+def format_array(name, array):
+    return '%-15s %6s %6s' % (name, format_size(len(array)), format_size(array.nbytes))

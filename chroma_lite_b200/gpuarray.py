@@ -1,0 +1,149 @@
+"""Minimal GPUArray-like device array over the C ABI's raw allocations.
+
+Covers what the reference's hot-path host code uses from pycuda.gpuarray
+(SURVEY App. C): empty/zeros/to_gpu/zeros_like/ones_like, .get/.set/.fill,
+.gpudata/.size/.dtype/.nbytes/len and contiguous 1-D slicing.
+"""
+import ctypes as C
+import numpy as np
+
+from . import _lib
+
+
+class vec(object):
+    """Stand-ins for pycuda.gpuarray.vec dtypes used by the reference."""
+    float3 = np.dtype([('x', np.float32), ('y', np.float32), ('z', np.float32)])
+    uint3 = np.dtype([('x', np.uint32), ('y', np.uint32), ('z', np.uint32)])
+    uint4 = np.dtype([('x', np.uint32), ('y', np.uint32), ('z', np.uint32), ('w', np.uint32)])
+    float4 = np.dtype([('x', np.float32), ('y', np.float32), ('z', np.float32), ('w', np.float32)])
+
+    @staticmethod
+    def make_float3(x, y, z):
+        a = np.zeros((), dtype=vec.float3)
+        a['x'], a['y'], a['z'] = x, y, z
+        return a
+
+
+class _Allocation(object):
+    """Owns one device allocation; freed when the last view goes away."""
+    def __init__(self, nbytes):
+        p = C.c_void_p()
+        _lib.check(_lib.lib().cb_malloc(int(nbytes), C.byref(p)))
+        self.ptr = p.value
+        self.nbytes = int(nbytes)
+
+    def __del__(self):
+        try:
+            if self.ptr and _lib._lib is not None:
+                _lib._lib.cb_free(C.c_void_p(self.ptr))
+        except Exception:
+            pass
+        self.ptr = None
+
+
+class DeviceArray(object):
+    def __init__(self, shape, dtype, _alloc=None, _ptr=None):
+        if np.isscalar(shape):
+            shape = (int(shape),)
+        self.shape = tuple(int(s) for s in shape)
+        self.dtype = np.dtype(dtype)
+        self.size = int(np.prod(self.shape)) if len(self.shape) else 1
+        self.nbytes = self.size * self.dtype.itemsize
+        if _alloc is None and _ptr is None:
+            self._alloc = _Allocation(max(self.nbytes, 16))
+            self.ptr = self._alloc.ptr
+        else:
+            self._alloc = _alloc      # keeps the owner alive (None for foreign memory)
+            self.ptr = _ptr
+
+    # -- pycuda-compatible surface
+    @property
+    def gpudata(self):
+        return self.ptr
+
+    def __int__(self):
+        return int(self.ptr)
+
+    def __len__(self):
+        return self.shape[0] if self.shape else 1
+
+    @property
+    def __cuda_array_interface__(self):
+        # lets torch.as_tensor(..., device='cuda') alias the memory (NCCL plumbing)
+        if self.dtype.fields is not None:
+            raise TypeError('structured dtype cannot be exported; use .view()')
+        return {'shape': self.shape, 'typestr': self.dtype.str, 'data': (int(self.ptr), False),
+                'version': 2}
+
+    def view(self, dtype):
+        dtype = np.dtype(dtype)
+        assert self.nbytes % dtype.itemsize == 0
+        return DeviceArray(self.nbytes // dtype.itemsize, dtype, _alloc=self._alloc, _ptr=self.ptr)
+
+    def get(self):
+        out = np.empty(self.shape, dtype=self.dtype)
+        if self.nbytes:
+            _lib.check(_lib.lib().cb_memcpy_d2h(out.ctypes.data, self.ptr, self.nbytes))
+        return out
+
+    def set(self, arr):
+        arr = np.ascontiguousarray(arr)
+        if arr.nbytes != self.nbytes:
+            raise ValueError('size mismatch in DeviceArray.set: %d != %d bytes' % (arr.nbytes, self.nbytes))
+        if self.nbytes:
+            _lib.check(_lib.lib().cb_memcpy_h2d(self.ptr, arr.ctypes.data, self.nbytes))
+        return self
+
+    def copy_from_device(self, other, nbytes=None):
+        n = self.nbytes if nbytes is None else int(nbytes)
+        _lib.check(_lib.lib().cb_memcpy_d2d(self.ptr, int(other), n))
+        return self
+
+    def fill(self, value):
+        if self.dtype.itemsize != 4 or self.dtype.fields is not None:
+            raise TypeError('fill() supports 4-byte scalar dtypes')
+        bits = int(np.array(value, dtype=self.dtype).view(np.uint32))
+        _lib.check(_lib.lib().cb_memset32(self.ptr, bits, self.size))
+        return self
+
+    def __getitem__(self, key):
+        if not isinstance(key, slice):
+            raise TypeError('DeviceArray supports contiguous slices only')
+        start, stop, step = key.indices(len(self))
+        if step != 1:
+            raise ValueError('DeviceArray slices must be contiguous')
+        n = max(0, stop - start)
+        return DeviceArray(n, self.dtype, _alloc=self._alloc or self, _ptr=self.ptr + start * self.dtype.itemsize)
+
+
+GPUArray = DeviceArray
+
+
+def empty(shape, dtype):
+    return DeviceArray(shape, dtype)
+
+
+def zeros(shape, dtype):
+    a = DeviceArray(shape, dtype)
+    if a.nbytes:
+        _lib.check(_lib.lib().cb_memset32(a.ptr, 0, (a.nbytes + 3) // 4))
+    return a
+
+
+def to_gpu(arr):
+    arr = np.ascontiguousarray(arr)
+    return DeviceArray(arr.shape, arr.dtype).set(arr)
+
+
+def zeros_like(other, dtype=None):
+    return zeros(other.shape, dtype or other.dtype)
+
+
+def ones_like(other, dtype=None):
+    a = DeviceArray(other.shape, dtype or other.dtype)
+    a.fill(1)
+    return a
+
+
+def empty_like(other):
+    return DeviceArray(other.shape, other.dtype)

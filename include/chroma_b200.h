@@ -1,0 +1,262 @@
+/*
+ * chroma_b200.h -- C ABI of libchroma_b200.so, the B200-native (sm_100a) photon
+ * transport engine that sits behind Chroma's Python API.
+ *
+ * Every entry point is `extern "C"`, takes plain pointers / sizes only, returns
+ * 0 on success or a negative CbStatus, and leaves a message retrievable with
+ * cb_last_error().  The reference binds its device code through PyCUDA
+ * (compile-at-run-time + driver API); each entry below names the reference
+ * interface it replaces (paths relative to the reference checkout).
+ *
+ * Conventions
+ *   - "device pointer" arguments are CUDA device addresses obtained from
+ *     cb_malloc() (or any other allocator of the same context).
+ *   - host arrays are borrowed for the duration of the call only.
+ *   - all calls are synchronous on return unless stated otherwise (the
+ *     reference synchronises at the end of propagate/acquire/end_acquire:
+ *     chroma/gpu/photon.py:290, chroma/gpu/daq.py:92,99).
+ *   - one library instance drives one CUDA device (cb_init); one process per
+ *     GPU is the multi-GPU model.
+ */
+#ifndef CHROMA_B200_H
+#define CHROMA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CB_ABI_VERSION 1
+
+typedef enum {
+    CB_OK = 0,
+    CB_ERR_CUDA = -1,
+    CB_ERR_INVALID = -2,
+    CB_ERR_NOMEM = -3,
+    CB_ERR_UNSUPPORTED = -4
+} CbStatus;
+
+typedef uint64_t cb_geom_t;
+typedef uint64_t cb_rng_t;
+typedef uint64_t cb_daq_t;
+
+/* Surface models, chroma/cuda/geometry_types.h:22 */
+enum { CB_SURFACE_DEFAULT = 0, CB_SURFACE_COMPLEX = 1, CB_SURFACE_WLS = 2,
+       CB_SURFACE_DICHROIC = 3, CB_SURFACE_ANGULAR = 4 };
+
+/* History bits, chroma/cuda/photon.h:53-68 (NAN_ABORT is bit 15 in the kernel). */
+enum {
+    CB_NO_HIT = 0x1, CB_BULK_ABSORB = 0x2, CB_SURFACE_DETECT = 0x4,
+    CB_SURFACE_ABSORB = 0x8, CB_RAYLEIGH_SCATTER = 0x10, CB_REFLECT_DIFFUSE = 0x20,
+    CB_REFLECT_SPECULAR = 0x40, CB_SURFACE_REEMIT = 0x80, CB_SURFACE_TRANSMIT = 0x100,
+    CB_BULK_REEMIT = 0x200, CB_CHERENKOV = 0x400, CB_SCINTILLATION = 0x800,
+    CB_NAN_ABORT = 0x8000
+};
+
+/*
+ * Optical tables.  All wavelength/time tables live in ONE float pool
+ * (`table_pool`); materials and surfaces reference it by float offset.  This
+ * replaces the per-table device allocations + pointer structs assembled by
+ * make_gpu_struct (chroma/gpu/geometry.py:44-341, chroma/gpu/tools.py:207-229;
+ * device structs chroma/cuda/geometry_types.h:4-79).  Offsets < 0 mean
+ * "absent".  Per-component tables are stored as [num_comp][n] blocks.
+ */
+typedef struct {
+    int32_t refractive_index;       /* [wavelength_n] */
+    int32_t absorption_length;      /* [wavelength_n] */
+    int32_t scattering_length;      /* [wavelength_n] */
+    int32_t num_comp;
+    int32_t comp_reemission_prob;      /* [num_comp][wavelength_n] */
+    int32_t comp_reemission_wvl_cdf;   /* [num_comp][wavelength_n] */
+    int32_t comp_reemission_time_cdf;  /* [num_comp][time_n]       */
+    int32_t comp_absorption_length;    /* [num_comp][wavelength_n] */
+} CbMaterial;
+
+typedef struct {
+    int32_t detect, absorb, reemit, reflect_diffuse, reflect_specular, eta, k,
+            reemission_cdf;         /* each [wavelength_n] */
+    int32_t model;                  /* CB_SURFACE_*; -1 = null surface slot */
+    int32_t transmissive;
+    float   thickness;
+    /* DichroicProps (geometry_types.h:24-30): angles[n], reflect[n][W], transmit[n][W] */
+    int32_t dichroic_nangles, dichroic_angles, dichroic_reflect, dichroic_transmit;
+    /* AngularProps (geometry_types.h:32-39): 4 arrays of [n] */
+    int32_t angular_nangles, angular_angles, angular_transmit,
+            angular_reflect_specular, angular_reflect_diffuse;
+} CbSurface;
+
+/*
+ * Flattened geometry handed to the engine; mirrors what GPUGeometry.__init__
+ * uploads (chroma/gpu/geometry.py:389-520) and `struct Geometry`
+ * (chroma/cuda/geometry_types.h:124-139).  `nodes` is the reference uint4
+ * packing (x,y,z = lo16 | hi16<<16, w = nchild<<28 | child; root = node 0);
+ * the library derives its own traversal layout from it.
+ */
+typedef struct {
+    const float*    vertices;        uint64_t nvertices;   /* [nvertices][3]  */
+    const uint32_t* triangles;       uint64_t ntriangles;  /* [ntriangles][3] */
+    const uint32_t* material_codes;  /* [ntriangles] m1<<24 | m2<<16 | surf<<8 */
+    const uint32_t* solid_id;        /* [ntriangles] or NULL */
+    const uint32_t* colors;          /* [ntriangles] or NULL */
+    const uint32_t* nodes;           uint64_t nnodes;      /* [nnodes][4] */
+    float world_origin[3];
+    float world_scale;
+    const float*      table_pool;    uint64_t table_floats;
+    const CbMaterial* materials;     int32_t nmaterials;
+    const CbSurface*  surfaces;      int32_t nsurfaces;
+    int32_t wavelength_n; float wavelength_start, wavelength_step;
+    int32_t time_n;       float time_start, time_step;
+    int32_t nwireplanes;             /* must be 0 (analytic wire planes: unsupported) */
+} CbGeometryDesc;
+
+/* Device-side views of what the library uploaded (for the GPUGeometry mirror). */
+typedef struct {
+    void* vertices; void* triangles; void* material_codes; void* colors;
+    void* solid_id_map; void* nodes;           /* reference-layout copies */
+    void* solid_id_to_channel_index; void* time_cdf_x; void* time_cdf_y;
+    void* charge_cdf_x; void* charge_cdf_y;    /* NULL until cb_detector_attach */
+    uint64_t nvertices, ntriangles, nnodes;
+    int32_t  nchannels;
+    uint64_t device_bytes;                     /* total bytes held by this geometry */
+    uint32_t max_stack_depth;                  /* deepest traversal stack the tree can need */
+} CbGeometryInfo;
+
+/* Photon bank: struct-of-arrays of DEVICE pointers, same arrays as GPUPhotons
+ * (chroma/gpu/photon.py:46-62).  pos/dir/pol are packed float3 (12 B). */
+typedef struct {
+    float*    pos; float* dir; float* pol;
+    float*    wavelengths; float* t;
+    int32_t*  last_hit_triangles;
+    uint32_t* flags;
+    float*    weights;
+    uint32_t* evidx;
+    uint64_t  n;
+} CbPhotonBank;
+
+typedef struct {
+    uint64_t photons;        /* photons processed */
+    uint64_t steps;          /* total propagation steps taken */
+    uint64_t nodes_visited;  /* BVH node boxes tested (0 unless stats build) */
+    uint64_t tris_tested;    /* triangle tests        (0 unless stats build) */
+    uint32_t launches;       /* kernels launched by this call */
+    float    kernel_ms;      /* device time of those kernels (CUDA events) */
+} CbPropagateStats;
+
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+/* ---- runtime --------------------------------------------------------- */
+/* replaces chroma/gpu/tools.py:182-203 create_cuda_context */
+int         cb_init(int device);
+int         cb_device_count(void);
+int         cb_abi_version(void);
+const char* cb_last_error(void);
+int         cb_synchronize(void);
+int         cb_sm_count(void);
+
+/* replaces pycuda.driver.mem_alloc / memcpy_* / GPUArray.fill */
+int cb_malloc(uint64_t bytes, void** dptr);
+int cb_free(void* dptr);
+int cb_memcpy_h2d(void* dptr, const void* hptr, uint64_t bytes);
+int cb_memcpy_d2h(void* hptr, const void* dptr, uint64_t bytes);
+int cb_memcpy_d2d(void* dst, const void* src, uint64_t bytes);
+int cb_memset32(void* dptr, uint32_t value, uint64_t count);
+int cb_host_alloc(uint64_t bytes, void** hptr);   /* pinned */
+int cb_host_free(void* hptr);
+int cb_mem_info(uint64_t* free_bytes, uint64_t* total_bytes);
+
+/* device timers (CUDA events on the library stream) for bench.py */
+int cb_timer_start(void);
+int cb_timer_stop(float* ms);
+int cb_flush_l2(void);     /* writes a buffer larger than L2 */
+
+/* ---- geometry / detector --------------------------------------------- */
+/* replaces GPUGeometry.__init__ (chroma/gpu/geometry.py:14-526) */
+int cb_geometry_create(const CbGeometryDesc* desc, cb_geom_t* out);
+int cb_geometry_destroy(cb_geom_t g);
+int cb_geometry_info(cb_geom_t g, CbGeometryInfo* info);
+/* replaces GPUDetector.__init__ (chroma/gpu/detector.py:15-39), struct Detector (cuda/detector.h:4-22) */
+int cb_detector_attach(cb_geom_t g, const int32_t* solid_id_to_channel_index,
+                       uint64_t nsolids, int32_t nchannels,
+                       const float* time_cdf_x, const float* time_cdf_y, int32_t time_cdf_len,
+                       const float* charge_cdf_x, const float* charge_cdf_y, int32_t charge_cdf_len,
+                       float charge_unit);
+
+/* ---- BVH construction ------------------------------------------------ */
+/* replaces make_recursive_grid_bvh (chroma/bvh/grid.py:11-95) and its kernels
+ * make_leaves / make_parents_detailed / copy_and_offset / collapse_child
+ * (chroma/cuda/bvh.cu:148,269,364,530).  Two-call protocol: with nodes_out ==
+ * NULL only *nnodes_out / *nlayers_out are written. */
+int cb_bvh_build(const float* vertices, uint64_t nvertices,
+                 const uint32_t* triangles, uint64_t ntriangles,
+                 int32_t target_degree,
+                 float world_origin_out[3], float* world_scale_out,
+                 uint32_t* nodes_out, uint64_t* nnodes_out,
+                 uint64_t* layer_offsets_out, int32_t* nlayers_out);
+
+/* ---- RNG ---------------------------------------------------------------- */
+/* replaces get_rng_states / init_rng (chroma/gpu/tools.py:117-145,
+ * chroma/cuda/random.h:60-70): state i == curand_init(seed, i, offset). */
+int cb_rng_create(uint64_t n, uint64_t seed, uint64_t offset, cb_rng_t* out);
+int cb_rng_destroy(cb_rng_t r);
+int cb_rng_size(cb_rng_t r, uint64_t* n);
+/* test hooks: state words {d, v0..v4} and fill_uniform (chroma/cuda/random.h:72-82) */
+int cb_rng_download(cb_rng_t r, uint64_t first, uint64_t count, uint32_t* out6);
+int cb_rng_fill_uniform(cb_rng_t r, uint64_t n, float low, float high, float* d_out);
+
+/* ---- ray intersection -------------------------------------------------- */
+/* replaces distance_to_mesh / intersect_mesh (chroma/cuda/mesh.h:45-155); also
+ * returns the triangle index (-1 = miss; distance untouched on miss, as in the
+ * reference).  d_last_hit may be NULL. All pointers are device pointers. */
+int cb_intersect(cb_geom_t g, const float* d_origins, const float* d_directions,
+                 const int32_t* d_last_hit, uint64_t n,
+                 int32_t* d_triangle_out, float* d_distance_out);
+
+/* ---- propagation -------------------------------------------------------- */
+/* replaces GPUPhotons.propagate + the propagate kernel
+ * (chroma/gpu/photon.py:227-290, chroma/cuda/propagate.cu:254-366).
+ * nthreads_per_block*max_blocks is NOT a launch shape here; it only has to
+ * match the rng pool contract (pool >= n gives photon i <-> stream i). */
+int cb_propagate(const CbPhotonBank* bank, cb_geom_t g, cb_rng_t rng,
+                 int32_t nthreads_per_block, int32_t max_blocks, int32_t max_steps,
+                 int32_t use_weights, int32_t scatter_first, CbPropagateStats* stats);
+
+/* ---- photon bank utilities (chroma/cuda/propagate.cu:29-251) ------------ */
+int cb_photon_duplicate(const CbPhotonBank* bank, uint64_t nphotons, int32_t ncopies);
+int cb_count_photons(const CbPhotonBank* bank, uint64_t first, uint64_t n,
+                     uint32_t target_flag, uint32_t* count_out);
+int cb_copy_photons(const CbPhotonBank* src, uint64_t first, uint64_t n,
+                    uint32_t target_flag, const CbPhotonBank* dst, uint32_t* count_out);
+int cb_count_photon_hits(const CbPhotonBank* bank, uint64_t first, uint64_t n,
+                         uint32_t target_flag, cb_geom_t g, uint32_t* count_out);
+int cb_copy_photon_hits(const CbPhotonBank* src, uint64_t first, uint64_t n,
+                        uint32_t target_flag, cb_geom_t g, const CbPhotonBank* dst,
+                        int32_t* d_channels_out, uint32_t* count_out);
+int cb_copy_photon_queue(const CbPhotonBank* src, const uint32_t* d_queue, uint64_t n,
+                         const CbPhotonBank* dst);
+
+/* ---- DAQ (chroma/gpu/daq.py:37-101, chroma/cuda/daq.cu) ----------------- */
+int cb_daq_create(cb_geom_t g, int32_t ndaq, cb_daq_t* out);
+int cb_daq_destroy(cb_daq_t d);
+int cb_daq_begin_acquire(cb_daq_t d);
+int cb_daq_acquire(cb_daq_t d, const CbPhotonBank* bank, cb_rng_t rng,
+                   int32_t nthreads_per_block, int32_t max_blocks,
+                   uint64_t start_photon, uint64_t nphotons, float weight);
+int cb_daq_end_acquire(cb_daq_t d);
+/* device pointers of earliest_time(float), q(float), flags(u32), and the raw
+ * integer accumulators time_int(u32), q_int(u32); each [nchannels*ndaq] */
+int cb_daq_pointers(cb_daq_t d, void** t, void** q, void** flags,
+                    void** time_int, void** q_int, uint64_t* count);
+/* finalise from integer accumulators only (after a cross-GPU reduction) */
+int cb_daq_finalize(cb_daq_t d);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CHROMA_B200_H */

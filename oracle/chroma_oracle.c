@@ -1,0 +1,1116 @@
+/*
+ * chroma_oracle.c -- TEST INFRASTRUCTURE ONLY.
+ *
+ * CPU restatement (plain C, scalar) of the reference's photon-transport hot
+ * path, used as the checker in tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline leg.  Nothing in the product package may import, link or call
+ * this file.  Every function cites the reference source it follows (paths
+ * relative to the reference checkout, chroma/cuda/...).
+ *
+ * Parity status:
+ *   - XORWOW (third-party: cuRAND device API, CUDA toolkit 12.9,
+ *     curand_kernel.h:772-874, curand_uniform.h:69-72) is integer arithmetic and
+ *     is pinned bit-for-bit against libcurand's host generator
+ *     (tests/test_oracle_rng.py) and against the toolkit's precalculated
+ *     skip-ahead matrices (curand_precalc.h).
+ *   - BVH traversal / triangle test follow mesh.h / intersect.h line by line and
+ *     are pinned against the reference's golden vector
+ *     test/data/ray_intersection.npy to float tolerance (the reference kernels
+ *     are built with --use_fast_math and FMA contraction, which plain C cannot
+ *     reproduce bit-for-bit; bit-level parity is defined against the reference's
+ *     own kernels compiled into oracle/_ref and run on the GPU).
+ *   - Physics (photon.h) is parity-unpinned by the reference's own tests (they
+ *     are statistical and stale); it is pinned here against
+ *     the reference kernels run on the GPU (oracle/_ref) within tolerance.
+ *
+ * Analytic wire planes (photon.h:108-270) are not restated: nwireplanes == 0 in
+ * every BASELINE config.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <float.h>
+
+#include "../include/chroma_b200.h"
+
+#define ORC_EXPORT __attribute__((visibility("default")))
+
+/* ===================================================================== */
+/* XORWOW                                                                */
+/* ===================================================================== */
+
+typedef struct { uint32_t d, v[5]; } orc_rng;
+
+/* curand_kernel.h:863-874 */
+static inline uint32_t xorwow_next(orc_rng *s)
+{
+    uint32_t t = s->v[0] ^ (s->v[0] >> 2);
+    s->v[0] = s->v[1]; s->v[1] = s->v[2]; s->v[2] = s->v[3]; s->v[3] = s->v[4];
+    s->v[4] = (s->v[4] ^ (s->v[4] << 4)) ^ (t ^ (t << 1));
+    s->d += 362437u;
+    return s->v[4] + s->d;
+}
+
+/* curand_uniform.h:69-72 : x * 2^-32 + 2^-33, in (0, 1] */
+static inline float xorwow_uniform(orc_rng *s)
+{
+    uint32_t x = xorwow_next(s);
+    return (float)x * 2.3283064e-10f + (2.3283064e-10f / 2.0f);
+}
+
+/* 160x160 GF(2) matrices in cuRAND's row layout: row i (bit i of the state
+ * vector) holds the 5-word image of that basis bit
+ * (curand_kernel.h:568-586 __curand_generate_skipahead_matrix_xor). */
+#define XW_N 5
+#define XW_ROWS 160
+typedef struct { uint32_t r[XW_ROWS][XW_N]; } xw_mat;
+
+static void xw_matvec(const xw_mat *m, const uint32_t *v, uint32_t *out)
+{
+    uint32_t acc[XW_N] = {0, 0, 0, 0, 0};
+    for (int i = 0; i < XW_ROWS; i++)
+        if (v[i >> 5] & (1u << (i & 31)))
+            for (int j = 0; j < XW_N; j++) acc[j] ^= m->r[i][j];
+    memcpy(out, acc, sizeof(acc));
+}
+
+/* out = "apply a then b": row i of out = b applied to (row i of a) */
+static void xw_matmat(const xw_mat *a, const xw_mat *b, xw_mat *out)
+{
+    xw_mat tmp;
+    for (int i = 0; i < XW_ROWS; i++) xw_matvec(b, a->r[i], tmp.r[i]);
+    *out = tmp;
+}
+
+static void xw_one_step(xw_mat *m)
+{
+    for (int i = 0; i < XW_ROWS; i++) {
+        orc_rng s; s.d = 0;
+        for (int j = 0; j < XW_N; j++) s.v[j] = 0;
+        s.v[i >> 5] = 1u << (i & 31);
+        xorwow_next(&s);
+        for (int j = 0; j < XW_N; j++) m->r[i][j] = s.v[j];
+    }
+}
+
+/* seq[k] = M^(2^67 * 2^k)  (sequence skip, curand_kernel.h:719-735),
+ * off[k] = M^(2^k)         (offset skip,  curand_kernel.h:700-717).  */
+static xw_mat *g_seq = NULL, *g_off = NULL;
+
+static void xw_tables(void)
+{
+    if (g_seq) return;
+    xw_mat *off = (xw_mat *)malloc(sizeof(xw_mat) * 64);
+    xw_mat *seq = (xw_mat *)malloc(sizeof(xw_mat) * 64);
+    xw_one_step(&off[0]);
+    for (int k = 1; k < 64; k++) xw_matmat(&off[k - 1], &off[k - 1], &off[k]);
+    xw_mat m = off[63];
+    for (int k = 64; k <= 67; k++) xw_matmat(&m, &m, &m); /* -> M^(2^67) */
+    seq[0] = m;
+    for (int k = 1; k < 64; k++) xw_matmat(&seq[k - 1], &seq[k - 1], &seq[k]);
+    g_off = off; g_seq = seq;
+}
+
+/* curand_init(seed, subsequence, offset): curand_kernel.h:772-800 */
+ORC_EXPORT void orc_xorwow_init(uint64_t seed, uint64_t subsequence, uint64_t offset,
+                                uint32_t state[6])
+{
+    xw_tables();
+    uint32_t s0 = ((uint32_t)seed) ^ 0xaad26b49u;
+    uint32_t s1 = (uint32_t)(seed >> 32) ^ 0xf7dcefddu;
+    uint32_t t0 = 1099087573u * s0;
+    uint32_t t1 = 2591861531u * s1;
+    orc_rng s;
+    s.d = 6615241u + t1 + t0;
+    s.v[0] = 123456789u + t0;
+    s.v[1] = 362436069u ^ t0;
+    s.v[2] = 521288629u + t1;
+    s.v[3] = 88675123u ^ t1;
+    s.v[4] = 5783321u + t0;
+    for (int k = 0; k < 64; k++)
+        if (subsequence & (1ull << k)) xw_matvec(&g_seq[k], s.v, s.v);
+    for (int k = 0; k < 64; k++)
+        if (offset & (1ull << k)) xw_matvec(&g_off[k], s.v, s.v);
+    s.d += 362437u * (uint32_t)offset;
+    state[0] = s.d;
+    for (int j = 0; j < 5; j++) state[1 + j] = s.v[j];
+}
+
+ORC_EXPORT uint32_t orc_xorwow_next(uint32_t state[6])
+{
+    orc_rng s; s.d = state[0]; memcpy(s.v, state + 1, 20);
+    uint32_t x = xorwow_next(&s);
+    state[0] = s.d; memcpy(state + 1, s.v, 20);
+    return x;
+}
+
+/* matrix accessors so the tests can compare with curand_precalc.h:
+ * which=0 -> M^(2^67 * 4^k) (precalc_xorwow_matrix[k]),
+ * which=1 -> M^(4^k)        (precalc_xorwow_offset_matrix[k]); PRECALC_BLOCK_SIZE=2 */
+ORC_EXPORT void orc_xorwow_matrix(int which, int k, uint32_t out[800])
+{
+    xw_tables();
+    const xw_mat *m = which == 0 ? &g_seq[2 * k] : &g_off[2 * k];
+    memcpy(out, m->r, sizeof(uint32_t) * 800);
+}
+
+/* states[i] = curand_init(seed, first_stream + i, offset); mirrors init_rng
+ * (random.h:60-70) */
+ORC_EXPORT void orc_rng_init(uint64_t seed, uint64_t first_stream, uint64_t n,
+                             uint64_t offset, uint32_t *states6)
+{
+    for (uint64_t i = 0; i < n; i++)
+        orc_xorwow_init(seed, first_stream + i, offset, states6 + 6 * i);
+}
+
+/* fill_uniform (random.h:72-82): one draw per state */
+ORC_EXPORT void orc_rng_fill_uniform(uint32_t *states6, uint64_t n, float low, float high,
+                                     float *out)
+{
+    for (uint64_t i = 0; i < n; i++) {
+        orc_rng s; s.d = states6[6 * i]; memcpy(s.v, states6 + 6 * i + 1, 20);
+        out[i] = low + xorwow_uniform(&s) * (high - low);
+        states6[6 * i] = s.d; memcpy(states6 + 6 * i + 1, s.v, 20);
+    }
+}
+
+/* ===================================================================== */
+/* linalg.h                                                              */
+/* ===================================================================== */
+typedef struct { float x, y, z; } f3;
+static inline f3 mk(float x, float y, float z) { f3 r = {x, y, z}; return r; }
+static inline f3 add(f3 a, f3 b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); }
+static inline f3 sub(f3 a, f3 b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }
+static inline f3 neg(f3 a) { return mk(-a.x, -a.y, -a.z); }
+static inline f3 scale(f3 a, float c) { return mk(a.x * c, a.y * c, a.z * c); }
+static inline f3 divs(f3 a, float c) { return mk(a.x / c, a.y / c, a.z / c); }
+static inline float dot(f3 a, f3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+static inline f3 cross(f3 a, f3 b)
+{
+    return mk(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+static inline float norm(f3 a) { return sqrtf(dot(a, a)); }
+static inline f3 normalize(f3 a) { return divs(a, norm(a)); }
+
+#define SPEED_OF_LIGHT 299.792458f /* physical_constants.h */
+#define PI_F 3.141592653589793f
+
+/* rotate.h:22-28 */
+static f3 rotate(f3 a, float phi, f3 n)
+{
+    float c = cosf(phi), s = sinf(phi);
+    return add(add(scale(a, c), scale(n, dot(a, n) * (1.0f - c))), scale(cross(a, n), s));
+}
+
+/* ===================================================================== */
+/* geometry.h / intersect.h / mesh.h                                     */
+/* ===================================================================== */
+typedef struct { f3 lower, upper; uint32_t child, nchild; } Node;
+
+/* geometry.h:31-47 */
+static inline Node get_node(const CbGeometryDesc *g, uint32_t i)
+{
+    const uint32_t *p = g->nodes + 4ull * i;
+    Node n;
+    n.lower = mk(g->world_origin[0] + (float)(p[0] & 0xFFFF) * g->world_scale,
+                 g->world_origin[1] + (float)(p[1] & 0xFFFF) * g->world_scale,
+                 g->world_origin[2] + (float)(p[2] & 0xFFFF) * g->world_scale);
+    n.upper = mk(g->world_origin[0] + (float)(p[0] >> 16) * g->world_scale,
+                 g->world_origin[1] + (float)(p[1] >> 16) * g->world_scale,
+                 g->world_origin[2] + (float)(p[2] >> 16) * g->world_scale);
+    n.child = p[3] & 0x0FFFFFFFu;
+    n.nchild = p[3] >> 28;
+    return n;
+}
+
+static inline f3 vtx(const CbGeometryDesc *g, uint32_t i)
+{
+    return mk(g->vertices[3ull * i], g->vertices[3ull * i + 1], g->vertices[3ull * i + 2]);
+}
+
+/* intersect.h:26-101 (Moller-Trumbore with double-promoted reciprocal/compares) */
+static int intersect_triangle(f3 origin, f3 direction, f3 v0, f3 v1, f3 v2, float *distance)
+{
+    f3 edge1 = sub(v1, v0), edge2 = sub(v2, v0);
+    f3 h = cross(direction, edge2);
+    float a = dot(edge1, h);
+    if (a > -FLT_EPSILON && a < FLT_EPSILON) return 0;
+    float f = (float)(1.0 / (double)a);
+    f3 s = sub(origin, v0);
+    float u = f * dot(s, h);
+    if ((double)u < -1e-6 || (double)u > 1.0 + 1e-6) return 0;
+    f3 q = cross(s, edge1);
+    float v = f * dot(direction, q);
+    if ((double)v < -1e-6 || (double)(u + v) > 1.0 + 1e-6) return 0;
+    float t = f * dot(edge2, q);
+    if ((double)t > 1e-6 && t < INFINITY) { *distance = t; return 1; }
+    return 0;
+}
+
+/* intersect.h:112-157 */
+static int intersect_box(f3 noid, f3 inv, f3 lo, f3 hi, float *dist)
+{
+    float tmin = 0.0f, tmax = INFINITY, t0, t1;
+    if (isfinite(inv.x)) {
+        t0 = lo.x * inv.x + noid.x; t1 = hi.x * inv.x + noid.x;
+        tmin = fmaxf(tmin, fminf(t0, t1)); tmax = fminf(tmax, fmaxf(t0, t1));
+    }
+    if (isfinite(inv.y)) {
+        t0 = lo.y * inv.y + noid.y; t1 = hi.y * inv.y + noid.y;
+        tmin = fmaxf(tmin, fminf(t0, t1)); tmax = fminf(tmax, fmaxf(t0, t1));
+    }
+    if (isfinite(inv.z)) {
+        t0 = lo.z * inv.z + noid.z; t1 = hi.z * inv.z + noid.z;
+        tmin = fmaxf(tmin, fminf(t0, t1)); tmax = fminf(tmax, fmaxf(t0, t1));
+    }
+    if (tmin > tmax) return 0;
+    *dist = tmin;
+    return 1;
+}
+
+/* mesh.h:16-38 */
+static int intersect_node(f3 noid, f3 inv, const Node *n, float min_distance)
+{
+    float d;
+    if (intersect_box(noid, inv, n->lower, n->upper, &d)) {
+        if (min_distance < 0.0f) return 1;
+        if (d > min_distance) return 0;
+        return 1;
+    }
+    return 0;
+}
+
+#define STACK_SIZE 1000
+typedef struct { uint64_t nodes, tris, calls; uint32_t max_stack; } orc_counters;
+
+/* mesh.h:45-126 */
+static int intersect_mesh(const CbGeometryDesc *g, f3 origin, f3 direction,
+                          float *min_distance_out, int last_hit_triangle, orc_counters *c)
+{
+    int triangle_index = -1;
+    float distance, min_distance = -1.0f;
+    Node root = get_node(g, 0);
+    f3 noid = mk(-origin.x / direction.x, -origin.y / direction.y, -origin.z / direction.z);
+    f3 inv = mk(1.0f / direction.x, 1.0f / direction.y, 1.0f / direction.z);
+    if (c) c->calls++;
+    *min_distance_out = min_distance;
+    if (!intersect_node(noid, inv, &root, min_distance)) return -1;
+
+    uint32_t child_ptr_stack[STACK_SIZE], nchild_ptr_stack[STACK_SIZE];
+    child_ptr_stack[0] = root.child;
+    nchild_ptr_stack[0] = root.nchild;
+    int curr = 0;
+    while (curr >= 0) {
+        uint32_t first_child = child_ptr_stack[curr], nchild = nchild_ptr_stack[curr];
+        curr--;
+        for (uint32_t i = first_child; i < first_child + nchild; i++) {
+            Node node = get_node(g, i);
+            if (c) c->nodes++;
+            if (intersect_node(noid, inv, &node, min_distance)) {
+                if (node.nchild == 0) {
+                    if ((int)node.child != last_hit_triangle) {
+                        if (c) c->tris++;
+                        const uint32_t *t = g->triangles + 3ull * node.child;
+                        if (intersect_triangle(origin, direction, vtx(g, t[0]), vtx(g, t[1]),
+                                               vtx(g, t[2]), &distance)) {
+                            if (triangle_index == -1 || distance < min_distance) {
+                                triangle_index = (int)node.child;
+                                min_distance = distance;
+                            }
+                        }
+                    }
+                } else {
+                    curr++;
+                    child_ptr_stack[curr] = node.child;
+                    nchild_ptr_stack[curr] = node.nchild;
+                    if (c && (uint32_t)(curr + 1) > c->max_stack) c->max_stack = curr + 1;
+                }
+            }
+            if (curr >= STACK_SIZE) break;
+        }
+    }
+    *min_distance_out = min_distance;
+    return triangle_index;
+}
+
+/* distance_to_mesh (mesh.h:131-155) extended with the triangle index.
+ * counters = {nodes, tris, calls, max_stack} or NULL. */
+ORC_EXPORT void orc_intersect(const CbGeometryDesc *g, const float *origins, const float *dirs,
+                              const int32_t *last_hit, uint64_t n, int32_t *tri_out,
+                              float *dist_out, uint64_t *counters)
+{
+    orc_counters c = {0, 0, 0, 0};
+    for (uint64_t i = 0; i < n; i++) {
+        f3 o = mk(origins[3 * i], origins[3 * i + 1], origins[3 * i + 2]);
+        f3 d = mk(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]);
+        d = divs(d, norm(d));
+        float dist;
+        int t = intersect_mesh(g, o, d, &dist, last_hit ? last_hit[i] : -1, &c);
+        tri_out[i] = t;
+        if (t != -1) dist_out[i] = dist;
+    }
+    if (counters) { counters[0] = c.nodes; counters[1] = c.tris; counters[2] = c.calls; counters[3] = c.max_stack; }
+}
+
+/* Reference test order of every triangle: the position at
+ * which intersect_mesh would test the triangle if no box were ever pruned.
+ * order(N) = leaf children ascending, then internal children in LIFO order. */
+ORC_EXPORT void orc_triangle_rank(const CbGeometryDesc *g, uint32_t *rank_out)
+{
+    uint64_t cap = 1024, top = 0;
+    uint32_t *stk = (uint32_t *)malloc(sizeof(uint32_t) * cap);
+    const uint32_t *root = g->nodes;
+    uint32_t r = 0;
+    for (uint64_t i = 0; i < g->ntriangles; i++) rank_out[i] = 0xFFFFFFFFu;
+    stk[top++] = root[3];
+    while (top) {
+        uint32_t w = stk[--top];
+        uint32_t first = w & 0x0FFFFFFFu, nchild = w >> 28;
+        for (uint32_t i = first; i < first + nchild; i++) {
+            uint32_t cw = g->nodes[4ull * i + 3];
+            if ((cw >> 28) == 0) {
+                uint32_t tri = cw & 0x0FFFFFFFu;
+                if (tri < g->ntriangles && rank_out[tri] == 0xFFFFFFFFu) rank_out[tri] = r++;
+            } else {
+                if (top == cap) { cap *= 2; stk = (uint32_t *)realloc(stk, sizeof(uint32_t) * cap); }
+                stk[top++] = cw;
+            }
+        }
+    }
+    free(stk);
+}
+
+/* ===================================================================== */
+/* photon.h                                                              */
+/* ===================================================================== */
+typedef struct {
+    f3 position, direction, polarization;
+    float wavelength, time, weight;
+    uint16_t history;
+    int last_hit_triangle;
+    uint32_t evidx;
+} Photon;
+
+typedef struct {
+    int inside_to_outside;
+    f3 surface_normal;
+    float refractive_index1, refractive_index2, absorption_length, scattering_length;
+    const CbMaterial *material1;
+    int surface_index;
+    float distance_to_boundary;
+} State;
+
+enum { BREAK, CONTINUE, PASS };
+#define WEIGHT_LOWER_THRESHOLD 0.0001f
+
+static inline float uniform(orc_rng *s, float low, float high)
+{
+    return low + xorwow_uniform(s) * (high - low); /* random.h:9-13 */
+}
+
+/* random.h:15-23 */
+static f3 uniform_sphere(orc_rng *s)
+{
+    float theta = uniform(s, 0.0f, 2 * PI_F);
+    float u = uniform(s, -1.0f, 1.0f);
+    float c = sqrtf(1.0f - u * u);
+    return mk(c * cosf(theta), c * sinf(theta), u);
+}
+
+/* interpolate.h:33-58 */
+static float interp(float x, int n, const float *xp, const float *fp)
+{
+    int lower = 0, upper = n - 1;
+    if (x <= xp[lower]) return fp[lower];
+    if (x >= xp[upper]) return fp[upper];
+    while (lower < upper - 1) {
+        int half = (lower + upper) / 2;
+        if (x < xp[half]) upper = half; else lower = half;
+    }
+    float df = fp[upper] - fp[lower], dx = xp[upper] - xp[lower];
+    return fp[lower] + df * (x - xp[lower]) / dx;
+}
+
+/* interpolate.h:5-29 */
+static float interp_idx(float x, int n, const float *xp)
+{
+    int lower = 0, upper = n - 1;
+    if (x <= xp[lower]) return (float)lower;
+    if (x >= xp[upper]) return (float)upper;
+    while (lower < upper - 1) {
+        int half = (lower + upper) / 2;
+        if (x < xp[half]) upper = half; else lower = half;
+    }
+    float dx = xp[upper] - xp[lower];
+    return (float)((double)lower + 1.0 * (double)(x - xp[lower]) / (double)dx);
+}
+
+/* random.h:27-31 */
+static float sample_cdf_xy(orc_rng *rng, int ncdf, const float *cdf_x, const float *cdf_y)
+{
+    return interp(xorwow_uniform(rng), ncdf, cdf_y, cdf_x);
+}
+
+/* random.h:33-55 */
+static float sample_cdf_uniform(orc_rng *rng, int ncdf, float x0, float delta, const float *cdf_y)
+{
+    float u = xorwow_uniform(rng);
+    int lower = 0, upper = ncdf - 1;
+    while (lower < upper - 1) {
+        int half = (lower + upper) / 2;
+        if (u < cdf_y[half]) upper = half; else lower = half;
+    }
+    float delta_cdf_y = cdf_y[upper] - cdf_y[lower];
+    return x0 + delta * lower + delta * (u - cdf_y[lower]) / delta_cdf_y;
+}
+
+/* geometry.h:61-74 */
+static float interp_property(const CbGeometryDesc *g, float x, const float *fp)
+{
+    float start = g->wavelength_start, step = g->wavelength_step;
+    int n = g->wavelength_n;
+    if (x < start) return fp[0];
+    if (x > (start + (n - 1) * step)) return fp[n - 1];
+    int jl = (int)((x - start) / step);
+    return fp[jl] + (x - (start + jl * step)) * (fp[jl + 1] - fp[jl]) / step;
+}
+
+static inline int convert8(int c) { return (c & 0x80) ? (int)(0xFFFFFF00u | (unsigned)c) : c; }
+static inline float get_theta(f3 a, f3 b) { return acosf(fmaxf(-1.0f, fminf(1.0f, dot(a, b)))); }
+static inline const float *tab(const CbGeometryDesc *g, int32_t off) { return g->table_pool + off; }
+
+/* photon.h:87-397 (mesh branch only) */
+static void fill_state(State *s, Photon *p, const CbGeometryDesc *g, orc_counters *c)
+{
+    int tri = intersect_mesh(g, p->position, p->direction, &s->distance_to_boundary,
+                             p->last_hit_triangle, c);
+    if (tri == -1) { p->last_hit_triangle = -1; p->history |= CB_NO_HIT; return; }
+    p->last_hit_triangle = tri;
+    const uint32_t *t = g->triangles + 3ull * (uint32_t)tri;
+    f3 v0 = vtx(g, t[0]), v1 = vtx(g, t[1]), v2 = vtx(g, t[2]);
+    uint32_t code = g->material_codes[tri];
+    int inner = convert8(0xFF & (code >> 24));
+    int outer = convert8(0xFF & (code >> 16));
+    s->surface_index = convert8(0xFF & (code >> 8));
+    s->surface_normal = normalize(cross(sub(v1, v0), sub(v2, v1)));
+    const CbMaterial *m1, *m2;
+    if (dot(s->surface_normal, neg(p->direction)) > 0.0f) {
+        m1 = &g->materials[outer]; m2 = &g->materials[inner]; s->inside_to_outside = 0;
+    } else {
+        m1 = &g->materials[inner]; m2 = &g->materials[outer];
+        s->surface_normal = neg(s->surface_normal); s->inside_to_outside = 1;
+    }
+    s->refractive_index1 = interp_property(g, p->wavelength, tab(g, m1->refractive_index));
+    s->refractive_index2 = interp_property(g, p->wavelength, tab(g, m2->refractive_index));
+    s->absorption_length = interp_property(g, p->wavelength, tab(g, m1->absorption_length));
+    s->scattering_length = interp_property(g, p->wavelength, tab(g, m1->scattering_length));
+    s->material1 = m1;
+}
+
+/* photon.h:399-424 */
+static f3 pick_new_direction(f3 axis, float theta, float phi)
+{
+    float cos_theta = cosf(theta), sin_theta = sinf(theta);
+    float cos_phi = cosf(phi), sin_phi = sinf(phi);
+    float sin_axis_theta = sqrtf(1.0f - axis.z * axis.z);
+    float cos_axis_phi, sin_axis_phi;
+    if (isnan(sin_axis_theta) || sin_axis_theta < 0.00001f) { cos_axis_phi = 1.0f; sin_axis_phi = 0.0f; }
+    else { cos_axis_phi = axis.x / sin_axis_theta; sin_axis_phi = axis.y / sin_axis_theta; }
+    float dirx = cos_theta * axis.x + sin_theta * (axis.z * cos_phi * cos_axis_phi - sin_phi * sin_axis_phi);
+    float diry = cos_theta * axis.y + sin_theta * (cos_phi * axis.z * sin_axis_phi + sin_phi * cos_axis_phi);
+    float dirz = cos_theta * axis.z - sin_theta * cos_phi * sin_axis_theta;
+    return mk(dirx, diry, dirz);
+}
+
+/* photon.h:426-453 */
+static void rayleigh_scatter(Photon *p, orc_rng *rng)
+{
+    float cos_theta = 2.0f * cosf((acosf(1.0f - 2.0f * xorwow_uniform(rng)) - 2 * PI_F) / 3.0f);
+    if (cos_theta > 1.0f) cos_theta = 1.0f; else if (cos_theta < -1.0f) cos_theta = -1.0f;
+    float theta = acosf(cos_theta);
+    float phi = uniform(rng, 0.0f, 2.0f * PI_F);
+    p->direction = pick_new_direction(p->polarization, theta, phi);
+    if (1.0f - fabsf(cos_theta) < 1e-6f)
+        p->polarization = pick_new_direction(p->polarization, PI_F / 2.0f, phi);
+    else
+        p->polarization = sub(p->polarization, scale(p->direction, cos_theta));
+    p->direction = divs(p->direction, norm(p->direction));
+    p->polarization = divs(p->polarization, norm(p->polarization));
+}
+
+/* photon.h:455-570 */
+static int propagate_to_boundary(Photon *p, State *s, orc_rng *rng, const CbGeometryDesc *g,
+                                 int use_weights, int scatter_first)
+{
+    float absorption_distance = -s->absorption_length * logf(xorwow_uniform(rng));
+    float scattering_distance = -s->scattering_length * logf(xorwow_uniform(rng));
+    if (use_weights && p->weight > WEIGHT_LOWER_THRESHOLD) absorption_distance = 1e30f;
+    else use_weights = 0;
+
+    if (scatter_first == 1) {
+        float scatter_prob = 1.0f - expf(-s->distance_to_boundary / s->scattering_length);
+        if (scatter_prob > WEIGHT_LOWER_THRESHOLD) {
+            int i = 0;
+            while (i < 1000 && scattering_distance > s->distance_to_boundary) {
+                scattering_distance = -s->scattering_length * logf(xorwow_uniform(rng));
+                i++;
+            }
+            p->weight *= scatter_prob;
+        }
+    } else if (scatter_first == -1) {
+        float no_scatter_prob = expf(-s->distance_to_boundary / s->scattering_length);
+        if (no_scatter_prob > WEIGHT_LOWER_THRESHOLD) {
+            int i = 0;
+            while (i < 1000 && scattering_distance <= s->distance_to_boundary) {
+                scattering_distance = -s->scattering_length * logf(xorwow_uniform(rng));
+                i++;
+            }
+            p->weight *= no_scatter_prob;
+        }
+    }
+
+    if (absorption_distance <= scattering_distance) {
+        if (absorption_distance <= s->distance_to_boundary) {
+            p->time += absorption_distance / (SPEED_OF_LIGHT / s->refractive_index1);
+            p->position = add(p->position, scale(p->direction, absorption_distance));
+            const CbMaterial *m = s->material1;
+            if (m->num_comp == 0) {
+                p->last_hit_triangle = -1; p->history |= CB_BULK_ABSORB; return BREAK;
+            }
+            float uniform_sample_comp = xorwow_uniform(rng);
+            float prob = 0.0f;
+            int comp;
+            for (comp = 0;; comp++) {
+                float comp_abs = interp_property(g, p->wavelength,
+                    tab(g, m->comp_absorption_length) + (size_t)comp * g->wavelength_n);
+                prob += s->absorption_length / comp_abs;
+                if (uniform_sample_comp < prob || comp + 1 == m->num_comp) break;
+            }
+            float uniform_sample_reemit = xorwow_uniform(rng);
+            float comp_reemit_prob = interp_property(g, p->wavelength,
+                tab(g, m->comp_reemission_prob) + (size_t)comp * g->wavelength_n);
+            if (uniform_sample_reemit < comp_reemit_prob) {
+                p->wavelength = sample_cdf_uniform(rng, g->wavelength_n, g->wavelength_start,
+                    g->wavelength_step, tab(g, m->comp_reemission_wvl_cdf) + (size_t)comp * g->wavelength_n);
+                p->time += sample_cdf_uniform(rng, g->time_n, g->time_start, g->time_step,
+                    tab(g, m->comp_reemission_time_cdf) + (size_t)comp * g->time_n);
+                p->direction = uniform_sphere(rng);
+                p->polarization = cross(uniform_sphere(rng), p->direction);
+                p->polarization = divs(p->polarization, norm(p->polarization));
+                p->last_hit_triangle = -1;
+                p->history |= CB_BULK_REEMIT;
+                return CONTINUE;
+            }
+            p->last_hit_triangle = -1; p->history |= CB_BULK_ABSORB; return BREAK;
+        }
+    } else {
+        if (scattering_distance <= s->distance_to_boundary) {
+            if (use_weights) p->weight *= expf(-scattering_distance / s->absorption_length);
+            p->time += scattering_distance / (SPEED_OF_LIGHT / s->refractive_index1);
+            p->position = add(p->position, scale(p->direction, scattering_distance));
+            rayleigh_scatter(p, rng);
+            p->history |= CB_RAYLEIGH_SCATTER;
+            p->last_hit_triangle = -1;
+            return CONTINUE;
+        }
+    }
+    if (use_weights) p->weight *= expf(-s->distance_to_boundary / s->absorption_length);
+    p->position = add(p->position, scale(p->direction, s->distance_to_boundary));
+    p->time += s->distance_to_boundary / (SPEED_OF_LIGHT / s->refractive_index1);
+    return PASS;
+}
+
+/* photon.h:572-632 */
+static void propagate_at_boundary(Photon *p, State *s, orc_rng *rng)
+{
+    float incident_angle = get_theta(s->surface_normal, neg(p->direction));
+    float refracted_angle = asinf(sinf(incident_angle) * s->refractive_index1 / s->refractive_index2);
+    f3 ipn = cross(p->direction, s->surface_normal);
+    float ipn_len = norm(ipn);
+    if (ipn_len < 1e-6f) ipn = p->polarization; else ipn = divs(ipn, ipn_len);
+    float normal_coefficient = dot(p->polarization, ipn);
+    float normal_probability = normal_coefficient * normal_coefficient;
+    float rc;
+    if (xorwow_uniform(rng) < normal_probability) {
+        rc = -sinf(incident_angle - refracted_angle) / sinf(incident_angle + refracted_angle);
+        float u = xorwow_uniform(rng);
+        if ((u < rc * rc) || isnan(refracted_angle)) {
+            p->direction = rotate(s->surface_normal, incident_angle, ipn);
+            p->history |= CB_REFLECT_SPECULAR;
+        } else {
+            p->direction = rotate(s->surface_normal, PI_F - refracted_angle, ipn);
+        }
+        p->polarization = ipn;
+    } else {
+        rc = tanf(incident_angle - refracted_angle) / tanf(incident_angle + refracted_angle);
+        float u = xorwow_uniform(rng);
+        if ((u < rc * rc) || isnan(refracted_angle)) {
+            p->direction = rotate(s->surface_normal, incident_angle, ipn);
+            p->history |= CB_REFLECT_SPECULAR;
+        } else {
+            p->direction = rotate(s->surface_normal, PI_F - refracted_angle, ipn);
+        }
+        p->polarization = cross(ipn, p->direction);
+        p->polarization = divs(p->polarization, norm(p->polarization));
+    }
+}
+
+/* photon.h:634-646 */
+static int propagate_at_specular_reflector(Photon *p, State *s)
+{
+    float incident_angle = get_theta(s->surface_normal, neg(p->direction));
+    f3 ipn = cross(p->direction, s->surface_normal);
+    ipn = divs(ipn, norm(ipn));
+    p->direction = rotate(s->surface_normal, incident_angle, ipn);
+    p->history |= CB_REFLECT_SPECULAR;
+    return CONTINUE;
+}
+
+/* photon.h:648-667 */
+static int propagate_at_diffuse_reflector(Photon *p, State *s, orc_rng *rng)
+{
+    float ndotv;
+    do {
+        p->direction = uniform_sphere(rng);
+        ndotv = dot(p->direction, s->surface_normal);
+        if (ndotv < 0.0f) { p->direction = neg(p->direction); ndotv = -ndotv; }
+    } while (!(xorwow_uniform(rng) < ndotv));
+    p->polarization = cross(uniform_sphere(rng), p->direction);
+    p->polarization = divs(p->polarization, norm(p->polarization));
+    p->history |= CB_REFLECT_DIFFUSE;
+    return CONTINUE;
+}
+
+/* cuComplex.h (CUDA toolkit) + cx.h */
+typedef struct { float x, y; } cxf;
+static inline cxf cx(float r, float i) { cxf c = {r, i}; return c; }
+static inline cxf cadd(cxf a, cxf b) { return cx(a.x + b.x, a.y + b.y); }
+static inline cxf csub(cxf a, cxf b) { return cx(a.x - b.x, a.y - b.y); }
+static inline cxf cmul(cxf a, cxf b) { return cx(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+static cxf cdiv(cxf x, cxf y)
+{
+    float s = fabsf(y.x) + fabsf(y.y);
+    float oos = 1.0f / s;
+    float ars = x.x * oos, ais = x.y * oos, brs = y.x * oos, bis = y.y * oos;
+    s = (brs * brs) + (bis * bis);
+    oos = 1.0f / s;
+    return cx(((ars * brs) + (ais * bis)) * oos, ((ais * brs) - (ars * bis)) * oos);
+}
+static float cabsf_(cxf x)
+{
+    float a = fabsf(x.x), b = fabsf(x.y), v, w, t;
+    if (a > b) { v = a; w = b; } else { v = b; w = a; }
+    t = w / v; t = 1.0f + t * t; t = v * sqrtf(t);
+    if ((v == 0.0f) || (v > 3.402823466e38f) || (w > 3.402823466e38f)) t = v + w;
+    return t;
+}
+static inline float cargf_(cxf x) { return atan2f(x.y, x.x); }
+static cxf csqrtf_(cxf x)
+{
+    float r = sqrtf(cabsf_(x)), t = cargf_(x) / 2.0f;
+    return cx(r * cosf(t), r * sinf(t));
+}
+
+/* photon.h:669-827 */
+static int propagate_complex(Photon *p, State *s, orc_rng *rng, const CbGeometryDesc *g,
+                             const CbSurface *surface, int use_weights)
+{
+    float detect = interp_property(g, p->wavelength, tab(g, surface->detect));
+    float reflect_diffuse = interp_property(g, p->wavelength, tab(g, surface->reflect_diffuse));
+    float n2_eta = interp_property(g, p->wavelength, tab(g, surface->eta));
+    float n2_k = interp_property(g, p->wavelength, tab(g, surface->k));
+
+    cxf n1 = cx(s->refractive_index1, 0.0f), n2 = cx(n2_eta, n2_k), n3 = cx(s->refractive_index2, 0.0f);
+    float cos_t1 = dot(p->direction, s->surface_normal);
+    if (cos_t1 < 0.0f) cos_t1 = -cos_t1;
+    float theta = acosf(cos_t1);
+    cxf cos1 = cx(cosf(theta), 0.0f), sin1 = cx(sinf(theta), 0.0f);
+    float e = 2.0f * PI_F * surface->thickness / p->wavelength;
+    cxf ratio13sin = cmul(cmul(cdiv(n1, n3), cdiv(n1, n3)), cmul(sin1, sin1));
+    cxf cos3 = csqrtf_(csub(cx(1.0f, 0.0f), ratio13sin));
+    cxf ratio12sin = cmul(cmul(cdiv(n1, n2), cdiv(n1, n2)), cmul(sin1, sin1));
+    cxf cos2 = csqrtf_(csub(cx(1.0f, 0.0f), ratio12sin));
+    float u = cmul(n2, cos2).x, v = cmul(n2, cos2).y;
+
+    cxf s_n1c1 = cmul(n1, cos1), s_n2c2 = cmul(n2, cos2), s_n3c3 = cmul(n3, cos3);
+    cxf s_r12 = cdiv(csub(s_n1c1, s_n2c2), cadd(s_n1c1, s_n2c2));
+    cxf s_r23 = cdiv(csub(s_n2c2, s_n3c3), cadd(s_n2c2, s_n3c3));
+    cxf s_t12 = cdiv(cmul(cx(2.0f, 0.0f), s_n1c1), cadd(s_n1c1, s_n2c2));
+    cxf s_t23 = cdiv(cmul(cx(2.0f, 0.0f), s_n2c2), cadd(s_n2c2, s_n3c3));
+    cxf s_g = cdiv(s_n3c3, s_n1c1);
+    float s_abs_r12 = cabsf_(s_r12), s_abs_r23 = cabsf_(s_r23);
+    float s_abs_t12 = cabsf_(s_t12), s_abs_t23 = cabsf_(s_t23);
+    float s_arg_r12 = cargf_(s_r12), s_arg_r23 = cargf_(s_r23);
+    float s_exp1 = expf(2.0f * v * e), s_exp2 = 1.0f / s_exp1;
+    float s_denom = s_exp1 + s_abs_r12 * s_abs_r12 * s_abs_r23 * s_abs_r23 * s_exp2 +
+                    2.0f * s_abs_r12 * s_abs_r23 * cosf(s_arg_r23 + s_arg_r12 + 2.0f * u * e);
+    float s_r = s_abs_r12 * s_abs_r12 * s_exp1 + s_abs_r23 * s_abs_r23 * s_exp2 +
+                2.0f * s_abs_r12 * s_abs_r23 * cosf(s_arg_r23 - s_arg_r12 + 2.0f * u * e);
+    s_r /= s_denom;
+    float s_t = s_g.x * s_abs_t12 * s_abs_t12 * s_abs_t23 * s_abs_t23;
+    s_t /= s_denom;
+
+    cxf p_n2c1 = cmul(n2, cos1), p_n3c2 = cmul(n3, cos2), p_n2c3 = cmul(n2, cos3), p_n1c2 = cmul(n1, cos2);
+    cxf p_r12 = cdiv(csub(p_n2c1, p_n1c2), cadd(p_n2c1, p_n1c2));
+    cxf p_r23 = cdiv(csub(p_n3c2, p_n2c3), cadd(p_n3c2, p_n2c3));
+    cxf p_t12 = cdiv(cmul(cmul(cx(2.0f, 0.0f), n1), cos1), cadd(p_n2c1, p_n1c2));
+    cxf p_t23 = cdiv(cmul(cmul(cx(2.0f, 0.0f), n2), cos2), cadd(p_n3c2, p_n2c3));
+    cxf p_g = cdiv(cmul(n3, cos3), cmul(n1, cos1));
+    float p_abs_r12 = cabsf_(p_r12), p_abs_r23 = cabsf_(p_r23);
+    float p_abs_t12 = cabsf_(p_t12), p_abs_t23 = cabsf_(p_t23);
+    float p_arg_r12 = cargf_(p_r12), p_arg_r23 = cargf_(p_r23);
+    float p_exp1 = expf(2.0f * v * e), p_exp2 = 1.0f / p_exp1;
+    float p_denom = p_exp1 + p_abs_r12 * p_abs_r12 * p_abs_r23 * p_abs_r23 * p_exp2 +
+                    2.0f * p_abs_r12 * p_abs_r23 * cosf(p_arg_r23 + p_arg_r12 + 2.0f * u * e);
+    float p_r = p_abs_r12 * p_abs_r12 * p_exp1 + p_abs_r23 * p_abs_r23 * p_exp2 +
+                2.0f * p_abs_r12 * p_abs_r23 * cosf(p_arg_r23 - p_arg_r12 + 2.0f * u * e);
+    p_r /= p_denom;
+    float p_t = p_g.x * p_abs_t12 * p_abs_t12 * p_abs_t23 * p_abs_t23;
+    p_t /= p_denom;
+
+    float incident_angle = get_theta(s->surface_normal, neg(p->direction));
+    float refracted_angle = asinf(sinf(incident_angle) * s->refractive_index1 / s->refractive_index2);
+    f3 ipn = cross(p->direction, s->surface_normal);
+    float ipn_len = norm(ipn);
+    if (ipn_len < 1e-6f) ipn = p->polarization; else ipn = divs(ipn, ipn_len);
+    float normal_coefficient = dot(p->polarization, ipn);
+    float normal_probability = normal_coefficient * normal_coefficient;
+
+    float transmit = normal_probability * s_t + (1.0f - normal_probability) * p_t;
+    if (!surface->transmissive) transmit = 0.0f;
+    float reflect = normal_probability * s_r + (1.0f - normal_probability) * p_r;
+    float absorb = 1.0f - transmit - reflect;
+
+    if (use_weights && p->weight > WEIGHT_LOWER_THRESHOLD && absorb < (1.0f - WEIGHT_LOWER_THRESHOLD)) {
+        float survive = 1.0f - absorb;
+        absorb = 0.0f;
+        p->weight *= survive;
+        detect /= survive; reflect /= survive; transmit /= survive;
+    }
+    if (use_weights && detect > 0.0f) {
+        p->history |= CB_SURFACE_DETECT; p->weight *= detect; return BREAK;
+    }
+    float uniform_sample = xorwow_uniform(rng);
+    if (uniform_sample < absorb) {
+        float uniform_sample_detect = xorwow_uniform(rng);
+        if (uniform_sample_detect < detect) p->history |= CB_SURFACE_DETECT;
+        else p->history |= CB_SURFACE_ABSORB;
+        return BREAK;
+    } else if (uniform_sample < absorb + reflect || !surface->transmissive) {
+        float uniform_sample_reflect = xorwow_uniform(rng);
+        if (uniform_sample_reflect < reflect_diffuse) return propagate_at_diffuse_reflector(p, s, rng);
+        return propagate_at_specular_reflector(p, s);
+    } else {
+        p->direction = rotate(s->surface_normal, PI_F - refracted_angle, ipn);
+        p->polarization = cross(ipn, p->direction);
+        p->polarization = divs(p->polarization, norm(p->polarization));
+        p->history |= CB_SURFACE_TRANSMIT;
+        return CONTINUE;
+    }
+}
+
+/* photon.h:829-874 */
+static int propagate_at_wls(Photon *p, State *s, orc_rng *rng, const CbGeometryDesc *g,
+                            const CbSurface *surface, int use_weights)
+{
+    float absorb = interp_property(g, p->wavelength, tab(g, surface->absorb));
+    float reflect_specular = interp_property(g, p->wavelength, tab(g, surface->reflect_specular));
+    float reflect_diffuse = interp_property(g, p->wavelength, tab(g, surface->reflect_diffuse));
+    float reemit = interp_property(g, p->wavelength, tab(g, surface->reemit));
+    float uniform_sample = xorwow_uniform(rng);
+    if (use_weights && p->weight > WEIGHT_LOWER_THRESHOLD && absorb < (1.0f - WEIGHT_LOWER_THRESHOLD)) {
+        float survive = 1.0f - absorb;
+        absorb = 0.0f;
+        p->weight *= survive;
+        reflect_diffuse /= survive; reflect_specular /= survive;
+    }
+    if (uniform_sample < absorb) {
+        float uniform_sample_reemit = xorwow_uniform(rng);
+        if (uniform_sample_reemit < reemit) {
+            p->history |= CB_SURFACE_REEMIT;
+            p->wavelength = sample_cdf_uniform(rng, g->wavelength_n, g->wavelength_start,
+                                               g->wavelength_step, tab(g, surface->reemission_cdf));
+            p->direction = uniform_sphere(rng);
+            p->polarization = cross(uniform_sphere(rng), p->direction);
+            p->polarization = divs(p->polarization, norm(p->polarization));
+            return CONTINUE;
+        }
+        p->history |= CB_SURFACE_ABSORB;
+        return BREAK;
+    } else if (uniform_sample < absorb + reflect_specular + reflect_diffuse) {
+        float uniform_sample_reflect = xorwow_uniform(rng) * (reflect_specular + reflect_diffuse);
+        if (uniform_sample_reflect < reflect_specular) return propagate_at_specular_reflector(p, s);
+        return propagate_at_diffuse_reflector(p, s, rng);
+    }
+    p->history |= CB_SURFACE_TRANSMIT;
+    return PASS;
+}
+
+/* photon.h:877-907 */
+static int propagate_at_dichroic(Photon *p, State *s, orc_rng *rng, const CbGeometryDesc *g,
+                                 const CbSurface *surface)
+{
+    float incident_angle = get_theta(s->surface_normal, neg(p->direction));
+    float idx = interp_idx(incident_angle, surface->dichroic_nangles, tab(g, surface->dichroic_angles));
+    unsigned iidx = (unsigned)(int)idx;
+    size_t W = (size_t)g->wavelength_n;
+    float r_lo = interp_property(g, p->wavelength, tab(g, surface->dichroic_reflect) + iidx * W);
+    float r_hi = interp_property(g, p->wavelength, tab(g, surface->dichroic_reflect) + (iidx + 1) * W);
+    float t_lo = interp_property(g, p->wavelength, tab(g, surface->dichroic_transmit) + iidx * W);
+    float t_hi = interp_property(g, p->wavelength, tab(g, surface->dichroic_transmit) + (iidx + 1) * W);
+    float reflect_prob = r_lo + (r_hi - r_lo) * (idx - iidx);
+    float transmit_prob = t_lo + (t_hi - t_lo) * (idx - iidx);
+    float uniform_sample = xorwow_uniform(rng);
+    if (uniform_sample < reflect_prob) return propagate_at_specular_reflector(p, s);
+    if (uniform_sample < transmit_prob + reflect_prob) { p->history |= CB_SURFACE_TRANSMIT; return PASS; }
+    p->history |= CB_SURFACE_ABSORB;
+    return BREAK;
+}
+
+/* photon.h:909-951 */
+static int propagate_at_angular(Photon *p, State *s, orc_rng *rng, const CbGeometryDesc *g,
+                                const CbSurface *surface, int use_weights)
+{
+    float incident_angle = get_theta(s->surface_normal, neg(p->direction));
+    float idx = interp_idx(incident_angle, surface->angular_nangles, tab(g, surface->angular_angles));
+    unsigned iidx = (unsigned)(int)idx;
+    float t = idx - iidx;
+    const float *tr = tab(g, surface->angular_transmit), *rs = tab(g, surface->angular_reflect_specular),
+                *rd = tab(g, surface->angular_reflect_diffuse);
+    float transmit_prob = tr[iidx] + t * (tr[iidx + 1] - tr[iidx]);
+    float reflect_spec_prob = rs[iidx] + t * (rs[iidx + 1] - rs[iidx]);
+    float reflect_diff_prob = rd[iidx] + t * (rd[iidx + 1] - rd[iidx]);
+    float absorb_prob = 1.0f - transmit_prob - reflect_spec_prob - reflect_diff_prob;
+    if (use_weights && p->weight > WEIGHT_LOWER_THRESHOLD && absorb_prob < (1.0f - WEIGHT_LOWER_THRESHOLD)) {
+        float survive = 1.0f - absorb_prob;
+        absorb_prob = 0.0f;
+        p->weight *= survive;
+        transmit_prob /= survive; reflect_spec_prob /= survive; reflect_diff_prob /= survive;
+    }
+    float uniform_sample = xorwow_uniform(rng);
+    if (uniform_sample < absorb_prob) { p->history |= CB_SURFACE_ABSORB; return BREAK; }
+    if (uniform_sample < absorb_prob + transmit_prob) { p->history |= CB_SURFACE_TRANSMIT; return PASS; }
+    if (uniform_sample < absorb_prob + transmit_prob + reflect_spec_prob)
+        return propagate_at_specular_reflector(p, s);
+    return propagate_at_diffuse_reflector(p, s, rng);
+}
+
+/* photon.h:953-1037 (CHROMA_FORCE_SCATTER_AT_PASS == 0, the reference's
+ * effective default: gpu/tools.py:29-38 adds no -D when the variable is unset) */
+static int propagate_at_surface(Photon *p, State *s, orc_rng *rng, const CbGeometryDesc *g,
+                                int use_weights)
+{
+    const CbSurface *surface = &g->surfaces[s->surface_index];
+    if (surface->model == CB_SURFACE_COMPLEX) return propagate_complex(p, s, rng, g, surface, use_weights);
+    if (surface->model == CB_SURFACE_WLS) return propagate_at_wls(p, s, rng, g, surface, use_weights);
+    if (surface->model == CB_SURFACE_DICHROIC) return propagate_at_dichroic(p, s, rng, g, surface);
+    if (surface->model == CB_SURFACE_ANGULAR) return propagate_at_angular(p, s, rng, g, surface, use_weights);
+
+    float detect = interp_property(g, p->wavelength, tab(g, surface->detect));
+    float absorb = interp_property(g, p->wavelength, tab(g, surface->absorb));
+    float reflect_diffuse = interp_property(g, p->wavelength, tab(g, surface->reflect_diffuse));
+    float reflect_specular = interp_property(g, p->wavelength, tab(g, surface->reflect_specular));
+    float uniform_sample = xorwow_uniform(rng);
+    if (use_weights && p->weight > WEIGHT_LOWER_THRESHOLD && absorb < (1.0f - WEIGHT_LOWER_THRESHOLD)) {
+        float survive = 1.0f - absorb;
+        absorb = 0.0f;
+        p->weight *= survive;
+        detect /= survive; reflect_diffuse /= survive; reflect_specular /= survive;
+    }
+    if (use_weights && detect > 0.0f) { p->history |= CB_SURFACE_DETECT; p->weight *= detect; return BREAK; }
+    if (uniform_sample < absorb) { p->history |= CB_SURFACE_ABSORB; return BREAK; }
+    if (uniform_sample < absorb + detect) { p->history |= CB_SURFACE_DETECT; return BREAK; }
+    if (uniform_sample < absorb + detect + reflect_diffuse) return propagate_at_diffuse_reflector(p, s, rng);
+    if (uniform_sample < absorb + detect + reflect_diffuse + reflect_specular)
+        return propagate_at_specular_reflector(p, s);
+    return PASS;
+}
+
+/* propagate kernel body, propagate.cu:254-366, one photon.  Returns steps taken. */
+static int propagate_one(Photon *p, orc_rng *rng, const CbGeometryDesc *g, int max_steps,
+                         int use_weights, int scatter_first, orc_counters *c)
+{
+    const uint16_t term = CB_NO_HIT | CB_BULK_ABSORB | CB_SURFACE_DETECT | CB_SURFACE_ABSORB | CB_NAN_ABORT;
+    if (p->history & term) return 0;
+    State s;
+    int steps = 0;
+    while (steps < max_steps) {
+        steps++;
+        int command;
+        if (isnan(p->direction.x * p->direction.y * p->direction.z * p->position.x * p->position.y * p->position.z)) {
+            p->history |= CB_NO_HIT | CB_NAN_ABORT;
+            break;
+        }
+        fill_state(&s, p, g, c);
+        if (p->last_hit_triangle == -1) break;
+        command = propagate_to_boundary(p, &s, rng, g, use_weights, scatter_first);
+        scatter_first = 0;
+        if (command == BREAK) break;
+        if (command == CONTINUE) continue;
+        if (s.surface_index != -1) {
+            command = propagate_at_surface(p, &s, rng, g, use_weights);
+            if (command == BREAK) break;
+            if (command == CONTINUE) continue;
+        }
+        propagate_at_boundary(p, &s, rng);
+    }
+    return steps;
+}
+
+/* Whole-bank propagate in replay mode: photon i uses rng
+ * state i (states6 has >= bank->n entries) and every photon runs to
+ * completion or max_steps, i.e. the reference kernel launched once with
+ * nsteps = max_steps.  All pointers are HOST pointers here.
+ * counters = {nodes, tris, intersect calls, max_stack, total steps} or NULL. */
+ORC_EXPORT void orc_propagate(const CbGeometryDesc *g, const CbPhotonBank *b, uint32_t *states6,
+                              int max_steps, int use_weights, int scatter_first, uint64_t *counters)
+{
+    orc_counters c = {0, 0, 0, 0};
+    uint64_t total_steps = 0;
+    for (uint64_t i = 0; i < b->n; i++) {
+        Photon p;
+        p.position = mk(b->pos[3 * i], b->pos[3 * i + 1], b->pos[3 * i + 2]);
+        p.direction = mk(b->dir[3 * i], b->dir[3 * i + 1], b->dir[3 * i + 2]);
+        p.direction = divs(p.direction, norm(p.direction));
+        p.polarization = mk(b->pol[3 * i], b->pol[3 * i + 1], b->pol[3 * i + 2]);
+        p.polarization = divs(p.polarization, norm(p.polarization));
+        p.wavelength = b->wavelengths[i];
+        p.time = b->t[i];
+        p.last_hit_triangle = b->last_hit_triangles[i];
+        p.history = (uint16_t)b->flags[i];
+        p.weight = b->weights[i];
+        p.evidx = b->evidx[i];
+        const uint16_t term = CB_NO_HIT | CB_BULK_ABSORB | CB_SURFACE_DETECT | CB_SURFACE_ABSORB | CB_NAN_ABORT;
+        if (p.history & term) continue; /* early return: nothing written back (propagate.cu:295) */
+        orc_rng rng; rng.d = states6[6 * i]; memcpy(rng.v, states6 + 6 * i + 1, 20);
+        total_steps += (uint64_t)propagate_one(&p, &rng, g, max_steps, use_weights, scatter_first, &c);
+        states6[6 * i] = rng.d; memcpy(states6 + 6 * i + 1, rng.v, 20);
+        b->pos[3 * i] = p.position.x; b->pos[3 * i + 1] = p.position.y; b->pos[3 * i + 2] = p.position.z;
+        b->dir[3 * i] = p.direction.x; b->dir[3 * i + 1] = p.direction.y; b->dir[3 * i + 2] = p.direction.z;
+        b->pol[3 * i] = p.polarization.x; b->pol[3 * i + 1] = p.polarization.y; b->pol[3 * i + 2] = p.polarization.z;
+        b->wavelengths[i] = p.wavelength;
+        b->t[i] = p.time;
+        b->flags[i] = p.history;
+        b->last_hit_triangles[i] = p.last_hit_triangle;
+        b->weights[i] = p.weight;
+        b->evidx[i] = p.evidx;
+    }
+    if (counters) {
+        counters[0] = c.nodes; counters[1] = c.tris; counters[2] = c.calls;
+        counters[3] = c.max_stack; counters[4] = total_steps;
+    }
+}
+
+/* run_daq, daq.cu:35-86 (ndaq == 1).  rng state index = photon - start_photon
+ * (single chunk).  time_int/q_int/hist are [nchannels] accumulators prepared by
+ * the caller as begin_acquire does (gpu/daq.py:55-59). */
+ORC_EXPORT void orc_run_daq(const CbPhotonBank *b, uint32_t *states6, uint32_t detection_state,
+                            uint64_t first_photon, uint64_t nphotons, const uint32_t *solid_map,
+                            const int32_t *solid_id_to_channel_index,
+                            const float *time_cdf_x, const float *time_cdf_y, int time_cdf_len,
+                            const float *charge_cdf_x, const float *charge_cdf_y, int charge_cdf_len,
+                            float charge_unit, float global_weight,
+                            uint32_t *earliest_time_int, uint32_t *channel_q_int,
+                            uint32_t *channel_histories)
+{
+    for (uint64_t id = 0; id < nphotons; id++) {
+        orc_rng rng; rng.d = states6[6 * id]; memcpy(rng.v, states6 + 6 * id + 1, 20);
+        uint64_t photon_id = id + first_photon;
+        int triangle_id = b->last_hit_triangles[photon_id];
+        if (triangle_id > -1) {
+            int solid_id = (int)solid_map[triangle_id];
+            uint32_t history = b->flags[photon_id];
+            int channel_index = solid_id_to_channel_index[solid_id];
+            if (channel_index >= 0 && (history & detection_state)) {
+                float weight = b->weights[photon_id] * global_weight;
+                if (xorwow_uniform(&rng) < weight) {
+                    float time = b->t[photon_id] + sample_cdf_xy(&rng, time_cdf_len, time_cdf_x, time_cdf_y);
+                    uint32_t time_int; memcpy(&time_int, &time, 4);
+                    float charge = sample_cdf_xy(&rng, charge_cdf_len, charge_cdf_x, charge_cdf_y);
+                    uint32_t charge_int = (uint32_t)roundf(charge / charge_unit);
+                    if (time_int < earliest_time_int[channel_index]) earliest_time_int[channel_index] = time_int;
+                    channel_q_int[channel_index] += charge_int;
+                    channel_histories[channel_index] |= history;
+                }
+            }
+        }
+        states6[6 * id] = rng.d; memcpy(states6 + 6 * id + 1, rng.v, 20);
+    }
+}
+
+/* ===================================================================== */
+/* BVH build kernels restated (bvh.cu); the host part (bvh/grid.py) is   */
+/* restated in numpy in oracle/bvh_oracle.py.                            */
+/* ===================================================================== */
+static inline uint64_t spread3_16(uint32_t input) /* bvh.cu:41-52 */
+{
+    uint64_t x = input;
+    x = (x | (x << 16)) & 0x00000000FF0000FFull;
+    x = (x | (x << 8)) & 0x000000F00F00F00Full;
+    x = (x | (x << 4)) & 0x00000C30C30C30C3ull;
+    x = (x | (x << 2)) & 0x0000249249249249ull;
+    return x;
+}
+static inline uint32_t quantize(float v, float o, float s) { return (uint32_t)((v - o) / s); } /* bvh.cu:65-69 */
+
+/* make_leaves, bvh.cu:148-203 */
+ORC_EXPORT void orc_make_leaves(const float *vertices, const uint32_t *triangles, uint64_t ntriangles,
+                                const float world_origin[3], float world_scale,
+                                uint32_t *leaf_nodes, uint64_t *morton_codes)
+{
+    for (uint64_t t = 0; t < ntriangles; t++) {
+        float lo[3], hi[3], ce[3];
+        for (int a = 0; a < 3; a++) {
+            float v0 = vertices[3ull * triangles[3 * t] + a];
+            float v1 = vertices[3ull * triangles[3 * t + 1] + a];
+            float v2 = vertices[3ull * triangles[3 * t + 2] + a];
+            lo[a] = fminf(fminf(v0, v1), v2);
+            hi[a] = fmaxf(fmaxf(v0, v1), v2);
+            ce[a] = ((v0 + v1) + v2) / 3.0f;
+        }
+        uint32_t ql[3], qu[3], qc[3];
+        for (int a = 0; a < 3; a++) {
+            ql[a] = quantize(lo[a], world_origin[a], world_scale);
+            if (ql[a] > 0) ql[a]--;
+            qu[a] = quantize(hi[a], world_origin[a], world_scale) + 1;
+            qc[a] = quantize(ce[a], world_origin[a], world_scale);
+        }
+        morton_codes[t] = spread3_16(qc[0]) | (spread3_16(qc[1]) << 1) | (spread3_16(qc[2]) << 2);
+        leaf_nodes[4 * t + 0] = ql[0] | (qu[0] << 16);
+        leaf_nodes[4 * t + 1] = ql[1] | (qu[1] << 16);
+        leaf_nodes[4 * t + 2] = ql[2] | (qu[2] << 16);
+        leaf_nodes[4 * t + 3] = (uint32_t)t;
+    }
+}
+
+/* make_parents_detailed, bvh.cu:269-308 */
+ORC_EXPORT void orc_make_parents(const uint32_t *child_nodes, const uint32_t *first_children,
+                                 const uint32_t *nchildren, uint64_t nparent, uint32_t *parent_nodes)
+{
+    for (uint64_t p = 0; p < nparent; p++) {
+        uint32_t first = first_children[p], n = nchildren[p];
+        uint32_t lo[3], hi[3];
+        for (int a = 0; a < 3; a++) { lo[a] = 0xFFFF; hi[a] = 0; }
+        for (uint32_t i = 0; i < n; i++)
+            for (int a = 0; a < 3; a++) {
+                uint32_t w = child_nodes[4ull * (first + i) + a];
+                if ((w & 0xFFFF) < lo[a]) lo[a] = w & 0xFFFF;
+                if ((w >> 16) > hi[a]) hi[a] = w >> 16;
+            }
+        for (int a = 0; a < 3; a++) parent_nodes[4 * p + a] = (hi[a] << 16) | lo[a];
+        parent_nodes[4 * p + 3] = (n << 28) | first;
+    }
+}
+
+/* collapse_child, bvh.cu:530-543, applied to [start, end) */
+ORC_EXPORT void orc_collapse_child(uint32_t *nodes, uint64_t start, uint64_t end)
+{
+    for (uint64_t i = start; i < end; i++) {
+        uint32_t w = nodes[4 * i + 3];
+        if ((w >> 28) == 1) {
+            uint32_t c = w & 0x0FFFFFFFu;
+            memcpy(nodes + 4 * i, nodes + 4ull * c, 16);
+        }
+    }
+}

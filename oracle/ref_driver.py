@@ -1,0 +1,405 @@
+"""Run the REFERENCE's own CUDA kernels (oracle/_ref/*.cubin, built from the
+reference sources by oracle/Makefile) on the GPU.  TEST INFRASTRUCTURE ONLY.
+
+PyCUDA is not installable here, so this is a direct CUDA-driver-API harness
+(ctypes on libcuda) that replays the reference host code launch for launch:
+  get_rng_states      chroma/gpu/tools.py:136-145  (init_rng, block 64)
+  GPUGeometry structs chroma/gpu/geometry.py:44-520 (make_gpu_struct layouts of
+                      geometry_types.h: Material 88 B, Surface 104 B, Geometry 96 B)
+  GPUPhotons.propagate chroma/gpu/photon.py:240-290 (queues, chunk_iterator,
+                      nsteps rule, 4-byte D2H per step)
+  GPUDaq              chroma/gpu/daq.py:55-101
+It shares the primary context with libchroma_b200 but no code or memory.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+REF_DIR = os.path.join(_HERE, '_ref')
+_cu = None
+_ctx_ready = False
+
+
+class RefError(RuntimeError):
+    pass
+
+
+def _ck(rc, what=''):
+    if rc != 0:
+        raise RefError('CUDA driver error %d in %s' % (rc, what))
+
+
+def available():
+    return all(os.path.exists(os.path.join(REF_DIR, f)) for f in ('propagate.cubin', 'daq.cubin', 'ref_wrap.cubin'))
+
+
+def cu():
+    global _cu, _ctx_ready
+    if _cu is None:
+        _cu = C.CDLL('libcuda.so.1')
+    if not _ctx_ready:
+        _ck(_cu.cuInit(0), 'cuInit')
+        dev = C.c_int()
+        _ck(_cu.cuDeviceGet(C.byref(dev), int(os.environ.get('CHROMA_REF_DEVICE', '0'))), 'cuDeviceGet')
+        ctx = C.c_void_p()
+        _ck(_cu.cuDevicePrimaryCtxRetain(C.byref(ctx), dev), 'cuDevicePrimaryCtxRetain')
+        _ck(_cu.cuCtxSetCurrent(ctx), 'cuCtxSetCurrent')
+        _ctx_ready = True
+    return _cu
+
+
+class DevMem(object):
+    def __init__(self, nbytes):
+        self.nbytes = max(int(nbytes), 16)
+        p = C.c_uint64()
+        _ck(cu().cuMemAlloc_v2(C.byref(p), C.c_size_t(self.nbytes)), 'cuMemAlloc')
+        self.ptr = p.value
+
+    def __del__(self):
+        try:
+            if self.ptr and _cu is not None:
+                _cu.cuMemFree_v2(C.c_uint64(self.ptr))
+        except Exception:
+            pass
+        self.ptr = 0
+
+
+def to_dev(arr):
+    arr = np.ascontiguousarray(arr)
+    m = DevMem(arr.nbytes)
+    if arr.nbytes:
+        _ck(cu().cuMemcpyHtoD_v2(C.c_uint64(m.ptr), arr.ctypes.data_as(C.c_void_p), C.c_size_t(arr.nbytes)), 'HtoD')
+    m.dtype, m.shape = arr.dtype, arr.shape
+    return m
+
+
+def from_dev(m, dtype=None, shape=None, offset=0, nbytes=None):
+    dtype = np.dtype(dtype or m.dtype)
+    if shape is None:
+        shape = m.shape
+    out = np.empty(shape, dtype=dtype)
+    n = out.nbytes if nbytes is None else nbytes
+    if n:
+        _ck(cu().cuMemcpyDtoH_v2(out.ctypes.data_as(C.c_void_p), C.c_uint64(m.ptr + offset), C.c_size_t(n)), 'DtoH')
+    return out
+
+
+def sync():
+    _ck(cu().cuCtxSynchronize(), 'sync')
+
+
+class Module(object):
+    def __init__(self, name):
+        path = os.path.join(REF_DIR, name)
+        with open(path, 'rb') as f:
+            self.image = f.read()
+        self.mod = C.c_void_p()
+        _ck(cu().cuModuleLoadData(C.byref(self.mod), self.image), 'cuModuleLoadData(%s)' % name)
+        self.funcs = {}
+
+    def func(self, name):
+        if name not in self.funcs:
+            f = C.c_void_p()
+            _ck(cu().cuModuleGetFunction(C.byref(f), self.mod, name.encode()), 'cuModuleGetFunction(%s)' % name)
+            self.funcs[name] = f
+        return self.funcs[name]
+
+    def launch(self, name, grid, block, *args):
+        """args: ctypes scalars, DevMem (passed as pointer) or raw ints (pointers)."""
+        vals = []
+        for a in args:
+            if isinstance(a, DevMem):
+                vals.append(C.c_uint64(a.ptr))
+            elif a is None:
+                vals.append(C.c_uint64(0))
+            elif isinstance(a, int):
+                vals.append(C.c_uint64(a))
+            else:
+                vals.append(a)
+        ptrs = (C.c_void_p * len(vals))(*[C.cast(C.byref(v), C.c_void_p) for v in vals])
+        _ck(cu().cuLaunchKernel(self.func(name), int(grid), 1, 1, int(block), 1, 1, 0, None, ptrs, None),
+            'cuLaunchKernel(%s)' % name)
+
+
+_modules = {}
+
+
+def module(name):
+    if name not in _modules:
+        _modules[name] = Module(name)
+    return _modules[name]
+
+
+class Timer(object):
+    def __init__(self):
+        self.e0, self.e1 = C.c_void_p(), C.c_void_p()
+        _ck(cu().cuEventCreate(C.byref(self.e0), 0), 'cuEventCreate')
+        _ck(cu().cuEventCreate(C.byref(self.e1), 0), 'cuEventCreate')
+
+    def start(self):
+        _ck(cu().cuEventRecord(self.e0, None), 'cuEventRecord')
+
+    def stop(self):
+        _ck(cu().cuEventRecord(self.e1, None), 'cuEventRecord')
+        _ck(cu().cuEventSynchronize(self.e1), 'cuEventSynchronize')
+        ms = C.c_float()
+        _ck(cu().cuEventElapsedTime(C.byref(ms), self.e0, self.e1), 'cuEventElapsedTime')
+        return ms.value
+
+
+def chunk_iterator(nelements, nthreads_per_block=64, max_blocks=1024):
+    first = 0
+    while first < nelements:
+        left = nelements - first
+        blocks = int(left // nthreads_per_block)
+        if left % nthreads_per_block != 0:
+            blocks += 1
+        blocks = min(max_blocks, blocks)
+        n = min(left, blocks * nthreads_per_block)
+        yield (first, n, blocks)
+        first += n
+
+
+SIZEOF_CURANDSTATE = 48
+
+
+class RefRNG(object):
+    """get_rng_states(size, seed): init_rng<<<size//64+1, 64>>>(size, s, seed, 0)."""
+
+    def __init__(self, size, seed=1):
+        self.size = int(size)
+        self.mem = DevMem(self.size * SIZEOF_CURANDSTATE)
+        module('propagate.cubin').launch('init_rng', self.size // 64 + 1, 64, C.c_int(self.size), self.mem,
+                                         C.c_ulonglong(seed), C.c_ulonglong(0))
+        sync()
+
+    def states6(self, first=0, count=None):
+        """{d, v0..v4} words of each curandStateXORWOW (d at offset 0, v at 4..24)."""
+        count = self.size - first if count is None else count
+        raw = from_dev(self.mem, np.uint32, (count, 12), offset=first * 48, nbytes=count * 48)
+        return np.ascontiguousarray(raw[:, :6])
+
+
+def _struct(parts):
+    """Pack (ctype value) members like make_gpu_struct: pointers 8-aligned, scalars packed."""
+    buf = bytearray()
+    for p in parts:
+        b = bytes(p) if not isinstance(p, (bytes, bytearray)) else p
+        if len(b) == 8 and len(buf) % 8:
+            raise RefError('cannot align 64-bit pointer')
+        buf += b
+    return buf
+
+
+def _ptr(v):
+    return np.uint64(v).tobytes()
+
+
+class RefGeometry(object):
+    """Device structs exactly as GPUGeometry builds them, from the same desc."""
+
+    def __init__(self, desc, keep):
+        self.keep = keep
+        self.vertices = to_dev(keep['vertices'])
+        self.triangles = to_dev(keep['triangles'])
+        self.codes = to_dev(keep['codes'])
+        self.colors = to_dev(keep['colors'])
+        self.solid_id = to_dev(keep['solid_id'])
+        self.nodes = to_dev(keep['nodes'])
+        self.extra_nodes = DevMem(16)
+        pool = np.concatenate([keep['pool'], np.zeros(8, np.float32)])
+        self.pool = to_dev(pool)
+        P = self.pool.ptr
+        W, T = desc.wavelength_n, desc.time_n
+        self._aux = []
+        mat_ptrs = []
+        for i in range(desc.nmaterials):
+            m = keep['mats'][i]
+            comp_ptr = [0, 0, 0, 0]
+            if m.num_comp:
+                for j, (off, stride) in enumerate(((m.comp_reemission_prob, W), (m.comp_reemission_wvl_cdf, W),
+                                                   (m.comp_reemission_time_cdf, T), (m.comp_absorption_length, W))):
+                    arr = np.array([P + 4 * (off + c * stride) for c in range(m.num_comp)], dtype=np.uint64)
+                    d = to_dev(arr)
+                    self._aux.append(d)
+                    comp_ptr[j] = d.ptr
+            s = _struct([_ptr(P + 4 * m.refractive_index), _ptr(P + 4 * m.absorption_length),
+                         _ptr(P + 4 * m.scattering_length), _ptr(comp_ptr[0]), _ptr(comp_ptr[1]), _ptr(comp_ptr[2]),
+                         _ptr(comp_ptr[3]), np.uint32(m.num_comp).tobytes(), np.uint32(W).tobytes(),
+                         np.float32(desc.wavelength_step).tobytes(), np.float32(desc.wavelength_start).tobytes(),
+                         np.uint32(T).tobytes(), np.float32(desc.time_step).tobytes(),
+                         np.float32(desc.time_start).tobytes()])
+            s += b'\0' * (88 - len(s))
+            d = to_dev(np.frombuffer(bytes(s), dtype=np.uint8))
+            self._aux.append(d)
+            mat_ptrs.append(d.ptr)
+        self.material_ptrs = to_dev(np.array(mat_ptrs, dtype=np.uint64))
+        surf_ptrs = []
+        for i in range(desc.nsurfaces):
+            sf = keep['surfs'][i]
+            if sf.model < 0:
+                surf_ptrs.append(0)
+                continue
+            dich = 0
+            if sf.dichroic_nangles > 0:
+                n = sf.dichroic_nangles
+                r = to_dev(np.array([P + 4 * (sf.dichroic_reflect + a * W) for a in range(n)], dtype=np.uint64))
+                t = to_dev(np.array([P + 4 * (sf.dichroic_transmit + a * W) for a in range(n)], dtype=np.uint64))
+                ds = _struct([_ptr(P + 4 * sf.dichroic_angles), _ptr(r.ptr), _ptr(t.ptr), np.uint32(n).tobytes()])
+                ds += b'\0' * (32 - len(ds))
+                dd = to_dev(np.frombuffer(bytes(ds), dtype=np.uint8))
+                self._aux += [r, t, dd]
+                dich = dd.ptr
+            ang = 0
+            if sf.angular_nangles > 0:
+                as_ = _struct([_ptr(P + 4 * sf.angular_angles), _ptr(P + 4 * sf.angular_transmit),
+                               _ptr(P + 4 * sf.angular_reflect_specular), _ptr(P + 4 * sf.angular_reflect_diffuse),
+                               np.uint32(sf.angular_nangles).tobytes()])
+                as_ += b'\0' * (40 - len(as_))
+                ad = to_dev(np.frombuffer(bytes(as_), dtype=np.uint8))
+                self._aux.append(ad)
+                ang = ad.ptr
+            s = _struct([_ptr(P + 4 * sf.detect), _ptr(P + 4 * sf.absorb), _ptr(P + 4 * sf.reemit),
+                         _ptr(P + 4 * sf.reflect_diffuse), _ptr(P + 4 * sf.reflect_specular), _ptr(P + 4 * sf.eta),
+                         _ptr(P + 4 * sf.k), _ptr(P + 4 * sf.reemission_cdf), _ptr(dich), _ptr(ang),
+                         np.uint32(sf.model).tobytes(), np.uint32(W).tobytes(), np.uint32(sf.transmissive).tobytes(),
+                         np.float32(desc.wavelength_step).tobytes(), np.float32(desc.wavelength_start).tobytes(),
+                         np.float32(sf.thickness).tobytes()])
+            s += b'\0' * (104 - len(s))
+            d = to_dev(np.frombuffer(bytes(s), dtype=np.uint8))
+            self._aux.append(d)
+            surf_ptrs.append(d.ptr)
+        self.surface_ptrs = to_dev(np.array(surf_ptrs if surf_ptrs else [0], dtype=np.uint64))
+        g = _struct([_ptr(self.vertices.ptr), _ptr(self.triangles.ptr), _ptr(self.codes.ptr), _ptr(self.colors.ptr),
+                     _ptr(self.nodes.ptr), _ptr(self.extra_nodes.ptr), _ptr(self.material_ptrs.ptr),
+                     _ptr(self.surface_ptrs.ptr), _ptr(0),
+                     np.array(list(desc.world_origin), dtype=np.float32).tobytes(),
+                     np.float32(desc.world_scale).tobytes(), np.int32(desc.nnodes).tobytes(), np.int32(0).tobytes()])
+        assert len(g) == 96, len(g)
+        self.gpudata = to_dev(np.frombuffer(bytes(g), dtype=np.uint8))
+
+    def attach_detector(self, detector):
+        self.s2c = to_dev(np.asarray(detector.solid_id_to_channel_index, dtype=np.int32))
+        self.tx = to_dev(np.asarray(detector.time_cdf[0], dtype=np.float32))
+        self.ty = to_dev(np.asarray(detector.time_cdf[1], dtype=np.float32))
+        self.qx = to_dev(np.asarray(detector.charge_cdf[0], dtype=np.float32))
+        self.qy = to_dev(np.asarray(detector.charge_cdf[1], dtype=np.float32))
+        self.nchannels = detector.num_channels()
+        s = _struct([_ptr(self.s2c.ptr), _ptr(self.tx.ptr), _ptr(self.ty.ptr), _ptr(self.qx.ptr), _ptr(self.qy.ptr),
+                     np.int32(self.nchannels).tobytes(), np.int32(len(detector.time_cdf[0])).tobytes(),
+                     np.int32(len(detector.charge_cdf[0])).tobytes(),
+                     np.float32(detector.charge_cdf[0][-1] / 2 ** 16).tobytes()])
+        assert len(s) == 56
+        self.detector_gpu = to_dev(np.frombuffer(bytes(s), dtype=np.uint8))
+
+
+class RefPhotons(object):
+    FIELDS = ('pos', 'dir', 'pol', 'wavelengths', 't', 'last_hit_triangles', 'flags', 'weights', 'evidx')
+
+    def __init__(self, photons):
+        self.n = len(photons.pos)
+        self.pos = to_dev(np.asarray(photons.pos, dtype=np.float32))
+        self.dir = to_dev(np.asarray(photons.dir, dtype=np.float32))
+        self.pol = to_dev(np.asarray(photons.pol, dtype=np.float32))
+        self.wavelengths = to_dev(np.asarray(photons.wavelengths, dtype=np.float32))
+        self.t = to_dev(np.asarray(photons.t, dtype=np.float32))
+        self.last_hit_triangles = to_dev(np.asarray(photons.last_hit_triangles, dtype=np.int32))
+        self.flags = to_dev(np.asarray(photons.flags, dtype=np.uint32))
+        self.weights = to_dev(np.asarray(photons.weights, dtype=np.float32))
+        self.evidx = to_dev(np.asarray(photons.evidx, dtype=np.uint32))
+
+    def get(self):
+        from chroma_lite_b200 import event
+        return event.Photons(*[from_dev(getattr(self, f)) for f in self.FIELDS])
+
+    def propagate(self, geom, rng, nthreads_per_block=256, max_blocks=1024, max_steps=10, use_weights=False,
+                  scatter_first=0, force_single_launch=False):
+        """Launch-for-launch replay of GPUPhotons.propagate (gpu/photon.py:240-290).
+        force_single_launch=True runs the kernel once with nsteps=max_steps (the
+        deterministic replay mode of SURVEY App. A-2; needs rng.size >= n).
+        Returns dict(launches, ms)."""
+        mod = module('propagate.cubin')
+        nphotons = self.n
+        iq = np.empty(nphotons + 1, dtype=np.uint32)
+        iq[0] = 0
+        iq[1:] = np.arange(nphotons, dtype=np.uint32)
+        oq = np.zeros(nphotons + 1, dtype=np.uint32)
+        oq[0] = 1
+        input_queue, output_queue = to_dev(iq), to_dev(oq)
+        one = np.ones(1, dtype=np.uint32)
+        step, launches = 0, 0
+        timer = Timer()
+        timer.start()
+        while step < max_steps:
+            if force_single_launch or nphotons < nthreads_per_block * 16 * 8 or use_weights:
+                nsteps = max_steps - step
+            else:
+                nsteps = 1
+            if force_single_launch:
+                chunks = [(0, nphotons, (nphotons + nthreads_per_block - 1) // nthreads_per_block)]
+            else:
+                chunks = chunk_iterator(nphotons, nthreads_per_block, max_blocks)
+            for first, n, blocks in chunks:
+                mod.launch('propagate', blocks, nthreads_per_block, C.c_int(first), C.c_int(n), input_queue.ptr + 4,
+                           output_queue, rng.mem, self.pos, self.dir, self.wavelengths, self.pol, self.t, self.flags,
+                           self.last_hit_triangles, self.weights, self.evidx, C.c_int(nsteps), C.c_int(int(use_weights)),
+                           C.c_int(scatter_first), geom.gpudata)
+                launches += 1
+            step += nsteps
+            scatter_first = 0
+            if step < max_steps:
+                input_queue, output_queue = output_queue, input_queue
+                _ck(cu().cuMemcpyHtoD_v2(C.c_uint64(output_queue.ptr), one.ctypes.data_as(C.c_void_p), C.c_size_t(4)), 'HtoD')
+                nphotons = int(from_dev(input_queue, np.uint32, (1,), nbytes=4)[0]) - 1
+                if nphotons == 0:
+                    break
+        sync()
+        return dict(launches=launches, ms=timer.stop())
+
+
+def intersect(geom, origins, directions, last_hit=None, block=64):
+    """ref_intersect: the reference's intersect_mesh on every ray (tri, dist)."""
+    o = to_dev(np.asarray(origins, dtype=np.float32))
+    d = to_dev(np.asarray(directions, dtype=np.float32))
+    n = len(origins)
+    lh = to_dev(np.asarray(last_hit, dtype=np.int32)) if last_hit is not None else None
+    tri = to_dev(np.full(n, -1, dtype=np.int32))
+    dist = to_dev(np.zeros(n, dtype=np.float32))
+    timer = Timer()
+    timer.start()
+    module('ref_wrap.cubin').launch('ref_intersect', n // block + 1, block, C.c_int(n), o, d, lh, geom.gpudata, tri, dist)
+    ms = timer.stop()
+    return from_dev(tri), from_dev(dist), ms
+
+
+def rng_words(n, seed, first_stream=0, offset=0, ndraw=4):
+    """(words uint32 (n,ndraw), state6 uint32 (n,6)) straight from curand_init/curand."""
+    out = to_dev(np.zeros((n, ndraw), dtype=np.uint32))
+    st = to_dev(np.zeros((n, 6), dtype=np.uint32))
+    module('ref_wrap.cubin').launch('ref_rng_words', n // 64 + 1, 64, C.c_int(n), C.c_ulonglong(seed),
+                                    C.c_ulonglong(first_stream), C.c_ulonglong(offset), C.c_int(ndraw), out, st)
+    sync()
+    return from_dev(out), from_dev(st)
+
+
+def run_daq(geom, photons, rng, nthreads_per_block=64, max_blocks=1024, start_photon=0, nphotons=None, weight=1.0):
+    """GPUDaq.begin_acquire/acquire/end_acquire (gpu/daq.py:55-101), ndaq=1.
+    Returns (t float32, q float32, flags uint32, time_int, q_int)."""
+    mod = module('daq.cubin')
+    nch = geom.nchannels
+    nphotons = photons.n - start_photon if nphotons is None else nphotons
+    tint = to_dev(np.zeros(nch, dtype=np.uint32))
+    qint = to_dev(np.zeros(nch, dtype=np.uint32))
+    hist = to_dev(np.zeros(nch, dtype=np.uint32))
+    tf = to_dev(np.zeros(nch, dtype=np.float32))
+    qf = to_dev(np.zeros(nch, dtype=np.float32))
+    mod.launch('reset_earliest_time_int', nch // 64 + 1, 64, C.c_float(1e9), C.c_int(nch), tint)
+    for first, n, blocks in chunk_iterator(nphotons, nthreads_per_block, max_blocks):
+        mod.launch('run_daq', blocks, nthreads_per_block, rng.mem, C.c_uint(0x4), C.c_int(start_photon + first), C.c_int(n),
+                   photons.t, photons.flags, photons.last_hit_triangles, photons.weights, geom.solid_id, geom.detector_gpu,
+                   tint, qint, hist, C.c_float(weight))
+    mod.launch('convert_sortable_int_to_float', nch // 64 + 1, 64, C.c_int(nch), tint, tf)
+    mod.launch('convert_charge_int_to_float', nch // 64 + 1, 64, geom.detector_gpu, qint, qf)
+    sync()
+    return from_dev(tf), from_dev(qf), from_dev(hist), from_dev(tint), from_dev(qint)

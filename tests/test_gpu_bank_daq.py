@@ -1,0 +1,193 @@
+"""Photon-bank utilities, DAQ, BVH build and the Simulation front end on the GPU."""
+import numpy as np
+import pytest
+
+from chroma_lite_b200 import gpu, event, sim
+from chroma_lite_b200 import gpuarray as ga
+from chroma_lite_b200.bvh import make_recursive_grid_bvh
+from oracle import orc, ref_driver, bvh_oracle
+import scenes
+
+pytestmark = pytest.mark.gpu
+
+
+def propagated_bank(geo, n=120000, seed=3, max_steps=100):
+    g = gpu.GPUDetector(geo)
+    ph = scenes.point_source(n, seed=seed, wl_range=(300, 600))
+    ph.evidx[:] = np.arange(n) % 3
+    rng = gpu.get_rng_states(n, seed=21)
+    gp = gpu.GPUPhotons(ph)
+    gp.propagate(g, rng, max_blocks=(n + 255) // 256, max_steps=max_steps)
+    return g, gp, rng
+
+
+def test_select_matches_numpy_and_keeps_order(gpu_ready):
+    geo = scenes.tiny_detector()
+    g, gp, _ = propagated_bank(geo)
+    host = gp.get()
+    for flag in (event.SURFACE_DETECT, event.BULK_ABSORB | event.RAYLEIGH_SCATTER, 1 << 14):
+        sel = gp.select(flag).get()
+        mask = (host.flags & flag) != 0
+        assert len(sel) == mask.sum()
+        assert np.array_equal(sel.pos, host.pos[mask]) and np.array_equal(sel.flags, host.flags[mask])
+        assert np.array_equal(sel.evidx, host.evidx[mask]) and np.array_equal(sel.t, host.t[mask])
+    sub = gp.select(event.SURFACE_DETECT, start_photon=1000, nphotons=5000).get()
+    m = (host.flags[1000:6000] & event.SURFACE_DETECT) != 0
+    assert np.array_equal(sub.wavelengths, host.wavelengths[1000:6000][m])
+
+
+def test_flat_hits_match_numpy(gpu_ready):
+    geo = scenes.tiny_detector()
+    g, gp, _ = propagated_bank(geo)
+    host = gp.get()
+    hits = gp.get_flat_hits(g)
+    tri = host.last_hit_triangles
+    det = (host.flags & event.SURFACE_DETECT) != 0
+    chan = np.full(len(host), -1)
+    ok = det & (tri > -1)
+    chan[ok] = geo.solid_id_to_channel_index[geo.solid_id[tri[ok]]]
+    mask = chan >= 0
+    assert len(hits) == mask.sum() and len(hits) > 100
+    assert np.array_equal(hits.channel.astype(np.int64), chan[mask])
+    assert np.array_equal(hits.pos, host.pos[mask]) and np.array_equal(hits.evidx, host.evidx[mask])
+    hm = gp.get_hits(g)
+    assert sum(len(v) for v in hm.values()) == len(hits)
+
+
+def test_duplicate_and_iterate_copies(gpu_ready):
+    ph = scenes.point_source(1000, seed=8)
+    gp = gpu.GPUPhotons(ph, ncopies=3)
+    host = gp.get()
+    assert len(host) == 3000
+    for c in range(3):
+        assert np.array_equal(host.pos[c * 1000:(c + 1) * 1000], ph.pos)
+        assert np.array_equal(host.wavelengths[c * 1000:(c + 1) * 1000], ph.wavelengths)
+    copies = list(gp.iterate_copies())
+    assert len(copies) == 3 and np.array_equal(copies[2].get().dir, ph.dir)
+
+
+def test_copy_queue(gpu_ready):
+    ph = scenes.point_source(5000, seed=9)
+    gp = gpu.GPUPhotons(ph)
+    q = np.random.default_rng(0).permutation(5000)[:777].astype(np.uint32)
+    out = gp.copy_queue(ga.to_gpu(q), len(q)).get()
+    assert np.array_equal(out.pos, ph.pos[q]) and np.array_equal(out.pol, ph.pol[q])
+
+
+def test_daq_vs_reference_kernel_and_oracle(gpu_ready):
+    geo = scenes.tiny_detector()
+    g, gp, _ = propagated_bank(geo, n=150000)
+    host = gp.get()
+    n = len(host)
+    # engine
+    rng = gpu.get_rng_states(n, seed=5)
+    daq = gpu.GPUDaq(g)
+    daq.begin_acquire()
+    daq.acquire(gp, rng, nthreads_per_block=64, max_blocks=(n + 63) // 64)
+    ch = daq.end_acquire().get()
+    # reference run_daq on the same photons and seed
+    desc, keep = scenes.desc_of(geo)
+    rg = ref_driver.RefGeometry(desc, keep)
+    rg.attach_detector(geo)
+    rrng = ref_driver.RefRNG(n, seed=5)
+    rt, rq, rh, rti, rqi = ref_driver.run_daq(rg, ref_driver.RefPhotons(host), rrng, nthreads_per_block=64,
+                                              max_blocks=(n + 63) // 64)
+    assert np.array_equal(ch.flags, rh)
+    assert np.array_equal(ch.q, rq)
+    assert np.array_equal(ch.t, rt)
+    assert ch.hit.sum() > 20 and np.array_equal(ch.hit, rt < 1e8)
+    # CPU oracle (integer accumulators exact, times to float tolerance)
+    tint, qint, hist, unit = orc.run_daq(orc.HostBank(host), orc.rng_init(5, 0, n), geo, geo.solid_id)
+    assert np.array_equal(hist, ch.flags)
+    assert np.array_equal(qint, daq.channel_q_int_gpu.get())
+    assert np.allclose(tint.view(np.float32), ch.t, rtol=1e-6)
+
+
+def test_daq_time_and_charge_response(gpu_ready):
+    # test/test_detector.py: time spread and charge mean/rms of single photoelectrons
+    from chroma_lite_b200.detector import Detector
+    from chroma_lite_b200.geometry import Solid, vacuum
+    from chroma_lite_b200.make import cube
+    from chroma_lite_b200.demo import optics
+    det = Detector(vacuum)
+    cath = scenes.Surface('cathode')
+    cath.set('detect', 1.0)
+    det.add_pmt(Solid(cube(100.0), vacuum, vacuum, surface=cath))
+    det.set_time_dist_gaussian(1.2, -6.0, 6.0)
+    det.set_charge_dist_gaussian(1.0, 0.1, 0.5, 1.5)
+    scenes.with_bvh(det)
+    g = gpu.GPUDetector(det)
+    daq = gpu.GPUDaq(g)
+    n = 2000
+    rng = gpu.get_rng_states(4096, seed=3)
+    ts, qs = [], []
+    for i in range(n):
+        ph = event.Photons(np.zeros((1, 3)), np.array([[1.0, 0, 0]]), np.array([[0, 1.0, 0]]), np.array([400.0]))
+        gp = gpu.GPUPhotons(ph)
+        gp.propagate(g, rng, max_steps=10)
+        daq.begin_acquire()
+        daq.acquire(gp, rng)
+        ch = daq.end_acquire().get()
+        assert ch.hit[0]
+        ts.append(ch.t[0])
+        qs.append(ch.q[0])
+    ts, qs = np.array(ts), np.array(qs)
+    assert abs(ts.std() - 1.2) < 0.1 and abs(ts.mean() - 50.0 / 299.792458) < 0.15
+    assert abs(qs.mean() - 1.0) < 0.02 and abs(qs.std() - 0.1) < 0.02
+
+
+def test_bvh_build_matches_oracle(gpu_ready):
+    for geo in (scenes.sphere_scene(16), scenes.tiny_detector()):
+        bvh = make_recursive_grid_bvh(geo.mesh)
+        o, s, nodes, offs = bvh_oracle.make_recursive_grid_bvh(geo.mesh.vertices, geo.mesh.triangles)
+        assert np.array_equal(bvh.world_coords.world_origin, o) and bvh.world_coords.world_scale == s
+        mine = bvh.nodes.view(np.uint32).reshape(-1, 4)
+        assert list(bvh.layer_offsets) == list(offs)
+        # the device quantisation uses approximate division: allow rare +-1 quantum differences
+        assert mine.shape == nodes.shape
+        assert (mine == nodes).all(axis=1).mean() > 0.999
+        assert np.array_equal(mine[:, 3], nodes[:, 3])
+
+
+def test_bvh_is_conservative(gpu_ready):
+    geo = scenes.tiny_detector()
+    bvh = make_recursive_grid_bvh(geo.mesh)
+    from chroma_lite_b200.bvh import unpack_nodes
+    u = unpack_nodes(bvh.nodes)
+    leaves = u[u['nchild'] == 0]
+    leaves = leaves[leaves['child'] < len(geo.mesh.triangles)]
+    tri = geo.mesh.assemble()[leaves['child'].astype(np.int64)]
+    wc = bvh.world_coords
+    for a, (lo, hi) in enumerate((('xlo', 'xhi'), ('ylo', 'yhi'), ('zlo', 'zhi'))):
+        lo_w = wc.world_origin[a] + leaves[lo].astype(np.float64) * wc.world_scale
+        hi_w = wc.world_origin[a] + leaves[hi].astype(np.float64) * wc.world_scale
+        assert (lo_w <= tri[:, :, a].min(axis=1) + 1e-3).all() and (hi_w >= tri[:, :, a].max(axis=1) - 1e-3).all()
+
+
+def test_simulation_front_end(gpu_ready):
+    geo = scenes.tiny_detector()
+    s = sim.Simulation(geo, seed=12, nthreads_per_block=256, max_blocks=512)
+    evs = [scenes.point_source(20000, seed=k, wl_range=(300, 600)) for k in range(3)]
+    out = list(s.simulate(evs, keep_photons_end=True, keep_hits=True, keep_flat_hits=True, run_daq=True,
+                          max_steps=100, photons_per_batch=45000))
+    assert len(out) == 3
+    for ev in out:
+        assert len(ev.photons_end) == 20000 and ev.photons_beg is None
+        assert ((ev.photons_end.flags & event.TERMINAL_MASK) != 0).mean() > 0.99
+        assert len(ev.flat_hits) > 10 and sum(len(v) for v in ev.hits.values()) == len(ev.flat_hits)
+        assert ev.channels.hit.sum() > 5 and (ev.channels.t[ev.channels.hit] < 1e8).all()
+        hit_channels = np.unique(ev.flat_hits.channel)
+        assert set(np.flatnonzero(ev.channels.hit)) <= set(hit_channels.astype(int))
+    single = list(s.simulate(scenes.point_source(1000, seed=5), keep_photons_end=True, max_steps=10))
+    assert len(single) == 1 and len(single[0].photons_end) == 1000
+
+
+def test_errors_are_loud(gpu_ready):
+    from chroma_lite_b200 import _lib
+    geo = scenes.water_box(10.0)
+    g = gpu.GPUGeometry(geo)
+    with pytest.raises(AssertionError):
+        gpu.GPUDaq(gpu.GPUDetector(scenes.with_bvh(__import__('chroma_lite_b200').detector.Detector(None))) if False else type('X', (), {'nchannels': 0})())
+    gp = gpu.GPUPhotons(scenes.point_source(10))
+    with pytest.raises(_lib.ChromaB200Error):
+        gp.propagate(g, type('R', (), {'handle': 987654})(), max_steps=1)
