@@ -1,0 +1,100 @@
+"""Statistical pins of the oracle's physics, modelled on the reference's own
+(stale) GPU tests: test_rayleigh.py, test_propagation.py, test_detector.py."""
+import numpy as np
+from scipy import stats
+
+from chroma_lite_b200 import event
+from oracle import orc
+import scenes
+
+
+def test_rayleigh_scattering_angle_distribution():
+    # test/test_rayleigh.py: photons along +x polarised along +z in water, one step;
+    # the scattered direction relative to the polarisation follows sin^3(theta)
+    geo = scenes.water_box(100.0)
+    desc, keep = scenes.desc_of(geo)
+    n = 200000
+    ph = event.Photons(np.zeros((n, 3)), np.tile([1.0, 0, 0], (n, 1)), np.tile([0, 0, 1.0], (n, 1)),
+                       np.full(n, 400.0))
+    # shorten the scattering length so that most photons scatter inside the box
+    w = keep['mats'][[m.name for m in geo.unique_materials].index('water')]
+    keep['pool'][w.scattering_length:w.scattering_length + desc.wavelength_n] = 10.0
+    bank, cnt = orc.propagate(desc, ph, orc.rng_init(1, 0, n), max_steps=1)
+    sc = (bank.flags & event.RAYLEIGH_SCATTER) != 0
+    assert sc.mean() > 0.9
+    cos_pol = bank.dir[sc][:, 2]                  # angle between new direction and old polarisation
+    # pdf(cos) = 3/4 (1 - cos^2): CDF = (3c - c^3 + 2)/4
+    cdf = lambda c: (3 * c - c ** 3 + 2) / 4
+    assert stats.kstest(cos_pol[:20000], cdf).pvalue > 0.01
+    # new polarisation is perpendicular to the new direction
+    assert np.abs(np.einsum('ij,ij->i', bank.dir[sc], bank.pol[sc])).max() < 1e-3
+
+
+def test_no_nan_no_abort_and_termination():
+    geo = scenes.sphere_scene(16)
+    desc, keep = scenes.desc_of(geo)
+    ph = scenes.point_source(5000, seed=1)
+    bank, cnt = orc.propagate(desc, ph, orc.rng_init(1, 0, 5000), max_steps=100)
+    assert not np.isnan(bank.pos).any() and (bank.flags & event.NAN_ABORT_KERNEL == 0).all()
+    assert ((bank.flags & event.TERMINAL_MASK) != 0).mean() > 0.995
+    assert cnt['steps'] >= 5000 and cnt['max_stack'] < 64
+    # every photon that ended on a surface reports that triangle; bulk ends report -1
+    bulk = (bank.flags & event.BULK_ABSORB) != 0
+    assert (bank.last_hit_triangles[bulk] == -1).all()
+    surf = (bank.flags & event.SURFACE_ABSORB) != 0
+    assert (bank.last_hit_triangles[surf] >= 0).all() and surf.mean() > 0.3
+    # time is consistent with distance travelled at c/n for unscattered straight paths
+    direct = bank.flags == event.SURFACE_ABSORB
+    r = np.linalg.norm(bank.pos[direct], axis=1)
+    assert (r > 4800.0).all() and (r < 5000.5).all()      # coarse 16-step polyhedron inscribed in R = 5 m
+    assert (bank.t[direct] > 4800.0 / 299.792458).all()
+
+
+def test_terminal_photons_are_skipped():
+    geo = scenes.water_box(50.0)
+    desc, keep = scenes.desc_of(geo)
+    ph = scenes.point_source(100, seed=2)
+    ph.flags[:] = event.SURFACE_ABSORB
+    st = orc.rng_init(3, 0, 100)
+    bank, cnt = orc.propagate(desc, ph, st, max_steps=10)
+    assert cnt['steps'] == 0 and np.array_equal(st, orc.rng_init(3, 0, 100))
+    assert np.array_equal(bank.pos, ph.pos)
+
+
+def test_all_surface_models_fire():
+    geo = scenes.scintillator_scene(12)
+    desc, keep = scenes.desc_of(geo)
+    ph = scenes.point_source(30000, seed=3, wl_range=(250, 450))
+    bank, cnt = orc.propagate(desc, ph, orc.rng_init(7, 0, len(ph)), max_steps=200)
+    for bit in (event.BULK_REEMIT, event.SURFACE_REEMIT, event.SURFACE_TRANSMIT, event.SURFACE_DETECT,
+                event.REFLECT_SPECULAR, event.REFLECT_DIFFUSE, event.RAYLEIGH_SCATTER, event.SURFACE_ABSORB,
+                event.BULK_ABSORB):
+        assert ((bank.flags & bit) != 0).sum() > 10, hex(bit)
+    re = (bank.flags & event.BULK_REEMIT) != 0
+    assert bank.wavelengths[re].min() >= 60 and bank.wavelengths[re].max() <= 995
+    assert not np.isnan(bank.pos).any()
+
+
+def test_daq_time_and_charge_response():
+    # test/test_detector.py: sigma_t = 1.2 ns, charge 1.0 +- 0.1
+    geo = scenes.scintillator_scene(8)
+    n = 20000
+    ph = scenes.point_source(n)
+    bank = orc.HostBank(ph)
+    pmt_tri = int(np.flatnonzero(geo.solid_id_to_channel_index[geo.solid_id] == 0)[0])
+    bank.flags[:] = event.SURFACE_DETECT
+    bank.last_hit_triangles[:] = pmt_tri
+    bank.t[:] = 10.0
+    ts, qs = [], []
+    st = orc.rng_init(4, 0, n)
+    for i in range(0, 400):
+        tint, qint, hist, unit = orc.run_daq(bank, st[i:i + 1], geo, geo.solid_id, start=i, n=1)
+        ts.append(tint.view(np.float32)[0])
+        qs.append(qint[0] * unit)
+        assert hist[0] == event.SURFACE_DETECT and hist[1] == 0
+    assert abs(np.std(ts) - 1.2) < 0.15 and abs(np.mean(ts) - 10.0) < 0.2
+    assert abs(np.mean(qs) - 1.0) < 0.03 and abs(np.std(qs) - 0.1) < 0.03
+    # all photons on one channel: earliest time is the minimum, charge adds up
+    tint, qint, hist, unit = orc.run_daq(bank, orc.rng_init(4, 0, n), geo, geo.solid_id)
+    assert tint.view(np.float32)[0] < 10.0 - 3.0 and abs(qint[0] * unit / n - 1.0) < 0.01
+    assert tint[1] == np.float32(1e9).view(np.uint32)

@@ -1,0 +1,70 @@
+"""Multi-GPU host logic on CPU: sharding and the per-channel reduction, run as a
+world_size-2 gloo job (no GPU needed)."""
+import os
+import subprocess
+import sys
+import numpy as np
+
+from chroma_lite_b200 import parallel
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_shard_range_partitions_exactly():
+    for n in (0, 1, 7, 100, 2500000):
+        for w in (1, 2, 3, 8):
+            r = [parallel.shard_range(n, k, w) for k in range(w)]
+            assert r[0][0] == 0 and r[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(r, r[1:]))
+            sizes = [b - a for a, b in r]
+            assert max(sizes) - min(sizes) <= 1
+    assert list(parallel.shard_events(5, 1, 2)) == [3, 4]
+
+
+def test_sum_buffer_roundtrip():
+    rng = np.random.default_rng(0)
+    q = rng.integers(0, 2 ** 31, 100).astype(np.uint32)
+    h = rng.integers(0, 2 ** 16, 100).astype(np.uint32)
+    q2, h2 = parallel.unpack_sum_buffer(parallel.pack_sum_buffer(q, h), 100)
+    assert np.array_equal(q, q2) and np.array_equal(h, h2)
+
+
+WORKER = r'''
+import os, sys, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+from chroma_lite_b200 import parallel
+dist.init_process_group('gloo', init_method='tcp://127.0.0.1:%%s' %% os.environ['PORT'],
+                        rank=int(os.environ['RANK']), world_size=int(os.environ['WORLD_SIZE']))
+rank, world = dist.get_rank(), dist.get_world_size()
+C = 257
+rng = np.random.default_rng(100 + rank)
+t = rng.integers(1, 2**31 - 1, C); q = rng.integers(0, 2**20, C); h = rng.integers(0, 2**16, C)
+rt, rq, rh = parallel.reduce_channels(torch.from_numpy(t), torch.from_numpy(q), torch.from_numpy(h))
+# expected from all ranks' seeds
+ts, qs, hs = [], [], []
+for r in range(world):
+    g = np.random.default_rng(100 + r)
+    ts.append(g.integers(1, 2**31 - 1, C)); qs.append(g.integers(0, 2**20, C)); hs.append(g.integers(0, 2**16, C))
+assert np.array_equal(rt.numpy(), np.min(ts, axis=0))
+assert np.array_equal(rq.numpy(), np.sum(qs, axis=0))
+assert np.array_equal(rh.numpy(), np.bitwise_or.reduce(hs, axis=0))
+s, e = parallel.shard_range(1000, rank, world)
+tot = torch.tensor([e - s]); dist.all_reduce(tot); assert tot.item() == 1000
+dist.destroy_process_group()
+print('rank', rank, 'ok')
+'''
+
+
+def test_reduce_channels_world_size_2_gloo(tmp_path):
+    script = tmp_path / 'worker.py'
+    script.write_text(WORKER % ROOT)
+    port = str(29500 + os.getpid() % 2000)
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE='2', PORT=port, MASTER_ADDR='127.0.0.1')
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=180)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
+        assert 'ok' in o
