@@ -1,0 +1,405 @@
+#!/usr/bin/env python
+"""bench.py -- photons propagated per second on the 29k-PMT water-Cherenkov
+detector (BASELINE.json metric; config 3 of BASELINE.md), 1..8 B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                  [--workload pmt29k|tiny|rays] [--photons P]
+
+A "step" = one event of P photons (default 2.5 M, isotropic point source at the
+origin, lambda ~ U(300,600) nm) propagated to termination (max_steps=100) in the
+detector, photons already resident in HBM (`value`), or the same event pushed
+through the public API Simulation.simulate from HOST arrays incl. upload, hit
+read-back and DAQ (`e2e`).  Photons shard across ranks (weak scaling: every rank
+propagates its own P-photon events; geometry replicated); per-channel DAQ
+accumulators are combined with one NCCL reduction.
+
+--impl reference runs the REFERENCE's own CUDA kernels (oracle/_ref/*.cubin,
+compiled from /root/reference by oracle/Makefile) through a launch-for-launch
+replay of chroma/gpu/photon.py:240-290 on the same inputs: the reference has no
+CPU propagator, so this is "the reference's implementation of the path"
+(BASELINE.md section 2).  Rank 0 only.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+
+MAX_STEPS = 100
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ------------------------------------------------------------------ clocks
+class ClockSampler(object):
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for r in self.rows if len(r) >= 7]
+        sm = [float(r[0]) for r in rows if r[0].replace('.', '').isdigit()]
+        mx = [float(r[1]) for r in rows if r[1].replace('.', '').isdigit()]
+        names = ('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap')
+        reasons = sorted({n for r in rows for n, v in zip(names, r[3:7]) if v.lower().startswith('active')})
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': reasons, 'samples': len(rows)}
+
+
+# ------------------------------------------------------------------ workload
+def cache_dir():
+    d = os.environ.get('CHROMA_B200_CACHE', '/tmp/chroma_b200_cache')
+    os.makedirs(d, exist_ok=True)
+    return d
+
+
+class FlatGeometry(object):
+    """A flattened detector restored from the cache (duck-types Geometry/Detector)."""
+    pass
+
+
+def build_detector(workload, timings):
+    """Build (or load) the flattened detector + reference-format BVH."""
+    from chroma_lite_b200 import demo
+    from chroma_lite_b200.bvh import BVH, WorldCoords, make_recursive_grid_bvh, uint4
+    from chroma_lite_b200.geometry import Mesh
+    path = os.path.join(cache_dir(), 'det_%s_v2.npz' % workload)
+    t0 = time.perf_counter()
+    if workload == 'pmt29k':
+        det = demo.detector_29k()
+    elif workload == 'tiny':
+        det = demo.tiny()
+    else:
+        raise SystemExit('unknown workload ' + workload)
+    timings['author_s'] = time.perf_counter() - t0
+    if os.path.exists(path):
+        z = np.load(path)
+        det.mesh = Mesh.__new__(Mesh)
+        det.mesh.vertices, det.mesh.triangles = z['vertices'], z['triangles']
+        det.colors, det.solid_id = z['colors'], z['solid_id']
+        det.material1_index, det.material2_index, det.surface_index = z['m1'], z['m2'], z['surf']
+        # material/surface object lists in the same order the cache was written with
+        det.flatten_objects_only = True
+        _restore_object_lists(det)
+        det.solid_id_to_channel_index = np.asarray(det.solid_id_to_channel_index, dtype=np.int32)
+        det.bvh = BVH(WorldCoords(z['world_origin'], z['world_scale']), z['nodes'].view(uint4)[:, 0], z['layers'])
+        timings['flatten_s'] = float(z['flatten_s'])
+        timings['bvh_s'] = float(z['bvh_s'])
+        timings['cached'] = True
+        return det
+    t0 = time.perf_counter()
+    det.flatten()                       # incl. global vertex de-duplication, as the reference does
+    timings['flatten_s'] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    det.bvh = make_recursive_grid_bvh(det.mesh)
+    timings['bvh_s'] = time.perf_counter() - t0
+    timings['cached'] = False
+    try:
+        np.savez(path, vertices=det.mesh.vertices, triangles=det.mesh.triangles, colors=det.colors,
+                 solid_id=det.solid_id, m1=det.material1_index, m2=det.material2_index, surf=det.surface_index,
+                 world_origin=det.bvh.world_coords.world_origin, world_scale=det.bvh.world_coords.world_scale,
+                 nodes=det.bvh.nodes.view(np.uint32).reshape(-1, 4), layers=np.asarray(det.bvh.layer_offsets),
+                 flatten_s=timings['flatten_s'], bvh_s=timings['bvh_s'])
+    except Exception as e:               # cache is best effort
+        log('cache write failed:', e)
+    return det
+
+
+def _restore_object_lists(det):
+    from chroma_lite_b200.geometry import _unique_objects
+    det.unique_materials = _unique_objects([m for s in det.solids for m in s.unique_materials])
+    det.unique_surfaces = _unique_objects([x for s in det.solids for x in s.unique_surfaces])
+
+
+def make_event(n, seed):
+    import scenes
+    return scenes.point_source(n, seed=seed, wl_range=(300.0, 600.0))
+
+
+def algorithmic_bytes(det, desc, sample_photons, timings):
+    """B_photon = 120 + S*(16*Nnode + 48*Ntri + 64) with Nnode/Ntri/S measured by the
+    oracle's reference-order traversal on a bounded sample; also times
+    the oracle = the cpu_baseline ("port", 1 core)."""
+    from oracle import orc
+    t0 = time.perf_counter()
+    st = orc.rng_init(42, 0, len(sample_photons))
+    t1 = time.perf_counter()
+    bank, cnt = orc.propagate(desc, sample_photons, st, max_steps=MAX_STEPS)
+    t2 = time.perf_counter()
+    n = len(sample_photons)
+    nnode = cnt['nodes'] / max(cnt['calls'], 1)
+    ntri = cnt['tris'] / max(cnt['calls'], 1)
+    steps = cnt['steps'] / n
+    b = 120.0 + steps * (16.0 * nnode + 48.0 * ntri + 64.0)
+    timings['oracle'] = {'photons': n, 'seconds': t2 - t1, 'rng_init_s': t1 - t0, 'nodes_per_call': nnode,
+                         'tris_per_call': ntri, 'steps_per_photon': steps, 'bytes_per_photon': b,
+                         'max_stack': cnt['max_stack']}
+    return b, n / (t2 - t1)
+
+
+def dist_setup(ngpus):
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    return rank, world, local
+
+
+def barrier(world):
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        dist.barrier()
+        torch.cuda.synchronize()
+
+
+def max_over_ranks(x, world):
+    if world == 1:
+        return x
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([x], dtype=torch.float64, device='cuda')
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_over_ranks(x, world):
+    if world == 1:
+        return x
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([x], dtype=torch.float64, device='cuda')
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+# ------------------------------------------------------------------ our arm
+def run_ours(args):
+    import ctypes as C
+    from chroma_lite_b200 import gpu, sim, _lib, parallel, event
+    from chroma_lite_b200.gpu.geometry import make_desc
+    rank, world, local = dist_setup(args.gpus)
+    _lib.init(local)
+    lib = _lib.lib()
+    timings = {}
+    det = build_detector(args.workload, timings)
+    t0 = time.perf_counter()
+    s = sim.Simulation(det, seed=42 + rank, cuda_device=local, nthreads_per_block=512,
+                       max_blocks=max(1024, -(-args.photons // 512)))
+    timings['upload_geometry_s'] = time.perf_counter() - t0
+    g, rng = s.gpu_geometry, s.rng_states
+    n = args.photons
+    ev = make_event(n, seed=1000 + rank)
+    gp = gpu.GPUPhotons(ev)
+    pristine = gpu.GPUPhotons(ev)
+    fields = ('pos', 'dir', 'pol', 'wavelengths', 't', 'last_hit_triangles', 'flags', 'weights', 'evidx')
+
+    def restore():
+        for f in fields:
+            getattr(gp, f).copy_from_device(getattr(pristine, f).ptr)
+
+    def one_step():
+        restore()
+        lib.cb_flush_l2()
+        gp.propagate(g, rng, nthreads_per_block=512, max_blocks=s.max_blocks, max_steps=MAX_STEPS)
+        return gp.last_stats
+
+    for _ in range(args.warmup):
+        one_step()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier(world)
+    _lib.check(lib.cb_synchronize())
+    kernel_ms, launches, steps_taken = 0.0, 0, 0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        st = one_step()
+        kernel_ms += st.kernel_ms
+        launches += st.launches
+        steps_taken += st.steps
+    _lib.check(lib.cb_synchronize())
+    barrier(world)
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    # device time of the propagate kernels (CUDA events on the launching stream), max over ranks
+    dev_s = max_over_ranks(kernel_ms / 1e3, world)
+    total_photons = sum_over_ranks(float(n * args.steps), world)
+    value = total_photons / dev_s
+
+    # ---- e2e through the public API: host arrays in, hits + channels out
+    h2d = sum(getattr(ev, f).nbytes for f in ('pos', 'dir', 'pol', 'wavelengths', 't', 'flags', 'evidx'))
+    d2h = 0
+    for _ in range(2):
+        list(s.simulate([ev], keep_hits=False, keep_flat_hits=True, run_daq=True, max_steps=MAX_STEPS,
+                        photons_per_batch=n))
+    barrier(world)
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        out = list(s.simulate([ev], keep_hits=False, keep_flat_hits=True, run_daq=True, max_steps=MAX_STEPS,
+                              photons_per_batch=n))
+        if world > 1:
+            parallel.reduce_daq(s.gpu_daq, dst=0)
+    _lib.check(lib.cb_synchronize())
+    barrier(world)
+    e2e_s = max_over_ranks(time.perf_counter() - t0, world)
+    fh = out[0].flat_hits
+    d2h = sum(getattr(fh, f).nbytes for f in fields) + fh.channel.nbytes + 3 * 4 * s.gpu_geometry.nchannels
+    e2e = total_photons / e2e_s
+
+    if rank != 0:
+        return
+    # ---- roofline + cpu baseline (rank 0, N=1 only does the CPU leg)
+    roofline, cpu_baseline = None, None
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    peak = float(peaks.get('hbm_gbs', 6650.0))
+    if world == 1:
+        desc, keep = make_desc(det)
+        b, cpu_rate = algorithmic_bytes(det, desc, make_event(args.cpu_sample, seed=999), timings)
+        per_launch_s = (kernel_ms / 1e3) / max(launches, 1)
+        achieved = b * n / per_launch_s / 1e9
+        roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                    'traffic': None, 'kernel': 'propagate_kernel', 'bytes_per_photon': b,
+                    'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback 6650 GB/s'}
+        cpu_baseline = {'value': cpu_rate, 'unit': 'photons/s', 'cores': 1, 'kind': 'port',
+                        'sample': '%d photons of the same event type through oracle/chroma_oracle.c '
+                                  '(orc_propagate, max_steps=%d), host cores on this box: %d'
+                                  % (args.cpu_sample, MAX_STEPS, os.cpu_count())}
+    line = {
+        'metric': 'photons propagated/sec (whole box) on 29k-PMT detector', 'value': value, 'unit': 'photons/s',
+        'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dev_s * 1e3 / args.steps,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': args.workload, 'photons_per_event': n, 'max_steps': MAX_STEPS,
+                   'triangles': int(len(det.mesh.triangles)), 'bvh_nodes': int(len(det.bvh.nodes)),
+                   'channels': int(det.num_channels()), 'rng_pool': int(len(rng)),
+                   'l2': 'flushed between steps (cb_flush_l2 writes 2x L2) and node+triangle arrays exceed L2',
+                   'parallelism': 'photon banks sharded x%d, geometry replicated' % world},
+        'e2e': {'value': e2e, 'unit': 'photons/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h)},
+        'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu_baseline,
+        'extra': {'steps_per_photon': steps_taken / float(n * args.steps), 'wall_s': wall, 'setup': timings,
+                  'host_cores': os.cpu_count()},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------ reference arm
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    from oracle import ref_driver
+    if not ref_driver.available():
+        print(json.dumps({'impl': 'reference', 'unavailable': 'oracle/_ref cubins missing (build() needs /root/reference)'}))
+        return
+    from chroma_lite_b200 import _lib
+    from chroma_lite_b200.gpu.geometry import make_desc
+    _lib.init(0)                         # only for the BVH builder / cache; no engine kernel is timed below
+    timings = {}
+    det = build_detector(args.workload, timings)
+    desc, keep = make_desc(det)
+    t0 = time.perf_counter()
+    rg = ref_driver.RefGeometry(desc, keep)
+    timings['upload_geometry_s'] = time.perf_counter() - t0
+    n = args.photons
+    ev = make_event(n, seed=1000)
+    rng = ref_driver.RefRNG(512 * 1024, seed=42)        # Simulation defaults (chroma/sim.py:23-24,50)
+    sampler = ClockSampler(0)
+
+    def one_step():
+        rp = ref_driver.RefPhotons(ev)
+        return rp, rp.propagate(rg, rng, nthreads_per_block=512, max_blocks=1024, max_steps=MAX_STEPS)
+
+    for _ in range(args.warmup):
+        one_step()
+    sampler.start()
+    ms, launches = 0.0, 0
+    t_e2e = 0.0
+    for _ in range(args.steps):
+        ref_driver.sync()
+        t0 = time.perf_counter()
+        rp, r = one_step()
+        out = rp.get()
+        ref_driver.sync()
+        t_e2e += time.perf_counter() - t0
+        ms += r['ms']
+        launches += r['launches']
+    clocks = sampler.stop()
+    value = n * args.steps / (ms / 1e3)
+    e2e = n * args.steps / t_e2e
+    line = {
+        'impl': 'reference', 'metric': 'photons propagated/sec (whole box) on 29k-PMT detector', 'value': value,
+        'unit': 'photons/s', 'n_gpus': 1, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': args.workload, 'photons_per_event': n, 'max_steps': MAX_STEPS,
+                   'triangles': int(len(det.mesh.triangles)), 'bvh_nodes': int(len(det.bvh.nodes)),
+                   'launch': '512 threads x 1024 blocks, rng pool 524288, host queue loop (chroma/gpu/photon.py:240-290)'},
+        'cpu_baseline': {'value': value, 'unit': 'photons/s', 'cores': 1, 'kind': 'reference',
+                         'sample': 'reference CUDA kernels (oracle/_ref/propagate.cubin, sm_100a, reference nvcc flags) '
+                                   'on one B200 driven by one host thread; the reference has no CPU propagator'},
+        'e2e': {'value': e2e, 'unit': 'photons/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': int(launches), 'clocks': clocks,
+        'extra': {'setup': timings, 'host_cores': os.cpu_count(),
+                  'terminal_fraction': float(((out.flags & 0x800F) != 0).mean())},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='pmt29k')
+    ap.add_argument('--photons', type=int, default=2500000)
+    ap.add_argument('--cpu-sample', type=int, default=40000)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -60,7 +60,7 @@ class CbPhotonBank(C.Structure):
 
 
 class CbPropagateStats(C.Structure):
-    _fields_ = [('photons', u64), ('steps', u64), ('nodes_visited', u64), ('tris_tested', u64),
+    _fields_ = [('photons', u64), ('steps', u64), ('nodes_visited', u64), ('tris_tested', u64), ('rays_resolved', u64),
                 ('launches', u32), ('kernel_ms', f32)]
 
 

@@ -117,30 +117,45 @@ struct Tables {
     }
 };
 
-struct TraverseCounters { uint32_t nodes, tris; };
+struct TraverseCounters { uint32_t nodes, tris, resolved; };
 
 // ------------------------------------------------------------------ triangle test
 // Moller-Trumbore with the reference's tolerances and mixed precision
 // (behaviour of chroma/cuda/intersect.h:26-101): reject
 // |a| < FLT_EPSILON, reciprocal in double, u/v bounds +-1e-6 compared in
 // double, accept 1e-6 < t < inf.
+// The arithmetic is pinned instruction by instruction to what nvcc emits for the
+// reference (SASS of intersect_triangle in oracle/_ref: cross = fma(a.y,b.z,-(a.z*b.y)),
+// dot = fma(a.z,b.z,fma(a.x,b.x,a.y*b.y)), and u+v contracted to fma(f,dot(s,h),v)),
+// because rays aimed at shared edges/vertices sit right on the +-1e-6 tolerances.
+__device__ __forceinline__ float3 cross_pinned(const float3& a, const float3& b)
+{
+    return f3(__fmaf_rn(a.y, b.z, -__fmul_rn(a.z, b.y)), __fmaf_rn(a.z, b.x, -__fmul_rn(a.x, b.z)),
+              __fmaf_rn(a.x, b.y, -__fmul_rn(a.y, b.x)));
+}
+__device__ __forceinline__ float dot_pinned(const float3& a, const float3& b)
+{
+    return __fmaf_rn(a.z, b.z, __fmaf_rn(a.x, b.x, __fmul_rn(a.y, b.y)));
+}
 __device__ __forceinline__ bool hit_triangle(const float3& origin, const float3& direction,
                                              const float3& v0, const float3& v1, const float3& v2,
                                              float& distance)
 {
-    float3 edge1 = v1 - v0;
-    float3 edge2 = v2 - v0;
-    float3 h = cross(direction, edge2);
-    float a = dot(edge1, h);
+    const float3 edge1 = f3(__fadd_rn(v1.x, -v0.x), __fadd_rn(v1.y, -v0.y), __fadd_rn(v1.z, -v0.z));
+    const float3 edge2 = f3(__fadd_rn(v2.x, -v0.x), __fadd_rn(v2.y, -v0.y), __fadd_rn(v2.z, -v0.z));
+    const float3 h = cross_pinned(direction, edge2);
+    const float a = dot_pinned(edge1, h);
     if (a > -FLT_EPSILON && a < FLT_EPSILON) return false;
-    float f = 1.0 / a;
-    float3 s = origin - v0;
-    float u = f * dot(s, h);
+    const float f = 1.0 / a;
+    const float3 s = f3(__fadd_rn(origin.x, -v0.x), __fadd_rn(origin.y, -v0.y), __fadd_rn(origin.z, -v0.z));
+    const float sh = dot_pinned(s, h);
+    const float u = __fmul_rn(f, sh);
     if (u < -1e-6 || u > 1.0 + 1e-6) return false;
-    float3 q = cross(s, edge1);
-    float v = f * dot(direction, q);
-    if (v < -1e-6 || u + v > 1.0 + 1e-6) return false;
-    float t = f * dot(edge2, q);
+    const float3 q = cross_pinned(s, edge1);
+    const float v = __fmul_rn(f, dot_pinned(direction, q));
+    const float upv = __fmaf_rn(f, sh, v);
+    if (v < -1e-6 || upv > 1.0 + 1e-6) return false;
+    const float t = __fmul_rn(f, dot_pinned(edge2, q));
     if (t > 1e-6 && t < __int_as_float(0x7f800000)) {
         distance = t;
         return true;
@@ -165,26 +180,26 @@ __device__ __forceinline__ bool hit_box(const DevGeometry& g, const RaySetup& r,
     const float INF = __int_as_float(0x7f800000);
     float tmin = 0.0f, tmax = INF;
     if (r.fx) {
-        float lo = g.world_origin.x + u16f_lo(px) * g.world_scale;
-        float hi = g.world_origin.x + u16f_hi(px) * g.world_scale;
-        float t0 = lo * r.inv.x + r.noid.x;
-        float t1 = hi * r.inv.x + r.noid.x;
+        float lo = __fmaf_rn(u16f_lo(px), g.world_scale, g.world_origin.x);
+        float hi = __fmaf_rn(u16f_hi(px), g.world_scale, g.world_origin.x);
+        float t0 = __fmaf_rn(lo, r.inv.x, r.noid.x);
+        float t1 = __fmaf_rn(hi, r.inv.x, r.noid.x);
         tmin = fmaxf(tmin, fminf(t0, t1));
         tmax = fminf(tmax, fmaxf(t0, t1));
     }
     if (r.fy) {
-        float lo = g.world_origin.y + u16f_lo(py) * g.world_scale;
-        float hi = g.world_origin.y + u16f_hi(py) * g.world_scale;
-        float t0 = lo * r.inv.y + r.noid.y;
-        float t1 = hi * r.inv.y + r.noid.y;
+        float lo = __fmaf_rn(u16f_lo(py), g.world_scale, g.world_origin.y);
+        float hi = __fmaf_rn(u16f_hi(py), g.world_scale, g.world_origin.y);
+        float t0 = __fmaf_rn(lo, r.inv.y, r.noid.y);
+        float t1 = __fmaf_rn(hi, r.inv.y, r.noid.y);
         tmin = fmaxf(tmin, fminf(t0, t1));
         tmax = fminf(tmax, fmaxf(t0, t1));
     }
     if (r.fz) {
-        float lo = g.world_origin.z + u16f_lo(pz) * g.world_scale;
-        float hi = g.world_origin.z + u16f_hi(pz) * g.world_scale;
-        float t0 = lo * r.inv.z + r.noid.z;
-        float t1 = hi * r.inv.z + r.noid.z;
+        float lo = __fmaf_rn(u16f_lo(pz), g.world_scale, g.world_origin.z);
+        float hi = __fmaf_rn(u16f_hi(pz), g.world_scale, g.world_origin.z);
+        float t0 = __fmaf_rn(lo, r.inv.z, r.noid.z);
+        float t1 = __fmaf_rn(hi, r.inv.z, r.noid.z);
         tmin = fmaxf(tmin, fminf(t0, t1));
         tmax = fminf(tmax, fmaxf(t0, t1));
     }
@@ -193,6 +208,64 @@ __device__ __forceinline__ bool hit_box(const DevGeometry& g, const RaySetup& r,
 }
 
 // ------------------------------------------------------------------ traversal
+constexpr int CB_SSTACK = 12;   // entries per lane in shared memory
+constexpr int CB_LSTACK = 52;   // overflow entries in local memory
+
+struct TravStack {
+    uint2* s;          // shared-memory part, lane-interleaved: entry e at s[e*stride]
+    int stride;
+    uint2* l;          // local-memory overflow
+    __device__ __forceinline__ uint2 get(int i) const { return (i < CB_SSTACK) ? s[i * stride] : l[i - CB_SSTACK]; }
+    __device__ __forceinline__ void put(int i, uint2 e) const { if (i < CB_SSTACK) s[i * stride] = e; else l[i - CB_SSTACK] = e; }
+};
+
+// Exact emulation of the reference's visit order (behaviour of mesh.h:45-126:
+// children ascending, leaves tested on the spot, internal children pushed and
+// popped LIFO, prune against the current minimum).  Only used for the rare rays
+// the ordered traversal flags as order-sensitive (see traverse()).
+template <bool COUNT>
+static __device__ __noinline__ int traverse_reference_order(const DevGeometry& g, const float3& origin,
+                                                            const float3& direction, const RaySetup& r, int last_hit,
+                                                            float& min_distance, TravStack st,
+                                                            uint32_t* overflow_flag, TraverseCounters* cnt)
+{
+    int triangle_index = -1;
+    min_distance = -1.0f;
+    int sp = 0;
+    st.put(sp++, make_uint2(g.root_w, 0u));
+    while (sp > 0) {
+        const uint32_t cur = st.get(--sp).x;
+        const uint32_t first = cur & 0x0FFFFFFFu, n = cur >> 28;
+        for (uint32_t i = first; i < first + n; i++) {
+            const uint4 nd = __ldg(&g.nodes[i]);
+            if (COUNT) cnt->nodes++;
+            float tmin;
+            if (hit_box(g, r, nd.x, nd.y, nd.z, tmin) && (min_distance < 0.0f || !(tmin > min_distance))) {
+                const uint32_t w = nd.w;
+                if ((w >> 28) == 0) {
+                    if ((int)w != last_hit) {
+                        if (COUNT) cnt->tris++;
+                        const float4* tp = g.tri48 + 3ull * w;
+                        float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+                        float t;
+                        if (hit_triangle(origin, direction, f3(a.x, a.y, a.z), f3(a.w, b.x, b.y), f3(b.z, b.w, c.x), t)) {
+                            if (triangle_index == -1 || t < min_distance) {
+                                triangle_index = (int)w;
+                                min_distance = t;
+                            }
+                        }
+                    }
+                } else if (sp < CB_SSTACK + CB_LSTACK) {
+                    st.put(sp++, make_uint2(w, 0u));
+                } else {
+                    atomicOr(overflow_flag, 1u);
+                }
+            }
+        }
+    }
+    return triangle_index;
+}
+
 // Nearest-hit search over the reference tree topology with
 //   * near-child-first ordering and cull-at-pop (the reference does neither),
 //   * batched 128-bit node fetches (4 siblings in flight),
@@ -200,10 +273,11 @@ __device__ __forceinline__ bool hit_box(const DevGeometry& g, const RaySetup& r,
 //     lane l lives at stack[e*blockDim + l]) with a local-memory overflow area,
 //   * (distance, reference-test-rank) lexicographic minimum, which reproduces the
 //     reference's first-tested-wins tie rule under ANY visit order (SURVEY A-1).
-// Returns the triangle index or -1; `best_t` is the hit distance.
-constexpr int CB_SSTACK = 12;   // entries per lane in shared memory
-constexpr int CB_LSTACK = 52;   // overflow entries in local memory
-
+// Exactness: whenever every triangle hit lies inside its own leaf box in float
+// arithmetic (t >= box tmin) the result provably equals the reference's.  Boxes
+// are pruned with a small guard band so that any hit violating this (rounding at
+// a box face, ~1e-5 of rays) is seen and flagged; flagged rays are redone in the
+// reference's own visit order.  Returns the triangle index or -1.
 template <bool COUNT>
 __device__ __forceinline__ int traverse(const DevGeometry& g, const float3& origin,
                                         const float3& direction, int last_hit, float& best_t,
@@ -223,7 +297,18 @@ __device__ __forceinline__ int traverse(const DevGeometry& g, const float3& orig
     float tn;
     if (!hit_box(g, r, g.root_x, g.root_y, g.root_z, tn)) { best_t = -1.0f; return -1; }
 
+    // rounding scale of the slab arithmetic: |o/d| of the finite axes
+    const float GUARD = 1e-5f;
+    float mag = 0.0f;
+    if (r.fx) mag = fmaxf(mag, fabsf(r.noid.x));
+    if (r.fy) mag = fmaxf(mag, fabsf(r.noid.y));
+    if (r.fz) mag = fmaxf(mag, fabsf(r.noid.z));
+    const float guard_abs = GUARD * mag;
+    float limit = INF;           // prune boxes with tmin > limit = best_t + guard
+    bool order_sensitive = false;
+
     uint2 lstack[CB_LSTACK];
+    TravStack st = {sstack, sstride, lstack};
     int sp = 0;
     uint32_t cur = g.root_w;     // node group being expanded: nchild<<28 | first
     float top_t = INF;           // tmin of the entry on top of the stack (valid when sp > 0)
@@ -243,7 +328,7 @@ __device__ __forceinline__ int traverse(const DevGeometry& g, const float3& orig
                 if (i + k < n) {
                     if (COUNT) cnt->nodes++;
                     float tmin;
-                    if (hit_box(g, r, nd[k].x, nd[k].y, nd[k].z, tmin) && !(tmin > best_t)) {
+                    if (hit_box(g, r, nd[k].x, nd[k].y, nd[k].z, tmin) && !(tmin > limit)) {
                         const uint32_t w = nd[k].w;
                         if ((w >> 28) == 0) {
                             if ((int)w != last_hit) {
@@ -253,9 +338,11 @@ __device__ __forceinline__ int traverse(const DevGeometry& g, const float3& orig
                                 float t;
                                 if (hit_triangle(origin, direction, f3(a.x, a.y, a.z), f3(a.w, b.x, b.y),
                                                  f3(b.z, b.w, c.x), t)) {
+                                    if (t < tmin) order_sensitive = true;
                                     uint32_t rank = __float_as_uint(c.y);
                                     if (t < best_t || (t == best_t && rank < best_rank)) {
                                         best_t = t; best_tri = (int)w; best_rank = rank;
+                                        limit = best_t + (GUARD * best_t + guard_abs);
                                     }
                                 }
                             }
@@ -263,17 +350,14 @@ __device__ __forceinline__ int traverse(const DevGeometry& g, const float3& orig
                             // push, keeping the nearest entry on top
                             uint2 e = make_uint2(w, __float_as_uint(tmin));
                             if (sp > 0 && tmin > top_t) {
-                                // new entry goes below the current top
-                                uint2 top = (sp - 1 < CB_SSTACK) ? sstack[(sp - 1) * sstride] : lstack[sp - 1 - CB_SSTACK];
-                                if (sp - 1 < CB_SSTACK) sstack[(sp - 1) * sstride] = e; else lstack[sp - 1 - CB_SSTACK] = e;
+                                uint2 top = st.get(sp - 1);      // new entry goes below the current top
+                                st.put(sp - 1, e);
                                 e = top;
                             } else {
                                 top_t = tmin;
                             }
-                            if (sp < CB_SSTACK) sstack[sp * sstride] = e;
-                            else if (sp < CB_SSTACK + CB_LSTACK) lstack[sp - CB_SSTACK] = e;
-                            else { atomicOr(overflow_flag, 1u); sp--; }
-                            sp++;
+                            if (sp < CB_SSTACK + CB_LSTACK) st.put(sp++, e);
+                            else atomicOr(overflow_flag, 1u);
                         }
                     }
                 }
@@ -283,14 +367,15 @@ __device__ __forceinline__ int traverse(const DevGeometry& g, const float3& orig
         bool found = false;
         while (sp > 0) {
             sp--;
-            uint2 e = (sp < CB_SSTACK) ? sstack[sp * sstride] : lstack[sp - CB_SSTACK];
-            if (sp > 0) {
-                uint2 nt = (sp - 1 < CB_SSTACK) ? sstack[(sp - 1) * sstride] : lstack[sp - 1 - CB_SSTACK];
-                top_t = __uint_as_float(nt.y);
-            }
-            if (!(__uint_as_float(e.y) > best_t)) { cur = e.x; found = true; break; }
+            uint2 e = st.get(sp);
+            if (sp > 0) top_t = __uint_as_float(st.get(sp - 1).y);
+            if (!(__uint_as_float(e.y) > limit)) { cur = e.x; found = true; break; }
         }
         if (!found) break;
+    }
+    if (order_sensitive) {
+        if (COUNT) cnt->resolved++;
+        return traverse_reference_order<COUNT>(g, origin, direction, r, last_hit, best_t, st, overflow_flag, cnt);
     }
     if (best_tri == -1) best_t = -1.0f;
     return best_tri;

@@ -56,7 +56,7 @@ intersect_kernel(DevGeometry g, const float* __restrict__ origins, const float* 
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint2* sstack = reinterpret_cast<uint2*>(smem_raw) + threadIdx.x;
-    TraverseCounters cnt = {0, 0};
+    TraverseCounters cnt = {0, 0, 0};
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         float3 o = ld3(origins, i);
@@ -71,6 +71,7 @@ intersect_kernel(DevGeometry g, const float* __restrict__ origins, const float* 
     if (COUNT) {
         atomicAdd(counters + 1, (unsigned long long)cnt.nodes);
         atomicAdd(counters + 2, (unsigned long long)cnt.tris);
+        atomicAdd(counters + 5, (unsigned long long)cnt.resolved);
     }
 }
 
@@ -109,7 +110,7 @@ propagate_kernel(DevGeometry g, PropParams P)
     Photon p;
     Rng rng;
     int steps = 0, sf = 0;
-    TraverseCounters cnt = {0, 0};
+    TraverseCounters cnt = {0, 0, 0};
     unsigned long long nsteps_total = 0;
 
     while (true) {
@@ -187,6 +188,7 @@ propagate_kernel(DevGeometry g, PropParams P)
     if (COUNT) {
         atomicAdd(P.counters + 1, (unsigned long long)cnt.nodes);
         atomicAdd(P.counters + 2, (unsigned long long)cnt.tris);
+        atomicAdd(P.counters + 5, (unsigned long long)cnt.resolved);
     }
 }
 
@@ -565,12 +567,12 @@ int cb_propagate(const CbPhotonBank* bank, cb_geom_t gh, cb_rng_t rh, int32_t nt
         launches++;
         CB_CUDA(cudaMemcpyAsync(c.h_counters, c.d_counters, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c.stream));
         CB_CUDA(cudaStreamSynchronize(c.stream));
-        for (int i = 1; i < 5; i++) tot[i] += c.h_counters[i];
+        for (int i = 1; i < 6; i++) tot[i] += c.h_counters[i];
     }
     CB_CUDA(cudaEventRecord(c.kev1, c.stream));
     CB_CUDA(cudaEventSynchronize(c.kev1));
     if (stats) {
-        stats->photons = bank->n; stats->steps = tot[4]; stats->nodes_visited = tot[1]; stats->tris_tested = tot[2];
+        stats->photons = bank->n; stats->steps = tot[4]; stats->nodes_visited = tot[1]; stats->tris_tested = tot[2]; stats->rays_resolved = tot[5];
         stats->launches = launches;
         cudaEventElapsedTime(&stats->kernel_ms, c.kev0, c.kev1);
     }

@@ -139,6 +139,7 @@ typedef struct {
     uint64_t steps;          /* total propagation steps taken */
     uint64_t nodes_visited;  /* BVH node boxes tested (0 unless stats build) */
     uint64_t tris_tested;    /* triangle tests        (0 unless stats build) */
+    uint64_t rays_resolved;  /* rays redone in reference visit order (0 unless stats build) */
     uint32_t launches;       /* kernels launched by this call */
     float    kernel_ms;      /* device time of those kernels (CUDA events) */
 } CbPropagateStats;

@@ -20,8 +20,10 @@ def count_unique_in_sorted(a):
     return int((np.ediff1d(a) > 0).sum()) + 1
 
 
-def make_recursive_grid_bvh(vertices, triangles, target_degree=3):
-    """Returns (world_origin f32[3], world_scale f32, nodes uint32 (N,4), layer_offsets)."""
+def make_recursive_grid_bvh(vertices, triangles, target_degree=3, leaves=None):
+    """Returns (world_origin f32[3], world_scale f32, nodes uint32 (N,4), layer_offsets).
+    `leaves` = callable(v, t, origin, scale) -> (leaf_nodes, morton) replaces the C
+    restatement of make_leaves (used to plug in the reference's own kernel)."""
     lib = orc.lib()
     v = np.ascontiguousarray(vertices, dtype=np.float32)
     t = np.ascontiguousarray(triangles, dtype=np.uint32)
@@ -29,9 +31,13 @@ def make_recursive_grid_bvh(vertices, triangles, target_degree=3):
     world_scale = np.float32(np.float64(np.max(v.max(axis=0) - world_origin)) / (2 ** 16 - 2))
     leaf = np.zeros((len(t), 4), dtype=np.uint32)
     codes = np.zeros(len(t), dtype=np.uint64)
-    lib.orc_make_leaves(v.ctypes.data_as(C.c_void_p), t.ctypes.data_as(C.c_void_p), C.c_uint64(len(t)),
-                        world_origin.ctypes.data_as(C.c_void_p), C.c_float(world_scale),
-                        leaf.ctypes.data_as(C.c_void_p), codes.ctypes.data_as(C.c_void_p))
+    if leaves is None:
+        lib.orc_make_leaves(v.ctypes.data_as(C.c_void_p), t.ctypes.data_as(C.c_void_p), C.c_uint64(len(t)),
+                            world_origin.ctypes.data_as(C.c_void_p), C.c_float(world_scale),
+                            leaf.ctypes.data_as(C.c_void_p), codes.ctypes.data_as(C.c_void_p))
+    else:
+        leaf, codes = leaves(v, t, world_origin, world_scale)
+        leaf, codes = np.ascontiguousarray(leaf, dtype=np.uint32), np.ascontiguousarray(codes, dtype=np.uint64)
     order = np.argsort(codes, kind='stable')
     leaf, codes = np.ascontiguousarray(leaf[order]), codes[order]
     layers = [leaf]

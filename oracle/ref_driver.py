@@ -403,3 +403,22 @@ def run_daq(geom, photons, rng, nthreads_per_block=64, max_blocks=1024, start_ph
     mod.launch('convert_charge_int_to_float', nch // 64 + 1, 64, geom.detector_gpu, qint, qf)
     sync()
     return from_dev(tf), from_dev(qf), from_dev(hist), from_dev(tint), from_dev(qint)
+
+
+def make_leaves(vertices, triangles, world_origin, world_scale):
+    """The reference's make_leaves kernel (chroma/cuda/bvh.cu:148-203, launched as
+    in chroma/gpu/bvh.py:66-78).  Returns (leaf_nodes uint32 (T,4), morton uint64 (T,))."""
+    v = to_dev(np.asarray(vertices, dtype=np.float32))
+    t = to_dev(np.asarray(triangles, dtype=np.uint32))
+    n = len(triangles)
+    nodes = to_dev(np.zeros((n, 4), dtype=np.uint32))
+    codes = to_dev(np.zeros(n, dtype=np.uint64))
+
+    class float3(C.Structure):
+        _fields_ = [('x', C.c_float), ('y', C.c_float), ('z', C.c_float)]
+    o = float3(*[float(x) for x in world_origin])
+    mod = module('bvh.cubin')
+    for first, cnt, blocks in chunk_iterator(n, 256, 30000):
+        mod.launch('make_leaves', blocks, 256, C.c_uint(first), C.c_uint(cnt), t, v, o, C.c_float(world_scale), nodes, codes)
+    sync()
+    return from_dev(nodes), from_dev(codes)

@@ -124,31 +124,39 @@ def test_daq_time_and_charge_response(gpu_ready):
     rng = gpu.get_rng_states(4096, seed=3)
     ts, qs = [], []
     for i in range(n):
-        ph = event.Photons(np.zeros((1, 3)), np.array([[1.0, 0, 0]]), np.array([[0, 1.0, 0]]), np.array([400.0]))
+        # t0 = 100 ns: the DAQ orders times by raw float bits, valid for t >= 0 only
+        ph = event.Photons(np.zeros((1, 3)), np.array([[1.0, 0, 0]]), np.array([[0, 1.0, 0]]), np.array([400.0]),
+                           t=np.array([100.0]))
         gp = gpu.GPUPhotons(ph)
         gp.propagate(g, rng, max_steps=10)
         daq.begin_acquire()
         daq.acquire(gp, rng)
         ch = daq.end_acquire().get()
-        assert ch.hit[0]
-        ts.append(ch.t[0])
-        qs.append(ch.q[0])
+        if ch.hit[0]:            # a photon can be absorbed in the bulk (P ~ 1e-4)
+            ts.append(ch.t[0])
+            qs.append(ch.q[0])
     ts, qs = np.array(ts), np.array(qs)
-    assert abs(ts.std() - 1.2) < 0.1 and abs(ts.mean() - 50.0 / 299.792458) < 0.15
+    assert len(ts) > 0.99 * n
+    assert abs(ts.std() - 1.2) < 0.1 and abs(ts.mean() - 100.0 - 50.0 / 299.792458) < 0.15
     assert abs(qs.mean() - 1.0) < 0.02 and abs(qs.std() - 0.1) < 0.02
 
 
-def test_bvh_build_matches_oracle(gpu_ready):
-    for geo in (scenes.sphere_scene(16), scenes.tiny_detector()):
+def test_bvh_build_matches_reference_kernels(gpu_ready):
+    # leaves + Morton codes from the reference's own make_leaves kernel, host grouping
+    # restated from bvh/grid.py: the engine's builder must give the identical tree
+    for geo in (scenes.sphere_scene(16), scenes.tiny_detector(), scenes.scintillator_scene(12)):
         bvh = make_recursive_grid_bvh(geo.mesh)
-        o, s, nodes, offs = bvh_oracle.make_recursive_grid_bvh(geo.mesh.vertices, geo.mesh.triangles)
+        o, s, nodes, offs = bvh_oracle.make_recursive_grid_bvh(geo.mesh.vertices, geo.mesh.triangles,
+                                                               leaves=ref_driver.make_leaves)
         assert np.array_equal(bvh.world_coords.world_origin, o) and bvh.world_coords.world_scale == s
         mine = bvh.nodes.view(np.uint32).reshape(-1, 4)
         assert list(bvh.layer_offsets) == list(offs)
-        # the device quantisation uses approximate division: allow rare +-1 quantum differences
-        assert mine.shape == nodes.shape
-        assert (mine == nodes).all(axis=1).mean() > 0.999
-        assert np.array_equal(mine[:, 3], nodes[:, 3])
+        assert np.array_equal(mine, nodes)
+        # CPU restatement (exact division instead of the device's approximate one): same
+        # topology unless a vertex sits exactly on a quantum boundary
+        o2, s2, nodes2, offs2 = bvh_oracle.make_recursive_grid_bvh(geo.mesh.vertices, geo.mesh.triangles)
+        if nodes2.shape == nodes.shape:
+            assert (np.abs(nodes2[:, :3].astype(np.int64) - nodes[:, :3].astype(np.int64)) % 65536 <= 1).mean() > 0.9
 
 
 def test_bvh_is_conservative(gpu_ready):
