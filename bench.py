@@ -247,12 +247,16 @@ def run_ours(args):
     barrier(world)
     _lib.check(lib.cb_synchronize())
     kernel_ms, launches, steps_taken = 0.0, 0, 0
+    nodes_v, tris_v, resolved = 0, 0, 0
     t0 = time.perf_counter()
     for _ in range(args.steps):
         st = one_step()
         kernel_ms += st.kernel_ms
         launches += st.launches
         steps_taken += st.steps
+        nodes_v += st.nodes_visited
+        tris_v += st.tris_tested
+        resolved += st.rays_resolved
     _lib.check(lib.cb_synchronize())
     barrier(world)
     wall = time.perf_counter() - t0
@@ -316,6 +320,10 @@ def run_ours(args):
         'e2e': {'value': e2e, 'unit': 'photons/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h)},
         'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu_baseline,
         'extra': {'steps_per_photon': steps_taken / float(n * args.steps), 'wall_s': wall, 'setup': timings,
+                  'engine_counters': {'entries_per_traversal': nodes_v / max(steps_taken, 1),
+                                      'tris_per_traversal': tris_v / max(steps_taken, 1),
+                                      'rays_redone_fraction': resolved / max(steps_taken, 1),
+                                      'enabled': bool(os.environ.get('CHROMA_B200_STATS'))},
                   'host_cores': os.cpu_count()},
     }
     print(json.dumps(line), flush=True)

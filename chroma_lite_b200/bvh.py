@@ -88,3 +88,18 @@ def make_recursive_grid_bvh(mesh, target_degree=3):
                                 C.byref(origin), C.byref(scale), nodes.ctypes.data, C.byref(nnodes),
                                 layers.ctypes.data, C.byref(nlayers)))
     return BVH(WorldCoords(np.array(list(origin), dtype=np.float32), scale.value), nodes, layers.astype(np.int64))
+
+
+def native_tree(nodes, ntriangles, solid_id=None):
+    """The engine's own traversal tree (uint4 entries, root at 0) for a
+    reference-format tree; host-only helper around cb_native_tree_build."""
+    lib = _lib.load()
+    nodes = np.ascontiguousarray(nodes)
+    sid = None if solid_id is None else np.ascontiguousarray(solid_id, dtype=np.uint32)
+    count = C.c_uint64()
+    _lib.check(lib.cb_native_tree_build(nodes.ctypes.data, len(nodes), int(ntriangles),
+                                        sid.ctypes.data if sid is not None else None, None, C.byref(count)))
+    out = np.empty(count.value, dtype=uint4)
+    _lib.check(lib.cb_native_tree_build(nodes.ctypes.data, len(nodes), int(ntriangles),
+                                        sid.ctypes.data if sid is not None else None, out.ctypes.data, C.byref(count)))
+    return out

@@ -1,0 +1,312 @@
+// bvh_native.cu -- the engine's own traversal tree.
+//
+// The reference tree (Morton grid, mean fan-out ~4, chroma/bvh/grid.py) is an
+// INPUT: it defines the leaf boxes and the tie-break rank.  For traversal the
+// engine builds its own hierarchy over the same leaves:
+//   * top-down binned SAH, collapsed on the fly to <= 8 children per node
+//     (always split the sub-range with the largest surface area next),
+//   * two-level when the mesh comes as many solids (29k PMTs): a SAH tree over
+//     solids, then one independent SAH subtree per solid, built in parallel on
+//     the host cores,
+//   * same 16-byte entry format as the reference (6 x uint16 box on the world
+//     grid + nchild<<28|child), children of a node contiguous and 64/128-byte
+//     aligned so a node's children arrive in one or two 128-bit-vector bursts,
+//   * leaf entries are the reference's leaf nodes verbatim, which is what makes
+//     the order-independence argument of traverse() exact,
+//   * breadth-first storage: the top of the tree is one contiguous prefix (L2
+//     persistence window).
+#include "host.h"
+#include <algorithm>
+#include <atomic>
+#include <thread>
+#include <string.h>
+
+namespace cb {
+
+struct Entry { uint32_t x, y, z, w; };   // reference node packing
+
+static inline void box_of(const Entry& e, int lo[3], int hi[3])
+{
+    lo[0] = e.x & 0xFFFF; hi[0] = e.x >> 16;
+    lo[1] = e.y & 0xFFFF; hi[1] = e.y >> 16;
+    lo[2] = e.z & 0xFFFF; hi[2] = e.z >> 16;
+}
+struct IBox {
+    int lo[3], hi[3];
+    void reset() { for (int a = 0; a < 3; a++) { lo[a] = 0x7fffffff; hi[a] = -1; } }
+    void grow(const int l[3], const int h[3]) { for (int a = 0; a < 3; a++) { lo[a] = std::min(lo[a], l[a]); hi[a] = std::max(hi[a], h[a]); } }
+    void grow(const IBox& b) { grow(b.lo, b.hi); }
+    double area() const
+    {
+        if (hi[0] < lo[0]) return 0.0;
+        double dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+        return dx * dy + dy * dz + dz * dx;
+    }
+};
+
+struct Range { uint64_t b, e; IBox box; };
+
+constexpr int NBINS = 16;
+constexpr int WIDE = 8;
+
+// Binned SAH split of prims[b,e) (partitioned in place).  Returns the split point.
+static uint64_t sah_split(Entry* prims, uint64_t b, uint64_t e, IBox& left, IBox& right)
+{
+    const uint64_t n = e - b;
+    int clo[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff}, chi[3] = {-1, -1, -1};
+    for (uint64_t i = b; i < e; i++) {
+        int lo[3], hi[3];
+        box_of(prims[i], lo, hi);
+        for (int a = 0; a < 3; a++) { int c = lo[a] + hi[a]; clo[a] = std::min(clo[a], c); chi[a] = std::max(chi[a], c); }
+    }
+    double best = 1e300;
+    int best_axis = -1, best_bin = -1;
+    for (int a = 0; a < 3; a++) {
+        if (chi[a] == clo[a]) continue;
+        const double scale = (double)NBINS / ((double)(chi[a] - clo[a]) + 1.0);
+        IBox bb[NBINS];
+        uint64_t cnt[NBINS];
+        for (int k = 0; k < NBINS; k++) { bb[k].reset(); cnt[k] = 0; }
+        for (uint64_t i = b; i < e; i++) {
+            int lo[3], hi[3];
+            box_of(prims[i], lo, hi);
+            int k = (int)((double)(lo[a] + hi[a] - clo[a]) * scale);
+            k = std::min(std::max(k, 0), NBINS - 1);
+            bb[k].grow(lo, hi);
+            cnt[k]++;
+        }
+        double ra[NBINS];
+        uint64_t rc[NBINS];
+        IBox acc; acc.reset();
+        uint64_t c = 0;
+        for (int k = NBINS - 1; k > 0; k--) { acc.grow(bb[k]); c += cnt[k]; ra[k] = acc.area(); rc[k] = c; }
+        acc.reset(); c = 0;
+        for (int k = 0; k < NBINS - 1; k++) {
+            acc.grow(bb[k]); c += cnt[k];
+            if (c == 0 || rc[k + 1] == 0) continue;
+            double cost = acc.area() * (double)c + ra[k + 1] * (double)rc[k + 1];
+            if (cost < best) { best = cost; best_axis = a; best_bin = k; }
+        }
+    }
+    uint64_t mid;
+    if (best_axis < 0) {
+        mid = b + n / 2;                              // all centroids coincide: split by index
+    } else {
+        const int a = best_axis;
+        const double scale = (double)NBINS / ((double)(chi[a] - clo[a]) + 1.0);
+        Entry* m = std::partition(prims + b, prims + e, [&](const Entry& p) {
+            int lo[3], hi[3];
+            box_of(p, lo, hi);
+            int k = (int)((double)(lo[a] + hi[a] - clo[a]) * scale);
+            k = std::min(std::max(k, 0), NBINS - 1);
+            return k <= best_bin;
+        });
+        mid = (uint64_t)(m - prims);
+        if (mid == b || mid == e) mid = b + n / 2;
+    }
+    left.reset(); right.reset();
+    for (uint64_t i = b; i < mid; i++) { int lo[3], hi[3]; box_of(prims[i], lo, hi); left.grow(lo, hi); }
+    for (uint64_t i = mid; i < e; i++) { int lo[3], hi[3]; box_of(prims[i], lo, hi); right.grow(lo, hi); }
+    return mid;
+}
+
+struct Arena { uint64_t cur = 0, end = 0; };   // per-thread bump allocator over the node pool
+constexpr uint64_t ARENA_CHUNK = 1 << 16;
+
+struct Builder {
+    Entry* prims;                     // leaf entries (reordered in place)
+    std::vector<Entry>* out;          // wide nodes (pre-sized)
+    std::atomic<uint64_t> next{8};    // entry 0 is the root
+    std::atomic<int> overflow{0};
+
+    uint64_t alloc(Arena& A, int k)
+    {
+        // 8-entry (128 B line) alignment for wide blocks, 2-entry (32 B sector) for small ones
+        const uint64_t align = (k > 4) ? 8 : 2;
+        uint64_t start = (A.cur + align - 1) / align * align;
+        if (start + k > A.end) {
+            A.cur = next.fetch_add(ARENA_CHUNK);
+            A.end = A.cur + ARENA_CHUNK;
+            start = A.cur;                         // chunk starts are multiples of 8
+        }
+        if (start + k > out->size()) { overflow = 1; return 0; }
+        A.cur = start + k;
+        return start;
+    }
+
+    static Entry pack(const IBox& b, uint32_t w)
+    {
+        Entry e;
+        e.x = (uint32_t)b.lo[0] | ((uint32_t)b.hi[0] << 16);
+        e.y = (uint32_t)b.lo[1] | ((uint32_t)b.hi[1] << 16);
+        e.z = (uint32_t)b.lo[2] | ((uint32_t)b.hi[2] << 16);
+        e.w = w;
+        return e;
+    }
+
+    // split [b,e) into <= WIDE sub-ranges, always refining the largest-area one
+    int widen(uint64_t b, uint64_t e, const IBox& box, Range* r)
+    {
+        int k = 1;
+        r[0].b = b; r[0].e = e; r[0].box = box;
+        while (k < WIDE) {
+            int pick = -1;
+            double pa = -1.0;
+            for (int i = 0; i < k; i++)
+                if (r[i].e - r[i].b > 1) {
+                    double a = r[i].box.area() + 1e-9 * (double)(r[i].e - r[i].b);
+                    if (a > pa) { pa = a; pick = i; }
+                }
+            if (pick < 0) break;
+            IBox L, R;
+            uint64_t mid = sah_split(prims, r[pick].b, r[pick].e, L, R);
+            Range right; right.b = mid; right.e = r[pick].e; right.box = R;
+            r[pick].e = mid; r[pick].box = L;
+            for (int i = k; i > pick + 1; i--) r[i] = r[i - 1];     // keep spatial order
+            r[pick + 1] = right;
+            k++;
+        }
+        return k;
+    }
+
+    void build(Arena& A, uint64_t b, uint64_t e, const IBox& box, uint64_t slot)
+    {
+        if (e - b == 1) { (*out)[slot] = prims[b]; return; }
+        Range r[WIDE + 1];
+        int k = widen(b, e, box, r);
+        uint64_t blk = alloc(A, k);
+        if (overflow) return;
+        (*out)[slot] = pack(box, ((uint32_t)k << 28) | (uint32_t)blk);
+        for (int i = 0; i < k; i++) build(A, r[i].b, r[i].e, r[i].box, blk + i);
+    }
+};
+
+// Build the native tree.  leaves: one reference leaf entry per triangle that the
+// reference tree can reach; solid_of[tri] (may be null) groups triangles.
+// Returns entries in `nodes` (root at 0).
+int build_native_tree(std::vector<Entry>& leaves, const uint32_t* solid_of, std::vector<Entry>& nodes)
+{
+    const uint64_t n = leaves.size();
+    nodes.clear();
+    if (n == 0) { nodes.push_back(Entry{0, 0, 0, 0}); return CB_OK; }
+    // group by solid (stable counting sort keeps triangle order inside a solid)
+    std::vector<uint64_t> solid_begin;
+    if (solid_of) {
+        uint32_t nsolids = 0;
+        for (uint64_t i = 0; i < n; i++) nsolids = std::max(nsolids, solid_of[leaves[i].w & 0x0FFFFFFFu] + 1);
+        std::vector<uint64_t> count(nsolids + 1, 0);
+        for (uint64_t i = 0; i < n; i++) count[solid_of[leaves[i].w & 0x0FFFFFFFu] + 1]++;
+        for (uint32_t s = 0; s < nsolids; s++) count[s + 1] += count[s];
+        std::vector<Entry> sorted(n);
+        std::vector<uint64_t> cursor(count.begin(), count.end() - 1);
+        for (uint64_t i = 0; i < n; i++) sorted[cursor[solid_of[leaves[i].w & 0x0FFFFFFFu]]++] = leaves[i];
+        leaves.swap(sorted);
+        for (uint32_t s = 0; s < nsolids; s++)
+            if (count[s + 1] > count[s]) solid_begin.push_back(count[s]);
+        solid_begin.push_back(n);
+    } else {
+        solid_begin = {0, n};
+    }
+    const uint64_t nsol = solid_begin.size() - 1;
+    nodes.assign(2 * n + n / 4 + 64 * ARENA_CHUNK, Entry{0, 0, 0, 0});
+    Builder B;
+    B.prims = leaves.data();
+    B.out = &nodes;
+
+    struct Task { uint64_t b, e; IBox box; uint64_t slot; };
+    std::vector<Task> tasks;
+    if (nsol == 1) {
+        IBox box; box.reset();
+        for (uint64_t i = 0; i < n; i++) { int lo[3], hi[3]; box_of(leaves[i], lo, hi); box.grow(lo, hi); }
+        tasks.push_back(Task{0, n, box, 0});
+    } else {
+        // top level: SAH over solids, each solid represented by its bounding box
+        std::vector<Entry> tl(nsol);
+        std::vector<IBox> sbox(nsol);
+        for (uint64_t s = 0; s < nsol; s++) {
+            IBox box; box.reset();
+            for (uint64_t i = solid_begin[s]; i < solid_begin[s + 1]; i++) { int lo[3], hi[3]; box_of(leaves[i], lo, hi); box.grow(lo, hi); }
+            sbox[s] = box;
+            tl[s] = Builder::pack(box, (uint32_t)s);
+        }
+        Builder T;
+        T.prims = tl.data();
+        std::vector<Entry> top(nsol * 2 + 2 * ARENA_CHUNK, Entry{0, 0, 0, 0});
+        T.out = &top;
+        Arena TA;
+        IBox all; all.reset();
+        for (uint64_t s = 0; s < nsol; s++) all.grow(sbox[s]);
+        T.build(TA, 0, nsol, all, 0);
+        if (T.overflow) return fail(CB_ERR_NOMEM, "native BVH: top-level node pool overflow");
+        // copy the top tree into the output; its leaves (w = solid id, nchild = 0) become tasks
+        const uint64_t ntop = std::min<uint64_t>(T.next.load(), top.size());
+        for (uint64_t i = 0; i < ntop; i++) nodes[i] = top[i];
+        B.next = (ntop + 7) / 8 * 8;
+        // walk the top tree to find referenced leaf slots
+        std::vector<uint64_t> stack = {0};
+        if ((top[0].w >> 28) == 0) {
+            tasks.push_back(Task{solid_begin[top[0].w], solid_begin[top[0].w + 1], sbox[top[0].w], 0});
+        } else {
+            while (!stack.empty()) {
+                uint64_t i = stack.back();
+                stack.pop_back();
+                uint32_t first = top[i].w & 0x0FFFFFFFu, k = top[i].w >> 28;
+                for (uint32_t c = first; c < first + k; c++) {
+                    if ((top[c].w >> 28) == 0) {
+                        uint32_t s = top[c].w;
+                        tasks.push_back(Task{solid_begin[s], solid_begin[s + 1], sbox[s], c});
+                    } else {
+                        stack.push_back(c);
+                    }
+                }
+            }
+        }
+    }
+    // biggest tasks first, then a simple work-stealing loop over host threads
+    std::sort(tasks.begin(), tasks.end(), [](const Task& a, const Task& b) { return (a.e - a.b) > (b.e - b.b); });
+    std::atomic<size_t> cursor{0};
+    unsigned nthreads = std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
+    auto worker = [&]() {
+        Arena A;
+        for (;;) {
+            size_t i = cursor.fetch_add(1);
+            if (i >= tasks.size()) break;
+            B.build(A, tasks[i].b, tasks[i].e, tasks[i].box, tasks[i].slot);
+        }
+    };
+    std::vector<std::thread> pool;
+    for (unsigned t = 1; t < nthreads; t++) pool.emplace_back(worker);
+    worker();
+    for (auto& t : pool) t.join();
+    if (B.overflow) return fail(CB_ERR_NOMEM, "native BVH: node pool overflow");
+    nodes.resize(std::min<uint64_t>(B.next.load() + 16, nodes.size()));
+
+    // breadth-first relayout: children blocks in level order, same alignment rule
+    std::vector<Entry> bfs(nodes.size() + 8 * 1024, Entry{0, 0, 0, 0});
+    std::vector<std::pair<uint64_t, uint64_t>> level = {{0, 0}}, nextlevel;   // (old slot, new slot)
+    bfs[0] = nodes[0];
+    uint64_t cur = 1;
+    while (!level.empty()) {
+        nextlevel.clear();
+        for (auto& pr : level) {
+            const Entry& en = nodes[pr.first];
+            uint32_t k = en.w >> 28, first = en.w & 0x0FFFFFFFu;
+            if (k == 0) continue;
+            uint64_t align = (k > 4) ? 8 : 2;
+            uint64_t start = (cur + align - 1) / align * align;
+            if (start + k + 8 > bfs.size()) bfs.resize(bfs.size() * 2, Entry{0, 0, 0, 0});
+            for (uint32_t c = 0; c < k; c++) {
+                bfs[start + c] = nodes[first + c];
+                nextlevel.push_back({first + c, start + c});
+            }
+            bfs[pr.second].w = (k << 28) | (uint32_t)start;
+            cur = start + k;
+        }
+        level.swap(nextlevel);
+    }
+    bfs.resize(cur + 16);
+    nodes.swap(bfs);
+    return CB_OK;
+}
+
+} // namespace cb

@@ -91,7 +91,9 @@ __device__ __forceinline__ float3 rng_sphere(Rng& s)
 
 // ------------------------------------------------------------------ geometry view
 struct DevGeometry {
-    const uint4*  nodes;      // reference packing, children of a node contiguous
+    const uint4*  nodes;      // the engine's traversal tree (reference packing, children contiguous)
+    const uint4*  ref_nodes;  // the reference tree itself: visit-order fallback only
+    uint32_t ref_root_w;
     const float4* tri48;      // 3 x float4 per triangle: v0.xyz v1.x | v1.yz v2.xy | v2.z rank code pad
     const float*  tables;     // global table pool
     const CbMaterial* materials;
@@ -208,16 +210,9 @@ __device__ __forceinline__ bool hit_box(const DevGeometry& g, const RaySetup& r,
 }
 
 // ------------------------------------------------------------------ traversal
-constexpr int CB_SSTACK = 12;   // entries per lane in shared memory
-constexpr int CB_LSTACK = 52;   // overflow entries in local memory
-
-struct TravStack {
-    uint2* s;          // shared-memory part, lane-interleaved: entry e at s[e*stride]
-    int stride;
-    uint2* l;          // local-memory overflow
-    __device__ __forceinline__ uint2 get(int i) const { return (i < CB_SSTACK) ? s[i * stride] : l[i - CB_SSTACK]; }
-    __device__ __forceinline__ void put(int i, uint2 e) const { if (i < CB_SSTACK) s[i * stride] = e; else l[i - CB_SSTACK] = e; }
-};
+constexpr int CB_SSTACK = 16;   // stack entries per lane in shared memory (lane-interleaved)
+constexpr int CB_LSTACK = 48;   // overflow entries per lane in local memory (rarely touched)
+constexpr int CB_RSTACK = 64;   // local stack of the reference-order fallback
 
 // Exact emulation of the reference's visit order (behaviour of mesh.h:45-126:
 // children ascending, leaves tested on the spot, internal children pushed and
@@ -225,19 +220,29 @@ struct TravStack {
 // the ordered traversal flags as order-sensitive (see traverse()).
 template <bool COUNT>
 static __device__ __noinline__ int traverse_reference_order(const DevGeometry& g, const float3& origin,
-                                                            const float3& direction, const RaySetup& r, int last_hit,
-                                                            float& min_distance, TravStack st,
-                                                            uint32_t* overflow_flag, TraverseCounters* cnt)
+                                                            const float3& direction, int last_hit,
+                                                            float& min_distance, uint32_t* overflow_flag,
+                                                            TraverseCounters* cnt)
 {
+    RaySetup r;
+    r.noid = f3(-origin.x / direction.x, -origin.y / direction.y, -origin.z / direction.z);
+    r.inv = f3(1.0f / direction.x, 1.0f / direction.y, 1.0f / direction.z);
+    r.fx = isfinite(r.inv.x); r.fy = isfinite(r.inv.y); r.fz = isfinite(r.inv.z);
     int triangle_index = -1;
     min_distance = -1.0f;
+    uint32_t stack[CB_RSTACK];
+    {
+        const uint4 root = __ldg(&g.ref_nodes[0]);
+        float tn;
+        if (!hit_box(g, r, root.x, root.y, root.z, tn)) return -1;
+    }
     int sp = 0;
-    st.put(sp++, make_uint2(g.root_w, 0u));
+    stack[sp++] = g.ref_root_w;
     while (sp > 0) {
-        const uint32_t cur = st.get(--sp).x;
+        const uint32_t cur = stack[--sp];
         const uint32_t first = cur & 0x0FFFFFFFu, n = cur >> 28;
         for (uint32_t i = first; i < first + n; i++) {
-            const uint4 nd = __ldg(&g.nodes[i]);
+            const uint4 nd = __ldg(&g.ref_nodes[i]);
             if (COUNT) cnt->nodes++;
             float tmin;
             if (hit_box(g, r, nd.x, nd.y, nd.z, tmin) && (min_distance < 0.0f || !(tmin > min_distance))) {
@@ -255,8 +260,8 @@ static __device__ __noinline__ int traverse_reference_order(const DevGeometry& g
                             }
                         }
                     }
-                } else if (sp < CB_SSTACK + CB_LSTACK) {
-                    st.put(sp++, make_uint2(w, 0u));
+                } else if (sp < CB_RSTACK) {
+                    stack[sp++] = w;
                 } else {
                     atomicOr(overflow_flag, 1u);
                 }
@@ -266,18 +271,25 @@ static __device__ __noinline__ int traverse_reference_order(const DevGeometry& g
     return triangle_index;
 }
 
-// Nearest-hit search over the reference tree topology with
-//   * near-child-first ordering and cull-at-pop (the reference does neither),
-//   * batched 128-bit node fetches (4 siblings in flight),
-//   * a lane-interleaved shared-memory short stack (conflict-free: entry e of
-//     lane l lives at stack[e*blockDim + l]) with a local-memory overflow area,
-//   * (distance, reference-test-rank) lexicographic minimum, which reproduces the
+// Nearest-hit search over the engine's tree (bvh_native.cu; same entry format as
+// the reference, children of a node contiguous).
+//   * ONE uniform loop: pop an entry; an internal entry expands its <= 8 children
+//     (two bursts of four 128-bit loads), continues with the nearest hit child and
+//     pushes the others; a leaf entry runs the triangle test.  Leaves travel on
+//     the stack with their box distance, so they are culled again at pop time and
+//     there is a single copy of each code path (the 4x unrolled inline triangle
+//     test of the first version thrashed the instruction cache).
+//   * inner while loops keep a warp in the "expand" or the "triangle" phase
+//     together (while-while traversal).
+//   * lane-interleaved shared-memory stack: entry e of lane l at stack[e*stride+l],
+//     conflict-free; a ray that would overflow it is handed to the fallback.
+//   * (distance, reference-test-rank) lexicographic minimum reproduces the
 //     reference's first-tested-wins tie rule under ANY visit order (SURVEY A-1).
-// Exactness: whenever every triangle hit lies inside its own leaf box in float
-// arithmetic (t >= box tmin) the result provably equals the reference's.  Boxes
-// are pruned with a small guard band so that any hit violating this (rounding at
-// a box face, ~1e-5 of rays) is seen and flagged; flagged rays are redone in the
-// reference's own visit order.  Returns the triangle index or -1.
+// Exactness: whenever every triangle hit lies inside its own (reference) leaf box
+// in float arithmetic (t >= box tmin) the result provably equals the reference's.
+// Boxes are pruned with a small guard band so that any hit violating this
+// (rounding at a box face, ~1e-5 of rays) is seen and flagged; flagged rays are
+// redone in the reference's own visit order.  Returns the triangle index or -1.
 template <bool COUNT>
 __device__ __forceinline__ int traverse(const DevGeometry& g, const float3& origin,
                                         const float3& direction, int last_hit, float& best_t,
@@ -295,7 +307,7 @@ __device__ __forceinline__ int traverse(const DevGeometry& g, const float3& orig
     best_t = INF;
 
     float tn;
-    if (!hit_box(g, r, g.root_x, g.root_y, g.root_z, tn)) { best_t = -1.0f; return -1; }
+    if (!hit_box(g, r, g.root_x, g.root_y, g.root_z, tn) || (g.root_w >> 28) == 0) { best_t = -1.0f; return -1; }
 
     // rounding scale of the slab arithmetic: |o/d| of the finite axes
     const float GUARD = 1e-5f;
@@ -305,77 +317,85 @@ __device__ __forceinline__ int traverse(const DevGeometry& g, const float3& orig
     if (r.fz) mag = fmaxf(mag, fabsf(r.noid.z));
     const float guard_abs = GUARD * mag;
     float limit = INF;           // prune boxes with tmin > limit = best_t + guard
-    bool order_sensitive = false;
+    bool redo = false;           // stack overflow, or (decided at the end) an order-sensitive winner
 
     uint2 lstack[CB_LSTACK];
-    TravStack st = {sstack, sstride, lstack};
+    auto push = [&](int i, uint2 e) { if (i < CB_SSTACK) sstack[i * sstride] = e; else lstack[i - CB_SSTACK] = e; };
+    auto peek = [&](int i) -> uint2 { return (i < CB_SSTACK) ? sstack[i * sstride] : lstack[i - CB_SSTACK]; };
     int sp = 0;
-    uint32_t cur = g.root_w;     // node group being expanded: nchild<<28 | first
-    float top_t = INF;           // tmin of the entry on top of the stack (valid when sp > 0)
+    uint32_t cur = g.root_w;     // entry being processed: nchild<<28 | first  (nchild == 0: leaf, child = triangle)
+    float cur_t = 0.0f;          // its box distance
+    float best_box_t = 0.0f;     // box distance of the leaf that holds the current best hit
+    bool have = true;
 
-    while (true) {
-        const uint32_t first = cur & 0x0FFFFFFFu;
-        const uint32_t n = cur >> 28;
-        for (uint32_t i = 0; i < n; i += 4) {
-            uint4 nd[4];
+    while (have) {
+        // ---- phase A: expand internal entries until a leaf comes up
+        while (have && (cur >> 28) != 0) {
+            const uint32_t first = cur & 0x0FFFFFFFu;
+            const uint32_t n = cur >> 28;
+            uint32_t near_w = 0;
+            float near_t = INF;
+            bool near_ok = false;
+            for (uint32_t i = 0; i < n; i += 4) {
+                uint4 nd[4];
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                uint32_t idx = first + min(i + k, n - 1);
-                nd[k] = __ldg(&g.nodes[idx]);
-            }
+                for (int k = 0; k < 4; k++) nd[k] = __ldg(&g.nodes[first + min(i + k, n - 1)]);
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                if (i + k < n) {
-                    if (COUNT) cnt->nodes++;
+                for (int k = 0; k < 4; k++) {
                     float tmin;
-                    if (hit_box(g, r, nd[k].x, nd[k].y, nd[k].z, tmin) && !(tmin > limit)) {
-                        const uint32_t w = nd[k].w;
-                        if ((w >> 28) == 0) {
-                            if ((int)w != last_hit) {
-                                if (COUNT) cnt->tris++;
-                                const float4* tp = g.tri48 + 3ull * w;
-                                float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
-                                float t;
-                                if (hit_triangle(origin, direction, f3(a.x, a.y, a.z), f3(a.w, b.x, b.y),
-                                                 f3(b.z, b.w, c.x), t)) {
-                                    if (t < tmin) order_sensitive = true;
-                                    uint32_t rank = __float_as_uint(c.y);
-                                    if (t < best_t || (t == best_t && rank < best_rank)) {
-                                        best_t = t; best_tri = (int)w; best_rank = rank;
-                                        limit = best_t + (GUARD * best_t + guard_abs);
-                                    }
-                                }
-                            }
-                        } else {
-                            // push, keeping the nearest entry on top
-                            uint2 e = make_uint2(w, __float_as_uint(tmin));
-                            if (sp > 0 && tmin > top_t) {
-                                uint2 top = st.get(sp - 1);      // new entry goes below the current top
-                                st.put(sp - 1, e);
-                                e = top;
-                            } else {
-                                top_t = tmin;
-                            }
-                            if (sp < CB_SSTACK + CB_LSTACK) st.put(sp++, e);
-                            else atomicOr(overflow_flag, 1u);
+                    const bool ok = (i + k < n) && hit_box(g, r, nd[k].x, nd[k].y, nd[k].z, tmin) && !(tmin > limit);
+                    if (COUNT && i + k < n) cnt->nodes++;
+                    if (ok) {
+                        uint32_t w = nd[k].w;
+                        if (!near_ok || tmin < near_t) {          // new nearest: the old one goes to the stack
+                            const uint32_t ow = near_w; const float ot = near_t; const bool had = near_ok;
+                            near_w = w; near_t = tmin; near_ok = true;
+                            w = ow; tmin = ot;
+                            if (!had) continue;
                         }
+                        if (sp < CB_SSTACK + CB_LSTACK) push(sp++, make_uint2(w, __float_as_uint(tmin)));
+                        else redo = true;
                     }
                 }
             }
+            if (near_ok) { cur = near_w; cur_t = near_t; }
+            else {
+                have = false;
+                while (sp > 0) {
+                    const uint2 e = peek(--sp);
+                    if (!(__uint_as_float(e.y) > limit)) { cur = e.x; cur_t = __uint_as_float(e.y); have = true; break; }
+                }
+            }
         }
-        // pop the next group whose box can still contain a nearer hit
-        bool found = false;
-        while (sp > 0) {
-            sp--;
-            uint2 e = st.get(sp);
-            if (sp > 0) top_t = __uint_as_float(st.get(sp - 1).y);
-            if (!(__uint_as_float(e.y) > limit)) { cur = e.x; found = true; break; }
+        // ---- phase B: triangle tests while leaves keep coming
+        while (have && (cur >> 28) == 0) {
+            if ((int)cur != last_hit) {
+                if (COUNT) cnt->tris++;
+                const float4* tp = g.tri48 + 3ull * cur;
+                const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+                float t;
+                if (hit_triangle(origin, direction, f3(a.x, a.y, a.z), f3(a.w, b.x, b.y), f3(b.z, b.w, c.x), t)) {
+                    const uint32_t rank = __float_as_uint(c.y);
+                    if (t < best_t || (t == best_t && rank < best_rank)) {
+                        best_t = t; best_tri = (int)cur; best_rank = rank; best_box_t = cur_t;
+                        limit = best_t + (GUARD * best_t + guard_abs);
+                    }
+                }
+            }
+            have = false;
+            while (sp > 0) {
+                const uint2 e = peek(--sp);
+                if (!(__uint_as_float(e.y) > limit)) { cur = e.x; cur_t = __uint_as_float(e.y); have = true; break; }
+            }
         }
-        if (!found) break;
     }
-    if (order_sensitive) {
+    // The reference returns the same lexicographic minimum unless it never tests the
+    // winner, which can only happen when the winner's hit lies in front of its own
+    // leaf box (t < box tmin); every other hit is irrelevant to the outcome.
+    if (best_tri != -1 && best_t < best_box_t) redo = true;
+    if (redo) {
         if (COUNT) cnt->resolved++;
-        return traverse_reference_order<COUNT>(g, origin, direction, r, last_hit, best_t, st, overflow_flag, cnt);
+        return traverse_reference_order<COUNT>(g, origin, direction, last_hit, best_t, overflow_flag, cnt);
     }
     if (best_tri == -1) best_t = -1.0f;
     return best_tri;

@@ -8,6 +8,9 @@
 
 namespace cb {
 
+struct Entry { uint32_t x, y, z, w; };
+int build_native_tree(std::vector<Entry>& leaves, const uint32_t* solid_of, std::vector<Entry>& nodes);
+
 // Pack triangles for the traversal: 48 B = 3 x float4 per triangle holding the
 // three world-space vertices, the reference test rank (tie-break, SURVEY A-1)
 // and the material code, so a leaf test is three coalescable 128-bit loads
@@ -53,6 +56,24 @@ static void reference_test_rank(const uint32_t* nodes, uint64_t nnodes, uint64_t
     }
 }
 
+// one leaf entry per triangle the reference traversal can reach, verbatim
+static void collect_reference_leaves(const uint32_t* nodes, uint64_t nnodes, uint64_t ntriangles,
+                                     const std::vector<uint32_t>& rank, std::vector<Entry>& leaves)
+{
+    leaves.clear();
+    leaves.reserve(ntriangles);
+    // a root that is itself a leaf is never tested by the reference (mesh.h:55-68)
+    if ((nodes[3] >> 28) == 0) return;
+    std::vector<uint8_t> seen(ntriangles, 0);
+    for (uint64_t i = 0; i < nnodes; i++) {
+        const uint32_t w = nodes[4 * i + 3];
+        if ((w >> 28) == 0 && w < ntriangles && rank[w] != 0xFFFFFFFFu && !seen[w]) {
+            seen[w] = 1;
+            leaves.push_back(Entry{nodes[4 * i], nodes[4 * i + 1], nodes[4 * i + 2], w});
+        }
+    }
+}
+
 template <typename T>
 static int upload(T** dst, const T* src, uint64_t count, uint64_t& total)
 {
@@ -67,7 +88,7 @@ static int upload(T** dst, const T* src, uint64_t count, uint64_t& total)
 static void free_geometry(Geometry* g)
 {
     cudaFree(g->vertices); cudaFree(g->triangles); cudaFree(g->material_codes); cudaFree(g->colors);
-    cudaFree(g->solid_id); cudaFree(g->nodes); cudaFree(g->tri48); cudaFree(g->tables);
+    cudaFree(g->solid_id); cudaFree(g->nodes); cudaFree(g->native_nodes); cudaFree(g->tri48); cudaFree(g->tables);
     cudaFree(g->materials); cudaFree(g->surfaces); cudaFree(g->solid_to_channel);
     cudaFree(g->time_cdf_x); cudaFree(g->time_cdf_y); cudaFree(g->charge_cdf_x); cudaFree(g->charge_cdf_y);
     delete g;
@@ -147,14 +168,34 @@ int cb_geometry_create(const CbGeometryDesc* d, cb_geom_t* out)
         cudaFree(d_rank);
     }
 
+    // the engine's own traversal tree over the reference's leaves (bvh_native.cu)
+    const uint32_t* root_entry = d->nodes;
+    std::vector<Entry> native;
+    const char* tree_env = getenv("CHROMA_B200_TREE");
+    const bool use_reference_tree = tree_env && strcmp(tree_env, "reference") == 0;
+    if (!use_reference_tree && d->ntriangles > 0) {
+        std::vector<Entry> leaves;
+        collect_reference_leaves(d->nodes, d->nnodes, d->ntriangles, rank, leaves);
+        rc = build_native_tree(leaves, d->solid_id, native);
+        if (rc != CB_OK) { free_geometry(g); return rc; }
+        native.resize(native.size() + 16, Entry{0, 0, 0, 0});
+        cudaError_t e = cudaMalloc((void**)&g->native_nodes, native.size() * sizeof(Entry));
+        if (e != cudaSuccess) { free_geometry(g); return cuda_fail(e, "cudaMalloc(native nodes)"); }
+        cudaMemcpy(g->native_nodes, native.data(), native.size() * sizeof(Entry), cudaMemcpyHostToDevice);
+        total += native.size() * sizeof(Entry);
+        g->nnative = native.size();
+        root_entry = reinterpret_cast<const uint32_t*>(native.data());
+    }
+
     DevGeometry& v = g->dev;
-    v.nodes = g->nodes; v.tri48 = g->tri48; v.tables = g->tables;
+    v.nodes = g->native_nodes ? g->native_nodes : g->nodes; v.tri48 = g->tri48; v.tables = g->tables;
+    v.ref_nodes = g->nodes; v.ref_root_w = d->nodes[3];
     v.materials = g->materials; v.surfaces = g->surfaces;
     v.world_origin = make_float3(d->world_origin[0], d->world_origin[1], d->world_origin[2]);
     v.world_scale = d->world_scale;
     v.wavelength_n = d->wavelength_n; v.wavelength_start = d->wavelength_start; v.wavelength_step = d->wavelength_step;
     v.time_n = d->time_n; v.time_start = d->time_start; v.time_step = d->time_step;
-    v.root_x = d->nodes[0]; v.root_y = d->nodes[1]; v.root_z = d->nodes[2]; v.root_w = d->nodes[3];
+    v.root_x = root_entry[0]; v.root_y = root_entry[1]; v.root_z = root_entry[2]; v.root_w = root_entry[3];
     v.nmaterials = d->nmaterials; v.nsurfaces = d->nsurfaces;
     // stage the leading part of the pool (the wavelength tables; the host lays
     // the long time CDFs out last) into shared memory, up to 48 KB
@@ -379,6 +420,34 @@ static void build_layers(std::vector<uint32_t>& leaf_nodes, std::vector<uint64_t
 }
 
 } // namespace cb
+
+// Host-only: the engine's traversal tree for a reference-format tree (test / tooling hook;
+// needs no GPU).  Two-call protocol: out_nodes == NULL returns the entry count only.
+extern "C" int cb_native_tree_build(const uint32_t* ref_nodes, uint64_t nnodes, uint64_t ntriangles,
+                                    const uint32_t* solid_id, uint32_t* out_nodes, uint64_t* out_count)
+{
+    static std::vector<Entry> cached;
+    if (!ref_nodes || nnodes == 0 || !out_count) return fail(CB_ERR_INVALID, "cb_native_tree_build: bad arguments");
+    if (out_nodes && !cached.empty()) {
+        memcpy(out_nodes, cached.data(), cached.size() * sizeof(Entry));
+        *out_count = cached.size();
+        cached.clear();
+        cached.shrink_to_fit();
+        return CB_OK;
+    }
+    std::vector<uint32_t> rank;
+    reference_test_rank(ref_nodes, nnodes, ntriangles, rank);
+    std::vector<Entry> leaves;
+    collect_reference_leaves(ref_nodes, nnodes, ntriangles, rank, leaves);
+    int rc = build_native_tree(leaves, solid_id, cached);
+    if (rc != CB_OK) return rc;
+    *out_count = cached.size();
+    if (out_nodes) {
+        memcpy(out_nodes, cached.data(), cached.size() * sizeof(Entry));
+        cached.clear();
+    }
+    return CB_OK;
+}
 
 extern "C" int cb_bvh_build(const float* vertices, uint64_t nvertices, const uint32_t* triangles,
                             uint64_t ntriangles, int32_t target_degree, float world_origin_out[3],

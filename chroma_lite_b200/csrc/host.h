@@ -25,6 +25,8 @@ struct Context {
     unsigned long long* d_counters = nullptr;      // 16 x u64 scratch (work counter, stats, flags)
     unsigned long long* h_counters = nullptr;      // pinned mirror
     uint32_t* d_block_counts = nullptr; size_t block_counts_cap = 0;   // compaction scratch
+    uint32_t* d_queue[2] = {nullptr, nullptr}; int32_t* d_hit_tri = nullptr; float* d_hit_dist = nullptr;
+    uint64_t scratch_cap = 0;                       // wavefront scratch (one rng-pool chunk)
 };
 
 Context& ctx();
@@ -48,6 +50,7 @@ struct Geometry {
     float* vertices = nullptr; uint32_t* triangles = nullptr; uint32_t* material_codes = nullptr;
     uint32_t* colors = nullptr; uint32_t* solid_id = nullptr; uint4* nodes = nullptr;
     // native
+    uint4* native_nodes = nullptr; uint64_t nnative = 0;   // engine-built traversal tree
     float4* tri48 = nullptr; float* tables = nullptr; CbMaterial* materials = nullptr; CbSurface* surfaces = nullptr;
     uint64_t nvertices = 0, ntriangles = 0, nnodes = 0, table_floats = 0;
     // detector

@@ -49,7 +49,7 @@ __device__ __forceinline__ void stage_tables(float* smem_dst, const float* gsrc,
 
 // ---------------------------------------------------------------- intersection
 template <bool COUNT>
-__global__ void __launch_bounds__(PROP_THREADS)
+__global__ void __launch_bounds__(PROP_THREADS, 4)
 intersect_kernel(DevGeometry g, const float* __restrict__ origins, const float* __restrict__ directions,
                  const int32_t* __restrict__ last_hit, uint64_t n, int32_t* __restrict__ tri_out,
                  float* __restrict__ dist_out, unsigned long long* counters)
@@ -76,24 +76,138 @@ intersect_kernel(DevGeometry g, const float* __restrict__ origins, const float* 
 }
 
 // ---------------------------------------------------------------- propagation
+// Wavefront scheduler.  One propagate call = a loop over physics steps; each step is
+//   step_intersect_kernel : one ray per thread, traversal only (few registers, high
+//                           occupancy), writes (triangle, distance) per photon;
+//   step_physics_kernel   : bulk + surface physics for the same photons, then the
+//                           survivors are appended to the next queue with one
+//                           warp-aggregated atomic per warp (ballot + popc prefix).
+// The queues hold chunk-local photon indices; RNG state k belongs to photon
+// first+k (replay contract), so results do not depend on the
+// order in which photons are scheduled.  When few photons are left the remaining
+// steps run in ONE persistent launch (propagate_tail_kernel) instead of a launch
+// pair per step.  This replaces the reference's host loop, which relaunches the
+// monolithic kernel per step, reloads 108 B of state per photon per step and
+// blocks on a 4-byte D2H copy between steps (gpu/photon.py:259-286).
 struct PropParams {
     CbPhotonBank bank;
-    uint32_t* rng;            // state of photon (first + k) is rng[k]
-    uint64_t first, count;
+    uint32_t* rng;                  // state of photon (first + k) is rng[k]
+    uint64_t first;                 // chunk base
+    const uint32_t* queue_in;       // chunk-local indices, nullptr = identity
+    uint32_t* queue_out;
+    int32_t* hit_tri;               // per chunk-local index
+    float* hit_dist;
+    uint32_t n_in;
+    int32_t step;                   // steps already taken by every photon in queue_in
     int32_t max_steps, use_weights, scatter_first;
-    unsigned long long* counters;   // [0] work cursor, [1] nodes, [2] tris, [3] overflow flag, [4] steps
+    unsigned long long* counters;   // [0] cursor / out count, [1] nodes, [2] tris, [3] overflow, [4] steps, [5] resolved
 };
 
-// Persistent-thread propagation: every lane owns one photon at a time and runs
-// it to termination (all steps in ONE launch, no host round trips); a lane whose
-// photon finished refills from a global cursor with one warp-aggregated atomic
-// (ballot + popc prefix), so warps stay populated without the reference's
-// per-step relaunch, 108 B/photon state reload and host-side queue swap
-// (gpu/photon.py:259-286).  RNG state k belongs to photon first+k (replay
-// contract), so results do not depend on scheduling.
+__device__ __forceinline__ void load_photon(const CbPhotonBank& b, uint64_t id, uint32_t hist, bool normalise, Photon& p)
+{
+    p.pos = ld3(b.pos, id);
+    p.dir = ld3(b.dir, id);
+    p.pol = ld3(b.pol, id);
+    if (normalise) {                 // once per propagate call, like the reference kernel's prologue
+        p.dir = p.dir / norm(p.dir);
+        p.pol = p.pol / norm(p.pol);
+    }
+    p.wavelength = b.wavelengths[id];
+    p.time = b.t[id];
+    p.last_hit_triangle = b.last_hit_triangles[id];
+    p.history = hist;
+    p.weight = b.weights[id];
+}
+__device__ __forceinline__ void store_photon(const CbPhotonBank& b, uint64_t id, const Photon& p)
+{
+    st3(b.pos, id, p.pos);
+    st3(b.dir, id, p.dir);
+    st3(b.pol, id, p.pol);
+    b.wavelengths[id] = p.wavelength;
+    b.t[id] = p.time;
+    b.flags[id] = p.history;
+    b.last_hit_triangles[id] = p.last_hit_triangle;
+    b.weights[id] = p.weight;
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(PROP_THREADS, 4)
+step_intersect_kernel(DevGeometry g, PropParams P)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint2* sstack = reinterpret_cast<uint2*>(smem_raw) + threadIdx.x;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n_in) return;
+    const uint32_t k = P.queue_in ? P.queue_in[i] : i;
+    const uint64_t id = P.first + k;
+    if (P.step == 0 && (P.bank.flags[id] & 0xFFFFu & CB_TERMINAL)) return;   // never ran: untouched
+    float3 pos = ld3(P.bank.pos, id);
+    float3 dir = ld3(P.bank.dir, id);
+    if (P.step == 0) dir = dir / norm(dir);
+    TraverseCounters cnt = {0, 0, 0};
+    float dist;
+    const int tri = traverse<COUNT>(g, pos, dir, P.bank.last_hit_triangles[id], dist, sstack, PROP_THREADS,
+                                    (uint32_t*)(P.counters + 3), &cnt);
+    P.hit_tri[k] = tri;
+    P.hit_dist[k] = dist;
+    if (COUNT) {
+        atomicAdd(P.counters + 1, (unsigned long long)cnt.nodes);
+        atomicAdd(P.counters + 2, (unsigned long long)cnt.tris);
+        atomicAdd(P.counters + 5, (unsigned long long)cnt.resolved);
+    }
+}
+
+__global__ void __launch_bounds__(PROP_THREADS, 2)
+step_physics_kernel(DevGeometry g, PropParams P)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ unsigned long long mbar;
+    float* stab = reinterpret_cast<float*>(smem_raw);
+    stage_tables(stab, g.tables, g.smem_floats * 4u, &mbar);
+    Tables T = {stab, g.tables, g.smem_floats};
+    const unsigned lane = threadIdx.x & 31u;
+    const bool last_step = (P.step + 1 >= P.max_steps);
+    // grid-stride over whole warps so the ballot below always sees full warps
+    const uint32_t n_round = (P.n_in + 31u) & ~31u;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+        bool alive = false;
+        uint32_t k = 0;
+        if (i < P.n_in) {
+            k = P.queue_in ? P.queue_in[i] : i;
+            const uint64_t id = P.first + k;
+            const uint32_t hist = P.bank.flags[id] & 0xFFFFu;
+            if (!(P.step == 0 && (hist & CB_TERMINAL))) {
+                Photon p;
+                load_photon(P.bank, id, hist, P.step == 0, p);
+                Rng rng = rng_load(P.rng, k);
+                if (photon_is_nan(p)) {
+                    p.history |= CB_NO_HIT | CB_NAN_ABORT;
+                } else {
+                    alive = physics_step(g, T, p, rng, P.hit_tri[k], P.hit_dist[k], P.use_weights != 0,
+                                         P.step == 0 ? P.scatter_first : 0);
+                }
+                rng_store(P.rng, k, rng);
+                store_photon(P.bank, id, p);
+                alive = alive && !last_step;
+            }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, alive);
+        if (m) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(P.counters, (unsigned long long)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (alive) P.queue_out[base + __popc(m & ((1u << lane) - 1u))] = k;
+        }
+    }
+}
+
+// Persistent-thread tail: every lane owns one photon at a time and runs it to
+// termination; a lane whose photon finished refills from a global cursor with one
+// warp-aggregated atomic, so the few long histories (reflections, re-emission
+// chains) do not cost a launch pair per step.
 template <bool COUNT>
 __global__ void __launch_bounds__(PROP_THREADS, 2)
-propagate_kernel(DevGeometry g, PropParams P)
+propagate_tail_kernel(DevGeometry g, PropParams P)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ unsigned long long mbar;
@@ -105,7 +219,7 @@ propagate_kernel(DevGeometry g, PropParams P)
 
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
-    long long my = -1;        // index within the chunk, -1 = lane is empty
+    long long my = -1;        // chunk-local photon index, -1 = lane is empty
     bool exhausted = false;
     Photon p;
     Rng rng;
@@ -119,29 +233,21 @@ propagate_kernel(DevGeometry g, PropParams P)
         const unsigned need_mask = __ballot_sync(0xffffffffu, need);
         if (need_mask) {
             unsigned long long base = 0;
-            if (lane == (unsigned)(__ffs(need_mask) - 1))
-                base = atomicAdd(P.counters, (unsigned long long)__popc(need_mask));
-            base = __shfl_sync(0xffffffffu, base, __ffs(need_mask) - 1);
+            const int leader = __ffs(need_mask) - 1;
+            if ((int)lane == leader) base = atomicAdd(P.counters, (unsigned long long)__popc(need_mask));
+            base = __shfl_sync(0xffffffffu, base, leader);
             if (need) {
-                unsigned long long k = base + __popc(need_mask & lt_mask);
-                if (k < P.count) {
+                const unsigned long long q = base + __popc(need_mask & lt_mask);
+                if (q < P.n_in) {
+                    const uint32_t k = P.queue_in ? P.queue_in[q] : (uint32_t)q;
                     const uint64_t id = P.first + k;
-                    uint32_t hist = P.bank.flags[id] & 0xFFFFu;
-                    if (!(hist & CB_TERMINAL)) {
+                    const uint32_t hist = P.bank.flags[id] & 0xFFFFu;
+                    if (!(P.step == 0 && (hist & CB_TERMINAL))) {
                         my = (long long)k;
-                        p.pos = ld3(P.bank.pos, id);
-                        p.dir = ld3(P.bank.dir, id);
-                        p.dir = p.dir / norm(p.dir);
-                        p.pol = ld3(P.bank.pol, id);
-                        p.pol = p.pol / norm(p.pol);
-                        p.wavelength = P.bank.wavelengths[id];
-                        p.time = P.bank.t[id];
-                        p.last_hit_triangle = P.bank.last_hit_triangles[id];
-                        p.history = hist;
-                        p.weight = P.bank.weights[id];
+                        load_photon(P.bank, id, hist, P.step == 0, p);
                         rng = rng_load(P.rng, k);
-                        steps = 0;
-                        sf = P.scatter_first;
+                        steps = P.step;
+                        sf = (P.step == 0) ? P.scatter_first : 0;
                     }
                 } else {
                     exhausted = true;
@@ -156,33 +262,24 @@ propagate_kernel(DevGeometry g, PropParams P)
         if (my >= 0) {
             bool alive;
             steps++;
+            nsteps_total++;
             if (photon_is_nan(p)) {
                 p.history |= CB_NO_HIT | CB_NAN_ABORT;
                 alive = false;
             } else {
                 float dist;
-                int tri = traverse<COUNT>(g, p.pos, p.dir, p.last_hit_triangle, dist, sstack, PROP_THREADS,
-                                          (uint32_t*)(P.counters + 3), &cnt);
+                const int tri = traverse<COUNT>(g, p.pos, p.dir, p.last_hit_triangle, dist, sstack, PROP_THREADS,
+                                                (uint32_t*)(P.counters + 3), &cnt);
                 alive = physics_step(g, T, p, rng, tri, dist, P.use_weights != 0, sf);
                 sf = 0;
             }
             if (!alive || steps >= P.max_steps) {
-                const uint64_t id = P.first + (uint64_t)my;
                 rng_store(P.rng, (uint64_t)my, rng);
-                st3(P.bank.pos, id, p.pos);
-                st3(P.bank.dir, id, p.dir);
-                st3(P.bank.pol, id, p.pol);
-                P.bank.wavelengths[id] = p.wavelength;
-                P.bank.t[id] = p.time;
-                P.bank.flags[id] = p.history;
-                P.bank.last_hit_triangles[id] = p.last_hit_triangle;
-                P.bank.weights[id] = p.weight;
-                nsteps_total += (unsigned long long)steps;
+                store_photon(P.bank, P.first + (uint64_t)my, p);
                 my = -1;
             }
         }
     }
-    // per-warp reduction of the statistics, one atomic per warp
     for (int o = 16; o > 0; o >>= 1) nsteps_total += __shfl_down_sync(0xffffffffu, nsteps_total, o);
     if (lane == 0 && nsteps_total) atomicAdd(P.counters + 4, nsteps_total);
     if (COUNT) {
@@ -538,16 +635,35 @@ int cb_propagate(const CbPhotonBank* bank, cb_geom_t gh, cb_rng_t rh, int32_t nt
     if (nthreads_per_block <= 0 || max_blocks <= 0) return fail(CB_ERR_INVALID, "cb_propagate: bad launch parameters");
     const uint64_t pool = std::min<uint64_t>((uint64_t)nthreads_per_block * (uint64_t)max_blocks, r->n);
     if (pool == 0) return fail(CB_ERR_INVALID, "cb_propagate: empty rng pool");
+    if (pool >= (1ull << 32)) return fail(CB_ERR_INVALID, "cb_propagate: rng pool too large");
     if (stats) { memset(stats, 0, sizeof(*stats)); }
     if (bank->n == 0 || max_steps <= 0) return CB_OK;
     Context& c = ctx();
     const bool count = getenv("CHROMA_B200_STATS") != nullptr;
-    auto kern = count ? propagate_kernel<true> : propagate_kernel<false>;
-    size_t smem = ((g->smem_table_bytes + 127u) & ~127u) + stack_smem_bytes();
-    CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    CB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, PROP_THREADS, smem));
-    if (per_sm < 1) return fail(CB_ERR_CUDA, "cb_propagate: kernel does not fit on an SM (smem %zu B)", smem);
+    static const uint64_t tail_threshold = getenv("CHROMA_B200_TAIL") ? (uint64_t)atoll(getenv("CHROMA_B200_TAIL")) : 16384;
+
+    // scratch: two queues + hit arrays, sized for one chunk
+    const uint64_t cap = std::min<uint64_t>(pool, bank->n);
+    if (c.scratch_cap < cap) {
+        cudaFree(c.d_queue[0]); cudaFree(c.d_queue[1]); cudaFree(c.d_hit_tri); cudaFree(c.d_hit_dist);
+        c.d_queue[0] = c.d_queue[1] = nullptr; c.d_hit_tri = nullptr; c.d_hit_dist = nullptr; c.scratch_cap = 0;
+        CB_CUDA(cudaMalloc(&c.d_queue[0], cap * 4)); CB_CUDA(cudaMalloc(&c.d_queue[1], cap * 4));
+        CB_CUDA(cudaMalloc(&c.d_hit_tri, cap * 4)); CB_CUDA(cudaMalloc(&c.d_hit_dist, cap * 4));
+        c.scratch_cap = cap;
+    }
+
+    auto k_int = count ? step_intersect_kernel<true> : step_intersect_kernel<false>;
+    auto k_tail = count ? propagate_tail_kernel<true> : propagate_tail_kernel<false>;
+    const size_t smem_int = stack_smem_bytes();
+    const size_t smem_tab = (g->smem_table_bytes + 127u) & ~127u;
+    const size_t smem_tail = smem_tab + stack_smem_bytes();
+    CB_CUDA(cudaFuncSetAttribute(k_int, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_int));
+    CB_CUDA(cudaFuncSetAttribute(step_physics_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_tab, 16)));
+    CB_CUDA(cudaFuncSetAttribute(k_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tail));
+    int phys_per_sm = 0, tail_per_sm = 0;
+    CB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&phys_per_sm, step_physics_kernel, PROP_THREADS, smem_tab));
+    CB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tail_per_sm, k_tail, PROP_THREADS, smem_tail));
+    if (phys_per_sm < 1 || tail_per_sm < 1) return fail(CB_ERR_CUDA, "cb_propagate: kernels do not fit on an SM");
 
     unsigned long long tot[16] = {0};
     uint32_t launches = 0;
@@ -555,16 +671,42 @@ int cb_propagate(const CbPhotonBank* bank, cb_geom_t gh, cb_rng_t rh, int32_t nt
     // photons beyond the pool reuse states chunk by chunk, in order, exactly as
     // the reference's chunk_iterator does for one step (gpu/photon.py:266-268)
     for (uint64_t first = 0; first < bank->n; first += pool) {
-        uint64_t cnt = std::min<uint64_t>(pool, bank->n - first);
-        CB_CUDA(cudaMemsetAsync(c.d_counters, 0, 16 * sizeof(unsigned long long), c.stream));
+        const uint64_t cnt = std::min<uint64_t>(pool, bank->n - first);
         PropParams P;
-        P.bank = *bank; P.rng = r->states; P.first = first; P.count = cnt;
+        P.bank = *bank; P.rng = r->states; P.first = first;
+        P.hit_tri = c.d_hit_tri; P.hit_dist = c.d_hit_dist;
         P.max_steps = max_steps; P.use_weights = use_weights; P.scatter_first = scatter_first;
         P.counters = c.d_counters;
-        unsigned blocks = (unsigned)std::min<uint64_t>((cnt + PROP_THREADS - 1) / PROP_THREADS, (uint64_t)c.sm_count * per_sm);
-        kern<<<blocks, PROP_THREADS, smem, c.stream>>>(g->dev, P);
-        CB_CUDA(cudaGetLastError());
-        launches++;
+        uint64_t n_alive = cnt;
+        const uint32_t* q_in = nullptr;
+        int qsel = 0;
+        CB_CUDA(cudaMemsetAsync(c.d_counters, 0, 16 * sizeof(unsigned long long), c.stream));
+        for (int step = 0; step < max_steps && n_alive > 0; step++) {
+            P.queue_in = q_in; P.queue_out = c.d_queue[qsel]; P.n_in = (uint32_t)n_alive; P.step = step;
+            if (n_alive <= tail_threshold || step + 1 == max_steps) {
+                // finish everything that is left in one persistent launch
+                unsigned blocks = (unsigned)std::min<uint64_t>((n_alive + PROP_THREADS - 1) / PROP_THREADS,
+                                                               (uint64_t)c.sm_count * tail_per_sm);
+                k_tail<<<blocks, PROP_THREADS, smem_tail, c.stream>>>(g->dev, P);
+                CB_CUDA(cudaGetLastError());
+                launches++;
+                n_alive = 0;
+                break;
+            }
+            unsigned blocks = (unsigned)((n_alive + PROP_THREADS - 1) / PROP_THREADS);
+            k_int<<<blocks, PROP_THREADS, smem_int, c.stream>>>(g->dev, P);
+            unsigned pblocks = (unsigned)std::min<uint64_t>(blocks, (uint64_t)c.sm_count * phys_per_sm);
+            step_physics_kernel<<<pblocks, PROP_THREADS, smem_tab, c.stream>>>(g->dev, P);
+            CB_CUDA(cudaGetLastError());
+            launches += 2;
+            CB_CUDA(cudaMemcpyAsync(c.h_counters, c.d_counters, 8, cudaMemcpyDeviceToHost, c.stream));
+            CB_CUDA(cudaMemsetAsync(c.d_counters, 0, 8, c.stream));
+            CB_CUDA(cudaStreamSynchronize(c.stream));
+            tot[4] += n_alive;                       // every queued photon took one step
+            n_alive = c.h_counters[0];
+            q_in = c.d_queue[qsel];
+            qsel ^= 1;
+        }
         CB_CUDA(cudaMemcpyAsync(c.h_counters, c.d_counters, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c.stream));
         CB_CUDA(cudaStreamSynchronize(c.stream));
         for (int i = 1; i < 6; i++) tot[i] += c.h_counters[i];
@@ -572,7 +714,8 @@ int cb_propagate(const CbPhotonBank* bank, cb_geom_t gh, cb_rng_t rh, int32_t nt
     CB_CUDA(cudaEventRecord(c.kev1, c.stream));
     CB_CUDA(cudaEventSynchronize(c.kev1));
     if (stats) {
-        stats->photons = bank->n; stats->steps = tot[4]; stats->nodes_visited = tot[1]; stats->tris_tested = tot[2]; stats->rays_resolved = tot[5];
+        stats->photons = bank->n; stats->steps = tot[4]; stats->nodes_visited = tot[1]; stats->tris_tested = tot[2];
+        stats->rays_resolved = tot[5];
         stats->launches = launches;
         cudaEventElapsedTime(&stats->kernel_ms, c.kev0, c.kev1);
     }

@@ -197,6 +197,14 @@ int cb_bvh_build(const float* vertices, uint64_t nvertices,
                  uint32_t* nodes_out, uint64_t* nnodes_out,
                  uint64_t* layer_offsets_out, int32_t* nlayers_out);
 
+/* The engine's own traversal tree (SAH, <= 8 children, two-level by solid) over the
+ * leaves of a reference-format tree; same entry packing, root at entry 0.  Host
+ * only (no GPU needed); cb_geometry_create does this internally.  Two-call
+ * protocol like cb_bvh_build.  No reference counterpart (the reference traverses
+ * its build tree directly, chroma/cuda/mesh.h:45-126). */
+int cb_native_tree_build(const uint32_t* ref_nodes, uint64_t nnodes, uint64_t ntriangles,
+                         const uint32_t* solid_id, uint32_t* out_nodes, uint64_t* out_count);
+
 /* ---- RNG ---------------------------------------------------------------- */
 /* replaces get_rng_states / init_rng (chroma/gpu/tools.py:117-145,
  * chroma/cuda/random.h:60-70): state i == curand_init(seed, i, offset). */

@@ -19,7 +19,7 @@ desc, keep = scenes.desc_of(geo)
 rg = ref_driver.RefGeometry(desc, keep)
 rtri, rdist, _ = ref_driver.intersect(rg, o, d)
 bad = np.flatnonzero(tri != rtri)
-print('mismatch', len(bad), bad)
+print("mismatch", len(bad), bad)
 otri, odist, cnt = orc.intersect(desc, o[bad], d[bad])
 rank = orc.triangle_rank(desc)
 for k, i in enumerate(bad):
