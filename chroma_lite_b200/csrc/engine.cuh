@@ -272,63 +272,76 @@ static __device__ __noinline__ int traverse_reference_order(const DevGeometry& g
 }
 
 // Nearest-hit search over the engine's tree (bvh_native.cu; same entry format as
-// the reference, children of a node contiguous).
+// the reference, children of a node contiguous), written as a resumable state
+// machine so that a persistent warp can retire finished rays and refill the idle
+// lanes instead of waiting for its longest ray (the first version kept only ~6 of
+// 32 lanes busy).
 //   * ONE uniform loop: pop an entry; an internal entry expands its <= 8 children
 //     (two bursts of four 128-bit loads), continues with the nearest hit child and
 //     pushes the others; a leaf entry runs the triangle test.  Leaves travel on
 //     the stack with their box distance, so they are culled again at pop time and
 //     there is a single copy of each code path (the 4x unrolled inline triangle
 //     test of the first version thrashed the instruction cache).
-//   * inner while loops keep a warp in the "expand" or the "triangle" phase
-//     together (while-while traversal).
+//   * round(): one "expand until a leaf comes up" phase followed by one "triangle
+//     tests while leaves keep coming" phase (while-while traversal).
 //   * lane-interleaved shared-memory stack: entry e of lane l at stack[e*stride+l],
-//     conflict-free; a ray that would overflow it is handed to the fallback.
+//     conflict-free, with a local-memory overflow area.
 //   * (distance, reference-test-rank) lexicographic minimum reproduces the
 //     reference's first-tested-wins tie rule under ANY visit order (SURVEY A-1).
-// Exactness: whenever every triangle hit lies inside its own (reference) leaf box
-// in float arithmetic (t >= box tmin) the result provably equals the reference's.
-// Boxes are pruned with a small guard band so that any hit violating this
-// (rounding at a box face, ~1e-5 of rays) is seen and flagged; flagged rays are
-// redone in the reference's own visit order.  Returns the triangle index or -1.
-template <bool COUNT>
-__device__ __forceinline__ int traverse(const DevGeometry& g, const float3& origin,
-                                        const float3& direction, int last_hit, float& best_t,
-                                        uint2* sstack, int sstride, uint32_t* overflow_flag,
-                                        TraverseCounters* cnt)
-{
-    const float INF = __int_as_float(0x7f800000);
+// Exactness: the reference returns the same lexicographic minimum unless it never
+// tests the winner, which can only happen when the winner's hit lies in front of
+// its own (reference) leaf box in float arithmetic (t < box tmin).  Boxes are
+// pruned with a small guard band so that such a winner is always seen; those rays
+// (~1e-7) are redone in the reference's own visit order on the reference tree.
+struct Trav {
+    float3 origin, direction;
     RaySetup r;
-    r.noid = f3(-origin.x / direction.x, -origin.y / direction.y, -origin.z / direction.z);
-    r.inv = f3(1.0f / direction.x, 1.0f / direction.y, 1.0f / direction.z);
-    r.fx = isfinite(r.inv.x); r.fy = isfinite(r.inv.y); r.fz = isfinite(r.inv.z);
-
-    int best_tri = -1;
-    uint32_t best_rank = 0xFFFFFFFFu;
-    best_t = INF;
-
-    float tn;
-    if (!hit_box(g, r, g.root_x, g.root_y, g.root_z, tn) || (g.root_w >> 28) == 0) { best_t = -1.0f; return -1; }
-
-    // rounding scale of the slab arithmetic: |o/d| of the finite axes
-    const float GUARD = 1e-5f;
-    float mag = 0.0f;
-    if (r.fx) mag = fmaxf(mag, fabsf(r.noid.x));
-    if (r.fy) mag = fmaxf(mag, fabsf(r.noid.y));
-    if (r.fz) mag = fmaxf(mag, fabsf(r.noid.z));
-    const float guard_abs = GUARD * mag;
-    float limit = INF;           // prune boxes with tmin > limit = best_t + guard
-    bool redo = false;           // stack overflow, or (decided at the end) an order-sensitive winner
-
+    float best_t, limit, guard_abs, cur_t, best_box_t;
+    uint32_t best_rank, cur;
+    int best_tri, last_hit, sp;
+    bool have, redo;
     uint2 lstack[CB_LSTACK];
-    auto push = [&](int i, uint2 e) { if (i < CB_SSTACK) sstack[i * sstride] = e; else lstack[i - CB_SSTACK] = e; };
-    auto peek = [&](int i) -> uint2 { return (i < CB_SSTACK) ? sstack[i * sstride] : lstack[i - CB_SSTACK]; };
-    int sp = 0;
-    uint32_t cur = g.root_w;     // entry being processed: nchild<<28 | first  (nchild == 0: leaf, child = triangle)
-    float cur_t = 0.0f;          // its box distance
-    float best_box_t = 0.0f;     // box distance of the leaf that holds the current best hit
-    bool have = true;
 
-    while (have) {
+    __device__ __forceinline__ void push(uint2* sstack, int sstride, uint2 e)
+    {
+        if (sp < CB_SSTACK) sstack[sp * sstride] = e; else lstack[sp - CB_SSTACK] = e;
+        sp++;
+    }
+    __device__ __forceinline__ void pop_next(const uint2* sstack, int sstride)
+    {
+        have = false;
+        while (sp > 0) {
+            --sp;
+            const uint2 e = (sp < CB_SSTACK) ? sstack[sp * sstride] : lstack[sp - CB_SSTACK];
+            if (!(__uint_as_float(e.y) > limit)) { cur = e.x; cur_t = __uint_as_float(e.y); have = true; break; }
+        }
+    }
+
+    // returns false when the ray misses the world box (result: no hit)
+    __device__ __forceinline__ bool init(const DevGeometry& g, const float3& o, const float3& d, int last)
+    {
+        const float INF = __int_as_float(0x7f800000);
+        origin = o; direction = d; last_hit = last;
+        r.noid = f3(-o.x / d.x, -o.y / d.y, -o.z / d.z);
+        r.inv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+        r.fx = isfinite(r.inv.x); r.fy = isfinite(r.inv.y); r.fz = isfinite(r.inv.z);
+        best_tri = -1; best_rank = 0xFFFFFFFFu; best_t = INF; limit = INF; best_box_t = 0.0f;
+        sp = 0; cur = g.root_w; cur_t = 0.0f; redo = false;
+        float tn;
+        have = hit_box(g, r, g.root_x, g.root_y, g.root_z, tn) && (g.root_w >> 28) != 0;
+        // rounding scale of the slab arithmetic: |o/d| of the finite axes
+        float mag = 0.0f;
+        if (r.fx) mag = fmaxf(mag, fabsf(r.noid.x));
+        if (r.fy) mag = fmaxf(mag, fabsf(r.noid.y));
+        if (r.fz) mag = fmaxf(mag, fabsf(r.noid.z));
+        guard_abs = 1e-5f * mag;
+        return have;
+    }
+
+    template <bool COUNT>
+    __device__ __forceinline__ void round(const DevGeometry& g, uint2* sstack, int sstride, TraverseCounters* cnt)
+    {
+        const float INF = __int_as_float(0x7f800000);
         // ---- phase A: expand internal entries until a leaf comes up
         while (have && (cur >> 28) != 0) {
             const uint32_t first = cur & 0x0FFFFFFFu;
@@ -353,19 +366,13 @@ __device__ __forceinline__ int traverse(const DevGeometry& g, const float3& orig
                             w = ow; tmin = ot;
                             if (!had) continue;
                         }
-                        if (sp < CB_SSTACK + CB_LSTACK) push(sp++, make_uint2(w, __float_as_uint(tmin)));
+                        if (sp < CB_SSTACK + CB_LSTACK) push(sstack, sstride, make_uint2(w, __float_as_uint(tmin)));
                         else redo = true;
                     }
                 }
             }
             if (near_ok) { cur = near_w; cur_t = near_t; }
-            else {
-                have = false;
-                while (sp > 0) {
-                    const uint2 e = peek(--sp);
-                    if (!(__uint_as_float(e.y) > limit)) { cur = e.x; cur_t = __uint_as_float(e.y); have = true; break; }
-                }
-            }
+            else pop_next(sstack, sstride);
         }
         // ---- phase B: triangle tests while leaves keep coming
         while (have && (cur >> 28) == 0) {
@@ -378,27 +385,38 @@ __device__ __forceinline__ int traverse(const DevGeometry& g, const float3& orig
                     const uint32_t rank = __float_as_uint(c.y);
                     if (t < best_t || (t == best_t && rank < best_rank)) {
                         best_t = t; best_tri = (int)cur; best_rank = rank; best_box_t = cur_t;
-                        limit = best_t + (GUARD * best_t + guard_abs);
+                        limit = best_t + (1e-5f * best_t + guard_abs);
                     }
                 }
             }
-            have = false;
-            while (sp > 0) {
-                const uint2 e = peek(--sp);
-                if (!(__uint_as_float(e.y) > limit)) { cur = e.x; cur_t = __uint_as_float(e.y); have = true; break; }
-            }
+            pop_next(sstack, sstride);
         }
     }
-    // The reference returns the same lexicographic minimum unless it never tests the
-    // winner, which can only happen when the winner's hit lies in front of its own
-    // leaf box (t < box tmin); every other hit is irrelevant to the outcome.
-    if (best_tri != -1 && best_t < best_box_t) redo = true;
-    if (redo) {
-        if (COUNT) cnt->resolved++;
-        return traverse_reference_order<COUNT>(g, origin, direction, last_hit, best_t, overflow_flag, cnt);
+
+    // call once have == false; returns the triangle (or -1) and its distance
+    template <bool COUNT>
+    __device__ __forceinline__ int finish(const DevGeometry& g, float& dist, uint32_t* overflow_flag, TraverseCounters* cnt)
+    {
+        if (redo || (best_tri != -1 && best_t < best_box_t)) {
+            if (COUNT) cnt->resolved++;
+            return traverse_reference_order<COUNT>(g, origin, direction, last_hit, dist, overflow_flag, cnt);
+        }
+        dist = (best_tri == -1) ? -1.0f : best_t;
+        return best_tri;
     }
-    if (best_tri == -1) best_t = -1.0f;
-    return best_tri;
+};
+
+// one ray, start to finish (used where a lane owns a whole photon history)
+template <bool COUNT>
+__device__ __forceinline__ int traverse(const DevGeometry& g, const float3& origin,
+                                        const float3& direction, int last_hit, float& best_t,
+                                        uint2* sstack, int sstride, uint32_t* overflow_flag,
+                                        TraverseCounters* cnt)
+{
+    Trav tv;
+    tv.init(g, origin, direction, last_hit);
+    while (tv.have) tv.template round<COUNT>(g, sstack, sstride, cnt);
+    return tv.template finish<COUNT>(g, best_t, overflow_flag, cnt);
 }
 
 // ------------------------------------------------------------------ physics

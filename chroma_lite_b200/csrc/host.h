@@ -26,6 +26,8 @@ struct Context {
     unsigned long long* h_counters = nullptr;      // pinned mirror
     uint32_t* d_block_counts = nullptr; size_t block_counts_cap = 0;   // compaction scratch
     uint32_t* d_queue[2] = {nullptr, nullptr}; int32_t* d_hit_tri = nullptr; float* d_hit_dist = nullptr;
+    uint32_t* d_keys[2] = {nullptr, nullptr}; uint32_t* d_sorted = nullptr; void* d_sort_tmp = nullptr;
+    size_t sort_tmp_bytes = 0;
     uint64_t scratch_cap = 0;                       // wavefront scratch (one rng-pool chunk)
 };
 

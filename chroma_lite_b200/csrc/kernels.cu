@@ -1,6 +1,7 @@
 // kernels.cu -- the hot path: ray intersection, photon propagation, photon-bank
 // utilities and the DAQ, plus their C-ABI entry points.
 #include "host.h"
+#include <cub/device/device_radix_sort.cuh>
 #include <algorithm>
 #include <string.h>
 #include <stdlib.h>
@@ -48,31 +49,91 @@ __device__ __forceinline__ void stage_tables(float* smem_dst, const float* gsrc,
 }
 
 // ---------------------------------------------------------------- intersection
-template <bool COUNT>
-__global__ void __launch_bounds__(PROP_THREADS, 4)
-intersect_kernel(DevGeometry g, const float* __restrict__ origins, const float* __restrict__ directions,
-                 const int32_t* __restrict__ last_hit, uint64_t n, int32_t* __restrict__ tri_out,
-                 float* __restrict__ dist_out, unsigned long long* counters)
+// Persistent traversal with per-lane ray refill: every lane carries one ray; after
+// each while-while round the warp retires finished rays and, once REFILL_MIN lanes
+// are idle, claims that many new rays with ONE atomic on the queue cursor (ballot +
+// popc prefix).  Warps therefore stay populated however uneven the ray lengths are.
+constexpr int REFILL_MIN = 8;
+
+template <bool COUNT, class Source>
+__device__ __forceinline__ void persistent_intersect(const DevGeometry& g, Source& src, unsigned long long n,
+                                                     unsigned long long* cursor, uint2* sstack,
+                                                     unsigned long long* counters)
 {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    uint2* sstack = reinterpret_cast<uint2*>(smem_raw) + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    Trav tv;
+    tv.have = false;
+    bool active = false, exhausted = false;
+    unsigned long long slot = 0;
     TraverseCounters cnt = {0, 0, 0};
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        float3 o = ld3(origins, i);
-        float3 d = ld3(directions, i);
-        d = d / norm(d);
-        float dist;
-        int tri = traverse<COUNT>(g, o, d, last_hit ? last_hit[i] : -1, dist, sstack, PROP_THREADS,
-                                  (uint32_t*)(counters + 3), &cnt);
-        tri_out[i] = tri;
-        if (tri != -1) dist_out[i] = dist;
+    for (;;) {
+        const unsigned idle = __ballot_sync(0xffffffffu, !active);
+        if (!exhausted && (idle == 0xffffffffu || __popc(idle) >= REFILL_MIN)) {
+            unsigned long long base = 0;
+            const int leader = __ffs(idle) - 1;
+            if ((int)lane == leader) base = atomicAdd(cursor, (unsigned long long)__popc(idle));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (!active) {
+                const unsigned long long q = base + __popc(idle & lt_mask);
+                if (q < n) {
+                    float3 o, d;
+                    int last;
+                    slot = q;
+                    if (src.load(q, o, d, last)) {
+                        active = true;
+                        if (!tv.init(g, o, d, last)) { src.store(slot, -1, -1.0f); active = false; }
+                    }
+                }
+            }
+            exhausted = __any_sync(0xffffffffu, base + __popc(idle) >= n);
+        }
+        if (__ballot_sync(0xffffffffu, active) == 0) {
+            if (exhausted) break;
+            continue;
+        }
+        if (active) {
+            tv.template round<COUNT>(g, sstack, PROP_THREADS, &cnt);
+            if (!tv.have) {
+                float dist;
+                const int tri = tv.template finish<COUNT>(g, dist, (uint32_t*)(counters + 3), &cnt);
+                src.store(slot, tri, dist);
+                active = false;
+            }
+        }
     }
     if (COUNT) {
         atomicAdd(counters + 1, (unsigned long long)cnt.nodes);
         atomicAdd(counters + 2, (unsigned long long)cnt.tris);
         atomicAdd(counters + 5, (unsigned long long)cnt.resolved);
     }
+}
+
+struct RaySource {           // cb_intersect: free rays, direction normalised like distance_to_mesh
+    const float* origins; const float* directions; const int32_t* last_hit;
+    int32_t* tri_out; float* dist_out;
+    __device__ __forceinline__ bool load(unsigned long long i, float3& o, float3& d, int& last) const
+    {
+        o = ld3(origins, i);
+        d = ld3(directions, i);
+        d = d / norm(d);
+        last = last_hit ? last_hit[i] : -1;
+        return true;
+    }
+    __device__ __forceinline__ void store(unsigned long long i, int tri, float dist) const
+    {
+        tri_out[i] = tri;
+        if (tri != -1) dist_out[i] = dist;          // untouched on a miss, like the reference
+    }
+};
+
+template <bool COUNT>
+__global__ void __launch_bounds__(PROP_THREADS, 4)
+intersect_kernel(DevGeometry g, RaySource src, uint64_t n, unsigned long long* counters)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint2* sstack = reinterpret_cast<uint2*>(smem_raw) + threadIdx.x;
+    persistent_intersect<COUNT>(g, src, n, counters, sstack, counters);
 }
 
 // ---------------------------------------------------------------- propagation
@@ -130,31 +191,79 @@ __device__ __forceinline__ void store_photon(const CbPhotonBank& b, uint64_t id,
     b.weights[id] = p.weight;
 }
 
+// Coherence key of a ray: coarse origin cell (4 bits/axis of the world box) above
+// the direction in an octahedral map (Morton-interleaved, 9 bits/axis).  Sorting
+// the step's queue by this key puts rays that walk the same part of the tree into
+// the same warp: fewer divergent iterations and the nodes they share stay in L1.
+__device__ __forceinline__ uint32_t spread9(uint32_t x)
+{
+    x &= 0x000001ffu;                       // interleave zeros between the low 9 bits
+    x = (x ^ (x << 8)) & 0x00ff00ffu;
+    x = (x ^ (x << 4)) & 0x0f0f0f0fu;
+    x = (x ^ (x << 2)) & 0x33333333u;
+    x = (x ^ (x << 1)) & 0x55555555u;
+    return x;
+}
+__global__ void __launch_bounds__(256)
+ray_key_kernel(DevGeometry g, PropParams P, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n_in) return;
+    const uint32_t k = P.queue_in ? P.queue_in[i] : i;
+    const uint64_t id = P.first + k;
+    const float3 pos = ld3(P.bank.pos, id);
+    float3 d = ld3(P.bank.dir, id);
+    const float extent = 65535.0f * g.world_scale;
+    const float inv = 16.0f / extent;
+    const uint32_t cx = (uint32_t)fminf(fmaxf((pos.x - g.world_origin.x) * inv, 0.0f), 15.0f);
+    const uint32_t cy = (uint32_t)fminf(fmaxf((pos.y - g.world_origin.y) * inv, 0.0f), 15.0f);
+    const uint32_t cz = (uint32_t)fminf(fmaxf((pos.z - g.world_origin.z) * inv, 0.0f), 15.0f);
+    // octahedral map of the direction to [0,1]^2
+    const float s = 1.0f / (fabsf(d.x) + fabsf(d.y) + fabsf(d.z) + 1e-30f);
+    float u = d.x * s, v = d.y * s;
+    if (d.z < 0.0f) {
+        const float uu = (1.0f - fabsf(v)) * (u >= 0.0f ? 1.0f : -1.0f);
+        const float vv = (1.0f - fabsf(u)) * (v >= 0.0f ? 1.0f : -1.0f);
+        u = uu; v = vv;
+    }
+    const uint32_t qu = (uint32_t)fminf(fmaxf((u * 0.5f + 0.5f) * 512.0f, 0.0f), 511.0f);
+    const uint32_t qv = (uint32_t)fminf(fmaxf((v * 0.5f + 0.5f) * 512.0f, 0.0f), 511.0f);
+    const uint32_t dirkey = spread9(qu) | (spread9(qv) << 1);            // 18 bits
+    keys[i] = (((cx << 8) | (cy << 4) | cz) << 18) | dirkey;            // 30 bits
+    vals[i] = k;
+}
+
+struct PhotonRaySource {     // one propagation step: rays of the photons in the queue
+    PropParams P;
+    uint32_t k_of[1];        // (unused; keeps the struct trivially copyable)
+    __device__ __forceinline__ bool load(unsigned long long q, float3& o, float3& d, int& last) const
+    {
+        const uint32_t k = P.queue_in ? P.queue_in[q] : (uint32_t)q;
+        const uint64_t id = P.first + k;
+        if (P.step == 0 && (P.bank.flags[id] & 0xFFFFu & CB_TERMINAL)) return false;   // never ran: untouched
+        o = ld3(P.bank.pos, id);
+        d = ld3(P.bank.dir, id);
+        if (P.step == 0) d = d / norm(d);
+        last = P.bank.last_hit_triangles[id];
+        return true;
+    }
+    __device__ __forceinline__ void store(unsigned long long q, int tri, float dist) const
+    {
+        const uint32_t k = P.queue_in ? P.queue_in[q] : (uint32_t)q;
+        P.hit_tri[k] = tri;
+        P.hit_dist[k] = dist;
+    }
+};
+
 template <bool COUNT>
 __global__ void __launch_bounds__(PROP_THREADS, 4)
 step_intersect_kernel(DevGeometry g, PropParams P)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint2* sstack = reinterpret_cast<uint2*>(smem_raw) + threadIdx.x;
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P.n_in) return;
-    const uint32_t k = P.queue_in ? P.queue_in[i] : i;
-    const uint64_t id = P.first + k;
-    if (P.step == 0 && (P.bank.flags[id] & 0xFFFFu & CB_TERMINAL)) return;   // never ran: untouched
-    float3 pos = ld3(P.bank.pos, id);
-    float3 dir = ld3(P.bank.dir, id);
-    if (P.step == 0) dir = dir / norm(dir);
-    TraverseCounters cnt = {0, 0, 0};
-    float dist;
-    const int tri = traverse<COUNT>(g, pos, dir, P.bank.last_hit_triangles[id], dist, sstack, PROP_THREADS,
-                                    (uint32_t*)(P.counters + 3), &cnt);
-    P.hit_tri[k] = tri;
-    P.hit_dist[k] = dist;
-    if (COUNT) {
-        atomicAdd(P.counters + 1, (unsigned long long)cnt.nodes);
-        atomicAdd(P.counters + 2, (unsigned long long)cnt.tris);
-        atomicAdd(P.counters + 5, (unsigned long long)cnt.resolved);
-    }
+    PhotonRaySource src;
+    src.P = P;
+    persistent_intersect<COUNT>(g, src, P.n_in, P.counters + 6, sstack, P.counters);
 }
 
 __global__ void __launch_bounds__(PROP_THREADS, 2)
@@ -611,9 +720,9 @@ int cb_intersect(cb_geom_t gh, const float* d_origins, const float* d_directions
     int per_sm = 0;
     CB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, intersect_kernel<false>, PROP_THREADS, smem));
     if (per_sm < 1) per_sm = 1;
-    unsigned blocks = (unsigned)std::min<uint64_t>((n + PROP_THREADS - 1) / PROP_THREADS, (uint64_t)c.sm_count * per_sm * 4);
-    intersect_kernel<false><<<blocks, PROP_THREADS, smem, c.stream>>>(g->dev, d_origins, d_directions, d_last_hit, n,
-                                                                     d_triangle_out, d_distance_out, c.d_counters);
+    unsigned blocks = (unsigned)std::min<uint64_t>((n + PROP_THREADS - 1) / PROP_THREADS, (uint64_t)c.sm_count * per_sm);
+    RaySource src = {d_origins, d_directions, d_last_hit, d_triangle_out, d_distance_out};
+    intersect_kernel<false><<<blocks, PROP_THREADS, smem, c.stream>>>(g->dev, src, n, c.d_counters);
     CB_CUDA(cudaGetLastError());
     CB_CUDA(cudaMemcpyAsync(c.h_counters, c.d_counters, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c.stream));
     CB_CUDA(cudaStreamSynchronize(c.stream));
@@ -649,8 +758,17 @@ int cb_propagate(const CbPhotonBank* bank, cb_geom_t gh, cb_rng_t rh, int32_t nt
         c.d_queue[0] = c.d_queue[1] = nullptr; c.d_hit_tri = nullptr; c.d_hit_dist = nullptr; c.scratch_cap = 0;
         CB_CUDA(cudaMalloc(&c.d_queue[0], cap * 4)); CB_CUDA(cudaMalloc(&c.d_queue[1], cap * 4));
         CB_CUDA(cudaMalloc(&c.d_hit_tri, cap * 4)); CB_CUDA(cudaMalloc(&c.d_hit_dist, cap * 4));
+        cudaFree(c.d_keys[0]); cudaFree(c.d_keys[1]); cudaFree(c.d_sorted); cudaFree(c.d_sort_tmp);
+        c.d_keys[0] = c.d_keys[1] = c.d_sorted = nullptr; c.d_sort_tmp = nullptr;
+        CB_CUDA(cudaMalloc(&c.d_keys[0], cap * 4)); CB_CUDA(cudaMalloc(&c.d_keys[1], cap * 4));
+        CB_CUDA(cudaMalloc(&c.d_sorted, cap * 4));
+        c.sort_tmp_bytes = 0;
+        CB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, c.sort_tmp_bytes, c.d_keys[0], c.d_keys[1], c.d_queue[0],
+                                                c.d_sorted, (int)cap, 0, 30, c.stream));
+        CB_CUDA(cudaMalloc(&c.d_sort_tmp, c.sort_tmp_bytes));
         c.scratch_cap = cap;
     }
+    static const uint64_t sort_threshold = getenv("CHROMA_B200_SORT") ? (uint64_t)atoll(getenv("CHROMA_B200_SORT")) : 0;
 
     auto k_int = count ? step_intersect_kernel<true> : step_intersect_kernel<false>;
     auto k_tail = count ? propagate_tail_kernel<true> : propagate_tail_kernel<false>;
@@ -660,7 +778,9 @@ int cb_propagate(const CbPhotonBank* bank, cb_geom_t gh, cb_rng_t rh, int32_t nt
     CB_CUDA(cudaFuncSetAttribute(k_int, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_int));
     CB_CUDA(cudaFuncSetAttribute(step_physics_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_tab, 16)));
     CB_CUDA(cudaFuncSetAttribute(k_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tail));
-    int phys_per_sm = 0, tail_per_sm = 0;
+    int phys_per_sm = 0, tail_per_sm = 0, int_per_sm = 0;
+    CB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&int_per_sm, k_int, PROP_THREADS, smem_int));
+    if (int_per_sm < 1) int_per_sm = 1;
     CB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&phys_per_sm, step_physics_kernel, PROP_THREADS, smem_tab));
     CB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tail_per_sm, k_tail, PROP_THREADS, smem_tail));
     if (phys_per_sm < 1 || tail_per_sm < 1) return fail(CB_ERR_CUDA, "cb_propagate: kernels do not fit on an SM");
@@ -694,13 +814,25 @@ int cb_propagate(const CbPhotonBank* bank, cb_geom_t gh, cb_rng_t rh, int32_t nt
                 break;
             }
             unsigned blocks = (unsigned)((n_alive + PROP_THREADS - 1) / PROP_THREADS);
-            k_int<<<blocks, PROP_THREADS, smem_int, c.stream>>>(g->dev, P);
+            if (sort_threshold && n_alive >= sort_threshold) {
+                // regroup the queue so that warps hold rays of similar origin and direction
+                uint32_t* unsorted_vals = c.d_queue[qsel];         // free until the physics kernel writes it
+                ray_key_kernel<<<(unsigned)((n_alive + 255) / 256), 256, 0, c.stream>>>(g->dev, P, c.d_keys[0], unsorted_vals);
+                size_t tmp = c.sort_tmp_bytes;
+                CB_CUDA(cub::DeviceRadixSort::SortPairs(c.d_sort_tmp, tmp, c.d_keys[0], c.d_keys[1], unsorted_vals,
+                                                        c.d_sorted, (int)n_alive, 0, 30, c.stream));
+                P.queue_in = c.d_sorted;
+                launches += 2;
+            }
+            unsigned iblocks = (unsigned)std::min<uint64_t>(blocks, (uint64_t)c.sm_count * int_per_sm);
+            k_int<<<iblocks, PROP_THREADS, smem_int, c.stream>>>(g->dev, P);
             unsigned pblocks = (unsigned)std::min<uint64_t>(blocks, (uint64_t)c.sm_count * phys_per_sm);
             step_physics_kernel<<<pblocks, PROP_THREADS, smem_tab, c.stream>>>(g->dev, P);
             CB_CUDA(cudaGetLastError());
             launches += 2;
             CB_CUDA(cudaMemcpyAsync(c.h_counters, c.d_counters, 8, cudaMemcpyDeviceToHost, c.stream));
             CB_CUDA(cudaMemsetAsync(c.d_counters, 0, 8, c.stream));
+            CB_CUDA(cudaMemsetAsync(c.d_counters + 6, 0, 8, c.stream));
             CB_CUDA(cudaStreamSynchronize(c.stream));
             tot[4] += n_alive;                       // every queued photon took one step
             n_alive = c.h_counters[0];
