@@ -266,25 +266,37 @@ def run_ours(args):
     total_photons = sum_over_ranks(float(n * args.steps), world)
     value = total_photons / dev_s
 
-    # ---- e2e through the public API: host arrays in, hits + channels out
+    # ---- e2e through the public API: K events as HOST arrays in, flat hits + DAQ channels
+    # out (Simulation.simulate, batches double-buffered), then ONE reduction of the
+    # run-level per-channel hit counts / charge across ranks
+    import torch
     h2d = sum(getattr(ev, f).nbytes for f in ('pos', 'dir', 'pol', 'wavelengths', 't', 'flags', 'evidx'))
-    d2h = 0
-    for _ in range(2):
-        list(s.simulate([ev], keep_hits=False, keep_flat_hits=True, run_daq=True, max_steps=MAX_STEPS,
-                        photons_per_batch=n))
+    sim_kw = dict(keep_hits=False, keep_flat_hits=True, run_daq=True, max_steps=MAX_STEPS, photons_per_batch=n)
+    list(s.simulate((event.Event(photons_beg=ev) for _ in range(2)), **sim_kw))
+    nch = s.gpu_geometry.nchannels
     barrier(world)
+    _lib.check(lib.cb_synchronize())
     t0 = time.perf_counter()
-    for k in range(args.steps):
-        out = list(s.simulate([ev], keep_hits=False, keep_flat_hits=True, run_daq=True, max_steps=MAX_STEPS,
-                              photons_per_batch=n))
-        if world > 1:
-            parallel.reduce_daq(s.gpu_daq, dst=0)
+    hit_count = np.zeros(nch, dtype=np.int64)
+    charge = np.zeros(nch, dtype=np.float64)
+    d2h = 0
+    for out_ev in s.simulate((event.Event(photons_beg=ev) for _ in range(args.steps)), **sim_kw):
+        hit_count += out_ev.channels.hit
+        charge += np.where(out_ev.channels.hit, out_ev.channels.q, 0.0)
+        fh = out_ev.flat_hits
+        d2h = sum(getattr(fh, f).nbytes for f in fields) + fh.channel.nbytes + 3 * 4 * nch
+    if world > 1:
+        import torch.distributed as dist
+        buf = torch.from_numpy(np.concatenate([hit_count.astype(np.float64), charge])).cuda()
+        dist.reduce(buf, dst=0, op=dist.ReduceOp.SUM)
+        torch.cuda.synchronize()
     _lib.check(lib.cb_synchronize())
     barrier(world)
     e2e_s = max_over_ranks(time.perf_counter() - t0, world)
-    fh = out[0].flat_hits
-    d2h = sum(getattr(fh, f).nbytes for f in fields) + fh.channel.nbytes + 3 * 4 * s.gpu_geometry.nchannels
     e2e = total_photons / e2e_s
+    timings['e2e_last_batch'] = dict(s.last_timings)
+    timings['e2e_s_per_event'] = e2e_s / args.steps
+    timings['e2e_hits_per_event'] = int(len(fh))
 
     if rank != 0:
         return
@@ -352,9 +364,15 @@ def run_reference(args):
     rng = ref_driver.RefRNG(512 * 1024, seed=42)        # Simulation defaults (chroma/sim.py:23-24,50)
     sampler = ClockSampler(0)
 
+    rg.attach_detector(det)
+
     def one_step():
+        # chroma/sim.py:54-154 for one event: upload, propagate, flat hits, DAQ, channels
         rp = ref_driver.RefPhotons(ev)
-        return rp, rp.propagate(rg, rng, nthreads_per_block=512, max_blocks=1024, max_steps=MAX_STEPS)
+        r = rp.propagate(rg, rng, nthreads_per_block=512, max_blocks=1024, max_steps=MAX_STEPS)
+        hits = rp.get_flat_hits(rg)
+        ch = ref_driver.run_daq(rg, rp, rng, nthreads_per_block=512, max_blocks=1024)
+        return rp, r, hits, ch
 
     for _ in range(args.warmup):
         one_step()
@@ -364,12 +382,12 @@ def run_reference(args):
     for _ in range(args.steps):
         ref_driver.sync()
         t0 = time.perf_counter()
-        rp, r = one_step()
-        out = rp.get()
+        rp, r, hits, ch = one_step()
         ref_driver.sync()
         t_e2e += time.perf_counter() - t0
         ms += r['ms']
         launches += r['launches']
+    out = rp.get()
     clocks = sampler.stop()
     value = n * args.steps / (ms / 1e3)
     e2e = n * args.steps / t_e2e

@@ -94,7 +94,7 @@ struct DevGeometry {
     const uint4*  nodes;      // the engine's traversal tree (reference packing, children contiguous)
     const uint4*  ref_nodes;  // the reference tree itself: visit-order fallback only
     uint32_t ref_root_w;
-    const float4* tri48;      // 3 x float4 per triangle: v0.xyz v1.x | v1.yz v2.xy | v2.z rank code pad
+    const float4* tri64;      // 4 x float4 per triangle: v0.xyz v1.x | v1.yz v2.xy | v2.z rank code - | reference leaf box xyz -
     const float*  tables;     // global table pool
     const CbMaterial* materials;
     const CbSurface*  surfaces;
@@ -104,6 +104,7 @@ struct DevGeometry {
     int32_t time_n;       float time_start, time_step;
     uint32_t root_w;          // root node's child word
     uint32_t root_x, root_y, root_z;  // root node's packed box
+    uint32_t ref_root_x, ref_root_y, ref_root_z;   // the reference tree's root box
     uint32_t smem_floats;     // leading floats of the pool staged into shared memory
     uint32_t nmaterials, nsurfaces;
 };
@@ -209,6 +210,62 @@ __device__ __forceinline__ bool hit_box(const DevGeometry& g, const RaySetup& r,
     return !(tmin > tmax);
 }
 
+// Traversal-side box test.  Same boxes, cheaper arithmetic: per ray the affine map
+// t = q*(scale/d) + (world_origin - o)/d is folded into one FFMA per plane, the
+// uint16 -> float conversion is an integer multiply-add into the mantissa of 2^16
+// (exact), and the near/far plane of each axis is picked by the sign of d with one
+// byte-permute, so no min/max per axis is needed.  It differs from the reference's
+// arithmetic by rounding only (the guard band of traverse() covers that); the
+// reference-exact hit_box() above is still what decides order-sensitivity.
+struct FastRay {
+    float sx, sy, sz;          // world_scale / d
+    float nx, ny, nz;          // offset for the near planes  (-inf when the axis is ignored)
+    float fx, fy, fz;          // offset for the far planes   (+inf when the axis is ignored)
+    uint32_t selx, sely, selz; // byte-permute selectors: low half = near plane, high half = far plane
+};
+__device__ __forceinline__ void fast_ray_axis(float o, float d, float worigin, float wscale, float& s, float& n, float& f, uint32_t& sel)
+{
+    const float INF = __int_as_float(0x7f800000);
+    const float inv = 1.0f / d;
+    if (isfinite(inv)) {
+        s = wscale * inv;
+        const float off = (worigin - o) * inv - 65536.0f * s;   // the conversion below yields 65536 + q
+        n = off; f = off;
+        sel = (inv >= 0.0f) ? 0x3210u : 0x1032u;                // swap halves when the ray runs towards -axis
+    } else {                                                   // the reference skips such an axis (intersect.h:120)
+        s = 0.0f; n = -INF; f = INF; sel = 0x3210u;
+    }
+}
+__device__ __forceinline__ float q16f_lo(uint32_t w) { return __uint_as_float((w & 0xFFFFu) * 128u + 0x47800000u); }
+__device__ __forceinline__ float q16f_hi(uint32_t w) { return __uint_as_float((w >> 16) * 128u + 0x47800000u); }
+// slab test in the reference's arithmetic, recomputing the ray setup (rare path)
+static __device__ __noinline__ bool hit_box_exact(const DevGeometry& g, const float3& o, const float3& d,
+                                                  uint32_t px, uint32_t py, uint32_t pz, float& tnear)
+{
+    RaySetup rr;
+    rr.noid = f3(-o.x / d.x, -o.y / d.y, -o.z / d.z);
+    rr.inv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    rr.fx = isfinite(rr.inv.x); rr.fy = isfinite(rr.inv.y); rr.fz = isfinite(rr.inv.z);
+    return hit_box(g, rr, px, py, pz, tnear);
+}
+
+// Three-way result: clearly missed / clearly hit by more than the rounding bound
+// `eps` of this ray / marginal (caller re-decides with hit_box_exact, so the engine
+// never accepts or rejects a box the reference's arithmetic would judge otherwise).
+__device__ __forceinline__ int hit_box_fast(const FastRay& r, float eps, uint32_t px, uint32_t py, uint32_t pz, float& tnear)
+{
+    const uint32_t ax = __byte_perm(px, 0, r.selx), ay = __byte_perm(py, 0, r.sely), az = __byte_perm(pz, 0, r.selz);
+    const float tnx = __fmaf_rn(q16f_lo(ax), r.sx, r.nx), tfx = __fmaf_rn(q16f_hi(ax), r.sx, r.fx);
+    const float tny = __fmaf_rn(q16f_lo(ay), r.sy, r.ny), tfy = __fmaf_rn(q16f_hi(ay), r.sy, r.fy);
+    const float tnz = __fmaf_rn(q16f_lo(az), r.sz, r.nz), tfz = __fmaf_rn(q16f_hi(az), r.sz, r.fz);
+    const float tmin = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.0f));
+    const float tmax = fminf(fminf(tfx, tfy), tfz);
+    tnear = tmin;
+    if (tmin > tmax + eps) return 0;      // miss
+    if (tmin + eps <= tmax) return 1;     // hit
+    return 2;                             // marginal
+}
+
 // ------------------------------------------------------------------ traversal
 constexpr int CB_SSTACK = 16;   // stack entries per lane in shared memory (lane-interleaved)
 constexpr int CB_LSTACK = 48;   // overflow entries per lane in local memory (rarely touched)
@@ -250,7 +307,7 @@ static __device__ __noinline__ int traverse_reference_order(const DevGeometry& g
                 if ((w >> 28) == 0) {
                     if ((int)w != last_hit) {
                         if (COUNT) cnt->tris++;
-                        const float4* tp = g.tri48 + 3ull * w;
+                        const float4* tp = g.tri64 + 4ull * w;
                         float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
                         float t;
                         if (hit_triangle(origin, direction, f3(a.x, a.y, a.z), f3(a.w, b.x, b.y), f3(b.z, b.w, c.x), t)) {
@@ -295,8 +352,8 @@ static __device__ __noinline__ int traverse_reference_order(const DevGeometry& g
 // (~1e-7) are redone in the reference's own visit order on the reference tree.
 struct Trav {
     float3 origin, direction;
-    RaySetup r;
-    float best_t, limit, guard_abs, cur_t, best_box_t;
+    FastRay r;
+    float best_t, limit, eps, cur_t;
     uint32_t best_rank, cur;
     int best_tri, last_hit, sp;
     bool have, redo;
@@ -322,19 +379,26 @@ struct Trav {
     {
         const float INF = __int_as_float(0x7f800000);
         origin = o; direction = d; last_hit = last;
-        r.noid = f3(-o.x / d.x, -o.y / d.y, -o.z / d.z);
-        r.inv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
-        r.fx = isfinite(r.inv.x); r.fy = isfinite(r.inv.y); r.fz = isfinite(r.inv.z);
-        best_tri = -1; best_rank = 0xFFFFFFFFu; best_t = INF; limit = INF; best_box_t = 0.0f;
+        fast_ray_axis(o.x, d.x, g.world_origin.x, g.world_scale, r.sx, r.nx, r.fx, r.selx);
+        fast_ray_axis(o.y, d.y, g.world_origin.y, g.world_scale, r.sy, r.ny, r.fy, r.sely);
+        fast_ray_axis(o.z, d.z, g.world_origin.z, g.world_scale, r.sz, r.nz, r.fz, r.selz);
+        best_tri = -1; best_rank = 0xFFFFFFFFu; best_t = INF; limit = INF;
         sp = 0; cur = g.root_w; cur_t = 0.0f; redo = false;
+        // the world-box test itself stays in the reference's arithmetic (mesh.h:60)
+        RaySetup rr;
+        rr.noid = f3(-o.x / d.x, -o.y / d.y, -o.z / d.z);
+        rr.inv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+        rr.fx = isfinite(rr.inv.x); rr.fy = isfinite(rr.inv.y); rr.fz = isfinite(rr.inv.z);
         float tn;
-        have = hit_box(g, r, g.root_x, g.root_y, g.root_z, tn) && (g.root_w >> 28) != 0;
-        // rounding scale of the slab arithmetic: |o/d| of the finite axes
+        have = hit_box(g, rr, g.ref_root_x, g.ref_root_y, g.ref_root_z, tn) && (g.root_w >> 28) != 0;
+        // rounding bound of the slab arithmetic (fast and reference alike): a few ulps
+        // of the largest |coordinate / d| that enters the affine maps
+        const float extent = 2.0f * 65535.0f * g.world_scale;
         float mag = 0.0f;
-        if (r.fx) mag = fmaxf(mag, fabsf(r.noid.x));
-        if (r.fy) mag = fmaxf(mag, fabsf(r.noid.y));
-        if (r.fz) mag = fmaxf(mag, fabsf(r.noid.z));
-        guard_abs = 1e-5f * mag;
+        if (rr.fx) mag = fmaxf(mag, fabsf(rr.inv.x));
+        if (rr.fy) mag = fmaxf(mag, fabsf(rr.inv.y));
+        if (rr.fz) mag = fmaxf(mag, fabsf(rr.inv.z));
+        eps = 5e-7f * extent * mag;
         return have;
     }
 
@@ -356,8 +420,13 @@ struct Trav {
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
                     float tmin;
-                    const bool ok = (i + k < n) && hit_box(g, r, nd[k].x, nd[k].y, nd[k].z, tmin) && !(tmin > limit);
-                    if (COUNT && i + k < n) cnt->nodes++;
+                    bool ok = false;
+                    if (i + k < n) {
+                        const int h = hit_box_fast(r, eps, nd[k].x, nd[k].y, nd[k].z, tmin);
+                        ok = (h == 1) || (h == 2 && hit_box_exact(g, origin, direction, nd[k].x, nd[k].y, nd[k].z, tmin));
+                        ok = ok && !(tmin > limit);
+                        if (COUNT) cnt->nodes++;
+                    }
                     if (ok) {
                         uint32_t w = nd[k].w;
                         if (!near_ok || tmin < near_t) {          // new nearest: the old one goes to the stack
@@ -378,14 +447,14 @@ struct Trav {
         while (have && (cur >> 28) == 0) {
             if ((int)cur != last_hit) {
                 if (COUNT) cnt->tris++;
-                const float4* tp = g.tri48 + 3ull * cur;
+                const float4* tp = g.tri64 + 4ull * cur;
                 const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
                 float t;
                 if (hit_triangle(origin, direction, f3(a.x, a.y, a.z), f3(a.w, b.x, b.y), f3(b.z, b.w, c.x), t)) {
                     const uint32_t rank = __float_as_uint(c.y);
                     if (t < best_t || (t == best_t && rank < best_rank)) {
-                        best_t = t; best_tri = (int)cur; best_rank = rank; best_box_t = cur_t;
-                        limit = best_t + (1e-5f * best_t + guard_abs);
+                        best_t = t; best_tri = (int)cur; best_rank = rank;
+                        limit = best_t + (2e-5f * best_t + 2.0f * eps);
                     }
                 }
             }
@@ -397,7 +466,19 @@ struct Trav {
     template <bool COUNT>
     __device__ __forceinline__ int finish(const DevGeometry& g, float& dist, uint32_t* overflow_flag, TraverseCounters* cnt)
     {
-        if (redo || (best_tri != -1 && best_t < best_box_t)) {
+        if (best_tri != -1 && !redo) {
+            // order-sensitivity test on the winner, in the reference's own arithmetic:
+            // is the hit in front of the reference's leaf box of that triangle?
+            const float4 lb = __ldg(g.tri64 + 4ull * (uint32_t)best_tri + 3);
+            RaySetup rr;
+            rr.noid = f3(-origin.x / direction.x, -origin.y / direction.y, -origin.z / direction.z);
+            rr.inv = f3(1.0f / direction.x, 1.0f / direction.y, 1.0f / direction.z);
+            rr.fx = isfinite(rr.inv.x); rr.fy = isfinite(rr.inv.y); rr.fz = isfinite(rr.inv.z);
+            float box_t;
+            const bool in_box = hit_box(g, rr, __float_as_uint(lb.x), __float_as_uint(lb.y), __float_as_uint(lb.z), box_t);
+            redo = !in_box || best_t < box_t;
+        }
+        if (redo) {
             if (COUNT) cnt->resolved++;
             return traverse_reference_order<COUNT>(g, origin, direction, last_hit, dist, overflow_flag, cnt);
         }
@@ -500,7 +581,7 @@ __device__ __forceinline__ void classify_hit(const DevGeometry& g, const Tables&
                                              StepState& s, int tri)
 {
     p.last_hit_triangle = tri;
-    const float4* tp = g.tri48 + 3ull * (uint32_t)tri;
+    const float4* tp = g.tri64 + 4ull * (uint32_t)tri;
     float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
     float3 v0 = f3(a.x, a.y, a.z), v1 = f3(a.w, b.x, b.y), v2 = f3(b.z, b.w, c.x);
     uint32_t material_code = __float_as_uint(c.z);

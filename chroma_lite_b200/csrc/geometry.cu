@@ -11,22 +11,25 @@ namespace cb {
 struct Entry { uint32_t x, y, z, w; };
 int build_native_tree(std::vector<Entry>& leaves, const uint32_t* solid_of, std::vector<Entry>& nodes);
 
-// Pack triangles for the traversal: 48 B = 3 x float4 per triangle holding the
-// three world-space vertices, the reference test rank (tie-break, SURVEY A-1)
-// and the material code, so a leaf test is three coalescable 128-bit loads
-// instead of an index fetch + three scattered 12-byte gathers.
+// Pack triangles for the traversal: 64 B = 4 x float4 per triangle holding the
+// three world-space vertices, the reference test rank (tie-break, SURVEY A-1),
+// the material code and the triangle's reference leaf box, so a leaf test is
+// three 128-bit loads from two 32-byte sectors instead of an index fetch + three
+// scattered 12-byte gathers.
 __global__ void __launch_bounds__(256)
 pack_triangles_kernel(const float* __restrict__ vertices, const uint32_t* __restrict__ triangles,
                       const uint32_t* __restrict__ material_codes, const uint32_t* __restrict__ rank,
-                      uint64_t ntriangles, float4* __restrict__ tri48)
+                      const uint32_t* __restrict__ leafbox, uint64_t ntriangles, float4* __restrict__ tri64)
 {
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= ntriangles) return;
     uint32_t i0 = triangles[3 * t], i1 = triangles[3 * t + 1], i2 = triangles[3 * t + 2];
     float3 v0 = ld3(vertices, i0), v1 = ld3(vertices, i1), v2 = ld3(vertices, i2);
-    tri48[3 * t + 0] = make_float4(v0.x, v0.y, v0.z, v1.x);
-    tri48[3 * t + 1] = make_float4(v1.y, v1.z, v2.x, v2.y);
-    tri48[3 * t + 2] = make_float4(v2.z, __uint_as_float(rank[t]), __uint_as_float(material_codes[t]), 0.0f);
+    tri64[4 * t + 0] = make_float4(v0.x, v0.y, v0.z, v1.x);
+    tri64[4 * t + 1] = make_float4(v1.y, v1.z, v2.x, v2.y);
+    tri64[4 * t + 2] = make_float4(v2.z, __uint_as_float(rank[t]), __uint_as_float(material_codes[t]), 0.0f);
+    tri64[4 * t + 3] = make_float4(__uint_as_float(leafbox[3 * t]), __uint_as_float(leafbox[3 * t + 1]),
+                                   __uint_as_float(leafbox[3 * t + 2]), 0.0f);
 }
 
 // Position at which the reference traversal (mesh.h:75-117) would test each
@@ -88,7 +91,7 @@ static int upload(T** dst, const T* src, uint64_t count, uint64_t& total)
 static void free_geometry(Geometry* g)
 {
     cudaFree(g->vertices); cudaFree(g->triangles); cudaFree(g->material_codes); cudaFree(g->colors);
-    cudaFree(g->solid_id); cudaFree(g->nodes); cudaFree(g->native_nodes); cudaFree(g->tri48); cudaFree(g->tables);
+    cudaFree(g->solid_id); cudaFree(g->nodes); cudaFree(g->native_nodes); cudaFree(g->tri64); cudaFree(g->tables);
     cudaFree(g->materials); cudaFree(g->surfaces); cudaFree(g->solid_to_channel);
     cudaFree(g->time_cdf_x); cudaFree(g->time_cdf_y); cudaFree(g->charge_cdf_x); cudaFree(g->charge_cdf_y);
     delete g;
@@ -153,19 +156,34 @@ int cb_geometry_create(const CbGeometryDesc* d, cb_geom_t* out)
     std::vector<uint32_t> rank;
     reference_test_rank(d->nodes, d->nnodes, d->ntriangles, rank);
     uint32_t* d_rank = nullptr;
+    uint32_t* d_leafbox = nullptr;
     uint64_t scratch = 0;
     if ((rc = upload(&d_rank, rank.data(), d->ntriangles, scratch)) != CB_OK) { free_geometry(g); return rc; }
     {
-        cudaError_t e = cudaMalloc((void**)&g->tri48, std::max<uint64_t>(d->ntriangles, 1) * 48);
-        if (e != cudaSuccess) { cudaFree(d_rank); free_geometry(g); return cuda_fail(e, "cudaMalloc(tri48)"); }
-        total += d->ntriangles * 48;
+        // reference leaf box of every triangle (first reachable leaf entry)
+        std::vector<uint32_t> leafbox(3 * std::max<uint64_t>(d->ntriangles, 1), 0u);
+        std::vector<uint8_t> seen(d->ntriangles, 0);
+        for (uint64_t i = 0; i < d->nnodes; i++) {
+            const uint32_t w = d->nodes[4 * i + 3];
+            if ((w >> 28) == 0 && w < d->ntriangles && !seen[w]) {
+                seen[w] = 1;
+                leafbox[3ull * w] = d->nodes[4 * i]; leafbox[3ull * w + 1] = d->nodes[4 * i + 1]; leafbox[3ull * w + 2] = d->nodes[4 * i + 2];
+            }
+        }
+        if ((rc = upload(&d_leafbox, leafbox.data(), 3 * d->ntriangles, scratch)) != CB_OK) { cudaFree(d_rank); free_geometry(g); return rc; }
+    }
+    {
+        cudaError_t e = cudaMalloc((void**)&g->tri64, std::max<uint64_t>(d->ntriangles, 1) * 64);
+        if (e != cudaSuccess) { cudaFree(d_rank); cudaFree(d_leafbox); free_geometry(g); return cuda_fail(e, "cudaMalloc(tri64)"); }
+        total += d->ntriangles * 64;
         if (d->ntriangles) {
             pack_triangles_kernel<<<(unsigned)((d->ntriangles + 255) / 256), 256, 0, ctx().stream>>>(
-                g->vertices, g->triangles, g->material_codes, d_rank, d->ntriangles, g->tri48);
+                g->vertices, g->triangles, g->material_codes, d_rank, d_leafbox, d->ntriangles, g->tri64);
             e = cudaStreamSynchronize(ctx().stream);
-            if (e != cudaSuccess) { cudaFree(d_rank); free_geometry(g); return cuda_fail(e, "pack_triangles"); }
+            if (e != cudaSuccess) { cudaFree(d_rank); cudaFree(d_leafbox); free_geometry(g); return cuda_fail(e, "pack_triangles"); }
         }
         cudaFree(d_rank);
+        cudaFree(d_leafbox);
     }
 
     // the engine's own traversal tree over the reference's leaves (bvh_native.cu)
@@ -188,7 +206,7 @@ int cb_geometry_create(const CbGeometryDesc* d, cb_geom_t* out)
     }
 
     DevGeometry& v = g->dev;
-    v.nodes = g->native_nodes ? g->native_nodes : g->nodes; v.tri48 = g->tri48; v.tables = g->tables;
+    v.nodes = g->native_nodes ? g->native_nodes : g->nodes; v.tri64 = g->tri64; v.tables = g->tables;
     v.ref_nodes = g->nodes; v.ref_root_w = d->nodes[3];
     v.materials = g->materials; v.surfaces = g->surfaces;
     v.world_origin = make_float3(d->world_origin[0], d->world_origin[1], d->world_origin[2]);
@@ -196,6 +214,7 @@ int cb_geometry_create(const CbGeometryDesc* d, cb_geom_t* out)
     v.wavelength_n = d->wavelength_n; v.wavelength_start = d->wavelength_start; v.wavelength_step = d->wavelength_step;
     v.time_n = d->time_n; v.time_start = d->time_start; v.time_step = d->time_step;
     v.root_x = root_entry[0]; v.root_y = root_entry[1]; v.root_z = root_entry[2]; v.root_w = root_entry[3];
+    v.ref_root_x = d->nodes[0]; v.ref_root_y = d->nodes[1]; v.ref_root_z = d->nodes[2];
     v.nmaterials = d->nmaterials; v.nsurfaces = d->nsurfaces;
     // stage the leading part of the pool (the wavelength tables; the host lays
     // the long time CDFs out last) into shared memory, up to 48 KB

@@ -18,7 +18,8 @@ struct Context {
     int sm_count = 0;
     size_t l2_bytes = 0;
     int max_smem_optin = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;        // kernels
+    cudaStream_t copy_stream = nullptr;   // host<->device copies, bank initialisation
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;      // cb_timer_*
     cudaEvent_t kev0 = nullptr, kev1 = nullptr;    // per-call kernel timing
     void* flush_buf = nullptr; size_t flush_bytes = 0;
@@ -53,7 +54,7 @@ struct Geometry {
     uint32_t* colors = nullptr; uint32_t* solid_id = nullptr; uint4* nodes = nullptr;
     // native
     uint4* native_nodes = nullptr; uint64_t nnative = 0;   // engine-built traversal tree
-    float4* tri48 = nullptr; float* tables = nullptr; CbMaterial* materials = nullptr; CbSurface* surfaces = nullptr;
+    float4* tri64 = nullptr; float* tables = nullptr; CbMaterial* materials = nullptr; CbSurface* surfaces = nullptr;
     uint64_t nvertices = 0, ntriangles = 0, nnodes = 0, table_floats = 0;
     // detector
     int32_t* solid_to_channel = nullptr; uint64_t nsolids = 0; int32_t nchannels = 0;

@@ -749,7 +749,8 @@ int cb_propagate(const CbPhotonBank* bank, cb_geom_t gh, cb_rng_t rh, int32_t nt
     if (bank->n == 0 || max_steps <= 0) return CB_OK;
     Context& c = ctx();
     const bool count = getenv("CHROMA_B200_STATS") != nullptr;
-    static const uint64_t tail_threshold = getenv("CHROMA_B200_TAIL") ? (uint64_t)atoll(getenv("CHROMA_B200_TAIL")) : 16384;
+    // hand the rest to the persistent kernel once the survivors fit on the chip ~1.3 times over
+    static const uint64_t tail_threshold = getenv("CHROMA_B200_TAIL") ? (uint64_t)atoll(getenv("CHROMA_B200_TAIL")) : (uint64_t)(1.3 * 2048 * ctx().sm_count);
 
     // scratch: two queues + hit arrays, sized for one chunk
     const uint64_t cap = std::min<uint64_t>(pool, bank->n);

@@ -182,6 +182,7 @@ int cb_init(int device)
     c.l2_bytes = (size_t)prop.l2CacheSize;
     c.max_smem_optin = (int)prop.sharedMemPerBlockOptin;
     CB_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    CB_CUDA(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
     CB_CUDA(cudaEventCreate(&c.ev0)); CB_CUDA(cudaEventCreate(&c.ev1));
     CB_CUDA(cudaEventCreate(&c.kev0)); CB_CUDA(cudaEventCreate(&c.kev1));
     CB_CUDA(cudaMalloc(&c.d_counters, 16 * sizeof(unsigned long long)));
@@ -218,32 +219,33 @@ int cb_free(void* dptr)
 {
     if (!dptr) return CB_OK;
     CB_REQUIRE_INIT();
-    CB_CUDA(cudaStreamSynchronize(ctx().stream));
-    CB_CUDA(cudaFree(dptr));
+    CB_CUDA(cudaFree(dptr));          // cudaFree itself waits for work that uses the block
     return CB_OK;
 }
 int cb_memcpy_h2d(void* d, const void* h, uint64_t bytes)
 {
     CB_REQUIRE_INIT();
     if (bytes == 0) return CB_OK;
-    CB_CUDA(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, ctx().stream));
-    CB_CUDA(cudaStreamSynchronize(ctx().stream));
+    // host<->device copies run on their own stream so that an upload issued from a
+    // second host thread overlaps the kernels of a propagate call in flight
+    CB_CUDA(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, ctx().copy_stream));
+    CB_CUDA(cudaStreamSynchronize(ctx().copy_stream));
     return CB_OK;
 }
 int cb_memcpy_d2h(void* h, const void* d, uint64_t bytes)
 {
     CB_REQUIRE_INIT();
     if (bytes == 0) return CB_OK;
-    CB_CUDA(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, ctx().stream));
-    CB_CUDA(cudaStreamSynchronize(ctx().stream));
+    CB_CUDA(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, ctx().copy_stream));
+    CB_CUDA(cudaStreamSynchronize(ctx().copy_stream));
     return CB_OK;
 }
 int cb_memcpy_d2d(void* dst, const void* src, uint64_t bytes)
 {
     CB_REQUIRE_INIT();
     if (bytes == 0) return CB_OK;
-    CB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx().stream));
-    CB_CUDA(cudaStreamSynchronize(ctx().stream));
+    CB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx().copy_stream));
+    CB_CUDA(cudaStreamSynchronize(ctx().copy_stream));
     return CB_OK;
 }
 int cb_memset32(void* dptr, uint32_t value, uint64_t count)
@@ -251,9 +253,9 @@ int cb_memset32(void* dptr, uint32_t value, uint64_t count)
     CB_REQUIRE_INIT();
     if (count == 0) return CB_OK;
     int blocks = (int)std::min<uint64_t>((count + 255) / 256, (uint64_t)ctx().sm_count * 16);
-    fill32_kernel<<<blocks, 256, 0, ctx().stream>>>((uint32_t*)dptr, value, count);
+    fill32_kernel<<<blocks, 256, 0, ctx().copy_stream>>>((uint32_t*)dptr, value, count);
     CB_CUDA(cudaGetLastError());
-    CB_CUDA(cudaStreamSynchronize(ctx().stream));
+    CB_CUDA(cudaStreamSynchronize(ctx().copy_stream));
     return CB_OK;
 }
 int cb_host_alloc(uint64_t bytes, void** hptr)

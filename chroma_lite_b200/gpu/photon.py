@@ -113,6 +113,8 @@ class GPUPhotons(object):
                       start_photon=None, nphotons=None, no_map=False):
         """Photons with ``target_flag`` set that ended on a triangle of a solid mapped
         to a channel; ``.channel`` holds the channel index (gpu/photon.py:141-209)."""
+        import time as _time
+        _t0 = _time.perf_counter()
         lib = _lib.lib()
         start_photon = 0 if start_photon is None else start_photon
         nphotons = self.pos.size - start_photon if nphotons is None else nphotons
@@ -132,7 +134,9 @@ class GPUPhotons(object):
             _lib.check(lib.cb_copy_photon_hits(C.byref(src), int(start_photon), int(nphotons), int(target_flag),
                                                gpu_detector.handle, C.byref(dst), channels.ptr, C.byref(c2)))
             assert c2.value == n
+        _t1 = _time.perf_counter()
         g = lambda a: a.get()
+        self.last_hit_timings = (_t1 - _t0,)
         return event.Photons(g(out['pos']).view(np.float32).reshape((n, 3)), g(out['dir']).view(np.float32).reshape((n, 3)),
                              g(out['pol']).view(np.float32).reshape((n, 3)), g(out['wavelengths']), g(out['t']),
                              g(out['last_hit_triangles']), g(out['flags']), g(out['weights']), g(out['evidx']),

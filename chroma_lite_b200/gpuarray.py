@@ -5,6 +5,7 @@ Covers what the reference's hot-path host code uses from pycuda.gpuarray
 .gpudata/.size/.dtype/.nbytes/len and contiguous 1-D slicing.
 """
 import ctypes as C
+import threading
 import numpy as np
 
 from . import _lib
@@ -24,18 +25,77 @@ class vec(object):
         return a
 
 
+class _Pool(object):
+    """Size-bucketed cache of freed device blocks (cudaMalloc/cudaFree cost
+    milliseconds and synchronise; a simulation allocates the same bank sizes for
+    every batch).  Blocks are rounded up to a power of two below 16 MiB (hit lists
+    change size from event to event) and to 2 MiB multiples above."""
+    LIMIT = 16 << 30
+
+    def __init__(self):
+        self.free, self.cached, self.lock = {}, 0, threading.Lock()
+
+    @staticmethod
+    def bucket(nbytes):
+        n = max(int(nbytes), 256)
+        if n <= (16 << 20):
+            return 1 << (n - 1).bit_length()
+        g = 2 << 20
+        return (n + g - 1) // g * g
+
+    def take(self, size):
+        with self.lock:
+            lst = self.free.get(size)
+            if lst:
+                self.cached -= size
+                return lst.pop()
+        return None
+
+    def give(self, ptr, size):
+        with self.lock:
+            if self.cached + size <= self.LIMIT:
+                self.free.setdefault(size, []).append(ptr)
+                self.cached += size
+                return True
+        return False
+
+    def release_all(self):
+        with self.lock:
+            blocks = [p for lst in self.free.values() for p in lst]
+            self.free, self.cached = {}, 0
+        for p in blocks:
+            _lib._lib.cb_free(C.c_void_p(p))
+
+
+_pool = _Pool()
+
+
+def empty_cache():
+    """Return every cached device block to the driver."""
+    if _lib._lib is not None:
+        _pool.release_all()
+
+
 class _Allocation(object):
-    """Owns one device allocation; freed when the last view goes away."""
+    """Owns one device allocation; goes back to the pool when the last view dies."""
     def __init__(self, nbytes):
-        p = C.c_void_p()
-        _lib.check(_lib.lib().cb_malloc(int(nbytes), C.byref(p)))
-        self.ptr = p.value
+        self.size = _Pool.bucket(nbytes)
+        ptr = _pool.take(self.size)
+        if ptr is None:
+            p = C.c_void_p()
+            rc = _lib.lib().cb_malloc(self.size, C.byref(p))
+            if rc != 0:                      # out of memory: drop the cache and retry once
+                _pool.release_all()
+                _lib.check(_lib.lib().cb_malloc(self.size, C.byref(p)))
+            ptr = p.value
+        self.ptr = ptr
         self.nbytes = int(nbytes)
 
     def __del__(self):
         try:
             if self.ptr and _lib._lib is not None:
-                _lib._lib.cb_free(C.c_void_p(self.ptr))
+                if not _pool.give(self.ptr, self.size):
+                    _lib._lib.cb_free(C.c_void_p(self.ptr))
         except Exception:
             pass
         self.ptr = None

@@ -313,6 +313,37 @@ class RefPhotons(object):
         from chroma_lite_b200 import event
         return event.Photons(*[from_dev(getattr(self, f)) for f in self.FIELDS])
 
+    def get_flat_hits(self, geom, target_flag=0x4, nthreads_per_block=256, max_blocks=1024):
+        """GPUPhotons.get_flat_hits (gpu/photon.py:141-209): count kernel -> D2H count ->
+        allocate -> compaction kernel -> 10 D2H copies.  Returns dict of host arrays."""
+        mod = module('propagate.cubin')
+        sync()
+        counter = to_dev(np.zeros(1, dtype=np.uint32))
+        for first, n, blocks in chunk_iterator(self.n, nthreads_per_block, max_blocks):
+            mod.launch('count_photon_hits', blocks, nthreads_per_block, C.c_int(first), C.c_int(n), C.c_uint(target_flag),
+                       self.flags, geom.solid_id, self.last_hit_triangles, geom.detector_gpu, counter)
+        sync()
+        nhit = int(from_dev(counter)[0])
+        out = {f: DevMem(max(nhit, 1) * (12 if f in ('pos', 'dir', 'pol') else 4)) for f in self.FIELDS}
+        channels = DevMem(max(nhit, 1) * 4)
+        if nhit:
+            _ck(cu().cuMemsetD32_v2(C.c_uint64(counter.ptr), 0, C.c_size_t(1)), 'memset')
+            for first, n, blocks in chunk_iterator(self.n, nthreads_per_block, max_blocks):
+                mod.launch('copy_photon_hits', blocks, nthreads_per_block, C.c_int(first), C.c_int(n), C.c_uint(target_flag),
+                           geom.solid_id, geom.detector_gpu, counter,
+                           self.pos, self.dir, self.wavelengths, self.pol, self.t, self.flags, self.last_hit_triangles,
+                           self.weights, self.evidx,
+                           out['pos'], out['dir'], out['wavelengths'], out['pol'], out['t'], out['flags'],
+                           out['last_hit_triangles'], out['weights'], out['evidx'], channels)
+        host = {}
+        for f in self.FIELDS:
+            if f in ('pos', 'dir', 'pol'):
+                host[f] = from_dev(out[f], np.float32, (nhit, 3))
+            else:
+                host[f] = from_dev(out[f], getattr(self, f).dtype, (nhit,))
+        host['channel'] = from_dev(channels, np.int32, (nhit,))
+        return host
+
     def propagate(self, geom, rng, nthreads_per_block=256, max_blocks=1024, max_steps=10, use_weights=False,
                   scatter_first=0, force_single_launch=False):
         """Launch-for-launch replay of GPUPhotons.propagate (gpu/photon.py:240-290).
