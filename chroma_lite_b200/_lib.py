@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libchroma_b200.so')
+LIB_PATH = os.environ.get('CHROMA_B200_LIB', os.path.join(_HERE, 'libchroma_b200.so'))   # override: A/B builds
 
 u64, i32, u32, f32, vp = C.c_uint64, C.c_int32, C.c_uint32, C.c_float, C.c_void_p
 

@@ -350,6 +350,11 @@ static __device__ __noinline__ int traverse_reference_order(const DevGeometry& g
 // its own (reference) leaf box in float arithmetic (t < box tmin).  Boxes are
 // pruned with a small guard band so that such a winner is always seen; those rays
 // (~1e-7) are redone in the reference's own visit order on the reference tree.
+#ifdef CB_TRAV_IFIF
+#define CB_PHASE_LOOP if      /* one expansion + one triangle test per round */
+#else
+#define CB_PHASE_LOOP while   /* while-while */
+#endif
 struct Trav {
     float3 origin, direction;
     FastRay r;
@@ -407,7 +412,7 @@ struct Trav {
     {
         const float INF = __int_as_float(0x7f800000);
         // ---- phase A: expand internal entries until a leaf comes up
-        while (have && (cur >> 28) != 0) {
+        CB_PHASE_LOOP (have && (cur >> 28) != 0) {
             const uint32_t first = cur & 0x0FFFFFFFu;
             const uint32_t n = cur >> 28;
             uint32_t near_w = 0;
@@ -444,7 +449,7 @@ struct Trav {
             else pop_next(sstack, sstride);
         }
         // ---- phase B: triangle tests while leaves keep coming
-        while (have && (cur >> 28) == 0) {
+        CB_PHASE_LOOP (have && (cur >> 28) == 0) {
             if ((int)cur != last_hit) {
                 if (COUNT) cnt->tris++;
                 const float4* tp = g.tri64 + 4ull * cur;
@@ -498,6 +503,137 @@ __device__ __forceinline__ int traverse(const DevGeometry& g, const float3& orig
     tv.init(g, origin, direction, last_hit);
     while (tv.have) tv.template round<COUNT>(g, sstack, sstride, cnt);
     return tv.template finish<COUNT>(g, best_t, overflow_flag, cnt);
+}
+
+// ------------------------------------------------------------------ warp-cooperative traversal
+// One ray per WARP: the 32 lanes pop up to four entries from a shared-memory stack
+// and test their (<= 8) children in parallel, one child per lane; surviving leaves
+// go to a shared leaf queue and are tested 32 triangles at a time, the nearest hit
+// found by a shuffle reduction on (distance, rank).  A single ray's latency drops
+// from ~150 dependent box tests to ~10 warp iterations, which is what bounds the
+// late steps of a propagate call (few photons left, some with 100-step histories
+// or rays that graze dozens of PMTs).  Same exactness rule as Trav.
+constexpr int CB_WSTACK = 192;   // stack entries per warp
+constexpr int CB_WLEAF = 64;     // leaf-queue entries per warp
+
+template <bool COUNT>
+__device__ __forceinline__ int warp_traverse(const DevGeometry& g, const float3& origin, const float3& direction,
+                                             int last_hit, float& dist, uint2* wstack, uint2* wleaf,
+                                             uint32_t* overflow_flag, TraverseCounters* cnt)
+{
+    const float INF = __int_as_float(0x7f800000);
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    FastRay r;
+    fast_ray_axis(origin.x, direction.x, g.world_origin.x, g.world_scale, r.sx, r.nx, r.fx, r.selx);
+    fast_ray_axis(origin.y, direction.y, g.world_origin.y, g.world_scale, r.sy, r.ny, r.fy, r.sely);
+    fast_ray_axis(origin.z, direction.z, g.world_origin.z, g.world_scale, r.sz, r.nz, r.fz, r.selz);
+    RaySetup rr;
+    rr.noid = f3(-origin.x / direction.x, -origin.y / direction.y, -origin.z / direction.z);
+    rr.inv = f3(1.0f / direction.x, 1.0f / direction.y, 1.0f / direction.z);
+    rr.fx = isfinite(rr.inv.x); rr.fy = isfinite(rr.inv.y); rr.fz = isfinite(rr.inv.z);
+    float tn;
+    if (!hit_box(g, rr, g.ref_root_x, g.ref_root_y, g.ref_root_z, tn) || (g.root_w >> 28) == 0) { dist = -1.0f; return -1; }
+    const float extent = 2.0f * 65535.0f * g.world_scale;
+    float mag = 0.0f;
+    if (rr.fx) mag = fmaxf(mag, fabsf(rr.inv.x));
+    if (rr.fy) mag = fmaxf(mag, fabsf(rr.inv.y));
+    if (rr.fz) mag = fmaxf(mag, fabsf(rr.inv.z));
+    const float eps = 5e-7f * extent * mag;
+
+    float best_t = INF, limit = INF;
+    int best_tri = -1;
+    uint32_t best_rank = 0xFFFFFFFFu;
+    bool redo = false;
+    int sp = 0, nleaf = 0;                 // warp-uniform
+    if (lane == 0) wstack[0] = make_uint2(g.root_w, 0u);
+    sp = 1;
+    __syncwarp();
+
+    while (sp > 0 || nleaf > 0) {
+        if (nleaf >= 24 || sp == 0) {
+            // ---- triangle phase: up to 32 queued leaves at once
+            const int m = min(nleaf, 32);
+            nleaf -= m;
+            float t = INF;
+            uint32_t rank = 0xFFFFFFFFu;
+            int tri = -1;
+            if ((int)lane < m) {
+                const uint2 e = wleaf[nleaf + lane];
+                if (!(__uint_as_float(e.y) > limit) && (int)e.x != last_hit) {
+                    if (COUNT) cnt->tris++;
+                    const float4* tp = g.tri64 + 4ull * e.x;
+                    const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+                    float tt;
+                    if (hit_triangle(origin, direction, f3(a.x, a.y, a.z), f3(a.w, b.x, b.y), f3(b.z, b.w, c.x), tt)) {
+                        t = tt; rank = __float_as_uint(c.y); tri = (int)e.x;
+                    }
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float t2 = __shfl_xor_sync(0xffffffffu, t, o);
+                const uint32_t r2 = __shfl_xor_sync(0xffffffffu, rank, o);
+                const int tri2 = __shfl_xor_sync(0xffffffffu, tri, o);
+                if (t2 < t || (t2 == t && r2 < rank)) { t = t2; rank = r2; tri = tri2; }
+            }
+            if (tri != -1 && (t < best_t || (t == best_t && rank < best_rank))) {
+                best_t = t; best_tri = tri; best_rank = rank;
+                limit = best_t + (2e-5f * best_t + 2.0f * eps);
+            }
+            __syncwarp();
+            continue;
+        }
+        // ---- expand phase: pop up to four entries, one child per lane
+        const int take = min(sp, 4);
+        const int which = lane >> 3, c = lane & 7;
+        uint2 e = make_uint2(0u, 0u);
+        if (which < take) e = wstack[sp - 1 - which];
+        sp -= take;
+        __syncwarp();
+        const uint32_t n = e.x >> 28, first = e.x & 0x0FFFFFFFu;
+        bool ok = false;
+        float tmin = 0.0f;
+        uint32_t w = 0;
+        if (which < take && (uint32_t)c < n && !(__uint_as_float(e.y) > limit)) {
+            const uint4 nd = __ldg(&g.nodes[first + c]);
+            if (COUNT) cnt->nodes++;
+            const int h = hit_box_fast(r, eps, nd.x, nd.y, nd.z, tmin);
+            ok = (h == 1) || (h == 2 && hit_box(g, rr, nd.x, nd.y, nd.z, tmin));
+            ok = ok && !(tmin > limit);
+            w = nd.w;
+        }
+        const bool is_leaf = ok && (w >> 28) == 0;
+        const bool is_int = ok && (w >> 28) != 0;
+        const unsigned lm = __ballot_sync(0xffffffffu, is_leaf);
+        const unsigned im = __ballot_sync(0xffffffffu, is_int);
+        if (is_leaf) wleaf[nleaf + __popc(lm & lt_mask)] = make_uint2(w, __float_as_uint(tmin));
+        nleaf += __popc(lm);
+        const int ni = __popc(im);
+        if (sp + ni > CB_WSTACK) { redo = true; break; }
+        // push the internal hits far -> near, so that the nearest ends up on top
+        int pos = 0;
+        for (unsigned mm = im; mm; mm &= mm - 1) {
+            const int j = __ffs(mm) - 1;
+            const float tj = __shfl_sync(0xffffffffu, tmin, j);
+            pos += (tj > tmin) || (tj == tmin && j < (int)lane);
+        }
+        if (is_int) wstack[sp + pos] = make_uint2(w, __float_as_uint(tmin));
+        sp += ni;
+        __syncwarp();
+    }
+    if (best_tri != -1 && !redo) {
+        const float4 lb = __ldg(g.tri64 + 4ull * (uint32_t)best_tri + 3);
+        float box_t;
+        const bool in_box = hit_box(g, rr, __float_as_uint(lb.x), __float_as_uint(lb.y), __float_as_uint(lb.z), box_t);
+        redo = !in_box || best_t < box_t;
+    }
+    if (redo) {
+        if (COUNT) cnt->resolved++;
+        return traverse_reference_order<COUNT>(g, origin, direction, last_hit, dist, overflow_flag, cnt);
+    }
+    dist = (best_tri == -1) ? -1.0f : best_t;
+    return best_tri;
 }
 
 // ------------------------------------------------------------------ physics

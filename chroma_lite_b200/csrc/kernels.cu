@@ -310,66 +310,43 @@ step_physics_kernel(DevGeometry g, PropParams P)
     }
 }
 
-// Persistent-thread tail: every lane owns one photon at a time and runs it to
-// termination; a lane whose photon finished refills from a global cursor with one
-// warp-aggregated atomic, so the few long histories (reflections, re-emission
-// chains) do not cost a launch pair per step.
+// Persistent tail, one photon per WARP: the warp traverses cooperatively
+// (warp_traverse) and all lanes run the physics of their photon redundantly, so a
+// step costs a few microseconds instead of the ~50 us of a single-thread step.
+// Warps claim photons from the queue with one atomic each until it is empty.
+constexpr int TAIL_THREADS = 256;
 template <bool COUNT>
-__global__ void __launch_bounds__(PROP_THREADS, 2)
+__global__ void __launch_bounds__(TAIL_THREADS, 3)
 propagate_tail_kernel(DevGeometry g, PropParams P)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ unsigned long long mbar;
     float* stab = reinterpret_cast<float*>(smem_raw);
     const uint32_t tab_bytes = g.smem_floats * 4u;
-    uint2* sstack = reinterpret_cast<uint2*>(smem_raw + ((tab_bytes + 127u) & ~127u)) + threadIdx.x;
+    const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    uint2* wstack = reinterpret_cast<uint2*>(smem_raw + ((tab_bytes + 127u) & ~127u)) + warp * (CB_WSTACK + CB_WLEAF);
+    uint2* wleaf = wstack + CB_WSTACK;
     stage_tables(stab, g.tables, tab_bytes, &mbar);
     Tables T = {stab, g.tables, g.smem_floats};
-
-    const unsigned lane = threadIdx.x & 31u;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    long long my = -1;        // chunk-local photon index, -1 = lane is empty
-    bool exhausted = false;
-    Photon p;
-    Rng rng;
-    int steps = 0, sf = 0;
     TraverseCounters cnt = {0, 0, 0};
     unsigned long long nsteps_total = 0;
 
-    while (true) {
-        // ---- refill empty lanes
-        const bool need = (my < 0) && !exhausted;
-        const unsigned need_mask = __ballot_sync(0xffffffffu, need);
-        if (need_mask) {
-            unsigned long long base = 0;
-            const int leader = __ffs(need_mask) - 1;
-            if ((int)lane == leader) base = atomicAdd(P.counters, (unsigned long long)__popc(need_mask));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (need) {
-                const unsigned long long q = base + __popc(need_mask & lt_mask);
-                if (q < P.n_in) {
-                    const uint32_t k = P.queue_in ? P.queue_in[q] : (uint32_t)q;
-                    const uint64_t id = P.first + k;
-                    const uint32_t hist = P.bank.flags[id] & 0xFFFFu;
-                    if (!(P.step == 0 && (hist & CB_TERMINAL))) {
-                        my = (long long)k;
-                        load_photon(P.bank, id, hist, P.step == 0, p);
-                        rng = rng_load(P.rng, k);
-                        steps = P.step;
-                        sf = (P.step == 0) ? P.scatter_first : 0;
-                    }
-                } else {
-                    exhausted = true;
-                }
-            }
-        }
-        if (__all_sync(0xffffffffu, my < 0)) {
-            if (__any_sync(0xffffffffu, exhausted)) break;
-            continue;
-        }
-        // ---- one step for every populated lane
-        if (my >= 0) {
-            bool alive;
+    for (;;) {
+        unsigned long long q = 0;
+        if (lane == 0) q = atomicAdd(P.counters, 1ull);
+        q = __shfl_sync(0xffffffffu, q, 0);
+        if (q >= P.n_in) break;
+        const uint32_t k = P.queue_in ? P.queue_in[q] : (uint32_t)q;
+        const uint64_t id = P.first + k;
+        const uint32_t hist = P.bank.flags[id] & 0xFFFFu;
+        if (P.step == 0 && (hist & CB_TERMINAL)) continue;
+        Photon p;
+        load_photon(P.bank, id, hist, P.step == 0, p);
+        Rng rng = rng_load(P.rng, k);
+        int steps = P.step;
+        int sf = (P.step == 0) ? P.scatter_first : 0;
+        bool alive = true;
+        while (alive && steps < P.max_steps) {
             steps++;
             nsteps_total++;
             if (photon_is_nan(p)) {
@@ -377,24 +354,22 @@ propagate_tail_kernel(DevGeometry g, PropParams P)
                 alive = false;
             } else {
                 float dist;
-                const int tri = traverse<COUNT>(g, p.pos, p.dir, p.last_hit_triangle, dist, sstack, PROP_THREADS,
-                                                (uint32_t*)(P.counters + 3), &cnt);
+                const int tri = warp_traverse<COUNT>(g, p.pos, p.dir, p.last_hit_triangle, dist, wstack, wleaf,
+                                                     (uint32_t*)(P.counters + 3), &cnt);
                 alive = physics_step(g, T, p, rng, tri, dist, P.use_weights != 0, sf);
                 sf = 0;
             }
-            if (!alive || steps >= P.max_steps) {
-                rng_store(P.rng, (uint64_t)my, rng);
-                store_photon(P.bank, P.first + (uint64_t)my, p);
-                my = -1;
-            }
+        }
+        if (lane == 0) {
+            rng_store(P.rng, k, rng);
+            store_photon(P.bank, id, p);
         }
     }
-    for (int o = 16; o > 0; o >>= 1) nsteps_total += __shfl_down_sync(0xffffffffu, nsteps_total, o);
     if (lane == 0 && nsteps_total) atomicAdd(P.counters + 4, nsteps_total);
     if (COUNT) {
         atomicAdd(P.counters + 1, (unsigned long long)cnt.nodes);
         atomicAdd(P.counters + 2, (unsigned long long)cnt.tris);
-        atomicAdd(P.counters + 5, (unsigned long long)cnt.resolved);
+        if (lane == 0) atomicAdd(P.counters + 5, (unsigned long long)cnt.resolved);
     }
 }
 
@@ -775,7 +750,7 @@ int cb_propagate(const CbPhotonBank* bank, cb_geom_t gh, cb_rng_t rh, int32_t nt
     auto k_tail = count ? propagate_tail_kernel<true> : propagate_tail_kernel<false>;
     const size_t smem_int = stack_smem_bytes();
     const size_t smem_tab = (g->smem_table_bytes + 127u) & ~127u;
-    const size_t smem_tail = smem_tab + stack_smem_bytes();
+    const size_t smem_tail = smem_tab + (size_t)(TAIL_THREADS / 32) * (CB_WSTACK + CB_WLEAF) * sizeof(uint2);
     CB_CUDA(cudaFuncSetAttribute(k_int, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_int));
     CB_CUDA(cudaFuncSetAttribute(step_physics_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_tab, 16)));
     CB_CUDA(cudaFuncSetAttribute(k_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tail));
@@ -783,7 +758,7 @@ int cb_propagate(const CbPhotonBank* bank, cb_geom_t gh, cb_rng_t rh, int32_t nt
     CB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&int_per_sm, k_int, PROP_THREADS, smem_int));
     if (int_per_sm < 1) int_per_sm = 1;
     CB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&phys_per_sm, step_physics_kernel, PROP_THREADS, smem_tab));
-    CB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tail_per_sm, k_tail, PROP_THREADS, smem_tail));
+    CB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tail_per_sm, k_tail, TAIL_THREADS, smem_tail));
     if (phys_per_sm < 1 || tail_per_sm < 1) return fail(CB_ERR_CUDA, "cb_propagate: kernels do not fit on an SM");
 
     unsigned long long tot[16] = {0};
@@ -806,9 +781,10 @@ int cb_propagate(const CbPhotonBank* bank, cb_geom_t gh, cb_rng_t rh, int32_t nt
             P.queue_in = q_in; P.queue_out = c.d_queue[qsel]; P.n_in = (uint32_t)n_alive; P.step = step;
             if (n_alive <= tail_threshold || step + 1 == max_steps) {
                 // finish everything that is left in one persistent launch
-                unsigned blocks = (unsigned)std::min<uint64_t>((n_alive + PROP_THREADS - 1) / PROP_THREADS,
+                const uint64_t per_block = TAIL_THREADS / 32;          // one photon per warp
+                unsigned blocks = (unsigned)std::min<uint64_t>((n_alive + per_block - 1) / per_block,
                                                                (uint64_t)c.sm_count * tail_per_sm);
-                k_tail<<<blocks, PROP_THREADS, smem_tail, c.stream>>>(g->dev, P);
+                k_tail<<<blocks, TAIL_THREADS, smem_tail, c.stream>>>(g->dev, P);
                 CB_CUDA(cudaGetLastError());
                 launches++;
                 n_alive = 0;
