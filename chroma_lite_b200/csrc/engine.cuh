@@ -229,8 +229,13 @@ __device__ __forceinline__ void fast_ray_axis(float o, float d, float worigin, f
     const float inv = 1.0f / d;
     if (isfinite(inv)) {
         s = wscale * inv;
-        const float off = (worigin - o) * inv - 65536.0f * s;   // the conversion below yields 65536 + q
-        n = off; f = off;
+        const float a = (worigin - o) * inv, b = 65536.0f * s;  // the conversion below yields 65536 + q
+        const float off = a - b;
+        // interval arithmetic: widen this axis' slab by the rounding bound of its own
+        // affine map (a few ulps of the largest term), so a box the reference's
+        // arithmetic would hit is never missed here, whatever the ray direction
+        const float e = 5e-7f * (fabsf(a) + 2.0f * fabsf(b));
+        n = off - e; f = off + e;
         sel = (inv >= 0.0f) ? 0x3210u : 0x1032u;                // swap halves when the ray runs towards -axis
     } else {                                                   // the reference skips such an axis (intersect.h:120)
         s = 0.0f; n = -INF; f = INF; sel = 0x3210u;
@@ -249,10 +254,10 @@ static __device__ __noinline__ bool hit_box_exact(const DevGeometry& g, const fl
     return hit_box(g, rr, px, py, pz, tnear);
 }
 
-// Three-way result: clearly missed / clearly hit by more than the rounding bound
-// `eps` of this ray / marginal (caller re-decides with hit_box_exact, so the engine
-// never accepts or rejects a box the reference's arithmetic would judge otherwise).
-__device__ __forceinline__ int hit_box_fast(const FastRay& r, float eps, uint32_t px, uint32_t py, uint32_t pz, float& tnear)
+// Conservative: never misses a box the reference's arithmetic hits (slabs widened per
+// axis in fast_ray_axis); `tnear` is a lower bound of the reference's tmin.  A winner
+// found through a box the reference would have rejected is caught in finish().
+__device__ __forceinline__ bool hit_box_fast(const FastRay& r, uint32_t px, uint32_t py, uint32_t pz, float& tnear)
 {
     const uint32_t ax = __byte_perm(px, 0, r.selx), ay = __byte_perm(py, 0, r.sely), az = __byte_perm(pz, 0, r.selz);
     const float tnx = __fmaf_rn(q16f_lo(ax), r.sx, r.nx), tfx = __fmaf_rn(q16f_hi(ax), r.sx, r.fx);
@@ -261,9 +266,7 @@ __device__ __forceinline__ int hit_box_fast(const FastRay& r, float eps, uint32_
     const float tmin = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.0f));
     const float tmax = fminf(fminf(tfx, tfy), tfz);
     tnear = tmin;
-    if (tmin > tmax + eps) return 0;      // miss
-    if (tmin + eps <= tmax) return 1;     // hit
-    return 2;                             // marginal
+    return !(tmin > tmax);
 }
 
 // ------------------------------------------------------------------ traversal
@@ -358,7 +361,7 @@ static __device__ __noinline__ int traverse_reference_order(const DevGeometry& g
 struct Trav {
     float3 origin, direction;
     FastRay r;
-    float best_t, limit, eps, cur_t;
+    float best_t, limit, cur_t;
     uint32_t best_rank, cur;
     int best_tri, last_hit, sp;
     bool have, redo;
@@ -396,14 +399,6 @@ struct Trav {
         rr.fx = isfinite(rr.inv.x); rr.fy = isfinite(rr.inv.y); rr.fz = isfinite(rr.inv.z);
         float tn;
         have = hit_box(g, rr, g.ref_root_x, g.ref_root_y, g.ref_root_z, tn) && (g.root_w >> 28) != 0;
-        // rounding bound of the slab arithmetic (fast and reference alike): a few ulps
-        // of the largest |coordinate / d| that enters the affine maps
-        const float extent = 2.0f * 65535.0f * g.world_scale;
-        float mag = 0.0f;
-        if (rr.fx) mag = fmaxf(mag, fabsf(rr.inv.x));
-        if (rr.fy) mag = fmaxf(mag, fabsf(rr.inv.y));
-        if (rr.fz) mag = fmaxf(mag, fabsf(rr.inv.z));
-        eps = 5e-7f * extent * mag;
         return have;
     }
 
@@ -427,9 +422,7 @@ struct Trav {
                     float tmin;
                     bool ok = false;
                     if (i + k < n) {
-                        const int h = hit_box_fast(r, eps, nd[k].x, nd[k].y, nd[k].z, tmin);
-                        ok = (h == 1) || (h == 2 && hit_box_exact(g, origin, direction, nd[k].x, nd[k].y, nd[k].z, tmin));
-                        ok = ok && !(tmin > limit);
+                        ok = hit_box_fast(r, nd[k].x, nd[k].y, nd[k].z, tmin) && !(tmin > limit);
                         if (COUNT) cnt->nodes++;
                     }
                     if (ok) {
@@ -459,7 +452,7 @@ struct Trav {
                     const uint32_t rank = __float_as_uint(c.y);
                     if (t < best_t || (t == best_t && rank < best_rank)) {
                         best_t = t; best_tri = (int)cur; best_rank = rank;
-                        limit = best_t + (2e-5f * best_t + 2.0f * eps);
+                        limit = best_t + 2e-5f * best_t;     // slack for the triangle test's own rounding
                     }
                 }
             }
@@ -534,13 +527,6 @@ __device__ __forceinline__ int warp_traverse(const DevGeometry& g, const float3&
     rr.fx = isfinite(rr.inv.x); rr.fy = isfinite(rr.inv.y); rr.fz = isfinite(rr.inv.z);
     float tn;
     if (!hit_box(g, rr, g.ref_root_x, g.ref_root_y, g.ref_root_z, tn) || (g.root_w >> 28) == 0) { dist = -1.0f; return -1; }
-    const float extent = 2.0f * 65535.0f * g.world_scale;
-    float mag = 0.0f;
-    if (rr.fx) mag = fmaxf(mag, fabsf(rr.inv.x));
-    if (rr.fy) mag = fmaxf(mag, fabsf(rr.inv.y));
-    if (rr.fz) mag = fmaxf(mag, fabsf(rr.inv.z));
-    const float eps = 5e-7f * extent * mag;
-
     float best_t = INF, limit = INF;
     int best_tri = -1;
     uint32_t best_rank = 0xFFFFFFFFu;
@@ -579,7 +565,7 @@ __device__ __forceinline__ int warp_traverse(const DevGeometry& g, const float3&
             }
             if (tri != -1 && (t < best_t || (t == best_t && rank < best_rank))) {
                 best_t = t; best_tri = tri; best_rank = rank;
-                limit = best_t + (2e-5f * best_t + 2.0f * eps);
+                limit = best_t + 2e-5f * best_t;
             }
             __syncwarp();
             continue;
@@ -598,9 +584,7 @@ __device__ __forceinline__ int warp_traverse(const DevGeometry& g, const float3&
         if (which < take && (uint32_t)c < n && !(__uint_as_float(e.y) > limit)) {
             const uint4 nd = __ldg(&g.nodes[first + c]);
             if (COUNT) cnt->nodes++;
-            const int h = hit_box_fast(r, eps, nd.x, nd.y, nd.z, tmin);
-            ok = (h == 1) || (h == 2 && hit_box(g, rr, nd.x, nd.y, nd.z, tmin));
-            ok = ok && !(tmin > limit);
+            ok = hit_box_fast(r, nd.x, nd.y, nd.z, tmin) && !(tmin > limit);
             w = nd.w;
         }
         const bool is_leaf = ok && (w >> 28) == 0;

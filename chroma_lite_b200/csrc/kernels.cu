@@ -9,6 +9,9 @@
 namespace cb {
 
 constexpr int PROP_THREADS = 256;
+#ifndef CB_INT_BLOCKS
+#define CB_INT_BLOCKS 4      /* resident CTAs per SM of the thread-per-ray traversal kernels */
+#endif
 
 // ---------------------------------------------------------------- smem staging
 // The wavelength tables (a few KB .. 48 KB) are staged once per CTA with the bulk
@@ -128,7 +131,7 @@ struct RaySource {           // cb_intersect: free rays, direction normalised li
 };
 
 template <bool COUNT>
-__global__ void __launch_bounds__(PROP_THREADS, 4)
+__global__ void __launch_bounds__(PROP_THREADS, CB_INT_BLOCKS)
 intersect_kernel(DevGeometry g, RaySource src, uint64_t n, unsigned long long* counters)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -256,7 +259,7 @@ struct PhotonRaySource {     // one propagation step: rays of the photons in the
 };
 
 template <bool COUNT>
-__global__ void __launch_bounds__(PROP_THREADS, 4)
+__global__ void __launch_bounds__(PROP_THREADS, CB_INT_BLOCKS)
 step_intersect_kernel(DevGeometry g, PropParams P)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
