@@ -34,10 +34,21 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, 'tests'))
 
 MAX_STEPS = 100
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel from the
+# committed `ncu --set full` capture (profiles/), keyed by (workload, photons per event)
+NCU_TRAFFIC_BYTES_PER_LAUNCH = {}
+
+
+_REAL_STDOUT = None
 
 
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
+
+
+def emit(obj):
+    data = (json.dumps(obj) + '\n').encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
 
 
 # ------------------------------------------------------------------ clocks
@@ -126,11 +137,13 @@ def build_detector(workload, timings):
     timings['bvh_s'] = time.perf_counter() - t0
     timings['cached'] = False
     try:
-        np.savez(path, vertices=det.mesh.vertices, triangles=det.mesh.triangles, colors=det.colors,
+        tmp = path + '.tmp%d.npz' % os.getpid()
+        np.savez(tmp, vertices=det.mesh.vertices, triangles=det.mesh.triangles, colors=det.colors,
                  solid_id=det.solid_id, m1=det.material1_index, m2=det.material2_index, surf=det.surface_index,
                  world_origin=det.bvh.world_coords.world_origin, world_scale=det.bvh.world_coords.world_scale,
                  nodes=det.bvh.nodes.view(np.uint32).reshape(-1, 4), layers=np.asarray(det.bvh.layer_offsets),
                  flatten_s=timings['flatten_s'], bvh_s=timings['bvh_s'])
+        os.replace(tmp, path)
     except Exception as e:               # cache is best effort
         log('cache write failed:', e)
     return det
@@ -248,6 +261,7 @@ def run_ours(args):
     _lib.check(lib.cb_synchronize())
     kernel_ms, launches, steps_taken = 0.0, 0, 0
     nodes_v, tris_v, resolved = 0, 0, 0
+    int0_ms, int0_rays, int0_n = 0.0, 0, 0
     t0 = time.perf_counter()
     for _ in range(args.steps):
         st = one_step()
@@ -257,6 +271,10 @@ def run_ours(args):
         nodes_v += st.nodes_visited
         tris_v += st.tris_tested
         resolved += st.rays_resolved
+        if st.intersect0_rays:
+            int0_ms += st.intersect0_ms
+            int0_rays += st.intersect0_rays
+            int0_n += 1
     _lib.check(lib.cb_synchronize())
     barrier(world)
     wall = time.perf_counter() - t0
@@ -298,6 +316,10 @@ def run_ours(args):
     timings['e2e_s_per_event'] = e2e_s / args.steps
     timings['e2e_hits_per_event'] = int(len(fh))
 
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     # ---- roofline + cpu baseline (rank 0, N=1 only does the CPU leg)
@@ -309,13 +331,27 @@ def run_ours(args):
         pass
     peak = float(peaks.get('hbm_gbs', 6650.0))
     if world == 1:
+        from oracle import orc
         desc, keep = make_desc(det)
-        b, cpu_rate = algorithmic_bytes(det, desc, make_event(args.cpu_sample, seed=999), timings)
-        per_launch_s = (kernel_ms / 1e3) / max(launches, 1)
-        achieved = b * n / per_launch_s / 1e9
-        roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                    'traffic': None, 'kernel': 'propagate_kernel', 'bytes_per_photon': b,
-                    'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback 6650 GB/s'}
+        b_photon, cpu_rate = algorithmic_bytes(det, desc, make_event(args.cpu_sample, seed=999), timings)
+        # dominant kernel = the first step's traversal kernel (one ray per photon).  Algorithmic
+        # bytes per ray B_ray = 32 + 16*Nnode + 48*Ntri with Nnode/Ntri counted by the REFERENCE
+        # traversal (oracle, reference tree) on a sample of the same rays
+        smp = make_event(min(args.cpu_sample, 20000), seed=998)
+        _, _, c0 = orc.intersect(desc, smp.pos, smp.dir)
+        b_ray = 32.0 + 16.0 * c0['nodes'] / len(smp) + 48.0 * c0['tris'] / len(smp)
+        timings['oracle']['first_step_nodes_per_ray'] = c0['nodes'] / len(smp)
+        timings['oracle']['first_step_tris_per_ray'] = c0['tris'] / len(smp)
+        if int0_n:
+            per_launch_s = int0_ms / 1e3 / int0_n
+            rays_per_launch = int0_rays / int0_n
+            achieved = b_ray * rays_per_launch / per_launch_s / 1e9
+            roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                        'traffic': NCU_TRAFFIC_BYTES_PER_LAUNCH.get((args.workload, n)),
+                        'kernel': 'step_intersect_kernel (first step)', 'bytes_per_ray': b_ray,
+                        'rays_per_launch': rays_per_launch, 'ms_per_launch': per_launch_s * 1e3,
+                        'rays_per_s': rays_per_launch / per_launch_s, 'bytes_per_photon_all_steps': b_photon,
+                        'peak_source': 'MEASURED_PEAKS.json hbm_gbs (burst copy)' if peaks else 'fallback 6650 GB/s'}
         cpu_baseline = {'value': cpu_rate, 'unit': 'photons/s', 'cores': 1, 'kind': 'port',
                         'sample': '%d photons of the same event type through oracle/chroma_oracle.c '
                                   '(orc_propagate, max_steps=%d), host cores on this box: %d'
@@ -338,7 +374,7 @@ def run_ours(args):
                                       'enabled': bool(os.environ.get('CHROMA_B200_STATS'))},
                   'host_cores': os.cpu_count()},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------ reference arm
@@ -348,7 +384,7 @@ def run_reference(args):
         return
     from oracle import ref_driver
     if not ref_driver.available():
-        print(json.dumps({'impl': 'reference', 'unavailable': 'oracle/_ref cubins missing (build() needs /root/reference)'}))
+        emit({'impl': 'reference', 'unavailable': 'oracle/_ref cubins missing (build() needs /root/reference)'})
         return
     from chroma_lite_b200 import _lib
     from chroma_lite_b200.gpu.geometry import make_desc
@@ -407,10 +443,16 @@ def run_reference(args):
         'extra': {'setup': timings, 'host_cores': os.cpu_count(),
                   'terminal_fraction': float(((out.flags & 0x800F) != 0).mean())},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
+    # stdout carries exactly ONE JSON line: anything libraries print there (NCCL's
+    # version banner, ...) is diverted to stderr
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=5)

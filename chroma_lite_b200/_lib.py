@@ -61,7 +61,7 @@ class CbPhotonBank(C.Structure):
 
 class CbPropagateStats(C.Structure):
     _fields_ = [('photons', u64), ('steps', u64), ('nodes_visited', u64), ('tris_tested', u64), ('rays_resolved', u64),
-                ('launches', u32), ('kernel_ms', f32)]
+                ('launches', u32), ('kernel_ms', f32), ('intersect0_ms', f32), ('intersect0_rays', u64)]
 
 
 # name -> (restype, argtypes); every symbol include/chroma_b200.h declares

@@ -22,6 +22,7 @@ struct Context {
     cudaStream_t copy_stream = nullptr;   // host<->device copies, bank initialisation
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;      // cb_timer_*
     cudaEvent_t kev0 = nullptr, kev1 = nullptr;    // per-call kernel timing
+    cudaEvent_t iev0 = nullptr, iev1 = nullptr;    // first-step traversal kernel timing
     void* flush_buf = nullptr; size_t flush_bytes = 0;
     unsigned long long* d_counters = nullptr;      // 16 x u64 scratch (work counter, stats, flags)
     unsigned long long* h_counters = nullptr;      // pinned mirror
@@ -42,9 +43,17 @@ int cuda_fail(cudaError_t e, const char* what);
         if (_e != cudaSuccess) return cb::cuda_fail(_e, #call);               \
     } while (0)
 
+// every entry point may be called from any host thread: bind it to the library's device once
+inline void bind_thread()
+{
+    static thread_local bool bound = false;
+    if (!bound) { cudaSetDevice(ctx().device); bound = true; }
+}
+
 #define CB_REQUIRE_INIT()                                                     \
     do {                                                                      \
         if (cb::ctx().device < 0) return cb::fail(CB_ERR_INVALID, "cb_init() has not been called"); \
+        cb::bind_thread();                                                    \
     } while (0)
 
 struct Geometry {

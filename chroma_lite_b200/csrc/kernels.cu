@@ -728,7 +728,7 @@ int cb_propagate(const CbPhotonBank* bank, cb_geom_t gh, cb_rng_t rh, int32_t nt
     Context& c = ctx();
     const bool count = getenv("CHROMA_B200_STATS") != nullptr;
     // hand the rest to the persistent kernel once the survivors fit on the chip ~1.3 times over
-    static const uint64_t tail_threshold = getenv("CHROMA_B200_TAIL") ? (uint64_t)atoll(getenv("CHROMA_B200_TAIL")) : (uint64_t)(1.3 * 2048 * ctx().sm_count);
+    const uint64_t tail_threshold = getenv("CHROMA_B200_TAIL") ? (uint64_t)atoll(getenv("CHROMA_B200_TAIL")) : (uint64_t)(1.3 * 2048 * ctx().sm_count);
 
     // scratch: two queues + hit arrays, sized for one chunk
     const uint64_t cap = std::min<uint64_t>(pool, bank->n);
@@ -747,7 +747,7 @@ int cb_propagate(const CbPhotonBank* bank, cb_geom_t gh, cb_rng_t rh, int32_t nt
         CB_CUDA(cudaMalloc(&c.d_sort_tmp, c.sort_tmp_bytes));
         c.scratch_cap = cap;
     }
-    static const uint64_t sort_threshold = getenv("CHROMA_B200_SORT") ? (uint64_t)atoll(getenv("CHROMA_B200_SORT")) : 0;
+    const uint64_t sort_threshold = getenv("CHROMA_B200_SORT") ? (uint64_t)atoll(getenv("CHROMA_B200_SORT")) : 0;
 
     auto k_int = count ? step_intersect_kernel<true> : step_intersect_kernel<false>;
     auto k_tail = count ? propagate_tail_kernel<true> : propagate_tail_kernel<false>;
@@ -766,6 +766,7 @@ int cb_propagate(const CbPhotonBank* bank, cb_geom_t gh, cb_rng_t rh, int32_t nt
 
     unsigned long long tot[16] = {0};
     uint32_t launches = 0;
+    uint64_t int0_rays = 0;
     CB_CUDA(cudaEventRecord(c.kev0, c.stream));
     // photons beyond the pool reuse states chunk by chunk, in order, exactly as
     // the reference's chunk_iterator does for one step (gpu/photon.py:266-268)
@@ -805,7 +806,10 @@ int cb_propagate(const CbPhotonBank* bank, cb_geom_t gh, cb_rng_t rh, int32_t nt
                 launches += 2;
             }
             unsigned iblocks = (unsigned)std::min<uint64_t>(blocks, (uint64_t)c.sm_count * int_per_sm);
+            const bool time_it = (step == 0 && first == 0);
+            if (time_it) CB_CUDA(cudaEventRecord(c.iev0, c.stream));
             k_int<<<iblocks, PROP_THREADS, smem_int, c.stream>>>(g->dev, P);
+            if (time_it) { CB_CUDA(cudaEventRecord(c.iev1, c.stream)); int0_rays = n_alive; }
             unsigned pblocks = (unsigned)std::min<uint64_t>(blocks, (uint64_t)c.sm_count * phys_per_sm);
             step_physics_kernel<<<pblocks, PROP_THREADS, smem_tab, c.stream>>>(g->dev, P);
             CB_CUDA(cudaGetLastError());
@@ -830,6 +834,7 @@ int cb_propagate(const CbPhotonBank* bank, cb_geom_t gh, cb_rng_t rh, int32_t nt
         stats->rays_resolved = tot[5];
         stats->launches = launches;
         cudaEventElapsedTime(&stats->kernel_ms, c.kev0, c.kev1);
+        if (int0_rays) { cudaEventElapsedTime(&stats->intersect0_ms, c.iev0, c.iev1); stats->intersect0_rays = int0_rays; }
     }
     if (tot[3]) return fail(CB_ERR_CUDA, "cb_propagate: traversal stack overflow");
     return CB_OK;

@@ -185,6 +185,7 @@ int cb_init(int device)
     CB_CUDA(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
     CB_CUDA(cudaEventCreate(&c.ev0)); CB_CUDA(cudaEventCreate(&c.ev1));
     CB_CUDA(cudaEventCreate(&c.kev0)); CB_CUDA(cudaEventCreate(&c.kev1));
+    CB_CUDA(cudaEventCreate(&c.iev0)); CB_CUDA(cudaEventCreate(&c.iev1));
     CB_CUDA(cudaMalloc(&c.d_counters, 16 * sizeof(unsigned long long)));
     CB_CUDA(cudaMemset(c.d_counters, 0, 16 * sizeof(unsigned long long)));
     CB_CUDA(cudaMallocHost(&c.h_counters, 16 * sizeof(unsigned long long)));
@@ -222,30 +223,42 @@ int cb_free(void* dptr)
     CB_CUDA(cudaFree(dptr));          // cudaFree itself waits for work that uses the block
     return CB_OK;
 }
+// host<->device copies run on per-host-thread streams, so that uploads issued from
+// worker threads overlap each other and the kernels of a propagate call in flight
+static cudaStream_t thread_copy_stream()
+{
+    static thread_local cudaStream_t s = nullptr;
+    if (!s) {
+        cudaSetDevice(ctx().device);
+        if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); s = ctx().copy_stream; }
+    }
+    return s;
+}
 int cb_memcpy_h2d(void* d, const void* h, uint64_t bytes)
 {
     CB_REQUIRE_INIT();
     if (bytes == 0) return CB_OK;
-    // host<->device copies run on their own stream so that an upload issued from a
-    // second host thread overlaps the kernels of a propagate call in flight
-    CB_CUDA(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, ctx().copy_stream));
-    CB_CUDA(cudaStreamSynchronize(ctx().copy_stream));
+    cudaStream_t s = thread_copy_stream();
+    CB_CUDA(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, s));
+    CB_CUDA(cudaStreamSynchronize(s));
     return CB_OK;
 }
 int cb_memcpy_d2h(void* h, const void* d, uint64_t bytes)
 {
     CB_REQUIRE_INIT();
     if (bytes == 0) return CB_OK;
-    CB_CUDA(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, ctx().copy_stream));
-    CB_CUDA(cudaStreamSynchronize(ctx().copy_stream));
+    cudaStream_t s = thread_copy_stream();
+    CB_CUDA(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, s));
+    CB_CUDA(cudaStreamSynchronize(s));
     return CB_OK;
 }
 int cb_memcpy_d2d(void* dst, const void* src, uint64_t bytes)
 {
     CB_REQUIRE_INIT();
     if (bytes == 0) return CB_OK;
-    CB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx().copy_stream));
-    CB_CUDA(cudaStreamSynchronize(ctx().copy_stream));
+    cudaStream_t s = thread_copy_stream();
+    CB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, s));
+    CB_CUDA(cudaStreamSynchronize(s));
     return CB_OK;
 }
 int cb_memset32(void* dptr, uint32_t value, uint64_t count)
@@ -253,9 +266,15 @@ int cb_memset32(void* dptr, uint32_t value, uint64_t count)
     CB_REQUIRE_INIT();
     if (count == 0) return CB_OK;
     int blocks = (int)std::min<uint64_t>((count + 255) / 256, (uint64_t)ctx().sm_count * 16);
-    fill32_kernel<<<blocks, 256, 0, ctx().copy_stream>>>((uint32_t*)dptr, value, count);
-    CB_CUDA(cudaGetLastError());
-    CB_CUDA(cudaStreamSynchronize(ctx().copy_stream));
+    cudaStream_t s = thread_copy_stream();
+    if (value == 0u || value == 0xFFFFFFFFu) {
+        // byte patterns go through the copy engine and do not queue behind persistent kernels
+        CB_CUDA(cudaMemsetAsync(dptr, value ? 0xFF : 0, count * 4, s));
+    } else {
+        fill32_kernel<<<blocks, 256, 0, s>>>((uint32_t*)dptr, value, count);
+        CB_CUDA(cudaGetLastError());
+    }
+    CB_CUDA(cudaStreamSynchronize(s));
     return CB_OK;
 }
 int cb_host_alloc(uint64_t bytes, void** hptr)

@@ -25,6 +25,17 @@ def _resolve_nphotons(ph):
     raise TypeError('Cannot determine photon count from object of type %r' % type(ph))
 
 
+_pool = None
+
+
+def _upload_pool():
+    global _pool
+    if _pool is None:
+        import concurrent.futures
+        _pool = concurrent.futures.ThreadPoolExecutor(max_workers=3, thread_name_prefix='cb-upload')
+    return _pool
+
+
 def _alloc_bank(n):
     return dict(pos=ga.empty(n, ga.vec.float3), dir=ga.empty(n, ga.vec.float3), pol=ga.empty(n, ga.vec.float3),
                 wavelengths=ga.empty(n, np.float32), t=ga.empty(n, np.float32),
@@ -67,18 +78,22 @@ class GPUPhotons(object):
                 dest[:nphotons].set(np.asarray(source, dtype=dtype))
 
         if nphotons:
-            put_vec(self.pos, photons.pos)
-            put_vec(self.dir, photons.dir)
-            put_vec(self.pol, photons.pol)
-            put(self.wavelengths, photons.wavelengths, np.float32)
-            put(self.t, photons.t, np.float32)
+            jobs = [(put_vec, self.pos, photons.pos), (put_vec, self.dir, photons.dir), (put_vec, self.pol, photons.pol),
+                    (put, self.wavelengths, photons.wavelengths, np.float32), (put, self.t, photons.t, np.float32),
+                    (put, self.evidx, photons.evidx, np.uint32)]
             if copy_triangles:
-                put(self.last_hit_triangles, photons.last_hit_triangles, np.int32)
+                jobs.append((put, self.last_hit_triangles, photons.last_hit_triangles, np.int32))
             if copy_flags:
-                put(self.flags, photons.flags, np.uint32)
+                jobs.append((put, self.flags, photons.flags, np.uint32))
             if copy_weights:
-                put(self.weights, photons.weights, np.float32)
-            put(self.evidx, photons.evidx, np.uint32)
+                jobs.append((put, self.weights, photons.weights, np.float32))
+            if nphotons >= 200000:
+                # large banks: stage the arrays from a few host threads at once (each
+                # thread has its own copy stream; the C calls release the GIL)
+                list(_upload_pool().map(lambda j: j[0](*j[1:]), jobs))
+            else:
+                for j in jobs:
+                    j[0](*j[1:])
 
         self.true_nphotons = getattr(photons, 'true_nphotons', nphotons)
         self.ncopies = ncopies

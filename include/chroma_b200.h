@@ -142,6 +142,8 @@ typedef struct {
     uint64_t rays_resolved;  /* rays redone in reference visit order (0 unless stats build) */
     uint32_t launches;       /* kernels launched by this call */
     float    kernel_ms;      /* device time of those kernels (CUDA events) */
+    float    intersect0_ms;  /* device time of the first step's traversal kernel (0 if not launched) */
+    uint64_t intersect0_rays;/* rays that kernel traced */
 } CbPropagateStats;
 
 #if defined(__GNUC__)

@@ -167,3 +167,23 @@ def test_empty_bank(gpu_ready):
     gp = gpu.GPUPhotons(event.Photons())
     gp.propagate(g, gpu.get_rng_states(64), max_steps=5)
     assert len(gp.get()) == 0
+
+
+def test_scheduler_invariance(gpu_ready, monkeypatch):
+    # wavefront steps, warp-cooperative persistent tail and the ray-sorting option are
+    # scheduling choices only: photon i owns RNG stream i, so the results are identical
+    import os
+    geo = scenes.tiny_detector()
+    ph = scenes.point_source(150000, seed=9, wl_range=(300, 600))
+    outs = []
+    for tail, sort in (('0', '0'), ('1000000000', '0'), ('20000', '0'), ('20000', '1')):
+        monkeypatch.setenv('CHROMA_B200_TAIL', tail)
+        monkeypatch.setenv('CHROMA_B200_SORT', sort)
+        mine, st, gp = engine_run(geo, ph, 17, 100, detector=True)
+        outs.append((mine, st, gp.last_stats.launches))
+    base = outs[0][0]
+    for mine, st, launches in outs[1:]:
+        assert np.array_equal(mine.flags, base.flags) and np.array_equal(mine.last_hit_triangles, base.last_hit_triangles)
+        assert np.array_equal(mine.pos, base.pos) and np.array_equal(mine.t, base.t)
+        assert np.array_equal(st, outs[0][1])
+    assert outs[1][2] == 1 and outs[0][2] > 10      # one persistent launch vs a launch pair per step
