@@ -244,7 +244,7 @@ __device__ __forceinline__ void fast_ray_axis(float o, float d, float worigin, f
 __device__ __forceinline__ float q16f_lo(uint32_t w) { return __uint_as_float((w & 0xFFFFu) * 128u + 0x47800000u); }
 __device__ __forceinline__ float q16f_hi(uint32_t w) { return __uint_as_float((w >> 16) * 128u + 0x47800000u); }
 // slab test in the reference's arithmetic, recomputing the ray setup (rare path)
-static __device__ __noinline__ bool hit_box_exact(const DevGeometry& g, const float3& o, const float3& d,
+static __device__ __noinline__ bool hit_box_exact(const DevGeometry& g, const float3 o, const float3 d,
                                                   uint32_t px, uint32_t py, uint32_t pz, float& tnear)
 {
     RaySetup rr;
@@ -279,8 +279,8 @@ constexpr int CB_RSTACK = 64;   // local stack of the reference-order fallback
 // popped LIFO, prune against the current minimum).  Only used for the rare rays
 // the ordered traversal flags as order-sensitive (see traverse()).
 template <bool COUNT>
-static __device__ __noinline__ int traverse_reference_order(const DevGeometry& g, const float3& origin,
-                                                            const float3& direction, int last_hit,
+static __device__ __noinline__ int traverse_reference_order(const DevGeometry& g, const float3 origin,
+                                                            const float3 direction, int last_hit,
                                                             float& min_distance, uint32_t* overflow_flag,
                                                             TraverseCounters* cnt)
 {
@@ -497,6 +497,221 @@ __device__ __forceinline__ int traverse(const DevGeometry& g, const float3& orig
     while (tv.have) tv.template round<COUNT>(g, sstack, sstride, cnt);
     return tv.template finish<COUNT>(g, best_t, overflow_flag, cnt);
 }
+
+// ------------------------------------------------------------------ phased traversal
+// Second-generation one-ray-per-lane traversal.  Profiling the first one (Trav) showed
+// the box tests running with ~9 of 32 lanes and the per-child push logic with ~3: a
+// lane that popped a leaf sat out until every other lane of its warp had one too, and
+// every child hit took a divergent branch.  Here
+//   * leaves never go on the stack: an expansion drops its leaf hits into a small
+//     per-lane queue; a lane with queued leaves tests one triangle per iteration, a
+//     lane without expands its node, and both share one load sequence (if-if
+//     traversal with a unified 64-byte fetch), so lanes do not wait for each other's
+//     phase;
+//   * the child loop is straight-line: hit tests, nearest-child selection and the
+//     pushes are predicated, no branch per child;
+//   * stack and leaf queue live in shared memory only, addressed by running 32-bit
+//     shared addresses (st.shared/ld.shared), lane-interleaved; a ray that would
+//     overflow them is redone in the reference's order (counted in `resolved`);
+//   * a plane test is PRMT + FFMA: the byte-permute builds the float 2^23+q straight
+//     from the packed uint16, the affine map folds 2^23 into its offset.
+// Same exactness rule as Trav.
+constexpr int CB_PSTACK = 16;    // internal entries per lane
+constexpr int CB_PLEAF = 8;      // leaf queue per lane: one expansion's worth
+constexpr int CB_PLSTACK = 48;   // overflow entries per lane in local memory (rarely touched)
+constexpr uint32_t CB_PSTRIDE = 256u * 8u;   // bytes between consecutive entries of a lane (256 lanes x uint2)
+
+__device__ __forceinline__ void sts64(uint32_t addr, uint32_t x, uint32_t y)
+{
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ uint2 lds64(uint32_t addr)
+{
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+// Per-ray constants of the plane test t = (2^23 + q) * s + off, q = packed uint16 plane.
+// `off` folds the 2^23 and is widened by a bound on the difference between this
+// arithmetic and the reference's (intersect.h:112-157 on geometry.h:31-47 boxes), so
+// a box the reference would hit is never missed:
+//   ours:      inv 1 ulp (rcp.approx), s = scale*inv 1.5 ulp, a = (origin-o)*inv 2 ulp,
+//              off = a - 2^23 s half an ulp of (|a|+|b|)         -> 3.0e-7|a| + 2.4e-7|b|
+//   reference: lo = fma(q,scale,origin), t = fma(lo, 1/d, -o/d)   -> < 2.4e-7 (|lo|+|o|)/|d|
+struct PhasedRay {
+    float sx, sy, sz;
+    float nx, ny, nz, fx, fy, fz;     // near / far offsets (-inf / +inf when the axis is ignored)
+    uint32_t selx, sely, selz;        // PRMT selector of the near plane; far = near ^ 0x22
+};
+__device__ __forceinline__ void phased_ray_axis(float o, float d, float worigin, float wscale, float& s, float& n,
+                                                float& f, uint32_t& sel)
+{
+    const float INF = __int_as_float(0x7f800000);
+    const float inv = 1.0f / d;
+    if (isfinite(inv)) {
+        s = wscale * inv;
+        const float a = (worigin - o) * inv, b = 8388608.0f * s;
+        const float off = a - b;
+        const float c = (fabsf(worigin) + fabsf(o) + 65536.0f * wscale) * fabsf(inv);
+        const float e = 6e-7f * c + 3e-7f * fabsf(b);
+        n = off - e; f = off + e;
+        sel = (inv >= 0.0f) ? 0x7610u : 0x7632u;   // low half first when the ray runs towards +axis
+    } else {                                       // the reference skips such an axis (intersect.h:120)
+        s = 0.0f; n = -INF; f = INF; sel = 0x7610u;
+    }
+}
+__device__ __forceinline__ bool hit_box_phased(const PhasedRay& r, uint32_t px, uint32_t py, uint32_t pz, float& tnear)
+{
+    const uint32_t K = 0x4B000000u;                // bytes {q_lo, q_hi, 0x00, 0x4B} = 2^23 + q
+    const float tnx = __fmaf_rn(__uint_as_float(prmt(px, K, r.selx)), r.sx, r.nx);
+    const float tfx = __fmaf_rn(__uint_as_float(prmt(px, K, r.selx ^ 0x22u)), r.sx, r.fx);
+    const float tny = __fmaf_rn(__uint_as_float(prmt(py, K, r.sely)), r.sy, r.ny);
+    const float tfy = __fmaf_rn(__uint_as_float(prmt(py, K, r.sely ^ 0x22u)), r.sy, r.fy);
+    const float tnz = __fmaf_rn(__uint_as_float(prmt(pz, K, r.selz)), r.sz, r.nz);
+    const float tfz = __fmaf_rn(__uint_as_float(prmt(pz, K, r.selz ^ 0x22u)), r.sz, r.fz);
+    const float tmin = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.0f));
+    const float tmax = fminf(fminf(tfx, tfy), tfz);
+    tnear = tmin;
+    return !(tmin > tmax);
+}
+
+struct PTrav {
+    float3 origin, direction;
+    PhasedRay r;
+    float best_t, limit, cur_t;
+    uint32_t best_rank, cur;
+    int best_tri, last_hit;
+    uint32_t sp, lq;           // shared addresses one past the top of this lane's stack / leaf queue
+    int lsp;                   // entries in the local-memory overflow area (on top of the shared ones)
+    bool have, redo;
+
+    __device__ __forceinline__ void pop_next(uint32_t sbase, const uint2* lstack)
+    {
+        have = false;
+        while (lsp > 0 || sp > sbase) {
+            uint2 e;
+            if (lsp > 0) e = lstack[--lsp];
+            else { sp -= CB_PSTRIDE; e = lds64(sp); }
+            if (!(__uint_as_float(e.y) > limit)) { cur = e.x; cur_t = __uint_as_float(e.y); have = true; break; }
+        }
+    }
+
+    // returns false when the ray misses the world box (result: no hit)
+    __device__ __forceinline__ bool init(const DevGeometry& g, const float3& o, const float3& d, int last,
+                                         uint32_t sbase, uint32_t lbase)
+    {
+        const float INF = __int_as_float(0x7f800000);
+        origin = o; direction = d; last_hit = last;
+        phased_ray_axis(o.x, d.x, g.world_origin.x, g.world_scale, r.sx, r.nx, r.fx, r.selx);
+        phased_ray_axis(o.y, d.y, g.world_origin.y, g.world_scale, r.sy, r.ny, r.fy, r.sely);
+        phased_ray_axis(o.z, d.z, g.world_origin.z, g.world_scale, r.sz, r.nz, r.fz, r.selz);
+        best_tri = -1; best_rank = 0xFFFFFFFFu; best_t = INF; limit = INF;
+        sp = sbase; lq = lbase; lsp = 0; cur = g.root_w; cur_t = 0.0f; redo = false;
+        float tn;                                  // the world-box test stays in the reference's arithmetic (mesh.h:60)
+        have = hit_box_exact(g, o, d, g.ref_root_x, g.ref_root_y, g.ref_root_z, tn) && (g.root_w >> 28) != 0;
+        return have;
+    }
+
+    // ---- expansion of the current internal entry, in bursts of four children
+    struct Nearest { uint32_t w; float t; };     // nearest internal hit so far (w == 0: none; an internal word is never 0)
+
+    // test children i..i+3 of the current entry (already fetched into nd; slots >= n hold a copy of child n-1)
+    template <bool COUNT>
+    __device__ __forceinline__ void process4(const uint4 (&nd)[4], uint32_t i, uint32_t n, Nearest& nr, uint32_t sbase,
+                                             uint2* lstack, TraverseCounters* cnt)
+    {
+        const uint32_t stop = sbase + CB_PSTACK * CB_PSTRIDE;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            float tmin;
+            const bool ok = hit_box_phased(r, nd[k].x, nd[k].y, nd[k].z, tmin) && !(tmin > limit) && (i + k < n);
+            if (COUNT) cnt->nodes += (i + k < n);
+            const uint32_t w = nd[k].w;
+            const bool is_leaf = ok && w < 0x10000000u;
+            const bool is_int = ok && w >= 0x10000000u;
+            if (is_leaf) sts64(lq, w, __float_as_uint(tmin));
+            lq += is_leaf ? CB_PSTRIDE : 0u;
+            // keep the nearest internal hit in registers, the others go to the stack
+            const bool better = is_int && tmin < nr.t;
+            const uint32_t pw = better ? nr.w : w;
+            const float pt = better ? nr.t : tmin;
+            nr.w = better ? w : nr.w;
+            nr.t = better ? tmin : nr.t;
+            const bool want_push = is_int && pw != 0;
+            const bool do_push = want_push && sp < stop;
+            if (do_push) sts64(sp, pw, __float_as_uint(pt));
+            sp += do_push ? CB_PSTRIDE : 0u;
+            if (want_push && !do_push) {               // rare: deeper than the shared-memory stack
+                if (lsp < CB_PLSTACK) lstack[lsp++] = make_uint2(pw, __float_as_uint(pt));
+                else redo = true;                      // redone in reference order
+            }
+        }
+    }
+    __device__ __forceinline__ void expand_end(const Nearest& nr, uint32_t sbase, const uint2* lstack)
+    {
+        if (nr.w) { cur = nr.w; cur_t = nr.t; }
+        else pop_next(sbase, lstack);
+    }
+
+    // ---- leaves
+    // next queued leaf worth testing (entries behind `limit` and the excluded triangle are dropped)
+    __device__ __forceinline__ bool pop_leaf(uint32_t lbase, uint32_t& tri)
+    {
+        while (lq > lbase) {
+            lq -= CB_PSTRIDE;
+            const uint2 e = lds64(lq);
+            if (!(__uint_as_float(e.y) > limit) && (int)e.x != last_hit) { tri = e.x; return true; }
+        }
+        return false;
+    }
+    // a, b, c: the first three float4 of the triangle's tri64 record
+    __device__ __forceinline__ void test_triangle(uint32_t tri, const float4& a, const float4& b, const float4& c)
+    {
+        float t;
+        if (hit_triangle(origin, direction, f3(a.x, a.y, a.z), f3(a.w, b.x, b.y), f3(b.z, b.w, c.x), t)) {
+            const uint32_t rank = __float_as_uint(c.y);
+            if (t < best_t || (t == best_t && rank < best_rank)) {
+                best_t = t; best_tri = (int)tri; best_rank = rank;
+                limit = best_t + 2e-5f * best_t;     // slack for the triangle test's own rounding
+            }
+        }
+    }
+    // after the leaf queue has drained: the pending node may have fallen behind the new limit
+    __device__ __forceinline__ void after_leaves(uint32_t sbase, uint32_t lbase, const uint2* lstack)
+    {
+        if (lq == lbase && have && cur_t > limit) pop_next(sbase, lstack);
+    }
+
+    // call once !have and the leaf queue is empty; returns the triangle (or -1) and its distance
+    template <bool COUNT>
+    __device__ __forceinline__ int finish(const DevGeometry& g, float& dist, uint32_t* overflow_flag, TraverseCounters* cnt)
+    {
+        if (best_tri != -1 && !redo) {
+            const float4 lb = __ldg(g.tri64 + 4ull * (uint32_t)best_tri + 3);
+            float box_t;
+            const bool in_box = hit_box_exact(g, origin, direction, __float_as_uint(lb.x), __float_as_uint(lb.y),
+                                              __float_as_uint(lb.z), box_t);
+            redo = !in_box || best_t < box_t;
+        }
+        if (redo) {
+            TraverseCounters local = {0, 0, 0};
+            float rd;
+            const int tri = traverse_reference_order<COUNT>(g, origin, direction, last_hit, rd, overflow_flag, &local);
+            if (COUNT) { cnt->nodes += local.nodes; cnt->tris += local.tris; cnt->resolved++; }
+            dist = rd;
+            return tri;
+        }
+        dist = (best_tri == -1) ? -1.0f : best_t;
+        return best_tri;
+    }
+};
 
 // ------------------------------------------------------------------ warp-cooperative traversal
 // One ray per WARP: the 32 lanes pop up to four entries from a shared-memory stack

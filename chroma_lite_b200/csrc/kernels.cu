@@ -139,6 +139,117 @@ intersect_kernel(DevGeometry g, RaySource src, uint64_t n, unsigned long long* c
     persistent_intersect<COUNT>(g, src, n, counters, sstack, counters);
 }
 
+// Second generation (PTrav), persistent with per-lane refill.  Every iteration each
+// lane takes ONE step: a lane with queued leaves tests a triangle, a lane without
+// expands its node; both fetch from one 64-byte block, so the warp issues a single
+// load sequence and waits for memory once per iteration.  Finished rays wait until
+// `refill_min` lanes are free and are then finished (winner re-check + store) and
+// replaced together with one atomic on the queue cursor.
+struct Tune { int refill_min; };
+#ifndef CB_INT2_BLOCKS
+#define CB_INT2_BLOCKS 2     /* resident CTAs per SM of the phased traversal kernels: 109 registers, no spills */
+#endif
+
+template <bool COUNT, class Source>
+__device__ __forceinline__ void persistent_intersect2(const DevGeometry& g, const Source& src, unsigned long long n,
+                                                      unsigned long long* cursor, uint32_t smem_base,
+                                                      unsigned long long* counters, const Tune tune)
+{
+    static_assert(CB_PSTRIDE == PROP_THREADS * 8u, "lane-interleaved stack stride");
+    const unsigned FULL = 0xffffffffu;
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const uint32_t sbase = smem_base + threadIdx.x * 8u;            // this lane's stack, entry e at sbase + e*CB_PSTRIDE
+    const uint32_t lbase = sbase + CB_PSTACK * CB_PSTRIDE;          // this lane's leaf queue
+    PTrav tv;
+    uint2 lstack[CB_PLSTACK];               // overflow of the shared-memory stack (local memory, rarely touched)
+    tv.have = false; tv.sp = sbase; tv.lq = lbase; tv.lsp = 0;
+    bool active = false, exhausted = false;
+    unsigned long long slot = 0;
+    TraverseCounters cnt = {0, 0, 0};
+    for (;;) {
+        const bool done = active && !tv.have && tv.lq == lbase;
+        const unsigned dm = __ballot_sync(FULL, done);
+        const unsigned fm = dm | __ballot_sync(FULL, !active);
+        const int nfree = __popc(fm);
+        if (nfree == 32 || nfree >= tune.refill_min || (exhausted && dm)) {
+            if (done) {
+                float dist;
+                const int tri = tv.template finish<COUNT>(g, dist, (uint32_t*)(counters + 3), &cnt);
+                src.store(slot, tri, dist);
+                active = false;
+            }
+            if (!exhausted) {
+                unsigned long long base = 0;
+                const int leader = __ffs(fm) - 1;
+                if ((int)lane == leader) base = atomicAdd(cursor, (unsigned long long)nfree);
+                base = __shfl_sync(FULL, base, leader);
+                if (!active) {
+                    const unsigned long long q = base + __popc(fm & lt_mask);
+                    if (q < n) {
+                        float3 o, d;
+                        int last;
+                        slot = q;
+                        if (src.load(q, o, d, last)) {
+                            active = tv.init(g, o, d, last, sbase, lbase);
+                            if (!active) src.store(slot, -1, -1.0f);
+                        }
+                    }
+                }
+                exhausted = (base + nfree >= n);
+            }
+        }
+        if (!__any_sync(FULL, active)) {
+            if (exhausted) break;
+            continue;
+        }
+        // One step per lane and iteration: a lane with queued leaves tests a triangle, a lane
+        // without expands its node.  Both kinds fetch four 16-byte words from one 64-byte
+        // block (a tri64 record / four child entries), so they share ONE load sequence and
+        // the warp waits for memory once per iteration.
+        uint32_t tri = 0;
+        const bool do_tri = active && tv.pop_leaf(lbase, tri);
+        const bool do_exp = active && !do_tri && tv.lq == lbase && tv.have;
+        const uint32_t first = tv.cur & 0x0FFFFFFFu, n = tv.cur >> 28;
+        const uint4* blk = do_tri ? reinterpret_cast<const uint4*>(g.tri64) + 4ull * tri : g.nodes + first;
+        const uint32_t last_k = do_tri ? 2u : n - 1u;
+        uint4 q[4];
+        if (do_tri || do_exp) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) q[k] = __ldg(blk + min((uint32_t)k, last_k));
+        }
+        if (do_tri) {
+            if (COUNT) cnt.tris++;
+            tv.test_triangle(tri, *reinterpret_cast<const float4*>(&q[0]), *reinterpret_cast<const float4*>(&q[1]),
+                             *reinterpret_cast<const float4*>(&q[2]));
+        } else if (do_exp) {
+            PTrav::Nearest nr = {0u, __int_as_float(0x7f800000)};
+            tv.template process4<COUNT>(q, 0, n, nr, sbase, lstack, &cnt);
+            if (n > 4) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) q[k] = __ldg(g.nodes + first + min(4u + k, n - 1u));
+                tv.template process4<COUNT>(q, 4, n, nr, sbase, lstack, &cnt);
+            }
+            tv.expand_end(nr, sbase, lstack);
+        }
+        if (active && !do_exp) tv.after_leaves(sbase, lbase, lstack);
+    }
+    if (COUNT) {
+        atomicAdd(counters + 1, (unsigned long long)cnt.nodes);
+        atomicAdd(counters + 2, (unsigned long long)cnt.tris);
+        atomicAdd(counters + 5, (unsigned long long)cnt.resolved);
+    }
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(PROP_THREADS, CB_INT2_BLOCKS)
+intersect2_kernel(const __grid_constant__ DevGeometry g, const __grid_constant__ RaySource src, uint64_t n,
+                  unsigned long long* counters, Tune tune)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    persistent_intersect2<COUNT>(g, src, n, counters, (uint32_t)__cvta_generic_to_shared(smem_raw), counters, tune);
+}
+
 // ---------------------------------------------------------------- propagation
 // Wavefront scheduler.  One propagate call = a loop over physics steps; each step is
 //   step_intersect_kernel : one ray per thread, traversal only (few registers, high
@@ -267,6 +378,36 @@ step_intersect_kernel(DevGeometry g, PropParams P)
     PhotonRaySource src;
     src.P = P;
     persistent_intersect<COUNT>(g, src, P.n_in, P.counters + 6, sstack, P.counters);
+}
+
+struct PhotonRaySourceRef {  // same as PhotonRaySource, reading the parameters in place
+    const PropParams& P;
+    __device__ __forceinline__ bool load(unsigned long long q, float3& o, float3& d, int& last) const
+    {
+        const uint32_t k = P.queue_in ? P.queue_in[q] : (uint32_t)q;
+        const uint64_t id = P.first + k;
+        if (P.step == 0 && (P.bank.flags[id] & 0xFFFFu & CB_TERMINAL)) return false;   // never ran: untouched
+        o = ld3(P.bank.pos, id);
+        d = ld3(P.bank.dir, id);
+        if (P.step == 0) d = d / norm(d);
+        last = P.bank.last_hit_triangles[id];
+        return true;
+    }
+    __device__ __forceinline__ void store(unsigned long long q, int tri, float dist) const
+    {
+        const uint32_t k = P.queue_in ? P.queue_in[q] : (uint32_t)q;
+        P.hit_tri[k] = tri;
+        P.hit_dist[k] = dist;
+    }
+};
+
+template <bool COUNT>
+__global__ void __launch_bounds__(PROP_THREADS, CB_INT2_BLOCKS)
+step_intersect2_kernel(const __grid_constant__ DevGeometry g, const __grid_constant__ PropParams P, Tune tune)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const PhotonRaySourceRef src = {P};
+    persistent_intersect2<COUNT>(g, src, P.n_in, P.counters + 6, (uint32_t)__cvta_generic_to_shared(smem_raw), P.counters, tune);
 }
 
 __global__ void __launch_bounds__(PROP_THREADS, 2)
@@ -632,6 +773,19 @@ static int check_bank(const CbPhotonBank* b, const char* who)
 }
 
 static size_t stack_smem_bytes() { return (size_t)CB_SSTACK * PROP_THREADS * sizeof(uint2); }
+static size_t stack2_smem_bytes() { return (size_t)(CB_PSTACK + CB_PLEAF) * PROP_THREADS * sizeof(uint2); }
+// CHROMA_B200_TRAV=lane selects the first-generation traversal kernels (A/B aid)
+static bool first_generation()
+{
+    const char* e = getenv("CHROMA_B200_TRAV");
+    return e && strcmp(e, "lane") == 0;
+}
+static Tune tune_from_env()
+{
+    Tune t = {12};
+    if (const char* e = getenv("CHROMA_B200_REFILL_MIN")) t.refill_min = atoi(e);
+    return t;
+}
 
 static int ensure_tile_scratch(uint64_t ntiles)
 {
@@ -693,14 +847,18 @@ int cb_intersect(cb_geom_t gh, const float* d_origins, const float* d_directions
         return fail(CB_ERR_INVALID, "cb_intersect: null array");
     Context& c = ctx();
     CB_CUDA(cudaMemsetAsync(c.d_counters, 0, 16 * sizeof(unsigned long long), c.stream));
-    size_t smem = stack_smem_bytes();
-    CB_CUDA(cudaFuncSetAttribute(intersect_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const bool gen1 = first_generation();
+    size_t smem = gen1 ? stack_smem_bytes() : stack2_smem_bytes();
+    CB_CUDA(cudaFuncSetAttribute(intersect_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stack_smem_bytes()));
+    CB_CUDA(cudaFuncSetAttribute(intersect2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stack2_smem_bytes()));
     int per_sm = 0;
-    CB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, intersect_kernel<false>, PROP_THREADS, smem));
+    if (gen1) CB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, intersect_kernel<false>, PROP_THREADS, smem));
+    else CB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, intersect2_kernel<false>, PROP_THREADS, smem));
     if (per_sm < 1) per_sm = 1;
     unsigned blocks = (unsigned)std::min<uint64_t>((n + PROP_THREADS - 1) / PROP_THREADS, (uint64_t)c.sm_count * per_sm);
     RaySource src = {d_origins, d_directions, d_last_hit, d_triangle_out, d_distance_out};
-    intersect_kernel<false><<<blocks, PROP_THREADS, smem, c.stream>>>(g->dev, src, n, c.d_counters);
+    if (gen1) intersect_kernel<false><<<blocks, PROP_THREADS, smem, c.stream>>>(g->dev, src, n, c.d_counters);
+    else intersect2_kernel<false><<<blocks, PROP_THREADS, smem, c.stream>>>(g->dev, src, n, c.d_counters, tune_from_env());
     CB_CUDA(cudaGetLastError());
     CB_CUDA(cudaMemcpyAsync(c.h_counters, c.d_counters, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c.stream));
     CB_CUDA(cudaStreamSynchronize(c.stream));
@@ -727,6 +885,11 @@ int cb_propagate(const CbPhotonBank* bank, cb_geom_t gh, cb_rng_t rh, int32_t nt
     if (bank->n == 0 || max_steps <= 0) return CB_OK;
     Context& c = ctx();
     const bool count = getenv("CHROMA_B200_STATS") != nullptr;
+    const bool gen1 = first_generation();
+    const Tune tune = tune_from_env();
+    const bool trace = getenv("CHROMA_B200_TRACE") != nullptr;   // per-step timing to stderr (debug aid)
+    cudaEvent_t tev[3] = {nullptr, nullptr, nullptr};
+    if (trace) for (auto& e : tev) cudaEventCreate(&e);
     // hand the rest to the persistent kernel once the survivors fit on the chip ~1.3 times over
     const uint64_t tail_threshold = getenv("CHROMA_B200_TAIL") ? (uint64_t)atoll(getenv("CHROMA_B200_TAIL")) : (uint64_t)(1.3 * 2048 * ctx().sm_count);
 
@@ -750,15 +913,18 @@ int cb_propagate(const CbPhotonBank* bank, cb_geom_t gh, cb_rng_t rh, int32_t nt
     const uint64_t sort_threshold = getenv("CHROMA_B200_SORT") ? (uint64_t)atoll(getenv("CHROMA_B200_SORT")) : 0;
 
     auto k_int = count ? step_intersect_kernel<true> : step_intersect_kernel<false>;
+    auto k_int2 = count ? step_intersect2_kernel<true> : step_intersect2_kernel<false>;
     auto k_tail = count ? propagate_tail_kernel<true> : propagate_tail_kernel<false>;
-    const size_t smem_int = stack_smem_bytes();
+    const size_t smem_int = gen1 ? stack_smem_bytes() : stack2_smem_bytes();
     const size_t smem_tab = (g->smem_table_bytes + 127u) & ~127u;
     const size_t smem_tail = smem_tab + (size_t)(TAIL_THREADS / 32) * (CB_WSTACK + CB_WLEAF) * sizeof(uint2);
-    CB_CUDA(cudaFuncSetAttribute(k_int, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_int));
+    CB_CUDA(cudaFuncSetAttribute(k_int, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stack_smem_bytes()));
+    CB_CUDA(cudaFuncSetAttribute(k_int2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stack2_smem_bytes()));
     CB_CUDA(cudaFuncSetAttribute(step_physics_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_tab, 16)));
     CB_CUDA(cudaFuncSetAttribute(k_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tail));
     int phys_per_sm = 0, tail_per_sm = 0, int_per_sm = 0;
-    CB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&int_per_sm, k_int, PROP_THREADS, smem_int));
+    if (gen1) CB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&int_per_sm, k_int, PROP_THREADS, smem_int));
+    else CB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&int_per_sm, k_int2, PROP_THREADS, smem_int));
     if (int_per_sm < 1) int_per_sm = 1;
     CB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&phys_per_sm, step_physics_kernel, PROP_THREADS, smem_tab));
     CB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tail_per_sm, k_tail, TAIL_THREADS, smem_tail));
@@ -788,8 +954,14 @@ int cb_propagate(const CbPhotonBank* bank, cb_geom_t gh, cb_rng_t rh, int32_t nt
                 const uint64_t per_block = TAIL_THREADS / 32;          // one photon per warp
                 unsigned blocks = (unsigned)std::min<uint64_t>((n_alive + per_block - 1) / per_block,
                                                                (uint64_t)c.sm_count * tail_per_sm);
+                if (trace) cudaEventRecord(tev[0], c.stream);
                 k_tail<<<blocks, TAIL_THREADS, smem_tail, c.stream>>>(g->dev, P);
                 CB_CUDA(cudaGetLastError());
+                if (trace) {
+                    cudaEventRecord(tev[1], c.stream); cudaEventSynchronize(tev[1]);
+                    float ms = 0; cudaEventElapsedTime(&ms, tev[0], tev[1]);
+                    fprintf(stderr, "[cb trace] step %d tail: %llu photons %.3f ms\n", step, (unsigned long long)n_alive, ms);
+                }
                 launches++;
                 n_alive = 0;
                 break;
@@ -808,16 +980,26 @@ int cb_propagate(const CbPhotonBank* bank, cb_geom_t gh, cb_rng_t rh, int32_t nt
             unsigned iblocks = (unsigned)std::min<uint64_t>(blocks, (uint64_t)c.sm_count * int_per_sm);
             const bool time_it = (step == 0 && first == 0);
             if (time_it) CB_CUDA(cudaEventRecord(c.iev0, c.stream));
-            k_int<<<iblocks, PROP_THREADS, smem_int, c.stream>>>(g->dev, P);
+            if (trace) cudaEventRecord(tev[0], c.stream);
+            if (gen1) k_int<<<iblocks, PROP_THREADS, smem_int, c.stream>>>(g->dev, P);
+            else k_int2<<<iblocks, PROP_THREADS, smem_int, c.stream>>>(g->dev, P, tune);
+            if (trace) cudaEventRecord(tev[1], c.stream);
             if (time_it) { CB_CUDA(cudaEventRecord(c.iev1, c.stream)); int0_rays = n_alive; }
             unsigned pblocks = (unsigned)std::min<uint64_t>(blocks, (uint64_t)c.sm_count * phys_per_sm);
             step_physics_kernel<<<pblocks, PROP_THREADS, smem_tab, c.stream>>>(g->dev, P);
             CB_CUDA(cudaGetLastError());
             launches += 2;
+            if (trace) cudaEventRecord(tev[2], c.stream);
             CB_CUDA(cudaMemcpyAsync(c.h_counters, c.d_counters, 8, cudaMemcpyDeviceToHost, c.stream));
             CB_CUDA(cudaMemsetAsync(c.d_counters, 0, 8, c.stream));
             CB_CUDA(cudaMemsetAsync(c.d_counters + 6, 0, 8, c.stream));
             CB_CUDA(cudaStreamSynchronize(c.stream));
+            if (trace) {
+                float a = 0, b = 0;
+                cudaEventElapsedTime(&a, tev[0], tev[1]); cudaEventElapsedTime(&b, tev[1], tev[2]);
+                fprintf(stderr, "[cb trace] step %d: %llu rays intersect %.3f ms physics %.3f ms -> %llu alive\n",
+                        step, (unsigned long long)n_alive, a, b, c.h_counters[0]);
+            }
             tot[4] += n_alive;                       // every queued photon took one step
             n_alive = c.h_counters[0];
             q_in = c.d_queue[qsel];
@@ -829,6 +1011,7 @@ int cb_propagate(const CbPhotonBank* bank, cb_geom_t gh, cb_rng_t rh, int32_t nt
     }
     CB_CUDA(cudaEventRecord(c.kev1, c.stream));
     CB_CUDA(cudaEventSynchronize(c.kev1));
+    if (trace) for (auto& e : tev) cudaEventDestroy(e);
     if (stats) {
         stats->photons = bank->n; stats->steps = tot[4]; stats->nodes_visited = tot[1]; stats->tris_tested = tot[2];
         stats->rays_resolved = tot[5];

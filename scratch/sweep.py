@@ -1,0 +1,58 @@
+"""Scratch: build the 29k-PMT scene once, then time cb_propagate under several env settings.
+usage: python scratch/sweep.py "DEFER=0,TAIL=98304" "DEFER=28" ...   (TRACE=1 prints per-step times)
+       CHROMA_B200_LIB variants are not switchable in-process; run once per library."""
+import os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
+import numpy as np
+import bench
+
+
+def main():
+    from chroma_lite_b200 import gpu, sim, _lib
+    _lib.init(0)
+    lib = _lib.lib()
+    workload = os.environ.get('WORKLOAD', 'pmt29k')
+    n = int(os.environ.get('PHOTONS', '2500000'))
+    det = bench.build_detector(workload, {})
+    s = sim.Simulation(det, seed=42, cuda_device=0, nthreads_per_block=512, max_blocks=max(1024, -(-n // 512)))
+    g, rng = s.gpu_geometry, s.rng_states
+    ev = bench.make_event(n, seed=1000)
+    gp = gpu.GPUPhotons(ev); pristine = gpu.GPUPhotons(ev)
+    fields = ('pos', 'dir', 'pol', 'wavelengths', 't', 'last_hit_triangles', 'flags', 'weights', 'evidx')
+
+    def one():
+        for f in fields:
+            getattr(gp, f).copy_from_device(getattr(pristine, f).ptr)
+        lib.cb_flush_l2()
+        gp.propagate(g, rng, nthreads_per_block=512, max_blocks=s.max_blocks, max_steps=100)
+        return gp.last_stats
+
+    ref_flags = None
+    for spec in sys.argv[1:] or ['']:
+        keys = []
+        for kv in filter(None, spec.split(',')):
+            k, v = kv.split('=')
+            os.environ['CHROMA_B200_' + k] = v
+            keys.append('CHROMA_B200_' + k)
+        os.environ.pop('CHROMA_B200_TRACE', None) if 'CHROMA_B200_TRACE' not in keys else None
+        tr = os.environ.pop('CHROMA_B200_TRACE', None)
+        for _ in range(3):
+            one()
+        ms = [one().kernel_ms for _ in range(5)]
+        st = gp.last_stats
+        print('SPEC %-40s kernel ms median %.3f min %.3f  launches %d  int0 %.3f ms' %
+              (spec, float(np.median(ms)), min(ms), st.launches, st.intersect0_ms), flush=True)
+        if st.nodes_visited:
+            print('     stats: steps %d entries/trav %.1f tris/trav %.2f redone %.3g' % (st.steps, st.nodes_visited / st.steps,
+                  st.tris_tested / st.steps, st.rays_resolved / st.steps), flush=True)
+        if tr:
+            os.environ['CHROMA_B200_TRACE'] = tr
+            one()
+            os.environ.pop('CHROMA_B200_TRACE')
+        for k in keys:
+            os.environ.pop(k, None)
+
+
+if __name__ == '__main__':
+    main()
