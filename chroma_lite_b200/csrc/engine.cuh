@@ -210,39 +210,6 @@ __device__ __forceinline__ bool hit_box(const DevGeometry& g, const RaySetup& r,
     return !(tmin > tmax);
 }
 
-// Traversal-side box test.  Same boxes, cheaper arithmetic: per ray the affine map
-// t = q*(scale/d) + (world_origin - o)/d is folded into one FFMA per plane, the
-// uint16 -> float conversion is an integer multiply-add into the mantissa of 2^16
-// (exact), and the near/far plane of each axis is picked by the sign of d with one
-// byte-permute, so no min/max per axis is needed.  It differs from the reference's
-// arithmetic by rounding only (the guard band of traverse() covers that); the
-// reference-exact hit_box() above is still what decides order-sensitivity.
-struct FastRay {
-    float sx, sy, sz;          // world_scale / d
-    float nx, ny, nz;          // offset for the near planes  (-inf when the axis is ignored)
-    float fx, fy, fz;          // offset for the far planes   (+inf when the axis is ignored)
-    uint32_t selx, sely, selz; // byte-permute selectors: low half = near plane, high half = far plane
-};
-__device__ __forceinline__ void fast_ray_axis(float o, float d, float worigin, float wscale, float& s, float& n, float& f, uint32_t& sel)
-{
-    const float INF = __int_as_float(0x7f800000);
-    const float inv = 1.0f / d;
-    if (isfinite(inv)) {
-        s = wscale * inv;
-        const float a = (worigin - o) * inv, b = 65536.0f * s;  // the conversion below yields 65536 + q
-        const float off = a - b;
-        // interval arithmetic: widen this axis' slab by the rounding bound of its own
-        // affine map (a few ulps of the largest term), so a box the reference's
-        // arithmetic would hit is never missed here, whatever the ray direction
-        const float e = 5e-7f * (fabsf(a) + 2.0f * fabsf(b));
-        n = off - e; f = off + e;
-        sel = (inv >= 0.0f) ? 0x3210u : 0x1032u;                // swap halves when the ray runs towards -axis
-    } else {                                                   // the reference skips such an axis (intersect.h:120)
-        s = 0.0f; n = -INF; f = INF; sel = 0x3210u;
-    }
-}
-__device__ __forceinline__ float q16f_lo(uint32_t w) { return __uint_as_float((w & 0xFFFFu) * 128u + 0x47800000u); }
-__device__ __forceinline__ float q16f_hi(uint32_t w) { return __uint_as_float((w >> 16) * 128u + 0x47800000u); }
 // slab test in the reference's arithmetic, recomputing the ray setup (rare path)
 static __device__ __noinline__ bool hit_box_exact(const DevGeometry& g, const float3 o, const float3 d,
                                                   uint32_t px, uint32_t py, uint32_t pz, float& tnear)
@@ -254,30 +221,13 @@ static __device__ __noinline__ bool hit_box_exact(const DevGeometry& g, const fl
     return hit_box(g, rr, px, py, pz, tnear);
 }
 
-// Conservative: never misses a box the reference's arithmetic hits (slabs widened per
-// axis in fast_ray_axis); `tnear` is a lower bound of the reference's tmin.  A winner
-// found through a box the reference would have rejected is caught in finish().
-__device__ __forceinline__ bool hit_box_fast(const FastRay& r, uint32_t px, uint32_t py, uint32_t pz, float& tnear)
-{
-    const uint32_t ax = __byte_perm(px, 0, r.selx), ay = __byte_perm(py, 0, r.sely), az = __byte_perm(pz, 0, r.selz);
-    const float tnx = __fmaf_rn(q16f_lo(ax), r.sx, r.nx), tfx = __fmaf_rn(q16f_hi(ax), r.sx, r.fx);
-    const float tny = __fmaf_rn(q16f_lo(ay), r.sy, r.ny), tfy = __fmaf_rn(q16f_hi(ay), r.sy, r.fy);
-    const float tnz = __fmaf_rn(q16f_lo(az), r.sz, r.nz), tfz = __fmaf_rn(q16f_hi(az), r.sz, r.fz);
-    const float tmin = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.0f));
-    const float tmax = fminf(fminf(tfx, tfy), tfz);
-    tnear = tmin;
-    return !(tmin > tmax);
-}
-
 // ------------------------------------------------------------------ traversal
-constexpr int CB_SSTACK = 16;   // stack entries per lane in shared memory (lane-interleaved)
-constexpr int CB_LSTACK = 48;   // overflow entries per lane in local memory (rarely touched)
 constexpr int CB_RSTACK = 64;   // local stack of the reference-order fallback
 
 // Exact emulation of the reference's visit order (behaviour of mesh.h:45-126:
 // children ascending, leaves tested on the spot, internal children pushed and
 // popped LIFO, prune against the current minimum).  Only used for the rare rays
-// the ordered traversal flags as order-sensitive (see traverse()).
+// the traversal flags as order-sensitive (see PTrav::finish).
 template <bool COUNT>
 static __device__ __noinline__ int traverse_reference_order(const DevGeometry& g, const float3 origin,
                                                             const float3 direction, int last_hit,
@@ -331,178 +281,24 @@ static __device__ __noinline__ int traverse_reference_order(const DevGeometry& g
     return triangle_index;
 }
 
-// Nearest-hit search over the engine's tree (bvh_native.cu; same entry format as
-// the reference, children of a node contiguous), written as a resumable state
-// machine so that a persistent warp can retire finished rays and refill the idle
-// lanes instead of waiting for its longest ray (the first version kept only ~6 of
-// 32 lanes busy).
-//   * ONE uniform loop: pop an entry; an internal entry expands its <= 8 children
-//     (two bursts of four 128-bit loads), continues with the nearest hit child and
-//     pushes the others; a leaf entry runs the triangle test.  Leaves travel on
-//     the stack with their box distance, so they are culled again at pop time and
-//     there is a single copy of each code path (the 4x unrolled inline triangle
-//     test of the first version thrashed the instruction cache).
-//   * round(): one "expand until a leaf comes up" phase followed by one "triangle
-//     tests while leaves keep coming" phase (while-while traversal).
-//   * lane-interleaved shared-memory stack: entry e of lane l at stack[e*stride+l],
-//     conflict-free, with a local-memory overflow area.
-//   * (distance, reference-test-rank) lexicographic minimum reproduces the
-//     reference's first-tested-wins tie rule under ANY visit order (SURVEY A-1).
-// Exactness: the reference returns the same lexicographic minimum unless it never
-// tests the winner, which can only happen when the winner's hit lies in front of
-// its own (reference) leaf box in float arithmetic (t < box tmin).  Boxes are
-// pruned with a small guard band so that such a winner is always seen; those rays
-// (~1e-7) are redone in the reference's own visit order on the reference tree.
-#ifdef CB_TRAV_IFIF
-#define CB_PHASE_LOOP if      /* one expansion + one triangle test per round */
-#else
-#define CB_PHASE_LOOP while   /* while-while */
-#endif
-struct Trav {
-    float3 origin, direction;
-    FastRay r;
-    float best_t, limit, cur_t;
-    uint32_t best_rank, cur;
-    int best_tri, last_hit, sp;
-    bool have, redo;
-    uint2 lstack[CB_LSTACK];
-
-    __device__ __forceinline__ void push(uint2* sstack, int sstride, uint2 e)
-    {
-        if (sp < CB_SSTACK) sstack[sp * sstride] = e; else lstack[sp - CB_SSTACK] = e;
-        sp++;
-    }
-    __device__ __forceinline__ void pop_next(const uint2* sstack, int sstride)
-    {
-        have = false;
-        while (sp > 0) {
-            --sp;
-            const uint2 e = (sp < CB_SSTACK) ? sstack[sp * sstride] : lstack[sp - CB_SSTACK];
-            if (!(__uint_as_float(e.y) > limit)) { cur = e.x; cur_t = __uint_as_float(e.y); have = true; break; }
-        }
-    }
-
-    // returns false when the ray misses the world box (result: no hit)
-    __device__ __forceinline__ bool init(const DevGeometry& g, const float3& o, const float3& d, int last)
-    {
-        const float INF = __int_as_float(0x7f800000);
-        origin = o; direction = d; last_hit = last;
-        fast_ray_axis(o.x, d.x, g.world_origin.x, g.world_scale, r.sx, r.nx, r.fx, r.selx);
-        fast_ray_axis(o.y, d.y, g.world_origin.y, g.world_scale, r.sy, r.ny, r.fy, r.sely);
-        fast_ray_axis(o.z, d.z, g.world_origin.z, g.world_scale, r.sz, r.nz, r.fz, r.selz);
-        best_tri = -1; best_rank = 0xFFFFFFFFu; best_t = INF; limit = INF;
-        sp = 0; cur = g.root_w; cur_t = 0.0f; redo = false;
-        // the world-box test itself stays in the reference's arithmetic (mesh.h:60)
-        RaySetup rr;
-        rr.noid = f3(-o.x / d.x, -o.y / d.y, -o.z / d.z);
-        rr.inv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
-        rr.fx = isfinite(rr.inv.x); rr.fy = isfinite(rr.inv.y); rr.fz = isfinite(rr.inv.z);
-        float tn;
-        have = hit_box(g, rr, g.ref_root_x, g.ref_root_y, g.ref_root_z, tn) && (g.root_w >> 28) != 0;
-        return have;
-    }
-
-    template <bool COUNT>
-    __device__ __forceinline__ void round(const DevGeometry& g, uint2* sstack, int sstride, TraverseCounters* cnt)
-    {
-        const float INF = __int_as_float(0x7f800000);
-        // ---- phase A: expand internal entries until a leaf comes up
-        CB_PHASE_LOOP (have && (cur >> 28) != 0) {
-            const uint32_t first = cur & 0x0FFFFFFFu;
-            const uint32_t n = cur >> 28;
-            uint32_t near_w = 0;
-            float near_t = INF;
-            bool near_ok = false;
-            for (uint32_t i = 0; i < n; i += 4) {
-                uint4 nd[4];
-#pragma unroll
-                for (int k = 0; k < 4; k++) nd[k] = __ldg(&g.nodes[first + min(i + k, n - 1)]);
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    float tmin;
-                    bool ok = false;
-                    if (i + k < n) {
-                        ok = hit_box_fast(r, nd[k].x, nd[k].y, nd[k].z, tmin) && !(tmin > limit);
-                        if (COUNT) cnt->nodes++;
-                    }
-                    if (ok) {
-                        uint32_t w = nd[k].w;
-                        if (!near_ok || tmin < near_t) {          // new nearest: the old one goes to the stack
-                            const uint32_t ow = near_w; const float ot = near_t; const bool had = near_ok;
-                            near_w = w; near_t = tmin; near_ok = true;
-                            w = ow; tmin = ot;
-                            if (!had) continue;
-                        }
-                        if (sp < CB_SSTACK + CB_LSTACK) push(sstack, sstride, make_uint2(w, __float_as_uint(tmin)));
-                        else redo = true;
-                    }
-                }
-            }
-            if (near_ok) { cur = near_w; cur_t = near_t; }
-            else pop_next(sstack, sstride);
-        }
-        // ---- phase B: triangle tests while leaves keep coming
-        CB_PHASE_LOOP (have && (cur >> 28) == 0) {
-            if ((int)cur != last_hit) {
-                if (COUNT) cnt->tris++;
-                const float4* tp = g.tri64 + 4ull * cur;
-                const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
-                float t;
-                if (hit_triangle(origin, direction, f3(a.x, a.y, a.z), f3(a.w, b.x, b.y), f3(b.z, b.w, c.x), t)) {
-                    const uint32_t rank = __float_as_uint(c.y);
-                    if (t < best_t || (t == best_t && rank < best_rank)) {
-                        best_t = t; best_tri = (int)cur; best_rank = rank;
-                        limit = best_t + 2e-5f * best_t;     // slack for the triangle test's own rounding
-                    }
-                }
-            }
-            pop_next(sstack, sstride);
-        }
-    }
-
-    // call once have == false; returns the triangle (or -1) and its distance
-    template <bool COUNT>
-    __device__ __forceinline__ int finish(const DevGeometry& g, float& dist, uint32_t* overflow_flag, TraverseCounters* cnt)
-    {
-        if (best_tri != -1 && !redo) {
-            // order-sensitivity test on the winner, in the reference's own arithmetic:
-            // is the hit in front of the reference's leaf box of that triangle?
-            const float4 lb = __ldg(g.tri64 + 4ull * (uint32_t)best_tri + 3);
-            RaySetup rr;
-            rr.noid = f3(-origin.x / direction.x, -origin.y / direction.y, -origin.z / direction.z);
-            rr.inv = f3(1.0f / direction.x, 1.0f / direction.y, 1.0f / direction.z);
-            rr.fx = isfinite(rr.inv.x); rr.fy = isfinite(rr.inv.y); rr.fz = isfinite(rr.inv.z);
-            float box_t;
-            const bool in_box = hit_box(g, rr, __float_as_uint(lb.x), __float_as_uint(lb.y), __float_as_uint(lb.z), box_t);
-            redo = !in_box || best_t < box_t;
-        }
-        if (redo) {
-            if (COUNT) cnt->resolved++;
-            return traverse_reference_order<COUNT>(g, origin, direction, last_hit, dist, overflow_flag, cnt);
-        }
-        dist = (best_tri == -1) ? -1.0f : best_t;
-        return best_tri;
-    }
-};
-
-// one ray, start to finish (used where a lane owns a whole photon history)
-template <bool COUNT>
-__device__ __forceinline__ int traverse(const DevGeometry& g, const float3& origin,
-                                        const float3& direction, int last_hit, float& best_t,
-                                        uint2* sstack, int sstride, uint32_t* overflow_flag,
-                                        TraverseCounters* cnt)
-{
-    Trav tv;
-    tv.init(g, origin, direction, last_hit);
-    while (tv.have) tv.template round<COUNT>(g, sstack, sstride, cnt);
-    return tv.template finish<COUNT>(g, best_t, overflow_flag, cnt);
-}
-
 // ------------------------------------------------------------------ phased traversal
-// Second-generation one-ray-per-lane traversal.  Profiling the first one (Trav) showed
-// the box tests running with ~9 of 32 lanes and the per-child push logic with ~3: a
-// lane that popped a leaf sat out until every other lane of its warp had one too, and
-// every child hit took a divergent branch.  Here
+// One ray per lane over the engine's tree (bvh_native.cu: same 16-byte entry format
+// as the reference, <= 8 children per node stored contiguously).
+//
+// Exactness (what makes ANY visit order return the reference's triangle, SURVEY A-1):
+//   * the result is the lexicographic minimum of (distance, reference test rank) over
+//     all triangle hits, the triangle test being pinned to the reference's arithmetic;
+//   * boxes are culled against limit = best_t * (1 + 2e-5) with slabs widened by the
+//     rounding bound of the plane arithmetic (phased_ray_axis), so no box that the
+//     reference's arithmetic would enter with a candidate inside is ever skipped;
+//   * the reference returns the same minimum unless it never tests the winner, which
+//     needs the winner's hit to lie in FRONT of its own reference leaf box in float
+//     arithmetic; finish() re-evaluates exactly that in the reference's arithmetic
+//     and such rays (~5e-7) are redone in the reference's own visit order on the
+//     reference tree (traverse_reference_order).
+//
+// Scheduling.  A first version (while-while, leaves on the stack, one branch per
+// child hit) ran its box tests with ~9 of 32 lanes and the push logic with ~3.  Here
 //   * leaves never go on the stack: an expansion drops its leaf hits into a small
 //     per-lane queue; a lane with queued leaves tests one triangle per iteration, a
 //     lane without expands its node, and both share one load sequence (if-if
@@ -510,12 +306,11 @@ __device__ __forceinline__ int traverse(const DevGeometry& g, const float3& orig
 //     phase;
 //   * the child loop is straight-line: hit tests, nearest-child selection and the
 //     pushes are predicated, no branch per child;
-//   * stack and leaf queue live in shared memory only, addressed by running 32-bit
-//     shared addresses (st.shared/ld.shared), lane-interleaved; a ray that would
-//     overflow them is redone in the reference's order (counted in `resolved`);
+//   * stack and leaf queue live in shared memory, addressed by running 32-bit shared
+//     addresses (st.shared/ld.shared), lane-interleaved, with a local-memory overflow
+//     area behind the stack (touched by ~2 % of the rays of the 29k-PMT detector);
 //   * a plane test is PRMT + FFMA: the byte-permute builds the float 2^23+q straight
 //     from the packed uint16, the affine map folds 2^23 into its offset.
-// Same exactness rule as Trav.
 constexpr int CB_PSTACK = 16;    // internal entries per lane
 constexpr int CB_PLEAF = 8;      // leaf queue per lane: one expansion's worth
 constexpr int CB_PLSTACK = 48;   // overflow entries per lane in local memory (rarely touched)
@@ -624,8 +419,8 @@ struct PTrav {
 
     // test children i..i+3 of the current entry (already fetched into nd; slots >= n hold a copy of child n-1)
     template <bool COUNT>
-    __device__ __forceinline__ void process4(const uint4 (&nd)[4], uint32_t i, uint32_t n, Nearest& nr, uint32_t sbase,
-                                             uint2* lstack, TraverseCounters* cnt)
+    __device__ __forceinline__ void process4(const uint4 (&nd)[4], uint32_t i, uint32_t n, Nearest& nr,
+                                             uint32_t sbase, uint2* lstack, TraverseCounters* cnt)
     {
         const uint32_t stop = sbase + CB_PSTACK * CB_PSTRIDE;
 #pragma unroll
@@ -732,10 +527,10 @@ __device__ __forceinline__ int warp_traverse(const DevGeometry& g, const float3&
     const float INF = __int_as_float(0x7f800000);
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
-    FastRay r;
-    fast_ray_axis(origin.x, direction.x, g.world_origin.x, g.world_scale, r.sx, r.nx, r.fx, r.selx);
-    fast_ray_axis(origin.y, direction.y, g.world_origin.y, g.world_scale, r.sy, r.ny, r.fy, r.sely);
-    fast_ray_axis(origin.z, direction.z, g.world_origin.z, g.world_scale, r.sz, r.nz, r.fz, r.selz);
+    PhasedRay r;
+    phased_ray_axis(origin.x, direction.x, g.world_origin.x, g.world_scale, r.sx, r.nx, r.fx, r.selx);
+    phased_ray_axis(origin.y, direction.y, g.world_origin.y, g.world_scale, r.sy, r.ny, r.fy, r.sely);
+    phased_ray_axis(origin.z, direction.z, g.world_origin.z, g.world_scale, r.sz, r.nz, r.fz, r.selz);
     RaySetup rr;
     rr.noid = f3(-origin.x / direction.x, -origin.y / direction.y, -origin.z / direction.z);
     rr.inv = f3(1.0f / direction.x, 1.0f / direction.y, 1.0f / direction.z);
@@ -799,7 +594,7 @@ __device__ __forceinline__ int warp_traverse(const DevGeometry& g, const float3&
         if (which < take && (uint32_t)c < n && !(__uint_as_float(e.y) > limit)) {
             const uint4 nd = __ldg(&g.nodes[first + c]);
             if (COUNT) cnt->nodes++;
-            ok = hit_box_fast(r, nd.x, nd.y, nd.z, tmin) && !(tmin > limit);
+            ok = hit_box_phased(r, nd.x, nd.y, nd.z, tmin) && !(tmin > limit);
             w = nd.w;
         }
         const bool is_leaf = ok && (w >> 28) == 0;

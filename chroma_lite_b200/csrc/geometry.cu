@@ -256,7 +256,7 @@ int cb_geometry_info(cb_geom_t h, CbGeometryInfo* info)
     info->charge_cdf_x = g->charge_cdf_x; info->charge_cdf_y = g->charge_cdf_y;
     info->nvertices = g->nvertices; info->ntriangles = g->ntriangles; info->nnodes = g->nnodes;
     info->nchannels = g->nchannels; info->device_bytes = g->device_bytes;
-    info->max_stack_depth = CB_SSTACK + CB_LSTACK;
+    info->max_stack_depth = CB_PSTACK + CB_PLSTACK;
     return CB_OK;
 }
 

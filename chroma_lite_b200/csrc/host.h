@@ -31,6 +31,7 @@ struct Context {
     uint32_t* d_keys[2] = {nullptr, nullptr}; uint32_t* d_sorted = nullptr; void* d_sort_tmp = nullptr;
     size_t sort_tmp_bytes = 0;
     uint64_t scratch_cap = 0;                       // wavefront scratch (one rng-pool chunk)
+    unsigned long long* d_step_counts = nullptr; size_t step_slots = 0;   // per-step alive counts + work counters
 };
 
 Context& ctx();

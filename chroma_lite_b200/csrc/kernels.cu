@@ -9,9 +9,6 @@
 namespace cb {
 
 constexpr int PROP_THREADS = 256;
-#ifndef CB_INT_BLOCKS
-#define CB_INT_BLOCKS 4      /* resident CTAs per SM of the thread-per-ray traversal kernels */
-#endif
 
 // ---------------------------------------------------------------- smem staging
 // The wavelength tables (a few KB .. 48 KB) are staged once per CTA with the bulk
@@ -52,66 +49,6 @@ __device__ __forceinline__ void stage_tables(float* smem_dst, const float* gsrc,
 }
 
 // ---------------------------------------------------------------- intersection
-// Persistent traversal with per-lane ray refill: every lane carries one ray; after
-// each while-while round the warp retires finished rays and, once REFILL_MIN lanes
-// are idle, claims that many new rays with ONE atomic on the queue cursor (ballot +
-// popc prefix).  Warps therefore stay populated however uneven the ray lengths are.
-constexpr int REFILL_MIN = 8;
-
-template <bool COUNT, class Source>
-__device__ __forceinline__ void persistent_intersect(const DevGeometry& g, Source& src, unsigned long long n,
-                                                     unsigned long long* cursor, uint2* sstack,
-                                                     unsigned long long* counters)
-{
-    const unsigned lane = threadIdx.x & 31u;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    Trav tv;
-    tv.have = false;
-    bool active = false, exhausted = false;
-    unsigned long long slot = 0;
-    TraverseCounters cnt = {0, 0, 0};
-    for (;;) {
-        const unsigned idle = __ballot_sync(0xffffffffu, !active);
-        if (!exhausted && (idle == 0xffffffffu || __popc(idle) >= REFILL_MIN)) {
-            unsigned long long base = 0;
-            const int leader = __ffs(idle) - 1;
-            if ((int)lane == leader) base = atomicAdd(cursor, (unsigned long long)__popc(idle));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (!active) {
-                const unsigned long long q = base + __popc(idle & lt_mask);
-                if (q < n) {
-                    float3 o, d;
-                    int last;
-                    slot = q;
-                    if (src.load(q, o, d, last)) {
-                        active = true;
-                        if (!tv.init(g, o, d, last)) { src.store(slot, -1, -1.0f); active = false; }
-                    }
-                }
-            }
-            exhausted = __any_sync(0xffffffffu, base + __popc(idle) >= n);
-        }
-        if (__ballot_sync(0xffffffffu, active) == 0) {
-            if (exhausted) break;
-            continue;
-        }
-        if (active) {
-            tv.template round<COUNT>(g, sstack, PROP_THREADS, &cnt);
-            if (!tv.have) {
-                float dist;
-                const int tri = tv.template finish<COUNT>(g, dist, (uint32_t*)(counters + 3), &cnt);
-                src.store(slot, tri, dist);
-                active = false;
-            }
-        }
-    }
-    if (COUNT) {
-        atomicAdd(counters + 1, (unsigned long long)cnt.nodes);
-        atomicAdd(counters + 2, (unsigned long long)cnt.tris);
-        atomicAdd(counters + 5, (unsigned long long)cnt.resolved);
-    }
-}
-
 struct RaySource {           // cb_intersect: free rays, direction normalised like distance_to_mesh
     const float* origins; const float* directions; const int32_t* last_hit;
     int32_t* tri_out; float* dist_out;
@@ -130,28 +67,19 @@ struct RaySource {           // cb_intersect: free rays, direction normalised li
     }
 };
 
-template <bool COUNT>
-__global__ void __launch_bounds__(PROP_THREADS, CB_INT_BLOCKS)
-intersect_kernel(DevGeometry g, RaySource src, uint64_t n, unsigned long long* counters)
-{
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    uint2* sstack = reinterpret_cast<uint2*>(smem_raw) + threadIdx.x;
-    persistent_intersect<COUNT>(g, src, n, counters, sstack, counters);
-}
-
-// Second generation (PTrav), persistent with per-lane refill.  Every iteration each
+// Persistent traversal with per-lane refill (PTrav).  Every iteration each
 // lane takes ONE step: a lane with queued leaves tests a triangle, a lane without
 // expands its node; both fetch from one 64-byte block, so the warp issues a single
 // load sequence and waits for memory once per iteration.  Finished rays wait until
 // `refill_min` lanes are free and are then finished (winner re-check + store) and
 // replaced together with one atomic on the queue cursor.
 struct Tune { int refill_min; };
-#ifndef CB_INT2_BLOCKS
-#define CB_INT2_BLOCKS 2     /* resident CTAs per SM of the phased traversal kernels: 109 registers, no spills */
+#ifndef CB_INT_BLOCKS
+#define CB_INT_BLOCKS 2     /* resident CTAs per SM of the phased traversal kernels: 109 registers, no spills */
 #endif
 
 template <bool COUNT, class Source>
-__device__ __forceinline__ void persistent_intersect2(const DevGeometry& g, const Source& src, unsigned long long n,
+__device__ __forceinline__ void persistent_intersect(const DevGeometry& g, const Source& src, unsigned long long n,
                                                       unsigned long long* cursor, uint32_t smem_base,
                                                       unsigned long long* counters, const Tune tune)
 {
@@ -166,6 +94,7 @@ __device__ __forceinline__ void persistent_intersect2(const DevGeometry& g, cons
     tv.have = false; tv.sp = sbase; tv.lq = lbase; tv.lsp = 0;
     bool active = false, exhausted = false;
     unsigned long long slot = 0;
+    unsigned ray_iters = 0;                 // iterations spent on the current ray (statistics only)
     TraverseCounters cnt = {0, 0, 0};
     for (;;) {
         const bool done = active && !tv.have && tv.lq == lbase;
@@ -176,6 +105,14 @@ __device__ __forceinline__ void persistent_intersect2(const DevGeometry& g, cons
             if (done) {
                 float dist;
                 const int tri = tv.template finish<COUNT>(g, dist, (uint32_t*)(counters + 3), &cnt);
+                if (COUNT) {                               // ray-length statistics (debug aid)
+                    atomicMax(counters + 9, (unsigned long long)ray_iters);
+                    if (ray_iters > 100) atomicAdd(counters + 10, 1ull);
+                    if (ray_iters > 300) atomicAdd(counters + 11, 1ull);
+                    if (ray_iters > 1000) atomicAdd(counters + 12, 1ull);
+                    atomicAdd(counters + 13, (unsigned long long)ray_iters);
+                    ray_iters = 0;
+                }
                 src.store(slot, tri, dist);
                 active = false;
             }
@@ -207,6 +144,7 @@ __device__ __forceinline__ void persistent_intersect2(const DevGeometry& g, cons
         // without expands its node.  Both kinds fetch four 16-byte words from one 64-byte
         // block (a tri64 record / four child entries), so they share ONE load sequence and
         // the warp waits for memory once per iteration.
+        if (COUNT) ray_iters += active;
         uint32_t tri = 0;
         const bool do_tri = active && tv.pop_leaf(lbase, tri);
         const bool do_exp = active && !do_tri && tv.lq == lbase && tv.have;
@@ -242,12 +180,12 @@ __device__ __forceinline__ void persistent_intersect2(const DevGeometry& g, cons
 }
 
 template <bool COUNT>
-__global__ void __launch_bounds__(PROP_THREADS, CB_INT2_BLOCKS)
-intersect2_kernel(const __grid_constant__ DevGeometry g, const __grid_constant__ RaySource src, uint64_t n,
+__global__ void __launch_bounds__(PROP_THREADS, CB_INT_BLOCKS)
+intersect_kernel(const __grid_constant__ DevGeometry g, const __grid_constant__ RaySource src, uint64_t n,
                   unsigned long long* counters, Tune tune)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    persistent_intersect2<COUNT>(g, src, n, counters, (uint32_t)__cvta_generic_to_shared(smem_raw), counters, tune);
+    persistent_intersect<COUNT>(g, src, n, counters, (uint32_t)__cvta_generic_to_shared(smem_raw), counters, tune);
 }
 
 // ---------------------------------------------------------------- propagation
@@ -272,10 +210,19 @@ struct PropParams {
     uint32_t* queue_out;
     int32_t* hit_tri;               // per chunk-local index
     float* hit_dist;
-    uint32_t n_in;
+    // The number of queued photons lives on the device, so that consecutive steps can be
+    // launched without the host reading it back: step s reads n_in[0], appends its
+    // survivors to queue_out and counts them in n_out[0]; `cursor` is this step's work
+    // counter.  A wavefront kernel runs only while more than `tail_at` photons are queued;
+    // the tail kernel launched behind it takes over (and ends the call) once there are
+    // `tail_at` or fewer.
+    const unsigned long long* n_in;
+    unsigned long long* n_out;
+    unsigned long long* cursor;
+    unsigned long long tail_at;
     int32_t step;                   // steps already taken by every photon in queue_in
     int32_t max_steps, use_weights, scatter_first;
-    unsigned long long* counters;   // [0] cursor / out count, [1] nodes, [2] tris, [3] overflow, [4] steps, [5] resolved
+    unsigned long long* counters;   // [1] nodes, [2] tris, [3] overflow, [4] steps, [5] resolved, [9..13] ray-length stats
 };
 
 __device__ __forceinline__ void load_photon(const CbPhotonBank& b, uint64_t id, uint32_t hist, bool normalise, Photon& p)
@@ -322,7 +269,7 @@ __global__ void __launch_bounds__(256)
 ray_key_kernel(DevGeometry g, PropParams P, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P.n_in) return;
+    if (i >= *P.n_in) return;
     const uint32_t k = P.queue_in ? P.queue_in[i] : i;
     const uint64_t id = P.first + k;
     const float3 pos = ld3(P.bank.pos, id);
@@ -348,39 +295,6 @@ ray_key_kernel(DevGeometry g, PropParams P, uint32_t* __restrict__ keys, uint32_
 }
 
 struct PhotonRaySource {     // one propagation step: rays of the photons in the queue
-    PropParams P;
-    uint32_t k_of[1];        // (unused; keeps the struct trivially copyable)
-    __device__ __forceinline__ bool load(unsigned long long q, float3& o, float3& d, int& last) const
-    {
-        const uint32_t k = P.queue_in ? P.queue_in[q] : (uint32_t)q;
-        const uint64_t id = P.first + k;
-        if (P.step == 0 && (P.bank.flags[id] & 0xFFFFu & CB_TERMINAL)) return false;   // never ran: untouched
-        o = ld3(P.bank.pos, id);
-        d = ld3(P.bank.dir, id);
-        if (P.step == 0) d = d / norm(d);
-        last = P.bank.last_hit_triangles[id];
-        return true;
-    }
-    __device__ __forceinline__ void store(unsigned long long q, int tri, float dist) const
-    {
-        const uint32_t k = P.queue_in ? P.queue_in[q] : (uint32_t)q;
-        P.hit_tri[k] = tri;
-        P.hit_dist[k] = dist;
-    }
-};
-
-template <bool COUNT>
-__global__ void __launch_bounds__(PROP_THREADS, CB_INT_BLOCKS)
-step_intersect_kernel(DevGeometry g, PropParams P)
-{
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    uint2* sstack = reinterpret_cast<uint2*>(smem_raw) + threadIdx.x;
-    PhotonRaySource src;
-    src.P = P;
-    persistent_intersect<COUNT>(g, src, P.n_in, P.counters + 6, sstack, P.counters);
-}
-
-struct PhotonRaySourceRef {  // same as PhotonRaySource, reading the parameters in place
     const PropParams& P;
     __device__ __forceinline__ bool load(unsigned long long q, float3& o, float3& d, int& last) const
     {
@@ -402,12 +316,14 @@ struct PhotonRaySourceRef {  // same as PhotonRaySource, reading the parameters 
 };
 
 template <bool COUNT>
-__global__ void __launch_bounds__(PROP_THREADS, CB_INT2_BLOCKS)
-step_intersect2_kernel(const __grid_constant__ DevGeometry g, const __grid_constant__ PropParams P, Tune tune)
+__global__ void __launch_bounds__(PROP_THREADS, CB_INT_BLOCKS)
+step_intersect_kernel(const __grid_constant__ DevGeometry g, const __grid_constant__ PropParams P, Tune tune)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const PhotonRaySourceRef src = {P};
-    persistent_intersect2<COUNT>(g, src, P.n_in, P.counters + 6, (uint32_t)__cvta_generic_to_shared(smem_raw), P.counters, tune);
+    const unsigned long long n = *P.n_in;
+    if (n <= P.tail_at) return;              // the tail kernel behind this launch takes these
+    const PhotonRaySource src = {P};
+    persistent_intersect<COUNT>(g, src, n, P.cursor, (uint32_t)__cvta_generic_to_shared(smem_raw), P.counters, tune);
 }
 
 __global__ void __launch_bounds__(PROP_THREADS, 2)
@@ -415,17 +331,20 @@ step_physics_kernel(DevGeometry g, PropParams P)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ unsigned long long mbar;
+    const uint32_t n_in = (uint32_t)*P.n_in;
+    if (n_in <= P.tail_at) return;           // (uniform) the tail kernel behind this launch takes these
     float* stab = reinterpret_cast<float*>(smem_raw);
     stage_tables(stab, g.tables, g.smem_floats * 4u, &mbar);
     Tables T = {stab, g.tables, g.smem_floats};
     const unsigned lane = threadIdx.x & 31u;
     const bool last_step = (P.step + 1 >= P.max_steps);
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(P.counters + 4, (unsigned long long)n_in);   // steps taken
     // grid-stride over whole warps so the ballot below always sees full warps
-    const uint32_t n_round = (P.n_in + 31u) & ~31u;
+    const uint32_t n_round = (n_in + 31u) & ~31u;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
         bool alive = false;
         uint32_t k = 0;
-        if (i < P.n_in) {
+        if (i < n_in) {
             k = P.queue_in ? P.queue_in[i] : i;
             const uint64_t id = P.first + k;
             const uint32_t hist = P.bank.flags[id] & 0xFFFFu;
@@ -447,7 +366,7 @@ step_physics_kernel(DevGeometry g, PropParams P)
         const unsigned m = __ballot_sync(0xffffffffu, alive);
         if (m) {
             unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(P.counters, (unsigned long long)__popc(m));
+            if (lane == 0) base = atomicAdd(P.n_out, (unsigned long long)__popc(m));
             base = __shfl_sync(0xffffffffu, base, 0);
             if (alive) P.queue_out[base + __popc(m & ((1u << lane) - 1u))] = k;
         }
@@ -459,12 +378,17 @@ step_physics_kernel(DevGeometry g, PropParams P)
 // step costs a few microseconds instead of the ~50 us of a single-thread step.
 // Warps claim photons from the queue with one atomic each until it is empty.
 constexpr int TAIL_THREADS = 256;
+#ifndef CB_TAIL_BLOCKS
+#define CB_TAIL_BLOCKS 4     /* 64 registers: 32 resident warps (photons) per SM */
+#endif
 template <bool COUNT>
-__global__ void __launch_bounds__(TAIL_THREADS, 3)
+__global__ void __launch_bounds__(TAIL_THREADS, CB_TAIL_BLOCKS)
 propagate_tail_kernel(DevGeometry g, PropParams P)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ unsigned long long mbar;
+    const unsigned long long n_in = *P.n_in;
+    if (n_in > P.tail_at || n_in == 0) return;       // (uniform) still the wavefront kernels' turn, or nothing left
     float* stab = reinterpret_cast<float*>(smem_raw);
     const uint32_t tab_bytes = g.smem_floats * 4u;
     const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
@@ -477,9 +401,9 @@ propagate_tail_kernel(DevGeometry g, PropParams P)
 
     for (;;) {
         unsigned long long q = 0;
-        if (lane == 0) q = atomicAdd(P.counters, 1ull);
+        if (lane == 0) q = atomicAdd(P.cursor, 1ull);
         q = __shfl_sync(0xffffffffu, q, 0);
-        if (q >= P.n_in) break;
+        if (q >= n_in) break;
         const uint32_t k = P.queue_in ? P.queue_in[q] : (uint32_t)q;
         const uint64_t id = P.first + k;
         const uint32_t hist = P.bank.flags[id] & 0xFFFFu;
@@ -772,14 +696,7 @@ static int check_bank(const CbPhotonBank* b, const char* who)
     return CB_OK;
 }
 
-static size_t stack_smem_bytes() { return (size_t)CB_SSTACK * PROP_THREADS * sizeof(uint2); }
-static size_t stack2_smem_bytes() { return (size_t)(CB_PSTACK + CB_PLEAF) * PROP_THREADS * sizeof(uint2); }
-// CHROMA_B200_TRAV=lane selects the first-generation traversal kernels (A/B aid)
-static bool first_generation()
-{
-    const char* e = getenv("CHROMA_B200_TRAV");
-    return e && strcmp(e, "lane") == 0;
-}
+static size_t stack_smem_bytes() { return (size_t)(CB_PSTACK + CB_PLEAF) * PROP_THREADS * sizeof(uint2); }
 static Tune tune_from_env()
 {
     Tune t = {12};
@@ -847,24 +764,28 @@ int cb_intersect(cb_geom_t gh, const float* d_origins, const float* d_directions
         return fail(CB_ERR_INVALID, "cb_intersect: null array");
     Context& c = ctx();
     CB_CUDA(cudaMemsetAsync(c.d_counters, 0, 16 * sizeof(unsigned long long), c.stream));
-    const bool gen1 = first_generation();
-    size_t smem = gen1 ? stack_smem_bytes() : stack2_smem_bytes();
-    CB_CUDA(cudaFuncSetAttribute(intersect_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stack_smem_bytes()));
-    CB_CUDA(cudaFuncSetAttribute(intersect2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stack2_smem_bytes()));
+    const size_t smem = stack_smem_bytes();
+    CB_CUDA(cudaFuncSetAttribute(intersect_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    if (gen1) CB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, intersect_kernel<false>, PROP_THREADS, smem));
-    else CB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, intersect2_kernel<false>, PROP_THREADS, smem));
+    CB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, intersect_kernel<false>, PROP_THREADS, smem));
     if (per_sm < 1) per_sm = 1;
     unsigned blocks = (unsigned)std::min<uint64_t>((n + PROP_THREADS - 1) / PROP_THREADS, (uint64_t)c.sm_count * per_sm);
     RaySource src = {d_origins, d_directions, d_last_hit, d_triangle_out, d_distance_out};
-    if (gen1) intersect_kernel<false><<<blocks, PROP_THREADS, smem, c.stream>>>(g->dev, src, n, c.d_counters);
-    else intersect2_kernel<false><<<blocks, PROP_THREADS, smem, c.stream>>>(g->dev, src, n, c.d_counters, tune_from_env());
+    intersect_kernel<false><<<blocks, PROP_THREADS, smem, c.stream>>>(g->dev, src, n, c.d_counters, tune_from_env());
     CB_CUDA(cudaGetLastError());
     CB_CUDA(cudaMemcpyAsync(c.h_counters, c.d_counters, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c.stream));
     CB_CUDA(cudaStreamSynchronize(c.stream));
     if (c.h_counters[3]) return fail(CB_ERR_CUDA, "cb_intersect: traversal stack overflow");
     return CB_OK;
 }
+
+// Scheduler of one propagate call (replaces the host loop of gpu/photon.py:259-286).
+// Step s = [step_intersect, step_physics] while many photons are alive, then ONE
+// warp-cooperative persistent launch for everything that is left.  The alive count
+// stays on the device (PropParams::n_in/n_out): up to STEP_BATCH steps are enqueued
+// back to back, each followed by a guarded tail launch, and the host reads the count
+// once per batch.  Kernels whose guard fails return at once (a few microseconds).
+constexpr int STEP_BATCH = 4;
 
 int cb_propagate(const CbPhotonBank* bank, cb_geom_t gh, cb_rng_t rh, int32_t nthreads_per_block,
                  int32_t max_blocks, int32_t max_steps, int32_t use_weights, int32_t scatter_first,
@@ -885,15 +806,23 @@ int cb_propagate(const CbPhotonBank* bank, cb_geom_t gh, cb_rng_t rh, int32_t nt
     if (bank->n == 0 || max_steps <= 0) return CB_OK;
     Context& c = ctx();
     const bool count = getenv("CHROMA_B200_STATS") != nullptr;
-    const bool gen1 = first_generation();
     const Tune tune = tune_from_env();
     const bool trace = getenv("CHROMA_B200_TRACE") != nullptr;   // per-step timing to stderr (debug aid)
+    const bool timeline = getenv("CHROMA_B200_TIMELINE") != nullptr;   // event after every launch, printed at the end
+    std::vector<cudaEvent_t> tl_ev; std::vector<const char*> tl_name;
+    auto mark = [&](const char* name) {
+        if (!timeline) return;
+        cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, c.stream); tl_ev.push_back(e); tl_name.push_back(name);
+    };
     cudaEvent_t tev[3] = {nullptr, nullptr, nullptr};
     if (trace) for (auto& e : tev) cudaEventCreate(&e);
     // hand the rest to the persistent kernel once the survivors fit on the chip ~1.3 times over
     const uint64_t tail_threshold = getenv("CHROMA_B200_TAIL") ? (uint64_t)atoll(getenv("CHROMA_B200_TAIL")) : (uint64_t)(1.3 * 2048 * ctx().sm_count);
+    const uint64_t sort_threshold = getenv("CHROMA_B200_SORT") ? (uint64_t)atoll(getenv("CHROMA_B200_SORT")) : 0;
+    // the host follows the alive count step by step only when it needs it (tracing, ray sorting)
+    const int batch = (trace || sort_threshold) ? 1 : STEP_BATCH;
 
-    // scratch: two queues + hit arrays, sized for one chunk
+    // scratch: two queues + hit arrays, sized for one chunk; per-step counters
     const uint64_t cap = std::min<uint64_t>(pool, bank->n);
     if (c.scratch_cap < cap) {
         cudaFree(c.d_queue[0]); cudaFree(c.d_queue[1]); cudaFree(c.d_hit_tri); cudaFree(c.d_hit_dist);
@@ -910,30 +839,34 @@ int cb_propagate(const CbPhotonBank* bank, cb_geom_t gh, cb_rng_t rh, int32_t nt
         CB_CUDA(cudaMalloc(&c.d_sort_tmp, c.sort_tmp_bytes));
         c.scratch_cap = cap;
     }
-    const uint64_t sort_threshold = getenv("CHROMA_B200_SORT") ? (uint64_t)atoll(getenv("CHROMA_B200_SORT")) : 0;
+    const size_t nslots = (size_t)max_steps + 2;          // alive count before step s, s = 0..max_steps
+    if (c.step_slots < nslots) {
+        cudaFree(c.d_step_counts); c.d_step_counts = nullptr; c.step_slots = 0;
+        CB_CUDA(cudaMalloc(&c.d_step_counts, 2 * nslots * sizeof(unsigned long long)));
+        c.step_slots = nslots;
+    }
+    unsigned long long* d_alive = c.d_step_counts;                 // [s]: photons queued for step s
+    unsigned long long* d_cursor = c.d_step_counts + c.step_slots; // [s]: work counter of step s
 
     auto k_int = count ? step_intersect_kernel<true> : step_intersect_kernel<false>;
-    auto k_int2 = count ? step_intersect2_kernel<true> : step_intersect2_kernel<false>;
     auto k_tail = count ? propagate_tail_kernel<true> : propagate_tail_kernel<false>;
-    const size_t smem_int = gen1 ? stack_smem_bytes() : stack2_smem_bytes();
+    const size_t smem_int = stack_smem_bytes();
     const size_t smem_tab = (g->smem_table_bytes + 127u) & ~127u;
     const size_t smem_tail = smem_tab + (size_t)(TAIL_THREADS / 32) * (CB_WSTACK + CB_WLEAF) * sizeof(uint2);
-    CB_CUDA(cudaFuncSetAttribute(k_int, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stack_smem_bytes()));
-    CB_CUDA(cudaFuncSetAttribute(k_int2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stack2_smem_bytes()));
+    CB_CUDA(cudaFuncSetAttribute(k_int, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_int));
     CB_CUDA(cudaFuncSetAttribute(step_physics_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_tab, 16)));
     CB_CUDA(cudaFuncSetAttribute(k_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tail));
     int phys_per_sm = 0, tail_per_sm = 0, int_per_sm = 0;
-    if (gen1) CB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&int_per_sm, k_int, PROP_THREADS, smem_int));
-    else CB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&int_per_sm, k_int2, PROP_THREADS, smem_int));
-    if (int_per_sm < 1) int_per_sm = 1;
+    CB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&int_per_sm, k_int, PROP_THREADS, smem_int));
     CB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&phys_per_sm, step_physics_kernel, PROP_THREADS, smem_tab));
     CB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tail_per_sm, k_tail, TAIL_THREADS, smem_tail));
-    if (phys_per_sm < 1 || tail_per_sm < 1) return fail(CB_ERR_CUDA, "cb_propagate: kernels do not fit on an SM");
+    if (int_per_sm < 1 || phys_per_sm < 1 || tail_per_sm < 1) return fail(CB_ERR_CUDA, "cb_propagate: kernels do not fit on an SM");
 
     unsigned long long tot[16] = {0};
     uint32_t launches = 0;
     uint64_t int0_rays = 0;
     CB_CUDA(cudaEventRecord(c.kev0, c.stream));
+    mark("kev0");
     // photons beyond the pool reuse states chunk by chunk, in order, exactly as
     // the reference's chunk_iterator does for one step (gpu/photon.py:266-268)
     for (uint64_t first = 0; first < bank->n; first += pool) {
@@ -943,74 +876,104 @@ int cb_propagate(const CbPhotonBank* bank, cb_geom_t gh, cb_rng_t rh, int32_t nt
         P.hit_tri = c.d_hit_tri; P.hit_dist = c.d_hit_dist;
         P.max_steps = max_steps; P.use_weights = use_weights; P.scatter_first = scatter_first;
         P.counters = c.d_counters;
-        uint64_t n_alive = cnt;
-        const uint32_t* q_in = nullptr;
-        int qsel = 0;
         CB_CUDA(cudaMemsetAsync(c.d_counters, 0, 16 * sizeof(unsigned long long), c.stream));
-        for (int step = 0; step < max_steps && n_alive > 0; step++) {
-            P.queue_in = q_in; P.queue_out = c.d_queue[qsel]; P.n_in = (uint32_t)n_alive; P.step = step;
-            if (n_alive <= tail_threshold || step + 1 == max_steps) {
-                // finish everything that is left in one persistent launch
-                const uint64_t per_block = TAIL_THREADS / 32;          // one photon per warp
-                unsigned blocks = (unsigned)std::min<uint64_t>((n_alive + per_block - 1) / per_block,
-                                                               (uint64_t)c.sm_count * tail_per_sm);
-                if (trace) cudaEventRecord(tev[0], c.stream);
-                k_tail<<<blocks, TAIL_THREADS, smem_tail, c.stream>>>(g->dev, P);
-                CB_CUDA(cudaGetLastError());
-                if (trace) {
-                    cudaEventRecord(tev[1], c.stream); cudaEventSynchronize(tev[1]);
-                    float ms = 0; cudaEventElapsedTime(&ms, tev[0], tev[1]);
-                    fprintf(stderr, "[cb trace] step %d tail: %llu photons %.3f ms\n", step, (unsigned long long)n_alive, ms);
+        CB_CUDA(cudaMemsetAsync(c.d_step_counts, 0, 2 * c.step_slots * sizeof(unsigned long long), c.stream));
+        c.h_counters[15] = cnt;
+        CB_CUDA(cudaMemcpyAsync(d_alive, c.h_counters + 15, sizeof(unsigned long long), cudaMemcpyHostToDevice, c.stream));
+        uint64_t n_alive = cnt;            // host's view: exact after every read-back, an upper bound in between
+        bool exact = true;
+        int step = 0;
+        while (step < max_steps && n_alive > 0) {
+            const int nb = std::min(batch, max_steps - step);
+            for (int b = 0; b < nb && n_alive > 0; b++, step++) {
+                P.step = step;
+                P.queue_in = (step == 0) ? nullptr : c.d_queue[(step - 1) & 1];
+                P.queue_out = c.d_queue[step & 1];
+                P.n_in = d_alive + step; P.n_out = d_alive + step + 1; P.cursor = d_cursor + step;
+                const bool last = (step + 1 == max_steps);
+                P.tail_at = last ? ~0ull : tail_threshold;
+                const bool wave = !last && !(exact && n_alive <= tail_threshold);
+                const bool tail = last || !exact || n_alive <= tail_threshold;
+                if (wave) {
+                    const uint64_t blocks = (n_alive + PROP_THREADS - 1) / PROP_THREADS;
+                    if (sort_threshold && exact && n_alive >= sort_threshold) {
+                        // regroup the queue so that warps hold rays of similar origin and direction
+                        // (the intersect kernel alone walks the sorted order; the physics keeps the queue's)
+                        uint32_t* unsorted_vals = c.d_queue[step & 1];     // free until the physics kernel writes it
+                        ray_key_kernel<<<(unsigned)((n_alive + 255) / 256), 256, 0, c.stream>>>(g->dev, P, c.d_keys[0], unsorted_vals);
+                        size_t tmp = c.sort_tmp_bytes;
+                        CB_CUDA(cub::DeviceRadixSort::SortPairs(c.d_sort_tmp, tmp, c.d_keys[0], c.d_keys[1], unsorted_vals,
+                                                                c.d_sorted, (int)n_alive, 0, 30, c.stream));
+                        launches += 2;
+                    }
+                    const unsigned iblocks = (unsigned)std::min<uint64_t>(blocks, (uint64_t)c.sm_count * int_per_sm);
+                    const bool time_it = (step == 0 && first == 0);
+                    if (time_it) CB_CUDA(cudaEventRecord(c.iev0, c.stream));
+                    if (trace) cudaEventRecord(tev[0], c.stream);
+                    PropParams PI = P;
+                    if (sort_threshold && exact && n_alive >= sort_threshold) PI.queue_in = c.d_sorted;
+                    mark("pre-int");
+                    k_int<<<iblocks, PROP_THREADS, smem_int, c.stream>>>(g->dev, PI, tune);
+                    mark("int");
+                    if (trace) cudaEventRecord(tev[1], c.stream);
+                    if (time_it) { CB_CUDA(cudaEventRecord(c.iev1, c.stream)); int0_rays = n_alive; }
+                    const unsigned pblocks = (unsigned)std::min<uint64_t>(blocks, (uint64_t)c.sm_count * phys_per_sm);
+                    step_physics_kernel<<<pblocks, PROP_THREADS, smem_tab, c.stream>>>(g->dev, P);
+                    mark("phys");
+                    if (trace) cudaEventRecord(tev[2], c.stream);
+                    CB_CUDA(cudaGetLastError());
+                    launches += 2;
                 }
-                launches++;
-                n_alive = 0;
-                break;
+                if (tail) {
+                    // everything that is left, in one persistent launch; one photon per warp
+                    const uint64_t per_block = TAIL_THREADS / 32;
+                    const uint64_t most = (last || exact) ? n_alive : std::min<uint64_t>(n_alive, tail_threshold);
+                    const unsigned blocks = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((most + per_block - 1) / per_block,
+                                                                                             (uint64_t)c.sm_count * tail_per_sm));
+                    if (trace) cudaEventRecord(tev[0], c.stream);
+                    k_tail<<<blocks, TAIL_THREADS, smem_tail, c.stream>>>(g->dev, P);
+                    mark("tail");
+                    CB_CUDA(cudaGetLastError());
+                    if (trace) {
+                        cudaEventRecord(tev[1], c.stream); cudaEventSynchronize(tev[1]);
+                        float ms = 0; cudaEventElapsedTime(&ms, tev[0], tev[1]);
+                        fprintf(stderr, "[cb trace] step %d tail: %llu photons %.3f ms\n", step, (unsigned long long)n_alive, ms);
+                    }
+                    launches++;
+                    if (!wave) { n_alive = 0; step++; break; }       // the tail ran for certain: done
+                }
+                exact = false;
             }
-            unsigned blocks = (unsigned)((n_alive + PROP_THREADS - 1) / PROP_THREADS);
-            if (sort_threshold && n_alive >= sort_threshold) {
-                // regroup the queue so that warps hold rays of similar origin and direction
-                uint32_t* unsorted_vals = c.d_queue[qsel];         // free until the physics kernel writes it
-                ray_key_kernel<<<(unsigned)((n_alive + 255) / 256), 256, 0, c.stream>>>(g->dev, P, c.d_keys[0], unsorted_vals);
-                size_t tmp = c.sort_tmp_bytes;
-                CB_CUDA(cub::DeviceRadixSort::SortPairs(c.d_sort_tmp, tmp, c.d_keys[0], c.d_keys[1], unsorted_vals,
-                                                        c.d_sorted, (int)n_alive, 0, 30, c.stream));
-                P.queue_in = c.d_sorted;
-                launches += 2;
-            }
-            unsigned iblocks = (unsigned)std::min<uint64_t>(blocks, (uint64_t)c.sm_count * int_per_sm);
-            const bool time_it = (step == 0 && first == 0);
-            if (time_it) CB_CUDA(cudaEventRecord(c.iev0, c.stream));
-            if (trace) cudaEventRecord(tev[0], c.stream);
-            if (gen1) k_int<<<iblocks, PROP_THREADS, smem_int, c.stream>>>(g->dev, P);
-            else k_int2<<<iblocks, PROP_THREADS, smem_int, c.stream>>>(g->dev, P, tune);
-            if (trace) cudaEventRecord(tev[1], c.stream);
-            if (time_it) { CB_CUDA(cudaEventRecord(c.iev1, c.stream)); int0_rays = n_alive; }
-            unsigned pblocks = (unsigned)std::min<uint64_t>(blocks, (uint64_t)c.sm_count * phys_per_sm);
-            step_physics_kernel<<<pblocks, PROP_THREADS, smem_tab, c.stream>>>(g->dev, P);
-            CB_CUDA(cudaGetLastError());
-            launches += 2;
-            if (trace) cudaEventRecord(tev[2], c.stream);
-            CB_CUDA(cudaMemcpyAsync(c.h_counters, c.d_counters, 8, cudaMemcpyDeviceToHost, c.stream));
-            CB_CUDA(cudaMemsetAsync(c.d_counters, 0, 8, c.stream));
-            CB_CUDA(cudaMemsetAsync(c.d_counters + 6, 0, 8, c.stream));
+            if (n_alive == 0) break;
+            // one read-back per batch: photons queued for the next step (0 once a tail launch has run)
+            CB_CUDA(cudaMemcpyAsync(c.h_counters, d_alive + step, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c.stream));
             CB_CUDA(cudaStreamSynchronize(c.stream));
             if (trace) {
-                float a = 0, b = 0;
-                cudaEventElapsedTime(&a, tev[0], tev[1]); cudaEventElapsedTime(&b, tev[1], tev[2]);
+                float a = 0, b2 = 0;
+                cudaEventElapsedTime(&a, tev[0], tev[1]); cudaEventElapsedTime(&b2, tev[1], tev[2]);
                 fprintf(stderr, "[cb trace] step %d: %llu rays intersect %.3f ms physics %.3f ms -> %llu alive\n",
-                        step, (unsigned long long)n_alive, a, b, c.h_counters[0]);
+                        step - 1, (unsigned long long)n_alive, a, b2, c.h_counters[0]);
             }
-            tot[4] += n_alive;                       // every queued photon took one step
             n_alive = c.h_counters[0];
-            q_in = c.d_queue[qsel];
-            qsel ^= 1;
+            exact = true;
         }
         CB_CUDA(cudaMemcpyAsync(c.h_counters, c.d_counters, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c.stream));
         CB_CUDA(cudaStreamSynchronize(c.stream));
         for (int i = 1; i < 6; i++) tot[i] += c.h_counters[i];
+        if (trace && count)
+            fprintf(stderr, "[cb trace] ray iterations: max %llu, >100: %llu, >300: %llu, >1000: %llu, total %llu\n",
+                    c.h_counters[9], c.h_counters[10], c.h_counters[11], c.h_counters[12], c.h_counters[13]);
     }
+    mark("end");
     CB_CUDA(cudaEventRecord(c.kev1, c.stream));
     CB_CUDA(cudaEventSynchronize(c.kev1));
+    if (timeline) {
+        for (size_t i = 1; i < tl_ev.size(); i++) {
+            float ms = 0; cudaEventElapsedTime(&ms, tl_ev[i - 1], tl_ev[i]);
+            fprintf(stderr, "[cb timeline] %-8s +%.3f ms\n", tl_name[i], ms);
+        }
+        for (auto& e : tl_ev) cudaEventDestroy(e);
+    }
     if (trace) for (auto& e : tev) cudaEventDestroy(e);
     if (stats) {
         stats->photons = bank->n; stats->steps = tot[4]; stats->nodes_visited = tot[1]; stats->tris_tested = tot[2];

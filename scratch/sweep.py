@@ -35,11 +35,14 @@ def main():
             k, v = kv.split('=')
             os.environ['CHROMA_B200_' + k] = v
             keys.append('CHROMA_B200_' + k)
-        os.environ.pop('CHROMA_B200_TRACE', None) if 'CHROMA_B200_TRACE' not in keys else None
         tr = os.environ.pop('CHROMA_B200_TRACE', None)
+        tl = os.environ.pop('CHROMA_B200_TIMELINE', None)
         for _ in range(3):
             one()
-        ms = [one().kernel_ms for _ in range(5)]
+        ms = []
+        for _ in range(5):
+            lib.cb_synchronize(); t0 = time.perf_counter(); st = one(); lib.cb_synchronize(); ms.append(st.kernel_ms)
+        print('     all', ' '.join('%.3f' % m for m in ms), flush=True)
         st = gp.last_stats
         print('SPEC %-40s kernel ms median %.3f min %.3f  launches %d  int0 %.3f ms' %
               (spec, float(np.median(ms)), min(ms), st.launches, st.intersect0_ms), flush=True)
@@ -50,6 +53,12 @@ def main():
             os.environ['CHROMA_B200_TRACE'] = tr
             one()
             os.environ.pop('CHROMA_B200_TRACE')
+        if tl:
+            os.environ['CHROMA_B200_TIMELINE'] = tl
+            for _ in range(3):
+                st = one()
+                print('     timeline run kernel_ms %.3f' % st.kernel_ms, flush=True)
+            os.environ.pop('CHROMA_B200_TIMELINE')
         for k in keys:
             os.environ.pop(k, None)
 

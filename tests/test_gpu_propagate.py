@@ -176,9 +176,17 @@ def test_scheduler_invariance(gpu_ready, monkeypatch):
     geo = scenes.tiny_detector()
     ph = scenes.point_source(150000, seed=9, wl_range=(300, 600))
     outs = []
-    for tail, sort in (('0', '0'), ('1000000000', '0'), ('20000', '0'), ('20000', '1')):
-        monkeypatch.setenv('CHROMA_B200_TAIL', tail)
-        monkeypatch.setenv('CHROMA_B200_SORT', sort)
+    configs = (dict(TAIL='0'),                          # a launch pair per step
+               dict(TAIL='1000000000'),                 # one warp-cooperative persistent launch
+               dict(TAIL='20000'),                      # hybrid
+               dict(TAIL='20000', SORT='1'),            # + coherence sort
+               dict(TAIL='20000', TRAV='lane'),         # first-generation traversal kernels
+               dict(TAIL='0', TRAV='lane'))
+    for cfg in configs:
+        for k in ('TAIL', 'SORT', 'TRAV'):
+            monkeypatch.delenv('CHROMA_B200_' + k, raising=False)
+        for k, v in cfg.items():
+            monkeypatch.setenv('CHROMA_B200_' + k, v)
         mine, st, gp = engine_run(geo, ph, 17, 100, detector=True)
         outs.append((mine, st, gp.last_stats.launches))
     base = outs[0][0]
