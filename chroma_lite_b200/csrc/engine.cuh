@@ -313,8 +313,12 @@ static __device__ __noinline__ int traverse_reference_order(const DevGeometry& g
 //     from the packed uint16, the affine map folds 2^23 into its offset.
 constexpr int CB_PSTACK = 16;    // internal entries per lane
 constexpr int CB_PLEAF = 8;      // leaf queue per lane: one expansion's worth
+constexpr int CB_PCOLD = 3;      // slots per lane for rarely used ray state (origin, direction)
 constexpr int CB_PLSTACK = 48;   // overflow entries per lane in local memory (rarely touched)
-constexpr uint32_t CB_PSTRIDE = 256u * 8u;   // bytes between consecutive entries of a lane (256 lanes x uint2)
+#ifndef CB_INT_THREADS
+#define CB_INT_THREADS 128       /* threads per CTA of the traversal kernels */
+#endif
+constexpr uint32_t CB_PSTRIDE = CB_INT_THREADS * 8u;   // bytes between consecutive entries of a lane (lanes x uint2)
 
 __device__ __forceinline__ void sts64(uint32_t addr, uint32_t x, uint32_t y)
 {
@@ -378,7 +382,8 @@ __device__ __forceinline__ bool hit_box_phased(const PhasedRay& r, uint32_t px, 
 }
 
 struct PTrav {
-    float3 origin, direction;
+    // (the ray's origin and direction are only needed by the triangle test and finish():
+    //  they live in three extra shared-memory slots behind the leaf queue, not in registers)
     PhasedRay r;
     float best_t, limit, cur_t;
     uint32_t best_rank, cur;
@@ -403,7 +408,11 @@ struct PTrav {
                                          uint32_t sbase, uint32_t lbase)
     {
         const float INF = __int_as_float(0x7f800000);
-        origin = o; direction = d; last_hit = last;
+        last_hit = last;
+        const uint32_t cold = lbase + CB_PLEAF * CB_PSTRIDE;
+        sts64(cold, __float_as_uint(o.x), __float_as_uint(o.y));
+        sts64(cold + CB_PSTRIDE, __float_as_uint(o.z), __float_as_uint(d.x));
+        sts64(cold + 2 * CB_PSTRIDE, __float_as_uint(d.y), __float_as_uint(d.z));
         phased_ray_axis(o.x, d.x, g.world_origin.x, g.world_scale, r.sx, r.nx, r.fx, r.selx);
         phased_ray_axis(o.y, d.y, g.world_origin.y, g.world_scale, r.sy, r.ny, r.fy, r.sely);
         phased_ray_axis(o.z, d.z, g.world_origin.z, g.world_scale, r.sz, r.nz, r.fz, r.selz);
@@ -467,8 +476,17 @@ struct PTrav {
         return false;
     }
     // a, b, c: the first three float4 of the triangle's tri64 record
-    __device__ __forceinline__ void test_triangle(uint32_t tri, const float4& a, const float4& b, const float4& c)
+    __device__ __forceinline__ void load_ray(uint32_t lbase, float3& origin, float3& direction) const
     {
+        const uint32_t cold = lbase + CB_PLEAF * CB_PSTRIDE;
+        const uint2 a = lds64(cold), b = lds64(cold + CB_PSTRIDE), c = lds64(cold + 2 * CB_PSTRIDE);
+        origin = f3(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(b.x));
+        direction = f3(__uint_as_float(b.y), __uint_as_float(c.x), __uint_as_float(c.y));
+    }
+    __device__ __forceinline__ void test_triangle(uint32_t lbase, uint32_t tri, const float4& a, const float4& b, const float4& c)
+    {
+        float3 origin, direction;
+        load_ray(lbase, origin, direction);
         float t;
         if (hit_triangle(origin, direction, f3(a.x, a.y, a.z), f3(a.w, b.x, b.y), f3(b.z, b.w, c.x), t)) {
             const uint32_t rank = __float_as_uint(c.y);
@@ -486,8 +504,11 @@ struct PTrav {
 
     // call once !have and the leaf queue is empty; returns the triangle (or -1) and its distance
     template <bool COUNT>
-    __device__ __forceinline__ int finish(const DevGeometry& g, float& dist, uint32_t* overflow_flag, TraverseCounters* cnt)
+    __device__ __forceinline__ int finish(const DevGeometry& g, uint32_t lbase, float& dist, uint32_t* overflow_flag,
+                                          TraverseCounters* cnt)
     {
+        float3 origin, direction;
+        load_ray(lbase, origin, direction);
         if (best_tri != -1 && !redo) {
             const float4 lb = __ldg(g.tri64 + 4ull * (uint32_t)best_tri + 3);
             float box_t;

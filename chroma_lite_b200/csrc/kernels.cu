@@ -9,6 +9,7 @@
 namespace cb {
 
 constexpr int PROP_THREADS = 256;
+constexpr int INT_THREADS = CB_INT_THREADS;   // traversal kernels
 
 // ---------------------------------------------------------------- smem staging
 // The wavelength tables (a few KB .. 48 KB) are staged once per CTA with the bulk
@@ -75,7 +76,7 @@ struct RaySource {           // cb_intersect: free rays, direction normalised li
 // replaced together with one atomic on the queue cursor.
 struct Tune { int refill_min; };
 #ifndef CB_INT_BLOCKS
-#define CB_INT_BLOCKS 2     /* resident CTAs per SM of the phased traversal kernels: 109 registers, no spills */
+#define CB_INT_BLOCKS 5     /* resident CTAs per SM of the traversal kernels: 5 x 128 threads at 96 registers */
 #endif
 
 template <bool COUNT, class Source>
@@ -83,7 +84,7 @@ __device__ __forceinline__ void persistent_intersect(const DevGeometry& g, const
                                                       unsigned long long* cursor, uint32_t smem_base,
                                                       unsigned long long* counters, const Tune tune)
 {
-    static_assert(CB_PSTRIDE == PROP_THREADS * 8u, "lane-interleaved stack stride");
+    static_assert(CB_PSTRIDE == INT_THREADS * 8u, "lane-interleaved stack stride");
     const unsigned FULL = 0xffffffffu;
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -104,7 +105,7 @@ __device__ __forceinline__ void persistent_intersect(const DevGeometry& g, const
         if (nfree == 32 || nfree >= tune.refill_min || (exhausted && dm)) {
             if (done) {
                 float dist;
-                const int tri = tv.template finish<COUNT>(g, dist, (uint32_t*)(counters + 3), &cnt);
+                const int tri = tv.template finish<COUNT>(g, lbase, dist, (uint32_t*)(counters + 3), &cnt);
                 if (COUNT) {                               // ray-length statistics (debug aid)
                     atomicMax(counters + 9, (unsigned long long)ray_iters);
                     if (ray_iters > 100) atomicAdd(counters + 10, 1ull);
@@ -158,7 +159,7 @@ __device__ __forceinline__ void persistent_intersect(const DevGeometry& g, const
         }
         if (do_tri) {
             if (COUNT) cnt.tris++;
-            tv.test_triangle(tri, *reinterpret_cast<const float4*>(&q[0]), *reinterpret_cast<const float4*>(&q[1]),
+            tv.test_triangle(lbase, tri, *reinterpret_cast<const float4*>(&q[0]), *reinterpret_cast<const float4*>(&q[1]),
                              *reinterpret_cast<const float4*>(&q[2]));
         } else if (do_exp) {
             PTrav::Nearest nr = {0u, __int_as_float(0x7f800000)};
@@ -180,7 +181,7 @@ __device__ __forceinline__ void persistent_intersect(const DevGeometry& g, const
 }
 
 template <bool COUNT>
-__global__ void __launch_bounds__(PROP_THREADS, CB_INT_BLOCKS)
+__global__ void __launch_bounds__(INT_THREADS, CB_INT_BLOCKS)
 intersect_kernel(const __grid_constant__ DevGeometry g, const __grid_constant__ RaySource src, uint64_t n,
                   unsigned long long* counters, Tune tune)
 {
@@ -316,7 +317,7 @@ struct PhotonRaySource {     // one propagation step: rays of the photons in the
 };
 
 template <bool COUNT>
-__global__ void __launch_bounds__(PROP_THREADS, CB_INT_BLOCKS)
+__global__ void __launch_bounds__(INT_THREADS, CB_INT_BLOCKS)
 step_intersect_kernel(const __grid_constant__ DevGeometry g, const __grid_constant__ PropParams P, Tune tune)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -696,7 +697,7 @@ static int check_bank(const CbPhotonBank* b, const char* who)
     return CB_OK;
 }
 
-static size_t stack_smem_bytes() { return (size_t)(CB_PSTACK + CB_PLEAF) * PROP_THREADS * sizeof(uint2); }
+static size_t stack_smem_bytes() { return (size_t)(CB_PSTACK + CB_PLEAF + CB_PCOLD) * INT_THREADS * sizeof(uint2); }
 static Tune tune_from_env()
 {
     Tune t = {12};
@@ -767,11 +768,11 @@ int cb_intersect(cb_geom_t gh, const float* d_origins, const float* d_directions
     const size_t smem = stack_smem_bytes();
     CB_CUDA(cudaFuncSetAttribute(intersect_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    CB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, intersect_kernel<false>, PROP_THREADS, smem));
+    CB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, intersect_kernel<false>, INT_THREADS, smem));
     if (per_sm < 1) per_sm = 1;
-    unsigned blocks = (unsigned)std::min<uint64_t>((n + PROP_THREADS - 1) / PROP_THREADS, (uint64_t)c.sm_count * per_sm);
+    unsigned blocks = (unsigned)std::min<uint64_t>((n + INT_THREADS - 1) / INT_THREADS, (uint64_t)c.sm_count * per_sm);
     RaySource src = {d_origins, d_directions, d_last_hit, d_triangle_out, d_distance_out};
-    intersect_kernel<false><<<blocks, PROP_THREADS, smem, c.stream>>>(g->dev, src, n, c.d_counters, tune_from_env());
+    intersect_kernel<false><<<blocks, INT_THREADS, smem, c.stream>>>(g->dev, src, n, c.d_counters, tune_from_env());
     CB_CUDA(cudaGetLastError());
     CB_CUDA(cudaMemcpyAsync(c.h_counters, c.d_counters, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c.stream));
     CB_CUDA(cudaStreamSynchronize(c.stream));
@@ -857,7 +858,7 @@ int cb_propagate(const CbPhotonBank* bank, cb_geom_t gh, cb_rng_t rh, int32_t nt
     CB_CUDA(cudaFuncSetAttribute(step_physics_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_tab, 16)));
     CB_CUDA(cudaFuncSetAttribute(k_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tail));
     int phys_per_sm = 0, tail_per_sm = 0, int_per_sm = 0;
-    CB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&int_per_sm, k_int, PROP_THREADS, smem_int));
+    CB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&int_per_sm, k_int, INT_THREADS, smem_int));
     CB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&phys_per_sm, step_physics_kernel, PROP_THREADS, smem_tab));
     CB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tail_per_sm, k_tail, TAIL_THREADS, smem_tail));
     if (int_per_sm < 1 || phys_per_sm < 1 || tail_per_sm < 1) return fail(CB_ERR_CUDA, "cb_propagate: kernels do not fit on an SM");
@@ -906,14 +907,15 @@ int cb_propagate(const CbPhotonBank* bank, cb_geom_t gh, cb_rng_t rh, int32_t nt
                                                                 c.d_sorted, (int)n_alive, 0, 30, c.stream));
                         launches += 2;
                     }
-                    const unsigned iblocks = (unsigned)std::min<uint64_t>(blocks, (uint64_t)c.sm_count * int_per_sm);
+                    const unsigned iblocks = (unsigned)std::min<uint64_t>((n_alive + INT_THREADS - 1) / INT_THREADS,
+                                                                          (uint64_t)c.sm_count * int_per_sm);
                     const bool time_it = (step == 0 && first == 0);
                     if (time_it) CB_CUDA(cudaEventRecord(c.iev0, c.stream));
                     if (trace) cudaEventRecord(tev[0], c.stream);
                     PropParams PI = P;
                     if (sort_threshold && exact && n_alive >= sort_threshold) PI.queue_in = c.d_sorted;
                     mark("pre-int");
-                    k_int<<<iblocks, PROP_THREADS, smem_int, c.stream>>>(g->dev, PI, tune);
+                    k_int<<<iblocks, INT_THREADS, smem_int, c.stream>>>(g->dev, PI, tune);
                     mark("int");
                     if (trace) cudaEventRecord(tev[1], c.stream);
                     if (time_it) { CB_CUDA(cudaEventRecord(c.iev1, c.stream)); int0_rays = n_alive; }
