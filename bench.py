@@ -290,6 +290,9 @@ def run_ours(args):
     import torch
     h2d = sum(getattr(ev, f).nbytes for f in ('pos', 'dir', 'pol', 'wavelengths', 't', 'flags', 'evidx'))
     sim_kw = dict(keep_hits=False, keep_flat_hits=True, run_daq=True, max_steps=MAX_STEPS, photons_per_batch=n)
+    # the event's host arrays live in page-locked memory (gpu.pagelocked_empty, the role of
+    # pycuda's pagelocked_empty in the reference): every step uploads them again, host -> device
+    ev = gpu.pin_photons(ev)
     list(s.simulate((event.Event(photons_beg=ev) for _ in range(2)), **sim_kw))
     nch = s.gpu_geometry.nchannels
     barrier(world)

@@ -30,6 +30,12 @@ class CbSurface(C.Structure):
             'angular_reflect_specular', 'angular_reflect_diffuse')])
 
 
+class CbWirePlane(C.Structure):
+    _fields_ = [('origin', f32 * 3), ('u', f32 * 3), ('v', f32 * 3),
+                ('pitch', f32), ('radius', f32), ('umin', f32), ('umax', f32), ('vmin', f32), ('vmax', f32), ('v0', f32),
+                ('surface_index', i32), ('material_outer_index', i32), ('material_inner_index', i32), ('color', u32)]
+
+
 class CbGeometryDesc(C.Structure):
     _fields_ = [
         ('vertices', vp), ('nvertices', u64),
@@ -42,7 +48,7 @@ class CbGeometryDesc(C.Structure):
         ('surfaces', C.POINTER(CbSurface)), ('nsurfaces', i32),
         ('wavelength_n', i32), ('wavelength_start', f32), ('wavelength_step', f32),
         ('time_n', i32), ('time_start', f32), ('time_step', f32),
-        ('nwireplanes', i32),
+        ('nwireplanes', i32), ('wireplanes', C.POINTER(CbWirePlane)),
     ]
 
 

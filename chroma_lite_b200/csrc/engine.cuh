@@ -107,6 +107,8 @@ struct DevGeometry {
     uint32_t ref_root_x, ref_root_y, ref_root_z;   // the reference tree's root box
     uint32_t smem_floats;     // leading floats of the pool staged into shared memory
     uint32_t nmaterials, nsurfaces;
+    const CbWirePlane* wireplanes;   // analytic wire planes (cold path; usually none)
+    int32_t nwireplanes;
 };
 
 // shared-memory view handed to the physics (tables staged by the kernel prologue)
@@ -1229,19 +1231,205 @@ __device__ __forceinline__ int at_surface(const DevGeometry& g, const Tables& T,
     return CMD_PASS;
 }
 
+// Nearest analytic wire-plane boundary along the photon's ray (behaviour of the
+// analytic branch of fill_state, photon.h:108-270): per plane an orthonormal (u, v, n)
+// frame in double precision, the ray clipped to the plane's u extent and to the slab
+// |n| <= radius, the range of wire indices k the clipped segment can reach, and for
+// each of them the roots of the ray-cylinder quadratic in the (v, n) plane.  The root
+// taken depends on whether the origin is outside (entry root), inside (exit root) or
+// numerically on the cylinder (a 1e-4 mm step).  Candidates never prune against each
+// other except through `distance` (strictly nearer wins, compared in float).
+struct WireHit {
+    float distance;            // 1e30f: none
+    int surface, material_inner, material_outer;
+    float3 normal;             // outward cylinder normal at the hit (unoriented)
+    float dot_raw;             // normal . (-direction)
+};
+static __device__ __noinline__ void wire_planes_nearest(const DevGeometry& g, const float3 pos, const float3 dir,
+                                                        float best_distance, WireHit& hit)
+{
+    hit.distance = 1e30f;
+    hit.surface = -1; hit.material_inner = -1; hit.material_outer = -1;
+    hit.normal = f3(0.0f, 0.0f, 0.0f);
+    hit.dot_raw = 0.0f;
+    for (int ip = 0; ip < g.nwireplanes; ip++) {
+        const CbWirePlane& wp = g.wireplanes[ip];
+        // orthonormal frame: u normalised, v made orthogonal to u and normalised, n = u x v
+        const double ux = (double)wp.u[0], uy = (double)wp.u[1], uz = (double)wp.u[2];
+        const double vx0 = (double)wp.v[0], vy0 = (double)wp.v[1], vz0 = (double)wp.v[2];
+        const double un = 1.0 / sqrt(ux * ux + uy * uy + uz * uz);
+        const double ux1 = ux * un, uy1 = uy * un, uz1 = uz * un;
+        const double vdotu = vx0 * ux1 + vy0 * uy1 + vz0 * uz1;
+        const double vx1 = vx0 - vdotu * ux1;
+        const double vy1 = vy0 - vdotu * uy1;
+        const double vz1 = vz0 - vdotu * uz1;
+        const double vn = 1.0 / sqrt(vx1 * vx1 + vy1 * vy1 + vz1 * vz1);
+        const double vx = vx1 * vn, vy = vy1 * vn, vz = vz1 * vn;
+        const double nx = uy1 * vz - uz1 * vy;
+        const double ny = uz1 * vx - ux1 * vz;
+        const double nz = ux1 * vy - uy1 * vx;
+
+        const float3 w = pos - f3(wp.origin[0], wp.origin[1], wp.origin[2]);
+        const double du = (double)dir.x * ux1 + (double)dir.y * uy1 + (double)dir.z * uz1;
+        const double dv = (double)dir.x * vx + (double)dir.y * vy + (double)dir.z * vz;
+        const double dn = (double)dir.x * nx + (double)dir.y * ny + (double)dir.z * nz;
+        const double wu = (double)w.x * ux1 + (double)w.y * uy1 + (double)w.z * uz1;
+        const double wv0 = (double)w.x * vx + (double)w.y * vy + (double)w.z * vz - (double)wp.v0;
+        const double wn0 = (double)w.x * nx + (double)w.y * ny + (double)w.z * nz;
+
+        // the ray's parameter window inside the plane's u extent
+        double t_in = -1.0e300, t_out = 1.0e300;
+        if (fabs(du) < 1e-15) {
+            if (wu < (double)wp.umin || wu > (double)wp.umax) continue;
+        } else {
+            double t1 = ((double)wp.umin - wu) / du;
+            double t2 = ((double)wp.umax - wu) / du;
+            if (t1 > t2) { const double tmp = t1; t1 = t2; t2 = tmp; }
+            if (t1 > t_in) t_in = t1;
+            if (t2 < t_out) t_out = t2;
+            if (t_in > t_out) continue;
+        }
+
+        const double pitch = (double)wp.pitch;
+        const double inv_pitch = (pitch != 0.0) ? (1.0 / pitch) : 0.0;
+        const double wire_radius = (double)wp.radius;
+        const double wire_thickness = 2.0 * wire_radius;
+        const double pad_v = 0.5 * wire_thickness + 1e-6;
+        const double pad_n = 0.5 * wire_thickness + 1e-6;
+
+        const int kmin = (int)ceil(((double)wp.vmin - (double)wp.v0) / pitch);
+        const int kmax = (int)floor(((double)wp.vmax - (double)wp.v0) / pitch);
+        const double A = dv * dv + dn * dn;
+        int k_start = kmin, k_stop = kmax;
+
+        if (kmin <= kmax) {
+            // wires the segment can reach: clip to the slab around the plane, then to v
+            const double t_eps = 1.0e-4;
+            double t_lo = fmax(t_in, t_eps);
+            double t_hi = t_out;
+            const double best_cap = (double)best_distance;
+            if (best_cap < t_hi) t_hi = best_cap;
+            if (fabs(dn) > 1e-12) {
+                double tn1 = (-pad_n - wn0) / dn;
+                double tn2 = (pad_n - wn0) / dn;
+                if (tn1 > tn2) { const double tmp = tn1; tn1 = tn2; tn2 = tmp; }
+                t_lo = fmax(t_lo, tn1);
+                t_hi = fmin(t_hi, tn2);
+            } else if (fabs(wn0) > pad_n) {
+                continue;
+            }
+            if (t_hi < t_lo) continue;
+            if (fabs(dn) <= 1e-12 && fabs(dv) > 1e-12) {
+                const double t_span = (pitch + wire_thickness) / fabs(dv);
+                t_hi = fmin(t_hi, t_lo + t_span);
+            }
+            const double v_entry = wv0 + dv * t_lo;
+            const double v_exit = wv0 + dv * t_hi;
+            double v_lo = fmin(v_entry, v_exit) - pad_v;
+            double v_hi = fmax(v_entry, v_exit) + pad_v;
+            if (wv0 - pad_v < v_lo) v_lo = wv0 - pad_v;
+            if (wv0 + pad_v > v_hi) v_hi = wv0 + pad_v;
+            long long k_lo = (long long)floor(v_lo * inv_pitch);
+            long long k_hi = (long long)ceil(v_hi * inv_pitch);
+            if (k_lo < kmin) k_lo = kmin;
+            if (k_hi > kmax) k_hi = kmax;
+            if (k_lo > k_hi) continue;
+            k_start = (int)k_lo;
+            k_stop = (int)k_hi;
+        }
+
+        for (int k = k_start; k <= k_stop; k++) {
+            const double wv = wv0 - (double)k * pitch;
+            const double B = wv * dv + wn0 * dn;
+            const double Cq = wv * wv + wn0 * wn0 - wire_radius * wire_radius;
+            const double disc = B * B - A * Cq;
+            if (disc < 0.0) continue;
+            const double sqrt_disc = sqrt(disc);
+            const double t_small = (-B - sqrt_disc) / A;
+            const double t_large = (-B + sqrt_disc) / A;
+            const double t_min = 1.0e-4;
+            const double r2_wire = wire_radius * wire_radius;
+            const double r2_0 = wv * wv + wn0 * wn0;
+            const double eps0 = fmax(1e-18, 1e-12 * r2_wire);
+            double t;
+            if (r2_0 > r2_wire + eps0) {            // origin outside: forward entry root
+                if (t_small <= t_min) continue;
+                t = t_small;
+            } else if (r2_0 < r2_wire - eps0) {     // origin inside: forward exit root
+                if (t_large <= t_min) continue;
+                t = t_large;
+            } else {                                // numerically on the surface
+                t = t_min;
+            }
+            const double uc = wu + du * t;
+            if (uc < wp.umin || uc > wp.umax) continue;
+            if ((float)t >= hit.distance) continue;
+            if (t < t_in || t > t_out) continue;
+            const double vn_hit = wv + dv * t;
+            const double nn_hit = wn0 + dn * t;
+            const double len = sqrt(vn_hit * vn_hit + nn_hit * nn_hit);
+            if (len <= 0.0) continue;
+            const float3 n_local = f3((float)((vn_hit / len) * vx + (nn_hit / len) * nx),
+                                      (float)((vn_hit / len) * vy + (nn_hit / len) * ny),
+                                      (float)((vn_hit / len) * vz + (nn_hit / len) * nz));
+            hit.distance = (float)t;
+            hit.surface = wp.surface_index;
+            hit.material_inner = wp.material_inner_index;
+            hit.material_outer = wp.material_outer_index;
+            hit.normal = n_local;
+            hit.dot_raw = dot(n_local, -dir);
+        }
+    }
+}
+
+// The analytic candidate competes with the mesh hit (photon.h:272-330): it wins when it
+// is nearer (in double, by more than 1e-12) and its plane has a surface; the photon's
+// last_hit_triangle becomes -2 and the materials follow the side the photon comes from.
+static __device__ __noinline__ bool wire_plane_boundary(const DevGeometry& g, const Tables& T, Photon& p, StepState& s,
+                                                        int tri, float distance)
+{
+    WireHit wh;
+    const float best = (tri == -1) ? 1e30f : distance;
+    wire_planes_nearest(g, p.pos, p.dir, best, wh);
+    if (!(wh.surface >= 0 && (double)wh.distance + 1e-12 < (double)best)) return false;
+    s.distance = wh.distance;
+    s.surface_index = wh.surface;
+    p.last_hit_triangle = -2;
+    const CbMaterial *m1, *m2;
+    if (wh.dot_raw > 0.0f) {                 // outside -> inside: the outward normal already faces the photon
+        m1 = &g.materials[wh.material_outer]; m2 = &g.materials[wh.material_inner];
+        s.normal = wh.normal;
+    } else {
+        m1 = &g.materials[wh.material_inner]; m2 = &g.materials[wh.material_outer];
+        s.normal = -wh.normal;
+    }
+    s.n1 = interp_property(g, p.wavelength, T.at(m1->refractive_index));
+    s.n2 = interp_property(g, p.wavelength, T.at(m2->refractive_index));
+    s.absorption_length = interp_property(g, p.wavelength, T.at(m1->absorption_length));
+    s.scattering_length = interp_property(g, p.wavelength, T.at(m1->scattering_length));
+    s.material1 = m1;
+    return true;
+}
+
 // everything after the intersection for one step (propagate.cu:312-336).
 // Returns true when the photon continues to another step.
+// WIRES: geometry with analytic wire planes (a separate instantiation, so that the cold
+// path costs the usual kernels neither registers nor instructions).
+template <bool WIRES>
 __device__ __forceinline__ bool physics_step(const DevGeometry& g, const Tables& T, Photon& p, Rng& rng,
                                              int tri, float distance, bool use_weights, int scatter_first)
 {
-    if (tri == -1) {
-        p.last_hit_triangle = -1;
-        p.history |= CB_NO_HIT;
-        return false;
-    }
     StepState s;
-    s.distance = distance;
-    classify_hit(g, T, p, s, tri);
+    const bool analytic = WIRES && g.nwireplanes > 0 && wire_plane_boundary(g, T, p, s, tri, distance);
+    if (!analytic) {
+        if (tri == -1) {
+            p.last_hit_triangle = -1;
+            p.history |= CB_NO_HIT;
+            return false;
+        }
+        s.distance = distance;
+        classify_hit(g, T, p, s, tri);
+    }
     int command = to_boundary(g, T, p, s, rng, use_weights, scatter_first);
     if (command == CMD_BREAK) return false;
     if (command == CMD_CONTINUE) return true;

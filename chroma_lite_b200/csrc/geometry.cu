@@ -92,7 +92,7 @@ static void free_geometry(Geometry* g)
 {
     cudaFree(g->vertices); cudaFree(g->triangles); cudaFree(g->material_codes); cudaFree(g->colors);
     cudaFree(g->solid_id); cudaFree(g->nodes); cudaFree(g->native_nodes); cudaFree(g->tri64); cudaFree(g->tables);
-    cudaFree(g->materials); cudaFree(g->surfaces); cudaFree(g->solid_to_channel);
+    cudaFree(g->materials); cudaFree(g->surfaces); cudaFree(g->wireplanes); cudaFree(g->solid_to_channel);
     cudaFree(g->time_cdf_x); cudaFree(g->time_cdf_y); cudaFree(g->charge_cdf_x); cudaFree(g->charge_cdf_y);
     delete g;
 }
@@ -107,7 +107,14 @@ int cb_geometry_create(const CbGeometryDesc* d, cb_geom_t* out)
 {
     CB_REQUIRE_INIT();
     if (!d || !out) return fail(CB_ERR_INVALID, "cb_geometry_create: null argument");
-    if (d->nwireplanes != 0) return fail(CB_ERR_UNSUPPORTED, "analytic wire planes are not supported");
+    if (d->nwireplanes < 0 || (d->nwireplanes > 0 && !d->wireplanes))
+        return fail(CB_ERR_INVALID, "cb_geometry_create: nwireplanes without a wireplanes array");
+    for (int i = 0; i < d->nwireplanes; i++) {
+        const CbWirePlane& wp = d->wireplanes[i];
+        if (wp.material_inner_index < 0 || wp.material_inner_index >= d->nmaterials || wp.material_outer_index < 0 ||
+            wp.material_outer_index >= d->nmaterials || wp.surface_index >= d->nsurfaces)
+            return fail(CB_ERR_INVALID, "wire plane %d: material/surface index out of range", i);
+    }
     if (!d->vertices || !d->triangles || !d->material_codes || !d->nodes || d->nnodes == 0)
         return fail(CB_ERR_INVALID, "cb_geometry_create: vertices/triangles/material_codes/nodes are required");
     if (d->nmaterials <= 0 || d->nmaterials > 127 || d->nsurfaces < 0 || d->nsurfaces > 127)
@@ -151,6 +158,7 @@ int cb_geometry_create(const CbGeometryDesc* d, cb_geom_t* out)
     }
     UP(materials, d->materials, (uint64_t)d->nmaterials);
     UP(surfaces, d->surfaces, (uint64_t)d->nsurfaces);
+    UP(wireplanes, d->wireplanes, (uint64_t)d->nwireplanes);
 #undef UP
 
     std::vector<uint32_t> rank;
@@ -216,6 +224,7 @@ int cb_geometry_create(const CbGeometryDesc* d, cb_geom_t* out)
     v.root_x = root_entry[0]; v.root_y = root_entry[1]; v.root_z = root_entry[2]; v.root_w = root_entry[3];
     v.ref_root_x = d->nodes[0]; v.ref_root_y = d->nodes[1]; v.ref_root_z = d->nodes[2];
     v.nmaterials = d->nmaterials; v.nsurfaces = d->nsurfaces;
+    v.wireplanes = d->nwireplanes ? g->wireplanes : nullptr; v.nwireplanes = d->nwireplanes;
     // stage the leading part of the pool (the wavelength tables; the host lays
     // the long time CDFs out last) into shared memory, up to 48 KB
     uint64_t stage = std::min<uint64_t>(d->table_floats, 12288);

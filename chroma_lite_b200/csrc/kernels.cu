@@ -327,6 +327,7 @@ step_intersect_kernel(const __grid_constant__ DevGeometry g, const __grid_consta
     persistent_intersect<COUNT>(g, src, n, P.cursor, (uint32_t)__cvta_generic_to_shared(smem_raw), P.counters, tune);
 }
 
+template <bool WIRES>
 __global__ void __launch_bounds__(PROP_THREADS, 2)
 step_physics_kernel(DevGeometry g, PropParams P)
 {
@@ -356,7 +357,7 @@ step_physics_kernel(DevGeometry g, PropParams P)
                 if (photon_is_nan(p)) {
                     p.history |= CB_NO_HIT | CB_NAN_ABORT;
                 } else {
-                    alive = physics_step(g, T, p, rng, P.hit_tri[k], P.hit_dist[k], P.use_weights != 0,
+                    alive = physics_step<WIRES>(g, T, p, rng, P.hit_tri[k], P.hit_dist[k], P.use_weights != 0,
                                          P.step == 0 ? P.scatter_first : 0);
                 }
                 rng_store(P.rng, k, rng);
@@ -382,7 +383,7 @@ constexpr int TAIL_THREADS = 256;
 #ifndef CB_TAIL_BLOCKS
 #define CB_TAIL_BLOCKS 4     /* 64 registers: 32 resident warps (photons) per SM */
 #endif
-template <bool COUNT>
+template <bool COUNT, bool WIRES>
 __global__ void __launch_bounds__(TAIL_THREADS, CB_TAIL_BLOCKS)
 propagate_tail_kernel(DevGeometry g, PropParams P)
 {
@@ -425,7 +426,7 @@ propagate_tail_kernel(DevGeometry g, PropParams P)
                 float dist;
                 const int tri = warp_traverse<COUNT>(g, p.pos, p.dir, p.last_hit_triangle, dist, wstack, wleaf,
                                                      (uint32_t*)(P.counters + 3), &cnt);
-                alive = physics_step(g, T, p, rng, tri, dist, P.use_weights != 0, sf);
+                alive = physics_step<WIRES>(g, T, p, rng, tri, dist, P.use_weights != 0, sf);
                 sf = 0;
             }
         }
@@ -850,16 +851,19 @@ int cb_propagate(const CbPhotonBank* bank, cb_geom_t gh, cb_rng_t rh, int32_t nt
     unsigned long long* d_cursor = c.d_step_counts + c.step_slots; // [s]: work counter of step s
 
     auto k_int = count ? step_intersect_kernel<true> : step_intersect_kernel<false>;
-    auto k_tail = count ? propagate_tail_kernel<true> : propagate_tail_kernel<false>;
+    const bool wires = g->dev.nwireplanes > 0;
+    auto k_tail = wires ? (count ? propagate_tail_kernel<true, true> : propagate_tail_kernel<false, true>)
+                        : (count ? propagate_tail_kernel<true, false> : propagate_tail_kernel<false, false>);
+    auto k_phys = wires ? step_physics_kernel<true> : step_physics_kernel<false>;
     const size_t smem_int = stack_smem_bytes();
     const size_t smem_tab = (g->smem_table_bytes + 127u) & ~127u;
     const size_t smem_tail = smem_tab + (size_t)(TAIL_THREADS / 32) * (CB_WSTACK + CB_WLEAF) * sizeof(uint2);
     CB_CUDA(cudaFuncSetAttribute(k_int, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_int));
-    CB_CUDA(cudaFuncSetAttribute(step_physics_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_tab, 16)));
+    CB_CUDA(cudaFuncSetAttribute(k_phys, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_tab, 16)));
     CB_CUDA(cudaFuncSetAttribute(k_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tail));
     int phys_per_sm = 0, tail_per_sm = 0, int_per_sm = 0;
     CB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&int_per_sm, k_int, INT_THREADS, smem_int));
-    CB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&phys_per_sm, step_physics_kernel, PROP_THREADS, smem_tab));
+    CB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&phys_per_sm, k_phys, PROP_THREADS, smem_tab));
     CB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tail_per_sm, k_tail, TAIL_THREADS, smem_tail));
     if (int_per_sm < 1 || phys_per_sm < 1 || tail_per_sm < 1) return fail(CB_ERR_CUDA, "cb_propagate: kernels do not fit on an SM");
 
@@ -920,7 +924,7 @@ int cb_propagate(const CbPhotonBank* bank, cb_geom_t gh, cb_rng_t rh, int32_t nt
                     if (trace) cudaEventRecord(tev[1], c.stream);
                     if (time_it) { CB_CUDA(cudaEventRecord(c.iev1, c.stream)); int0_rays = n_alive; }
                     const unsigned pblocks = (unsigned)std::min<uint64_t>(blocks, (uint64_t)c.sm_count * phys_per_sm);
-                    step_physics_kernel<<<pblocks, PROP_THREADS, smem_tab, c.stream>>>(g->dev, P);
+                    k_phys<<<pblocks, PROP_THREADS, smem_tab, c.stream>>>(g->dev, P);
                     mark("phys");
                     if (trace) cudaEventRecord(tev[2], c.stream);
                     CB_CUDA(cudaGetLastError());

@@ -52,13 +52,53 @@ def interp_property(wavelengths, prop):
     return np.interp(wavelengths, prop[:, 0], prop[:, 1]).astype(np.float32)
 
 
-def build_tables(geometry, wavelengths, times):
+def wireplane_lists(geometry):
+    """Material and surface lists extended by the objects that only analytic wire planes
+    reference (chroma/gpu/geometry.py:109-112, 265-270), plus the plane descriptors."""
+    materials = list(geometry.unique_materials)
+    surfaces = list(geometry.unique_surfaces)
+    planes = list(getattr(geometry, 'wireplanes', None) or [])
+    for desc in planes:
+        for mat in (desc.get('material_inner', None), desc.get('material_outer', None)):
+            if mat is not None and mat not in materials:
+                materials.append(mat)
+    for desc in planes:
+        surface = desc.get('surface', None)
+        if surface is not None and surface not in surfaces:
+            surfaces.append(surface)
+    return materials, surfaces, planes
+
+
+def build_wireplanes(planes, materials, surfaces):
+    """CbWirePlane[] from the reference's dict descriptors (chroma/gpu/geometry.py:343-387)."""
+    arr = (_lib.CbWirePlane * max(1, len(planes)))()
+    for i, desc in enumerate(planes):
+        wp = arr[i]
+        for name in ('origin', 'u', 'v'):
+            vals = np.asarray(desc[name], dtype=np.float32)
+            setattr(wp, name, (C.c_float * 3)(*[float(x) for x in vals]))
+        for name in ('pitch', 'radius', 'umin', 'umax', 'vmin', 'vmax', 'v0'):
+            setattr(wp, name, float(np.float32(desc[name])))
+        surface = desc.get('surface', None)
+        wp.surface_index = -1 if surface is None else (surfaces.index(surface) if surface in surfaces else -1)
+        mo, mi = desc.get('material_outer', None), desc.get('material_inner', None)
+        if mo is None or mi is None:           # "should not happen under normal use": the reference falls back to slot 0
+            wp.material_outer_index = wp.material_inner_index = 0
+        else:
+            wp.material_outer_index, wp.material_inner_index = materials.index(mo), materials.index(mi)
+        wp.color = int(desc.get('color', 0)) & 0xFFFFFFFF
+    return arr
+
+
+def build_tables(geometry, wavelengths, times, materials=None, surfaces=None):
     """(pool, materials[], surfaces[]) for CbGeometryDesc from a flattened geometry."""
     pool = _Pool()
-    mats = (_lib.CbMaterial * max(1, len(geometry.unique_materials)))()
+    materials = list(geometry.unique_materials) if materials is None else materials
+    surfaces = list(geometry.unique_surfaces) if surfaces is None else surfaces
+    mats = (_lib.CbMaterial * max(1, len(materials)))()
     pending_time = []
     W = len(wavelengths)
-    for i, m in enumerate(geometry.unique_materials):
+    for i, m in enumerate(materials):
         if m is None:
             raise Exception('one or more triangles is missing a material.')
         cm = mats[i]
@@ -76,8 +116,8 @@ def build_tables(geometry, wavelengths, times):
             cm.comp_reemission_wvl_cdf = pool.add(np.concatenate([interp_property(wavelengths, c) for c in m.comp_reemission_wvl_cdf]))
             cm.comp_absorption_length = pool.add(np.concatenate([interp_property(wavelengths, c) for c in m.comp_absorption_length]))
             pending_time.append((i, pool.add_back(np.concatenate([interp_property(times, c) for c in m.comp_reemission_time_cdf]))))
-    surfs = (_lib.CbSurface * max(1, len(geometry.unique_surfaces)))()
-    for i, s in enumerate(geometry.unique_surfaces):
+    surfs = (_lib.CbSurface * max(1, len(surfaces)))()
+    for i, s in enumerate(surfaces):
         cs = surfs[i]
         for f, _t in _lib.CbSurface._fields_:
             if f != 'thickness':
@@ -131,8 +171,6 @@ def make_desc(geometry, wavelengths=None, times=None):
         times = np.arange(0, 1000, time_step)
     else:
         time_step = _uniform_step(times, 'times')
-    if getattr(geometry, 'wireplanes', None):
-        raise NotImplementedError('analytic wire planes are not supported by chroma_lite_b200')
     if not hasattr(geometry, 'mesh'):
         geometry.flatten()
     if geometry.bvh is None:
@@ -146,8 +184,10 @@ def make_desc(geometry, wavelengths=None, times=None):
     keep['colors'] = np.ascontiguousarray(geometry.colors, dtype=np.uint32)
     nodes = np.ascontiguousarray(geometry.bvh.nodes)
     keep['nodes'] = nodes
-    pool, mats, surfs = build_tables(geometry, wavelengths, times)
+    materials, surfaces, planes = wireplane_lists(geometry)
+    pool, mats, surfs = build_tables(geometry, wavelengths, times, materials, surfaces)
     keep['pool'], keep['mats'], keep['surfs'] = pool, mats, surfs
+    keep['wireplanes'] = build_wireplanes(planes, materials, surfaces)
     d = _lib.CbGeometryDesc()
     d.vertices, d.nvertices = keep['vertices'].ctypes.data, len(keep['vertices'])
     d.triangles, d.ntriangles = keep['triangles'].ctypes.data, len(keep['triangles'])
@@ -159,11 +199,12 @@ def make_desc(geometry, wavelengths=None, times=None):
     d.world_origin = (C.c_float * 3)(*[float(x) for x in wo])
     d.world_scale = float(np.float32(geometry.bvh.world_coords.world_scale))
     d.table_pool, d.table_floats = pool.ctypes.data, len(pool)
-    d.materials, d.nmaterials = mats, len(geometry.unique_materials)
-    d.surfaces, d.nsurfaces = surfs, len(geometry.unique_surfaces)
+    d.materials, d.nmaterials = mats, len(materials)
+    d.surfaces, d.nsurfaces = surfs, len(surfaces)
     d.wavelength_n, d.wavelength_start, d.wavelength_step = len(wavelengths), float(wavelengths[0]), wavelength_step
     d.time_n, d.time_start, d.time_step = len(times), float(times[0]), time_step
-    d.nwireplanes = 0
+    d.nwireplanes = len(planes)
+    d.wireplanes = keep['wireplanes'] if planes else None
     return d, keep
 
 

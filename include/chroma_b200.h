@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CB_ABI_VERSION 1
+#define CB_ABI_VERSION 2
 
 typedef enum {
     CB_OK = 0,
@@ -86,6 +86,19 @@ typedef struct {
             angular_reflect_specular, angular_reflect_diffuse;
 } CbSurface;
 
+/* Analytic wire plane: a periodic row of parallel cylinders of radius `radius`, axes along
+ * `u`, centres at v0 + k*pitch along `v`, clipped to [umin,umax] x [vmin,vmax]
+ * (= struct WirePlane, chroma/cuda/geometry_types.h:42-58; filled like
+ * chroma/gpu/geometry.py:343-387).  The photon step picks the nearer of the mesh hit
+ * and the wire hit (chroma/cuda/photon.h:96-300). */
+typedef struct {
+    float origin[3], u[3], v[3];
+    float pitch, radius, umin, umax, vmin, vmax, v0;
+    int32_t surface_index;          /* planes with surface_index < 0 never win (photon.h:272) */
+    int32_t material_outer_index, material_inner_index;
+    uint32_t color;
+} CbWirePlane;
+
 /*
  * Flattened geometry handed to the engine; mirrors what GPUGeometry.__init__
  * uploads (chroma/gpu/geometry.py:389-520) and `struct Geometry`
@@ -107,7 +120,8 @@ typedef struct {
     const CbSurface*  surfaces;      int32_t nsurfaces;
     int32_t wavelength_n; float wavelength_start, wavelength_step;
     int32_t time_n;       float time_start, time_step;
-    int32_t nwireplanes;             /* must be 0 (analytic wire planes: unsupported) */
+    int32_t nwireplanes;
+    const CbWirePlane* wireplanes;   /* [nwireplanes] or NULL */
 } CbGeometryDesc;
 
 /* Device-side views of what the library uploaded (for the GPUGeometry mirror). */

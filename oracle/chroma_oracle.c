@@ -23,8 +23,10 @@
  *     are statistical and stale); it is pinned here against
  *     the reference kernels run on the GPU (oracle/_ref) within tolerance.
  *
- * Analytic wire planes (photon.h:108-270) are not restated: nwireplanes == 0 in
- * every BASELINE config.
+ * Analytic wire planes (photon.h:96-330) are restated in wire_planes_nearest();
+ * the reference's tests hold no fixture for them (the primitive is this fork's
+ * addition), so they are pinned against the reference kernel run on the GPU
+ * (tests/test_gpu_propagate.py::test_wire_planes_vs_reference).
  */
 #include <math.h>
 #include <stdint.h>
@@ -481,10 +483,127 @@ static inline float get_theta(f3 a, f3 b) { return acosf(fmaxf(-1.0f, fminf(1.0f
 static inline const float *tab(const CbGeometryDesc *g, int32_t off) { return g->table_pool + off; }
 
 /* photon.h:87-397 (mesh branch only) */
+/* Nearest analytic wire boundary (photon.h:108-270), all in double as in the reference. */
+typedef struct { float distance; int surface, m_inner, m_outer; f3 normal; float dot_raw; } WireHit;
+static void wire_planes_nearest(const CbGeometryDesc *g, f3 pos, f3 dir, float best_distance, WireHit *hit)
+{
+    hit->distance = 1e30f; hit->surface = -1; hit->m_inner = -1; hit->m_outer = -1;
+    hit->normal = mk(0, 0, 0); hit->dot_raw = 0.0f;
+    for (int ip = 0; ip < g->nwireplanes; ip++) {
+        const CbWirePlane *wp = &g->wireplanes[ip];
+        const double ux = wp->u[0], uy = wp->u[1], uz = wp->u[2];
+        const double vx0 = wp->v[0], vy0 = wp->v[1], vz0 = wp->v[2];
+        const double un = 1.0 / sqrt(ux * ux + uy * uy + uz * uz);
+        const double ux1 = ux * un, uy1 = uy * un, uz1 = uz * un;
+        const double vdotu = vx0 * ux1 + vy0 * uy1 + vz0 * uz1;
+        const double vx1 = vx0 - vdotu * ux1, vy1 = vy0 - vdotu * uy1, vz1 = vz0 - vdotu * uz1;
+        const double vn = 1.0 / sqrt(vx1 * vx1 + vy1 * vy1 + vz1 * vz1);
+        const double vx = vx1 * vn, vy = vy1 * vn, vz = vz1 * vn;
+        const double nx = uy1 * vz - uz1 * vy, ny = uz1 * vx - ux1 * vz, nz = ux1 * vy - uy1 * vx;
+        const f3 w = sub(pos, mk(wp->origin[0], wp->origin[1], wp->origin[2]));
+        const double du = (double)dir.x * ux1 + (double)dir.y * uy1 + (double)dir.z * uz1;
+        const double dv = (double)dir.x * vx + (double)dir.y * vy + (double)dir.z * vz;
+        const double dn = (double)dir.x * nx + (double)dir.y * ny + (double)dir.z * nz;
+        const double wu = (double)w.x * ux1 + (double)w.y * uy1 + (double)w.z * uz1;
+        const double wv0 = (double)w.x * vx + (double)w.y * vy + (double)w.z * vz - (double)wp->v0;
+        const double wn0 = (double)w.x * nx + (double)w.y * ny + (double)w.z * nz;
+        double t_in = -1.0e300, t_out = 1.0e300;
+        if (fabs(du) < 1e-15) {
+            if (wu < (double)wp->umin || wu > (double)wp->umax) continue;
+        } else {
+            double t1 = ((double)wp->umin - wu) / du, t2 = ((double)wp->umax - wu) / du;
+            if (t1 > t2) { double tmp = t1; t1 = t2; t2 = tmp; }
+            if (t1 > t_in) t_in = t1;
+            if (t2 < t_out) t_out = t2;
+            if (t_in > t_out) continue;
+        }
+        const double pitch = wp->pitch;
+        const double inv_pitch = (pitch != 0.0) ? (1.0 / pitch) : 0.0;
+        const double wire_radius = wp->radius, wire_thickness = 2.0 * wire_radius;
+        const double pad_v = 0.5 * wire_thickness + 1e-6, pad_n = 0.5 * wire_thickness + 1e-6;
+        const int kmin = (int)ceil(((double)wp->vmin - (double)wp->v0) / pitch);
+        const int kmax = (int)floor(((double)wp->vmax - (double)wp->v0) / pitch);
+        const double A = dv * dv + dn * dn;
+        int k_start = kmin, k_stop = kmax;
+        if (kmin <= kmax) {
+            double t_lo = fmax(t_in, 1.0e-4), t_hi = t_out;
+            if ((double)best_distance < t_hi) t_hi = (double)best_distance;
+            if (fabs(dn) > 1e-12) {
+                double tn1 = (-pad_n - wn0) / dn, tn2 = (pad_n - wn0) / dn;
+                if (tn1 > tn2) { double tmp = tn1; tn1 = tn2; tn2 = tmp; }
+                t_lo = fmax(t_lo, tn1);
+                t_hi = fmin(t_hi, tn2);
+            } else if (fabs(wn0) > pad_n) {
+                continue;
+            }
+            if (t_hi < t_lo) continue;
+            if (fabs(dn) <= 1e-12 && fabs(dv) > 1e-12) t_hi = fmin(t_hi, t_lo + (pitch + wire_thickness) / fabs(dv));
+            const double v_entry = wv0 + dv * t_lo, v_exit = wv0 + dv * t_hi;
+            double v_lo = fmin(v_entry, v_exit) - pad_v, v_hi = fmax(v_entry, v_exit) + pad_v;
+            if (wv0 - pad_v < v_lo) v_lo = wv0 - pad_v;
+            if (wv0 + pad_v > v_hi) v_hi = wv0 + pad_v;
+            long long k_lo = (long long)floor(v_lo * inv_pitch), k_hi = (long long)ceil(v_hi * inv_pitch);
+            if (k_lo < kmin) k_lo = kmin;
+            if (k_hi > kmax) k_hi = kmax;
+            if (k_lo > k_hi) continue;
+            k_start = (int)k_lo; k_stop = (int)k_hi;
+        }
+        for (int k = k_start; k <= k_stop; k++) {
+            const double wv = wv0 - (double)k * pitch;
+            const double B = wv * dv + wn0 * dn;
+            const double Cq = wv * wv + wn0 * wn0 - wire_radius * wire_radius;
+            const double disc = B * B - A * Cq;
+            if (disc < 0.0) continue;
+            const double sq = sqrt(disc), t_small = (-B - sq) / A, t_large = (-B + sq) / A;
+            const double t_min = 1.0e-4, r2_wire = wire_radius * wire_radius, r2_0 = wv * wv + wn0 * wn0;
+            const double eps0 = fmax(1e-18, 1e-12 * r2_wire);
+            double t;
+            if (r2_0 > r2_wire + eps0) { if (t_small <= t_min) continue; t = t_small; }
+            else if (r2_0 < r2_wire - eps0) { if (t_large <= t_min) continue; t = t_large; }
+            else t = t_min;
+            const double uc = wu + du * t;
+            if (uc < wp->umin || uc > wp->umax) continue;
+            if ((float)t >= hit->distance) continue;
+            if (t < t_in || t > t_out) continue;
+            const double vh = wv + dv * t, nh = wn0 + dn * t, len = sqrt(vh * vh + nh * nh);
+            if (len <= 0.0) continue;
+            const f3 nl = mk((float)((vh / len) * vx + (nh / len) * nx), (float)((vh / len) * vy + (nh / len) * ny),
+                             (float)((vh / len) * vz + (nh / len) * nz));
+            hit->distance = (float)t; hit->surface = wp->surface_index;
+            hit->m_inner = wp->material_inner_index; hit->m_outer = wp->material_outer_index;
+            hit->normal = nl; hit->dot_raw = dot(nl, neg(dir));
+        }
+    }
+}
+
 static void fill_state(State *s, Photon *p, const CbGeometryDesc *g, orc_counters *c)
 {
     int tri = intersect_mesh(g, p->position, p->direction, &s->distance_to_boundary,
                              p->last_hit_triangle, c);
+    if (g->nwireplanes > 0 && g->wireplanes) {       /* photon.h:272-330 */
+        const float best = (tri == -1) ? 1e30f : s->distance_to_boundary;
+        WireHit wh;
+        wire_planes_nearest(g, p->position, p->direction, best, &wh);
+        if (wh.surface >= 0 && (double)wh.distance + 1e-12 < (double)best) {
+            const CbMaterial *m1, *m2;
+            s->distance_to_boundary = wh.distance;
+            s->surface_index = wh.surface;
+            p->last_hit_triangle = -2;
+            if (wh.dot_raw > 0.0f) {
+                m1 = &g->materials[wh.m_outer]; m2 = &g->materials[wh.m_inner];
+                s->surface_normal = wh.normal; s->inside_to_outside = 0;
+            } else {
+                m1 = &g->materials[wh.m_inner]; m2 = &g->materials[wh.m_outer];
+                s->surface_normal = neg(wh.normal); s->inside_to_outside = 1;
+            }
+            s->refractive_index1 = interp_property(g, p->wavelength, tab(g, m1->refractive_index));
+            s->refractive_index2 = interp_property(g, p->wavelength, tab(g, m2->refractive_index));
+            s->absorption_length = interp_property(g, p->wavelength, tab(g, m1->absorption_length));
+            s->scattering_length = interp_property(g, p->wavelength, tab(g, m1->scattering_length));
+            s->material1 = m1;
+            return;
+        }
+    }
     if (tri == -1) { p->last_hit_triangle = -1; p->history |= CB_NO_HIT; return; }
     p->last_hit_triangle = tri;
     const uint32_t *t = g->triangles + 3ull * (uint32_t)tri;

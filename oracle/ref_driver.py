@@ -271,11 +271,26 @@ class RefGeometry(object):
             self._aux.append(d)
             surf_ptrs.append(d.ptr)
         self.surface_ptrs = to_dev(np.array(surf_ptrs if surf_ptrs else [0], dtype=np.uint64))
+        # analytic wire planes: one 88-byte struct WirePlane each (geometry_types.h:42-58) behind a
+        # pointer array, as gpu/geometry.py:343-387 builds them
+        wp_ptrs = []
+        for i in range(desc.nwireplanes):
+            wp = keep['wireplanes'][i]
+            ws = _struct([np.array(list(wp.origin) + list(wp.u) + list(wp.v), dtype=np.float32).tobytes(),
+                          np.array([wp.pitch, wp.radius, wp.umin, wp.umax, wp.vmin, wp.vmax, wp.v0], dtype=np.float32).tobytes(),
+                          np.array([wp.surface_index, wp.material_outer_index, wp.material_inner_index], dtype=np.int32).tobytes(),
+                          np.uint32(wp.color).tobytes()])
+            assert len(ws) == 80, len(ws)
+            dws = to_dev(np.frombuffer(bytes(ws), dtype=np.uint8))
+            self._aux.append(dws)
+            wp_ptrs.append(dws.ptr)
+        self.wireplane_ptrs = to_dev(np.array(wp_ptrs, dtype=np.uint64)) if wp_ptrs else None
         g = _struct([_ptr(self.vertices.ptr), _ptr(self.triangles.ptr), _ptr(self.codes.ptr), _ptr(self.colors.ptr),
                      _ptr(self.nodes.ptr), _ptr(self.extra_nodes.ptr), _ptr(self.material_ptrs.ptr),
-                     _ptr(self.surface_ptrs.ptr), _ptr(0),
+                     _ptr(self.surface_ptrs.ptr), _ptr(self.wireplane_ptrs.ptr if wp_ptrs else 0),
                      np.array(list(desc.world_origin), dtype=np.float32).tobytes(),
-                     np.float32(desc.world_scale).tobytes(), np.int32(desc.nnodes).tobytes(), np.int32(0).tobytes()])
+                     np.float32(desc.world_scale).tobytes(), np.int32(desc.nnodes).tobytes(),
+                     np.int32(len(wp_ptrs)).tobytes()])
         assert len(g) == 96, len(g)
         self.gpudata = to_dev(np.frombuffer(bytes(g), dtype=np.uint8))
 

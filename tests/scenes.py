@@ -106,5 +106,34 @@ def scintillator_scene(nsteps=24):
     return with_bvh(geo)
 
 
+def wireplane_scene(size=400.0):
+    """Water cube with two crossed analytic wire planes (this fork's WirePlane primitive):
+    steel-like wires with a half-absorbing, half-reflecting surface, one plane along x at
+    z = 0 and one along y at z = 60, one of them referencing a material and a surface that
+    no triangle uses (chroma/gpu/geometry.py:109-112, 265-270)."""
+    geo = Geometry(optics.water)
+    geo.add_solid(Solid(cube(size), optics.water, vacuum, surface=optics.black_surface))
+    with_bvh(geo)
+    wl = standard_wavelengths.astype(np.float64)
+    steel = Material('steel')
+    steel.set('refractive_index', 2.5)
+    steel.set('absorption_length', 1e-3)
+    steel.set('scattering_length', 1e6)
+    wire_surface = Surface('wire')
+    wire_surface.set('absorb', 0.4)
+    wire_surface.set('reflect_specular', 0.3)
+    wire_surface.set('reflect_diffuse', 0.3)
+    glassy = Surface('glassy')          # transparent wires: exercises the inside branch
+    glassy.set('absorb', 0.0)
+    h = size / 2 - 20.0
+    geo.wireplanes = [
+        dict(origin=(0.0, 0.0, 0.0), u=(1.0, 0.0, 0.0), v=(0.0, 1.0, 0.0), pitch=5.0, radius=0.3, umin=-h, umax=h,
+             vmin=-h, vmax=h, v0=0.0, surface=wire_surface, material_inner=steel, material_outer=optics.water, color=0x33),
+        dict(origin=(0.0, 0.0, 60.0), u=(0.0, 2.0, 0.0), v=(1.0, 0.3, 0.0), pitch=3.0, radius=0.8, umin=-h, umax=h,
+             vmin=-0.5 * h, vmax=0.7 * h, v0=0.4, surface=glassy, material_inner=optics.glass, material_outer=optics.water),
+    ]
+    return geo
+
+
 def desc_of(geo):
     return make_desc(geo)

@@ -32,14 +32,16 @@ def reference_run(geo, photons, seed, max_steps, use_weights=False, scatter_firs
     return rp.get(), rng.states6()
 
 
-def compare(a, b, min_same=0.999, rtol=1e-4):
+def compare(a, b, min_same=0.999, rtol=1e-4, t_frac=1.0):
     same = (a.flags == b.flags) & (a.last_hit_triangles == b.last_hit_triangles)
     frac = same.mean()
     assert frac >= min_same, 'only %.5f of photons have identical flags + last_hit_triangle' % frac
     s = same
     scale = np.maximum(np.abs(b.pos[s]).max(axis=1), 1.0)
     assert (np.abs(a.pos[s] - b.pos[s]).max(axis=1) / scale < rtol).mean() > 0.999
-    assert np.allclose(a.t[s], b.t[s], rtol=rtol, atol=1e-3)
+    t_ok = np.isclose(a.t[s], b.t[s], rtol=rtol, atol=1e-3)
+    assert t_ok.mean() >= t_frac, 'times agree for %.5f of the photons with identical histories (worst %.3g ns)' % (
+        t_ok.mean(), np.abs(a.t[s] - b.t[s]).max())
     assert np.allclose(a.wavelengths[s], b.wavelengths[s], rtol=1e-5)
     return frac
 
@@ -195,3 +197,20 @@ def test_scheduler_invariance(gpu_ready, monkeypatch):
         assert np.array_equal(mine.pos, base.pos) and np.array_equal(mine.t, base.t)
         assert np.array_equal(st, outs[0][1])
     assert outs[1][2] == 1 and outs[0][2] > 10      # one persistent launch vs a launch pair per step
+
+
+@pytest.mark.parametrize('max_steps', [1, 30])
+def test_wire_planes_vs_reference(gpu_ready, max_steps):
+    # analytic wire planes (photon.h:96-330): photons from below cross two planes of wires;
+    # last_hit_triangle == -2 marks an analytic boundary
+    geo = scenes.wireplane_scene()
+    ph = scenes.point_source(60000, seed=21, wl_range=(350, 550), pos=(3.0, -7.0, -80.0))
+    mine, st_mine, _ = engine_run(geo, ph, 5, max_steps)
+    ref, st_ref = reference_run(geo, ph, 5, max_steps)
+    # (a photon bouncing inside a transparent wire can take a different number of bounces and still end
+    #  with the same flags: times are compared for 99.9 % like positions)
+    frac = compare(mine, ref, min_same=1.0 if max_steps == 1 else 0.999, t_frac=0.999)
+    assert (ref.last_hit_triangles == -2).sum() > 1000          # the planes are actually hit
+    if max_steps > 1:
+        assert (mine.flags & (event.SURFACE_ABSORB | event.REFLECT_SPECULAR | event.REFLECT_DIFFUSE)).astype(bool).mean() > 0.05
+    print('identical fraction', frac)

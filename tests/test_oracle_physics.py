@@ -98,3 +98,27 @@ def test_daq_time_and_charge_response():
     tint, qint, hist, unit = orc.run_daq(bank, orc.rng_init(4, 0, n), geo, geo.solid_id)
     assert tint.view(np.float32)[0] < 10.0 - 3.0 and abs(qint[0] * unit / n - 1.0) < 0.01
     assert tint[1] == np.float32(1e9).view(np.uint32)
+
+
+def test_oracle_wire_planes_geometry():
+    # analytic wire planes (photon.h:96-330): rays shot straight up through a plane of wires
+    # along x (pitch 5 mm, radius 0.3 mm) hit a wire iff |y - 5k| < 0.3, at z = -sqrt(r^2 - dy^2)
+    geo = scenes.wireplane_scene()
+    desc, keep = scenes.desc_of(geo)
+    assert desc.nwireplanes == 2 and desc.nmaterials == 4
+    n = 4001
+    y = np.linspace(-20.0, 20.0, n).astype(np.float32)
+    pos = np.column_stack([np.full(n, 1.0), y, np.full(n, -50.0)]).astype(np.float32)
+    d = np.tile(np.array([0, 0, 1], dtype=np.float32), (n, 1))
+    pol = np.tile(np.array([1, 0, 0], dtype=np.float32), (n, 1))
+    ph = event.Photons(pos, d, pol, np.full(n, 400.0, dtype=np.float32))
+    bank, cnt = orc.propagate(desc, ph, orc.rng_init(3, 0, n), max_steps=1)
+    dy = np.abs(y - 5.0 * np.round(y / 5.0))
+    on_wire = dy < 0.3 - 1e-4
+    off_wire = dy > 0.3 + 1e-4
+    hit = bank.last_hit_triangles == -2
+    # scattering/absorption in 50 mm of water is rare but possible: allow a handful of bulk events
+    assert (hit[on_wire]).mean() > 0.99 and not hit[off_wire & (bank.pos[:, 2] < -1.0)].any()
+    sel = on_wire & hit
+    z_expected = -np.sqrt(0.3 ** 2 - dy[sel].astype(np.float64) ** 2)
+    assert np.allclose(bank.pos[sel, 2], z_expected, atol=2e-4)
