@@ -380,6 +380,91 @@ def run_ours(args):
     emit(line)
 
 
+# ------------------------------------------------------------------ ray microbench (BASELINE config 2)
+def rays_scene():
+    """~1.2 M triangles: a finely tessellated sphere shell around a coarser one (the ~1M-triangle
+    STL BASELINE names is not shipped with the reference)."""
+    from chroma_lite_b200.geometry import Geometry, Solid, vacuum
+    from chroma_lite_b200.make import sphere
+    from chroma_lite_b200.demo import optics
+    geo = Geometry(optics.water)
+    geo.add_solid(Solid(sphere(1000.0, 708), optics.glass, optics.water))
+    geo.add_solid(Solid(sphere(600.0, 300), vacuum, optics.glass))
+    geo.flatten()
+    return geo
+
+
+def make_rays(geo, n, seed=1234):
+    rng = np.random.default_rng(seed)
+    lo, hi = geo.mesh.vertices.min(axis=0), geo.mesh.vertices.max(axis=0)
+    c, h = (lo + hi) / 2, (hi - lo) / 2 * 1.5
+    o = (c + h * rng.uniform(-1, 1, (n, 3))).astype(np.float32)
+    u = rng.uniform(-1, 1, n)
+    phi = rng.uniform(0, 2 * np.pi, n)
+    s = np.sqrt(1 - u * u)
+    d = np.column_stack([s * np.cos(phi), s * np.sin(phi), u]).astype(np.float32)
+    return o, d
+
+
+def run_rays(args):
+    """rays/s of the nearest-hit query (triangle index + distance) on a ~1.2 M-triangle mesh."""
+    from chroma_lite_b200 import gpu, _lib
+    from chroma_lite_b200 import gpuarray as ga
+    from chroma_lite_b200.gpu.tools import to_float3
+    from chroma_lite_b200.bvh import make_recursive_grid_bvh
+    _lib.init(0)
+    lib = _lib.lib()
+    n = args.photons if args.photons != 2500000 else 10000000
+    geo = rays_scene()
+    t0 = time.perf_counter()
+    geo.bvh = make_recursive_grid_bvh(geo.mesh)
+    bvh_s = time.perf_counter() - t0
+    o, d = make_rays(geo, n)
+    line = {'metric': 'rays/s, nearest-hit triangle + distance through the BVH', 'unit': 'rays/s', 'n_gpus': 1,
+            'steps': args.steps, 'warmup': args.warmup, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': 'rays', 'rays': n, 'triangles': int(len(geo.mesh.triangles)),
+                       'bvh_nodes': int(len(geo.bvh.nodes)), 'bvh_build_s': bvh_s,
+                       'l2': 'ray arrays (320 MB) and geometry exceed L2'}}
+    if args.impl == 'reference':
+        from oracle import ref_driver
+        from chroma_lite_b200.gpu.geometry import make_desc
+        desc, keep = make_desc(geo)
+        rg = ref_driver.RefGeometry(desc, keep)
+        ms = [ref_driver.intersect(rg, o, d, block=64)[2] for _ in range(args.warmup + args.steps)][args.warmup:]
+        line.update(impl='reference', value=n * len(ms) / (sum(ms) / 1e3), ms_per_step=sum(ms) / len(ms),
+                    e2e={'value': n * len(ms) / (sum(ms) / 1e3), 'unit': 'rays/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+                    cpu_baseline={'value': n * len(ms) / (sum(ms) / 1e3), 'unit': 'rays/s', 'cores': 1, 'kind': 'reference',
+                                  'sample': 'reference intersect_mesh (oracle/_ref/ref_wrap.cubin) on one B200, 64-thread blocks'})
+        emit(line)
+        return
+    g = gpu.GPUGeometry(geo)
+    do, dd = ga.to_gpu(to_float3(o)), ga.to_gpu(to_float3(d))
+    for _ in range(args.warmup):
+        gpu.intersect_mesh(g, do, dd)
+    ms = []
+    for _ in range(args.steps):
+        lib.cb_flush_l2()
+        _lib.check(lib.cb_synchronize())
+        _lib.check(lib.cb_timer_start())
+        tri, dist = gpu.intersect_mesh(g, do, dd)
+        t = _lib.C.c_float()
+        _lib.check(lib.cb_timer_stop(_lib.C.byref(t)))
+        ms.append(t.value)
+    # e2e: host arrays in (page-locked), triangle + distance back on the host
+    po, pd = gpu.pagelocked_copy(o), gpu.pagelocked_copy(d)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        tri, dist = gpu.intersect_mesh(g, po, pd)
+        ht, hd = tri.get(), dist.get()
+    e2e_s = time.perf_counter() - t0
+    line.update(value=n * len(ms) / (sum(ms) / 1e3), ms_per_step=sum(ms) / len(ms), gpu_launches=args.steps,
+                e2e={'value': n * args.steps / e2e_s, 'unit': 'rays/s', 'h2d_bytes_per_step': int(o.nbytes + d.nbytes),
+                     'd2h_bytes_per_step': int(ht.nbytes + hd.nbytes)},
+                extra={'hit_fraction': float((ht >= 0).mean())})
+    emit(line)
+
+
 # ------------------------------------------------------------------ reference arm
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
@@ -466,7 +551,9 @@ def main():
     ap.add_argument('--cpu-sample', type=int, default=40000)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
-    if args.impl == 'reference':
+    if args.workload == 'rays':
+        run_rays(args)
+    elif args.impl == 'reference':
         run_reference(args)
     else:
         run_ours(args)

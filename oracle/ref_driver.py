@@ -451,6 +451,31 @@ def run_daq(geom, photons, rng, nthreads_per_block=64, max_blocks=1024, start_ph
     return from_dev(tf), from_dev(qf), from_dev(hist), from_dev(tint), from_dev(qint)
 
 
+def run_daq_many(geom, photons, rng, ndaq, nthreads_per_block=64, max_blocks=1024, start_photon=0, nphotons=None,
+                 weight=1.0):
+    """GPUDaq(ndaq > 1): begin_acquire / acquire with run_daq_many, one block per photon
+    (gpu/daq.py:55-59, 80-101).  Returns (t, q, flags) of ndaq * nchannels entries."""
+    mod = module('daq.cubin')
+    nch = geom.nchannels
+    count = nch * ndaq
+    nphotons = photons.n - start_photon if nphotons is None else nphotons
+    tint = to_dev(np.zeros(count, dtype=np.uint32))
+    qint = to_dev(np.zeros(count, dtype=np.uint32))
+    hist = to_dev(np.zeros(count, dtype=np.uint32))
+    tf = to_dev(np.zeros(count, dtype=np.float32))
+    qf = to_dev(np.zeros(count, dtype=np.float32))
+    mod.launch('reset_earliest_time_int', count // 64 + 1, 64, C.c_float(1e9), C.c_int(count), tint)
+    for first, n, blocks in chunk_iterator(nphotons, 1, max_blocks):
+        mod.launch('run_daq_many', blocks, nthreads_per_block, rng.mem, C.c_uint(0x4), C.c_int(start_photon + first),
+                   C.c_int(n), photons.t, photons.flags, photons.last_hit_triangles, photons.weights, geom.solid_id,
+                   geom.detector_gpu, tint, qint, hist, C.c_int(ndaq), C.c_int(nch), C.c_float(weight))
+    mod.launch('convert_sortable_int_to_float', count // 64 + 1, 64, C.c_int(count), tint, tf)
+    # convert_charge_int_to_float covers nchannels entries per launch (daq.cu:163-173): one call per copy
+    sync()
+    q = from_dev(qint).astype(np.float32)
+    return from_dev(tf), q, from_dev(hist), from_dev(tint), from_dev(qint)
+
+
 def make_leaves(vertices, triangles, world_origin, world_scale):
     """The reference's make_leaves kernel (chroma/cuda/bvh.cu:148-203, launched as
     in chroma/gpu/bvh.py:66-78).  Returns (leaf_nodes uint32 (T,4), morton uint64 (T,))."""

@@ -105,6 +105,40 @@ def test_daq_vs_reference_kernel_and_oracle(gpu_ready):
     assert np.allclose(tint.view(np.float32), ch.t, rtol=1e-6)
 
 
+def test_daq_many_vs_reference_kernel(gpu_ready):
+    # ndaq > 1: run_daq_many, one block per photon, threads striding over the virtual DAQ copies,
+    # curand_normal (Box-Muller with its cached second value) in the time smearing (daq.cu:88-150)
+    geo = scenes.tiny_detector()
+    g, gp, _ = propagated_bank(geo, n=60000)
+    host = gp.get()
+    n = len(host)
+    ndaq, tpb, max_blocks = 6, 64, 1024
+    pool = tpb * max_blocks
+    rng = gpu.get_rng_states(pool, seed=11)
+    daq = gpu.GPUDaq(g, ndaq=ndaq)
+    daq.begin_acquire()
+    daq.acquire(gp, rng, nthreads_per_block=tpb, max_blocks=max_blocks, weight=0.8)
+    chans = daq.end_acquire()
+    desc, keep = scenes.desc_of(geo)
+    rg = ref_driver.RefGeometry(desc, keep)
+    rg.attach_detector(geo)
+    rrng = ref_driver.RefRNG(pool, seed=11)
+    rt, rq, rh, rti, rqi = ref_driver.run_daq_many(rg, ref_driver.RefPhotons(host), rrng, ndaq, nthreads_per_block=tpb,
+                                                    max_blocks=max_blocks, weight=0.8)
+    assert np.array_equal(daq.channel_history_gpu.get(), rh)
+    assert np.array_equal(daq.channel_q_int_gpu.get(), rqi)
+    assert np.array_equal(daq.earliest_time_int_gpu.get(), rti)
+    assert np.array_equal(daq.earliest_time_gpu.get(), rt)
+    assert (rti != np.float32(1e9).view(np.uint32)).sum() > 10 * ndaq          # every copy saw hits
+    # the copies are independent draws: they differ from each other
+    t = daq.earliest_time_gpu.get().reshape(ndaq, -1)
+    assert not np.array_equal(t[0], t[1])
+    # RNG pool advanced identically (incl. the lanes that never drew)
+    assert np.array_equal(rng.get(), rrng.states6())
+    copies = list(chans.iterate_copies())
+    assert len(copies) == ndaq
+
+
 def test_daq_time_and_charge_response(gpu_ready):
     # test/test_detector.py: time spread and charge mean/rms of single photoelectrons
     from chroma_lite_b200.detector import Detector
