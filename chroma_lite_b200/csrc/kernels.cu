@@ -226,6 +226,14 @@ struct PropParams {
     unsigned long long* counters;   // [1] nodes, [2] tris, [3] overflow, [4] steps, [5] resolved, [9..13] ray-length stats
 };
 
+// Queue entries: chunk-local photon index in the low 31 bits; bit 31 marks a photon that sits on
+// a surface (last_hit_triangle >= 0), which the tail kernel schedules first.
+constexpr uint32_t QUEUE_ON_SURFACE = 0x80000000u;
+__device__ __forceinline__ uint32_t queue_index(const PropParams& P, unsigned long long q)
+{
+    return P.queue_in ? (P.queue_in[q] & ~QUEUE_ON_SURFACE) : (uint32_t)q;
+}
+
 __device__ __forceinline__ void load_photon(const CbPhotonBank& b, uint64_t id, uint32_t hist, bool normalise, Photon& p)
 {
     p.pos = ld3(b.pos, id);
@@ -271,7 +279,7 @@ ray_key_kernel(DevGeometry g, PropParams P, uint32_t* __restrict__ keys, uint32_
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= *P.n_in) return;
-    const uint32_t k = P.queue_in ? P.queue_in[i] : i;
+    const uint32_t k = queue_index(P, i);
     const uint64_t id = P.first + k;
     const float3 pos = ld3(P.bank.pos, id);
     float3 d = ld3(P.bank.dir, id);
@@ -299,7 +307,7 @@ struct PhotonRaySource {     // one propagation step: rays of the photons in the
     const PropParams& P;
     __device__ __forceinline__ bool load(unsigned long long q, float3& o, float3& d, int& last) const
     {
-        const uint32_t k = P.queue_in ? P.queue_in[q] : (uint32_t)q;
+        const uint32_t k = queue_index(P, q);
         const uint64_t id = P.first + k;
         if (P.step == 0 && (P.bank.flags[id] & 0xFFFFu & CB_TERMINAL)) return false;   // never ran: untouched
         o = ld3(P.bank.pos, id);
@@ -310,7 +318,7 @@ struct PhotonRaySource {     // one propagation step: rays of the photons in the
     }
     __device__ __forceinline__ void store(unsigned long long q, int tri, float dist) const
     {
-        const uint32_t k = P.queue_in ? P.queue_in[q] : (uint32_t)q;
+        const uint32_t k = queue_index(P, q);
         P.hit_tri[k] = tri;
         P.hit_dist[k] = dist;
     }
@@ -327,8 +335,11 @@ step_intersect_kernel(const __grid_constant__ DevGeometry g, const __grid_consta
     persistent_intersect<COUNT>(g, src, n, P.cursor, (uint32_t)__cvta_generic_to_shared(smem_raw), P.counters, tune);
 }
 
+#ifndef CB_PHYS_BLOCKS
+#define CB_PHYS_BLOCKS 2
+#endif
 template <bool WIRES>
-__global__ void __launch_bounds__(PROP_THREADS, 2)
+__global__ void __launch_bounds__(PROP_THREADS, CB_PHYS_BLOCKS)
 step_physics_kernel(DevGeometry g, PropParams P)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -345,9 +356,9 @@ step_physics_kernel(DevGeometry g, PropParams P)
     const uint32_t n_round = (n_in + 31u) & ~31u;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
         bool alive = false;
-        uint32_t k = 0;
+        uint32_t k = 0, mark = 0;
         if (i < n_in) {
-            k = P.queue_in ? P.queue_in[i] : i;
+            k = queue_index(P, i);
             const uint64_t id = P.first + k;
             const uint32_t hist = P.bank.flags[id] & 0xFFFFu;
             if (!(P.step == 0 && (hist & CB_TERMINAL))) {
@@ -363,6 +374,7 @@ step_physics_kernel(DevGeometry g, PropParams P)
                 rng_store(P.rng, k, rng);
                 store_photon(P.bank, id, p);
                 alive = alive && !last_step;
+                mark = (p.last_hit_triangle >= 0) ? QUEUE_ON_SURFACE : 0u;
             }
         }
         const unsigned m = __ballot_sync(0xffffffffu, alive);
@@ -370,7 +382,7 @@ step_physics_kernel(DevGeometry g, PropParams P)
             unsigned long long base = 0;
             if (lane == 0) base = atomicAdd(P.n_out, (unsigned long long)__popc(m));
             base = __shfl_sync(0xffffffffu, base, 0);
-            if (alive) P.queue_out[base + __popc(m & ((1u << lane) - 1u))] = k;
+            if (alive) P.queue_out[base + __popc(m & ((1u << lane) - 1u))] = k | mark;
         }
     }
 }
@@ -401,12 +413,21 @@ propagate_tail_kernel(DevGeometry g, PropParams P)
     TraverseCounters cnt = {0, 0, 0};
     unsigned long long nsteps_total = 0;
 
+    // The queue is walked twice: photons sitting on a surface first, photons in the bulk second.
+    // Scheduling only (every photon is taken exactly once, results do not depend on it): the rare
+    // 50-step histories that end a propagate call are almost all photons rattling between
+    // surfaces (90 % of those alive after 25 steps were on a surface when the tail began, against
+    // 38 % of all its photons), and started early they finish under the cover of the bulk.
     for (;;) {
         unsigned long long q = 0;
         if (lane == 0) q = atomicAdd(P.cursor, 1ull);
         q = __shfl_sync(0xffffffffu, q, 0);
-        if (q >= n_in) break;
-        const uint32_t k = P.queue_in ? P.queue_in[q] : (uint32_t)q;
+        if (q >= 2 * n_in) break;
+        const bool first_pass = q < n_in;
+        if (!first_pass) q -= n_in;
+        const uint32_t entry = P.queue_in ? P.queue_in[q] : ((uint32_t)q | QUEUE_ON_SURFACE);
+        if (((entry & QUEUE_ON_SURFACE) != 0) != first_pass) continue;
+        const uint32_t k = entry & ~QUEUE_ON_SURFACE;
         const uint64_t id = P.first + k;
         const uint32_t hist = P.bank.flags[id] & 0xFFFFu;
         if (P.step == 0 && (hist & CB_TERMINAL)) continue;
@@ -803,7 +824,7 @@ int cb_propagate(const CbPhotonBank* bank, cb_geom_t gh, cb_rng_t rh, int32_t nt
     if (nthreads_per_block <= 0 || max_blocks <= 0) return fail(CB_ERR_INVALID, "cb_propagate: bad launch parameters");
     const uint64_t pool = std::min<uint64_t>((uint64_t)nthreads_per_block * (uint64_t)max_blocks, r->n);
     if (pool == 0) return fail(CB_ERR_INVALID, "cb_propagate: empty rng pool");
-    if (pool >= (1ull << 32)) return fail(CB_ERR_INVALID, "cb_propagate: rng pool too large");
+    if (pool >= (1ull << 31)) return fail(CB_ERR_INVALID, "cb_propagate: rng pool too large");
     if (stats) { memset(stats, 0, sizeof(*stats)); }
     if (bank->n == 0 || max_steps <= 0) return CB_OK;
     Context& c = ctx();
