@@ -293,7 +293,7 @@ def run_ours(args):
     # the event's host arrays live in page-locked memory (gpu.pagelocked_empty, the role of
     # pycuda's pagelocked_empty in the reference): every step uploads them again, host -> device
     ev = gpu.pin_photons(ev)
-    list(s.simulate((event.Event(photons_beg=ev) for _ in range(2)), **sim_kw))
+    list(s.simulate((event.Event(photons_beg=ev) for _ in range(max(4, args.warmup))), **sim_kw))   # warm-up: 3 batches in flight
     nch = s.gpu_geometry.nchannels
     barrier(world)
     _lib.check(lib.cb_synchronize())

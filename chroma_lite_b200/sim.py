@@ -58,32 +58,51 @@ class Simulation(object):
         gpu_photons = gpu.GPUPhotons(batch, copy_flags=True, copy_triangles=False, copy_weights=False)
         return gpu_photons, bounds, time.perf_counter() - t0
 
-    def _simulate_batch(self, batch_events, keep_photons_beg=False, keep_photons_end=False, keep_hits=True,
-                        keep_flat_hits=True, run_daq=False, max_steps=100, verbose=False, uploaded=None):
+    def _gpu_stage(self, batch_events, uploaded=None, keep_photons_end=False, keep_hits=True, keep_flat_hits=True,
+                   run_daq=False, max_steps=100, verbose=False, **_unused):
+        """Everything of one batch that needs the GPU, in the reference's order (chroma/sim.py:82-152):
+        propagate, photons_end / flat-hit read-back, then one DAQ acquisition per event.  Returns the
+        raw host arrays; building the Event objects from them (_host_stage) needs no GPU and overlaps
+        with the next batch's GPU stage."""
         t0 = time.perf_counter()
         gpu_photons, bounds, upload_s = uploaded if uploaded is not None else self._upload_batch(batch_events)
         t1 = time.perf_counter()
-        tracking = gpu_photons.propagate(self.gpu_geometry, self.rng_states,
-                                         nthreads_per_block=self.nthreads_per_block, max_blocks=self.max_blocks,
-                                         max_steps=max_steps, track=self.photon_tracking)
+        raw = {'bounds': bounds}
+        raw['tracking'] = gpu_photons.propagate(self.gpu_geometry, self.rng_states,
+                                                nthreads_per_block=self.nthreads_per_block, max_blocks=self.max_blocks,
+                                                max_steps=max_steps, track=self.photon_tracking)
         t2 = time.perf_counter()
         is_detector = hasattr(self.detector, 'num_channels')
         if keep_photons_end:
-            batch_photons_end = gpu_photons.get()
+            raw['photons_end'] = gpu_photons.get()
         if is_detector and (keep_hits or keep_flat_hits):
-            batch_hits = gpu_photons.get_flat_hits(self.gpu_geometry)
+            raw['hits'] = gpu_photons.get_flat_hits(self.gpu_geometry)
         t3 = time.perf_counter()
-        self.last_timings = {'upload_s': upload_s, 'propagate_s': t2 - t1, 'readback_s': t3 - t2,
-                             'nphotons': int(bounds[-1])}
+        if hasattr(self, 'gpu_daq') and run_daq:
+            # one acquisition per event (chroma/sim.py:141-152)
+            raw['channels'] = []
+            for start, end in zip(bounds[:-1], bounds[1:]):
+                self.gpu_daq.begin_acquire()
+                self.gpu_daq.acquire(gpu_photons, self.rng_states, start_photon=int(start),
+                                     nphotons=int(end - start), nthreads_per_block=self.nthreads_per_block,
+                                     max_blocks=self.max_blocks)
+                raw['channels'].append(self.gpu_daq.end_acquire().get())
+        t4 = time.perf_counter()
+        self.last_timings = {'upload_s': upload_s, 'propagate_s': t2 - t1, 'readback_s': t3 - t2, 'daq_s': t4 - t3,
+                             'nphotons': int(bounds[-1]), 'batch_total_s': t4 - t0}
         if verbose:
             print('GPU copy took %0.2f s, propagate %0.2f s' % (t1 - t0, t2 - t1))
+        return raw
 
-        t_daq = 0.0
+    def _host_stage(self, batch_events, raw, keep_photons_beg=False, keep_photons_end=False, keep_hits=True,
+                    keep_flat_hits=True, **_unused):
+        """Slice the batch results back into the events (chroma/sim.py:112-154); host only."""
+        bounds = raw['bounds']
         for i, (ev, start, end) in enumerate(zip(batch_events, bounds[:-1], bounds[1:])):
             if not keep_photons_beg:
                 ev.photons_beg = None
             if self.photon_tracking:
-                step_ids, step_photons = tracking
+                step_ids, step_photons = raw['tracking']
                 tracks = [[] for _ in range(end - start)]
                 for ids, photons in zip(step_ids, step_photons):
                     mask = np.logical_and(ids >= start, ids < end)
@@ -94,26 +113,22 @@ class Simulation(object):
                         tracks[pid].append(sel[j])
                 ev.photon_tracks = [event.Photons.join(t, concatenate=False) if len(t) > 0 else event.Photons()
                                     for t in tracks]
-            if keep_photons_end:
-                ev.photons_end = batch_photons_end[start:end]
-            if is_detector and (keep_hits or keep_flat_hits):
-                ev_hits = batch_hits[batch_hits.evidx == i]
+            if keep_photons_end and 'photons_end' in raw:
+                ev.photons_end = raw['photons_end'][start:end]
+            if 'hits' in raw:
+                batch_hits = raw['hits']
+                ev_hits = batch_hits if len(batch_events) == 1 else batch_hits[batch_hits.evidx == i]
                 if keep_hits:
                     ev.hits = {int(c): ev_hits[ev_hits.channel == c] for c in np.unique(ev_hits.channel)}
                 if keep_flat_hits:
                     ev.flat_hits = ev_hits
-            if hasattr(self, 'gpu_daq') and run_daq:
-                # one acquisition per event (chroma/sim.py:141-152)
-                td = time.perf_counter()
-                self.gpu_daq.begin_acquire()
-                self.gpu_daq.acquire(gpu_photons, self.rng_states, start_photon=int(start),
-                                     nphotons=int(end - start), nthreads_per_block=self.nthreads_per_block,
-                                     max_blocks=self.max_blocks)
-                ev.channels = self.gpu_daq.end_acquire().get()
-                t_daq += time.perf_counter() - td
-            self.last_timings['daq_s'] = t_daq
-            self.last_timings['batch_total_s'] = time.perf_counter() - t0
+            if 'channels' in raw:
+                ev.channels = raw['channels'][i]
             yield ev
+
+    def _simulate_batch(self, batch_events, uploaded=None, **kw):
+        raw = self._gpu_stage(batch_events, uploaded=uploaded, **kw)
+        yield from self._host_stage(batch_events, raw, **kw)
 
     def simulate(self, iterable, keep_photons_beg=False, keep_photons_end=False, keep_hits=True,
                  keep_flat_hits=True, run_daq=False, max_steps=1000, photons_per_batch=1000000):
@@ -150,24 +165,54 @@ class Simulation(object):
             if batch:
                 yield batch
 
-        # Double-buffered pipeline: while batch k propagates (the C call releases the
-        # GIL), a worker thread uploads batch k+1 on the copy stream.  The reference
-        # does upload -> propagate -> download strictly in sequence (sim.py:79-110).
-        import concurrent.futures
+        # Three-stage pipeline, one batch per stage: a worker thread uploads batch k+1 on its copy
+        # stream, a second one runs the GPU stage of batch k (propagate, hit read-back, DAQ; the C
+        # calls release the GIL), and this thread turns the raw arrays of batch k-1 into events.
+        # GPU stages run strictly one after the other, so the RNG pool is consumed in the reference's
+        # order (propagate k, DAQ k, propagate k+1, ...).  The reference does upload -> propagate ->
+        # download strictly in sequence (sim.py:79-110).
         it = batches()
-        nxt = next(it, None)
-        if nxt is None:
+        cur = next(it, None)
+        if cur is None:
             return
-        with concurrent.futures.ThreadPoolExecutor(max_workers=1) as pool:
-            pending = pool.submit(self._upload_batch, nxt)
-            while nxt is not None:
-                cur, uploaded = nxt, pending.result()
+        up_pool, gpu_pool = self._workers()
+        up_pending = up_pool.submit(self._upload_batch, cur)
+        prev = None                               # (batch, future of its raw results)
+        try:
+            while cur is not None:
+                uploaded = up_pending.result()
+                gpu_pending = gpu_pool.submit(self._gpu_stage, cur, uploaded, **kw)
                 nxt = next(it, None)
-                if nxt is not None:
-                    pending = pool.submit(self._upload_batch, nxt)
-                yield from self._simulate_batch(cur, uploaded=uploaded, **kw)
+                up_pending = up_pool.submit(self._upload_batch, nxt) if nxt is not None else None
+                if prev is not None:
+                    yield from self._host_stage(prev[0], prev[1].result(), **kw)
+                prev = (cur, gpu_pending)
+                cur = nxt
+            yield from self._host_stage(prev[0], prev[1].result(), **kw)
+        finally:
+            # a consumer that stops early must not leave work behind that still uses the RNG pool
+            for f in (up_pending, prev[1] if prev else None):
+                if f is not None:
+                    try:
+                        f.result()
+                    except Exception:
+                        pass
+
+    def _workers(self):
+        """The two pipeline threads live as long as the Simulation (their CUDA per-thread state --
+        device binding, copy stream -- is set up once, not per simulate() call)."""
+        if getattr(self, '_pools', None) is None:
+            import concurrent.futures
+            self._pools = (concurrent.futures.ThreadPoolExecutor(max_workers=1, thread_name_prefix='cb-upload-stage'),
+                           concurrent.futures.ThreadPoolExecutor(max_workers=1, thread_name_prefix='cb-gpu-stage'))
+        return self._pools
 
     def __del__(self):
+        try:
+            for p in (getattr(self, '_pools', None) or ()):
+                p.shutdown(wait=False)
+        except Exception:
+            pass
         try:
             self.context.pop()
         except Exception:
