@@ -551,7 +551,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='pmt29k')
     ap.add_argument('--photons', type=int, default=2500000)
-    ap.add_argument('--cpu-sample', type=int, default=40000)
+    ap.add_argument('--cpu-sample', type=int, default=1000000)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
     if args.workload == 'rays':

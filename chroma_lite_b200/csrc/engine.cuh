@@ -589,16 +589,20 @@ __device__ __forceinline__ int warp_traverse(const DevGeometry& g, const float3&
                     }
                 }
             }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const float t2 = __shfl_xor_sync(0xffffffffu, t, o);
-                const uint32_t r2 = __shfl_xor_sync(0xffffffffu, rank, o);
-                const int tri2 = __shfl_xor_sync(0xffffffffu, tri, o);
-                if (t2 < t || (t2 == t && r2 < rank)) { t = t2; rank = r2; tri = tri2; }
-            }
-            if (tri != -1 && (t < best_t || (t == best_t && rank < best_rank))) {
-                best_t = t; best_tri = tri; best_rank = rank;
-                limit = best_t + 2e-5f * best_t;
+            // nearest hit of the batch, ties by reference rank: two REDUX.MIN (a hit distance is
+            // positive, so its bit pattern orders like the float) + one ballot instead of a
+            // five-level shuffle tree on (t, rank, tri)
+            const uint32_t tmin_bits = __reduce_min_sync(0xffffffffu, __float_as_uint(t));
+            if (tmin_bits != 0x7f800000u) {
+                const bool cand = __float_as_uint(t) == tmin_bits;
+                const uint32_t rmin = __reduce_min_sync(0xffffffffu, cand ? rank : 0xFFFFFFFFu);
+                const int src = __ffs(__ballot_sync(0xffffffffu, cand && rank == rmin)) - 1;
+                const int wtri = __shfl_sync(0xffffffffu, tri, src);
+                const float wt = __uint_as_float(tmin_bits);
+                if (wt < best_t || (wt == best_t && rmin < best_rank)) {
+                    best_t = wt; best_tri = wtri; best_rank = rmin;
+                    limit = best_t + 2e-5f * best_t;
+                }
             }
             __syncwarp();
             continue;

@@ -454,6 +454,13 @@ propagate_tail_kernel(DevGeometry g, PropParams P)
         if (lane == 0) {
             rng_store(P.rng, k, rng);
             store_photon(P.bank, id, p);
+#ifdef CB_TAIL_PROFILE
+            // debug build only: steps taken here and finish time (x 64 ns, global timer) per photon
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            P.hit_tri[k] = steps - P.step;
+            reinterpret_cast<uint32_t*>(P.hit_dist)[k] = (uint32_t)(now >> 6);
+#endif
         }
     }
     if (lane == 0 && nsteps_total) atomicAdd(P.counters + 4, nsteps_total);
@@ -967,6 +974,38 @@ int cb_propagate(const CbPhotonBank* bank, cb_geom_t gh, cb_rng_t rh, int32_t nt
                         fprintf(stderr, "[cb trace] step %d tail: %llu photons %.3f ms\n", step, (unsigned long long)n_alive, ms);
                     }
                     launches++;
+#ifdef CB_TAIL_PROFILE
+                    if (!wave && P.queue_in) {
+                        // debug build only: when did the tail's photons finish, and after how many steps?
+                        cudaStreamSynchronize(c.stream);
+                        std::vector<uint32_t> q(n_alive), st(cap), tm(cap);
+                        cudaMemcpy(q.data(), P.queue_in, n_alive * 4, cudaMemcpyDeviceToHost);
+                        cudaMemcpy(st.data(), c.d_hit_tri, cap * 4, cudaMemcpyDeviceToHost);
+                        cudaMemcpy(tm.data(), c.d_hit_dist, cap * 4, cudaMemcpyDeviceToHost);
+                        std::vector<std::pair<uint32_t, uint32_t>> v;       // (finish time, steps)
+                        uint32_t t0 = ~0u;
+                        for (uint64_t i = 0; i < n_alive; i++) { uint32_t k = q[i] & 0x7fffffffu; t0 = std::min(t0, tm[k]); }
+                        for (uint64_t i = 0; i < n_alive; i++) { uint32_t k = q[i] & 0x7fffffffu; v.push_back({tm[k] - t0, st[k]}); }
+                        std::sort(v.begin(), v.end());
+                        fprintf(stderr, "[tail profile] %llu photons; finish-time percentiles (us):", (unsigned long long)n_alive);
+                        for (double f : {0.5, 0.9, 0.99, 0.999, 0.9999, 1.0})
+                            fprintf(stderr, " p%g=%.0f", f * 100, v[std::min<size_t>(v.size() - 1, (size_t)(f * v.size()))].first * 0.064);
+                        fprintf(stderr, "\n[tail profile] last 12 finishers (us, steps):");
+                        for (size_t i = v.size() >= 12 ? v.size() - 12 : 0; i < v.size(); i++) fprintf(stderr, " (%.0f,%u)", v[i].first * 0.064, v[i].second);
+                        unsigned long long hist[8] = {0}; unsigned long long stepsum = 0;
+                        for (auto& x : v) { stepsum += x.second; int b = x.second <= 1 ? 0 : x.second <= 2 ? 1 : x.second <= 4 ? 2 : x.second <= 8 ? 3 : x.second <= 16 ? 4 : x.second <= 32 ? 5 : x.second <= 64 ? 6 : 7; hist[b]++; }
+                        fprintf(stderr, "\n[tail profile] steps histogram (<=1,2,4,8,16,32,64,more):");
+                        for (int b = 0; b < 8; b++) fprintf(stderr, " %llu", hist[b]);
+                        fprintf(stderr, "  total steps %llu\n", stepsum);
+                        // photons alive (still being worked on or not yet started) at a few times
+                        fprintf(stderr, "[tail profile] unfinished at (us):");
+                        for (double us : {250.0, 500.0, 750.0, 1000.0, 1250.0, 1500.0, 1750.0, 2000.0, 2250.0}) {
+                            size_t lo = std::lower_bound(v.begin(), v.end(), std::make_pair((uint32_t)(us / 0.064), 0u)) - v.begin();
+                            fprintf(stderr, " %g:%zu", us, v.size() - lo);
+                        }
+                        fprintf(stderr, "\n");
+                    }
+#endif
                     if (!wave) { n_alive = 0; step++; break; }       // the tail ran for certain: done
                 }
                 exact = false;
