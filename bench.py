@@ -56,14 +56,37 @@ def emit(obj):
 
 # ------------------------------------------------------------------ clocks
 class ClockSampler(object):
+    """SM clock and throttle reasons sampled DURING the timed regions.  NVML in a thread
+    (2 ms period; the timed region of the default run is only ~40 ms, shorter than an
+    nvidia-smi process takes to start), nvidia-smi -lms as the fallback."""
     Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
          'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
          'clocks_event_reasons.sw_power_cap')
 
     def __init__(self, index=0):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.nvml = index, [], None, None
+        self.sm, self.reasons, self.sm_max = [], set(), None
+        self._stop = threading.Event()
+        self._on = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES when it is a plain index list
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES', '')
+            ids = [int(x) for x in vis.split(',')] if vis and all(x.strip().isdigit() for x in vis.split(',')) else None
+            phys = ids[index] if ids and index < len(ids) else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
 
     def start(self):
+        """Start the sampling thread (idle until resume())."""
+        if self.nvml is not None:
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
                                           '--format=csv,noheader,nounits', '-lms', '100'],
@@ -73,11 +96,42 @@ class ClockSampler(object):
         except Exception:
             self.proc = None
 
+    def resume(self):
+        self._on.set()
+
+    def pause(self):
+        self._on.clear()
+
+    def _poll(self):
+        nv = self.nvml
+        names = ((nv.nvmlClocksThrottleReasonHwSlowdown, 'hw_slowdown'),
+                 (nv.nvmlClocksThrottleReasonHwThermalSlowdown, 'hw_thermal_slowdown'),
+                 (nv.nvmlClocksThrottleReasonSwThermalSlowdown, 'sw_thermal_slowdown'),
+                 (nv.nvmlClocksThrottleReasonSwPowerCap, 'sw_power_cap'))
+        while not self._stop.is_set():
+            if not self._on.wait(0.05):
+                continue
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                for bit, name in names:
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(',')])
+            if self._on.is_set():
+                self.rows.append([x.strip() for x in line.split(',')])
 
     def stop(self):
+        self._stop.set()
+        if self.nvml is not None:
+            self.thread.join(timeout=1.0)
+            return {'sm_mhz': float(np.median(self.sm)) if self.sm else None, 'sm_max_mhz': self.sm_max,
+                    'reasons': sorted(self.reasons), 'samples': len(self.sm), 'source': 'nvml, 2 ms period, timed regions only'}
         if self.proc is None:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
         time.sleep(0.15)
@@ -88,7 +142,7 @@ class ClockSampler(object):
         names = ('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap')
         reasons = sorted({n for r in rows for n, v in zip(names, r[3:7]) if v.lower().startswith('active')})
         return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
-                'reasons': reasons, 'samples': len(rows)}
+                'reasons': reasons, 'samples': len(rows), 'source': 'nvidia-smi -lms 100'}
 
 
 # ------------------------------------------------------------------ workload
@@ -255,13 +309,14 @@ def run_ours(args):
         gp.propagate(g, rng, nthreads_per_block=512, max_blocks=s.max_blocks, max_steps=MAX_STEPS)
         return gp.last_stats
 
-    for _ in range(args.warmup):
-        one_step()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        one_step()
     barrier(world)
     _lib.check(lib.cb_synchronize())
+    sampler.resume()
     kernel_ms, launches, steps_taken = 0.0, 0, 0
     nodes_v, tris_v, resolved = 0, 0, 0
     int0_ms, int0_rays, int0_n = 0.0, 0, 0
@@ -281,7 +336,7 @@ def run_ours(args):
     _lib.check(lib.cb_synchronize())
     barrier(world)
     wall = time.perf_counter() - t0
-    clocks = sampler.stop() if rank == 0 else None
+    sampler.pause()
     # device time of the propagate kernels (CUDA events on the launching stream), max over ranks
     dev_s = max_over_ranks(kernel_ms / 1e3, world)
     total_photons = sum_over_ranks(float(n * args.steps), world)
@@ -300,6 +355,7 @@ def run_ours(args):
     nch = s.gpu_geometry.nchannels
     barrier(world)
     _lib.check(lib.cb_synchronize())
+    sampler.resume()
     t0 = time.perf_counter()
     hit_count = np.zeros(nch, dtype=np.int64)
     charge = np.zeros(nch, dtype=np.float64)
@@ -317,6 +373,7 @@ def run_ours(args):
     _lib.check(lib.cb_synchronize())
     barrier(world)
     e2e_s = max_over_ranks(time.perf_counter() - t0, world)
+    clocks = sampler.stop() if rank == 0 else None
     e2e = total_photons / e2e_s
     timings['e2e_last_batch'] = dict(s.last_timings)
     timings['e2e_s_per_event'] = e2e_s / args.steps
@@ -501,9 +558,10 @@ def run_reference(args):
         ch = ref_driver.run_daq(rg, rp, rng, nthreads_per_block=512, max_blocks=1024)
         return rp, r, hits, ch
 
+    sampler.start()
     for _ in range(args.warmup):
         one_step()
-    sampler.start()
+    sampler.resume()
     ms, launches = 0.0, 0
     t_e2e = 0.0
     for _ in range(args.steps):

@@ -632,12 +632,14 @@ __device__ __forceinline__ int warp_traverse(const DevGeometry& g, const float3&
         nleaf += __popc(lm);
         const int ni = __popc(im);
         if (sp + ni > CB_WSTACK) { redo = true; break; }
-        // push the internal hits far -> near, so that the nearest ends up on top
+        // push the internal hits far -> near, so that the nearest ends up on top: selection sort
+        // with one REDUX.MIN + ballot per hit (tmin >= 0, so its bit pattern orders like the float)
         int pos = 0;
-        for (unsigned mm = im; mm; mm &= mm - 1) {
-            const int j = __ffs(mm) - 1;
-            const float tj = __shfl_sync(0xffffffffu, tmin, j);
-            pos += (tj > tmin) || (tj == tmin && j < (int)lane);
+        uint32_t key = is_int ? __float_as_uint(tmin) : 0xFFFFFFFFu;
+        for (int r = ni - 1; r >= 0; r--) {
+            const uint32_t kmin = __reduce_min_sync(0xffffffffu, key);
+            const int leader = __ffs(__ballot_sync(0xffffffffu, key == kmin)) - 1;
+            if ((int)lane == leader) { pos = r; key = 0xFFFFFFFFu; }
         }
         if (is_int) wstack[sp + pos] = make_uint2(w, __float_as_uint(tmin));
         sp += ni;

@@ -74,7 +74,17 @@ struct RaySource {           // cb_intersect: free rays, direction normalised li
 // load sequence and waits for memory once per iteration.  Finished rays wait until
 // `refill_min` lanes are free and are then finished (winner re-check + store) and
 // replaced together with one atomic on the queue cursor.
-struct Tune { int refill_min; };
+//
+// End game (ray splitting).  Once the queue is exhausted a launch used to end with a
+// few lanes per warp walking the longest rays alone (up to ~460 iterations where the
+// mean is 40; 0.6-0.7 ms, which was the whole duration of a step with few rays).  Now
+// a lane that has run dry takes the top stack entry of a busy lane of its warp
+// together with a copy of that ray's state, traverses that subtree as a HELPER and
+// hands its best (distance, rank) back to the ray's owner lane, which stores the
+// result once all its helpers are back.  Any visit order returns the same triangle
+// (see PTrav), helpers start from the donor's culling limit, and the merge is the
+// same lexicographic minimum, so results are unchanged bit for bit.
+struct Tune { int refill_min; int split; };
 #ifndef CB_INT_BLOCKS
 #define CB_INT_BLOCKS 5     /* resident CTAs per SM of the traversal kernels: 5 x 128 threads at 96 registers */
 #endif
@@ -94,11 +104,35 @@ __device__ __forceinline__ void persistent_intersect(const DevGeometry& g, const
     uint2 lstack[CB_PLSTACK];               // overflow of the shared-memory stack (local memory, rarely touched)
     tv.have = false; tv.sp = sbase; tv.lq = lbase; tv.lsp = 0;
     bool active = false, exhausted = false;
+    int owner = (int)lane;                  // lane that owns the ray this lane works on (itself unless it is a helper)
+    int pending = 0;                        // owner: helpers still out
     unsigned long long slot = 0;
     unsigned ray_iters = 0;                 // iterations spent on the current ray (statistics only)
     TraverseCounters cnt = {0, 0, 0};
     for (;;) {
-        const bool done = active && !tv.have && tv.lq == lbase;
+        if (exhausted && tune.split) {
+            // helpers that have finished their share report to the owner and become free
+            unsigned hm = __ballot_sync(FULL, active && owner != (int)lane && !tv.have && tv.lq == lbase);
+            while (hm) {
+                const int h = __ffs(hm) - 1;
+                hm &= hm - 1;
+                const float ht = __shfl_sync(FULL, tv.best_t, h);
+                const uint32_t hr = __shfl_sync(FULL, tv.best_rank, h);
+                const int htri = __shfl_sync(FULL, tv.best_tri, h);
+                const int hredo = __shfl_sync(FULL, (int)tv.redo, h);
+                const int ho = __shfl_sync(FULL, owner, h);
+                if ((int)lane == ho) {
+                    if (htri != -1 && (ht < tv.best_t || (ht == tv.best_t && hr < tv.best_rank))) {
+                        tv.best_t = ht; tv.best_rank = hr; tv.best_tri = htri;
+                        tv.limit = ht + 2e-5f * ht;
+                    }
+                    tv.redo = tv.redo || (hredo != 0);
+                    pending--;
+                }
+                if ((int)lane == h) { active = false; owner = (int)lane; }
+            }
+        }
+        const bool done = active && !tv.have && tv.lq == lbase && owner == (int)lane && pending == 0;
         const unsigned dm = __ballot_sync(FULL, done);
         const unsigned fm = dm | __ballot_sync(FULL, !active);
         const int nfree = __popc(fm);
@@ -140,6 +174,58 @@ __device__ __forceinline__ void persistent_intersect(const DevGeometry& g, const
         if (!__any_sync(FULL, active)) {
             if (exhausted) break;
             continue;
+        }
+        if (exhausted && tune.split) {
+            // free lanes take the top stack entry of busy lanes (k-th free lane from the k-th busy one)
+            const bool can_give = active && tv.have && tv.sp > sbase;
+            const unsigned idle_m = __ballot_sync(FULL, !active);
+            const unsigned donor_m = __ballot_sync(FULL, can_give);
+            const int np = min(__popc(idle_m), __popc(donor_m));
+            if (np > 0) {
+                __syncwarp();
+                const bool giving = can_give && __popc(donor_m & lt_mask) < np;
+                const bool taking = !active && __popc(idle_m & lt_mask) < np;
+                uint2 e = make_uint2(0u, 0u);
+if (giving) { tv.sp -= CB_PSTRIDE; e = lds64(tv.sp); }
+                const int src = taking ? (int)__fns(donor_m, 0, __popc(idle_m & lt_mask) + 1) : (int)lane;
+                const uint32_t ex = __shfl_sync(FULL, e.x, src);
+                const float et = __uint_as_float(__shfl_sync(FULL, e.y, src));
+                PhasedRay r2;
+                r2.sx = __shfl_sync(FULL, tv.r.sx, src); r2.sy = __shfl_sync(FULL, tv.r.sy, src); r2.sz = __shfl_sync(FULL, tv.r.sz, src);
+                r2.nx = __shfl_sync(FULL, tv.r.nx, src); r2.ny = __shfl_sync(FULL, tv.r.ny, src); r2.nz = __shfl_sync(FULL, tv.r.nz, src);
+                r2.fx = __shfl_sync(FULL, tv.r.fx, src); r2.fy = __shfl_sync(FULL, tv.r.fy, src); r2.fz = __shfl_sync(FULL, tv.r.fz, src);
+                r2.selx = __shfl_sync(FULL, tv.r.selx, src); r2.sely = __shfl_sync(FULL, tv.r.sely, src);
+                r2.selz = __shfl_sync(FULL, tv.r.selz, src);
+                const float bt = __shfl_sync(FULL, tv.best_t, src);
+                const uint32_t br = __shfl_sync(FULL, tv.best_rank, src);
+                const float lim = __shfl_sync(FULL, tv.limit, src);
+                const int lh = __shfl_sync(FULL, tv.last_hit, src);
+                const int own = __shfl_sync(FULL, owner, src);
+                const bool took = taking && !(et > lim);        // an entry behind the limit is simply dropped
+                if (took) {
+                    tv.r = r2;
+                    tv.best_t = bt; tv.best_rank = br; tv.best_tri = -1; tv.limit = lim; tv.last_hit = lh;
+                    tv.cur = ex; tv.cur_t = et; tv.have = true; tv.redo = false;
+                    tv.sp = sbase; tv.lq = lbase; tv.lsp = 0;
+                    // the ray itself (origin, direction) sits in three slots behind the donor's leaf queue
+                    const uint32_t cold_src = lbase + ((uint32_t)src - lane) * 8u + CB_PLEAF * CB_PSTRIDE;
+                    const uint32_t cold_dst = lbase + CB_PLEAF * CB_PSTRIDE;
+#pragma unroll
+                    for (int k = 0; k < CB_PCOLD; k++) {
+                        const uint2 c = lds64(cold_src + k * CB_PSTRIDE);
+                        sts64(cold_dst + k * CB_PSTRIDE, c.x, c.y);
+                    }
+                    active = true; owner = own;
+                }
+                // owners count the helpers that just left
+                unsigned tm = __ballot_sync(FULL, took);
+                while (tm) {
+                    const int t = __ffs(tm) - 1;
+                    tm &= tm - 1;
+                    if ((int)lane == __shfl_sync(FULL, owner, t)) pending++;
+                }
+                __syncwarp();
+            }
         }
         // One step per lane and iteration: a lane with queued leaves tests a triangle, a lane
         // without expands its node.  Both kinds fetch four 16-byte words from one 64-byte
@@ -391,9 +477,12 @@ step_physics_kernel(DevGeometry g, PropParams P)
 // (warp_traverse) and all lanes run the physics of their photon redundantly, so a
 // step costs a few microseconds instead of the ~50 us of a single-thread step.
 // Warps claim photons from the queue with one atomic each until it is empty.
-constexpr int TAIL_THREADS = 256;
+#ifndef CB_TAIL_THREADS
+#define CB_TAIL_THREADS 1024   /* one CTA per SM: the tables are staged once per SM and ~150 KB stay L1 */
+#endif
+constexpr int TAIL_THREADS = CB_TAIL_THREADS;
 #ifndef CB_TAIL_BLOCKS
-#define CB_TAIL_BLOCKS 4     /* 64 registers: 32 resident warps (photons) per SM */
+#define CB_TAIL_BLOCKS 1     /* 64 registers: 32 resident warps (photons) per SM */
 #endif
 template <bool COUNT, bool WIRES>
 __global__ void __launch_bounds__(TAIL_THREADS, CB_TAIL_BLOCKS)
@@ -729,8 +818,9 @@ static int check_bank(const CbPhotonBank* b, const char* who)
 static size_t stack_smem_bytes() { return (size_t)(CB_PSTACK + CB_PLEAF + CB_PCOLD) * INT_THREADS * sizeof(uint2); }
 static Tune tune_from_env()
 {
-    Tune t = {12};
+    Tune t = {12, 1};
     if (const char* e = getenv("CHROMA_B200_REFILL_MIN")) t.refill_min = atoi(e);
+    if (const char* e = getenv("CHROMA_B200_SPLIT")) t.split = atoi(e);
     return t;
 }
 

@@ -51,6 +51,23 @@ def test_bit_exact_vs_reference_kernel(gpu_ready, scene):
     assert hit.mean() > 0.05
 
 
+def test_ray_splitting_does_not_change_results(gpu_ready, monkeypatch):
+    # the end game of a launch shares the longest rays among the free lanes of their warp
+    # (persistent_intersect); with few rays every warp is in that regime from the start
+    geo = scenes.tiny_detector()
+    for n in (3000, 200000):
+        o, d = random_rays(geo, n, 77)
+        monkeypatch.setenv('CHROMA_B200_SPLIT', '0')
+        tri0, dist0 = run_engine(geo, o, d)
+        monkeypatch.setenv('CHROMA_B200_SPLIT', '1')
+        tri1, dist1 = run_engine(geo, o, d)
+        assert np.array_equal(tri0, tri1)
+        hit = tri0 >= 0
+        assert np.array_equal(dist0[hit].view(np.uint32), dist1[hit].view(np.uint32))
+        assert hit.mean() > 0.05
+    monkeypatch.delenv('CHROMA_B200_SPLIT')
+
+
 def test_last_hit_exclusion_vs_reference(gpu_ready):
     geo = scenes.sphere_scene()
     n = 100000
