@@ -7,3 +7,4 @@ from .detector import GPUDetector  # noqa: F401
 from .photon import GPUPhotons, GPUPhotonsSlice  # noqa: F401
 from .daq import GPUDaq, GPUChannels  # noqa: F401
 from .intersect import intersect_mesh  # noqa: F401
+from .pdf import GPUPDF, GPUKernelPDF  # noqa: F401

@@ -198,6 +198,72 @@ class Simulation(object):
                     except Exception:
                         pass
 
+    # ------------------------------------------------------------------ PDFs / likelihood
+    # Upstream Chroma's Simulation.create_pdf / eval_pdf / eval_kernel, which this fork of the
+    # reference dropped while keeping gpu/pdf.py and cuda/pdf.cu: Monte
+    # Carlo events -> propagate -> DAQ -> per-channel accumulators (gpu.GPUPDF / gpu.GPUKernelPDF).
+    def _mc_channels(self, iterable, nreps=1, ndaq=1, max_steps=100):
+        """GPUChannels of every (event, repetition, DAQ pass) of the Monte Carlo."""
+        assert hasattr(self, 'gpu_daq'), 'PDFs need a detector with channels'
+        if isinstance(iterable, event.Photons) or hasattr(iterable, 'wavelengths'):
+            iterable = [iterable]
+        for item in iterable:
+            photons = item.photons_beg if hasattr(item, 'photons_beg') else item
+            gpu_photons = gpu.GPUPhotons(photons, ncopies=nreps)
+            gpu_photons.propagate(self.gpu_geometry, self.rng_states, nthreads_per_block=self.nthreads_per_block,
+                                  max_blocks=self.max_blocks, max_steps=max_steps)
+            n = gpu_photons.true_nphotons
+            for rep in range(nreps):
+                for _ in range(ndaq):
+                    self.gpu_daq.begin_acquire()
+                    self.gpu_daq.acquire(gpu_photons, self.rng_states, start_photon=rep * n, nphotons=n,
+                                         nthreads_per_block=self.nthreads_per_block, max_blocks=self.max_blocks)
+                    yield self.gpu_daq.end_acquire()
+
+    def create_pdf(self, iterable, tbins, trange, qbins, qrange, nreps=1, max_steps=100):
+        """(hit count per channel, [channel, time, charge] histogram) of the Monte Carlo events."""
+        if getattr(self, 'gpu_pdf', None) is None:
+            self.gpu_pdf = gpu.GPUPDF()
+        config = (tbins, tuple(trange), qbins, tuple(qrange))
+        if getattr(self, 'pdf_config', None) != config:
+            self.pdf_config = config
+            self.gpu_pdf.setup_pdf(self.gpu_geometry.nchannels, tbins, trange, qbins, qrange)
+        else:
+            self.gpu_pdf.clear_pdf()
+        for channels in self._mc_channels(iterable, nreps=nreps, max_steps=max_steps):
+            self.gpu_pdf.add_hits_to_pdf(channels)
+        return self.gpu_pdf.get_pdfs()
+
+    def eval_pdf(self, event_channels, iterable, min_twidth, trange, min_qwidth, qrange, min_bin_content=100,
+                 nreps=1, ndaq=1, time_only=True, max_steps=100):
+        """(hit count, PDF value, uncertainty) per channel at the times of `event_channels`
+        (event.Channels), estimated from the Monte Carlo events with an adaptive bin."""
+        if getattr(self, 'gpu_pdf', None) is None:
+            self.gpu_pdf = gpu.GPUPDF()
+        self.gpu_pdf.setup_pdf_eval(event_channels.hit, event_channels.t, event_channels.q, min_twidth, trange,
+                                    min_qwidth, qrange, min_bin_content=min_bin_content, time_only=time_only)
+        for channels in self._mc_channels(iterable, nreps=nreps, ndaq=ndaq, max_steps=max_steps):
+            self.gpu_pdf.accumulate_pdf_eval(channels)
+        return self.gpu_pdf.get_pdf_eval()
+
+    def eval_kernel(self, event_channels, kernel_generator, trange, qrange, nreps=1, ndaq=1, time_only=True,
+                    scale_factor=1.0, max_steps=100):
+        """Kernel-density version of eval_pdf: `kernel_generator` is iterated twice (a list, or a
+        callable returning a fresh iterable): first for the moments that set the bandwidths, then
+        for the kernel sums."""
+        source = kernel_generator if callable(kernel_generator) else (lambda: kernel_generator)
+        if getattr(self, 'gpu_pdf_kernel', None) is None:
+            self.gpu_pdf_kernel = gpu.GPUKernelPDF()
+        k = self.gpu_pdf_kernel
+        k.setup_moments(self.gpu_geometry.nchannels, trange, qrange, time_only=time_only)
+        for channels in self._mc_channels(source(), nreps=nreps, ndaq=ndaq, max_steps=max_steps):
+            k.accumulate_moments(channels)
+        k.compute_bandwidth(event_channels.hit, event_channels.t, event_channels.q, scale_factor=scale_factor)
+        k.setup_kernel(event_channels.hit, event_channels.t, event_channels.q)
+        for channels in self._mc_channels(source(), nreps=nreps, ndaq=ndaq, max_steps=max_steps):
+            k.accumulate_kernel(channels)
+        return k.get_kernel_eval()
+
     def _workers(self):
         """The two pipeline threads live as long as the Simulation (their CUDA per-thread state --
         device binding, copy stream -- is set up once, not per simulate() call)."""

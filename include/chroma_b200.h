@@ -277,6 +277,37 @@ int cb_daq_pointers(cb_daq_t d, void** t, void** q, void** flags,
 /* finalise from integer accumulators only (after a cross-GPU reduction) */
 int cb_daq_finalize(cb_daq_t d);
 
+/* ---- PDF / likelihood accumulators (chroma/gpu/pdf.py, chroma/cuda/pdf.cu) -
+ * All pointers are DEVICE pointers ([nchannels] unless stated); `t` / `q` are the
+ * arrays a DAQ acquisition leaves behind (cb_daq_pointers), ndaq copies one after
+ * the other.  Each call accumulates ONE acquisition into the caller's arrays.   */
+/* GPUPDF.add_hits_to_pdf (gpu/pdf.py:201-217, bin_hits pdf.cu:9-32):
+ * pdf is [nchannels][tbins][qbins], row major                                   */
+int cb_pdf_bin_hits(int32_t nchannels, const float* q, const float* t, uint32_t* hitcount,
+                    int32_t tbins, float tmin, float tmax, int32_t qbins, float qmin, float qmax,
+                    uint32_t* pdf);
+/* GPUKernelPDF.accumulate_moments (gpu/pdf.py:44-61, pdf.cu:223-266)            */
+int cb_pdf_accumulate_moments(int32_t time_only, int32_t nchannels, const float* mc_time,
+                              const float* mc_charge, float tmin, float tmax, float qmin, float qmax,
+                              uint32_t* mom0, float* t_mom1, float* t_mom2, float* q_mom1, float* q_mom2);
+/* GPUKernelPDF.accumulate_kernel (gpu/pdf.py:140-160, pdf.cu:271-368)           */
+int cb_pdf_accumulate_kernel_eval(int32_t time_only, int32_t nchannels, const uint32_t* event_hit,
+                                  const float* event_time, const float* event_charge,
+                                  const float* mc_time, const float* mc_charge,
+                                  float tmin, float tmax, float qmin, float qmax,
+                                  const float* inv_time_bandwidths, const float* inv_charge_bandwidths,
+                                  uint32_t* hitcount, float* time_pdf_values, float* charge_pdf_values);
+/* GPUPDF.accumulate_pdf_eval (gpu/pdf.py:297-330): accumulate_bincount (pdf.cu:34-96)
+ * + accumulate_nearest_neighbor_block (pdf.cu:152-219) in ONE launch, without the
+ * work-queue array and the host synchronisation between them.  mc_time is
+ * [ndaq][nchannels]; nearest_mc is [nhit][min_bin_content], kept sorted ascending,
+ * unused slots > 1e8; map_hit_offset_to_channel_id is [nhit].                   */
+int cb_pdf_accumulate_eval(int32_t nchannels, int32_t ndaq, int32_t nhit, const uint32_t* event_hit,
+                           const float* event_time, const float* mc_time, uint32_t* hitcount,
+                           uint32_t* bincount, float min_twidth, float tmin, float tmax,
+                           int32_t min_bin_content, const uint32_t* map_hit_offset_to_channel_id,
+                           float* nearest_mc);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

@@ -493,3 +493,95 @@ def make_leaves(vertices, triangles, world_origin, world_scale):
         mod.launch('make_leaves', blocks, 256, C.c_uint(first), C.c_uint(cnt), t, v, o, C.c_float(world_scale), nodes, codes)
     sync()
     return from_dev(nodes), from_dev(codes)
+
+
+# ---------------------------------------------------------------- PDF accumulators
+class RefKernelPDF(object):
+    """GPUKernelPDF's device side (gpu/pdf.py:44-61, 140-160) on the reference's pdf.cu kernels:
+    same launch shapes (block 64, grid n//64+1).  Arrays are host float32/uint32 in, state on the
+    device; `channels_t` / `channels_q` are the DAQ output of one acquisition."""
+
+    def __init__(self, nchannels, trange, qrange, time_only=True):
+        self.mod = module('pdf.cubin')
+        self.n, self.trange, self.qrange, self.time_only = nchannels, trange, qrange, time_only
+        z = lambda dt: to_dev(np.zeros(nchannels, dtype=dt))
+        self.hitcount, self.tmom1, self.tmom2, self.qmom1, self.qmom2 = z(np.uint32), z(np.float32), z(np.float32), z(np.float32), z(np.float32)
+
+    def accumulate_moments(self, channels_t, channels_q, block=64):
+        t, q = to_dev(np.asarray(channels_t, np.float32)), to_dev(np.asarray(channels_q, np.float32))
+        self.mod.launch('accumulate_moments', self.n // block + 1, block, C.c_int(int(self.time_only)), C.c_int(self.n), t, q,
+                        C.c_float(self.trange[0]), C.c_float(self.trange[1]), C.c_float(self.qrange[0]), C.c_float(self.qrange[1]),
+                        self.hitcount, self.tmom1, self.tmom2, self.qmom1, self.qmom2)
+        sync()
+
+    def moments(self):
+        return tuple(from_dev(a) for a in (self.hitcount, self.tmom1, self.tmom2, self.qmom1, self.qmom2))
+
+    def setup_kernel(self, event_hit, event_time, event_charge, inv_time_bw, inv_charge_bw):
+        self.event_hit = to_dev(np.asarray(event_hit, np.uint32))
+        self.event_time, self.event_charge = to_dev(np.asarray(event_time, np.float32)), to_dev(np.asarray(event_charge, np.float32))
+        self.inv_t, self.inv_q = to_dev(np.asarray(inv_time_bw, np.float32)), to_dev(np.asarray(inv_charge_bw, np.float32))
+        self.hitcount = to_dev(np.zeros(self.n, dtype=np.uint32))
+        self.tval, self.qval = to_dev(np.zeros(self.n, dtype=np.float32)), to_dev(np.zeros(self.n, dtype=np.float32))
+
+    def accumulate_kernel(self, channels_t, channels_q, block=64):
+        t, q = to_dev(np.asarray(channels_t, np.float32)), to_dev(np.asarray(channels_q, np.float32))
+        self.mod.launch('accumulate_kernel_eval', self.n // block + 1, block, C.c_int(int(self.time_only)), C.c_int(self.n),
+                        self.event_hit, self.event_time, self.event_charge, t, q,
+                        C.c_float(self.trange[0]), C.c_float(self.trange[1]), C.c_float(self.qrange[0]), C.c_float(self.qrange[1]),
+                        self.inv_t, self.inv_q, self.hitcount, self.tval, self.qval)
+        sync()
+
+    def kernel_state(self):
+        return from_dev(self.hitcount), from_dev(self.tval), from_dev(self.qval)
+
+
+class RefPDF(object):
+    """GPUPDF's device side (gpu/pdf.py:201-217, 297-330) on the reference's pdf.cu kernels."""
+
+    def __init__(self):
+        self.mod = module('pdf.cubin')
+
+    def setup_pdf(self, nchannels, tbins, trange, qbins, qrange):
+        self.n, self.tbins, self.trange, self.qbins, self.qrange = nchannels, tbins, trange, qbins, qrange
+        self.hitcount = to_dev(np.zeros(nchannels, dtype=np.uint32))
+        self.pdf = to_dev(np.zeros((nchannels, tbins, qbins), dtype=np.uint32))
+
+    def add_hits_to_pdf(self, channels_t, channels_q, block=64):
+        t, q = to_dev(np.asarray(channels_t, np.float32)), to_dev(np.asarray(channels_q, np.float32))
+        self.mod.launch('bin_hits', len(channels_t) // block + 1, block, C.c_int(self.n), q, t, self.hitcount, C.c_int(self.tbins),
+                        C.c_float(self.trange[0]), C.c_float(self.trange[1]), C.c_int(self.qbins), C.c_float(self.qrange[0]),
+                        C.c_float(self.qrange[1]), self.pdf)
+        sync()
+
+    def get_pdfs(self):
+        return from_dev(self.hitcount), from_dev(self.pdf)
+
+    def setup_pdf_eval(self, event_hit, event_time, min_twidth, trange, min_bin_content=10):
+        event_hit = np.asarray(event_hit)
+        self.n = len(event_hit)
+        self.nhit = int(np.count_nonzero(event_hit))
+        self.hit_to_channel = to_dev(np.flatnonzero(event_hit).astype(np.uint32))
+        self.channel_to_hit = to_dev(np.maximum(0, event_hit.astype(np.int64).cumsum() - 1).astype(np.uint32))
+        self.event_hit, self.event_time = to_dev(event_hit.astype(np.uint32)), to_dev(np.asarray(event_time, np.float32))
+        self.eval_hitcount, self.eval_bincount = to_dev(np.zeros(self.n, np.uint32)), to_dev(np.zeros(self.n, np.uint32))
+        self.nearest = to_dev(np.full(max(self.nhit * min_bin_content, 1), 1e9, dtype=np.float32))
+        self.min_twidth, self.trange, self.m = min_twidth, trange, min_bin_content
+
+    def accumulate_pdf_eval(self, channels_t, ndaq, block=64):
+        """channels_t: [ndaq * nchannels] DAQ times of one acquisition (host array, or a DevMem that
+        is already on the device).  The work-queue array is created and filled with 1 on every call,
+        as gpu/pdf.py:299-300 does."""
+        t = channels_t if isinstance(channels_t, DevMem) else to_dev(np.asarray(channels_t, np.float32))
+        queues = to_dev(np.ones(max(self.nhit * (ndaq + 1), 1), dtype=np.uint32))
+        self.mod.launch('accumulate_bincount', self.n // block + 1, block, C.c_int(self.n), C.c_int(ndaq), self.event_hit,
+                        self.event_time, t, self.eval_hitcount, self.eval_bincount, C.c_float(self.min_twidth),
+                        C.c_float(self.trange[0]), C.c_float(self.trange[1]), C.c_int(self.m), self.channel_to_hit, queues)
+        sync()
+        if self.nhit:
+            self.mod.launch('accumulate_nearest_neighbor_block', self.nhit, block, C.c_int(self.nhit), C.c_int(ndaq),
+                            self.hit_to_channel, queues, self.event_time, t, self.nearest, C.c_int(self.m))
+        sync()
+
+    def eval_state(self):
+        return from_dev(self.eval_hitcount), from_dev(self.eval_bincount), from_dev(self.nearest)
