@@ -138,24 +138,27 @@ class GPUPhotons(object):
         _lib.check(lib.cb_count_photon_hits(C.byref(src), int(start_photon), int(nphotons), int(target_flag),
                                             gpu_detector.handle, C.byref(count)))
         n = count.value
-        out = _alloc_bank(n)
-        channels = ga.empty(n, np.int32)
+        # the ten result arrays live in ONE device block and come back in ONE copy into a pooled
+        # page-locked buffer (the reference: ten gpuarray allocations and ten .get() calls)
+        words = (3, 3, 3, 1, 1, 1, 1, 1, 1, 1)             # 4-byte words per photon: _FIELDS + channel
+        block = ga.empty(max(n, 1) * sum(words), np.uint32)
+        offs = np.concatenate([[0], np.cumsum(words)]) * max(n, 1)
         if n:
             dst = _lib.CbPhotonBank()
-            for f in _FIELDS:
-                setattr(dst, f, out[f].ptr)
+            for f, o in zip(_FIELDS, offs):
+                setattr(dst, f, block.ptr + 4 * int(o))
             dst.n = n
             c2 = C.c_uint32()
             _lib.check(lib.cb_copy_photon_hits(C.byref(src), int(start_photon), int(nphotons), int(target_flag),
-                                               gpu_detector.handle, C.byref(dst), channels.ptr, C.byref(c2)))
+                                               gpu_detector.handle, C.byref(dst), block.ptr + 4 * int(offs[9]), C.byref(c2)))
             assert c2.value == n
         _t1 = _time.perf_counter()
-        g = lambda a: a.get()
         self.last_hit_timings = (_t1 - _t0,)
-        return event.Photons(g(out['pos']).view(np.float32).reshape((n, 3)), g(out['dir']).view(np.float32).reshape((n, 3)),
-                             g(out['pol']).view(np.float32).reshape((n, 3)), g(out['wavelengths']), g(out['t']),
-                             g(out['last_hit_triangles']), g(out['flags']), g(out['weights']), g(out['evidx']),
-                             g(channels))
+        host = block.get()
+        part = lambda i, dt: host[int(offs[i]):int(offs[i]) + n * words[i]].view(dt)
+        vec3 = lambda i: part(i, np.float32).reshape((n, 3))
+        return event.Photons(vec3(0), vec3(1), vec3(2), part(3, np.float32), part(4, np.float32), part(5, np.int32),
+                             part(6, np.uint32), part(7, np.float32), part(8, np.uint32), part(9, np.int32))
 
     def iterate_copies(self):
         for i in range(self.ncopies):
