@@ -117,6 +117,7 @@ SIGNATURES = {
     'cb_daq_end_acquire': (C.c_int, [u64]),
     'cb_daq_pointers': (C.c_int, [u64, _P(vp), _P(vp), _P(vp), _P(vp), _P(vp), _P(u64)]),
     'cb_daq_finalize': (C.c_int, [u64]),
+    'cb_unique_vertices': (C.c_int, [vp, u64, vp, vp, _P(u64)]),
     'cb_pdf_bin_hits': (C.c_int, [i32, vp, vp, vp, i32, f32, f32, i32, f32, f32, vp]),
     'cb_pdf_accumulate_moments': (C.c_int, [i32, i32, vp, vp, f32, f32, f32, f32, vp, vp, vp, vp, vp]),
     'cb_pdf_accumulate_kernel_eval': (C.c_int, [i32, i32, vp, vp, vp, vp, vp, f32, f32, f32, f32, vp, vp, vp, vp, vp]),

@@ -12,6 +12,28 @@ import numpy as np
 standard_wavelengths = np.arange(60, 1000, 5).astype(np.float32)
 
 
+NATIVE_UNIQUE_MIN = 200000      # vertices; below this np.unique is quick enough
+
+
+def _native_unique_vertices(vertices):
+    """(unique rows, inverse) from libchroma_b200's host routine, or (None, None) when the
+    library cannot be loaded (host-only convenience: NumPy then does the same job)."""
+    import ctypes as C
+    try:
+        from . import _lib
+        lib = _lib.load()
+    except Exception:
+        return None, None
+    v = np.ascontiguousarray(vertices, dtype=np.float32)
+    n = len(v)
+    uniq = np.empty((n, 3), dtype=np.float32)
+    inverse = np.empty(n, dtype=np.uint32)
+    count = C.c_uint64()
+    if lib.cb_unique_vertices(v.ctypes.data, n, uniq.ctypes.data, inverse.ctypes.data, C.byref(count)) != 0:
+        return None, None
+    return uniq[:count.value].copy(), inverse.astype(np.intp)
+
+
 class Mesh(object):
     """Triangle mesh: float32 vertices (V,3) and integer triangles (T,3)."""
 
@@ -40,7 +62,14 @@ class Mesh(object):
 
     def remove_duplicate_vertices(self):
         # unique rows in lexicographic order; triangles remapped through the inverse
-        uniq, inverse = np.unique(self.vertices, axis=0, return_inverse=True)
+        # (chroma/geometry.py:59-69).  Large meshes use the library's multi-threaded host
+        # routine (cb_unique_vertices, same result as np.unique; no GPU involved): the NumPy
+        # sort of the 29k-PMT detector's 18.6 M vertices takes 15-30 s on one core.
+        uniq = inverse = None
+        if len(self.vertices) >= NATIVE_UNIQUE_MIN:
+            uniq, inverse = _native_unique_vertices(self.vertices)
+        if uniq is None:
+            uniq, inverse = np.unique(self.vertices, axis=0, return_inverse=True)
         self.vertices = np.ascontiguousarray(uniq)
         self.triangles = np.asarray(inverse).reshape(-1)[self.triangles]
 

@@ -277,6 +277,14 @@ int cb_daq_pointers(cb_daq_t d, void** t, void** q, void** flags,
 /* finalise from integer accumulators only (after a cross-GPU reduction) */
 int cb_daq_finalize(cb_daq_t d);
 
+/* ---- host-side mesh preparation (no GPU needed) --------------------------
+ * Vertex de-duplication of Geometry.flatten / Mesh.remove_duplicate_vertices
+ * (chroma/geometry.py:59-69 = np.unique over vertex rows + inverse): unique rows
+ * in lexicographic float order into unique_out [<= n][3], inverse_out[i] = row of
+ * vertex i.  All host threads.                                               */
+int cb_unique_vertices(const float* vertices, uint64_t n, float* unique_out,
+                       uint32_t* inverse_out, uint64_t* nunique_out);
+
 /* ---- PDF / likelihood accumulators (chroma/gpu/pdf.py, chroma/cuda/pdf.cu) -
  * All pointers are DEVICE pointers ([nchannels] unless stated); `t` / `q` are the
  * arrays a DAQ acquisition leaves behind (cb_daq_pointers), ndaq copies one after

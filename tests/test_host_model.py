@@ -145,3 +145,28 @@ def test_photons_event_contract():
     ch = event.Channels(np.array([True, False]), np.array([1.0, 1e9]), np.array([1.0, 0.0]), np.array([4, 0]))
     ids, t, q = ch.hit_channels()
     assert list(ids) == [0]
+
+
+def test_native_vertex_dedup_equals_numpy(monkeypatch):
+    """cb_unique_vertices (multi-threaded host sort, csrc/hostmesh.cu) gives np.unique's rows and
+    inverse; Mesh uses it for large meshes (chroma/geometry.py:59-69)."""
+    from chroma_lite_b200 import geometry as G
+    rng = np.random.default_rng(3)
+    for n in (1, 2, 1000, 300000):
+        v = (rng.integers(-40, 40, (n, 3)) / 8.0).astype(np.float32)
+        v[::5] *= np.float32(-0.0) if n > 2 else 1          # signed zeros compare equal, as in NumPy
+        uniq, inverse = G._native_unique_vertices(v)
+        assert uniq is not None
+        ref_u, ref_i = np.unique(v, axis=0, return_inverse=True)
+        assert np.array_equal(uniq, ref_u) and np.array_equal(inverse, np.asarray(ref_i).reshape(-1))
+        assert np.array_equal(uniq[inverse], v)
+    # the same mesh through both paths
+    from chroma_lite_b200.make import sphere
+    m = sphere(10.0, 96)
+    tiled = np.concatenate([m.vertices + np.float32(k % 3) for k in range(12)])
+    tris = np.concatenate([m.triangles + k * len(m.vertices) for k in range(12)])
+    a = G.Mesh(tiled, tris, remove_duplicate_vertices=True, remove_null_triangles=False)
+    monkeypatch.setattr(G, 'NATIVE_UNIQUE_MIN', 1)
+    b = G.Mesh(tiled, tris, remove_duplicate_vertices=True, remove_null_triangles=False)
+    assert len(a.vertices) < len(tiled)
+    assert np.array_equal(a.vertices, b.vertices) and np.array_equal(a.triangles, b.triangles)
