@@ -541,6 +541,9 @@ struct PTrav {
 // or rays that graze dozens of PMTs).  Same exactness rule as Trav.
 constexpr int CB_WSTACK = 192;   // stack entries per warp
 constexpr int CB_WLEAF = 64;     // leaf-queue entries per warp
+#ifndef CB_WTRI_MIN
+#define CB_WTRI_MIN 24            /* queued leaves that trigger a triangle batch */
+#endif
 
 template <bool COUNT>
 __device__ __forceinline__ int warp_traverse(const DevGeometry& g, const float3& origin, const float3& direction,
@@ -570,7 +573,7 @@ __device__ __forceinline__ int warp_traverse(const DevGeometry& g, const float3&
     __syncwarp();
 
     while (sp > 0 || nleaf > 0) {
-        if (nleaf >= 24 || sp == 0) {
+        if (nleaf >= CB_WTRI_MIN || sp == 0) {
             // ---- triangle phase: up to 32 queued leaves at once
             const int m = min(nleaf, 32);
             nleaf -= m;
@@ -804,7 +807,17 @@ __device__ __forceinline__ void rayleigh_scatter(Photon& p, Rng& rng)
 }
 
 // bulk step: absorption / re-emission / Rayleigh / reach boundary (photon.h:455-570)
-static __device__ __noinline__ int to_boundary(const DevGeometry& g, const Tables& T, Photon& p, StepState& s,
+// to_boundary and at_boundary are inlined into the kernels (physics kernel 0.40 -> 0.35 ms: the photon
+// stays in registers across them).  The thin-film surface model stays ONE shared call: inlined copies differ
+// in the last bit between kernels (FMA contraction across the call boundary), which would make results depend
+// on the schedule (physics_step<WIRES, INLINE_SURFACES> exists for experiments only).
+#ifndef CB_PHYS_CALL
+#define CB_PHYS_CALL __forceinline__
+#endif
+#ifndef CB_PHYS_CALL2
+#define CB_PHYS_CALL2 __forceinline__
+#endif
+static __device__ CB_PHYS_CALL int to_boundary(const DevGeometry& g, const Tables& T, Photon& p, StepState& s,
                                         Rng& rng, bool use_weights, int scatter_first)
 {
     float absorption_distance = -s.absorption_length * logf(rng_uniform(rng));
@@ -889,7 +902,7 @@ static __device__ __noinline__ int to_boundary(const DevGeometry& g, const Table
 }
 
 // Fresnel reflection / refraction (photon.h:572-632)
-static __device__ __noinline__ void at_boundary(Photon& p, StepState& s, Rng& rng)
+static __device__ CB_PHYS_CALL2 void at_boundary(Photon& p, StepState& s, Rng& rng)
 {
     float incident_angle = get_theta(s.normal, -p.dir);
     float refracted_angle = asinf(sinf(incident_angle) * s.n1 / s.n2);
@@ -964,8 +977,8 @@ __device__ __forceinline__ cuFloatComplex cx_sqrt(cuFloatComplex x)
 }
 
 // thin-film surface (n1 | eta+ik, thickness | n3), photon.h:669-827
-static __device__ __noinline__ int surface_complex(const DevGeometry& g, const Tables& T, Photon& p, StepState& s,
-                                            Rng& rng, const CbSurface* surface, bool use_weights)
+__device__ __forceinline__ int surface_complex_body(const DevGeometry& g, const Tables& T, Photon& p, StepState& s,
+                                                    Rng& rng, const CbSurface* surface, bool use_weights)
 {
     float detect = interp_property(g, p.wavelength, T.at(surface->detect));
     float reflect_diffuse = interp_property(g, p.wavelength, T.at(surface->reflect_diffuse));
@@ -1092,6 +1105,19 @@ static __device__ __noinline__ int surface_complex(const DevGeometry& g, const T
     }
 }
 
+static __device__ __noinline__ int surface_complex_call(const DevGeometry& g, const Tables& T, Photon& p, StepState& s,
+                                                        Rng& rng, const CbSurface* surface, bool use_weights)
+{
+    return surface_complex_body(g, T, p, s, rng, surface, use_weights);
+}
+template <bool INLINE>
+__device__ __forceinline__ int surface_complex(const DevGeometry& g, const Tables& T, Photon& p, StepState& s,
+                                               Rng& rng, const CbSurface* surface, bool use_weights)
+{
+    if (INLINE) return surface_complex_body(g, T, p, s, rng, surface, use_weights);
+    return surface_complex_call(g, T, p, s, rng, surface, use_weights);
+}
+
 // wavelength-shifting surface (photon.h:829-874)
 __device__ __forceinline__ int surface_wls(const DevGeometry& g, const Tables& T, Photon& p, StepState& s,
                                            Rng& rng, const CbSurface* surface, bool use_weights)
@@ -1195,12 +1221,13 @@ __device__ __forceinline__ int surface_angular(const DevGeometry& g, const Table
 
 // surface dispatch + default model (photon.h:953-1037; the reference's
 // effective default is CHROMA_FORCE_SCATTER_AT_PASS == 0)
+template <bool INLINE_SURFACES>
 __device__ __forceinline__ int at_surface(const DevGeometry& g, const Tables& T, Photon& p, StepState& s,
                                           Rng& rng, bool use_weights)
 {
     const CbSurface* surface = &g.surfaces[s.surface_index];
     const int model = surface->model;
-    if (model == CB_SURFACE_COMPLEX) return surface_complex(g, T, p, s, rng, surface, use_weights);
+    if (model == CB_SURFACE_COMPLEX) return surface_complex<INLINE_SURFACES>(g, T, p, s, rng, surface, use_weights);
     if (model == CB_SURFACE_WLS) return surface_wls(g, T, p, s, rng, surface, use_weights);
     if (model == CB_SURFACE_DICHROIC) return surface_dichroic(g, T, p, s, rng, surface);
     if (model == CB_SURFACE_ANGULAR) return surface_angular(g, T, p, s, rng, surface, use_weights);
@@ -1421,7 +1448,7 @@ static __device__ __noinline__ bool wire_plane_boundary(const DevGeometry& g, co
 // Returns true when the photon continues to another step.
 // WIRES: geometry with analytic wire planes (a separate instantiation, so that the cold
 // path costs the usual kernels neither registers nor instructions).
-template <bool WIRES>
+template <bool WIRES, bool INLINE_SURFACES = false>
 __device__ __forceinline__ bool physics_step(const DevGeometry& g, const Tables& T, Photon& p, Rng& rng,
                                              int tri, float distance, bool use_weights, int scatter_first)
 {
@@ -1440,7 +1467,7 @@ __device__ __forceinline__ bool physics_step(const DevGeometry& g, const Tables&
     if (command == CMD_BREAK) return false;
     if (command == CMD_CONTINUE) return true;
     if (s.surface_index != -1) {
-        command = at_surface(g, T, p, s, rng, use_weights);
+        command = at_surface<INLINE_SURFACES>(g, T, p, s, rng, use_weights);
         if (command == CMD_BREAK) return false;
         if (command == CMD_CONTINUE) return true;
     }

@@ -421,6 +421,12 @@ step_intersect_kernel(const __grid_constant__ DevGeometry g, const __grid_consta
     persistent_intersect<COUNT>(g, src, n, P.cursor, (uint32_t)__cvta_generic_to_shared(smem_raw), P.counters, tune);
 }
 
+// Inlining the thin-film surface model into this kernel alone makes it 0.14 ms per event faster (no local
+// memory left) but its arithmetic then differs in the last bit from the tail kernel's copy, and results would
+// depend on the schedule (test_config3_scheduler_invariance_full_size): it stays one shared call.
+#ifndef CB_PHYS_INLINE_SURFACES
+#define CB_PHYS_INLINE_SURFACES false
+#endif
 #ifndef CB_PHYS_BLOCKS
 #define CB_PHYS_BLOCKS 2
 #endif
@@ -454,7 +460,7 @@ step_physics_kernel(DevGeometry g, PropParams P)
                 if (photon_is_nan(p)) {
                     p.history |= CB_NO_HIT | CB_NAN_ABORT;
                 } else {
-                    alive = physics_step<WIRES>(g, T, p, rng, P.hit_tri[k], P.hit_dist[k], P.use_weights != 0,
+                    alive = physics_step<WIRES, CB_PHYS_INLINE_SURFACES>(g, T, p, rng, P.hit_tri[k], P.hit_dist[k], P.use_weights != 0,
                                          P.step == 0 ? P.scatter_first : 0);
                 }
                 rng_store(P.rng, k, rng);
