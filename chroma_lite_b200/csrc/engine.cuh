@@ -313,7 +313,10 @@ static __device__ __noinline__ int traverse_reference_order(const DevGeometry& g
 //     area behind the stack (touched by ~2 % of the rays of the 29k-PMT detector);
 //   * a plane test is PRMT + FFMA: the byte-permute builds the float 2^23+q straight
 //     from the packed uint16, the affine map folds 2^23 into its offset.
-constexpr int CB_PSTACK = 16;    // internal entries per lane
+#ifndef CB_PSTACK_N
+#define CB_PSTACK_N 16
+#endif
+constexpr int CB_PSTACK = CB_PSTACK_N;    // internal entries per lane
 constexpr int CB_PLEAF = 8;      // leaf queue per lane: one expansion's worth
 constexpr int CB_PCOLD = 3;      // slots per lane for rarely used ray state (origin, direction)
 constexpr int CB_PLSTACK = 48;   // overflow entries per lane in local memory (rarely touched)
