@@ -568,12 +568,19 @@ class RefPDF(object):
         self.nearest = to_dev(np.full(max(self.nhit * min_bin_content, 1), 1e9, dtype=np.float32))
         self.min_twidth, self.trange, self.m = min_twidth, trange, min_bin_content
 
-    def accumulate_pdf_eval(self, channels_t, ndaq, block=64):
+    def accumulate_pdf_eval(self, channels_t, ndaq, block=64, timer=None):
         """channels_t: [ndaq * nchannels] DAQ times of one acquisition (host array, or a DevMem that
-        is already on the device).  The work-queue array is created and filled with 1 on every call,
-        as gpu/pdf.py:299-300 does."""
+        is already on the device).  The work-queue array is filled with 1 on every call, as
+        gpu/pdf.py:299-300 does.  With `timer` (a Timer) returns the device time in ms of the fill and
+        the two kernels (CUDA events on the launching stream), else None."""
         t = channels_t if isinstance(channels_t, DevMem) else to_dev(np.asarray(channels_t, np.float32))
-        queues = to_dev(np.ones(max(self.nhit * (ndaq + 1), 1), dtype=np.uint32))
+        nq = max(self.nhit * (ndaq + 1), 1)
+        if getattr(self, '_queues', None) is None or self._queues.nbytes < 4 * nq:
+            self._queues = DevMem(4 * nq)
+        queues = self._queues
+        if timer is not None:
+            timer.start()
+        _ck(cu().cuMemsetD32_v2(C.c_uint64(queues.ptr), C.c_uint(1), C.c_size_t(nq)), 'cuMemsetD32')
         self.mod.launch('accumulate_bincount', self.n // block + 1, block, C.c_int(self.n), C.c_int(ndaq), self.event_hit,
                         self.event_time, t, self.eval_hitcount, self.eval_bincount, C.c_float(self.min_twidth),
                         C.c_float(self.trange[0]), C.c_float(self.trange[1]), C.c_int(self.m), self.channel_to_hit, queues)
@@ -581,7 +588,9 @@ class RefPDF(object):
         if self.nhit:
             self.mod.launch('accumulate_nearest_neighbor_block', self.nhit, block, C.c_int(self.nhit), C.c_int(ndaq),
                             self.hit_to_channel, queues, self.event_time, t, self.nearest, C.c_int(self.m))
+        ms = timer.stop() if timer is not None else None
         sync()
+        return ms
 
     def eval_state(self):
         return from_dev(self.eval_hitcount), from_dev(self.eval_bincount), from_dev(self.nearest)
