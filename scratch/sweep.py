@@ -14,6 +14,7 @@ def main():
     lib = _lib.lib()
     workload = os.environ.get('WORKLOAD', 'pmt29k')
     n = int(os.environ.get('PHOTONS', '2500000'))
+    bench._workload = workload
     det = bench.build_detector(workload, {})
     s = sim.Simulation(det, seed=42, cuda_device=0, nthreads_per_block=512, max_blocks=max(1024, -(-n // 512)))
     g, rng = s.gpu_geometry, s.rng_states

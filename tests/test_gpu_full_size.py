@@ -150,6 +150,37 @@ def test_config3_hits_and_daq_full_size(full):
     assert np.array_equal(chans.t, rt) and np.array_equal(chans.q, rq) and np.array_equal(chans.flags, rh)
 
 
+def test_config4_ten_million_photons_scintillator(gpu_ready):
+    """BASELINE config 4 at its full 10 M photons: scintillator + WLS re-emission, dichroic, angular and
+    thin-film surfaces, engine vs the reference kernel on the same inputs and seed."""
+    import scenes
+    geo = scenes.scintillator_scene(96)
+    n = 10000000
+    ph = scenes.point_source(n, seed=21, wl_range=(250, 450))
+    g = gpu.GPUDetector(geo)
+    rng = gpu.get_rng_states(n, seed=9)
+    gp = gpu.GPUPhotons(ph)
+    gp.propagate(g, rng, nthreads_per_block=512, max_blocks=(n + 511) // 512, max_steps=200)
+    mine = gp.get()
+    desc, keep = make_desc(geo)
+    rg = ref_driver.RefGeometry(desc, keep)
+    rrng = ref_driver.RefRNG(n, seed=9)
+    rp = ref_driver.RefPhotons(ph)
+    rp.propagate(rg, rrng, nthreads_per_block=256, max_steps=200, force_single_launch=True)
+    ref = rp.get()
+    same = (mine.flags == ref.flags) & (mine.last_hit_triangles == ref.last_hit_triangles)
+    assert same.mean() >= 0.995, 'identical histories: %.5f' % same.mean()
+    scale = np.maximum(np.abs(ref.pos[same]).max(axis=1), 1.0)
+    assert (np.abs(mine.pos[same] - ref.pos[same]).max(axis=1) / scale < 1e-4).mean() > 0.999
+    assert np.isclose(mine.t[same], ref.t[same], rtol=1e-4, atol=1e-3).mean() > 0.999
+    assert ((mine.flags & TERM) != 0).mean() > 0.999
+    for bit in (event.BULK_REEMIT, event.SURFACE_REEMIT, event.SURFACE_TRANSMIT, event.SURFACE_DETECT,
+                event.RAYLEIGH_SCATTER, event.REFLECT_DIFFUSE, event.REFLECT_SPECULAR):
+        m, r = ((mine.flags & bit) != 0).mean(), ((ref.flags & bit) != 0).mean()
+        assert m > 0.001 and abs(m - r) < 1e-3, (hex(bit), m, r)
+    print('config 4 identical fraction %.5f' % same.mean())
+
+
 def test_config2_ten_million_rays_bit_exact(gpu_ready):
     geo = bench.rays_scene()
     from chroma_lite_b200.bvh import make_recursive_grid_bvh
