@@ -295,8 +295,9 @@ struct PropParams {
     uint64_t first;                 // chunk base
     const uint32_t* queue_in;       // chunk-local indices, nullptr = identity
     uint32_t* queue_out;
-    int32_t* hit_tri;               // per chunk-local index
+    int32_t* hit_tri;               // result of the step's traversal, per QUEUE SLOT (dense for the physics kernel)
     float* hit_dist;
+    const uint32_t* hit_slots;      // queue the physics kernel walks, when the traversal kernel walked another (sorted) one
     // The number of queued photons lives on the device, so that consecutive steps can be
     // launched without the host reading it back: step s reads n_in[0], appends its
     // survivors to queue_out and counts them in n_out[0]; `cursor` is this step's work
@@ -386,14 +387,14 @@ ray_key_kernel(DevGeometry g, PropParams P, uint32_t* __restrict__ keys, uint32_
     const uint32_t qv = (uint32_t)fminf(fmaxf((v * 0.5f + 0.5f) * 512.0f, 0.0f), 511.0f);
     const uint32_t dirkey = spread9(qu) | (spread9(qv) << 1);            // 18 bits
     keys[i] = (((cx << 8) | (cy << 4) | cz) << 18) | dirkey;            // 30 bits
-    vals[i] = k;
+    vals[i] = i;                                                        // the queue slot: where the hit goes
 }
 
 struct PhotonRaySource {     // one propagation step: rays of the photons in the queue
     const PropParams& P;
     __device__ __forceinline__ bool load(unsigned long long q, float3& o, float3& d, int& last) const
     {
-        const uint32_t k = queue_index(P, q);
+        const uint32_t k = queue_index(P, P.hit_slots ? (unsigned long long)P.hit_slots[q] : q);
         const uint64_t id = P.first + k;
         if (P.step == 0 && (P.bank.flags[id] & 0xFFFFu & CB_TERMINAL)) return false;   // never ran: untouched
         o = ld3(P.bank.pos, id);
@@ -404,9 +405,11 @@ struct PhotonRaySource {     // one propagation step: rays of the photons in the
     }
     __device__ __forceinline__ void store(unsigned long long q, int tri, float dist) const
     {
-        const uint32_t k = queue_index(P, q);
-        P.hit_tri[k] = tri;
-        P.hit_dist[k] = dist;
+        // normally by queue slot; with a coherence-sorted queue (CHROMA_B200_SORT) the slot of the
+        // physics kernel's queue comes from the sort's value array
+        const unsigned long long slot = P.hit_slots ? (unsigned long long)P.hit_slots[q] : q;
+        P.hit_tri[slot] = tri;
+        P.hit_dist[slot] = dist;
     }
 };
 
@@ -444,23 +447,28 @@ step_physics_kernel(DevGeometry g, PropParams P)
     const unsigned lane = threadIdx.x & 31u;
     const bool last_step = (P.step + 1 >= P.max_steps);
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(P.counters + 4, (unsigned long long)n_in);   // steps taken
-    // grid-stride over whole warps so the ballot below always sees full warps
+    // grid-stride over whole warps so the ballot below always sees full warps.  Two rounds of
+    // loads per photon instead of four dependent ones: (queue entry, hit triangle, hit distance) by
+    // queue slot, then (flags, state, RNG, triangle record) together.
     const uint32_t n_round = (n_in + 31u) & ~31u;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
         bool alive = false;
         uint32_t k = 0, mark = 0;
         if (i < n_in) {
             k = queue_index(P, i);
+            const int hit_tri = P.hit_tri[i];
+            const float hit_dist = P.hit_dist[i];
             const uint64_t id = P.first + k;
+            if (hit_tri >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(g.tri64 + 4ull * (uint32_t)hit_tri));
             const uint32_t hist = P.bank.flags[id] & 0xFFFFu;
+            Photon p;
+            load_photon(P.bank, id, hist, P.step == 0, p);
+            Rng rng = rng_load(P.rng, k);
             if (!(P.step == 0 && (hist & CB_TERMINAL))) {
-                Photon p;
-                load_photon(P.bank, id, hist, P.step == 0, p);
-                Rng rng = rng_load(P.rng, k);
                 if (photon_is_nan(p)) {
                     p.history |= CB_NO_HIT | CB_NAN_ABORT;
                 } else {
-                    alive = physics_step<WIRES, CB_PHYS_INLINE_SURFACES>(g, T, p, rng, P.hit_tri[k], P.hit_dist[k], P.use_weights != 0,
+                    alive = physics_step<WIRES, CB_PHYS_INLINE_SURFACES>(g, T, p, rng, hit_tri, hit_dist, P.use_weights != 0,
                                          P.step == 0 ? P.scatter_first : 0);
                 }
                 rng_store(P.rng, k, rng);
@@ -1002,7 +1010,7 @@ int cb_propagate(const CbPhotonBank* bank, cb_geom_t gh, cb_rng_t rh, int32_t nt
         const uint64_t cnt = std::min<uint64_t>(pool, bank->n - first);
         PropParams P;
         P.bank = *bank; P.rng = r->states; P.first = first;
-        P.hit_tri = c.d_hit_tri; P.hit_dist = c.d_hit_dist;
+        P.hit_tri = c.d_hit_tri; P.hit_dist = c.d_hit_dist; P.hit_slots = nullptr;
         P.max_steps = max_steps; P.use_weights = use_weights; P.scatter_first = scatter_first;
         P.counters = c.d_counters;
         CB_CUDA(cudaMemsetAsync(c.d_counters, 0, 16 * sizeof(unsigned long long), c.stream));
@@ -1041,7 +1049,7 @@ int cb_propagate(const CbPhotonBank* bank, cb_geom_t gh, cb_rng_t rh, int32_t nt
                     if (time_it) CB_CUDA(cudaEventRecord(c.iev0, c.stream));
                     if (trace) cudaEventRecord(tev[0], c.stream);
                     PropParams PI = P;
-                    if (sort_threshold && exact && n_alive >= sort_threshold) PI.queue_in = c.d_sorted;
+                    if (sort_threshold && exact && n_alive >= sort_threshold) PI.hit_slots = c.d_sorted;
                     mark("pre-int");
                     k_int<<<iblocks, INT_THREADS, smem_int, c.stream>>>(g->dev, PI, tune);
                     mark("int");
