@@ -28,11 +28,24 @@ def _resolve_nphotons(ph):
 _pool = None
 
 
+def _upload_threads():
+    """Host threads that stage a bank's arrays concurrently (each with its own copy stream and
+    spinning in its stream synchronisation).  Three when this process has the host to itself; one
+    when several ranks share it (LOCAL_WORLD_SIZE / WORLD_SIZE of torchrun >= 4): a single stream
+    still uploads a 130 MB event in ~3 ms, well inside the 7 ms GPU stage it overlaps with, and the
+    ranks' spinning threads no longer outnumber the cores.  CHROMA_B200_UPLOAD_THREADS overrides."""
+    import os
+    if os.environ.get('CHROMA_B200_UPLOAD_THREADS'):
+        return max(1, int(os.environ['CHROMA_B200_UPLOAD_THREADS']))
+    ranks = int(os.environ.get('LOCAL_WORLD_SIZE', os.environ.get('WORLD_SIZE', '1')) or 1)
+    return 1 if ranks >= 4 else 3
+
+
 def _upload_pool():
     global _pool
     if _pool is None:
         import concurrent.futures
-        _pool = concurrent.futures.ThreadPoolExecutor(max_workers=3, thread_name_prefix='cb-upload')
+        _pool = concurrent.futures.ThreadPoolExecutor(max_workers=_upload_threads(), thread_name_prefix='cb-upload')
     return _pool
 
 
