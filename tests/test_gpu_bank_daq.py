@@ -235,3 +235,22 @@ def test_errors_are_loud(gpu_ready):
     gp = gpu.GPUPhotons(scenes.point_source(10))
     with pytest.raises(_lib.ChromaB200Error):
         gp.propagate(g, type('R', (), {'handle': 987654})(), max_steps=1)
+
+
+def test_rat_bridge_request(gpu_ready):
+    """bin/chroma-server-rat's request -> propagate -> reply cycle through wire.handle_rat_request: the
+    reply holds the flat hits of the same event, grouped by channel."""
+    from chroma_lite_b200 import sim, wire
+    det = scenes.tiny_detector()
+    ph = scenes.point_source(80000, seed=31, wl_range=(300, 600))
+    msg = wire.encode_rat_request(ph, event_id=12)
+    s1 = sim.Simulation(det, seed=3, nthreads_per_block=256, max_blocks=512)
+    hits, evid = wire.decode_rat_reply(wire.handle_rat_request(s1, msg, max_steps=100))
+    s2 = sim.Simulation(det, seed=3, nthreads_per_block=256, max_blocks=512)
+    ev = next(s2.simulate(ph, keep_flat_hits=True, keep_hits=False, max_steps=100))
+    order = np.argsort(ev.flat_hits.channel, kind='stable')
+    assert evid == 12 and len(hits) == len(ev.flat_hits) > 100
+    assert np.array_equal(hits.channel, ev.flat_hits.channel[order])
+    assert np.array_equal(hits.t, ev.flat_hits.t[order]) and np.array_equal(hits.pos, ev.flat_hits.pos[order])
+    empty, _ = wire.decode_rat_reply(wire.handle_rat_request(s1, wire.encode_rat_request(ph[:0], event_id=1)))
+    assert len(empty) == 0
