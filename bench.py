@@ -37,8 +37,8 @@ MAX_STEPS = 100
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel from the
 # committed `ncu --set full` capture (profiles/), keyed by (workload, photons per event)
 NCU_TRAFFIC_BYTES_PER_LAUNCH = {
-    # profiles/r01_ncu_step_intersect_summary.txt: 2.638825 GB read + 48.133888 MB written
-    ('pmt29k', 2500000): 2638825000 + 48133888,
+    # profiles/r01_ncu_step_intersect_summary.txt: 2.678675 GB read + 47.112192 MB written
+    ('pmt29k', 2500000): 2678675000 + 47112192,
 }
 
 
