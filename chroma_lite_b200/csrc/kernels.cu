@@ -8,7 +8,10 @@
 
 namespace cb {
 
-constexpr int PROP_THREADS = 256;
+#ifndef CB_PHYS_THREADS
+#define CB_PHYS_THREADS 256
+#endif
+constexpr int PROP_THREADS = CB_PHYS_THREADS;   // physics kernel
 constexpr int INT_THREADS = CB_INT_THREADS;   // traversal kernels
 
 // ---------------------------------------------------------------- smem staging
