@@ -6,6 +6,7 @@ and hits / DAQ are extracted per event exactly like _simulate_batch does.
 """
 import os
 import time
+from types import SimpleNamespace
 import numpy as np
 
 from . import event, gpu
@@ -54,9 +55,49 @@ class Simulation(object):
         t0 = time.perf_counter()
         sources = [ev.photons_beg for ev in batch_events]
         bounds = np.cumsum(np.concatenate([[0], [len(s) for s in sources]])).astype(np.int64)
-        batch = sources[0] if len(sources) == 1 else event.Photons.join(sources)
+        if len(sources) == 1:
+            batch = sources[0]
+        else:
+            # device-resident sources are concatenated on the device (chroma/sim.py:155-226);
+            # anything else goes through the host join like the reference's fallback
+            batch = self._stack_gpu_photon_sources(sources, copy_flags=True, copy_triangles=False,
+                                                   copy_weights=False)
+            if batch is None:
+                batch = event.Photons.join(sources)
         gpu_photons = gpu.GPUPhotons(batch, copy_flags=True, copy_triangles=False, copy_weights=False)
         return gpu_photons, bounds, time.perf_counter() - t0
+
+    @staticmethod
+    def _is_gpu_photon_source(photons, copy_flags=True, copy_triangles=False, copy_weights=False):
+        """True when every field GPUPhotons would copy is already a device array
+        (chroma/sim.py:155-168)."""
+        fields = ['pos', 'dir', 'pol', 'wavelengths', 't', 'evidx']
+        fields += ['flags'] * bool(copy_flags) + ['last_hit_triangles'] * bool(copy_triangles)
+        fields += ['weights'] * bool(copy_weights)
+        return all(isinstance(getattr(photons, f, None), ga.DeviceArray) for f in fields)
+
+    @classmethod
+    def _stack_gpu_photon_sources(cls, photon_sources, copy_flags=True, copy_triangles=False, copy_weights=False):
+        """Concatenate device-resident photon sources into one device-resident source with
+        device-to-device copies (chroma/sim.py:170-226); None unless every source qualifies."""
+        if not photon_sources or not all(cls._is_gpu_photon_source(p, copy_flags, copy_triangles, copy_weights)
+                                         for p in photon_sources):
+            return None
+        counts = [gpu.photon._resolve_nphotons(p) for p in photon_sources]
+        total = int(sum(counts))
+        fields = ['pos', 'dir', 'pol', 'wavelengths', 't', 'evidx']
+        fields += ['flags'] * bool(copy_flags) + ['last_hit_triangles'] * bool(copy_triangles)
+        fields += ['weights'] * bool(copy_weights)
+        stacked = {}
+        for f in fields:
+            dest = ga.empty(total, getattr(photon_sources[0], f).dtype)
+            offset = 0
+            for p, n in zip(photon_sources, counts):
+                if n:
+                    dest[offset:offset + n].copy_from_device(getattr(p, f), n * dest.dtype.itemsize)
+                offset += n
+            stacked[f] = dest
+        return SimpleNamespace(true_nphotons=total, **stacked)
 
     def _gpu_stage(self, batch_events, uploaded=None, keep_photons_end=False, keep_hits=True, keep_flat_hits=True,
                    run_daq=False, max_steps=100, verbose=False, **_unused):

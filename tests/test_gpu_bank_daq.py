@@ -226,6 +226,70 @@ def test_simulation_front_end(gpu_ready):
     assert len(single) == 1 and len(single[0].photons_end) == 1000
 
 
+def _gpu_view(gp):
+    from types import SimpleNamespace
+    return SimpleNamespace(pos=gp.pos, dir=gp.dir, pol=gp.pol, wavelengths=gp.wavelengths, t=gp.t,
+                           last_hit_triangles=gp.last_hit_triangles, flags=gp.flags, weights=gp.weights,
+                           evidx=gp.evidx)
+
+
+def test_gpu_photons_from_device_arrays(gpu_ready):
+    """The reference's test/test_gpu_photon_gpu_input.py:50-85: a bank built from device arrays holds the
+    same photons (the constructor copies device-to-device, gpu/photon.py:62-89), replicates them with
+    ncopies, and resets the fields it is told not to copy."""
+    ph = scenes.point_source(777, seed=4, wl_range=(300, 600))
+    ph.flags[:] = np.arange(777) % 2
+    ph.weights[:] = 0.5
+    ph.last_hit_triangles[:] = 7
+    src = gpu.GPUPhotons(ph)
+    same = gpu.GPUPhotons(_gpu_view(src))
+    assert same.true_nphotons == 777 and len(same) == 777
+    a, b = src.get(), same.get()
+    for f in ('pos', 'dir', 'pol', 'wavelengths', 't', 'last_hit_triangles', 'flags', 'weights', 'evidx'):
+        assert np.array_equal(getattr(a, f), getattr(b, f)), f
+    dupe = gpu.GPUPhotons(_gpu_view(src), ncopies=2)
+    d = dupe.get()
+    assert len(dupe.pos) == 2 * 777
+    assert np.array_equal(d.pos[:777], d.pos[777:]) and np.array_equal(d.flags[:777], d.flags[777:])
+    assert np.array_equal(d.pos[:777], a.pos)
+    reset = gpu.GPUPhotons(_gpu_view(src), copy_flags=False, copy_triangles=False, copy_weights=False)
+    assert int(reset.flags.gpudata) != int(src.flags.gpudata)
+    assert (reset.flags.get() == 0).all() and (reset.last_hit_triangles.get() == -1).all()
+    assert np.allclose(reset.weights.get(), 1.0)
+
+
+def test_simulate_accepts_gpu_photons(gpu_ready, monkeypatch):
+    """test_gpu_photon_gpu_input.py:87-108: device-resident sources never go through the host join; several
+    of them in one batch are stacked on the device (sim.py:170-226) and give the events of the host path."""
+    geo = scenes.tiny_detector()
+    evs = [scenes.point_source(6000 + 500 * k, seed=40 + k, wl_range=(300, 600)) for k in range(3)]
+    kw = dict(keep_photons_end=True, keep_flat_hits=True, keep_hits=False, run_daq=True, max_steps=50,
+              photons_per_batch=13000)
+    host = list(sim.Simulation(geo, seed=9, nthreads_per_block=256, max_blocks=128).simulate(
+        [event.Event(photons_beg=p) for p in evs], **kw))
+    s = sim.Simulation(geo, seed=9, nthreads_per_block=256, max_blocks=128)
+    banks = [gpu.GPUPhotons(p) for p in evs]
+
+    def no_join(*a, **k):
+        raise AssertionError('CPU join should not be used for GPU sources')
+    monkeypatch.setattr(event.Photons, 'join', staticmethod(no_join))
+    dev = list(s.simulate([event.Event(photons_beg=b) for b in banks], **kw))
+    monkeypatch.undo()
+    assert len(dev) == len(host) == 3
+    for h, d in zip(host, dev):
+        assert np.array_equal(h.photons_end.flags, d.photons_end.flags)
+        assert np.array_equal(h.photons_end.pos, d.photons_end.pos)
+        assert np.array_equal(h.flat_hits.channel, d.flat_hits.channel) and len(d.flat_hits) > 5
+        assert np.array_equal(h.channels.t, d.channels.t) and np.array_equal(h.channels.q, d.channels.q)
+    stacked = sim.Simulation._stack_gpu_photon_sources([_gpu_view(b) for b in banks])
+    assert stacked.true_nphotons == sum(len(p) for p in evs)
+    assert np.array_equal(stacked.t.get(), np.concatenate([p.t for p in evs]))
+    assert sim.Simulation._stack_gpu_photon_sources([_gpu_view(banks[0]), evs[1]]) is None
+    one = list(s.simulate([event.Event(photons_beg=gpu.GPUPhotons(evs[0][:1]))], keep_hits=False,
+                          keep_flat_hits=False, run_daq=False, max_steps=1))
+    assert len(one) == 1
+
+
 def test_errors_are_loud(gpu_ready):
     from chroma_lite_b200 import _lib
     geo = scenes.water_box(10.0)
