@@ -28,6 +28,10 @@ def unpack_nodes(nodes):
     return out
 
 
+class OutOfRangeError(ValueError):
+    """World coordinates that do not fit the unsigned 16-bit grid (chroma/bvh/bvh.py:37-42)."""
+
+
 class WorldCoords(object):
     """world = world_origin + fixed * world_scale (chroma/bvh/bvh.py:44-94)."""
 
@@ -38,29 +42,61 @@ class WorldCoords(object):
         self.world_scale = np.float32(world_scale)
 
     def world_to_fixed(self, world):
-        fixed = ((np.asarray(world) - self.world_origin) / self.world_scale).round()
+        fixed = ((np.asarray(world, dtype=np.float64) - self.world_origin) / self.world_scale).round()
         if int(fixed.max()) > self.MAX_INT or fixed.min() < 0:
-            raise ValueError('world coordinates outside the 16-bit fixed point range')
+            raise OutOfRangeError('range = (%f, %f)' % (fixed.min(), fixed.max()))
         return fixed.astype(np.uint16)
 
     def fixed_to_world(self, fixed):
         return np.asarray(fixed) * self.world_scale + self.world_origin
 
 
+def node_areas(nodes):
+    """Surface area of every node's box in grid units (chroma/bvh/bvh.py:197-212)."""
+    u = unpack_nodes(nodes)
+    dx, dy, dz = (u[a + 'hi'].astype(np.float64) - u[a + 'lo'] for a in 'xyz')
+    return 2.0 * (dx * dy + dy * dz + dz * dx)
+
+
+class BVHLayerSlice(object):
+    """One layer of a BVH as a view of the parent's node array (chroma/bvh/bvh.py:214-260)."""
+
+    def __init__(self, world_coords, nodes):
+        self.world_coords = world_coords
+        self.nodes = nodes
+
+    def __len__(self):
+        return len(self.nodes)
+
+    def areas_fixed(self):
+        return node_areas(self.nodes)
+
+    def area_fixed(self):
+        return node_areas(self.nodes).sum()
+
+    def area(self):
+        return self.area_fixed() * float(self.world_coords.world_scale) ** 2
+
+    def get_bounds(self):
+        u = unpack_nodes(self.nodes)
+        lower = np.stack([u[a + 'lo'] for a in 'xyz'], axis=-1)
+        upper = np.stack([u[a + 'hi'] for a in 'xyz'], axis=-1)
+        return (np.atleast_2d(self.world_coords.fixed_to_world(lower)),
+                np.atleast_2d(self.world_coords.fixed_to_world(upper)))
+
+
 class BVH(object):
+    """Nodes root first, layers contiguous and in order of depth (chroma/bvh/bvh.py:106-195)."""
+
     def __init__(self, world_coords, nodes, layer_offsets):
         self.world_coords = world_coords
         self.nodes = nodes
         self.layer_offsets = list(layer_offsets)
-        layer = np.zeros(len(nodes), dtype=np.uint32)
-        for i, start in enumerate(self.layer_offsets):
-            layer[start:] = i
-        self.layer_lookup = layer
+        self.layer_bounds = self.layer_offsets + [len(nodes)]
 
     def get_layer(self, layer_number):
-        start = self.layer_offsets[layer_number]
-        end = self.layer_offsets[layer_number + 1] if layer_number + 1 < len(self.layer_offsets) else len(self.nodes)
-        return self.nodes[start:end]
+        return BVHLayerSlice(self.world_coords,
+                             self.nodes[self.layer_bounds[layer_number]:self.layer_bounds[layer_number + 1]])
 
     def layer_count(self):
         return len(self.layer_offsets)

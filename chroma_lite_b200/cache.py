@@ -103,7 +103,7 @@ class Cache(object):
         return os.path.join(self.geo_dir, name)
 
     def list_geometry(self):
-        return sorted(os.listdir(self.geo_dir))
+        return sorted(n for n in os.listdir(self.geo_dir) if '.tmp' not in n)
 
     def save_geometry(self, name, geometry):
         """Store the flattened arrays of `geometry` (flatten() is called if needed)."""
@@ -143,3 +143,19 @@ class Cache(object):
         d = self.get_geometry_filename(name)
         if os.path.isdir(d):
             shutil.rmtree(d)
+
+    def load_default_geometry(self, mmap=True):
+        """The geometry designated by set_default_geometry (chroma/cache.py:153-160)."""
+        return self.load_geometry('.default', mmap=mmap)
+
+    def set_default_geometry(self, name):
+        """Point '.default' at the cached geometry ``name`` (a symlink, chroma/cache.py:162-177)."""
+        link = self.get_geometry_filename('.default')
+        target = self.get_geometry_filename(name)
+        if not os.path.isfile(os.path.join(target, 'meta.json')):
+            raise GeometryNotFoundError(name)
+        if os.path.lexists(link):
+            if not os.path.islink(link):
+                raise IOError('Non-symlink found where expected a symlink: ' + link)
+            os.remove(link)
+        os.symlink(target, link)

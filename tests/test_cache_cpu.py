@@ -59,3 +59,87 @@ def test_flattened_geometry_round_trip(tmp_path):
     c.remove_geometry('tiny')
     with pytest.raises(cache.GeometryNotFoundError):
         c.load_geometry('tiny')
+
+
+def test_cache_directory_rules(tmp_path):
+    """The reference's test_cache.py:31-70: the directory is created when missing, reused when
+    present, and a plain file in its place is an error."""
+    import os
+    d = tmp_path / 'newdir'
+    cache.Cache(str(d))
+    assert os.path.isdir(d / 'geo') and os.path.isdir(d / 'bvh')
+    (d / 'geo' / 'keep').mkdir()
+    cache.Cache(str(d))
+    assert os.path.isdir(d / 'geo' / 'keep')
+    f = tmp_path / 'afile'
+    f.write_text('x')
+    with pytest.raises(IOError):
+        cache.Cache(str(f))
+
+
+def test_default_geometry_and_replacement(tmp_path):
+    """test_cache.py:116-178: replacing an entry, hashes of missing entries, the '.default' link and
+    a non-link in its place."""
+    import os
+    from chroma_lite_b200 import demo
+    c = cache.Cache(str(tmp_path / 'c'))
+    with pytest.raises(cache.GeometryNotFoundError):
+        c.get_geometry_hash('nothing')
+    with pytest.raises(cache.GeometryNotFoundError):
+        c.load_default_geometry()
+    with pytest.raises(cache.GeometryNotFoundError):
+        c.set_default_geometry('nothing')
+    a, b = demo.tiny(), demo.acrylic_sphere_scene(8)
+    c.save_geometry('one', a)
+    c.save_geometry('two', b)
+    c.set_default_geometry('one')
+    assert c.load_default_geometry()['mesh_hash'] == cache.mesh_hash(a.mesh)
+    c.set_default_geometry('two')                 # the link is replaced
+    assert c.load_default_geometry()['mesh_hash'] == cache.mesh_hash(b.mesh)
+    c.save_geometry('two', a)                     # replace the entry behind the link
+    assert c.get_geometry_hash('two') == cache.mesh_hash(a.mesh)
+    assert len(c.load_default_geometry()['triangles']) == len(a.mesh.triangles)
+    c.remove_geometry('does-not-exist')           # no action, no error
+    os.remove(c.get_geometry_filename('.default'))
+    os.mkdir(c.get_geometry_filename('.default'))
+    with pytest.raises(IOError):
+        c.set_default_geometry('one')
+
+
+def test_loader_uses_and_fills_the_bvh_cache(tmp_path, monkeypatch):
+    """chroma/loader.py:131-199: create_geometry_from_obj flattens, takes the BVH from the cache when
+    it is there and otherwise builds and stores it.  The build itself needs the GPU library, so it is
+    replaced here by the oracle's NumPy restatement of the same builder."""
+    from chroma_lite_b200 import loader, demo
+    from chroma_lite_b200.geometry import Geometry, Solid, Mesh
+    from chroma_lite_b200.make import sphere
+    from oracle import bvh_oracle
+    built = []
+
+    def build(mesh, target_degree=3):
+        built.append(target_degree)
+        o, sc, nodes, offs = bvh_oracle.make_recursive_grid_bvh(mesh.vertices, mesh.triangles, target_degree)
+        return BVH(WorldCoords(o, sc), nodes.view(uint4)[:, 0], offs)
+    monkeypatch.setattr(loader, 'make_recursive_grid_bvh', build)
+    d = str(tmp_path / 'c')
+    g1 = loader.create_geometry_from_obj(demo.tiny, cache_dir=d)              # callable -> Detector
+    assert built == [3] and g1.bvh is not None and hasattr(g1, 'mesh') and hasattr(g1, 'num_channels')
+    key = cache.mesh_hash(g1.mesh)
+    assert cache.Cache(d).list_bvh(key) == ['default']
+    g2 = loader.create_geometry_from_obj(demo.tiny(), cache_dir=d)            # cache hit: no build
+    assert built == [3]
+    assert np.array_equal(np.asarray(g2.bvh.nodes).view(np.uint32), np.asarray(g1.bvh.nodes).view(np.uint32))
+    assert g2.bvh.layer_offsets == list(g1.bvh.layer_offsets)
+    g3 = loader.create_geometry_from_obj(demo.tiny(), cache_dir=d, read_bvh_cache=False, update_bvh_cache=False)
+    assert built == [3, 3] and len(g3.bvh) == len(g1.bvh)
+    g4 = loader.create_geometry_from_obj(sphere(5.0, 8), cache_dir=d, auto_build_bvh=False)   # bare Mesh
+    assert isinstance(g4, Geometry) and g4.bvh is None and len(g4.solids) == 1
+    g5 = loader.create_geometry_from_obj(Solid(sphere(5.0, 8), scenes.optics.water, scenes.optics.water),
+                                         cache_dir=d, update_bvh_cache=False)
+    assert len(g5.bvh) > len(g5.mesh.triangles)
+    assert cache.Cache(d).list_bvh(cache.mesh_hash(g5.mesh)) == []
+    with pytest.raises(TypeError):
+        loader.create_geometry_from_obj(42, cache_dir=d)
+    g6 = demo.tiny()
+    g6.bvh = 'kept'
+    assert loader.create_geometry_from_obj(g6, cache_dir=d).bvh == 'kept'

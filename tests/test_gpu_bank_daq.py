@@ -193,6 +193,22 @@ def test_bvh_build_matches_reference_kernels(gpu_ready):
             assert (np.abs(nodes2[:, :3].astype(np.int64) - nodes[:, :3].astype(np.int64)) % 65536 <= 1).mean() > 0.9
 
 
+def test_loader_builds_caches_and_reloads(gpu_ready, tmp_path):
+    """chroma/loader.py:162-199 end to end: build on the GPU, store, reload (memory-mapped) and propagate
+    with the reloaded tree -- same photons as with the freshly built one."""
+    from chroma_lite_b200 import loader, demo
+    d = str(tmp_path / 'cache')
+    g1 = loader.create_geometry_from_obj(demo.tiny, cache_dir=d)
+    g2 = loader.create_geometry_from_obj(demo.tiny, cache_dir=d)
+    assert np.array_equal(np.asarray(g2.bvh.nodes).view(np.uint32), g1.bvh.nodes.view(np.uint32))
+    ends = []
+    for g in (g1, g2):
+        gp = gpu.GPUPhotons(scenes.point_source(20000, seed=2, wl_range=(300, 600)))
+        gp.propagate(gpu.GPUDetector(g), gpu.get_rng_states(20000, seed=5), max_blocks=128, max_steps=20)
+        ends.append(gp.get())
+    assert np.array_equal(ends[0].flags, ends[1].flags) and np.array_equal(ends[0].pos, ends[1].pos)
+
+
 def test_bvh_is_conservative(gpu_ready):
     geo = scenes.tiny_detector()
     bvh = make_recursive_grid_bvh(geo.mesh)

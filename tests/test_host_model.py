@@ -65,16 +65,22 @@ def _ref_test_bvh():
 
 def test_unpack_nodes_known_answers():
     bvh = _ref_test_bvh()
-    u = unpack_nodes(bvh.get_layer(2))
+    u = unpack_nodes(bvh.get_layer(2).nodes)
     assert list(u['xlo']) == [0, 1, 0, 0] and list(u['xhi']) == [1, 2, 1, 1]
     assert list(u['ylo']) == [0, 0, 1, 0] and list(u['yhi']) == [1, 1, 2, 1]
     assert list(u['zlo']) == [0, 0, 0, 1] and list(u['zhi']) == [1, 1, 1, 2]
-    u = unpack_nodes(bvh.get_layer(1))
+    u = unpack_nodes(bvh.get_layer(1).nodes)
     assert list(u['xhi']) == [2, 1] and list(u['yhi']) == [1, 2] and list(u['child']) == [3, 5]
-    u = unpack_nodes(bvh.get_layer(0))
+    u = unpack_nodes(bvh.get_layer(0).nodes)
     assert list(u['xhi']) == [2] and list(u['child']) == [1]
     assert len(bvh) == 7 and bvh.layer_count() == 3
     assert [len(bvh.get_layer(i)) for i in range(3)] == [1, 2, 4]
+    # layer areas in world units (the reference's test_bvh.py:148-156)
+    assert np.isclose(bvh.get_layer(2).area(), 4 * 6 * 0.1 ** 2)
+    assert np.isclose(bvh.get_layer(1).area(), (4 * 2 + 2 + 4 * 2 + 2 * 4) * 0.1 ** 2)
+    assert np.isclose(bvh.get_layer(0).area(), 6 * 2 * 2 * 0.1 ** 2)
+    lo, hi = bvh.get_layer(0).get_bounds()
+    assert np.allclose(lo, [[-1, -1, -1]]) and np.allclose(hi, [[-0.8, -0.8, -0.8]])
 
 
 def test_world_coords_known_answers():
@@ -82,9 +88,10 @@ def test_world_coords_known_answers():
     w = [[-1.0, -0.9, 9.0], [1.0, 3.0, 5.0], [20.0, 30.0, 40.0]]
     assert np.array_equal(wc.world_to_fixed(w), [[0, 1, 100], [20, 40, 60], [210, 310, 410]])
     assert np.allclose(wc.fixed_to_world([[0, 1, 100]]), [[-1.0, -0.9, 9.0]], atol=1e-6)
-    with pytest.raises(ValueError):
+    from chroma_lite_b200.bvh import OutOfRangeError
+    with pytest.raises(OutOfRangeError):
         wc.world_to_fixed([-2.0, 0.0, 0.0])
-    with pytest.raises(ValueError):
+    with pytest.raises(OutOfRangeError):
         wc.world_to_fixed([0.0, 1e9, 0.0])
 
 
