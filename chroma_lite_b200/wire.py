@@ -90,3 +90,26 @@ def serve_rat(sim, address='ipc:///tmp/ipc_chroma', max_requests=None):
     while max_requests is None or served < max_requests:
         socket.send(handle_rat_request(sim, socket.recv()))
         served += 1
+
+
+# ---- bin/chroma-server:12-40: pickled Photons in, the propagated event out ----------------------
+def handle_photons_request(sim, msg, max_steps=1000):
+    """One request of the reference's plain photon server: ``msg`` is what zmq's send_pyobj puts on
+    the wire (a pickle of a Photons object), the reply is the pickle of the event simulate() yields
+    with photons_end kept (bin/chroma-server:31-40).  Like the reference this unpickles what it is
+    sent: bind it to trusted peers only."""
+    import pickle
+    photons_in = pickle.loads(msg)
+    ev = next(sim.simulate(photons_in, keep_photons_end=True, max_steps=max_steps))
+    return pickle.dumps(ev, pickle.HIGHEST_PROTOCOL)
+
+
+def serve_photons(sim, address='tcp://*:5024', max_requests=None):
+    """ZeroMQ REP loop of bin/chroma-server (needs pyzmq)."""
+    import zmq
+    socket = zmq.Context.instance().socket(zmq.REP)
+    socket.bind(address)
+    served = 0
+    while max_requests is None or served < max_requests:
+        socket.send(handle_photons_request(sim, socket.recv()))
+        served += 1

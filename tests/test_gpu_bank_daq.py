@@ -334,3 +334,20 @@ def test_rat_bridge_request(gpu_ready):
     assert np.array_equal(hits.t, ev.flat_hits.t[order]) and np.array_equal(hits.pos, ev.flat_hits.pos[order])
     empty, _ = wire.decode_rat_reply(wire.handle_rat_request(s1, wire.encode_rat_request(ph[:0], event_id=1)))
     assert len(empty) == 0
+
+
+def test_photon_server_request(gpu_ready):
+    """bin/chroma-server:31-40: a pickled Photons object in, the pickled event with photons_end out."""
+    import pickle
+    from chroma_lite_b200 import sim, wire
+    det = scenes.tiny_detector()
+    ph = scenes.point_source(30000, seed=17, wl_range=(300, 600))
+    s1 = sim.Simulation(det, seed=4, nthreads_per_block=256, max_blocks=128)
+    ev = pickle.loads(wire.handle_photons_request(s1, pickle.dumps(ph), max_steps=100))
+    s2 = sim.Simulation(det, seed=4, nthreads_per_block=256, max_blocks=128)
+    ref = next(s2.simulate(ph, keep_photons_end=True, max_steps=100))
+    assert len(ev.photons_end) == 30000 and ev.photons_beg is None
+    assert np.array_equal(ev.photons_end.flags, ref.photons_end.flags)
+    assert np.array_equal(ev.photons_end.pos, ref.photons_end.pos)
+    assert np.array_equal(ev.flat_hits.channel, ref.flat_hits.channel)
+

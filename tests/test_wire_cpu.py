@@ -46,3 +46,16 @@ def test_reply_groups_hits_by_channel_like_the_reference():
     # empty reply
     empty, evid = wire.decode_rat_reply(wire.encode_rat_reply(event.Photons(channel=np.zeros(0, np.uint32)), 9))
     assert len(empty) == 0 and evid == 9
+
+
+def test_photon_server_frames_without_gpu():
+    """bin/chroma-server's pickled request/reply around a stand-in simulation (host logic only)."""
+    import pickle
+
+    class EchoSim(object):
+        def simulate(self, photons, keep_photons_end=False, max_steps=1000, **kw):
+            assert keep_photons_end and max_steps == 7
+            yield event.Event(photons_end=photons)
+    ph = scenes.point_source(50, seed=2)
+    ev = pickle.loads(wire.handle_photons_request(EchoSim(), pickle.dumps(ph), max_steps=7))
+    assert isinstance(ev, event.Event) and np.array_equal(ev.photons_end.dir, ph.dir)
