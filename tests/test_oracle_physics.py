@@ -122,3 +122,65 @@ def test_oracle_wire_planes_geometry():
     sel = on_wire & hit
     z_expected = -np.sqrt(0.3 ** 2 - dy[sel].astype(np.float64) ** 2)
     assert np.allclose(bank.pos[sel, 2], z_expected, atol=2e-4)
+
+
+# ---- pins against the reference's own kernels ------------------------------------------------------
+# tests/golden/ref_kernel_histories.npz holds the end states the REFERENCE's propagate / run_daq kernels
+# produced on a B200 for the cases of tests/golden/ref_kernel_cases.py (generator:
+# tests/golden/make_golden_gpu.py).  The oracle must replay them: identical history flags, last-hit
+# triangles and RNG streams, positions/times to float tolerance (libm here vs --use_fast_math there).
+import os
+import sys
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden'))
+from ref_kernel_cases import CASES, build   # noqa: E402
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'ref_kernel_histories.npz')
+# fraction of photons whose whole history must be identical; measured 1.0 except for the transparent
+# wires, where a photon bouncing inside a wire can take a different number of bounces (99.7 %)
+MIN_SAME = {'sphere': 0.999, 'tiny': 0.999, 'scint': 0.995, 'weights': 0.998, 'wires': 0.99, 'one_step': 1.0}
+
+
+@pytest.mark.parametrize('name', sorted(CASES))
+def test_oracle_replays_reference_kernel_histories(name):
+    g, c = np.load(GOLD), CASES[name]
+    geo, ph = build(name)
+    # the inputs are rebuilt from seeds: make sure they are the ones the fixture was made with
+    assert np.allclose(np.asarray(ph.dir, np.float32).sum(axis=0, dtype=np.float64), g[name + '.input_dir_sum'])
+    assert len(geo.mesh.triangles) == g[name + '.ntriangles']
+    desc, keep = scenes.desc_of(geo)
+    states = orc.rng_init(c['rng_seed'], 0, c['n'])
+    bank, _ = orc.propagate(desc, ph, states, max_steps=c['max_steps'], use_weights=c['use_weights'],
+                            scatter_first=c['scatter_first'])
+    ref = {f: g['%s.%s' % (name, f)] for f in ('pos', 't', 'wavelengths', 'weights', 'flags', 'last_hit_triangles', 'rng')}
+    same = (bank.flags == ref['flags']) & (bank.last_hit_triangles == ref['last_hit_triangles'])
+    assert same.mean() >= MIN_SAME[name], 'only %.5f identical histories' % same.mean()
+    # RNG pool after the call: identical draws were consumed (a same-flags photon can still differ by a
+    # bounce count in the scintillator / wires cases)
+    assert (states[same] == ref['rng'][same]).all(axis=1).mean() > (0.999 if name != 'wires' else 0.97)
+    scale = np.maximum(np.abs(ref['pos'][same]).max(axis=1), 1.0)
+    assert (np.abs(bank.pos[same] - ref['pos'][same]).max(axis=1) / scale < 1e-3).mean() > (0.999 if name != 'wires' else 0.97)
+    assert np.isclose(bank.t[same], ref['t'][same], rtol=1e-4, atol=1e-3).mean() > (0.999 if name != 'wires' else 0.97)
+    assert np.allclose(bank.wavelengths[same], ref['wavelengths'][same], rtol=1e-5)
+    assert np.allclose(bank.weights[same], ref['weights'][same], rtol=1e-3, atol=1e-6)
+    if name == 'scint':      # the case exists to exercise re-emission, WLS, dichroic / thin-film transmission
+        for bit in (event.BULK_REEMIT, event.SURFACE_REEMIT, event.SURFACE_TRANSMIT, event.SURFACE_DETECT):
+            assert ((ref['flags'] & bit) != 0).sum() > 30
+    if name == 'wires':
+        assert (ref['last_hit_triangles'] == -2).sum() > 30
+
+
+def test_oracle_daq_replays_reference_kernel():
+    """run_daq of the reference (daq.cu:35-86) on the reference's end state of the 'tiny' case."""
+    g, c = np.load(GOLD), CASES['tiny']
+    geo, _ = build('tiny')
+    end = event.Photons(*[g['tiny.' + f] for f in ('pos', 'dir', 'pol', 'wavelengths', 't', 'last_hit_triangles',
+                                                    'flags', 'weights')])
+    tint, qint, hist, unit = orc.run_daq(orc.HostBank(end), orc.rng_init(c['daq_seed'], 0, c['n']), geo, geo.solid_id)
+    assert np.array_equal(hist, g['tiny.daq_flags'])
+    # integer charge: the GPU divides by charge_unit approximately (+-1 count per hit at most)
+    assert np.abs(qint.astype(np.int64) - g['tiny.daq_q_int'].astype(np.int64)).max() <= 3
+    assert np.allclose(tint.view(np.float32), g['tiny.daq_t'], rtol=1e-6)
+    hit = g['tiny.daq_t'] < 1e8
+    assert hit.sum() > 10 and np.array_equal(hit, tint.view(np.float32) < 1e8)
