@@ -97,6 +97,7 @@ SIGNATURES = {
     'cb_detector_attach': (C.c_int, [u64, vp, u64, i32, vp, vp, i32, vp, vp, i32, f32]),
     'cb_bvh_build': (C.c_int, [vp, u64, vp, u64, i32, _P(f32 * 3), _P(f32), vp, _P(u64), vp, _P(i32)]),
     'cb_native_tree_build': (C.c_int, [vp, u64, u64, vp, vp, _P(u64)]),
+    'cb_native_tree_build_split': (C.c_int, [vp, u64, u64, vp, vp, vp, vp, f32, i32, i32, f32, vp, _P(u64)]),
     'cb_rng_create': (C.c_int, [u64, u64, u64, _P(u64)]),
     'cb_rng_destroy': (C.c_int, [u64]),
     'cb_rng_size': (C.c_int, [u64, _P(u64)]),

@@ -126,16 +126,30 @@ def make_recursive_grid_bvh(mesh, target_degree=3):
     return BVH(WorldCoords(np.array(list(origin), dtype=np.float32), scale.value), nodes, layers.astype(np.int64))
 
 
-def native_tree(nodes, ntriangles, solid_id=None):
+def native_tree(nodes, ntriangles, solid_id=None, mesh=None, world_coords=None, max_pieces=0, min_extent=8,
+                min_ratio=2.0):
     """The engine's own traversal tree (uint4 entries, root at 0) for a
-    reference-format tree; host-only helper around cb_native_tree_build."""
+    reference-format tree; host-only helper around cb_native_tree_build.  With ``mesh``,
+    ``world_coords`` and ``max_pieces`` > 1 loosely bounded triangles are referenced by several
+    leaves with tighter boxes (cb_native_tree_build_split)."""
     lib = _lib.load()
     nodes = np.ascontiguousarray(nodes)
     sid = None if solid_id is None else np.ascontiguousarray(solid_id, dtype=np.uint32)
+    sid_p = sid.ctypes.data if sid is not None else None
     count = C.c_uint64()
-    _lib.check(lib.cb_native_tree_build(nodes.ctypes.data, len(nodes), int(ntriangles),
-                                        sid.ctypes.data if sid is not None else None, None, C.byref(count)))
+    if mesh is not None and max_pieces > 1:
+        v = np.ascontiguousarray(mesh.vertices, dtype=np.float32)
+        t = np.ascontiguousarray(mesh.triangles, dtype=np.uint32)
+        origin = np.ascontiguousarray(world_coords.world_origin, dtype=np.float32)
+
+        def call(out):
+            return lib.cb_native_tree_build_split(nodes.ctypes.data, len(nodes), int(ntriangles), sid_p, v.ctypes.data,
+                                                  t.ctypes.data, origin.ctypes.data, float(world_coords.world_scale),
+                                                  int(max_pieces), int(min_extent), float(min_ratio), out, C.byref(count))
+    else:
+        def call(out):
+            return lib.cb_native_tree_build(nodes.ctypes.data, len(nodes), int(ntriangles), sid_p, out, C.byref(count))
+    _lib.check(call(None))
     out = np.empty(count.value, dtype=uint4)
-    _lib.check(lib.cb_native_tree_build(nodes.ctypes.data, len(nodes), int(ntriangles),
-                                        sid.ctypes.data if sid is not None else None, out.ctypes.data, C.byref(count)))
+    _lib.check(call(out.ctypes.data))
     return out

@@ -20,6 +20,7 @@
 #include <atomic>
 #include <thread>
 #include <string.h>
+#include <math.h>
 
 namespace cb {
 
@@ -181,12 +182,166 @@ struct Builder {
     }
 };
 
+// ---- optional leaf splitting ("early split clipping") -------------------------------------
+// A long triangle that lies obliquely to the axes has a box many times its own size (a PMT
+// lathed with 6 steps: every ray that enters a PMT's box tests ~27 triangles, a ray that
+// grazes one without hitting anything ~66).  With SplitInput::max_pieces > 1 such a leaf is
+// replaced by up to max_pieces leaves of the SAME triangle, each bounding the part of the
+// triangle inside one cell of a recursive midpoint subdivision of the leaf box (the triangle
+// is clipped in double precision on the world grid, boxes are rounded outward with the
+// reference's one-quantum padding, bvh.cu:148-203, and clamped to the reference leaf box).
+// Exactness is unaffected: a hit point lies in the triangle, hence in one of the pieces'
+// boxes, so the triangle is still tested whenever the ray can hit it, and testing it twice
+// returns the same (distance, rank).  finish() keeps checking the reference leaf box, which
+// comes from the tri64 record, not from the tree.
+struct SplitInput {
+    const float* vertices;        // world-space, 3 floats per vertex
+    const uint32_t* triangles;    // 3 indices per triangle
+    float origin[3], scale;       // world grid (WorldCoords)
+    int max_pieces;               // <= 1: no splitting
+    int min_extent;               // boxes whose longest side is shorter (grid quanta) are kept whole
+    double min_ratio;             // split only while box area > min_ratio * (2 x triangle-part area + rim)
+};
+
+constexpr int POLY_MAX = 16;   // a triangle clipped to a box has <= 9 corners; points on a plane can repeat
+struct Poly { int n; double p[POLY_MAX][3]; };
+
+// false when the result does not fit (the caller then keeps the piece whole)
+static bool clip_poly(const Poly& in, int axis, double plane, bool keep_below, Poly& out)
+{
+    out.n = 0;
+    for (int i = 0; i < in.n; i++) {
+        const double* a = in.p[i];
+        const double* b = in.p[(i + 1) % in.n];
+        const bool ina = keep_below ? a[axis] <= plane : a[axis] >= plane;
+        const bool inb = keep_below ? b[axis] <= plane : b[axis] >= plane;
+        if (ina) {
+            if (out.n == POLY_MAX) return false;
+            memcpy(out.p[out.n++], a, sizeof(double) * 3);
+        }
+        if (ina != inb) {
+            if (out.n == POLY_MAX) return false;
+            const double t = (plane - a[axis]) / (b[axis] - a[axis]);
+            double* q = out.p[out.n++];
+            for (int k = 0; k < 3; k++) q[k] = a[k] + t * (b[k] - a[k]);
+            q[axis] = plane;
+        }
+    }
+    return true;
+}
+
+static double poly_area(const Poly& P)
+{
+    double ax = 0, ay = 0, az = 0;
+    for (int i = 1; i + 1 < P.n; i++) {
+        const double u[3] = {P.p[i][0] - P.p[0][0], P.p[i][1] - P.p[0][1], P.p[i][2] - P.p[0][2]};
+        const double v[3] = {P.p[i + 1][0] - P.p[0][0], P.p[i + 1][1] - P.p[0][1], P.p[i + 1][2] - P.p[0][2]};
+        ax += u[1] * v[2] - u[2] * v[1]; ay += u[2] * v[0] - u[0] * v[2]; az += u[0] * v[1] - u[1] * v[0];
+    }
+    return 0.5 * sqrt(ax * ax + ay * ay + az * az);
+}
+
+// padded grid box of a polygon, clamped to `within`
+static IBox poly_box(const Poly& P, const IBox& within)
+{
+    IBox b;
+    for (int a = 0; a < 3; a++) {
+        double lo = P.p[0][a], hi = P.p[0][a];
+        for (int i = 1; i < P.n; i++) { lo = std::min(lo, P.p[i][a]); hi = std::max(hi, P.p[i][a]); }
+        b.lo[a] = std::max(within.lo[a], (int)floor(lo) - 1);
+        b.hi[a] = std::min(within.hi[a], (int)floor(hi) + 1);
+        if (b.hi[a] < b.lo[a]) b.hi[a] = b.lo[a];
+    }
+    return b;
+}
+
+struct Piece { Poly poly; IBox box; double area; bool done; };
+
+// pieces of one leaf (appended to out); returns the number of pieces
+static int split_leaf(const Entry& leaf, const SplitInput& S, std::vector<Entry>& out)
+{
+    IBox L;
+    box_of(leaf, L.lo, L.hi);
+    const uint32_t tri = leaf.w & 0x0FFFFFFFu;
+    Piece pc[32];
+    int np = 1;
+    const int maxp = std::min(S.max_pieces, 32);
+    for (int v = 0; v < 3; v++) {
+        const float* x = S.vertices + 3ull * S.triangles[3ull * tri + v];
+        for (int a = 0; a < 3; a++) pc[0].poly.p[v][a] = ((double)x[a] - (double)S.origin[a]) / (double)S.scale;
+    }
+    pc[0].poly.n = 3;
+    pc[0].box = L;
+    pc[0].area = poly_area(pc[0].poly);
+    pc[0].done = false;
+    while (np < maxp) {
+        // refine the piece with the largest box that is still worth splitting
+        int pick = -1;
+        double pa = 0.0;
+        for (int i = 0; i < np; i++) {
+            if (pc[i].done) continue;
+            const IBox& b = pc[i].box;
+            const int ex = std::max(b.hi[0] - b.lo[0], std::max(b.hi[1] - b.lo[1], b.hi[2] - b.lo[2]));
+            // a flat axis-aligned part has a box of 2 x its area + a rim from the padding
+            const double rim = 4.0 * ((b.hi[0] - b.lo[0]) + (b.hi[1] - b.lo[1]) + (b.hi[2] - b.lo[2]));
+            const double tight = 2.0 * pc[i].area + rim;
+            if (ex < std::max(S.min_extent, 4) || 2.0 * b.area() <= S.min_ratio * tight) { pc[i].done = true; continue; }
+            if (b.area() > pa) { pa = b.area(); pick = i; }
+        }
+        if (pick < 0) break;
+        Piece& P = pc[pick];
+        int axis = 0;
+        for (int a = 1; a < 3; a++) if (P.box.hi[a] - P.box.lo[a] > P.box.hi[axis] - P.box.lo[axis]) axis = a;
+        const double plane = (double)((P.box.lo[axis] + P.box.hi[axis]) / 2);
+        Piece A, B;
+        if (!clip_poly(P.poly, axis, plane, true, A.poly) || !clip_poly(P.poly, axis, plane, false, B.poly) ||
+            A.poly.n < 3 || B.poly.n < 3) { P.done = true; continue; }
+        A.box = poly_box(A.poly, P.box); B.box = poly_box(B.poly, P.box);
+        A.area = poly_area(A.poly); B.area = poly_area(B.poly);
+        A.done = B.done = false;
+        if (A.box.area() + B.box.area() > 0.9 * P.box.area()) { P.done = true; continue; }   // no gain
+        pc[pick] = A;
+        pc[np++] = B;
+    }
+    for (int i = 0; i < np; i++) out.push_back(Builder::pack(pc[i].box, leaf.w));
+    return np;
+}
+
+// Replace `leaves` by their pieces (parallel over host threads, order preserved).
+static void presplit_leaves(std::vector<Entry>& leaves, const SplitInput& S)
+{
+    const uint64_t n = leaves.size();
+    unsigned nthreads = std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
+    if (n < 4096) nthreads = 1;
+    std::vector<std::vector<Entry>> part(nthreads);
+    auto worker = [&](unsigned t) {
+        const uint64_t b = n * t / nthreads, e = n * (t + 1) / nthreads;
+        part[t].reserve((e - b) * 2);
+        for (uint64_t i = b; i < e; i++) split_leaf(leaves[i], S, part[t]);
+    };
+    std::vector<std::thread> pool;
+    for (unsigned t = 1; t < nthreads; t++) pool.emplace_back(worker, t);
+    worker(0);
+    for (auto& t : pool) t.join();
+    uint64_t total = 0;
+    for (auto& p : part) total += p.size();
+    std::vector<Entry> all;
+    all.reserve(total);
+    for (auto& p : part) { all.insert(all.end(), p.begin(), p.end()); std::vector<Entry>().swap(p); }
+    leaves.swap(all);
+}
+
 // Build the native tree.  leaves: one reference leaf entry per triangle that the
 // reference tree can reach; solid_of[tri] (may be null) groups triangles.
 // Returns entries in `nodes` (root at 0).
-int build_native_tree(std::vector<Entry>& leaves, const uint32_t* solid_of, std::vector<Entry>& nodes)
+int build_native_tree(std::vector<Entry>& leaves, const uint32_t* solid_of, std::vector<Entry>& nodes,
+                      const SplitInput* split)
 {
+    if (split && split->max_pieces > 1 && split->vertices && split->triangles && !leaves.empty())
+        presplit_leaves(leaves, *split);
     const uint64_t n = leaves.size();
+    if (2 * n + n / 4 + 64 * ARENA_CHUNK >= (1ull << 28))
+        return fail(CB_ERR_INVALID, "native BVH: too many leaf entries for the 28-bit child field (lower the split count)");
     nodes.clear();
     if (n == 0) { nodes.push_back(Entry{0, 0, 0, 0}); return CB_OK; }
     // group by solid (stable counting sort keeps triangle order inside a solid)

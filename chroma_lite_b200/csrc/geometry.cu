@@ -9,7 +9,28 @@
 namespace cb {
 
 struct Entry { uint32_t x, y, z, w; };
-int build_native_tree(std::vector<Entry>& leaves, const uint32_t* solid_of, std::vector<Entry>& nodes);
+struct SplitInput {               // bvh_native.cu: optional splitting of loosely bounded leaves
+    const float* vertices;
+    const uint32_t* triangles;
+    float origin[3], scale;
+    int max_pieces, min_extent;
+    double min_ratio;
+};
+int build_native_tree(std::vector<Entry>& leaves, const uint32_t* solid_of, std::vector<Entry>& nodes,
+                      const SplitInput* split);
+
+// CHROMA_B200_LEAF_SPLIT=<max pieces per triangle>[,<min extent in grid quanta>[,<min box/part area ratio>]]
+// turns leaf splitting on (default: off, one leaf per triangle).
+static bool split_from_env(SplitInput& s)
+{
+    const char* e = getenv("CHROMA_B200_LEAF_SPLIT");
+    s.max_pieces = 0; s.min_extent = 8; s.min_ratio = 2.0;
+    if (!e || !*e) return false;
+    double r = s.min_ratio;
+    int n = sscanf(e, "%d,%d,%lf", &s.max_pieces, &s.min_extent, &r);
+    if (n >= 3) s.min_ratio = r;
+    return n >= 1 && s.max_pieces > 1;
+}
 
 // Pack triangles for the traversal: 64 B = 4 x float4 per triangle holding the
 // three world-space vertices, the reference test rank (tie-break, SURVEY A-1),
@@ -202,7 +223,11 @@ int cb_geometry_create(const CbGeometryDesc* d, cb_geom_t* out)
     if (!use_reference_tree && d->ntriangles > 0) {
         std::vector<Entry> leaves;
         collect_reference_leaves(d->nodes, d->nnodes, d->ntriangles, rank, leaves);
-        rc = build_native_tree(leaves, d->solid_id, native);
+        SplitInput split;
+        const bool do_split = split_from_env(split);
+        split.vertices = d->vertices; split.triangles = d->triangles; split.scale = d->world_scale;
+        for (int a = 0; a < 3; a++) split.origin[a] = d->world_origin[a];
+        rc = build_native_tree(leaves, d->solid_id, native, do_split ? &split : nullptr);
         if (rc != CB_OK) { free_geometry(g); return rc; }
         native.resize(native.size() + 16, Entry{0, 0, 0, 0});
         cudaError_t e = cudaMalloc((void**)&g->native_nodes, native.size() * sizeof(Entry));
@@ -451,8 +476,9 @@ static void build_layers(std::vector<uint32_t>& leaf_nodes, std::vector<uint64_t
 
 // Host-only: the engine's traversal tree for a reference-format tree (test / tooling hook;
 // needs no GPU).  Two-call protocol: out_nodes == NULL returns the entry count only.
-extern "C" int cb_native_tree_build(const uint32_t* ref_nodes, uint64_t nnodes, uint64_t ntriangles,
-                                    const uint32_t* solid_id, uint32_t* out_nodes, uint64_t* out_count)
+static int native_tree_two_call(const uint32_t* ref_nodes, uint64_t nnodes, uint64_t ntriangles,
+                                const uint32_t* solid_id, const SplitInput* split, uint32_t* out_nodes,
+                                uint64_t* out_count)
 {
     static std::vector<Entry> cached;
     if (!ref_nodes || nnodes == 0 || !out_count) return fail(CB_ERR_INVALID, "cb_native_tree_build: bad arguments");
@@ -467,7 +493,7 @@ extern "C" int cb_native_tree_build(const uint32_t* ref_nodes, uint64_t nnodes, 
     reference_test_rank(ref_nodes, nnodes, ntriangles, rank);
     std::vector<Entry> leaves;
     collect_reference_leaves(ref_nodes, nnodes, ntriangles, rank, leaves);
-    int rc = build_native_tree(leaves, solid_id, cached);
+    int rc = build_native_tree(leaves, solid_id, cached, split);
     if (rc != CB_OK) return rc;
     *out_count = cached.size();
     if (out_nodes) {
@@ -475,6 +501,27 @@ extern "C" int cb_native_tree_build(const uint32_t* ref_nodes, uint64_t nnodes, 
         cached.clear();
     }
     return CB_OK;
+}
+
+extern "C" int cb_native_tree_build(const uint32_t* ref_nodes, uint64_t nnodes, uint64_t ntriangles,
+                                    const uint32_t* solid_id, uint32_t* out_nodes, uint64_t* out_count)
+{
+    return native_tree_two_call(ref_nodes, nnodes, ntriangles, solid_id, nullptr, out_nodes, out_count);
+}
+
+extern "C" int cb_native_tree_build_split(const uint32_t* ref_nodes, uint64_t nnodes, uint64_t ntriangles,
+                                          const uint32_t* solid_id, const float* vertices,
+                                          const uint32_t* triangles, const float world_origin[3],
+                                          float world_scale, int32_t max_pieces, int32_t min_extent,
+                                          float min_ratio, uint32_t* out_nodes, uint64_t* out_count)
+{
+    if (!vertices || !triangles || !world_origin || !(world_scale > 0.0f))
+        return fail(CB_ERR_INVALID, "cb_native_tree_build_split: mesh and world grid are required");
+    SplitInput s;
+    s.vertices = vertices; s.triangles = triangles; s.scale = world_scale;
+    for (int a = 0; a < 3; a++) s.origin[a] = world_origin[a];
+    s.max_pieces = max_pieces; s.min_extent = min_extent; s.min_ratio = min_ratio;
+    return native_tree_two_call(ref_nodes, nnodes, ntriangles, solid_id, &s, out_nodes, out_count);
 }
 
 extern "C" int cb_bvh_build(const float* vertices, uint64_t nvertices, const uint32_t* triangles,

@@ -220,6 +220,18 @@ int cb_bvh_build(const float* vertices, uint64_t nvertices,
  * its build tree directly, chroma/cuda/mesh.h:45-126). */
 int cb_native_tree_build(const uint32_t* ref_nodes, uint64_t nnodes, uint64_t ntriangles,
                          const uint32_t* solid_id, uint32_t* out_nodes, uint64_t* out_count);
+/* Same, with leaf splitting: a triangle whose box is much larger than the triangle (long
+ * and oblique to the axes) is referenced by up to max_pieces leaves, each bounding the part
+ * of the triangle inside one cell of its leaf box (boxes on the world grid of
+ * world_origin / world_scale).  min_extent: shortest box side (grid quanta) worth splitting;
+ * min_ratio: split while the box surface exceeds min_ratio x the surface of a tight box.
+ * cb_geometry_create does the same when CHROMA_B200_LEAF_SPLIT=max_pieces[,min_extent[,min_ratio]]
+ * is set (default: one leaf per triangle).  Results of a traversal are unchanged. */
+int cb_native_tree_build_split(const uint32_t* ref_nodes, uint64_t nnodes, uint64_t ntriangles,
+                               const uint32_t* solid_id, const float* vertices,
+                               const uint32_t* triangles, const float world_origin[3],
+                               float world_scale, int32_t max_pieces, int32_t min_extent,
+                               float min_ratio, uint32_t* out_nodes, uint64_t* out_count);
 
 /* ---- RNG ---------------------------------------------------------------- */
 /* replaces get_rng_states / init_rng (chroma/gpu/tools.py:117-145,

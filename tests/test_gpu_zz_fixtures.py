@@ -50,3 +50,45 @@ def test_engine_replays_reference_kernel_fixture(gpu_ready, name):
         assert np.array_equal(daq.channel_q_int_gpu.get(), g[name + '.daq_q_int'])
         assert np.array_equal(daq.earliest_time_int_gpu.get(), g[name + '.daq_time_int'])
         assert np.array_equal(ch.t, g[name + '.daq_t']) and np.array_equal(ch.q, g[name + '.daq_q'])
+
+
+def test_leaf_split_tree_gives_identical_results(gpu_ready, monkeypatch):
+    """CHROMA_B200_LEAF_SPLIT (bvh_native.cu: several tighter leaves per loosely bounded triangle) changes
+    the traversal tree only: nearest hits (triangle and distance, ties included) and whole propagations
+    are bit-identical to the one-leaf-per-triangle tree."""
+    from chroma_lite_b200.sample import uniform_sphere
+    geo = scenes.tiny_detector()
+    rng = np.random.default_rng(3)
+    n = 200000
+    lo, hi = geo.mesh.get_bounds()
+    o = ((lo + hi) / 2 + rng.uniform(-0.55, 0.55, (n, 3)) * (hi - lo)).astype(np.float32)
+    d = uniform_sphere(n, rng=rng).astype(np.float32)
+    # rays aimed at triangle corners and edge midpoints: distance ties between neighbouring triangles
+    verts = geo.mesh.assemble()
+    pick = rng.integers(0, len(verts), 20000)
+    corner = verts[pick, rng.integers(0, 3, 20000)]
+    mid = (verts[pick, 0] + verts[pick, 1]) / 2
+    aim = np.concatenate([corner, mid]).astype(np.float32)
+    o = np.concatenate([o, np.tile(np.array([[3.0, -2.0, 1.0]], np.float32), (len(aim), 1))])
+    d = np.concatenate([d, aim - o[n:]]).astype(np.float32)
+    ph = scenes.point_source(60000, seed=6, wl_range=(300, 600))
+    results = []
+    for spec in (None, '4,8,8', '16,4,1.5'):
+        if spec is None:
+            monkeypatch.delenv('CHROMA_B200_LEAF_SPLIT', raising=False)
+        else:
+            monkeypatch.setenv('CHROMA_B200_LEAF_SPLIT', spec)
+        g = gpu.GPUDetector(geo)
+        tri, dist = gpu.intersect_mesh(g, o, d)
+        gp = gpu.GPUPhotons(ph)
+        gp.propagate(g, gpu.get_rng_states(len(ph), seed=12), nthreads_per_block=256, max_blocks=(len(ph) + 255) // 256,
+                     max_steps=100)
+        results.append((tri.get(), dist.get(), gp.get(), g.gpudata if hasattr(g, 'gpudata') else None))
+    monkeypatch.delenv('CHROMA_B200_LEAF_SPLIT', raising=False)
+    tri0, dist0, end0, _ = results[0]
+    assert (tri0 >= 0).mean() > 0.3
+    for tri, dist, end, _ in results[1:]:
+        assert np.array_equal(tri, tri0)
+        assert np.array_equal(dist.view(np.uint32), dist0.view(np.uint32))
+        for f in ('pos', 'dir', 'pol', 't', 'wavelengths', 'flags', 'last_hit_triangles'):
+            assert np.array_equal(getattr(end, f), getattr(end0, f)), f
