@@ -50,32 +50,69 @@ struct Range { uint64_t b, e; IBox box; };
 constexpr int NBINS = 16;
 constexpr int WIDE = 8;
 
+// run fn(t, lo, hi) over [b,e) cut into nthreads contiguous chunks
+template <class F>
+static void parallel_chunks(uint64_t b, uint64_t e, unsigned nthreads, F fn)
+{
+    if (nthreads <= 1 || e - b < (1u << 16)) { fn(0u, b, e); return; }
+    std::vector<std::thread> pool;
+    const uint64_t n = e - b;
+    for (unsigned t = 1; t < nthreads; t++) pool.emplace_back(fn, t, b + n * t / nthreads, b + n * (t + 1) / nthreads);
+    fn(0u, b, b + n / nthreads);
+    for (auto& th : pool) th.join();
+}
+
 // Binned SAH split of prims[b,e) (partitioned in place).  Returns the split point.
-static uint64_t sah_split(Entry* prims, uint64_t b, uint64_t e, IBox& left, IBox& right)
+// nthreads > 1: the passes over a large range run on that many host threads (the top of a
+// single-level build over tens of millions of leaves).
+static uint64_t sah_split(Entry* prims, uint64_t b, uint64_t e, IBox& left, IBox& right, unsigned nthreads = 1)
 {
     const uint64_t n = e - b;
+    if (n < (1u << 18)) nthreads = 1;
+    const unsigned T = std::max(1u, nthreads);
     int clo[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff}, chi[3] = {-1, -1, -1};
-    for (uint64_t i = b; i < e; i++) {
-        int lo[3], hi[3];
-        box_of(prims[i], lo, hi);
-        for (int a = 0; a < 3; a++) { int c = lo[a] + hi[a]; clo[a] = std::min(clo[a], c); chi[a] = std::max(chi[a], c); }
+    {
+        std::vector<int> plo(3 * T, 0x7fffffff), phi(3 * T, -1);
+        parallel_chunks(b, e, T, [&](unsigned t, uint64_t lo_i, uint64_t hi_i) {
+            int l3[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff}, h3[3] = {-1, -1, -1};
+            for (uint64_t i = lo_i; i < hi_i; i++) {
+                int lo[3], hi[3];
+                box_of(prims[i], lo, hi);
+                for (int a = 0; a < 3; a++) { int c = lo[a] + hi[a]; l3[a] = std::min(l3[a], c); h3[a] = std::max(h3[a], c); }
+            }
+            for (int a = 0; a < 3; a++) { plo[3 * t + a] = l3[a]; phi[3 * t + a] = h3[a]; }
+        });
+        for (unsigned t = 0; t < T; t++)
+            for (int a = 0; a < 3; a++) { clo[a] = std::min(clo[a], plo[3 * t + a]); chi[a] = std::max(chi[a], phi[3 * t + a]); }
     }
+    // one pass bins all three axes
+    struct Bins { IBox bb[3][NBINS]; uint64_t cnt[3][NBINS]; };
+    double scale3[3];
+    for (int a = 0; a < 3; a++) scale3[a] = (double)NBINS / ((double)(chi[a] - clo[a]) + 1.0);
+    std::vector<Bins> bins(T);
+    for (auto& B : bins)
+        for (int a = 0; a < 3; a++) for (int k = 0; k < NBINS; k++) { B.bb[a][k].reset(); B.cnt[a][k] = 0; }
+    parallel_chunks(b, e, T, [&](unsigned t, uint64_t lo_i, uint64_t hi_i) {
+        Bins& B = bins[t];
+        for (uint64_t i = lo_i; i < hi_i; i++) {
+            int lo[3], hi[3];
+            box_of(prims[i], lo, hi);
+            for (int a = 0; a < 3; a++) {
+                int k = (int)((double)(lo[a] + hi[a] - clo[a]) * scale3[a]);
+                k = std::min(std::max(k, 0), NBINS - 1);
+                B.bb[a][k].grow(lo, hi);
+                B.cnt[a][k]++;
+            }
+        }
+    });
+    for (unsigned t = 1; t < T; t++)
+        for (int a = 0; a < 3; a++) for (int k = 0; k < NBINS; k++) { bins[0].bb[a][k].grow(bins[t].bb[a][k]); bins[0].cnt[a][k] += bins[t].cnt[a][k]; }
     double best = 1e300;
     int best_axis = -1, best_bin = -1;
     for (int a = 0; a < 3; a++) {
         if (chi[a] == clo[a]) continue;
-        const double scale = (double)NBINS / ((double)(chi[a] - clo[a]) + 1.0);
-        IBox bb[NBINS];
-        uint64_t cnt[NBINS];
-        for (int k = 0; k < NBINS; k++) { bb[k].reset(); cnt[k] = 0; }
-        for (uint64_t i = b; i < e; i++) {
-            int lo[3], hi[3];
-            box_of(prims[i], lo, hi);
-            int k = (int)((double)(lo[a] + hi[a] - clo[a]) * scale);
-            k = std::min(std::max(k, 0), NBINS - 1);
-            bb[k].grow(lo, hi);
-            cnt[k]++;
-        }
+        const IBox* bb = bins[0].bb[a];
+        const uint64_t* cnt = bins[0].cnt[a];
         double ra[NBINS];
         uint64_t rc[NBINS];
         IBox acc; acc.reset();
@@ -94,7 +131,7 @@ static uint64_t sah_split(Entry* prims, uint64_t b, uint64_t e, IBox& left, IBox
         mid = b + n / 2;                              // all centroids coincide: split by index
     } else {
         const int a = best_axis;
-        const double scale = (double)NBINS / ((double)(chi[a] - clo[a]) + 1.0);
+        const double scale = scale3[a];
         Entry* m = std::partition(prims + b, prims + e, [&](const Entry& p) {
             int lo[3], hi[3];
             box_of(p, lo, hi);
@@ -105,9 +142,19 @@ static uint64_t sah_split(Entry* prims, uint64_t b, uint64_t e, IBox& left, IBox
         mid = (uint64_t)(m - prims);
         if (mid == b || mid == e) mid = b + n / 2;
     }
-    left.reset(); right.reset();
-    for (uint64_t i = b; i < mid; i++) { int lo[3], hi[3]; box_of(prims[i], lo, hi); left.grow(lo, hi); }
-    for (uint64_t i = mid; i < e; i++) { int lo[3], hi[3]; box_of(prims[i], lo, hi); right.grow(lo, hi); }
+    auto bound = [&](uint64_t lo_i, uint64_t hi_i, IBox& out) {
+        std::vector<IBox> part(T);
+        for (auto& bx : part) bx.reset();
+        parallel_chunks(lo_i, hi_i, T, [&](unsigned t, uint64_t x, uint64_t y) {
+            IBox bx; bx.reset();
+            for (uint64_t i = x; i < y; i++) { int lo[3], hi[3]; box_of(prims[i], lo, hi); bx.grow(lo, hi); }
+            part[t] = bx;
+        });
+        out.reset();
+        for (unsigned t = 0; t < T; t++) if (part[t].hi[0] >= part[t].lo[0]) out.grow(part[t]);   // skip idle chunks
+    };
+    bound(b, mid, left);
+    bound(mid, e, right);
     return mid;
 }
 
@@ -146,7 +193,7 @@ struct Builder {
     }
 
     // split [b,e) into <= WIDE sub-ranges, always refining the largest-area one
-    int widen(uint64_t b, uint64_t e, const IBox& box, Range* r)
+    int widen(uint64_t b, uint64_t e, const IBox& box, Range* r, unsigned nthreads = 1)
     {
         int k = 1;
         r[0].b = b; r[0].e = e; r[0].box = box;
@@ -160,7 +207,7 @@ struct Builder {
                 }
             if (pick < 0) break;
             IBox L, R;
-            uint64_t mid = sah_split(prims, r[pick].b, r[pick].e, L, R);
+            uint64_t mid = sah_split(prims, r[pick].b, r[pick].e, L, R, nthreads);
             Range right; right.b = mid; right.e = r[pick].e; right.box = R;
             r[pick].e = mid; r[pick].box = L;
             for (int i = k; i > pick + 1; i--) r[i] = r[i - 1];     // keep spatial order
@@ -417,10 +464,30 @@ int build_native_tree(std::vector<Entry>& leaves, const uint32_t* solid_of, std:
             }
         }
     }
+    unsigned nthreads = std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
+    // Ranges too large for one thread (a single-level build starts with ONE range over all leaves)
+    // are expanded here, one node at a time with the passes of sah_split spread over the threads;
+    // their children join the task list.
+    {
+        constexpr uint64_t BIG = 1u << 19;
+        Arena A0;
+        std::vector<Task> pending;
+        pending.swap(tasks);
+        while (!pending.empty()) {
+            Task t = pending.back();
+            pending.pop_back();
+            if (t.e - t.b <= BIG || nthreads == 1) { tasks.push_back(t); continue; }
+            Range r[WIDE + 1];
+            const int k = B.widen(t.b, t.e, t.box, r, nthreads);
+            const uint64_t blk = B.alloc(A0, k);
+            if (B.overflow) break;
+            nodes[t.slot] = Builder::pack(t.box, ((uint32_t)k << 28) | (uint32_t)blk);
+            for (int i = 0; i < k; i++) pending.push_back(Task{r[i].b, r[i].e, r[i].box, blk + i});
+        }
+    }
     // biggest tasks first, then a simple work-stealing loop over host threads
     std::sort(tasks.begin(), tasks.end(), [](const Task& a, const Task& b) { return (a.e - a.b) > (b.e - b.b); });
     std::atomic<size_t> cursor{0};
-    unsigned nthreads = std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
     auto worker = [&]() {
         Arena A;
         for (;;) {

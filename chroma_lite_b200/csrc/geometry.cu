@@ -227,7 +227,9 @@ int cb_geometry_create(const CbGeometryDesc* d, cb_geom_t* out)
         const bool do_split = split_from_env(split);
         split.vertices = d->vertices; split.triangles = d->triangles; split.scale = d->world_scale;
         for (int a = 0; a < 3; a++) split.origin[a] = d->world_origin[a];
-        rc = build_native_tree(leaves, d->solid_id, native, do_split ? &split : nullptr);
+        // CHROMA_B200_TREE=single: one SAH hierarchy over all leaves instead of solids first
+        const bool single_level = tree_env && strcmp(tree_env, "single") == 0;
+        rc = build_native_tree(leaves, single_level ? nullptr : d->solid_id, native, do_split ? &split : nullptr);
         if (rc != CB_OK) { free_geometry(g); return rc; }
         native.resize(native.size() + 16, Entry{0, 0, 0, 0});
         cudaError_t e = cudaMalloc((void**)&g->native_nodes, native.size() * sizeof(Entry));
