@@ -387,7 +387,7 @@ int build_native_tree(std::vector<Entry>& leaves, const uint32_t* solid_of, std:
     if (split && split->max_pieces > 1 && split->vertices && split->triangles && !leaves.empty())
         presplit_leaves(leaves, *split);
     const uint64_t n = leaves.size();
-    if (2 * n + n / 4 + 64 * ARENA_CHUNK >= (1ull << 28))
+    if (n + n / 8 >= (1ull << 28))
         return fail(CB_ERR_INVALID, "native BVH: too many leaf entries for the 28-bit child field (lower the split count)");
     nodes.clear();
     if (n == 0) { nodes.push_back(Entry{0, 0, 0, 0}); return CB_OK; }
@@ -410,7 +410,8 @@ int build_native_tree(std::vector<Entry>& leaves, const uint32_t* solid_of, std:
         solid_begin = {0, n};
     }
     const uint64_t nsol = solid_begin.size() - 1;
-    nodes.assign(2 * n + n / 4 + 64 * ARENA_CHUNK, Entry{0, 0, 0, 0});
+    // (a tree needs ~1.3 entries per leaf; the slack is for the per-thread arenas; child indices are 28 bits)
+    nodes.assign(std::min<uint64_t>(2 * n + n / 4 + 64 * ARENA_CHUNK, (1ull << 28) - 1), Entry{0, 0, 0, 0});
     Builder B;
     B.prims = leaves.data();
     B.out = &nodes;
@@ -526,6 +527,7 @@ int build_native_tree(std::vector<Entry>& leaves, const uint32_t* solid_of, std:
         }
         level.swap(nextlevel);
     }
+    if (cur + 16 >= (1ull << 28)) return fail(CB_ERR_INVALID, "native BVH: tree exceeds the 28-bit child field (lower the split count)");
     bfs.resize(cur + 16);
     nodes.swap(bfs);
     return CB_OK;

@@ -1,7 +1,7 @@
 """scratch: traversal work (CPU emulation) with and without leaf splitting."""
 import os, sys, time; sys.path.insert(0,'/root/repo/scratch')
-from emu2 import *
-import emu2
+from emu3 import *
+import emu3 as emu2
 R = float(sys.argv[1]) if len(sys.argv) > 1 else 6000.0
 specs = [tuple(float(x) for x in a.split(',')) for a in sys.argv[2:]] or [(0,8,2.0),(4,8,2.0),(8,8,2.0),(16,8,2.0)]
 geo = demo.detector(pmt_radius=R, sphere_radius=R+500.0, spiral_step=350.0); geo.flatten(dedupe_vertices=False)
