@@ -302,6 +302,15 @@ static IBox poly_box(const Poly& P, const IBox& within)
     return b;
 }
 
+// Surface measure of a leaf box as the traversal sees it: the engine's plane test widens every slab by
+// ~2.5 grid quanta per side (phased_ray_axis), so a box that is a few quanta thin does not get thinner.
+constexpr double SLAB_SLACK = 5.0;
+static double seen_area(const IBox& b)
+{
+    const double dx = b.hi[0] - b.lo[0] + SLAB_SLACK, dy = b.hi[1] - b.lo[1] + SLAB_SLACK, dz = b.hi[2] - b.lo[2] + SLAB_SLACK;
+    return dx * dy + dy * dz + dz * dx;
+}
+
 struct Piece { Poly poly; IBox box; double area; bool done; };
 
 // pieces of one leaf (appended to out); returns the number of pieces
@@ -330,10 +339,10 @@ static int split_leaf(const Entry& leaf, const SplitInput& S, std::vector<Entry>
             const IBox& b = pc[i].box;
             const int ex = std::max(b.hi[0] - b.lo[0], std::max(b.hi[1] - b.lo[1], b.hi[2] - b.lo[2]));
             // a flat axis-aligned part has a box of 2 x its area + a rim from the padding
-            const double rim = 4.0 * ((b.hi[0] - b.lo[0]) + (b.hi[1] - b.lo[1]) + (b.hi[2] - b.lo[2]));
+            const double rim = (2.0 + SLAB_SLACK) * 2.0 * ((b.hi[0] - b.lo[0]) + (b.hi[1] - b.lo[1]) + (b.hi[2] - b.lo[2]));
             const double tight = 2.0 * pc[i].area + rim;
-            if (ex < std::max(S.min_extent, 4) || 2.0 * b.area() <= S.min_ratio * tight) { pc[i].done = true; continue; }
-            if (b.area() > pa) { pa = b.area(); pick = i; }
+            if (ex < std::max(S.min_extent, 4) || 2.0 * seen_area(b) <= S.min_ratio * tight) { pc[i].done = true; continue; }
+            if (seen_area(b) > pa) { pa = seen_area(b); pick = i; }
         }
         if (pick < 0) break;
         Piece& P = pc[pick];
@@ -346,7 +355,7 @@ static int split_leaf(const Entry& leaf, const SplitInput& S, std::vector<Entry>
         A.box = poly_box(A.poly, P.box); B.box = poly_box(B.poly, P.box);
         A.area = poly_area(A.poly); B.area = poly_area(B.poly);
         A.done = B.done = false;
-        if (A.box.area() + B.box.area() > 0.9 * P.box.area()) { P.done = true; continue; }   // no gain
+        if (seen_area(A.box) + seen_area(B.box) > 0.8 * seen_area(P.box)) { P.done = true; continue; }   // no gain
         pc[pick] = A;
         pc[np++] = B;
     }
