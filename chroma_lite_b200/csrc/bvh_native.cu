@@ -326,6 +326,12 @@ static int split_leaf(const Entry& leaf, const SplitInput& S, std::vector<Entry>
         const float* x = S.vertices + 3ull * S.triangles[3ull * tri + v];
         for (int a = 0; a < 3; a++) pc[0].poly.p[v][a] = ((double)x[a] - (double)S.origin[a]) / (double)S.scale;
     }
+    for (int v = 0; v < 3; v++)
+        for (int a = 0; a < 3; a++) {
+            const double q = pc[0].poly.p[v][a];
+            // a corner off the grid (or not a number) cannot be clipped on it: keep the leaf whole
+            if (!(q >= -2.0 && q <= 65538.0)) { out.push_back(leaf); return 1; }
+        }
     pc[0].poly.n = 3;
     pc[0].box = L;
     pc[0].area = poly_area(pc[0].poly);
