@@ -3,6 +3,9 @@
 #include "../oracle/chroma_oracle.c"
 static float g_widen = 0.0f;   /* world units added to every box side (the engine's plane test is widened by ~1.9 mm) */
 ORC_EXPORT void emu2_set_widen(float w) { g_widen = w; }
+static int64_t g_dbg = -1; static float g_rec[4096]; static int g_nrec = 0;
+ORC_EXPORT void emu2_set_debug(int64_t ray) { g_dbg = ray; g_nrec = 0; }
+ORC_EXPORT int emu2_get_debug(float *out) { memcpy(out, g_rec, sizeof(float) * 4 * g_nrec); return g_nrec; }
 ORC_EXPORT void emu2_intersect(const CbGeometryDesc *g, const uint32_t *solid_of, const float *origins, const float *dirs, uint64_t n,
                               int32_t *tri_out, uint64_t *counters, uint16_t *per_ray)
 {
@@ -29,7 +32,9 @@ ORC_EXPORT void emu2_intersect(const CbGeometryDesc *g, const uint32_t *solid_of
                     if (nd.nchild == 0) {
                         if (solid_of[nd.child] == 0) { tris0++; pr0++; } else { tris1++; pr1++; }
                         const uint32_t *t = g->triangles + 3ull*nd.child; float dist;
-                        if (intersect_triangle(o, d, vtx(g,t[0]), vtx(g,t[1]), vtx(g,t[2]), &dist) && dist < best) { best = dist; best_tri = nd.child; }
+                        int hit = intersect_triangle(o, d, vtx(g,t[0]), vtx(g,t[1]), vtx(g,t[2]), &dist);
+                        if ((int64_t)i == g_dbg && g_nrec < 1024) { g_rec[4*g_nrec] = (float)nd.child; g_rec[4*g_nrec+1] = tmin; g_rec[4*g_nrec+2] = hit ? dist : -1.0f; g_rec[4*g_nrec+3] = best; g_nrec++; }
+                        if (hit && dist < best) { best = dist; best_tri = nd.child; }
                     } else { hw[nh] = g->nodes[4ull*j+3]; ht[nh] = tmin; nh++; inner_hits++; }
                 }
             }
