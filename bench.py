@@ -233,7 +233,7 @@ def make_event(n, seed):
 def algorithmic_bytes(det, desc, sample_photons, timings):
     """B_photon = 120 + S*(16*Nnode + 48*Ntri + 64) with Nnode/Ntri/S measured by the
     oracle's reference-order traversal on a bounded sample; also times
-    the oracle = the cpu_baseline ("port", 1 core)."""
+    the oracle = the cpu_baseline ("port", all host cores: photons are independent)."""
     from oracle import orc
     t0 = time.perf_counter()
     st = orc.rng_init(42, 0, len(sample_photons))
@@ -245,7 +245,8 @@ def algorithmic_bytes(det, desc, sample_photons, timings):
     ntri = cnt['tris'] / max(cnt['calls'], 1)
     steps = cnt['steps'] / n
     b = 120.0 + steps * (16.0 * nnode + 48.0 * ntri + 64.0)
-    timings['oracle'] = {'photons': n, 'seconds': t2 - t1, 'rng_init_s': t1 - t0, 'nodes_per_call': nnode,
+    timings['oracle'] = {'photons': n, 'seconds': t2 - t1, 'rng_init_s': t1 - t0, 'threads': orc.threads(),
+                         'nodes_per_call': nnode,
                          'tris_per_call': ntri, 'steps_per_photon': steps, 'bytes_per_photon': b,
                          'max_stack': cnt['max_stack']}
     return b, n / (t2 - t1)
@@ -428,10 +429,10 @@ def run_ours(args):
                         'rays_per_launch': rays_per_launch, 'ms_per_launch': per_launch_s * 1e3,
                         'rays_per_s': rays_per_launch / per_launch_s, 'bytes_per_photon_all_steps': b_photon,
                         'peak_source': 'MEASURED_PEAKS.json hbm_gbs (burst copy)' if peaks else 'fallback 6650 GB/s'}
-        cpu_baseline = {'value': cpu_rate, 'unit': 'photons/s', 'cores': 1, 'kind': 'port',
+        cpu_baseline = {'value': cpu_rate, 'unit': 'photons/s', 'cores': orc.threads(), 'kind': 'port',
                         'sample': '%d photons of the same event type through oracle/chroma_oracle.c '
-                                  '(orc_propagate, max_steps=%d), host cores on this box: %d'
-                                  % (args.cpu_sample, MAX_STEPS, os.cpu_count())}
+                                  '(orc_propagate, max_steps=%d) on %d host threads, host cores on this box: %d'
+                                  % (args.cpu_sample, MAX_STEPS, orc.threads(), os.cpu_count())}
     line = {
         'metric': METRIC_NAME.get(args.workload, 'photons propagated/sec (whole box) on 29k-PMT detector'), 'value': value,
         'unit': 'photons/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dev_s * 1e3 / args.steps,

@@ -343,8 +343,9 @@ int cb_rng_create(uint64_t n, uint64_t seed, uint64_t offset, cb_rng_t* out)
     if (n) {
         unsigned blocks = (unsigned)((n + 255) / 256);
         rng_init_kernel<<<blocks, 256, 0, ctx().stream>>>(r->states, n, seed, 0, offset, d_xw_seq, d_xw_off);
-        CB_CUDA(cudaGetLastError());
-        CB_CUDA(cudaStreamSynchronize(ctx().stream));
+        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx().stream);
+        if (e != cudaSuccess) { cudaFree(r->states); delete r; return cuda_fail(e, "rng_init_kernel"); }
     }
     *out = rngs().add(r);
     return CB_OK;

@@ -33,6 +33,9 @@
 #include <stdlib.h>
 #include <string.h>
 #include <float.h>
+#include <pthread.h>
+#include <stdatomic.h>
+#include <unistd.h>
 
 #include "../include/chroma_b200.h"
 
@@ -159,11 +162,61 @@ ORC_EXPORT void orc_xorwow_matrix(int which, int k, uint32_t out[800])
 
 /* states[i] = curand_init(seed, first_stream + i, offset); mirrors init_rng
  * (random.h:60-70) */
+/* Host threads of the two bulk loops (orc_rng_init, orc_propagate): photons and streams are
+ * independent, so the results do not depend on the thread count.  0 = all cores. */
+static int g_threads = 0;
+ORC_EXPORT void orc_set_threads(int n) { g_threads = n; }
+ORC_EXPORT int orc_get_threads(void)
+{
+    if (g_threads > 0) return g_threads;
+    long n = sysconf(_SC_NPROCESSORS_ONLN);
+    return n < 1 ? 1 : (n > 256 ? 256 : (int)n);
+}
+
+/* fn(arg, begin, end, thread) over [0, n) in chunks handed out through an atomic cursor */
+typedef void (*orc_range_fn)(void *arg, uint64_t begin, uint64_t end, int thread);
+typedef struct { orc_range_fn fn; void *arg; uint64_t n, chunk; atomic_ullong *cursor; int thread; } orc_job;
+static void *orc_job_main(void *p)
+{
+    orc_job *j = (orc_job *)p;
+    for (;;) {
+        uint64_t b = atomic_fetch_add(j->cursor, j->chunk);
+        if (b >= j->n) break;
+        uint64_t e = b + j->chunk < j->n ? b + j->chunk : j->n;
+        j->fn(j->arg, b, e, j->thread);
+    }
+    return NULL;
+}
+static void orc_parallel_for(uint64_t n, uint64_t chunk, orc_range_fn fn, void *arg, int nthreads)
+{
+    if (nthreads > 256) nthreads = 256;
+    if (nthreads <= 1 || n <= chunk) { if (n) fn(arg, 0, n, 0); return; }
+    atomic_ullong cursor = 0;
+    pthread_t tid[256];
+    orc_job job[256];
+    int started = 0;
+    for (int t = 0; t < nthreads; t++) {
+        job[t].fn = fn; job[t].arg = arg; job[t].n = n; job[t].chunk = chunk; job[t].cursor = &cursor; job[t].thread = t;
+        if (t > 0 && pthread_create(&tid[t], NULL, orc_job_main, &job[t]) != 0) break;
+        started = t + 1;
+    }
+    orc_job_main(&job[0]);
+    for (int t = 1; t < started; t++) pthread_join(tid[t], NULL);
+}
+
+typedef struct { uint64_t seed, first_stream, offset; uint32_t *states6; } orc_rng_init_arg;
+static void orc_rng_init_range(void *p, uint64_t b, uint64_t e, int thread)
+{
+    const orc_rng_init_arg *a = (const orc_rng_init_arg *)p;
+    (void)thread;
+    for (uint64_t i = b; i < e; i++) orc_xorwow_init(a->seed, a->first_stream + i, a->offset, a->states6 + 6 * i);
+}
 ORC_EXPORT void orc_rng_init(uint64_t seed, uint64_t first_stream, uint64_t n,
                              uint64_t offset, uint32_t *states6)
 {
-    for (uint64_t i = 0; i < n; i++)
-        orc_xorwow_init(seed, first_stream + i, offset, states6 + 6 * i);
+    xw_tables();    /* built once, before the threads start */
+    orc_rng_init_arg a = {seed, first_stream, offset, states6};
+    orc_parallel_for(n, 4096, orc_rng_init_range, &a, orc_get_threads());
 }
 
 /* fill_uniform (random.h:72-82): one draw per state */
@@ -1082,12 +1135,22 @@ static int propagate_one(Photon *p, orc_rng *rng, const CbGeometryDesc *g, int m
  * completion or max_steps, i.e. the reference kernel launched once with
  * nsteps = max_steps.  All pointers are HOST pointers here.
  * counters = {nodes, tris, intersect calls, max_stack, total steps} or NULL. */
-ORC_EXPORT void orc_propagate(const CbGeometryDesc *g, const CbPhotonBank *b, uint32_t *states6,
-                              int max_steps, int use_weights, int scatter_first, uint64_t *counters)
+typedef struct {
+    const CbGeometryDesc *g; const CbPhotonBank *b; uint32_t *states6;
+    int max_steps, use_weights, scatter_first;
+    uint64_t total_steps[256], nodes[256], tris[256], calls[256];
+    uint32_t max_stack[256];
+} orc_propagate_arg;
+
+static void orc_propagate_range(void *arg, uint64_t begin, uint64_t end, int thread)
 {
+    orc_propagate_arg *a = (orc_propagate_arg *)arg;
+    const CbGeometryDesc *g = a->g;
+    const CbPhotonBank *b = a->b;
+    uint32_t *states6 = a->states6;
     orc_counters c = {0, 0, 0, 0};
     uint64_t total_steps = 0;
-    for (uint64_t i = 0; i < b->n; i++) {
+    for (uint64_t i = begin; i < end; i++) {
         Photon p;
         p.position = mk(b->pos[3 * i], b->pos[3 * i + 1], b->pos[3 * i + 2]);
         p.direction = mk(b->dir[3 * i], b->dir[3 * i + 1], b->dir[3 * i + 2]);
@@ -1103,7 +1166,7 @@ ORC_EXPORT void orc_propagate(const CbGeometryDesc *g, const CbPhotonBank *b, ui
         const uint16_t term = CB_NO_HIT | CB_BULK_ABSORB | CB_SURFACE_DETECT | CB_SURFACE_ABSORB | CB_NAN_ABORT;
         if (p.history & term) continue; /* early return: nothing written back (propagate.cu:295) */
         orc_rng rng; rng.d = states6[6 * i]; memcpy(rng.v, states6 + 6 * i + 1, 20);
-        total_steps += (uint64_t)propagate_one(&p, &rng, g, max_steps, use_weights, scatter_first, &c);
+        total_steps += (uint64_t)propagate_one(&p, &rng, g, a->max_steps, a->use_weights, a->scatter_first, &c);
         states6[6 * i] = rng.d; memcpy(states6 + 6 * i + 1, rng.v, 20);
         b->pos[3 * i] = p.position.x; b->pos[3 * i + 1] = p.position.y; b->pos[3 * i + 2] = p.position.z;
         b->dir[3 * i] = p.direction.x; b->dir[3 * i + 1] = p.direction.y; b->dir[3 * i + 2] = p.direction.z;
@@ -1115,10 +1178,27 @@ ORC_EXPORT void orc_propagate(const CbGeometryDesc *g, const CbPhotonBank *b, ui
         b->weights[i] = p.weight;
         b->evidx[i] = p.evidx;
     }
+    a->total_steps[thread] += total_steps;
+    a->nodes[thread] += c.nodes; a->tris[thread] += c.tris; a->calls[thread] += c.calls;
+    if (c.max_stack > a->max_stack[thread]) a->max_stack[thread] = c.max_stack;
+}
+
+ORC_EXPORT void orc_propagate(const CbGeometryDesc *g, const CbPhotonBank *b, uint32_t *states6,
+                              int max_steps, int use_weights, int scatter_first, uint64_t *counters)
+{
+    orc_propagate_arg *a = (orc_propagate_arg *)calloc(1, sizeof(orc_propagate_arg));
+    a->g = g; a->b = b; a->states6 = states6;
+    a->max_steps = max_steps; a->use_weights = use_weights; a->scatter_first = scatter_first;
+    orc_parallel_for(b->n, 512, orc_propagate_range, a, orc_get_threads());
     if (counters) {
-        counters[0] = c.nodes; counters[1] = c.tris; counters[2] = c.calls;
-        counters[3] = c.max_stack; counters[4] = total_steps;
+        memset(counters, 0, 5 * sizeof(uint64_t));
+        for (int t = 0; t < 256; t++) {
+            counters[0] += a->nodes[t]; counters[1] += a->tris[t]; counters[2] += a->calls[t];
+            if (a->max_stack[t] > counters[3]) counters[3] = a->max_stack[t];
+            counters[4] += a->total_steps[t];
+        }
     }
+    free(a);
 }
 
 /* run_daq, daq.cu:35-86 (ndaq == 1).  rng state index = photon - start_photon

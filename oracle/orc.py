@@ -28,6 +28,18 @@ def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
+def threads():
+    """Host threads orc_rng_init / orc_propagate run on (all cores unless set_threads was called)."""
+    f = lib().orc_get_threads
+    f.restype = C.c_int
+    return int(f())
+
+
+def set_threads(n):
+    """0 = all cores.  Results do not depend on the thread count (independent photons / streams)."""
+    lib().orc_set_threads(C.c_int(int(n)))
+
+
 def rng_init(seed, first_stream, n, offset=0):
     """uint32 (n,6) states == curand_init(seed, first_stream+i, offset)."""
     st = np.zeros((n, 6), dtype=np.uint32)
