@@ -53,8 +53,8 @@ def test_engine_replays_reference_kernel_fixture(gpu_ready, name):
 
 
 def test_leaf_split_tree_gives_identical_results(gpu_ready, monkeypatch):
-    """CHROMA_B200_LEAF_SPLIT (bvh_native.cu: several tighter leaves per loosely bounded triangle) changes
-    the traversal tree only: nearest hits (triangle and distance, ties included) and whole propagations
+    """CHROMA_B200_LEAF_SPLIT (bvh_native.cu: several tighter leaves per loosely bounded triangle) and
+    CHROMA_B200_TREE=single (one hierarchy over all leaves) change the traversal tree only: nearest hits (triangle and distance, ties included) and whole propagations
     are bit-identical to the one-leaf-per-triangle tree."""
     from chroma_lite_b200.sample import uniform_sphere
     geo = scenes.tiny_detector()
@@ -73,11 +73,12 @@ def test_leaf_split_tree_gives_identical_results(gpu_ready, monkeypatch):
     d = np.concatenate([d, aim - o[n:]]).astype(np.float32)
     ph = scenes.point_source(60000, seed=6, wl_range=(300, 600))
     results = []
-    for spec in (None, '4,8,8', '16,4,1.5'):
-        if spec is None:
-            monkeypatch.delenv('CHROMA_B200_LEAF_SPLIT', raising=False)
-        else:
-            monkeypatch.setenv('CHROMA_B200_LEAF_SPLIT', spec)
+    for spec, tree in ((None, None), ('4,8,8', None), ('16,4,1.5', None), (None, 'single'), ('8,8,2', 'single')):
+        for key, val in (('CHROMA_B200_LEAF_SPLIT', spec), ('CHROMA_B200_TREE', tree)):
+            if val is None:
+                monkeypatch.delenv(key, raising=False)
+            else:
+                monkeypatch.setenv(key, val)
         g = gpu.GPUDetector(geo)
         tri, dist = gpu.intersect_mesh(g, o, d)
         gp = gpu.GPUPhotons(ph)
@@ -85,6 +86,7 @@ def test_leaf_split_tree_gives_identical_results(gpu_ready, monkeypatch):
                      max_steps=100)
         results.append((tri.get(), dist.get(), gp.get(), g.gpudata if hasattr(g, 'gpudata') else None))
     monkeypatch.delenv('CHROMA_B200_LEAF_SPLIT', raising=False)
+    monkeypatch.delenv('CHROMA_B200_TREE', raising=False)
     tri0, dist0, end0, _ = results[0]
     assert (tri0 >= 0).mean() > 0.3
     for tri, dist, end, _ in results[1:]:

@@ -69,12 +69,14 @@ def test_split_leaves_cover_their_triangles_and_keep_results():
     tighter boxes.  Every piece lies inside the reference leaf box, every point of a triangle lies inside
     at least one of its pieces (so a ray that can hit the triangle still reaches it), and the oracle's
     traversal returns the same hits through the split tree."""
-    for geo, pieces in ((scenes.tiny_detector(), 8), (scenes.sphere_scene(16), 4), (scenes.scintillator_scene(10), 16)):
+    for geo, pieces, by_solid in ((scenes.tiny_detector(), 8, True), (scenes.tiny_detector(), 8, False),
+                                  (scenes.sphere_scene(16), 4, True), (scenes.scintillator_scene(10), 16, True)):
         desc, keep = scenes.desc_of(geo)
         ntri = len(geo.mesh.triangles)
         wc = geo.bvh.world_coords
-        plain = native_tree(keep['nodes'], ntri, geo.solid_id)
-        nat = native_tree(keep['nodes'], ntri, geo.solid_id, mesh=geo.mesh, world_coords=wc, max_pieces=pieces,
+        sid = geo.solid_id if by_solid else None          # None: one hierarchy over all leaves (CHROMA_B200_TREE=single)
+        plain = native_tree(keep['nodes'], ntri, sid)
+        nat = native_tree(keep['nodes'], ntri, sid, mesh=geo.mesh, world_coords=wc, max_pieces=pieces,
                           min_extent=4, min_ratio=1.5)
         tris, maxfan, ok = walk(nat)
         tris = np.asarray(tris)
