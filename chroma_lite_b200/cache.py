@@ -15,7 +15,10 @@ import numpy as np
 
 from .bvh import BVH, WorldCoords, uint4
 
-DEFAULT_DIR = os.path.join(os.path.expanduser('~'), '.chroma_b200')
+# the reference reads CHROMA_CACHE_DIR (chroma/cache.py:17); its entries are pickles under the same names, so this
+# cache lives in its own sub-directory of it
+DEFAULT_DIR = (os.path.join(os.environ['CHROMA_CACHE_DIR'], 'b200') if os.environ.get('CHROMA_CACHE_DIR')
+               else os.path.join(os.path.expanduser('~'), '.chroma_b200'))
 
 
 class GeometryNotFoundError(Exception):
