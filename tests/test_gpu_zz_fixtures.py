@@ -94,3 +94,43 @@ def test_leaf_split_tree_gives_identical_results(gpu_ready, monkeypatch):
         assert np.array_equal(dist.view(np.uint32), dist0.view(np.uint32))
         for f in ('pos', 'dir', 'pol', 't', 'wavelengths', 'flags', 'last_hit_triangles'):
             assert np.array_equal(getattr(end, f), getattr(end0, f)), f
+
+
+def test_photon_tracking_steps(gpu_ready):
+    """propagate(track=True) (gpu/photon.py:249-283): ids of the photons that enter every step and their state
+    after it; stepping one launch at a time ends in the same state as one call; Simulation(photon_tracking=True)
+    turns the snapshots into per-photon tracks (sim.py:117-130)."""
+    from chroma_lite_b200 import sim
+    geo = scenes.tiny_detector()
+    n = 5000
+    ph = scenes.point_source(n, seed=14, wl_range=(300, 600))
+    g = gpu.GPUDetector(geo)
+    gp = gpu.GPUPhotons(ph)
+    ids, snaps = gp.propagate(g, gpu.get_rng_states(n, seed=2), nthreads_per_block=256, max_blocks=(n + 255) // 256,
+                              max_steps=30, track=True)
+    end = gp.get()
+    assert np.array_equal(ids[0], np.arange(n)) and np.array_equal(snaps[0].pos, ph.pos.astype(np.float32))
+    assert len(ids) == len(snaps) >= 3
+    last_seen = np.zeros(n, dtype=np.int64)
+    for k in range(1, len(ids)):
+        assert len(snaps[k]) == len(ids[k]) and set(ids[k].tolist()) <= set(ids[k - 1].tolist())
+        last_seen[ids[k]] = k
+        # a photon that enters step k had no terminal flag after step k-1
+        prev = dict(zip(ids[k - 1].tolist(), snaps[k - 1].flags.tolist()))
+        assert all((prev[i] & event.TERMINAL_MASK) == 0 for i in ids[k][:200].tolist())
+    for k in range(1, len(ids)):                      # the last snapshot of a photon is its final state
+        sel = last_seen[ids[k]] == k
+        assert np.array_equal(snaps[k].flags[sel], end.flags[ids[k][sel]])
+        assert np.array_equal(snaps[k].pos[sel], end.pos[ids[k][sel]])
+    # same end state as one call over all steps (same RNG streams, one step per launch or not)
+    gp2 = gpu.GPUPhotons(ph)
+    gp2.propagate(g, gpu.get_rng_states(n, seed=2), nthreads_per_block=256, max_blocks=(n + 255) // 256, max_steps=30)
+    end2 = gp2.get()
+    assert np.array_equal(end.flags, end2.flags) and np.array_equal(end.pos, end2.pos)
+    s = sim.Simulation(geo, seed=3, photon_tracking=True, nthreads_per_block=256, max_blocks=32)
+    ev = next(s.simulate(scenes.point_source(800, seed=15, wl_range=(300, 600)), keep_photons_end=True, max_steps=20))
+    assert len(ev.photon_tracks) == 800
+    for i in (0, 17, 799):
+        tr = ev.photon_tracks[i]
+        assert len(tr) >= 2 and np.array_equal(tr.pos[-1], ev.photons_end.pos[i])
+        assert tr.flags[-1] == ev.photons_end.flags[i]
