@@ -177,3 +177,28 @@ def test_native_vertex_dedup_equals_numpy(monkeypatch):
     b = G.Mesh(tiled, tris, remove_duplicate_vertices=True, remove_null_triangles=False)
     assert len(a.vertices) < len(tiled)
     assert np.array_equal(a.vertices, b.vertices) and np.array_equal(a.triangles, b.triangles)
+
+
+def test_response_cdfs_are_uploaded_with_equal_lengths():
+    """gpu/detector.py: the reference's _pdf_to_cdf adds 0.0 to the cumulative sum instead of prepending it
+    (chroma/detector.py:104-107), so its y array is one short of x; the upload completes such a pair and
+    rejects anything else instead of reading past the end."""
+    import pytest
+    from chroma_lite_b200.gpu.detector import cdf_arrays
+    from chroma_lite_b200.detector import Detector
+    d = Detector(None)
+    d.set_time_dist_gaussian(1.2, -6.0, 6.0)
+    x, y = cdf_arrays(d.time_cdf)
+    assert len(x) == len(y) == 51 and y[0] == 0.0 and y[-1] == 1.0 and (np.diff(y) >= 0).all()
+    # the pair the reference's Detector produces for the same call
+    edges = np.linspace(-6.0, 6.0, 51)
+    contents = np.exp(-0.5 * (edges[1:] / 1.2) ** 2)
+    ref_y = np.array([0.0] + contents.cumsum())
+    ref_y /= ref_y[-1]
+    assert len(ref_y) == 50
+    x2, y2 = cdf_arrays((edges, ref_y))
+    assert np.array_equal(x2, x) and np.allclose(y2, y, atol=1e-7)
+    with pytest.raises(ValueError):
+        cdf_arrays((edges, ref_y[:-3]))
+    with pytest.raises(ValueError):
+        cdf_arrays((edges[:1], ref_y[:1]))
