@@ -54,6 +54,11 @@ class Mesh(object):
         if remove_null_triangles:
             self.remove_null_triangles()
 
+    def md5(self):
+        """MD5 of the vertex array, then the triangle array, hex (chroma/geometry.py:107-112)."""
+        from .cache import mesh_hash
+        return mesh_hash(self)
+
     def get_bounds(self):
         return np.min(self.vertices, axis=0), np.max(self.vertices, axis=0)
 

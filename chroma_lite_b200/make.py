@@ -60,6 +60,76 @@ def cube(size, height=None, center=(0, 0, 0)):
     return box(size, size, size if height is None else height, center=center)
 
 
+def mesh_grid(grid):
+    """Triangle index rows for a grid of vertex indices that is periodic along its second axis:
+    each cell (i, j) between rows i, i+1 and columns j, j+1 gives two triangles
+    (index arithmetic of chroma/make.py:6-20)."""
+    grid = np.asarray(grid)
+    a, b = grid[:-1], grid[1:]
+    an, bn = np.roll(a, -1, axis=1), np.roll(b, -1, axis=1)
+    first = np.stack([a.ravel(), b.ravel(), bn.ravel()], axis=1)
+    second = np.stack([a.ravel(), bn.ravel(), an.ravel()], axis=1)
+    return np.concatenate([first, second])
+
+
+def linear_extrude(x1, y1, height, x2=None, y2=None, center=None, endcaps=True):
+    """Prism from the counter-clockwise polygon (x1, y1) at z = -height/2 to (x2, y2) (default: the
+    same polygon) at z = +height/2; end caps are fans about the z axis (chroma/make.py:22-69)."""
+    x1, y1 = np.asarray(x1, dtype=np.float64), np.asarray(y1, dtype=np.float64)
+    if len(x1) != len(y1):
+        raise Exception('`x` and `y` arrays must have the same length.')
+    x2 = x1 if x2 is None else np.asarray(x2, dtype=np.float64)
+    y2 = y1 if y2 is None else np.asarray(y2, dtype=np.float64)
+    if len(x2) != len(y2) or len(x2) != len(x1):
+        raise Exception('`x` and `y` arrays must have the same length.')
+    n = len(x1)
+    zero = np.zeros(n)
+    rings = [np.column_stack([x1, y1, np.full(n, -height / 2.0)]), np.column_stack([x2, y2, np.full(n, height / 2.0)])]
+    if endcaps:
+        rings = ([np.column_stack([zero, zero, np.full(n, -height / 2.0)])] + rings +
+                 [np.column_stack([zero, zero, np.full(n, height / 2.0)])])
+    vertices = np.concatenate(rings)                       # ring r, corner j -> index r*n + j
+    if center is not None:
+        vertices = vertices + np.asarray(center, dtype=np.float64)
+    # rows from the top ring down so that a counter-clockwise polygon gives outward normals
+    grid = np.arange(len(vertices)).reshape(len(rings), n)[::-1]
+    return Mesh(vertices, mesh_grid(grid), remove_duplicate_vertices=True)
+
+
+def cylinder_along_z(radius, height, points=100):
+    """Cylinder with its axis along z (chroma/make.py:106-108)."""
+    angles = np.linspace(0.0, 2.0 * np.pi, points, endpoint=False)
+    return linear_extrude(radius * np.cos(angles), radius * np.sin(angles), height)
+
+
+def segmented_cylinder(radius, height, nsteps=64, nsegments=100):
+    """Cylinder about y whose profile is cut into about `nsegments` pieces (chroma/make.py:121-129)."""
+    nr = int((nsegments * radius / (2 * radius + height)) / 2)
+    nh = int((nsegments * height / (2 * radius + height)) / 2)
+    x = np.concatenate([np.linspace(0, radius, nr, endpoint=False), [radius] * nh,
+                        np.linspace(radius, 0, nr, endpoint=False), [0]])
+    y = np.concatenate([[-height / 2.0] * nr, np.linspace(-height / 2.0, height / 2.0, nh, endpoint=False),
+                        [height / 2.0] * (nr + 1)])
+    return rotate_extrude(x, y, nsteps)
+
+
+def torus(radius, offset, nsteps=64, circle_steps=None):
+    """Torus about y: barrel of `radius` centred `offset` from the axis (chroma/make.py:136-147)."""
+    if circle_steps is None:
+        circle_steps = nsteps
+    t = np.linspace(0.0, 2.0 * np.pi, circle_steps)
+    return rotate_extrude(radius * np.cos(t) + offset, radius * np.sin(t), nsteps)
+
+
+def convex_polygon(x, y):
+    """Fan triangulation of a convex polygon in the z = 0 plane, points given in order
+    (chroma/make.py:149-163)."""
+    x = np.asarray(x, dtype=np.float64)
+    vertices = np.column_stack([x, np.asarray(y, dtype=np.float64), np.zeros_like(x)])
+    k = np.arange(1, len(vertices) - 1)
+    return Mesh(vertices, np.column_stack([np.zeros_like(k), k, k + 1]))
+
+
 def subdivide(mesh, times=1):
     """1 -> 4 midpoint subdivision (used to grow the ray-microbench mesh)."""
     v = np.asarray(mesh.vertices, dtype=np.float64)

@@ -11,6 +11,9 @@ and is not importable.  Outputs (committed):
   flatten.npz       Geometry/Detector.flatten() of a small scene built with the
                     reference's classes (vertices, triangles, solid_id, indices)
   sphere_mesh.npz   reference make.sphere(1000, 16) (mesh-builder cross-check)
+  host_helpers.npz  chroma.transform (rotation matrices and rotated points, gen_rot, get_perp), triangle /
+                    vertex counts, area and signed volume of chroma.make's other builders, and
+                    chroma.sample.flashlight under a fixed NumPy seed
 """
 import os
 import sys
@@ -79,7 +82,50 @@ def main():
                         solid_id_to_channel_index=det.solid_id_to_channel_index,
                         small_vertices=small.vertices, small_triangles=small.triangles,
                         shell_vertices=det.solids[0].mesh.vertices, shell_triangles=det.solids[0].mesh.triangles)
+    helpers(os.path.join(HERE, 'host_helpers.npz'))
     print('wrote fixtures to', HERE)
+
+
+HELPER_AXIS, HELPER_PHI = np.array([0.3, -0.5, 0.8]), 0.7
+GEN_ROT_PAIRS = (([1, 0, 0], [0, 1, 0]), ([1, 0, 0], [1, 0, 0]), ([0, 1, 0], [0, 1, 0]), ([0, 0, 1], [0, 0, -1]),
+                 ([1, 2, 3], [-2, 0.5, 1]))
+
+
+def builder_cases():
+    ang = np.linspace(0, 2 * np.pi, 6, endpoint=False)
+    hexagon = (np.cos(ang), np.sin(ang))
+    return (('linear_extrude', hexagon + (2.0,), {}),
+            ('linear_extrude', hexagon + (2.0,), dict(x2=0.5 * hexagon[0], y2=0.5 * hexagon[1], center=(1, 2, 3))),
+            ('linear_extrude', hexagon + (2.0,), dict(endcaps=False)),
+            ('cylinder_along_z', (10.0, 30.0, 20), {}), ('segmented_cylinder', (10.0, 30.0, 16, 40), {}),
+            ('torus', (2.0, 10.0, 16, 12), {}), ('convex_polygon', hexagon, {}), ('cylinder', (5.0, 8.0, 3.0, 12), {}))
+
+
+def mesh_stats(mesh):
+    """(triangles, vertices, area, signed volume): independent of vertex numbering, sensitive to orientation."""
+    v = np.asarray(mesh.vertices, dtype=np.float64)[np.asarray(mesh.triangles)]
+    cr = np.cross(v[:, 1] - v[:, 0], v[:, 2] - v[:, 0])
+    return np.array([len(mesh.triangles), len(mesh.vertices), 0.5 * np.linalg.norm(cr, axis=1).sum(),
+                     np.einsum('ij,ij->i', v[:, 0], cr).sum() / 6.0])
+
+
+def helpers(path):
+    import chroma.transform as rtr
+    import chroma.sample as rsample
+    x = np.random.default_rng(0).normal(size=(5, 3))
+    out = {'points': x,
+           'matrix': rtr.make_rotation_matrix(HELPER_PHI, HELPER_AXIS),
+           'rotate': rtr.rotate(x, HELPER_PHI, HELPER_AXIS),
+           'rotate_many': rtr.rotate(x, np.linspace(0, 1, 5), HELPER_AXIS),
+           'rotate_matrix': rtr.rotate_matrix(x, HELPER_PHI, HELPER_AXIS),
+           'get_perp': rtr.get_perp(HELPER_AXIS),
+           'gen_rot': np.array([rtr.gen_rot(np.array(a, float), np.array(b, float)) for a, b in GEN_ROT_PAIRS]),
+           'builders': np.array([mesh_stats(getattr(rmake, n)(*a, **k)) for n, a, k in builder_cases()])}
+    np.random.seed(5)
+    out['flashlight'] = rsample.flashlight(0.3, (1, 2, 3), 1000)
+    np.random.seed(5)
+    out['flashlight_one'] = rsample.flashlight()
+    np.savez_compressed(path, **out)
 
 
 if __name__ == '__main__':

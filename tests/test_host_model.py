@@ -202,3 +202,55 @@ def test_response_cdfs_are_uploaded_with_equal_lengths():
         cdf_arrays((edges, ref_y[:-3]))
     with pytest.raises(ValueError):
         cdf_arrays((edges[:1], ref_y[:1]))
+
+
+def test_transform_builders_and_flashlight_match_the_reference():
+    """tests/golden/host_helpers.npz (made from the reference's chroma.transform / chroma.make / chroma.sample by
+    tests/golden/make_golden.py): same rotation sense and values, same meshes up to vertex numbering (triangle and
+    vertex counts, area, signed volume, so orientation too), same flashlight sample under the same NumPy seed."""
+    import os
+    import sys
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+    g = np.load(os.path.join(here, 'host_helpers.npz'))
+    from chroma_lite_b200 import transform, make, sample
+    axis, phi, x = np.array([0.3, -0.5, 0.8]), 0.7, g['points']
+    assert np.allclose(transform.make_rotation_matrix(phi, axis), g['matrix'], atol=1e-14)
+    assert np.allclose(transform.rotate(x, phi, axis), g['rotate'], atol=1e-13)
+    assert np.allclose(transform.rotate(x, np.linspace(0, 1, 5), axis), g['rotate_many'], atol=1e-13)
+    assert np.allclose(transform.rotate_matrix(x, phi, axis), g['rotate_matrix'], atol=1e-13)
+    assert np.allclose(np.inner(x, transform.make_rotation_matrix(phi, axis)), g['rotate'], atol=1e-13)
+    assert np.allclose(transform.get_perp(axis), g['get_perp'])
+    pairs = (([1, 0, 0], [0, 1, 0]), ([1, 0, 0], [1, 0, 0]), ([0, 1, 0], [0, 1, 0]), ([0, 0, 1], [0, 0, -1]),
+             ([1, 2, 3], [-2, 0.5, 1]))
+    for (a, b), want in zip(pairs, g['gen_rot']):
+        assert np.allclose(transform.gen_rot(a, b), want, atol=1e-13)
+    # the right-handed helper of this package is the transpose (what demo.detector compensates with -angle)
+    assert np.allclose(sample.make_rotation_matrix(phi, axis), g['matrix'].T, atol=1e-14)
+
+    ang = np.linspace(0, 2 * np.pi, 6, endpoint=False)
+    hexagon = (np.cos(ang), np.sin(ang))
+    cases = (('linear_extrude', hexagon + (2.0,), {}),
+             ('linear_extrude', hexagon + (2.0,), dict(x2=0.5 * hexagon[0], y2=0.5 * hexagon[1], center=(1, 2, 3))),
+             ('linear_extrude', hexagon + (2.0,), dict(endcaps=False)),
+             ('cylinder_along_z', (10.0, 30.0, 20), {}), ('segmented_cylinder', (10.0, 30.0, 16, 40), {}),
+             ('torus', (2.0, 10.0, 16, 12), {}), ('convex_polygon', hexagon, {}), ('cylinder', (5.0, 8.0, 3.0, 12), {}))
+    for (name, args, kw), want in zip(cases, g['builders']):
+        m = getattr(make, name)(*args, **kw)
+        v = np.asarray(m.vertices, dtype=np.float64)[np.asarray(m.triangles)]
+        cr = np.cross(v[:, 1] - v[:, 0], v[:, 2] - v[:, 0])
+        got = [len(m.triangles), len(m.vertices), 0.5 * np.linalg.norm(cr, axis=1).sum(),
+               np.einsum('ij,ij->i', v[:, 0], cr).sum() / 6.0]
+        assert got[0] == want[0] and got[1] == want[1], name
+        assert np.allclose(got[2:], want[2:], rtol=1e-9, atol=1e-9), name
+    with pytest.raises(Exception):
+        make.linear_extrude([0, 1], [0, 1, 2], 1.0)
+    # a closed prism: hexagon area * height
+    hexprism = make.linear_extrude(hexagon[0], hexagon[1], 2.0)
+    assert np.isclose(g['builders'][0][3], 2.0 * 1.5 * np.sqrt(3.0), rtol=1e-6) and len(hexprism.md5()) == 32
+
+    np.random.seed(5)
+    assert np.allclose(sample.flashlight(0.3, (1, 2, 3), 1000), g['flashlight'], atol=1e-12)
+    np.random.seed(5)
+    assert np.allclose(sample.flashlight(), g['flashlight_one'], atol=1e-12)
+    d = sample.flashlight(0.2, (0, 1, 0), 500, rng=np.random.default_rng(1))
+    assert np.allclose(np.linalg.norm(d, axis=1), 1.0) and (d[:, 1] >= np.cos(0.2) - 1e-12).all()
