@@ -1,0 +1,60 @@
+// scratch tool: like ordered_emul.c, plus a split of the triangle tests by solid class
+// (solid 0 = liner vs PMTs) and of the winning triangle.
+#include "../oracle/chroma_oracle.c"
+static float g_widen = 0.0f;   /* world units added to every box side (the engine's plane test is widened by ~1.9 mm) */
+ORC_EXPORT void emu2_set_widen(float w) { g_widen = w; }
+static int g_leaf_mode = 0;   /* 0: test leaves as found; 1: per node, nearest box first, re-checked against the best hit; 2: LIFO queue re-checked (the kernel) */
+ORC_EXPORT void emu2_set_leaf_mode(int m) { g_leaf_mode = m; }
+static int64_t g_dbg = -1; static float g_rec[4096]; static int g_nrec = 0;
+ORC_EXPORT void emu2_set_debug(int64_t ray) { g_dbg = ray; g_nrec = 0; }
+ORC_EXPORT int emu2_get_debug(float *out) { memcpy(out, g_rec, sizeof(float) * 4 * g_nrec); return g_nrec; }
+ORC_EXPORT void emu2_intersect(const CbGeometryDesc *g, const uint32_t *solid_of, const float *origins, const float *dirs, uint64_t n,
+                              int32_t *tri_out, uint64_t *counters, uint16_t *per_ray)
+{
+    uint64_t rounds=0, entries=0, tris0=0, tris1=0, halves=0, win0=0, win1=0, inner_hits=0;
+    for (uint64_t i = 0; i < n; i++) {
+        f3 o = mk(origins[3*i], origins[3*i+1], origins[3*i+2]);
+        f3 d = mk(dirs[3*i], dirs[3*i+1], dirs[3*i+2]);
+        d = divs(d, norm(d));
+        f3 noid = mk(-o.x/d.x, -o.y/d.y, -o.z/d.z), inv = mk(1.0f/d.x, 1.0f/d.y, 1.0f/d.z);
+        Node root = get_node(g, 0);
+        float best = INFINITY; int best_tri = -1; float tb; uint16_t pr0=0, pr1=0, prr=0;
+        if (!intersect_box(noid, inv, root.lower, root.upper, &tb)) { tri_out[i] = -1; continue; }
+        uint32_t sw[512]; float st[512]; int sp = 0;
+        uint32_t cur = g->nodes[3];
+        for (;;) {
+            uint32_t first = cur & 0x0FFFFFFF, k = cur >> 28;
+            rounds++; prr++; halves += (k + 3) / 4;
+            uint32_t hw[16]; float ht[16]; int nh = 0;
+            uint32_t lq_tri[16]; float lq_t[16]; int nl = 0;
+            for (uint32_t j = first; j < first + k; j++) {
+                Node nd = get_node(g, j); entries++;
+                nd.lower.x -= g_widen; nd.lower.y -= g_widen; nd.lower.z -= g_widen; nd.upper.x += g_widen; nd.upper.y += g_widen; nd.upper.z += g_widen;
+                float tmin;
+                if (intersect_box(noid, inv, nd.lower, nd.upper, &tmin) && !(tmin > best)) {
+                    if (nd.nchild == 0) {
+                        lq_tri[nl] = nd.child; lq_t[nl] = tmin; nl++;
+                    } else { hw[nh] = g->nodes[4ull*j+3]; ht[nh] = tmin; nh++; inner_hits++; }
+                }
+            }
+            if (g_leaf_mode == 1) for (int a = 0; a < nl; a++) for (int b = a+1; b < nl; b++) if (lq_t[b] < lq_t[a]) { float tt=lq_t[a]; lq_t[a]=lq_t[b]; lq_t[b]=tt; uint32_t ww=lq_tri[a]; lq_tri[a]=lq_tri[b]; lq_tri[b]=ww; }
+            for (int q = 0; q < nl; q++) {
+                int a = (g_leaf_mode == 2) ? nl - 1 - q : q;
+                if (g_leaf_mode != 0 && lq_t[a] > best) continue;
+                uint32_t tri_id = lq_tri[a];
+                if (solid_of[tri_id] == 0) { tris0++; pr0++; } else { tris1++; pr1++; }
+                const uint32_t *t = g->triangles + 3ull*tri_id; float dist;
+                int hit = intersect_triangle(o, d, vtx(g,t[0]), vtx(g,t[1]), vtx(g,t[2]), &dist);
+                if (hit && dist < best) { best = dist; best_tri = tri_id; }
+            }
+            for (int a = 0; a < nh; a++) for (int b = a+1; b < nh; b++) if (ht[b] > ht[a]) { float tt=ht[a]; ht[a]=ht[b]; ht[b]=tt; uint32_t ww=hw[a]; hw[a]=hw[b]; hw[b]=ww; }
+            for (int a = 0; a < nh; a++) { sw[sp]=hw[a]; st[sp]=ht[a]; sp++; }
+            int found = 0;
+            while (sp > 0) { sp--; if (!(st[sp] > best)) { cur = sw[sp]; found = 1; break; } }
+            if (!found) break;
+        }
+        tri_out[i] = best_tri; per_ray[3*i]=pr0; per_ray[3*i+1]=pr1; per_ray[3*i+2]=prr;
+        if (best_tri >= 0) { if (solid_of[best_tri] == 0) win0++; else win1++; }
+    }
+    counters[0]=rounds; counters[1]=entries; counters[2]=tris0; counters[3]=tris1; counters[4]=halves; counters[5]=win0; counters[6]=win1; counters[7]=inner_hits;
+}
