@@ -441,7 +441,9 @@ def run_ours(args):
                    'triangles': int(len(det.mesh.triangles)), 'bvh_nodes': int(len(det.bvh.nodes)),
                    'channels': int(det.num_channels()), 'rng_pool': int(len(rng)),
                    'l2': 'flushed between steps (cb_flush_l2 writes 2x L2) and node+triangle arrays exceed L2',
-                   'parallelism': 'photon banks sharded x%d, geometry replicated' % world},
+                   'parallelism': 'photon banks sharded x%d, geometry replicated' % world,
+                   'tree': '%s, leaf split %s' % (os.environ.get('CHROMA_B200_TREE') or 'solids first',
+                                                  os.environ.get('CHROMA_B200_LEAF_SPLIT') or 'off')},
         'e2e': {'value': e2e, 'unit': 'photons/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h)},
         'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu_baseline,
         'extra': {'steps_per_photon': steps_taken / float(n * args.steps), 'wall_s': wall, 'setup': timings,
