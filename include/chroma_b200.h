@@ -226,7 +226,9 @@ int cb_native_tree_build(const uint32_t* ref_nodes, uint64_t nnodes, uint64_t nt
  * world_origin / world_scale).  min_extent: shortest box side (grid quanta) worth splitting;
  * min_ratio: split while the box surface exceeds min_ratio x the surface of a tight box.
  * cb_geometry_create does the same when CHROMA_B200_LEAF_SPLIT=max_pieces[,min_extent[,min_ratio]]
- * is set (default: one leaf per triangle).  Results of a traversal are unchanged. */
+ * is set (default: one leaf per triangle).  NOT exact with respect to the reference: a ray that grazes a
+ * sliver can get the reference's (float32-spurious) hit on it only through the sliver's full leaf box;
+ * measured rate 0 of 2 M random rays, 1 of 40,000 rays aimed at corners / edges. */
 int cb_native_tree_build_split(const uint32_t* ref_nodes, uint64_t nnodes, uint64_t ntriangles,
                                const uint32_t* solid_id, const float* vertices,
                                const uint32_t* triangles, const float world_origin[3],

@@ -52,10 +52,13 @@ def test_engine_replays_reference_kernel_fixture(gpu_ready, name):
         assert np.array_equal(ch.t, g[name + '.daq_t']) and np.array_equal(ch.q, g[name + '.daq_q'])
 
 
-def test_leaf_split_tree_gives_identical_results(gpu_ready, monkeypatch):
-    """CHROMA_B200_LEAF_SPLIT (bvh_native.cu: several tighter leaves per loosely bounded triangle) and
-    CHROMA_B200_TREE=single (one hierarchy over all leaves) change the traversal tree only: nearest hits (triangle and distance, ties included) and whole propagations
-    are bit-identical to the one-leaf-per-triangle tree."""
+def test_tree_options_against_the_default_tree(gpu_ready, monkeypatch):
+    """CHROMA_B200_TREE=single (one hierarchy over all leaves) changes the traversal tree only: nearest hits
+    (triangle and distance, ties included) and whole propagations are bit-identical to the default tree.
+    CHROMA_B200_LEAF_SPLIT (several tighter leaves per loosely bounded triangle) is NOT exact: the reference's
+    float32 triangle test can report a hit several mm away from the triangle for a ray that grazes a sliver, the
+    reference finds it because the ray is inside the sliver's big leaf box, a split tree does not look there
+    (DESIGN section 7-0).  Measured here: how rare that is on random rays and on rays aimed at corners / edges."""
     from chroma_lite_b200.sample import uniform_sphere
     geo = scenes.tiny_detector()
     rng = np.random.default_rng(3)
@@ -73,7 +76,8 @@ def test_leaf_split_tree_gives_identical_results(gpu_ready, monkeypatch):
     d = np.concatenate([d, aim - o[n:]]).astype(np.float32)
     ph = scenes.point_source(60000, seed=6, wl_range=(300, 600))
     results = []
-    for spec, tree in ((None, None), ('4,8,8', None), ('16,4,1.5', None), (None, 'single'), ('8,8,2', 'single')):
+    variants = ((None, None), (None, 'single'), ('4,8,8', None), ('16,4,1.5', None), ('8,8,2', 'single'))
+    for spec, tree in variants:
         for key, val in (('CHROMA_B200_LEAF_SPLIT', spec), ('CHROMA_B200_TREE', tree)):
             if val is None:
                 monkeypatch.delenv(key, raising=False)
@@ -84,16 +88,23 @@ def test_leaf_split_tree_gives_identical_results(gpu_ready, monkeypatch):
         gp = gpu.GPUPhotons(ph)
         gp.propagate(g, gpu.get_rng_states(len(ph), seed=12), nthreads_per_block=256, max_blocks=(len(ph) + 255) // 256,
                      max_steps=100)
-        results.append((tri.get(), dist.get(), gp.get(), g.gpudata if hasattr(g, 'gpudata') else None))
+        results.append((tri.get(), dist.get(), gp.get()))
     monkeypatch.delenv('CHROMA_B200_LEAF_SPLIT', raising=False)
     monkeypatch.delenv('CHROMA_B200_TREE', raising=False)
-    tri0, dist0, end0, _ = results[0]
+    tri0, dist0, end0 = results[0]
     assert (tri0 >= 0).mean() > 0.3
-    for tri, dist, end, _ in results[1:]:
-        assert np.array_equal(tri, tri0)
-        assert np.array_equal(dist.view(np.uint32), dist0.view(np.uint32))
-        for f in ('pos', 'dir', 'pol', 't', 'wavelengths', 'flags', 'last_hit_triangles'):
-            assert np.array_equal(getattr(end, f), getattr(end0, f)), f
+    for (spec, tree), (tri, dist, end) in zip(variants[1:], results[1:]):
+        same = (tri == tri0) & (dist.view(np.uint32) == dist0.view(np.uint32))
+        same_end = (end.flags == end0.flags) & (end.last_hit_triangles == end0.last_hit_triangles)
+        print('tree %s split %s: rays identical %d of %d random, %d of %d aimed; histories identical %.6f'
+              % (tree, spec, same[:n].sum(), n, same[n:].sum(), len(same) - n, same_end.mean()))
+        if spec is None:                                   # same leaves, other hierarchy: exact
+            assert same.all()
+            for f in ('pos', 'dir', 'pol', 't', 'wavelengths', 'flags', 'last_hit_triangles'):
+                assert np.array_equal(getattr(end, f), getattr(end0, f)), f
+        else:                                              # split leaves: exact up to the grazing-ray cases
+            assert same[:n].mean() > 0.9999 and same[n:].mean() > 0.999 and same_end.mean() > 0.999
+            assert ((tri >= 0) == (tri0 >= 0)).mean() > 0.9999
 
 
 def test_photon_tracking_steps(gpu_ready):
