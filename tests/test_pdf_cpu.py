@@ -129,3 +129,41 @@ def test_host_estimators_without_gpu(monkeypatch):
     k.compute_bandwidth(np.array([1, 0]), np.array([41.0, 0.0]), np.array([5.0, 0.0]))
     inv_t = k.inv_time_bandwidths_gpu.get()
     assert inv_t[0] > 0 and np.isfinite(inv_t[0])
+
+
+def test_likelihood_host_layer_without_gpu():
+    """chroma/likelihood.py:47-180 over a stand-in simulation: hit / not-hit terms with the half-count floor,
+    flat-density floor for channels without Monte Carlo data, mean and standard error of the kernel estimates."""
+    from chroma_lite_b200 import event
+    from chroma_lite_b200.likelihood import Likelihood
+    hit = np.array([True, True, False, False, True])
+    ev = event.Event(channels=event.Channels(hit, np.array([10.0, 20.0, 1e9, 1e9, 30.0], np.float32),
+                                             np.array([1.0, 1.0, 0.0, 0.0, 2.0], np.float32)))
+
+    class FakeSim(object):
+        def __init__(self):
+            self.calls = []
+
+        def eval_pdf(self, channels, it, min_twidth, trange, min_qwidth, qrange, **kw):
+            self.calls.append(('pdf', len(list(it)), min_twidth, kw))
+            return (np.array([80, 0, 8, 0, 40]), np.array([0.05, 0.0, 0.0, 0.0, np.nan], np.float32),
+                    np.array([0.01, 0.0, 0.0, 0.0, 0.0], np.float32))
+
+        def eval_kernel(self, channels, events, trange, qrange, **kw):
+            self.calls.append(('kernel', len(events), kw))
+            k = len([c for c in self.calls if c[0] == 'kernel'])
+            return np.zeros(5), np.array([0.01 * k, 0.02, 0.0, 0.0, 0.04], np.float32), np.zeros(5, np.float32)
+    fs = FakeSim()
+    lk = Likelihood(fs, ev, trange=(0.0, 100.0))
+    nll = lk.eval(iter(range(1000)), nevals=4, nreps=2, ndaq=10)                      # ntotal = 80
+    assert fs.calls[0][:3] == ('pdf', 4, 0.2) and fs.calls[0][3]['min_bin_content'] == 320
+    p = np.array([80 / 80, 0.5 / 80, 1 - 8 / 80, 1.0, 40 / 80])                        # floor for the hit channel with no MC hits
+    want = -(np.log(p).sum() + np.log([0.05, 0.01, 0.01]).sum())                       # 1/(100-0) where the PDF is 0 / NaN
+    assert np.isclose(float(nll), want, rtol=1e-6) and lk.channels_without_data == 2
+    gen = iter(range(1000))
+    res = lk.eval_kernel(gen, nevals=3, nreps=1, ndaq=1, navg=4)
+    lls = [np.log([0.01 * k, 0.02, 0.04]).sum() for k in (1, 2, 3, 4)]
+    assert np.isclose(res.nominal_value, -np.mean(lls)) and np.isclose(res.std_dev, np.std(lls) / 2.0)
+    assert next(gen) == 12 and [c[1] for c in fs.calls if c[0] == 'kernel'] == [3, 3, 3, 3]
+    lk2 = Likelihood(fs, ev, trange=(0.0, 100.0), qrange=(0.0, 10.0), time_only=False)
+    assert np.isclose(lk2._pdf_floor(), 1e-3)
