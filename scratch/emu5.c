@@ -33,6 +33,9 @@ static int phased_box(const phased_ray *r, const uint32_t *w, float *tnear)
     *tnear = tmin;
     return !(tmin > tmax);
 }
+static uint64_t g_occ_hist[513]; static int g_occ_max = 0;   /* stack entries held after a node expansion (nearest child taken directly) */
+ORC_EXPORT int emu2_get_occupancy(uint64_t *hist) { memcpy(hist, g_occ_hist, sizeof(g_occ_hist)); return g_occ_max; }
+ORC_EXPORT void emu2_reset_occupancy(void) { memset(g_occ_hist, 0, sizeof(g_occ_hist)); g_occ_max = 0; }
 static int g_leaf_mode = 0;   /* 0: test leaves as found; 1: per node, nearest box first, re-checked against the best hit; 2: LIFO queue re-checked (the kernel) */
 ORC_EXPORT void emu2_set_leaf_mode(int m) { g_leaf_mode = m; }
 static int64_t g_dbg = -1; static float g_rec[4096]; static int g_nrec = 0;
@@ -84,6 +87,7 @@ ORC_EXPORT void emu2_intersect(const CbGeometryDesc *g, const uint32_t *solid_of
             }
             for (int a = 0; a < nh; a++) for (int b = a+1; b < nh; b++) if (ht[b] > ht[a]) { float tt=ht[a]; ht[a]=ht[b]; ht[b]=tt; uint32_t ww=hw[a]; hw[a]=hw[b]; hw[b]=ww; }
             for (int a = 0; a < nh; a++) { sw[sp]=hw[a]; st[sp]=ht[a]; sp++; }
+            { int occ = sp > 0 ? sp - 1 : 0; if (occ > 512) occ = 512; g_occ_hist[occ]++; if (occ > g_occ_max) g_occ_max = occ; }
             int found = 0;
             while (sp > 0) { sp--; if (!(st[sp] > (g_phased ? best + 2e-5f * best : best))) { cur = sw[sp]; found = 1; break; } }
             if (!found) break;

@@ -109,8 +109,10 @@ def test_tree_options_against_the_default_tree(gpu_ready, monkeypatch):
 
 def test_photon_tracking_steps(gpu_ready):
     """propagate(track=True) (gpu/photon.py:249-283): ids of the photons that enter every step and their state
-    after it; stepping one launch at a time ends in the same state as one call; Simulation(photon_tracking=True)
-    turns the snapshots into per-photon tracks (sim.py:117-130)."""
+    after it; stepping one launch at a time follows the same histories as one call (not bit-identically: every launch
+    renormalises dir and pol in its prologue like propagate.cu:285-287, see the oracle's
+    test_stepping_one_launch_at_a_time_vs_one_call); Simulation(photon_tracking=True) turns the snapshots into
+    per-photon tracks (sim.py:117-130)."""
     from chroma_lite_b200 import sim
     geo = scenes.tiny_detector()
     n = 5000
@@ -133,11 +135,14 @@ def test_photon_tracking_steps(gpu_ready):
         sel = last_seen[ids[k]] == k
         assert np.array_equal(snaps[k].flags[sel], end.flags[ids[k][sel]])
         assert np.array_equal(snaps[k].pos[sel], end.pos[ids[k][sel]])
-    # same end state as one call over all steps (same RNG streams, one step per launch or not)
+    # same histories as one call over all steps (same RNG streams; vectors a few ulp apart through the per-launch
+    # renormalisation of dir / pol)
     gp2 = gpu.GPUPhotons(ph)
     gp2.propagate(g, gpu.get_rng_states(n, seed=2), nthreads_per_block=256, max_blocks=(n + 255) // 256, max_steps=30)
     end2 = gp2.get()
-    assert np.array_equal(end.flags, end2.flags) and np.array_equal(end.pos, end2.pos)
+    same = (end.flags == end2.flags) & (end.last_hit_triangles == end2.last_hit_triangles)
+    assert same.mean() > 0.995
+    assert np.abs(end.pos[same] - end2.pos[same]).max() < 1e-2 and np.allclose(end.t[same], end2.t[same], rtol=1e-5, atol=1e-4)
     s = sim.Simulation(geo, seed=3, photon_tracking=True, nthreads_per_block=256, max_blocks=32)
     ev = next(s.simulate(scenes.point_source(800, seed=15, wl_range=(300, 600)), keep_photons_end=True, max_steps=20))
     assert len(ev.photon_tracks) == 800

@@ -184,3 +184,30 @@ def test_oracle_daq_replays_reference_kernel():
     assert np.allclose(tint.view(np.float32), g['tiny.daq_t'], rtol=1e-6)
     hit = g['tiny.daq_t'] < 1e8
     assert hit.sum() > 10 and np.array_equal(hit, tint.view(np.float32) < 1e8)
+
+
+def test_stepping_one_launch_at_a_time_vs_one_call():
+    """propagate.cu:254-366 keeps nothing between steps except the photon record and its RNG state (the State is
+    refilled by fill_state every step), but every launch renormalises dir and pol in its prologue (propagate.cu:285-287),
+    so max_steps launches of one step -- the reference's own host loop and propagate(track=True),
+    gpu/photon.py:249-283 -- follow the same histories as one launch of max_steps with the vectors a few ulp apart,
+    not bit-identically.  The engine's tracking path (one cb_propagate call per step) inherits exactly this."""
+    geo = scenes.tiny_detector()
+    n = 3000
+    ph = scenes.point_source(n, seed=14, wl_range=(300, 600))
+    desc, keep = scenes.desc_of(geo)
+    one, _ = orc.propagate(desc, ph, orc.rng_init(2, 0, n), max_steps=30)
+    states, bank = orc.rng_init(2, 0, n), orc.HostBank(ph)
+    alive = []
+    for _ in range(30):
+        alive.append(int(((bank.flags & event.TERMINAL_MASK) == 0).sum()))
+        orc.propagate(desc, bank, states, max_steps=1)
+    assert alive[0] == n and alive[-1] < alive[1] < n and all(a >= b for a, b in zip(alive, alive[1:]))
+    same = (one.flags == bank.flags) & (one.last_hit_triangles == bank.last_hit_triangles)
+    assert same.mean() > 0.995
+    assert np.array_equal(one.wavelengths[same], bank.wavelengths[same])
+    for f, tol in (('pos', 1e-2), ('dir', 1e-5), ('pol', 1e-5)):
+        assert np.abs(getattr(one, f)[same] - getattr(bank, f)[same]).max() < tol, f
+    assert np.allclose(one.t[same], bank.t[same], rtol=1e-5, atol=1e-4)
+    # and the vectors do differ in a few photons: the renormalisation is not a no-op in float32
+    assert 0 < (one.dir != bank.dir).any(axis=1).sum() < n // 10
