@@ -20,5 +20,8 @@ run single             CHROMA_B200_TREE=single
 run split8             CHROMA_B200_LEAF_SPLIT=8,8,2
 run single_split8      CHROMA_B200_TREE=single CHROMA_B200_LEAF_SPLIT=8,8,2
 run single_split4      CHROMA_B200_TREE=single CHROMA_B200_LEAF_SPLIT=4,8,2
+# single level holds more stack entries (scratch/emu_stack.py: 1.0 % of the expansions above 16 vs 0.05 %): same tree with
+# 24 shared-memory entries per lane; build the variant first with: bash scratch/mkvariant.sh pstack24 "-DCB_PSTACK_N=24"
+[ -f scratch/lib_pstack24.so ] && run single_pstack24 CHROMA_B200_TREE=single CHROMA_B200_LIB=$PWD/scratch/lib_pstack24.so
 run default_again      X=1
 cat $OUT
