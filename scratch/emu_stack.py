@@ -44,6 +44,6 @@ for label, sid in (('solids first (default)', geo.solid_id), ('single level', No
     ref = tri if ref is None else ref
     exp = hist.sum()
     print('%-24s build %.0f s, %d entries | expansions/ray %.1f | stack entries held: max %d, mean %.2f, '
-          'expansions with > 8: %.4f, > 16 (local-memory spill): %.5f, > 32: %.6f | same triangles as default: %.6f'
+          'expansions with > 8: %.4f, > 16 (local-memory spill): %.5f, > 24: %.6f, > 32: %.6f | same triangles as default: %.6f'
           % (label, time.time() - t, len(nat), c[0], mx, (hist * np.arange(513)).sum() / exp, hist[9:].sum() / exp,
-             hist[17:].sum() / exp, hist[33:].sum() / exp, (tri == ref).mean()), flush=True)
+             hist[17:].sum() / exp, hist[25:].sum() / exp, hist[33:].sum() / exp, (tri == ref).mean()), flush=True)
