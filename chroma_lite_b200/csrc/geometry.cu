@@ -276,6 +276,10 @@ int cb_geometry_destroy(cb_geom_t h)
     Geometry* g = geoms().take(h);
     if (!g) return fail(CB_ERR_INVALID, "cb_geometry_destroy: bad handle");
     cudaStreamSynchronize(ctx().stream);
+    if (ctx().l2_window_base == (g->native_nodes ? (const void*)g->native_nodes : (const void*)g->nodes)) {
+        ctx().l2_window_base = nullptr;      // a later allocation may reuse the address
+        ctx().l2_window_bytes = ~(size_t)0;
+    }
     free_geometry(g);
     return CB_OK;
 }

@@ -17,6 +17,10 @@ struct Context {
     int device = -1;
     int sm_count = 0;
     size_t l2_bytes = 0;
+    size_t l2_persist_max = 0;            // cudaDevAttrMaxPersistingL2CacheSize
+    size_t l2_window_max = 0;             // cudaDevAttrMaxAccessPolicyWindowSize
+    const void* l2_window_base = nullptr; // what the kernel stream's access-policy window currently covers
+    size_t l2_window_bytes = 0;
     int max_smem_optin = 0;
     cudaStream_t stream = nullptr;        // kernels
     cudaStream_t copy_stream = nullptr;   // host<->device copies, bank initialisation
@@ -97,6 +101,9 @@ struct Registry {
     T* get(uint64_t id) { std::lock_guard<std::mutex> l(mu); auto it = map.find(id); return it == map.end() ? nullptr : it->second; }
     T* take(uint64_t id) { std::lock_guard<std::mutex> l(mu); auto it = map.find(id); if (it == map.end()) return nullptr; T* p = it->second; map.erase(it); return p; }
 };
+// mark the leading `bytes` of the traversal tree (breadth-first: its top levels) as persisting in L2
+// for the kernels of the library stream; no-op when already set for this geometry
+int l2_pin_tree_prefix(const Geometry* g);
 Registry<Geometry>& geoms();
 Registry<RngPool>& rngs();
 Registry<Daq>& daqs();

@@ -900,6 +900,7 @@ int cb_intersect(cb_geom_t gh, const float* d_origins, const float* d_directions
     if (!d_origins || !d_directions || !d_triangle_out || !d_distance_out)
         return fail(CB_ERR_INVALID, "cb_intersect: null array");
     Context& c = ctx();
+    if (int lrc = l2_pin_tree_prefix(g)) return lrc;
     CB_CUDA(cudaMemsetAsync(c.d_counters, 0, 16 * sizeof(unsigned long long), c.stream));
     const size_t smem = stack_smem_bytes();
     CB_CUDA(cudaFuncSetAttribute(intersect_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -942,6 +943,7 @@ int cb_propagate(const CbPhotonBank* bank, cb_geom_t gh, cb_rng_t rh, int32_t nt
     if (stats) { memset(stats, 0, sizeof(*stats)); }
     if (bank->n == 0 || max_steps <= 0) return CB_OK;
     Context& c = ctx();
+    if (int lrc = l2_pin_tree_prefix(g)) return lrc;
     const bool count = getenv("CHROMA_B200_STATS") != nullptr;
     const Tune tune = tune_from_env();
     const bool trace = getenv("CHROMA_B200_TRACE") != nullptr;   // per-step timing to stderr (debug aid)

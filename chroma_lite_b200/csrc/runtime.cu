@@ -1,6 +1,11 @@
 // runtime.cu -- context, memory, timers and the XORWOW state pool.
 #include "host.h"
 #include <string.h>
+#include <stdlib.h>
+#include <algorithm>
+#ifndef CB_L2_WINDOW_MB_DEFAULT
+#define CB_L2_WINDOW_MB_DEFAULT 0.0   /* until measured */
+#endif
 
 namespace cb {
 
@@ -31,6 +36,42 @@ static Registry<Daq> g_daqs;
 Registry<Geometry>& geoms() { return g_geoms; }
 Registry<RngPool>& rngs() { return g_rngs; }
 Registry<Daq>& daqs() { return g_daqs; }
+
+// ---------------------------------------------------------------- L2 persistence
+// The engine's tree is stored breadth-first, so its first bytes are its top levels: the part every
+// ray walks.  An access-policy window on the kernel stream marks that prefix as persisting, so the
+// per-photon streaming traffic (bank, queues, triangle records of one-off leaves) cannot evict it.
+// CHROMA_B200_L2_WINDOW_MB: size of the prefix (0 = no window).
+int l2_pin_tree_prefix(const Geometry* g)
+{
+    Context& c = ctx();
+    const double want_mb = getenv("CHROMA_B200_L2_WINDOW_MB") ? atof(getenv("CHROMA_B200_L2_WINDOW_MB")) : CB_L2_WINDOW_MB_DEFAULT;
+    const void* base = g->native_nodes ? (const void*)g->native_nodes : (const void*)g->nodes;
+    const size_t have = (g->native_nodes ? g->nnative : g->nnodes) * sizeof(uint4);
+    size_t bytes = std::min<size_t>((size_t)(want_mb * 1048576.0), have);
+    bytes = std::min(bytes, c.l2_window_max);
+    if (c.l2_persist_max == 0) bytes = 0;
+    if (base == c.l2_window_base && bytes == c.l2_window_bytes) return CB_OK;
+    cudaStreamAttrValue attr;
+    memset(&attr, 0, sizeof(attr));
+    if (bytes) {
+        const size_t carve = std::min(bytes, c.l2_persist_max);
+        CB_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve));
+        attr.accessPolicyWindow.base_ptr = const_cast<void*>(base);
+        attr.accessPolicyWindow.num_bytes = bytes;
+        attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)carve / (double)bytes);
+        attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+    } else {
+        attr.accessPolicyWindow.num_bytes = 0;
+        attr.accessPolicyWindow.hitProp = cudaAccessPropertyNormal;
+        attr.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+    }
+    CB_CUDA(cudaStreamSetAttribute(c.stream, cudaStreamAttributeAccessPolicyWindow, &attr));
+    if (!bytes && c.l2_window_bytes) { cudaCtxResetPersistingL2Cache(); cudaGetLastError(); }
+    c.l2_window_base = base; c.l2_window_bytes = bytes;
+    return CB_OK;
+}
 
 // ---------------------------------------------------------------- XORWOW skip matrices
 // 160x160 GF(2) matrices in cuRAND's row layout (row i = image of state bit i,
@@ -189,10 +230,9 @@ int cb_init(int device)
     CB_CUDA(cudaMalloc(&c.d_counters, 16 * sizeof(unsigned long long)));
     CB_CUDA(cudaMemset(c.d_counters, 0, 16 * sizeof(unsigned long long)));
     CB_CUDA(cudaMallocHost(&c.h_counters, 16 * sizeof(unsigned long long)));
-    // keep the hot top of the BVH resident: let persisting lines use most of L2
-    if (prop.persistingL2CacheMaxSize > 0)
-        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)prop.persistingL2CacheMaxSize);
-    cudaGetLastError();
+    // L2 persistence: the carve-out is sized when a geometry's tree prefix is pinned (l2_pin_tree_prefix)
+    c.l2_persist_max = (size_t)prop.persistingL2CacheMaxSize;
+    c.l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
     c.device = device;
     return CB_OK;
 }

@@ -16,13 +16,26 @@ def main():
     n = int(os.environ.get('PHOTONS', '2500000'))
     bench._workload = workload
     det = bench.build_detector(workload, {})
-    s = sim.Simulation(det, seed=42, cuda_device=0, nthreads_per_block=512, max_blocks=max(1024, -(-n // 512)))
-    g, rng = s.gpu_geometry, s.rng_states
+    state = {'tree': None, 's': None}
+
+    def simulation(tree):
+        # the traversal tree is chosen when the geometry is created: a spec with TREE=... gets its own Simulation
+        if state['s'] is None or tree != state['tree']:
+            state['s'] = None
+            os.environ['CHROMA_B200_TREE'] = tree
+            t0 = time.perf_counter()
+            state['s'] = sim.Simulation(det, seed=42, cuda_device=0, nthreads_per_block=512, max_blocks=max(1024, -(-n // 512)))
+            state['tree'] = tree
+            print('     geometry upload (tree %r) %.1f s' % (tree, time.perf_counter() - t0), flush=True)
+        return state['s']
+    s = simulation(os.environ.get('CHROMA_B200_TREE', ''))
     ev = bench.make_event(n, seed=1000)
     gp = gpu.GPUPhotons(ev); pristine = gpu.GPUPhotons(ev)
     fields = ('pos', 'dir', 'pol', 'wavelengths', 't', 'last_hit_triangles', 'flags', 'weights', 'evidx')
 
     def one():
+        s = state['s']
+        g, rng = s.gpu_geometry, s.rng_states
         for f in fields:
             getattr(gp, f).copy_from_device(getattr(pristine, f).ptr)
         lib.cb_flush_l2()
@@ -34,6 +47,9 @@ def main():
         keys = []
         for kv in filter(None, spec.split(',')):
             k, v = kv.split('=')
+            if k == 'TREE':
+                simulation(v)
+                continue
             os.environ['CHROMA_B200_' + k] = v
             keys.append('CHROMA_B200_' + k)
         tr = os.environ.pop('CHROMA_B200_TRACE', None)
