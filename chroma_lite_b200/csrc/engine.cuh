@@ -7,7 +7,6 @@
 // with the same nvcc flags (--use_fast_math, default -fmad), decisions replay.
 #pragma once
 #include <cuda_runtime.h>
-#include <cuComplex.h>
 #include <stdint.h>
 #include <float.h>
 #include "../../include/chroma_b200.h"
@@ -107,7 +106,7 @@ struct DevGeometry {
     uint32_t ref_root_x, ref_root_y, ref_root_z;   // the reference tree's root box
     uint32_t smem_floats;     // leading floats of the pool staged into shared memory
     uint32_t nmaterials, nsurfaces;
-    const CbWirePlane* wireplanes;   // analytic wire planes (cold path; usually none)
+    const struct WireFrame* wireframes;   // analytic wire planes in their own frames (cold path; usually none)
     int32_t nwireplanes;
 };
 
@@ -179,30 +178,31 @@ struct RaySetup {
 
 // slab test on a packed node, same dequantisation and arithmetic as
 // geometry.h:31-47 + intersect.h:112-157.  Returns tmin through `tnear`.
-__device__ __forceinline__ bool hit_box(const DevGeometry& g, const RaySetup& r, uint32_t px,
+struct WorldGrid { float3 origin; float scale; };
+__device__ __forceinline__ bool hit_box(const WorldGrid& g, const RaySetup& r, uint32_t px,
                                         uint32_t py, uint32_t pz, float& tnear)
 {
     const float INF = __int_as_float(0x7f800000);
     float tmin = 0.0f, tmax = INF;
     if (r.fx) {
-        float lo = __fmaf_rn(u16f_lo(px), g.world_scale, g.world_origin.x);
-        float hi = __fmaf_rn(u16f_hi(px), g.world_scale, g.world_origin.x);
+        float lo = __fmaf_rn(u16f_lo(px), g.scale, g.origin.x);
+        float hi = __fmaf_rn(u16f_hi(px), g.scale, g.origin.x);
         float t0 = __fmaf_rn(lo, r.inv.x, r.noid.x);
         float t1 = __fmaf_rn(hi, r.inv.x, r.noid.x);
         tmin = fmaxf(tmin, fminf(t0, t1));
         tmax = fminf(tmax, fmaxf(t0, t1));
     }
     if (r.fy) {
-        float lo = __fmaf_rn(u16f_lo(py), g.world_scale, g.world_origin.y);
-        float hi = __fmaf_rn(u16f_hi(py), g.world_scale, g.world_origin.y);
+        float lo = __fmaf_rn(u16f_lo(py), g.scale, g.origin.y);
+        float hi = __fmaf_rn(u16f_hi(py), g.scale, g.origin.y);
         float t0 = __fmaf_rn(lo, r.inv.y, r.noid.y);
         float t1 = __fmaf_rn(hi, r.inv.y, r.noid.y);
         tmin = fmaxf(tmin, fminf(t0, t1));
         tmax = fminf(tmax, fmaxf(t0, t1));
     }
     if (r.fz) {
-        float lo = __fmaf_rn(u16f_lo(pz), g.world_scale, g.world_origin.z);
-        float hi = __fmaf_rn(u16f_hi(pz), g.world_scale, g.world_origin.z);
+        float lo = __fmaf_rn(u16f_lo(pz), g.scale, g.origin.z);
+        float hi = __fmaf_rn(u16f_hi(pz), g.scale, g.origin.z);
         float t0 = __fmaf_rn(lo, r.inv.z, r.noid.z);
         float t1 = __fmaf_rn(hi, r.inv.z, r.noid.z);
         tmin = fmaxf(tmin, fminf(t0, t1));
@@ -212,15 +212,29 @@ __device__ __forceinline__ bool hit_box(const DevGeometry& g, const RaySetup& r,
     return !(tmin > tmax);
 }
 
-// slab test in the reference's arithmetic, recomputing the ray setup (rare path)
-static __device__ __noinline__ bool hit_box_exact(const DevGeometry& g, const float3 o, const float3 d,
-                                                  uint32_t px, uint32_t py, uint32_t pz, float& tnear)
+__device__ __forceinline__ RaySetup ray_setup(const float3& o, const float3& d)
 {
-    RaySetup rr;
-    rr.noid = f3(-o.x / d.x, -o.y / d.y, -o.z / d.z);
-    rr.inv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
-    rr.fx = isfinite(rr.inv.x); rr.fy = isfinite(rr.inv.y); rr.fz = isfinite(rr.inv.z);
-    return hit_box(g, rr, px, py, pz, tnear);
+    RaySetup r;
+    r.noid = f3(-o.x / d.x, -o.y / d.y, -o.z / d.z);
+    r.inv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    r.fx = isfinite(r.inv.x); r.fy = isfinite(r.inv.y); r.fz = isfinite(r.inv.z);
+    return r;
+}
+__device__ __forceinline__ WorldGrid world_grid(const DevGeometry& g)
+{
+    WorldGrid w = {g.world_origin, g.world_scale};
+    return w;
+}
+
+// slab test in the reference's arithmetic, recomputing the ray setup (rare path).  Everything
+// by value: a caller never has to park its ray in local memory for this call.  Returns the
+// entry distance (>= 0), or -1 when the ray misses the box.
+static __device__ __noinline__ float box_entry_exact(const float3 worigin, const float wscale, const float3 o, const float3 d,
+                                                     uint32_t px, uint32_t py, uint32_t pz)
+{
+    const WorldGrid w = {worigin, wscale};
+    float tnear;
+    return hit_box(w, ray_setup(o, d), px, py, pz, tnear) ? tnear : -1.0f;
 }
 
 // ------------------------------------------------------------------ traversal
@@ -230,23 +244,21 @@ constexpr int CB_RSTACK = 64;   // local stack of the reference-order fallback
 // children ascending, leaves tested on the spot, internal children pushed and
 // popped LIFO, prune against the current minimum).  Only used for the rare rays
 // the traversal flags as order-sensitive (see PTrav::finish).
+struct RayHit { int tri; float dist; };      // tri == -1: no hit (dist -1)
+
 template <bool COUNT>
-static __device__ __noinline__ int traverse_reference_order(const DevGeometry& g, const float3 origin,
-                                                            const float3 direction, int last_hit,
-                                                            float& min_distance, uint32_t* overflow_flag,
-                                                            TraverseCounters* cnt)
+static __device__ __noinline__ RayHit traverse_reference_order(const DevGeometry& g, const float3 origin,
+                                                               const float3 direction, int last_hit,
+                                                               uint32_t* overflow_flag, TraverseCounters* cnt)
 {
-    RaySetup r;
-    r.noid = f3(-origin.x / direction.x, -origin.y / direction.y, -origin.z / direction.z);
-    r.inv = f3(1.0f / direction.x, 1.0f / direction.y, 1.0f / direction.z);
-    r.fx = isfinite(r.inv.x); r.fy = isfinite(r.inv.y); r.fz = isfinite(r.inv.z);
-    int triangle_index = -1;
-    min_distance = -1.0f;
+    const RaySetup r = ray_setup(origin, direction);
+    const WorldGrid w = world_grid(g);
+    RayHit best = {-1, -1.0f};
     uint32_t stack[CB_RSTACK];
     {
         const uint4 root = __ldg(&g.ref_nodes[0]);
         float tn;
-        if (!hit_box(g, r, root.x, root.y, root.z, tn)) return -1;
+        if (!hit_box(w, r, root.x, root.y, root.z, tn)) return best;
     }
     int sp = 0;
     stack[sp++] = g.ref_root_w;
@@ -257,30 +269,26 @@ static __device__ __noinline__ int traverse_reference_order(const DevGeometry& g
             const uint4 nd = __ldg(&g.ref_nodes[i]);
             if (COUNT) cnt->nodes++;
             float tmin;
-            if (hit_box(g, r, nd.x, nd.y, nd.z, tmin) && (min_distance < 0.0f || !(tmin > min_distance))) {
-                const uint32_t w = nd.w;
-                if ((w >> 28) == 0) {
-                    if ((int)w != last_hit) {
-                        if (COUNT) cnt->tris++;
-                        const float4* tp = g.tri64 + 4ull * w;
-                        float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
-                        float t;
-                        if (hit_triangle(origin, direction, f3(a.x, a.y, a.z), f3(a.w, b.x, b.y), f3(b.z, b.w, c.x), t)) {
-                            if (triangle_index == -1 || t < min_distance) {
-                                triangle_index = (int)w;
-                                min_distance = t;
-                            }
-                        }
-                    }
-                } else if (sp < CB_RSTACK) {
-                    stack[sp++] = w;
-                } else {
-                    atomicOr(overflow_flag, 1u);
-                }
+            if (!hit_box(w, r, nd.x, nd.y, nd.z, tmin) || (best.dist >= 0.0f && tmin > best.dist)) continue;
+            const uint32_t child = nd.w;
+            if ((child >> 28) != 0) {
+                if (sp < CB_RSTACK) stack[sp++] = child;
+                else atomicOr(overflow_flag, 1u);
+                continue;
+            }
+            if ((int)child == last_hit) continue;
+            if (COUNT) cnt->tris++;
+            const float4* tp = g.tri64 + 4ull * child;
+            const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+            float t;
+            if (hit_triangle(origin, direction, f3(a.x, a.y, a.z), f3(a.w, b.x, b.y), f3(b.z, b.w, c.x), t) &&
+                (best.tri == -1 || t < best.dist)) {
+                best.tri = (int)child;
+                best.dist = t;
             }
         }
     }
-    return triangle_index;
+    return best;
 }
 
 // ------------------------------------------------------------------ phased traversal
@@ -424,7 +432,8 @@ struct PTrav {
         best_tri = -1; best_rank = 0xFFFFFFFFu; best_t = INF; limit = INF;
         sp = sbase; lq = lbase; lsp = 0; cur = g.root_w; cur_t = 0.0f; redo = false;
         float tn;                                  // the world-box test stays in the reference's arithmetic (mesh.h:60)
-        have = hit_box_exact(g, o, d, g.ref_root_x, g.ref_root_y, g.ref_root_z, tn) && (g.root_w >> 28) != 0;
+        tn = box_entry_exact(g.world_origin, g.world_scale, o, d, g.ref_root_x, g.ref_root_y, g.ref_root_z);
+        have = tn >= 0.0f && (g.root_w >> 28) != 0;
         return have;
     }
 
@@ -516,18 +525,16 @@ struct PTrav {
         load_ray(lbase, origin, direction);
         if (best_tri != -1 && !redo) {
             const float4 lb = __ldg(g.tri64 + 4ull * (uint32_t)best_tri + 3);
-            float box_t;
-            const bool in_box = hit_box_exact(g, origin, direction, __float_as_uint(lb.x), __float_as_uint(lb.y),
-                                              __float_as_uint(lb.z), box_t);
-            redo = !in_box || best_t < box_t;
+            const float box_t = box_entry_exact(g.world_origin, g.world_scale, origin, direction, __float_as_uint(lb.x),
+                                                __float_as_uint(lb.y), __float_as_uint(lb.z));
+            redo = box_t < 0.0f || best_t < box_t;
         }
         if (redo) {
             TraverseCounters local = {0, 0, 0};
-            float rd;
-            const int tri = traverse_reference_order<COUNT>(g, origin, direction, last_hit, rd, overflow_flag, &local);
+            const RayHit h = traverse_reference_order<COUNT>(g, origin, direction, last_hit, overflow_flag, COUNT ? &local : nullptr);
             if (COUNT) { cnt->nodes += local.nodes; cnt->tris += local.tris; cnt->resolved++; }
-            dist = rd;
-            return tri;
+            dist = h.dist;
+            return h.tri;
         }
         dist = (best_tri == -1) ? -1.0f : best_t;
         return best_tri;
@@ -560,12 +567,10 @@ __device__ __forceinline__ int warp_traverse(const DevGeometry& g, const float3&
     phased_ray_axis(origin.x, direction.x, g.world_origin.x, g.world_scale, r.sx, r.nx, r.fx, r.selx);
     phased_ray_axis(origin.y, direction.y, g.world_origin.y, g.world_scale, r.sy, r.ny, r.fy, r.sely);
     phased_ray_axis(origin.z, direction.z, g.world_origin.z, g.world_scale, r.sz, r.nz, r.fz, r.selz);
-    RaySetup rr;
-    rr.noid = f3(-origin.x / direction.x, -origin.y / direction.y, -origin.z / direction.z);
-    rr.inv = f3(1.0f / direction.x, 1.0f / direction.y, 1.0f / direction.z);
-    rr.fx = isfinite(rr.inv.x); rr.fy = isfinite(rr.inv.y); rr.fz = isfinite(rr.inv.z);
-    float tn;
-    if (!hit_box(g, rr, g.ref_root_x, g.ref_root_y, g.ref_root_z, tn) || (g.root_w >> 28) == 0) { dist = -1.0f; return -1; }
+    // world-box test and the winner's leaf-box check use the reference's arithmetic through a by-value
+    // call, so that its ray setup (9 registers) is not kept alive across the traversal loop
+    if (box_entry_exact(g.world_origin, g.world_scale, origin, direction, g.ref_root_x, g.ref_root_y, g.ref_root_z) < 0.0f ||
+        (g.root_w >> 28) == 0) { dist = -1.0f; return -1; }
     float best_t = INF, limit = INF;
     int best_tri = -1;
     uint32_t best_rank = 0xFFFFFFFFu;
@@ -653,834 +658,18 @@ __device__ __forceinline__ int warp_traverse(const DevGeometry& g, const float3&
     }
     if (best_tri != -1 && !redo) {
         const float4 lb = __ldg(g.tri64 + 4ull * (uint32_t)best_tri + 3);
-        float box_t;
-        const bool in_box = hit_box(g, rr, __float_as_uint(lb.x), __float_as_uint(lb.y), __float_as_uint(lb.z), box_t);
-        redo = !in_box || best_t < box_t;
+        const float box_t = box_entry_exact(g.world_origin, g.world_scale, origin, direction, __float_as_uint(lb.x),
+                                            __float_as_uint(lb.y), __float_as_uint(lb.z));
+        redo = box_t < 0.0f || best_t < box_t;
     }
     if (redo) {
         if (COUNT) cnt->resolved++;
-        return traverse_reference_order<COUNT>(g, origin, direction, last_hit, dist, overflow_flag, cnt);
+        const RayHit h = traverse_reference_order<COUNT>(g, origin, direction, last_hit, overflow_flag, COUNT ? cnt : nullptr);
+        dist = h.dist;
+        return h.tri;
     }
     dist = (best_tri == -1) ? -1.0f : best_t;
     return best_tri;
-}
-
-// ------------------------------------------------------------------ physics
-struct Photon {
-    float3 pos, dir, pol;
-    float wavelength, time, weight;
-    uint32_t history;        // 16 significant bits (photon.h:29)
-    int last_hit_triangle;
-};
-
-struct StepState {
-    float3 normal;
-    float n1, n2, absorption_length, scattering_length;
-    const CbMaterial* material1;
-    int surface_index;
-    float distance;
-};
-
-enum { CMD_BREAK = 0, CMD_CONTINUE = 1, CMD_PASS = 2 };
-
-// clamp-then-linear table lookup on the uniform wavelength grid (geometry.h:61-74)
-__device__ __forceinline__ float interp_property(const DevGeometry& g, float x, const float* fp)
-{
-    if (x < g.wavelength_start) return fp[0];
-    if (x > (g.wavelength_start + (g.wavelength_n - 1) * g.wavelength_step)) return fp[g.wavelength_n - 1];
-    int jl = (x - g.wavelength_start) / g.wavelength_step;
-    return fp[jl] + (x - (g.wavelength_start + jl * g.wavelength_step)) * (fp[jl + 1] - fp[jl]) / g.wavelength_step;
-}
-
-// inverse-CDF sampling on a uniform x grid (random.h:33-55)
-__device__ __forceinline__ float sample_cdf_uniform(Rng& rng, int ncdf, float x0, float delta, const float* cdf_y)
-{
-    float u = rng_uniform(rng);
-    int lower = 0, upper = ncdf - 1;
-    while (lower < upper - 1) {
-        int half = (lower + upper) / 2;
-        if (u < cdf_y[half]) upper = half; else lower = half;
-    }
-    float delta_cdf_y = cdf_y[upper] - cdf_y[lower];
-    return x0 + delta * lower + delta * (u - cdf_y[lower]) / delta_cdf_y;
-}
-
-// piecewise-linear interpolation by bisection (interpolate.h:33-58)
-__device__ __forceinline__ float interp_xy(float x, int n, const float* xp, const float* fp)
-{
-    int lower = 0, upper = n - 1;
-    if (x <= xp[lower]) return fp[lower];
-    if (x >= xp[upper]) return fp[upper];
-    while (lower < upper - 1) {
-        int half = (lower + upper) / 2;
-        if (x < xp[half]) upper = half; else lower = half;
-    }
-    float df = fp[upper] - fp[lower];
-    float dx = xp[upper] - xp[lower];
-    return fp[lower] + df * (x - xp[lower]) / dx;
-}
-
-// fractional index of x in xp (interpolate.h:5-29)
-__device__ __forceinline__ float interp_idx(float x, int n, const float* xp)
-{
-    int lower = 0, upper = n - 1;
-    if (x <= xp[lower]) return lower;
-    if (x >= xp[upper]) return upper;
-    while (lower < upper - 1) {
-        int half = (lower + upper) / 2;
-        if (x < xp[half]) upper = half; else lower = half;
-    }
-    float dx = xp[upper] - xp[lower];
-    return lower + 1.0 * (x - xp[lower]) / dx;
-}
-
-__device__ __forceinline__ int sext8(int c) { return (c & 0x80) ? (0xFFFFFF00 | c) : c; }
-__device__ __forceinline__ float get_theta(const float3& a, const float3& b)
-{
-    return acosf(fmaxf(-1.0f, fminf(1.0f, dot(a, b))));
-}
-
-// Classify the boundary found by the traversal (mesh branch of fill_state,
-// photon.h:355-394).  `tri` >= 0.
-__device__ __forceinline__ void classify_hit(const DevGeometry& g, const Tables& T, Photon& p,
-                                             StepState& s, int tri)
-{
-    p.last_hit_triangle = tri;
-    const float4* tp = g.tri64 + 4ull * (uint32_t)tri;
-    float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
-    float3 v0 = f3(a.x, a.y, a.z), v1 = f3(a.w, b.x, b.y), v2 = f3(b.z, b.w, c.x);
-    uint32_t material_code = __float_as_uint(c.z);
-    int inner = sext8(0xFF & (material_code >> 24));
-    int outer = sext8(0xFF & (material_code >> 16));
-    s.surface_index = sext8(0xFF & (material_code >> 8));
-
-    float3 v01 = v1 - v0;
-    float3 v12 = v2 - v1;
-    s.normal = normalize(cross(v01, v12));
-
-    const CbMaterial *m1, *m2;
-    if (dot(s.normal, -p.dir) > 0.0f) {
-        m1 = &g.materials[outer]; m2 = &g.materials[inner];
-    } else {
-        m1 = &g.materials[inner]; m2 = &g.materials[outer];
-        s.normal = -s.normal;
-    }
-    s.n1 = interp_property(g, p.wavelength, T.at(m1->refractive_index));
-    s.n2 = interp_property(g, p.wavelength, T.at(m2->refractive_index));
-    s.absorption_length = interp_property(g, p.wavelength, T.at(m1->absorption_length));
-    s.scattering_length = interp_property(g, p.wavelength, T.at(m1->scattering_length));
-    s.material1 = m1;
-}
-
-// new direction at polar angle theta / azimuth phi about `axis` (photon.h:399-424)
-__device__ __forceinline__ float3 pick_new_direction(float3 axis, float theta, float phi)
-{
-    float cos_theta, sin_theta;
-    sincosf(theta, &sin_theta, &cos_theta);
-    float cos_phi, sin_phi;
-    sincosf(phi, &sin_phi, &cos_phi);
-    float sin_axis_theta = sqrt(1.0f - axis.z * axis.z);
-    float cos_axis_phi, sin_axis_phi;
-    if (isnan(sin_axis_theta) || sin_axis_theta < 0.00001f) {
-        cos_axis_phi = 1.0f;
-        sin_axis_phi = 0.0f;
-    } else {
-        cos_axis_phi = axis.x / sin_axis_theta;
-        sin_axis_phi = axis.y / sin_axis_theta;
-    }
-    float dirx = cos_theta * axis.x + sin_theta * (axis.z * cos_phi * cos_axis_phi - sin_phi * sin_axis_phi);
-    float diry = cos_theta * axis.y + sin_theta * (cos_phi * axis.z * sin_axis_phi + sin_phi * cos_axis_phi);
-    float dirz = cos_theta * axis.z - sin_theta * cos_phi * sin_axis_theta;
-    return f3(dirx, diry, dirz);
-}
-
-// Rayleigh scattering about the polarisation axis (photon.h:426-453)
-__device__ __forceinline__ void rayleigh_scatter(Photon& p, Rng& rng)
-{
-    float cos_theta = 2.0f * cosf((acosf(1.0f - 2.0f * rng_uniform(rng)) - 2 * CB_PI) / 3.0f);
-    if (cos_theta > 1.0f) cos_theta = 1.0f;
-    else if (cos_theta < -1.0f) cos_theta = -1.0f;
-    float theta = acosf(cos_theta);
-    float phi = rng_range(rng, 0.0f, 2.0f * CB_PI);
-    p.dir = pick_new_direction(p.pol, theta, phi);
-    if (1.0f - fabsf(cos_theta) < 1e-6f) p.pol = pick_new_direction(p.pol, CB_PI / 2.0f, phi);
-    else p.pol = p.pol - cos_theta * p.dir;
-    p.dir = p.dir / norm(p.dir);
-    p.pol = p.pol / norm(p.pol);
-}
-
-// bulk step: absorption / re-emission / Rayleigh / reach boundary (photon.h:455-570)
-// to_boundary and at_boundary are inlined into the kernels (physics kernel 0.40 -> 0.35 ms: the photon
-// stays in registers across them).  The thin-film surface model stays ONE shared call: inlined copies differ
-// in the last bit between kernels (FMA contraction across the call boundary), which would make results depend
-// on the schedule (physics_step<WIRES, INLINE_SURFACES> exists for experiments only).
-#ifndef CB_PHYS_CALL
-#define CB_PHYS_CALL __forceinline__
-#endif
-#ifndef CB_PHYS_CALL2
-#define CB_PHYS_CALL2 __forceinline__
-#endif
-static __device__ CB_PHYS_CALL int to_boundary(const DevGeometry& g, const Tables& T, Photon& p, StepState& s,
-                                        Rng& rng, bool use_weights, int scatter_first)
-{
-    float absorption_distance = -s.absorption_length * logf(rng_uniform(rng));
-    float scattering_distance = -s.scattering_length * logf(rng_uniform(rng));
-
-    if (use_weights && p.weight > CB_WEIGHT_LOWER_THRESHOLD) absorption_distance = 1e30;
-    else use_weights = false;
-
-    if (scatter_first == 1) {
-        float scatter_prob = 1.0f - expf(-s.distance / s.scattering_length);
-        if (scatter_prob > CB_WEIGHT_LOWER_THRESHOLD) {
-            int i = 0;
-            while (i < 1000 && scattering_distance > s.distance) {
-                scattering_distance = -s.scattering_length * logf(rng_uniform(rng));
-                i++;
-            }
-            p.weight *= scatter_prob;
-        }
-    } else if (scatter_first == -1) {
-        float no_scatter_prob = expf(-s.distance / s.scattering_length);
-        if (no_scatter_prob > CB_WEIGHT_LOWER_THRESHOLD) {
-            int i = 0;
-            while (i < 1000 && scattering_distance <= s.distance) {
-                scattering_distance = -s.scattering_length * logf(rng_uniform(rng));
-                i++;
-            }
-            p.weight *= no_scatter_prob;
-        }
-    }
-
-    if (absorption_distance <= scattering_distance) {
-        if (absorption_distance <= s.distance) {
-            p.time += absorption_distance / (CB_SPEED_OF_LIGHT / s.n1);
-            p.pos = p.pos + absorption_distance * p.dir;
-            const CbMaterial* m = s.material1;
-            if (m->num_comp == 0) {
-                p.last_hit_triangle = -1;
-                p.history |= CB_BULK_ABSORB;
-                return CMD_BREAK;
-            }
-            float uniform_sample_comp = rng_uniform(rng);
-            float prob = 0.0f;
-            int comp;
-            for (comp = 0;; comp++) {
-                float comp_abs = interp_property(g, p.wavelength, T.at(m->comp_absorption_length + comp * g.wavelength_n));
-                prob += s.absorption_length / comp_abs;
-                if (uniform_sample_comp < prob || comp + 1 == m->num_comp) break;
-            }
-            float uniform_sample_reemit = rng_uniform(rng);
-            float comp_reemit_prob = interp_property(g, p.wavelength, T.at(m->comp_reemission_prob + comp * g.wavelength_n));
-            if (uniform_sample_reemit < comp_reemit_prob) {
-                p.wavelength = sample_cdf_uniform(rng, g.wavelength_n, g.wavelength_start, g.wavelength_step,
-                                                  T.at(m->comp_reemission_wvl_cdf + comp * g.wavelength_n));
-                p.time += sample_cdf_uniform(rng, g.time_n, g.time_start, g.time_step,
-                                             T.at(m->comp_reemission_time_cdf + comp * g.time_n));
-                p.dir = rng_sphere(rng);
-                p.pol = cross(rng_sphere(rng), p.dir);
-                p.pol = p.pol / norm(p.pol);
-                p.last_hit_triangle = -1;
-                p.history |= CB_BULK_REEMIT;
-                return CMD_CONTINUE;
-            }
-            p.last_hit_triangle = -1;
-            p.history |= CB_BULK_ABSORB;
-            return CMD_BREAK;
-        }
-    } else {
-        if (scattering_distance <= s.distance) {
-            if (use_weights) p.weight *= expf(-scattering_distance / s.absorption_length);
-            p.time += scattering_distance / (CB_SPEED_OF_LIGHT / s.n1);
-            p.pos = p.pos + scattering_distance * p.dir;
-            rayleigh_scatter(p, rng);
-            p.history |= CB_RAYLEIGH_SCATTER;
-            p.last_hit_triangle = -1;
-            return CMD_CONTINUE;
-        }
-    }
-    if (use_weights) p.weight *= expf(-s.distance / s.absorption_length);
-    p.pos = p.pos + s.distance * p.dir;
-    p.time += s.distance / (CB_SPEED_OF_LIGHT / s.n1);
-    return CMD_PASS;
-}
-
-// Fresnel reflection / refraction (photon.h:572-632)
-static __device__ CB_PHYS_CALL2 void at_boundary(Photon& p, StepState& s, Rng& rng)
-{
-    float incident_angle = get_theta(s.normal, -p.dir);
-    float refracted_angle = asinf(sinf(incident_angle) * s.n1 / s.n2);
-
-    float3 incident_plane_normal = cross(p.dir, s.normal);
-    float incident_plane_normal_length = norm(incident_plane_normal);
-    if (incident_plane_normal_length < 1e-6f) incident_plane_normal = p.pol;
-    else incident_plane_normal = incident_plane_normal / incident_plane_normal_length;
-
-    float normal_coefficient = dot(p.pol, incident_plane_normal);
-    float normal_probability = normal_coefficient * normal_coefficient;
-
-    float reflection_coefficient;
-    if (rng_uniform(rng) < normal_probability) {
-        reflection_coefficient = -sinf(incident_angle - refracted_angle) / sinf(incident_angle + refracted_angle);
-        if ((rng_uniform(rng) < reflection_coefficient * reflection_coefficient) || isnan(refracted_angle)) {
-            p.dir = rotate(s.normal, incident_angle, incident_plane_normal);
-            p.history |= CB_REFLECT_SPECULAR;
-        } else {
-            p.dir = rotate(s.normal, CB_PI - refracted_angle, incident_plane_normal);
-        }
-        p.pol = incident_plane_normal;
-    } else {
-        reflection_coefficient = tanf(incident_angle - refracted_angle) / tanf(incident_angle + refracted_angle);
-        if ((rng_uniform(rng) < reflection_coefficient * reflection_coefficient) || isnan(refracted_angle)) {
-            p.dir = rotate(s.normal, incident_angle, incident_plane_normal);
-            p.history |= CB_REFLECT_SPECULAR;
-        } else {
-            p.dir = rotate(s.normal, CB_PI - refracted_angle, incident_plane_normal);
-        }
-        p.pol = cross(incident_plane_normal, p.dir);
-        p.pol = p.pol / norm(p.pol);
-    }
-}
-
-// mirror reflection (photon.h:634-646)
-__device__ __forceinline__ int specular_reflect(Photon& p, const StepState& s)
-{
-    float incident_angle = get_theta(s.normal, -p.dir);
-    float3 incident_plane_normal = cross(p.dir, s.normal);
-    incident_plane_normal = incident_plane_normal / norm(incident_plane_normal);
-    p.dir = rotate(s.normal, incident_angle, incident_plane_normal);
-    p.history |= CB_REFLECT_SPECULAR;
-    return CMD_CONTINUE;
-}
-
-// Lambertian reflection by rejection (photon.h:648-667)
-__device__ __forceinline__ int diffuse_reflect(Photon& p, const StepState& s, Rng& rng)
-{
-    float ndotv;
-    do {
-        p.dir = rng_sphere(rng);
-        ndotv = dot(p.dir, s.normal);
-        if (ndotv < 0.0f) {
-            p.dir = -p.dir;
-            ndotv = -ndotv;
-        }
-    } while (!(rng_uniform(rng) < ndotv));
-    p.pol = cross(rng_sphere(rng), p.dir);
-    p.pol = p.pol / norm(p.pol);
-    p.history |= CB_REFLECT_DIFFUSE;
-    return CMD_CONTINUE;
-}
-
-// complex helpers the reference adds to cuComplex.h (cx.h:29-35)
-__device__ __forceinline__ float cx_arg(cuFloatComplex x) { return atan2f(x.y, x.x); }
-__device__ __forceinline__ cuFloatComplex cx_sqrt(cuFloatComplex x)
-{
-    float r = sqrtf(cuCabsf(x));
-    float t = cx_arg(x) / 2.0f;
-    return make_cuFloatComplex(r * cosf(t), r * sinf(t));
-}
-
-// thin-film surface (n1 | eta+ik, thickness | n3), photon.h:669-827
-__device__ __forceinline__ int surface_complex_body(const DevGeometry& g, const Tables& T, Photon& p, StepState& s,
-                                                    Rng& rng, const CbSurface* surface, bool use_weights)
-{
-    float detect = interp_property(g, p.wavelength, T.at(surface->detect));
-    float reflect_diffuse = interp_property(g, p.wavelength, T.at(surface->reflect_diffuse));
-    float n2_eta = interp_property(g, p.wavelength, T.at(surface->eta));
-    float n2_k = interp_property(g, p.wavelength, T.at(surface->k));
-
-    cuFloatComplex n1 = make_cuFloatComplex(s.n1, 0.0f);
-    cuFloatComplex n2 = make_cuFloatComplex(n2_eta, n2_k);
-    cuFloatComplex n3 = make_cuFloatComplex(s.n2, 0.0f);
-
-    float cos_t1 = dot(p.dir, s.normal);
-    if (cos_t1 < 0.0f) cos_t1 = -cos_t1;
-    float theta = acosf(cos_t1);
-
-    cuFloatComplex cos1 = make_cuFloatComplex(cosf(theta), 0.0f);
-    cuFloatComplex sin1 = make_cuFloatComplex(sinf(theta), 0.0f);
-
-    float e = 2.0f * CB_PI * surface->thickness / p.wavelength;
-    cuFloatComplex ratio13sin = cuCmulf(cuCmulf(cuCdivf(n1, n3), cuCdivf(n1, n3)), cuCmulf(sin1, sin1));
-    cuFloatComplex cos3 = cx_sqrt(cuCsubf(make_cuFloatComplex(1.0f, 0.0f), ratio13sin));
-    cuFloatComplex ratio12sin = cuCmulf(cuCmulf(cuCdivf(n1, n2), cuCdivf(n1, n2)), cuCmulf(sin1, sin1));
-    cuFloatComplex cos2 = cx_sqrt(cuCsubf(make_cuFloatComplex(1.0f, 0.0f), ratio12sin));
-    float u = cuCrealf(cuCmulf(n2, cos2));
-    float v = cuCimagf(cuCmulf(n2, cos2));
-
-    // s polarisation
-    cuFloatComplex s_n1c1 = cuCmulf(n1, cos1);
-    cuFloatComplex s_n2c2 = cuCmulf(n2, cos2);
-    cuFloatComplex s_n3c3 = cuCmulf(n3, cos3);
-    cuFloatComplex s_r12 = cuCdivf(cuCsubf(s_n1c1, s_n2c2), cuCaddf(s_n1c1, s_n2c2));
-    cuFloatComplex s_r23 = cuCdivf(cuCsubf(s_n2c2, s_n3c3), cuCaddf(s_n2c2, s_n3c3));
-    cuFloatComplex s_t12 = cuCdivf(cuCmulf(make_cuFloatComplex(2.0f, 0.0f), s_n1c1), cuCaddf(s_n1c1, s_n2c2));
-    cuFloatComplex s_t23 = cuCdivf(cuCmulf(make_cuFloatComplex(2.0f, 0.0f), s_n2c2), cuCaddf(s_n2c2, s_n3c3));
-    cuFloatComplex s_g = cuCdivf(s_n3c3, s_n1c1);
-
-    float s_abs_r12 = cuCabsf(s_r12);
-    float s_abs_r23 = cuCabsf(s_r23);
-    float s_abs_t12 = cuCabsf(s_t12);
-    float s_abs_t23 = cuCabsf(s_t23);
-    float s_arg_r12 = cx_arg(s_r12);
-    float s_arg_r23 = cx_arg(s_r23);
-    float s_exp1 = exp(2.0f * v * e);
-    float s_exp2 = 1.0f / s_exp1;
-    float s_denom = s_exp1 + s_abs_r12 * s_abs_r12 * s_abs_r23 * s_abs_r23 * s_exp2 +
-                    2.0f * s_abs_r12 * s_abs_r23 * cosf(s_arg_r23 + s_arg_r12 + 2.0f * u * e);
-    float s_r = s_abs_r12 * s_abs_r12 * s_exp1 + s_abs_r23 * s_abs_r23 * s_exp2 +
-                2.0f * s_abs_r12 * s_abs_r23 * cosf(s_arg_r23 - s_arg_r12 + 2.0f * u * e);
-    s_r /= s_denom;
-    float s_t = cuCrealf(s_g) * s_abs_t12 * s_abs_t12 * s_abs_t23 * s_abs_t23;
-    s_t /= s_denom;
-
-    // p polarisation
-    cuFloatComplex p_n2c1 = cuCmulf(n2, cos1);
-    cuFloatComplex p_n3c2 = cuCmulf(n3, cos2);
-    cuFloatComplex p_n2c3 = cuCmulf(n2, cos3);
-    cuFloatComplex p_n1c2 = cuCmulf(n1, cos2);
-    cuFloatComplex p_r12 = cuCdivf(cuCsubf(p_n2c1, p_n1c2), cuCaddf(p_n2c1, p_n1c2));
-    cuFloatComplex p_r23 = cuCdivf(cuCsubf(p_n3c2, p_n2c3), cuCaddf(p_n3c2, p_n2c3));
-    cuFloatComplex p_t12 = cuCdivf(cuCmulf(cuCmulf(make_cuFloatComplex(2.0f, 0.0f), n1), cos1), cuCaddf(p_n2c1, p_n1c2));
-    cuFloatComplex p_t23 = cuCdivf(cuCmulf(cuCmulf(make_cuFloatComplex(2.0f, 0.0f), n2), cos2), cuCaddf(p_n3c2, p_n2c3));
-    cuFloatComplex p_g = cuCdivf(cuCmulf(n3, cos3), cuCmulf(n1, cos1));
-
-    float p_abs_r12 = cuCabsf(p_r12);
-    float p_abs_r23 = cuCabsf(p_r23);
-    float p_abs_t12 = cuCabsf(p_t12);
-    float p_abs_t23 = cuCabsf(p_t23);
-    float p_arg_r12 = cx_arg(p_r12);
-    float p_arg_r23 = cx_arg(p_r23);
-    float p_exp1 = exp(2.0f * v * e);
-    float p_exp2 = 1.0f / p_exp1;
-    float p_denom = p_exp1 + p_abs_r12 * p_abs_r12 * p_abs_r23 * p_abs_r23 * p_exp2 +
-                    2.0f * p_abs_r12 * p_abs_r23 * cosf(p_arg_r23 + p_arg_r12 + 2.0f * u * e);
-    float p_r = p_abs_r12 * p_abs_r12 * p_exp1 + p_abs_r23 * p_abs_r23 * p_exp2 +
-                2.0f * p_abs_r12 * p_abs_r23 * cosf(p_arg_r23 - p_arg_r12 + 2.0f * u * e);
-    p_r /= p_denom;
-    float p_t = cuCrealf(p_g) * p_abs_t12 * p_abs_t12 * p_abs_t23 * p_abs_t23;
-    p_t /= p_denom;
-
-    // s-polarisation fraction, as in at_boundary
-    float incident_angle = get_theta(s.normal, -p.dir);
-    float refracted_angle = asinf(sinf(incident_angle) * s.n1 / s.n2);
-    float3 incident_plane_normal = cross(p.dir, s.normal);
-    float incident_plane_normal_length = norm(incident_plane_normal);
-    if (incident_plane_normal_length < 1e-6f) incident_plane_normal = p.pol;
-    else incident_plane_normal = incident_plane_normal / incident_plane_normal_length;
-    float normal_coefficient = dot(p.pol, incident_plane_normal);
-    float normal_probability = normal_coefficient * normal_coefficient;
-
-    float transmit = normal_probability * s_t + (1.0f - normal_probability) * p_t;
-    if (!surface->transmissive) transmit = 0.0f;
-    float reflect = normal_probability * s_r + (1.0f - normal_probability) * p_r;
-    float absorb = 1.0f - transmit - reflect;
-
-    if (use_weights && p.weight > CB_WEIGHT_LOWER_THRESHOLD && absorb < (1.0f - CB_WEIGHT_LOWER_THRESHOLD)) {
-        float survive = 1.0f - absorb;
-        absorb = 0.0f;
-        p.weight *= survive;
-        detect /= survive;
-        reflect /= survive;
-        transmit /= survive;
-    }
-    if (use_weights && detect > 0.0f) {
-        p.history |= CB_SURFACE_DETECT;
-        p.weight *= detect;
-        return CMD_BREAK;
-    }
-
-    float uniform_sample = rng_uniform(rng);
-    if (uniform_sample < absorb) {
-        float uniform_sample_detect = rng_uniform(rng);
-        if (uniform_sample_detect < detect) p.history |= CB_SURFACE_DETECT;
-        else p.history |= CB_SURFACE_ABSORB;
-        return CMD_BREAK;
-    } else if (uniform_sample < absorb + reflect || !surface->transmissive) {
-        float uniform_sample_reflect = rng_uniform(rng);
-        if (uniform_sample_reflect < reflect_diffuse) return diffuse_reflect(p, s, rng);
-        return specular_reflect(p, s);
-    } else {
-        p.dir = rotate(s.normal, CB_PI - refracted_angle, incident_plane_normal);
-        p.pol = cross(incident_plane_normal, p.dir);
-        p.pol = p.pol / norm(p.pol);
-        p.history |= CB_SURFACE_TRANSMIT;
-        return CMD_CONTINUE;
-    }
-}
-
-static __device__ __noinline__ int surface_complex_call(const DevGeometry& g, const Tables& T, Photon& p, StepState& s,
-                                                        Rng& rng, const CbSurface* surface, bool use_weights)
-{
-    return surface_complex_body(g, T, p, s, rng, surface, use_weights);
-}
-template <bool INLINE>
-__device__ __forceinline__ int surface_complex(const DevGeometry& g, const Tables& T, Photon& p, StepState& s,
-                                               Rng& rng, const CbSurface* surface, bool use_weights)
-{
-    if (INLINE) return surface_complex_body(g, T, p, s, rng, surface, use_weights);
-    return surface_complex_call(g, T, p, s, rng, surface, use_weights);
-}
-
-// wavelength-shifting surface (photon.h:829-874)
-__device__ __forceinline__ int surface_wls(const DevGeometry& g, const Tables& T, Photon& p, StepState& s,
-                                           Rng& rng, const CbSurface* surface, bool use_weights)
-{
-    float absorb = interp_property(g, p.wavelength, T.at(surface->absorb));
-    float reflect_specular = interp_property(g, p.wavelength, T.at(surface->reflect_specular));
-    float reflect_diffuse = interp_property(g, p.wavelength, T.at(surface->reflect_diffuse));
-    float reemit = interp_property(g, p.wavelength, T.at(surface->reemit));
-
-    float uniform_sample = rng_uniform(rng);
-    if (use_weights && p.weight > CB_WEIGHT_LOWER_THRESHOLD && absorb < (1.0f - CB_WEIGHT_LOWER_THRESHOLD)) {
-        float survive = 1.0f - absorb;
-        absorb = 0.0f;
-        p.weight *= survive;
-        reflect_diffuse /= survive;
-        reflect_specular /= survive;
-    }
-    if (uniform_sample < absorb) {
-        float uniform_sample_reemit = rng_uniform(rng);
-        if (uniform_sample_reemit < reemit) {
-            p.history |= CB_SURFACE_REEMIT;
-            p.wavelength = sample_cdf_uniform(rng, g.wavelength_n, g.wavelength_start, g.wavelength_step,
-                                              T.at(surface->reemission_cdf));
-            p.dir = rng_sphere(rng);
-            p.pol = cross(rng_sphere(rng), p.dir);
-            p.pol = p.pol / norm(p.pol);
-            return CMD_CONTINUE;
-        }
-        p.history |= CB_SURFACE_ABSORB;
-        return CMD_BREAK;
-    } else if (uniform_sample < absorb + reflect_specular + reflect_diffuse) {
-        float uniform_sample_reflect = rng_uniform(rng) * (reflect_specular + reflect_diffuse);
-        if (uniform_sample_reflect < reflect_specular) return specular_reflect(p, s);
-        return diffuse_reflect(p, s, rng);
-    }
-    p.history |= CB_SURFACE_TRANSMIT;
-    return CMD_PASS;
-}
-
-// dichroic filter: angle-of-incidence blended reflect/transmit tables (photon.h:877-907)
-__device__ __forceinline__ int surface_dichroic(const DevGeometry& g, const Tables& T, Photon& p, StepState& s,
-                                                Rng& rng, const CbSurface* surface)
-{
-    float incident_angle = get_theta(s.normal, -p.dir);
-    float idx = interp_idx(incident_angle, surface->dichroic_nangles, T.at(surface->dichroic_angles));
-    unsigned int iidx = (int)idx;
-    const int W = g.wavelength_n;
-    float reflect_prob_low = interp_property(g, p.wavelength, T.at(surface->dichroic_reflect + iidx * W));
-    float reflect_prob_high = interp_property(g, p.wavelength, T.at(surface->dichroic_reflect + (iidx + 1) * W));
-    float transmit_prob_low = interp_property(g, p.wavelength, T.at(surface->dichroic_transmit + iidx * W));
-    float transmit_prob_high = interp_property(g, p.wavelength, T.at(surface->dichroic_transmit + (iidx + 1) * W));
-    float reflect_prob = reflect_prob_low + (reflect_prob_high - reflect_prob_low) * (idx - iidx);
-    float transmit_prob = transmit_prob_low + (transmit_prob_high - transmit_prob_low) * (idx - iidx);
-
-    float uniform_sample = rng_uniform(rng);
-    if (uniform_sample < reflect_prob) return specular_reflect(p, s);
-    if (uniform_sample < transmit_prob + reflect_prob) {
-        p.history |= CB_SURFACE_TRANSMIT;
-        return CMD_PASS;
-    }
-    p.history |= CB_SURFACE_ABSORB;
-    return CMD_BREAK;
-}
-
-// angle-tabulated surface (photon.h:909-951)
-__device__ __forceinline__ int surface_angular(const DevGeometry& g, const Tables& T, Photon& p, StepState& s,
-                                               Rng& rng, const CbSurface* surface, bool use_weights)
-{
-    float incident_angle = get_theta(s.normal, -p.dir);
-    float idx = interp_idx(incident_angle, surface->angular_nangles, T.at(surface->angular_angles));
-    unsigned int iidx = (int)idx;
-    float t = idx - iidx;
-    const float* tr = T.at(surface->angular_transmit);
-    const float* rs = T.at(surface->angular_reflect_specular);
-    const float* rd = T.at(surface->angular_reflect_diffuse);
-    float transmit_prob = tr[iidx] + t * (tr[iidx + 1] - tr[iidx]);
-    float reflect_spec_prob = rs[iidx] + t * (rs[iidx + 1] - rs[iidx]);
-    float reflect_diff_prob = rd[iidx] + t * (rd[iidx + 1] - rd[iidx]);
-    float absorb_prob = 1.0f - transmit_prob - reflect_spec_prob - reflect_diff_prob;
-
-    if (use_weights && p.weight > CB_WEIGHT_LOWER_THRESHOLD && absorb_prob < (1.0f - CB_WEIGHT_LOWER_THRESHOLD)) {
-        float survive = 1.0f - absorb_prob;
-        absorb_prob = 0.0f;
-        p.weight *= survive;
-        transmit_prob /= survive;
-        reflect_spec_prob /= survive;
-        reflect_diff_prob /= survive;
-    }
-    float uniform_sample = rng_uniform(rng);
-    if (uniform_sample < absorb_prob) {
-        p.history |= CB_SURFACE_ABSORB;
-        return CMD_BREAK;
-    }
-    if (uniform_sample < absorb_prob + transmit_prob) {
-        p.history |= CB_SURFACE_TRANSMIT;
-        return CMD_PASS;
-    }
-    if (uniform_sample < absorb_prob + transmit_prob + reflect_spec_prob) return specular_reflect(p, s);
-    return diffuse_reflect(p, s, rng);
-}
-
-// surface dispatch + default model (photon.h:953-1037; the reference's
-// effective default is CHROMA_FORCE_SCATTER_AT_PASS == 0)
-template <bool INLINE_SURFACES>
-__device__ __forceinline__ int at_surface(const DevGeometry& g, const Tables& T, Photon& p, StepState& s,
-                                          Rng& rng, bool use_weights)
-{
-    const CbSurface* surface = &g.surfaces[s.surface_index];
-    const int model = surface->model;
-    if (model == CB_SURFACE_COMPLEX) return surface_complex<INLINE_SURFACES>(g, T, p, s, rng, surface, use_weights);
-    if (model == CB_SURFACE_WLS) return surface_wls(g, T, p, s, rng, surface, use_weights);
-    if (model == CB_SURFACE_DICHROIC) return surface_dichroic(g, T, p, s, rng, surface);
-    if (model == CB_SURFACE_ANGULAR) return surface_angular(g, T, p, s, rng, surface, use_weights);
-
-    float detect = interp_property(g, p.wavelength, T.at(surface->detect));
-    float absorb = interp_property(g, p.wavelength, T.at(surface->absorb));
-    float reflect_diffuse = interp_property(g, p.wavelength, T.at(surface->reflect_diffuse));
-    float reflect_specular = interp_property(g, p.wavelength, T.at(surface->reflect_specular));
-
-    float uniform_sample = rng_uniform(rng);
-    if (use_weights && p.weight > CB_WEIGHT_LOWER_THRESHOLD && absorb < (1.0f - CB_WEIGHT_LOWER_THRESHOLD)) {
-        float survive = 1.0f - absorb;
-        absorb = 0.0f;
-        p.weight *= survive;
-        detect /= survive;
-        reflect_diffuse /= survive;
-        reflect_specular /= survive;
-    }
-    if (use_weights && detect > 0.0f) {
-        p.history |= CB_SURFACE_DETECT;
-        p.weight *= detect;
-        return CMD_BREAK;
-    }
-    if (uniform_sample < absorb) {
-        p.history |= CB_SURFACE_ABSORB;
-        return CMD_BREAK;
-    } else if (uniform_sample < absorb + detect) {
-        p.history |= CB_SURFACE_DETECT;
-        return CMD_BREAK;
-    } else if (uniform_sample < absorb + detect + reflect_diffuse)
-        return diffuse_reflect(p, s, rng);
-    else if (uniform_sample < absorb + detect + reflect_diffuse + reflect_specular)
-        return specular_reflect(p, s);
-    return CMD_PASS;
-}
-
-// Nearest analytic wire-plane boundary along the photon's ray (behaviour of the
-// analytic branch of fill_state, photon.h:108-270): per plane an orthonormal (u, v, n)
-// frame in double precision, the ray clipped to the plane's u extent and to the slab
-// |n| <= radius, the range of wire indices k the clipped segment can reach, and for
-// each of them the roots of the ray-cylinder quadratic in the (v, n) plane.  The root
-// taken depends on whether the origin is outside (entry root), inside (exit root) or
-// numerically on the cylinder (a 1e-4 mm step).  Candidates never prune against each
-// other except through `distance` (strictly nearer wins, compared in float).
-struct WireHit {
-    float distance;            // 1e30f: none
-    int surface, material_inner, material_outer;
-    float3 normal;             // outward cylinder normal at the hit (unoriented)
-    float dot_raw;             // normal . (-direction)
-};
-static __device__ __noinline__ void wire_planes_nearest(const DevGeometry& g, const float3 pos, const float3 dir,
-                                                        float best_distance, WireHit& hit)
-{
-    hit.distance = 1e30f;
-    hit.surface = -1; hit.material_inner = -1; hit.material_outer = -1;
-    hit.normal = f3(0.0f, 0.0f, 0.0f);
-    hit.dot_raw = 0.0f;
-    for (int ip = 0; ip < g.nwireplanes; ip++) {
-        const CbWirePlane& wp = g.wireplanes[ip];
-        // orthonormal frame: u normalised, v made orthogonal to u and normalised, n = u x v
-        const double ux = (double)wp.u[0], uy = (double)wp.u[1], uz = (double)wp.u[2];
-        const double vx0 = (double)wp.v[0], vy0 = (double)wp.v[1], vz0 = (double)wp.v[2];
-        const double un = 1.0 / sqrt(ux * ux + uy * uy + uz * uz);
-        const double ux1 = ux * un, uy1 = uy * un, uz1 = uz * un;
-        const double vdotu = vx0 * ux1 + vy0 * uy1 + vz0 * uz1;
-        const double vx1 = vx0 - vdotu * ux1;
-        const double vy1 = vy0 - vdotu * uy1;
-        const double vz1 = vz0 - vdotu * uz1;
-        const double vn = 1.0 / sqrt(vx1 * vx1 + vy1 * vy1 + vz1 * vz1);
-        const double vx = vx1 * vn, vy = vy1 * vn, vz = vz1 * vn;
-        const double nx = uy1 * vz - uz1 * vy;
-        const double ny = uz1 * vx - ux1 * vz;
-        const double nz = ux1 * vy - uy1 * vx;
-
-        const float3 w = pos - f3(wp.origin[0], wp.origin[1], wp.origin[2]);
-        const double du = (double)dir.x * ux1 + (double)dir.y * uy1 + (double)dir.z * uz1;
-        const double dv = (double)dir.x * vx + (double)dir.y * vy + (double)dir.z * vz;
-        const double dn = (double)dir.x * nx + (double)dir.y * ny + (double)dir.z * nz;
-        const double wu = (double)w.x * ux1 + (double)w.y * uy1 + (double)w.z * uz1;
-        const double wv0 = (double)w.x * vx + (double)w.y * vy + (double)w.z * vz - (double)wp.v0;
-        const double wn0 = (double)w.x * nx + (double)w.y * ny + (double)w.z * nz;
-
-        // the ray's parameter window inside the plane's u extent
-        double t_in = -1.0e300, t_out = 1.0e300;
-        if (fabs(du) < 1e-15) {
-            if (wu < (double)wp.umin || wu > (double)wp.umax) continue;
-        } else {
-            double t1 = ((double)wp.umin - wu) / du;
-            double t2 = ((double)wp.umax - wu) / du;
-            if (t1 > t2) { const double tmp = t1; t1 = t2; t2 = tmp; }
-            if (t1 > t_in) t_in = t1;
-            if (t2 < t_out) t_out = t2;
-            if (t_in > t_out) continue;
-        }
-
-        const double pitch = (double)wp.pitch;
-        const double inv_pitch = (pitch != 0.0) ? (1.0 / pitch) : 0.0;
-        const double wire_radius = (double)wp.radius;
-        const double wire_thickness = 2.0 * wire_radius;
-        const double pad_v = 0.5 * wire_thickness + 1e-6;
-        const double pad_n = 0.5 * wire_thickness + 1e-6;
-
-        const int kmin = (int)ceil(((double)wp.vmin - (double)wp.v0) / pitch);
-        const int kmax = (int)floor(((double)wp.vmax - (double)wp.v0) / pitch);
-        const double A = dv * dv + dn * dn;
-        int k_start = kmin, k_stop = kmax;
-
-        if (kmin <= kmax) {
-            // wires the segment can reach: clip to the slab around the plane, then to v
-            const double t_eps = 1.0e-4;
-            double t_lo = fmax(t_in, t_eps);
-            double t_hi = t_out;
-            const double best_cap = (double)best_distance;
-            if (best_cap < t_hi) t_hi = best_cap;
-            if (fabs(dn) > 1e-12) {
-                double tn1 = (-pad_n - wn0) / dn;
-                double tn2 = (pad_n - wn0) / dn;
-                if (tn1 > tn2) { const double tmp = tn1; tn1 = tn2; tn2 = tmp; }
-                t_lo = fmax(t_lo, tn1);
-                t_hi = fmin(t_hi, tn2);
-            } else if (fabs(wn0) > pad_n) {
-                continue;
-            }
-            if (t_hi < t_lo) continue;
-            if (fabs(dn) <= 1e-12 && fabs(dv) > 1e-12) {
-                const double t_span = (pitch + wire_thickness) / fabs(dv);
-                t_hi = fmin(t_hi, t_lo + t_span);
-            }
-            const double v_entry = wv0 + dv * t_lo;
-            const double v_exit = wv0 + dv * t_hi;
-            double v_lo = fmin(v_entry, v_exit) - pad_v;
-            double v_hi = fmax(v_entry, v_exit) + pad_v;
-            if (wv0 - pad_v < v_lo) v_lo = wv0 - pad_v;
-            if (wv0 + pad_v > v_hi) v_hi = wv0 + pad_v;
-            long long k_lo = (long long)floor(v_lo * inv_pitch);
-            long long k_hi = (long long)ceil(v_hi * inv_pitch);
-            if (k_lo < kmin) k_lo = kmin;
-            if (k_hi > kmax) k_hi = kmax;
-            if (k_lo > k_hi) continue;
-            k_start = (int)k_lo;
-            k_stop = (int)k_hi;
-        }
-
-        for (int k = k_start; k <= k_stop; k++) {
-            const double wv = wv0 - (double)k * pitch;
-            const double B = wv * dv + wn0 * dn;
-            const double Cq = wv * wv + wn0 * wn0 - wire_radius * wire_radius;
-            const double disc = B * B - A * Cq;
-            if (disc < 0.0) continue;
-            const double sqrt_disc = sqrt(disc);
-            const double t_small = (-B - sqrt_disc) / A;
-            const double t_large = (-B + sqrt_disc) / A;
-            const double t_min = 1.0e-4;
-            const double r2_wire = wire_radius * wire_radius;
-            const double r2_0 = wv * wv + wn0 * wn0;
-            const double eps0 = fmax(1e-18, 1e-12 * r2_wire);
-            double t;
-            if (r2_0 > r2_wire + eps0) {            // origin outside: forward entry root
-                if (t_small <= t_min) continue;
-                t = t_small;
-            } else if (r2_0 < r2_wire - eps0) {     // origin inside: forward exit root
-                if (t_large <= t_min) continue;
-                t = t_large;
-            } else {                                // numerically on the surface
-                t = t_min;
-            }
-            const double uc = wu + du * t;
-            if (uc < wp.umin || uc > wp.umax) continue;
-            if ((float)t >= hit.distance) continue;
-            if (t < t_in || t > t_out) continue;
-            const double vn_hit = wv + dv * t;
-            const double nn_hit = wn0 + dn * t;
-            const double len = sqrt(vn_hit * vn_hit + nn_hit * nn_hit);
-            if (len <= 0.0) continue;
-            const float3 n_local = f3((float)((vn_hit / len) * vx + (nn_hit / len) * nx),
-                                      (float)((vn_hit / len) * vy + (nn_hit / len) * ny),
-                                      (float)((vn_hit / len) * vz + (nn_hit / len) * nz));
-            hit.distance = (float)t;
-            hit.surface = wp.surface_index;
-            hit.material_inner = wp.material_inner_index;
-            hit.material_outer = wp.material_outer_index;
-            hit.normal = n_local;
-            hit.dot_raw = dot(n_local, -dir);
-        }
-    }
-}
-
-// The analytic candidate competes with the mesh hit (photon.h:272-330): it wins when it
-// is nearer (in double, by more than 1e-12) and its plane has a surface; the photon's
-// last_hit_triangle becomes -2 and the materials follow the side the photon comes from.
-static __device__ __noinline__ bool wire_plane_boundary(const DevGeometry& g, const Tables& T, Photon& p, StepState& s,
-                                                        int tri, float distance)
-{
-    WireHit wh;
-    const float best = (tri == -1) ? 1e30f : distance;
-    wire_planes_nearest(g, p.pos, p.dir, best, wh);
-    if (!(wh.surface >= 0 && (double)wh.distance + 1e-12 < (double)best)) return false;
-    s.distance = wh.distance;
-    s.surface_index = wh.surface;
-    p.last_hit_triangle = -2;
-    const CbMaterial *m1, *m2;
-    if (wh.dot_raw > 0.0f) {                 // outside -> inside: the outward normal already faces the photon
-        m1 = &g.materials[wh.material_outer]; m2 = &g.materials[wh.material_inner];
-        s.normal = wh.normal;
-    } else {
-        m1 = &g.materials[wh.material_inner]; m2 = &g.materials[wh.material_outer];
-        s.normal = -wh.normal;
-    }
-    s.n1 = interp_property(g, p.wavelength, T.at(m1->refractive_index));
-    s.n2 = interp_property(g, p.wavelength, T.at(m2->refractive_index));
-    s.absorption_length = interp_property(g, p.wavelength, T.at(m1->absorption_length));
-    s.scattering_length = interp_property(g, p.wavelength, T.at(m1->scattering_length));
-    s.material1 = m1;
-    return true;
-}
-
-// everything after the intersection for one step (propagate.cu:312-336).
-// Returns true when the photon continues to another step.
-// WIRES: geometry with analytic wire planes (a separate instantiation, so that the cold
-// path costs the usual kernels neither registers nor instructions).
-template <bool WIRES, bool INLINE_SURFACES = false>
-__device__ __forceinline__ bool physics_step(const DevGeometry& g, const Tables& T, Photon& p, Rng& rng,
-                                             int tri, float distance, bool use_weights, int scatter_first)
-{
-    StepState s;
-    const bool analytic = WIRES && g.nwireplanes > 0 && wire_plane_boundary(g, T, p, s, tri, distance);
-    if (!analytic) {
-        if (tri == -1) {
-            p.last_hit_triangle = -1;
-            p.history |= CB_NO_HIT;
-            return false;
-        }
-        s.distance = distance;
-        classify_hit(g, T, p, s, tri);
-    }
-    int command = to_boundary(g, T, p, s, rng, use_weights, scatter_first);
-    if (command == CMD_BREAK) return false;
-    if (command == CMD_CONTINUE) return true;
-    if (s.surface_index != -1) {
-        command = at_surface<INLINE_SURFACES>(g, T, p, s, rng, use_weights);
-        if (command == CMD_BREAK) return false;
-        if (command == CMD_CONTINUE) return true;
-    }
-    at_boundary(p, s, rng);
-    return true;
-}
-
-__device__ __forceinline__ bool photon_is_nan(const Photon& p)
-{
-    return isnan(p.dir.x * p.dir.y * p.dir.z * p.pos.x * p.pos.y * p.pos.z);
 }
 
 // ------------------------------------------------------------------ bank I/O
@@ -1494,3 +683,5 @@ __device__ __forceinline__ void st3(float* __restrict__ a, uint64_t i, const flo
 }
 
 } // namespace cb
+
+#include "physics.cuh"

@@ -4,6 +4,7 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <algorithm>
 #include <string.h>
+#include <math.h>
 #include <thread>
 
 namespace cb {
@@ -109,11 +110,40 @@ static int upload(T** dst, const T* src, uint64_t count, uint64_t& total)
     return CB_OK;
 }
 
+// Per-plane constants of the analytic wire planes, in double precision (physics.cuh WireFrame):
+// orthonormal frame (U normalised, V made orthogonal to U and normalised, N = U x V), the
+// wire index range inside [vmin, vmax] and the squared radius.  The reference recomputes
+// all of this per photon and step (chroma/cuda/photon.h:113-160).
+static WireFrame wire_frame(const CbWirePlane& wp)
+{
+    WireFrame f;
+    memset(&f, 0, sizeof(f));
+    double u[3] = {wp.u[0], wp.u[1], wp.u[2]}, v[3] = {wp.v[0], wp.v[1], wp.v[2]};
+    const double ul = 1.0 / sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
+    for (int a = 0; a < 3; a++) f.U[a] = u[a] * ul;
+    const double along = v[0] * f.U[0] + v[1] * f.U[1] + v[2] * f.U[2];
+    for (int a = 0; a < 3; a++) v[a] -= along * f.U[a];
+    const double vl = 1.0 / sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    for (int a = 0; a < 3; a++) f.V[a] = v[a] * vl;
+    f.N[0] = f.U[1] * f.V[2] - f.U[2] * f.V[1];
+    f.N[1] = f.U[2] * f.V[0] - f.U[0] * f.V[2];
+    f.N[2] = f.U[0] * f.V[1] - f.U[1] * f.V[0];
+    f.v0 = wp.v0; f.pitch = wp.pitch; f.inv_pitch = (f.pitch != 0.0) ? 1.0 / f.pitch : 0.0;
+    f.radius = wp.radius; f.radius2 = f.radius * f.radius;
+    f.umin = wp.umin; f.umax = wp.umax;
+    for (int a = 0; a < 3; a++) f.origin[a] = wp.origin[a];
+    f.kmin = (int)ceil(((double)wp.vmin - (double)wp.v0) / f.pitch);
+    f.kmax = (int)floor(((double)wp.vmax - (double)wp.v0) / f.pitch);
+    f.surface = wp.surface_index;
+    f.material_inner = wp.material_inner_index; f.material_outer = wp.material_outer_index;
+    return f;
+}
+
 static void free_geometry(Geometry* g)
 {
     cudaFree(g->vertices); cudaFree(g->triangles); cudaFree(g->material_codes); cudaFree(g->colors);
     cudaFree(g->solid_id); cudaFree(g->nodes); cudaFree(g->native_nodes); cudaFree(g->tri64); cudaFree(g->tables);
-    cudaFree(g->materials); cudaFree(g->surfaces); cudaFree(g->wireplanes); cudaFree(g->solid_to_channel);
+    cudaFree(g->materials); cudaFree(g->surfaces); cudaFree(g->wireframes); cudaFree(g->solid_to_channel);
     cudaFree(g->time_cdf_x); cudaFree(g->time_cdf_y); cudaFree(g->charge_cdf_x); cudaFree(g->charge_cdf_y);
     delete g;
 }
@@ -179,7 +209,11 @@ int cb_geometry_create(const CbGeometryDesc* d, cb_geom_t* out)
     }
     UP(materials, d->materials, (uint64_t)d->nmaterials);
     UP(surfaces, d->surfaces, (uint64_t)d->nsurfaces);
-    UP(wireplanes, d->wireplanes, (uint64_t)d->nwireplanes);
+    {
+        std::vector<WireFrame> frames;
+        for (int i = 0; i < d->nwireplanes; i++) frames.push_back(wire_frame(d->wireplanes[i]));
+        UP(wireframes, frames.data(), (uint64_t)d->nwireplanes);
+    }
 #undef UP
 
     std::vector<uint32_t> rank;
@@ -251,7 +285,7 @@ int cb_geometry_create(const CbGeometryDesc* d, cb_geom_t* out)
     v.root_x = root_entry[0]; v.root_y = root_entry[1]; v.root_z = root_entry[2]; v.root_w = root_entry[3];
     v.ref_root_x = d->nodes[0]; v.ref_root_y = d->nodes[1]; v.ref_root_z = d->nodes[2];
     v.nmaterials = d->nmaterials; v.nsurfaces = d->nsurfaces;
-    v.wireplanes = d->nwireplanes ? g->wireplanes : nullptr; v.nwireplanes = d->nwireplanes;
+    v.wireframes = d->nwireplanes ? g->wireframes : nullptr; v.nwireplanes = d->nwireplanes;
     // stage the leading part of the pool (the wavelength tables; the host lays
     // the long time CDFs out last) into shared memory, up to 48 KB
     uint64_t stage = std::min<uint64_t>(d->table_floats, 12288);

@@ -69,7 +69,7 @@ struct Geometry {
     // native
     uint4* native_nodes = nullptr; uint64_t nnative = 0;   // engine-built traversal tree
     float4* tri64 = nullptr; float* tables = nullptr; CbMaterial* materials = nullptr; CbSurface* surfaces = nullptr;
-    CbWirePlane* wireplanes = nullptr;
+    WireFrame* wireframes = nullptr;
     uint64_t nvertices = 0, ntriangles = 0, nnodes = 0, table_floats = 0;
     // detector
     int32_t* solid_to_channel = nullptr; uint64_t nsolids = 0; int32_t nchannels = 0;

@@ -427,18 +427,16 @@ step_intersect_kernel(const __grid_constant__ DevGeometry g, const __grid_consta
     persistent_intersect<COUNT>(g, src, n, P.cursor, (uint32_t)__cvta_generic_to_shared(smem_raw), P.counters, tune);
 }
 
-// Inlining the thin-film surface model into this kernel alone makes it 0.14 ms per event faster (no local
-// memory left) but its arithmetic then differs in the last bit from the tail kernel's copy, and results would
-// depend on the schedule (test_config3_scheduler_invariance_full_size): it stays one shared call.
-#ifndef CB_PHYS_INLINE_SURFACES
-#define CB_PHYS_INLINE_SURFACES false
-#endif
+// The thin-film optics are ONE shared, non-inlined pure function (physics.cuh thin_film): an inlined copy
+// would be contracted differently in each kernel and results would then depend on the schedule
+// (test_config3_scheduler_invariance_full_size).  It takes and returns values only, so no kernel has to
+// keep its photon in local memory around the call.
 #ifndef CB_PHYS_BLOCKS
 #define CB_PHYS_BLOCKS 2
 #endif
 template <bool WIRES>
 __global__ void __launch_bounds__(PROP_THREADS, CB_PHYS_BLOCKS)
-step_physics_kernel(DevGeometry g, PropParams P)
+step_physics_kernel(const __grid_constant__ DevGeometry g, const __grid_constant__ PropParams P)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ unsigned long long mbar;
@@ -471,7 +469,7 @@ step_physics_kernel(DevGeometry g, PropParams P)
                 if (photon_is_nan(p)) {
                     p.history |= CB_NO_HIT | CB_NAN_ABORT;
                 } else {
-                    alive = physics_step<WIRES, CB_PHYS_INLINE_SURFACES>(g, T, p, rng, hit_tri, hit_dist, P.use_weights != 0,
+                    alive = physics_step<WIRES>(g, T, p, rng, hit_tri, hit_dist, P.use_weights != 0,
                                          P.step == 0 ? P.scatter_first : 0);
                 }
                 rng_store(P.rng, k, rng);
@@ -503,7 +501,7 @@ constexpr int TAIL_THREADS = CB_TAIL_THREADS;
 #endif
 template <bool COUNT, bool WIRES>
 __global__ void __launch_bounds__(TAIL_THREADS, CB_TAIL_BLOCKS)
-propagate_tail_kernel(DevGeometry g, PropParams P)
+propagate_tail_kernel(const __grid_constant__ DevGeometry g, const __grid_constant__ PropParams P)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ unsigned long long mbar;
