@@ -3,7 +3,12 @@
 detector (BASELINE.json metric; config 3 of BASELINE.md), 1..8 B200.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                  [--workload pmt29k|tiny|rays] [--photons P]
+                  [--workload pmt29k|pmt29k_heavy|pmt29k_synth|tiny|scint|rays|pdf] [--photons P]
+
+Workloads: pmt29k = the reference's own demo detector (chroma/demo/__init__.py:32-64 with 28,995
+chroma.demo.pmt.build_8inch_pmt(nsteps=6) PMTs and the tables of chroma/demo/optics.py, restored from
+tests/golden/ref_detector_parts.npz); pmt29k_heavy = the same with build_8inch_pmt_with_lc(nsteps=24)
+(169.8 M triangles); pmt29k_synth = round 1's stand-in PMT profile and analytic tables.
 
 A "step" = one event of P photons (default 2.5 M, isotropic point source at the
 origin, lambda ~ U(300,600) nm) propagated to termination (max_steps=100) in the
@@ -34,12 +39,18 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, 'tests'))
 
 MAX_STEPS = 100
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel from the
-# committed `ncu --set full` capture (profiles/), keyed by (workload, photons per event)
-NCU_TRAFFIC_BYTES_PER_LAUNCH = {
-    # profiles/r01_ncu_step_intersect_summary.txt: 2.678675 GB read + 47.112192 MB written
-    ('pmt29k', 2500000): 2678675000 + 47112192,
-}
+STRONG_EVENTS = 40          # BASELINE config 5: 100 M photons = 40 events x 2.5 M, sharded over the ranks
+
+
+def ncu_traffic(workload, photons, kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of `kernel` from the committed
+    `ncu --set full` capture of this workload (profiles/ncu_traffic.json, written by
+    scratch/ncu_summary.py from the .ncu-rep); None when there is no capture for it."""
+    try:
+        table = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')))
+        return table['%s:%d' % (workload, photons)][kernel]['dram_bytes']
+    except Exception:
+        return None
 
 
 _REAL_STDOUT = None
@@ -157,12 +168,42 @@ class FlatGeometry(object):
     pass
 
 
-def build_detector(workload, timings):
-    """Build (or load) the flattened detector + reference-format BVH."""
+def author_detector(workload):
+    """The detector as placed solids (no flattening yet)."""
     from chroma_lite_b200 import demo
-    from chroma_lite_b200.bvh import BVH, WorldCoords, make_recursive_grid_bvh, uint4
+    from chroma_lite_b200.demo import refparts
+    if workload == 'pmt29k':
+        return refparts.detector_29k(pmt='pmt6')
+    if workload == 'pmt29k_heavy':
+        return refparts.detector_29k(pmt='pmt24lc')
+    if workload == 'tiny':
+        return refparts.tiny()
+    if workload == 'pmt29k_synth':
+        return demo.detector_29k()
+    if workload == 'tiny_synth':
+        return demo.tiny()
+    raise SystemExit('unknown workload ' + workload)
+
+
+DETECTOR_NOTE = {
+    'pmt29k': 'reference models: chroma.demo.pmt.build_8inch_pmt(nsteps=6) x 28,995 on the spiral of chroma/demo/__init__.py, '
+              'chroma/demo/optics.py tables (tests/golden/ref_detector_parts.npz)',
+    'pmt29k_heavy': 'reference models: chroma.demo.pmt.build_8inch_pmt_with_lc(nsteps=24) x 28,995, chroma/demo/optics.py tables',
+    'pmt29k_synth': 'stand-in PMT profile and analytic optics tables (round 1)',
+}
+
+
+def build_detector(workload, timings, native=True):
+    """Build (or load from the box-local cache) the flattened detector + reference-format BVH.
+
+    native=True: vertex de-duplication and BVH build through the product library (cb_unique_vertices,
+    cb_bvh_build).  native=False (the reference arm): NumPy np.unique + the oracle's restatement of the
+    reference's host-side recursive-grid builder (oracle/bvh_oracle.py: NumPy argsort / grouping per
+    layer as in chroma/bvh/grid.py:11-95) -- no product code touches the geometry; its wall time on this
+    box's host cores is the "reference's CPU-side geometry/BVH build" BASELINE.json asks for."""
+    from chroma_lite_b200.bvh import BVH, WorldCoords, uint4
     from chroma_lite_b200.geometry import Mesh
-    path = os.path.join(cache_dir(), 'det_%s_v2.npz' % workload)
+    path = os.path.join(cache_dir(), 'det_%s_v3.npz' % workload)
     t0 = time.perf_counter()
     if workload == 'scint':
         # BASELINE config 4: re-emitting scintillator in an acrylic vessel, WLS shell, dichroic /
@@ -172,12 +213,7 @@ def build_detector(workload, timings):
         det = scenes.scintillator_scene(96)
         timings.update(author_s=time.perf_counter() - t0, flatten_s=0.0, bvh_s=0.0, cached=False)
         return det
-    if workload == 'pmt29k':
-        det = demo.detector_29k()
-    elif workload == 'tiny':
-        det = demo.tiny()
-    else:
-        raise SystemExit('unknown workload ' + workload)
+    det = author_detector(workload)
     timings['author_s'] = time.perf_counter() - t0
     if os.path.exists(path):
         z = np.load(path)
@@ -186,20 +222,31 @@ def build_detector(workload, timings):
         det.colors, det.solid_id = z['colors'], z['solid_id']
         det.material1_index, det.material2_index, det.surface_index = z['m1'], z['m2'], z['surf']
         # material/surface object lists in the same order the cache was written with
-        det.flatten_objects_only = True
         _restore_object_lists(det)
         det.solid_id_to_channel_index = np.asarray(det.solid_id_to_channel_index, dtype=np.int32)
         det.bvh = BVH(WorldCoords(z['world_origin'], z['world_scale']), z['nodes'].view(uint4)[:, 0], z['layers'])
-        timings['flatten_s'] = float(z['flatten_s'])
-        timings['bvh_s'] = float(z['bvh_s'])
-        timings['cached'] = True
+        timings.update(flatten_s=float(z['flatten_s']), bvh_s=float(z['bvh_s']), cached=True, builder=str(z['builder']))
         return det
-    t0 = time.perf_counter()
-    det.flatten()                       # incl. global vertex de-duplication, as the reference does
-    timings['flatten_s'] = time.perf_counter() - t0
-    t0 = time.perf_counter()
-    det.bvh = make_recursive_grid_bvh(det.mesh)
-    timings['bvh_s'] = time.perf_counter() - t0
+    if native:
+        from chroma_lite_b200.bvh import make_recursive_grid_bvh
+        t0 = time.perf_counter()
+        det.flatten()                       # incl. global vertex de-duplication, as the reference does
+        timings['flatten_s'] = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        det.bvh = make_recursive_grid_bvh(det.mesh)
+        timings['bvh_s'] = time.perf_counter() - t0
+        timings['builder'] = 'libchroma_b200 (cb_unique_vertices on all host cores, cb_bvh_build)'
+    else:
+        import chroma_lite_b200.geometry as hostgeo
+        from oracle import bvh_oracle
+        hostgeo.NATIVE_UNIQUE_MIN = 1 << 62  # np.unique, as chroma/geometry.py:59-69 does
+        t0 = time.perf_counter()
+        det.flatten()
+        timings['flatten_s'] = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        bvh_oracle.attach_bvh(det)
+        timings['bvh_s'] = time.perf_counter() - t0
+        timings['builder'] = 'NumPy np.unique + oracle/bvh_oracle.py (restated chroma/bvh/grid.py host loop), 1 core'
     timings['cached'] = False
     try:
         tmp = path + '.tmp%d.npz' % os.getpid()
@@ -207,11 +254,19 @@ def build_detector(workload, timings):
                  solid_id=det.solid_id, m1=det.material1_index, m2=det.material2_index, surf=det.surface_index,
                  world_origin=det.bvh.world_coords.world_origin, world_scale=det.bvh.world_coords.world_scale,
                  nodes=det.bvh.nodes.view(np.uint32).reshape(-1, 4), layers=np.asarray(det.bvh.layer_offsets),
-                 flatten_s=timings['flatten_s'], bvh_s=timings['bvh_s'])
+                 flatten_s=timings['flatten_s'], bvh_s=timings['bvh_s'], builder=timings['builder'])
         os.replace(tmp, path)
     except Exception as e:               # cache is best effort
         log('cache write failed:', e)
     return det
+
+
+def common_config(args, det):
+    """The part of `config` both arms print identically (what is measured on what)."""
+    return {'workload': args.workload, 'detector': DETECTOR_NOTE.get(args.workload, args.workload),
+            'photons_per_event': args.photons, 'max_steps': MAX_STEPS, 'triangles': int(len(det.mesh.triangles)),
+            'bvh_nodes': int(len(det.bvh.nodes)), 'channels': int(det.num_channels()) if hasattr(det, 'num_channels') else 0,
+            'source': 'isotropic point source at the origin, wavelength uniform in the workload range, one event per step'}
 
 
 def _restore_object_lists(det):
@@ -295,17 +350,26 @@ def sum_over_ranks(x, world):
 # ------------------------------------------------------------------ our arm
 def run_ours(args):
     import ctypes as C
+    sys.setswitchinterval(2e-4)       # three pipeline threads per rank hand the GIL over quickly
     from chroma_lite_b200 import gpu, sim, _lib, parallel, event
     from chroma_lite_b200.gpu.geometry import make_desc
     rank, world, local = dist_setup(args.gpus)
     _lib.init(local)
     lib = _lib.lib()
+    if world > 1:
+        parallel.init_comm()              # the library's own NCCL communicator (cb_comm_init)
     timings = {}
-    det = build_detector(args.workload, timings)
+    # one rank builds the box-local cache, the others wait and load it
+    if local == 0:
+        det = build_detector(args.workload, timings)
+    barrier(world)
+    if local != 0:
+        det = build_detector(args.workload, timings)
     t0 = time.perf_counter()
-    s = sim.Simulation(det, seed=42 + rank, cuda_device=local, nthreads_per_block=512,
-                       max_blocks=max(1024, -(-args.photons // 512)))
+    max_blocks = max(1024, -(-args.photons // 512))
+    s = sim.Simulation(det, seed=42 + rank, cuda_device=local, nthreads_per_block=512, max_blocks=max_blocks)
     timings['upload_geometry_s'] = time.perf_counter() - t0
+    timings['blocking_sync'] = bool(parallel.host_threads_should_block()) and not os.environ.get('CHROMA_B200_SYNC')
     g, rng = s.gpu_geometry, s.rng_states
     n = args.photons
     ev = make_event(n, seed=1000 + rank)
@@ -331,18 +395,14 @@ def run_ours(args):
     barrier(world)
     _lib.check(lib.cb_synchronize())
     sampler.resume()
-    kernel_ms, launches, steps_taken = 0.0, 0, 0
-    nodes_v, tris_v, resolved = 0, 0, 0
+    acc = dict(kernel_ms=0.0, launches=0, steps=0, nodes_visited=0, tris_tested=0, rays_resolved=0, intersect_ms=0.0,
+               physics_ms=0.0, tail_ms=0.0, intersect_rays=0, physics_steps=0, tail_photons=0, tail_steps=0)
     int0_ms, int0_rays, int0_n = 0.0, 0, 0
     t0 = time.perf_counter()
     for _ in range(args.steps):
         st = one_step()
-        kernel_ms += st.kernel_ms
-        launches += st.launches
-        steps_taken += st.steps
-        nodes_v += st.nodes_visited
-        tris_v += st.tris_tested
-        resolved += st.rays_resolved
+        for k in acc:
+            acc[k] += getattr(st, k)
         if st.intersect0_rays:
             int0_ms += st.intersect0_ms
             int0_rays += st.intersect0_rays
@@ -352,14 +412,14 @@ def run_ours(args):
     wall = time.perf_counter() - t0
     sampler.pause()
     # device time of the propagate kernels (CUDA events on the launching stream), max over ranks
-    dev_s = max_over_ranks(kernel_ms / 1e3, world)
+    dev_s = max_over_ranks(acc['kernel_ms'] / 1e3, world)
     total_photons = sum_over_ranks(float(n * args.steps), world)
     value = total_photons / dev_s
 
-    # ---- e2e through the public API: K events as HOST arrays in, flat hits + DAQ channels
-    # out (Simulation.simulate, batches double-buffered), then ONE reduction of the
-    # run-level per-channel hit counts / charge across ranks
-    import torch
+    # ---- e2e through the public API: K events per rank as HOST arrays in, flat hits + DAQ channels
+    # out (Simulation.simulate, batches double-buffered); every event's photons also add to ONE run-level
+    # acquisition per rank, and the ranks' run-level accumulators are combined at the end with the
+    # library's NCCL all-reduce (cb_daq_allreduce: MIN time, SUM charge, OR history), inside the timed region
     h2d = sum(getattr(ev, f).nbytes for f in ('pos', 'dir', 'pol', 'wavelengths', 't', 'flags', 'evidx'))
     sim_kw = dict(keep_hits=False, keep_flat_hits=True, run_daq=True, max_steps=MAX_STEPS, photons_per_batch=n)
     # the event's host arrays live in page-locked memory (gpu.pagelocked_empty, the role of
@@ -367,23 +427,21 @@ def run_ours(args):
     ev = gpu.pin_photons(ev)
     list(s.simulate((event.Event(photons_beg=ev) for _ in range(max(4, args.warmup))), **sim_kw))   # warm-up: 3 batches in flight
     nch = s.gpu_geometry.nchannels
+    run_daq = gpu.GPUDaq(s.gpu_geometry)            # run-level accumulators
     barrier(world)
     _lib.check(lib.cb_synchronize())
     sampler.resume()
     t0 = time.perf_counter()
+    run_daq.begin_acquire()
     hit_count = np.zeros(nch, dtype=np.int64)
-    charge = np.zeros(nch, dtype=np.float64)
     d2h = 0
     for out_ev in s.simulate((event.Event(photons_beg=ev) for _ in range(args.steps)), **sim_kw):
         hit_count += out_ev.channels.hit
-        charge += np.where(out_ev.channels.hit, out_ev.channels.q, 0.0)
         fh = out_ev.flat_hits
         d2h = sum(getattr(fh, f).nbytes for f in fields) + fh.channel.nbytes + 3 * 4 * nch
-    if world > 1:
-        import torch.distributed as dist
-        buf = torch.from_numpy(np.concatenate([hit_count.astype(np.float64), charge])).cuda()
-        dist.reduce(buf, dst=0, op=dist.ReduceOp.SUM)
-        torch.cuda.synchronize()
+        # run-level: the event's per-channel result folds into the rank's accumulators on the device
+        run_daq.fold(s.gpu_daq)
+    run_channels = run_daq.allreduce().get()        # one NCCL exchange over NVLink + read-back (3 x 4 B x channels)
     _lib.check(lib.cb_synchronize())
     barrier(world)
     e2e_s = max_over_ranks(time.perf_counter() - t0, world)
@@ -392,43 +450,73 @@ def run_ours(args):
     timings['e2e_last_batch'] = dict(s.last_timings)
     timings['e2e_s_per_event'] = e2e_s / args.steps
     timings['e2e_hits_per_event'] = int(len(fh))
+    timings['e2e_run_channels_hit'] = int(run_channels.hit.sum())
+
+    # ---- BASELINE config 5, strong scaling: a fixed run of STRONG_EVENTS events sharded over the ranks,
+    # RNG stream == global photon index, ONE all-reduce of the run-level accumulators at the end.  The
+    # checksum of the reduced arrays must be the same for every N (partition invariance, on hardware).
+    strong = None
+    if args.workload.startswith('pmt29k') or args.workload.startswith('tiny'):
+        strong = strong_scaling(args, det, s, rank, world, local)
 
     if world > 1:
         import torch.distributed as dist
+        parallel.destroy_comm()
         dist.barrier()
         dist.destroy_process_group()
     if rank != 0:
         return
-    # ---- roofline + cpu baseline (rank 0, N=1 only does the CPU leg)
-    roofline, cpu_baseline = None, None
+    # ---- rooflines + cpu baseline (rank 0, N=1 only does the CPU leg)
+    roofline, rooflines, cpu_baseline = None, None, None
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
     except Exception:
         pass
     peak = float(peaks.get('hbm_gbs', 6650.0))
+    peak_source = 'MEASURED_PEAKS.json hbm_gbs (burst copy)' if peaks else 'fallback 6650 GB/s'
     if world == 1:
         from oracle import orc
         desc, keep = make_desc(det)
         b_photon, cpu_rate = algorithmic_bytes(det, desc, make_event(args.cpu_sample, seed=999), timings)
+        o = timings['oracle']
         # dominant kernel = the first step's traversal kernel (one ray per photon).  Algorithmic
         # bytes per ray B_ray = 32 + 16*Nnode + 48*Ntri with Nnode/Ntri counted by the REFERENCE
         # traversal (oracle, reference tree) on a sample of the same rays
         smp = make_event(min(args.cpu_sample, 20000), seed=998)
         _, _, c0 = orc.intersect(desc, smp.pos, smp.dir)
         b_ray = 32.0 + 16.0 * c0['nodes'] / len(smp) + 48.0 * c0['tris'] / len(smp)
-        timings['oracle']['first_step_nodes_per_ray'] = c0['nodes'] / len(smp)
-        timings['oracle']['first_step_tris_per_ray'] = c0['tris'] / len(smp)
+        o['first_step_nodes_per_ray'] = c0['nodes'] / len(smp)
+        o['first_step_tris_per_ray'] = c0['tris'] / len(smp)
+
+        def entry(kernel, units_name, units, ms, bytes_per_unit, note):
+            if not units or not ms:
+                return None
+            achieved = bytes_per_unit * units / (ms / 1e3) / 1e9
+            return {'kernel': kernel, 'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                    'traffic': ncu_traffic(args.workload, n, kernel), 'bytes_per_' + units_name: bytes_per_unit,
+                    units_name + 's_per_launch_set': units / args.steps, 'ms_per_event': ms / args.steps,
+                    'share_of_event': ms / acc['kernel_ms'], 'algorithmic_bytes': note, 'peak_source': peak_source}
+        b_trav = 16.0 * o['nodes_per_call'] + 48.0 * o['tris_per_call']          # one traversal, all steps' average
         if int0_n:
             per_launch_s = int0_ms / 1e3 / int0_n
             rays_per_launch = int0_rays / int0_n
             achieved = b_ray * rays_per_launch / per_launch_s / 1e9
             roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                        'traffic': NCU_TRAFFIC_BYTES_PER_LAUNCH.get((args.workload, n)),
+                        'traffic': ncu_traffic(args.workload, n, 'step_intersect_kernel (first step)'),
                         'kernel': 'step_intersect_kernel (first step)', 'bytes_per_ray': b_ray,
                         'rays_per_launch': rays_per_launch, 'ms_per_launch': per_launch_s * 1e3,
                         'rays_per_s': rays_per_launch / per_launch_s, 'bytes_per_photon_all_steps': b_photon,
-                        'peak_source': 'MEASURED_PEAKS.json hbm_gbs (burst copy)' if peaks else 'fallback 6650 GB/s'}
+                        'peak_source': peak_source}
+        rooflines = [r for r in (
+            entry('step_intersect_kernel', 'ray', acc['intersect_rays'], acc['intersect_ms'], 32.0 + b_trav,
+                  '32 B ray in/out + 16 B x nodes + 48 B x triangles of the reference traversal (SURVEY 8d), all wavefront steps'),
+            entry('step_physics_kernel', 'photon_step', acc['physics_steps'], acc['physics_ms'], 248.0,
+                  '120 B photon in/out + 48 B RNG state in/out + 16 B queue entry, hit triangle, hit distance + 64 B triangle record'),
+            entry('propagate_tail_kernel', 'photon_step', acc['tail_steps'], acc['tail_ms'],
+                  b_trav + 64.0 + 168.0 * acc['tail_photons'] / max(acc['tail_steps'], 1),
+                  'per step: traversal bytes as above + 64 B triangle record; per photon: 120 B state + 48 B RNG in/out'),
+        ) if r]
         cpu_baseline = {'value': cpu_rate, 'unit': 'photons/s', 'cores': orc.threads(), 'kind': 'port',
                         'sample': '%d photons of the same event type through oracle/chroma_oracle.c '
                                   '(orc_propagate, max_steps=%d) on %d host threads, host cores on this box: %d'
@@ -437,35 +525,102 @@ def run_ours(args):
         'metric': METRIC_NAME.get(args.workload, 'photons propagated/sec (whole box) on 29k-PMT detector'), 'value': value,
         'unit': 'photons/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dev_s * 1e3 / args.steps,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': args.workload, 'photons_per_event': n, 'max_steps': MAX_STEPS,
-                   'triangles': int(len(det.mesh.triangles)), 'bvh_nodes': int(len(det.bvh.nodes)),
-                   'channels': int(det.num_channels()), 'rng_pool': int(len(rng)),
-                   'l2': 'flushed between steps (cb_flush_l2 writes 2x L2) and node+triangle arrays exceed L2',
-                   'parallelism': 'photon banks sharded x%d, geometry replicated' % world,
-                   'tree': '%s, leaf split %s' % (os.environ.get('CHROMA_B200_TREE') or 'solids first',
-                                                  os.environ.get('CHROMA_B200_LEAF_SPLIT') or 'off')},
+        'config': common_config(args, det),
         'e2e': {'value': e2e, 'unit': 'photons/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h)},
-        'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu_baseline,
-        'extra': {'steps_per_photon': steps_taken / float(n * args.steps), 'wall_s': wall, 'setup': timings,
-                  'engine_counters': {'entries_per_traversal': nodes_v / max(steps_taken, 1),
-                                      'tris_per_traversal': tris_v / max(steps_taken, 1),
-                                      'rays_redone_fraction': resolved / max(steps_taken, 1),
+        'gpu_launches': int(acc['launches']), 'clocks': clocks, 'roofline': roofline, 'rooflines': rooflines,
+        'cpu_baseline': cpu_baseline, 'strong_scaling': strong,
+        'extra': {'steps_per_photon': acc['steps'] / float(n * args.steps), 'wall_s': wall, 'setup': timings,
+                  'rng_pool': int(len(rng)),
+                  'l2': 'flushed between steps (cb_flush_l2 writes 2x L2) and node+triangle arrays exceed L2; the first '
+                        '%s MB of the traversal tree are marked persisting (access-policy window)'
+                        % (os.environ.get('CHROMA_B200_L2_WINDOW_MB') or '16'),
+                  'parallelism': 'photon banks sharded x%d (whole events per rank), geometry replicated, run-level DAQ '
+                                 'accumulators combined by one in-library NCCL all-reduce inside the e2e region' % world,
+                  'tree': '%s, leaf split %s' % (os.environ.get('CHROMA_B200_TREE') or 'single level',
+                                                 os.environ.get('CHROMA_B200_LEAF_SPLIT') or 'off'),
+                  'kernel_ms_per_event': {k: acc[k] / args.steps for k in ('intersect_ms', 'physics_ms', 'tail_ms', 'kernel_ms')},
+                  'engine_counters': {'entries_per_traversal': acc['nodes_visited'] / max(acc['steps'], 1),
+                                      'tris_per_traversal': acc['tris_tested'] / max(acc['steps'], 1),
+                                      'rays_redone_fraction': acc['rays_resolved'] / max(acc['steps'], 1),
                                       'enabled': bool(os.environ.get('CHROMA_B200_STATS'))},
                   'host_cores': os.cpu_count()},
     }
     emit(line)
 
 
+def strong_scaling(args, det, s0, rank, world, local):
+    """BASELINE config 5: STRONG_EVENTS events of args.photons photons in total, whole events per rank
+    (parallel.EventPlan), every photon on the RNG stream of its index in the run, per-event hits read
+    back, every event accumulated into ONE acquisition per rank, and at the end one NCCL all-reduce of
+    the per-channel accumulators inside the library.  Timed end to end from host arrays (upload
+    included), max over ranks.  Returns the block rank 0 prints; `checksum` covers the reduced integer
+    accumulators and must not depend on N."""
+    import hashlib
+    from chroma_lite_b200 import gpu, sim, _lib, parallel, event
+    lib = _lib.lib()
+    n = args.photons
+    nev = STRONG_EVENTS
+    plan = parallel.EventPlan(nev, n, rank, world)
+    # the geometry on the device is shared with the weak-scaling Simulation; only the RNG pool differs
+    s = sim.Simulation.__new__(sim.Simulation)
+    s.__dict__.update(s0.__dict__)
+    s._pools = None
+    s.seed = 4242
+    s.rng_per_photon, s.rng_cursor = True, 0
+    s.rng_states = gpu.get_rng_states(max(plan.nphotons, 1), seed=s.seed, first_stream=plan.first_stream)
+    s.gpu_daq = gpu.GPUDaq(s.gpu_geometry)
+    # event e is the same on whichever rank it lands: one base event whose wavelengths are rotated by
+    # 997 e.  The rotated arrays are prepared before the clock starts (host-side event generation is not
+    # the engine's work); each event is then copied into one of four page-locked banks and uploaded.
+    base = make_event(n, seed=7000)
+    wl = [np.roll(base.wavelengths, 997 * e).astype(np.float32) for e in plan.events]
+    banks = [gpu.pin_photons(base) for _ in range(min(4, max(len(wl), 1)))]
+
+    def events():
+        for k, e in enumerate(plan.events):
+            b = banks[k % len(banks)]
+            b.wavelengths[:] = wl[k]
+            yield event.Event(photons_beg=b)
+    barrier(world)
+    _lib.check(lib.cb_synchronize())
+    t0 = time.perf_counter()
+    s.gpu_daq.begin_acquire()
+    nhits = 0
+    for out_ev in s.simulate(events(), keep_hits=False, keep_flat_hits=True, run_daq='accumulate', max_steps=MAX_STEPS,
+                             photons_per_batch=n):
+        nhits += len(out_ev.flat_hits)
+    ch = s.gpu_daq.allreduce()
+    host = ch.get()
+    _lib.check(lib.cb_synchronize())
+    barrier(world)
+    dt = max_over_ranks(time.perf_counter() - t0, world)
+    total_hits = sum_over_ranks(float(nhits), world)
+    digest = hashlib.sha256()
+    for a in (s.gpu_daq.earliest_time_int_gpu.get(), s.gpu_daq.channel_q_int_gpu.get(), s.gpu_daq.channel_history_gpu.get()):
+        digest.update(np.ascontiguousarray(a).tobytes())
+    return {'config': 'BASELINE config 5: %d events x %d photons sharded over %d rank(s), RNG stream = global photon index, '
+                      'one in-library NCCL all-reduce (MIN time, SUM charge, OR history)' % (nev, n, world),
+            'photons': nev * n, 'events_on_rank0': len(plan.events), 'seconds': dt, 'value': nev * n / dt, 'unit': 'photons/s',
+            'scaling': 'strong', 'hits': int(total_hits), 'channels_hit': int(host.hit.sum()),
+            'checksum': digest.hexdigest()[:16]}
+
+
 # ------------------------------------------------------------------ ray microbench (BASELINE config 2)
-def rays_scene():
-    """~1.2 M triangles: a finely tessellated sphere shell around a coarser one (the ~1M-triangle
-    STL BASELINE names is not shipped with the reference)."""
+def rays_scene(which='lion'):
+    """~1.2 M triangles.  BASELINE config 2 names a ~1M-triangle STL that is not shipped with the reference
+    (SURVEY section 8d); the largest bundled one, chroma/models/lionsolid.stl.bz2 (74,358 triangles, restored
+    from tests/golden/ref_detector_parts.npz), subdivided twice 1 -> 4 gives 1,189,728.  'sphere': round 1's
+    finely tessellated double sphere shell."""
     from chroma_lite_b200.geometry import Geometry, Solid, vacuum
     from chroma_lite_b200.make import sphere
     from chroma_lite_b200.demo import optics
     geo = Geometry(optics.water)
-    geo.add_solid(Solid(sphere(1000.0, 708), optics.glass, optics.water))
-    geo.add_solid(Solid(sphere(600.0, 300), vacuum, optics.glass))
+    if which == 'lion':
+        from chroma_lite_b200.demo import refparts
+        geo.add_solid(Solid(refparts.Parts().lion_mesh(subdivide=2), optics.glass, optics.water))
+    else:
+        geo.add_solid(Solid(sphere(1000.0, 708), optics.glass, optics.water))
+        geo.add_solid(Solid(sphere(600.0, 300), vacuum, optics.glass))
     geo.flatten()
     return geo
 
@@ -484,22 +639,30 @@ def make_rays(geo, n, seed=1234):
 
 def run_rays(args):
     """rays/s of the nearest-hit query (triangle index + distance) on a ~1.2 M-triangle mesh."""
-    from chroma_lite_b200 import gpu, _lib
-    from chroma_lite_b200 import gpuarray as ga
-    from chroma_lite_b200.gpu.tools import to_float3
-    from chroma_lite_b200.bvh import make_recursive_grid_bvh
-    _lib.init(0)
-    lib = _lib.lib()
     n = args.photons if args.photons != 2500000 else 10000000
-    geo = rays_scene()
+    which = 'sphere' if args.workload == 'rays_sphere' else 'lion'
+    if args.impl == 'reference':
+        import chroma_lite_b200.geometry as hostgeo
+        hostgeo.NATIVE_UNIQUE_MIN = 1 << 62          # np.unique: the product library stays unloaded
+    geo = rays_scene(which)
     t0 = time.perf_counter()
-    geo.bvh = make_recursive_grid_bvh(geo.mesh)
+    if args.impl == 'reference':
+        from oracle import bvh_oracle          # no product code on the reference arm
+        bvh_oracle.attach_bvh(geo)
+    else:
+        from chroma_lite_b200 import gpu, _lib
+        from chroma_lite_b200 import gpuarray as ga
+        from chroma_lite_b200.gpu.tools import to_float3
+        from chroma_lite_b200.bvh import make_recursive_grid_bvh
+        _lib.init(0)
+        lib = _lib.lib()
+        geo.bvh = make_recursive_grid_bvh(geo.mesh)
     bvh_s = time.perf_counter() - t0
     o, d = make_rays(geo, n)
     line = {'metric': 'rays/s, nearest-hit triangle + distance through the BVH', 'unit': 'rays/s', 'n_gpus': 1,
             'steps': args.steps, 'warmup': args.warmup, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': 'rays', 'rays': n, 'triangles': int(len(geo.mesh.triangles)),
+            'config': {'workload': args.workload, 'mesh': which, 'rays': n, 'triangles': int(len(geo.mesh.triangles)),
                        'bvh_nodes': int(len(geo.bvh.nodes)), 'bvh_build_s': bvh_s,
                        'l2': 'ray arrays (320 MB) and geometry exceed L2'}}
     if args.impl == 'reference':
@@ -616,6 +779,10 @@ def run_pdf(args):
 
 # ------------------------------------------------------------------ reference arm
 def run_reference(args):
+    """The REFERENCE's kernels (oracle/_ref/*.cubin) on the same detector and events.  No product
+    code runs here: the geometry is flattened with NumPy and its BVH built by the oracle's restatement
+    of the reference's host-side builder (build_detector(native=False)), the device work goes through
+    oracle/ref_driver.py (libcuda + the reference's cubins).  libchroma_b200.so is never loaded."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
@@ -623,11 +790,9 @@ def run_reference(args):
     if not ref_driver.available():
         emit({'impl': 'reference', 'unavailable': 'oracle/_ref cubins missing (build() needs /root/reference)'})
         return
-    from chroma_lite_b200 import _lib
     from chroma_lite_b200.gpu.geometry import make_desc
-    _lib.init(0)                         # only for the BVH builder / cache; no engine kernel is timed below
     timings = {}
-    det = build_detector(args.workload, timings)
+    det = build_detector(args.workload, timings, native=False)
     desc, keep = make_desc(det)
     t0 = time.perf_counter()
     rg = ref_driver.RefGeometry(desc, keep)
@@ -638,6 +803,7 @@ def run_reference(args):
     sampler = ClockSampler(0)
 
     rg.attach_detector(det)
+    nch = int(det.num_channels()) if hasattr(det, 'num_channels') else 0
 
     def one_step():
         # chroma/sim.py:54-154 for one event: upload, propagate, flat hits, DAQ, channels
@@ -665,22 +831,30 @@ def run_reference(args):
     clocks = sampler.stop()
     value = n * args.steps / (ms / 1e3)
     e2e = n * args.steps / t_e2e
+    # what its e2e region copies per event: the nine GPUPhotons arrays up (gpu/photon.py:46-62), the input
+    # queue up and a 4-byte alive count down per launch (gpu/photon.py:259-286), ten hit arrays + the count
+    # down (gpu/photon.py:141-209), three per-channel arrays down (gpu/daq.py:94-101)
+    h2d = sum(np.asarray(getattr(ev, f)).nbytes for f in ref_driver.RefPhotons.FIELDS) + 4 * (n + 1)
+    d2h = sum(np.asarray(v).nbytes for v in hits.values()) + 4 + 4 * launches // args.steps + 3 * 4 * nch
     line = {
         'impl': 'reference', 'metric': METRIC_NAME.get(args.workload, 'photons propagated/sec (whole box) on 29k-PMT detector'),
         'value': value,
         'unit': 'photons/s', 'n_gpus': 1, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': args.workload, 'photons_per_event': n, 'max_steps': MAX_STEPS,
-                   'triangles': int(len(det.mesh.triangles)), 'bvh_nodes': int(len(det.bvh.nodes)),
-                   'launch': '512 threads x 1024 blocks, rng pool 524288, host queue loop (chroma/gpu/photon.py:240-290)'},
+        'config': common_config(args, det),
         'cpu_baseline': {'value': value, 'unit': 'photons/s', 'cores': 1, 'kind': 'reference',
                          'sample': 'reference CUDA kernels (oracle/_ref/propagate.cubin, sm_100a, reference nvcc flags) '
                                    'on one B200 driven by one host thread; the reference has no CPU propagator'},
-        'e2e': {'value': e2e, 'unit': 'photons/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'e2e': {'value': e2e, 'unit': 'photons/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h)},
         'gpu_launches': int(launches), 'clocks': clocks,
         'extra': {'setup': timings, 'host_cores': os.cpu_count(),
-                  'terminal_fraction': float(((out.flags & 0x800F) != 0).mean())},
+                  'launch': '512 threads x 1024 blocks, rng pool 524288, host queue loop (chroma/gpu/photon.py:240-290)',
+                  'cpu_side_build': {'flatten_s': timings.get('flatten_s'), 'bvh_s': timings.get('bvh_s'),
+                                     'builder': timings.get('builder'), 'cached': timings.get('cached'),
+                                     'host_cores': os.cpu_count()},
+                  'terminal_fraction': float(((out.flags & 0x800F) != 0).mean()),
+                  'product_library_loaded': 'libchroma_b200' in open('/proc/self/maps').read()},
     }
     emit(line)
 
@@ -706,7 +880,7 @@ def main():
     if args.workload == 'scint' and args.photons == 2500000:
         args.photons = 10000000            # config 4 is quoted at 10 M photons per event
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
-    if args.workload == 'rays':
+    if args.workload in ('rays', 'rays_sphere'):
         run_rays(args)
     elif args.workload == 'pdf':
         run_pdf(args)

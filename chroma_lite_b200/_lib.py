@@ -67,7 +67,9 @@ class CbPhotonBank(C.Structure):
 
 class CbPropagateStats(C.Structure):
     _fields_ = [('photons', u64), ('steps', u64), ('nodes_visited', u64), ('tris_tested', u64), ('rays_resolved', u64),
-                ('launches', u32), ('kernel_ms', f32), ('intersect0_ms', f32), ('intersect0_rays', u64)]
+                ('launches', u32), ('kernel_ms', f32), ('intersect0_ms', f32), ('intersect0_rays', u64),
+                ('intersect_ms', f32), ('physics_ms', f32), ('tail_ms', f32), ('intersect_rays', u64),
+                ('physics_steps', u64), ('tail_photons', u64), ('tail_steps', u64)]
 
 
 # name -> (restype, argtypes); every symbol include/chroma_b200.h declares
@@ -99,6 +101,8 @@ SIGNATURES = {
     'cb_native_tree_build': (C.c_int, [vp, u64, u64, vp, vp, _P(u64)]),
     'cb_native_tree_build_split': (C.c_int, [vp, u64, u64, vp, vp, vp, vp, f32, i32, i32, f32, vp, _P(u64)]),
     'cb_rng_create': (C.c_int, [u64, u64, u64, _P(u64)]),
+    'cb_rng_create_streams': (C.c_int, [u64, u64, u64, u64, _P(u64)]),
+    'cb_rng_view': (C.c_int, [u64, u64, u64, _P(u64)]),
     'cb_rng_destroy': (C.c_int, [u64]),
     'cb_rng_size': (C.c_int, [u64, _P(u64)]),
     'cb_rng_download': (C.c_int, [u64, u64, u64, vp]),
@@ -118,6 +122,14 @@ SIGNATURES = {
     'cb_daq_end_acquire': (C.c_int, [u64]),
     'cb_daq_pointers': (C.c_int, [u64, _P(vp), _P(vp), _P(vp), _P(vp), _P(vp), _P(u64)]),
     'cb_daq_finalize': (C.c_int, [u64]),
+    'cb_daq_fold': (C.c_int, [u64, u64]),
+    'cb_comm_unique_id': (C.c_int, [vp]),
+    'cb_comm_init': (C.c_int, [i32, i32, vp]),
+    'cb_comm_destroy': (C.c_int, []),
+    'cb_comm_size': (C.c_int, [_P(i32), _P(i32)]),
+    'cb_daq_allreduce': (C.c_int, [u64]),
+    'cb_daq_reduce_local': (C.c_int, [_P(u64), i32]),
+    'cb_set_blocking_sync': (C.c_int, [i32]),
     'cb_unique_vertices': (C.c_int, [vp, u64, vp, vp, _P(u64)]),
     'cb_pdf_bin_hits': (C.c_int, [i32, vp, vp, vp, i32, f32, f32, i32, f32, f32, vp]),
     'cb_pdf_accumulate_moments': (C.c_int, [i32, i32, vp, vp, f32, f32, f32, f32, vp, vp, vp, vp, vp]),

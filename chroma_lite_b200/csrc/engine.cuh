@@ -104,7 +104,8 @@ struct DevGeometry {
     uint32_t root_w;          // root node's child word
     uint32_t root_x, root_y, root_z;  // root node's packed box
     uint32_t ref_root_x, ref_root_y, ref_root_z;   // the reference tree's root box
-    uint32_t smem_floats;     // leading floats of the pool staged into shared memory
+    uint32_t smem_floats;     // leading floats of the pool served from shared memory (ends on a table boundary)
+    uint32_t smem_bytes;      // bytes the kernels copy for that (one float beyond, rounded to 16 B)
     uint32_t nmaterials, nsurfaces;
     const struct WireFrame* wireframes;   // analytic wire planes in their own frames (cold path; usually none)
     int32_t nwireplanes;
@@ -322,7 +323,7 @@ static __device__ __noinline__ RayHit traverse_reference_order(const DevGeometry
 //   * a plane test is PRMT + FFMA: the byte-permute builds the float 2^23+q straight
 //     from the packed uint16, the affine map folds 2^23 into its offset.
 #ifndef CB_PSTACK_N
-#define CB_PSTACK_N 16
+#define CB_PSTACK_N 24   /* the single-level tree holds up to 31 entries; 0.013 % of its expansions exceed 24 */
 #endif
 constexpr int CB_PSTACK = CB_PSTACK_N;    // internal entries per lane
 constexpr int CB_PLEAF = 8;      // leaf queue per lane: one expansion's worth

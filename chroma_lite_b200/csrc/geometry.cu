@@ -157,6 +157,7 @@ extern "C" {
 int cb_geometry_create(const CbGeometryDesc* d, cb_geom_t* out)
 {
     CB_REQUIRE_INIT();
+    CB_SERIALISE();
     if (!d || !out) return fail(CB_ERR_INVALID, "cb_geometry_create: null argument");
     if (d->nwireplanes < 0 || (d->nwireplanes > 0 && !d->wireplanes))
         return fail(CB_ERR_INVALID, "cb_geometry_create: nwireplanes without a wireplanes array");
@@ -195,8 +196,11 @@ int cb_geometry_create(const CbGeometryDesc* d, cb_geom_t* out)
         uint64_t bytes = (d->nnodes + 16) * sizeof(uint4);
         cudaError_t e = cudaMalloc((void**)&g->nodes, bytes);
         if (e != cudaSuccess) { free_geometry(g); return cuda_fail(e, "cudaMalloc(nodes)"); }
-        cudaMemset(g->nodes, 0, bytes);
-        cudaMemcpy(g->nodes, d->nodes, d->nnodes * sizeof(uint4), cudaMemcpyHostToDevice);
+        if ((e = cudaMemset(g->nodes, 0, bytes)) != cudaSuccess ||
+            (e = cudaMemcpy(g->nodes, d->nodes, d->nnodes * sizeof(uint4), cudaMemcpyHostToDevice)) != cudaSuccess) {
+            free_geometry(g);
+            return cuda_fail(e, "upload(nodes)");
+        }
         total += bytes;
     }
     // table pool padded by 4 floats: interp_property may read fp[n] at the exact
@@ -242,7 +246,7 @@ int cb_geometry_create(const CbGeometryDesc* d, cb_geom_t* out)
         if (d->ntriangles) {
             pack_triangles_kernel<<<(unsigned)((d->ntriangles + 255) / 256), 256, 0, ctx().stream>>>(
                 g->vertices, g->triangles, g->material_codes, d_rank, d_leafbox, d->ntriangles, g->tri64);
-            e = cudaStreamSynchronize(ctx().stream);
+            e = stream_wait(ctx().stream);
             if (e != cudaSuccess) { cudaFree(d_rank); cudaFree(d_leafbox); free_geometry(g); return cuda_fail(e, "pack_triangles"); }
         }
         cudaFree(d_rank);
@@ -254,6 +258,17 @@ int cb_geometry_create(const CbGeometryDesc* d, cb_geom_t* out)
     std::vector<Entry> native;
     const char* tree_env = getenv("CHROMA_B200_TREE");
     const bool use_reference_tree = tree_env && strcmp(tree_env, "reference") == 0;
+    if (use_reference_tree) {
+        // the traversal kernels fetch at most 8 children per node (the native tree's bound); the reference
+        // format allows 15 (bvh/grid.py caps groups at MAX_CHILD): such a tree cannot be walked as it is
+        for (uint64_t i = 0; i < d->nnodes; i++)
+            if ((d->nodes[4 * i + 3] >> 28) > 8) {
+                free_geometry(g);
+                return fail(CB_ERR_UNSUPPORTED, "CHROMA_B200_TREE=reference: node %llu has %u children, the traversal "
+                            "handles at most 8 (unset CHROMA_B200_TREE to traverse the engine's own tree)",
+                            (unsigned long long)i, d->nodes[4 * i + 3] >> 28);
+            }
+    }
     if (!use_reference_tree && d->ntriangles > 0) {
         std::vector<Entry> leaves;
         collect_reference_leaves(d->nodes, d->nnodes, d->ntriangles, rank, leaves);
@@ -261,14 +276,17 @@ int cb_geometry_create(const CbGeometryDesc* d, cb_geom_t* out)
         const bool do_split = split_from_env(split);
         split.vertices = d->vertices; split.triangles = d->triangles; split.scale = d->world_scale;
         for (int a = 0; a < 3; a++) split.origin[a] = d->world_origin[a];
-        // CHROMA_B200_TREE=single: one SAH hierarchy over all leaves instead of solids first
-        const bool single_level = tree_env && strcmp(tree_env, "single") == 0;
+        // One SAH hierarchy over all leaves (default since round 2: -9 % / -19 % traversal iterations on the
+        // 29k-PMT detector, bit-identical hits); CHROMA_B200_TREE=solids builds solids first, then one
+        // subtree per solid (faster to build, the round-1 default)
+        const bool single_level = !(tree_env && strcmp(tree_env, "solids") == 0);
         rc = build_native_tree(leaves, single_level ? nullptr : d->solid_id, native, do_split ? &split : nullptr);
         if (rc != CB_OK) { free_geometry(g); return rc; }
         native.resize(native.size() + 16, Entry{0, 0, 0, 0});
         cudaError_t e = cudaMalloc((void**)&g->native_nodes, native.size() * sizeof(Entry));
         if (e != cudaSuccess) { free_geometry(g); return cuda_fail(e, "cudaMalloc(native nodes)"); }
-        cudaMemcpy(g->native_nodes, native.data(), native.size() * sizeof(Entry), cudaMemcpyHostToDevice);
+        e = cudaMemcpy(g->native_nodes, native.data(), native.size() * sizeof(Entry), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { free_geometry(g); return cuda_fail(e, "upload(native nodes)"); }
         total += native.size() * sizeof(Entry);
         g->nnative = native.size();
         root_entry = reinterpret_cast<const uint32_t*>(native.data());
@@ -286,20 +304,50 @@ int cb_geometry_create(const CbGeometryDesc* d, cb_geom_t* out)
     v.ref_root_x = d->nodes[0]; v.ref_root_y = d->nodes[1]; v.ref_root_z = d->nodes[2];
     v.nmaterials = d->nmaterials; v.nsurfaces = d->nsurfaces;
     v.wireframes = d->nwireplanes ? g->wireframes : nullptr; v.nwireplanes = d->nwireplanes;
-    // stage the leading part of the pool (the wavelength tables; the host lays
-    // the long time CDFs out last) into shared memory, up to 48 KB
-    uint64_t stage = std::min<uint64_t>(d->table_floats, 12288);
-    if (d->time_n > 0) {
-        // never split a table: only whole leading region before the first time CDF
-        int32_t first_time = INT32_MAX;
-        for (int i = 0; i < d->nmaterials; i++)
-            if (d->materials[i].num_comp > 0 && d->materials[i].comp_reemission_time_cdf >= 0)
-                first_time = std::min(first_time, d->materials[i].comp_reemission_time_cdf);
-        if (first_time != INT32_MAX) stage = std::min<uint64_t>(stage, (uint64_t)first_time);
+    // Stage the leading tables of the pool (the host lays the wavelength tables out first, the long
+    // time CDFs last) into shared memory, up to 48 KB.  The cut falls on a table boundary: Tables::at()
+    // decides shared vs global from a table's START offset, so no table may straddle it.
+    {
+        std::vector<std::pair<int64_t, int64_t>> spans;      // (offset, length) of every table in the pool
+        auto add = [&](int32_t off, int64_t len) { if (off >= 0 && len > 0) spans.push_back({off, len}); };
+        const int64_t W = d->wavelength_n;
+        for (int i = 0; i < d->nmaterials; i++) {
+            const CbMaterial& m = d->materials[i];
+            add(m.refractive_index, W); add(m.absorption_length, W); add(m.scattering_length, W);
+            const int64_t nc = std::max(m.num_comp, 0);
+            add(m.comp_reemission_prob, nc * W); add(m.comp_reemission_wvl_cdf, nc * W);
+            add(m.comp_absorption_length, nc * W); add(m.comp_reemission_time_cdf, nc * (int64_t)d->time_n);
+        }
+        for (int i = 0; i < d->nsurfaces; i++) {
+            const CbSurface& sf = d->surfaces[i];
+            if (sf.model < 0) continue;
+            add(sf.detect, W); add(sf.absorb, W); add(sf.reemit, W); add(sf.reflect_diffuse, W);
+            add(sf.reflect_specular, W); add(sf.eta, W); add(sf.k, W); add(sf.reemission_cdf, W);
+            const int64_t nd = std::max(sf.dichroic_nangles, 0), na = std::max(sf.angular_nangles, 0);
+            add(sf.dichroic_angles, nd); add(sf.dichroic_reflect, nd * W); add(sf.dichroic_transmit, nd * W);
+            add(sf.angular_angles, na); add(sf.angular_transmit, na); add(sf.angular_reflect_specular, na);
+            add(sf.angular_reflect_diffuse, na);
+        }
+        for (auto& sp : spans)
+            if ((uint64_t)(sp.first + sp.second) > d->table_floats) {
+                free_geometry(g);
+                return fail(CB_ERR_INVALID, "table at pool offset %lld (%lld floats) exceeds the table pool (%llu floats)",
+                            (long long)sp.first, (long long)sp.second, (unsigned long long)d->table_floats);
+            }
+        std::sort(spans.begin(), spans.end());
+        const int64_t LIMIT = 12288 - 4;          // 48 KB less the one-past-the-end read of interp_property
+        int64_t cut = 0, reach = 0;                 // reach: end of the tables that start before `cut`
+        for (auto& sp : spans) {
+            if (sp.first >= reach && reach <= LIMIT) cut = reach;    // a boundary nothing straddles
+            reach = std::max(reach, sp.first + sp.second);
+        }
+        if (reach <= LIMIT) cut = reach;
+        v.smem_floats = (uint32_t)cut;
+        // the copy covers one float beyond the cut (fp[n] at the exact upper edge) and is a 16-byte multiple;
+        // the pool itself is padded by 4 floats
+        g->smem_table_bytes = cut ? (uint32_t)(((cut + 1 + 3) / 4) * 16) : 0u;
+        v.smem_bytes = g->smem_table_bytes;
     }
-    stage = (stage / 4) * 4;
-    v.smem_floats = (uint32_t)stage;
-    g->smem_table_bytes = (uint32_t)(stage * 4);
     g->device_bytes = total;
     *out = geoms().add(g);
     return CB_OK;
@@ -307,9 +355,11 @@ int cb_geometry_create(const CbGeometryDesc* d, cb_geom_t* out)
 
 int cb_geometry_destroy(cb_geom_t h)
 {
+    CB_REQUIRE_INIT();
+    CB_SERIALISE();
     Geometry* g = geoms().take(h);
     if (!g) return fail(CB_ERR_INVALID, "cb_geometry_destroy: bad handle");
-    cudaStreamSynchronize(ctx().stream);
+    stream_wait(ctx().stream);
     if (ctx().l2_window_base == (g->native_nodes ? (const void*)g->native_nodes : (const void*)g->nodes)) {
         ctx().l2_window_base = nullptr;      // a later allocation may reuse the address
         ctx().l2_window_bytes = ~(size_t)0;
@@ -320,6 +370,7 @@ int cb_geometry_destroy(cb_geom_t h)
 
 int cb_geometry_info(cb_geom_t h, CbGeometryInfo* info)
 {
+    CB_REQUIRE_INIT();
     Geometry* g = geoms().get(h);
     if (!g || !info) return fail(CB_ERR_INVALID, "cb_geometry_info: bad handle");
     memset(info, 0, sizeof(*info));
@@ -339,6 +390,8 @@ int cb_detector_attach(cb_geom_t h, const int32_t* solid_id_to_channel_index, ui
                        int32_t time_cdf_len, const float* charge_cdf_x, const float* charge_cdf_y,
                        int32_t charge_cdf_len, float charge_unit)
 {
+    CB_REQUIRE_INIT();
+    CB_SERIALISE();
     Geometry* g = geoms().get(h);
     if (!g) return fail(CB_ERR_INVALID, "cb_detector_attach: bad handle");
     if (!solid_id_to_channel_index || time_cdf_len < 2 || charge_cdf_len < 2)
@@ -570,6 +623,7 @@ extern "C" int cb_bvh_build(const float* vertices, uint64_t nvertices, const uin
                             uint64_t* layer_offsets_out, int32_t* nlayers_out)
 {
     CB_REQUIRE_INIT();
+    CB_SERIALISE();
     if (!vertices || !triangles || nvertices == 0 || ntriangles == 0)
         return fail(CB_ERR_INVALID, "cb_bvh_build: empty mesh");
     if (ntriangles >= (1ull << 28)) return fail(CB_ERR_INVALID, "cb_bvh_build: too many triangles");
@@ -621,7 +675,7 @@ extern "C" int cb_bvh_build(const float* vertices, uint64_t nvertices, const uin
     BV(cudaMemcpyAsync(codes.data(), d_codes2, ntriangles * 8, cudaMemcpyDeviceToHost, c.stream));
     BV(cudaMemcpyAsync(ids.data(), d_ids2, ntriangles * 4, cudaMemcpyDeviceToHost, c.stream));
     BV(cudaMemcpyAsync(leaves.data(), d_leaves, ntriangles * 16, cudaMemcpyDeviceToHost, c.stream));
-    BV(cudaStreamSynchronize(c.stream));
+    BV(stream_wait(c.stream));
 #undef BV
     cleanup();
     for (uint64_t i = 0; i < ntriangles; i++) memcpy(&sorted[4 * i], &leaves[4ull * ids[i]], 16);

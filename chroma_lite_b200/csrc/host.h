@@ -27,6 +27,7 @@ struct Context {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;      // cb_timer_*
     cudaEvent_t kev0 = nullptr, kev1 = nullptr;    // per-call kernel timing
     cudaEvent_t iev0 = nullptr, iev1 = nullptr;    // first-step traversal kernel timing
+    std::vector<cudaEvent_t> class_ev;             // events around every launch of a propagate call (per-class kernel time)
     void* flush_buf = nullptr; size_t flush_bytes = 0;
     unsigned long long* d_counters = nullptr;      // 16 x u64 scratch (work counter, stats, flags)
     unsigned long long* h_counters = nullptr;      // pinned mirror
@@ -36,10 +37,19 @@ struct Context {
     size_t sort_tmp_bytes = 0;
     uint64_t scratch_cap = 0;                       // wavefront scratch (one rng-pool chunk)
     unsigned long long* d_step_counts = nullptr; size_t step_slots = 0;   // per-step alive counts + work counters
+    // The scratch above, the kernel stream and its events are shared by every entry point that launches
+    // kernels: those calls are serialised (CB_SERIALISE).  Host<->device copies (cb_memcpy_*) use per-thread
+    // streams and stay concurrent, which is what the upload | propagate | read-back pipeline needs.
+    std::recursive_mutex gpu_mu;
+    bool blocking_sync = false;           // host waits yield the core instead of spinning (cb_set_blocking_sync)
 };
 
 Context& ctx();
 int fail(int code, const char* fmt, ...);
+// host waits until `s` has drained: spins (cudaStreamSynchronize) or, in blocking mode, sleeps on a
+// cudaEventBlockingSync event so that many ranks / pipeline threads can share few cores
+cudaError_t stream_wait(cudaStream_t s);
+cudaError_t event_wait(cudaEvent_t e);
 int cuda_fail(cudaError_t e, const char* what);
 
 #define CB_CUDA(call)                                                         \
@@ -61,6 +71,8 @@ inline void bind_thread()
         cb::bind_thread();                                                    \
     } while (0)
 
+#define CB_SERIALISE() std::lock_guard<std::recursive_mutex> cb_serialise_guard(cb::ctx().gpu_mu)
+
 struct Geometry {
     DevGeometry dev;                 // kernel-side view (pointers below)
     // reference-layout copies (API mirror + bank utilities)
@@ -81,6 +93,8 @@ struct Geometry {
 
 struct RngPool {
     uint32_t* states = nullptr;      // 6 words per state {d, v0..v4}
+    RngPool* parent = nullptr;       // a view (cb_rng_view) borrows its parent's arrays
+    uint64_t first_stream = 0;       // state i follows stream first_stream + i
     float* bm_extra = nullptr;       // Box-Muller cache (allocated lazily for run_daq_many)
     uint32_t* bm_flag = nullptr;
     uint64_t n = 0;

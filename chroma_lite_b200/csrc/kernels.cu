@@ -313,7 +313,8 @@ struct PropParams {
     unsigned long long tail_at;
     int32_t step;                   // steps already taken by every photon in queue_in
     int32_t max_steps, use_weights, scatter_first;
-    unsigned long long* counters;   // [1] nodes, [2] tris, [3] overflow, [4] steps, [5] resolved, [9..13] ray-length stats
+    unsigned long long* counters;   // [1] nodes, [2] tris, [3] overflow, [4] steps, [5] resolved, [6] wavefront rays,
+                                    // [7] tail photons, [8] tail steps, [9..13] ray-length stats
 };
 
 // Queue entries: chunk-local photon index in the low 31 bits; bit 31 marks a photon that sits on
@@ -423,6 +424,7 @@ step_intersect_kernel(const __grid_constant__ DevGeometry g, const __grid_consta
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const unsigned long long n = *P.n_in;
     if (n <= P.tail_at) return;              // the tail kernel behind this launch takes these
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(P.counters + 6, n);   // rays traced by the wavefront
     const PhotonRaySource src = {P};
     persistent_intersect<COUNT>(g, src, n, P.cursor, (uint32_t)__cvta_generic_to_shared(smem_raw), P.counters, tune);
 }
@@ -443,7 +445,7 @@ step_physics_kernel(const __grid_constant__ DevGeometry g, const __grid_constant
     const uint32_t n_in = (uint32_t)*P.n_in;
     if (n_in <= P.tail_at) return;           // (uniform) the tail kernel behind this launch takes these
     float* stab = reinterpret_cast<float*>(smem_raw);
-    stage_tables(stab, g.tables, g.smem_floats * 4u, &mbar);
+    stage_tables(stab, g.tables, g.smem_bytes, &mbar);
     Tables T = {stab, g.tables, g.smem_floats};
     const unsigned lane = threadIdx.x & 31u;
     const bool last_step = (P.step + 1 >= P.max_steps);
@@ -508,7 +510,7 @@ propagate_tail_kernel(const __grid_constant__ DevGeometry g, const __grid_consta
     const unsigned long long n_in = *P.n_in;
     if (n_in > P.tail_at || n_in == 0) return;       // (uniform) still the wavefront kernels' turn, or nothing left
     float* stab = reinterpret_cast<float*>(smem_raw);
-    const uint32_t tab_bytes = g.smem_floats * 4u;
+    const uint32_t tab_bytes = g.smem_bytes;
     const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     uint2* wstack = reinterpret_cast<uint2*>(smem_raw + ((tab_bytes + 127u) & ~127u)) + warp * (CB_WSTACK + CB_WLEAF);
     uint2* wleaf = wstack + CB_WSTACK;
@@ -567,7 +569,8 @@ propagate_tail_kernel(const __grid_constant__ DevGeometry g, const __grid_consta
 #endif
         }
     }
-    if (lane == 0 && nsteps_total) atomicAdd(P.counters + 4, nsteps_total);
+    if (lane == 0 && nsteps_total) { atomicAdd(P.counters + 4, nsteps_total); atomicAdd(P.counters + 8, nsteps_total); }
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(P.counters + 7, n_in);
     if (COUNT) {
         atomicAdd(P.counters + 1, (unsigned long long)cnt.nodes);
         atomicAdd(P.counters + 2, (unsigned long long)cnt.tris);
@@ -822,6 +825,18 @@ __global__ void daq_finalize_kernel(uint64_t n, const uint32_t* time_int, const 
     q_out[i] = q_int[i] * charge_unit;
 }
 
+// dst (+)= src, the three atomics of run_daq applied array to array
+__global__ void daq_fold_into_kernel(uint64_t n, uint32_t* __restrict__ t_dst, const uint32_t* __restrict__ t_src,
+                                     uint32_t* __restrict__ q_dst, const uint32_t* __restrict__ q_src,
+                                     uint32_t* __restrict__ h_dst, const uint32_t* __restrict__ h_src)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    t_dst[i] = min(t_dst[i], t_src[i]);
+    q_dst[i] += q_src[i];
+    h_dst[i] |= h_src[i];
+}
+
 static int check_bank(const CbPhotonBank* b, const char* who)
 {
     if (!b) return fail(CB_ERR_INVALID, "%s: null photon bank", who);
@@ -870,14 +885,14 @@ static int compact(const CbPhotonBank* src, uint64_t first, uint64_t n, uint32_t
     CB_CUDA(cudaGetLastError());
     uint32_t total = 0;
     CB_CUDA(cudaMemcpyAsync(&total, c.d_block_counts + ntiles, 4, cudaMemcpyDeviceToHost, c.stream));
-    CB_CUDA(cudaStreamSynchronize(c.stream));
+    CB_CUDA(stream_wait(c.stream));
     if (count_out) *count_out = total;
     if (dst && total) {
         if (dst->n < total) return fail(CB_ERR_INVALID, "destination bank too small (%llu < %u)", (unsigned long long)dst->n, total);
         tile_scatter_kernel<HITS><<<(unsigned)ntiles, 256, 0, c.stream>>>(*src, first, n, flag, solid_map, s2c,
                                                                          c.d_block_counts, *dst, d_channels);
         CB_CUDA(cudaGetLastError());
-        CB_CUDA(cudaStreamSynchronize(c.stream));
+        CB_CUDA(stream_wait(c.stream));
     }
     return CB_OK;
 }
@@ -892,6 +907,7 @@ int cb_intersect(cb_geom_t gh, const float* d_origins, const float* d_directions
                  uint64_t n, int32_t* d_triangle_out, float* d_distance_out)
 {
     CB_REQUIRE_INIT();
+    CB_SERIALISE();
     Geometry* g = geoms().get(gh);
     if (!g) return fail(CB_ERR_INVALID, "cb_intersect: bad geometry handle");
     if (n == 0) return CB_OK;
@@ -910,7 +926,7 @@ int cb_intersect(cb_geom_t gh, const float* d_origins, const float* d_directions
     intersect_kernel<false><<<blocks, INT_THREADS, smem, c.stream>>>(g->dev, src, n, c.d_counters, tune_from_env());
     CB_CUDA(cudaGetLastError());
     CB_CUDA(cudaMemcpyAsync(c.h_counters, c.d_counters, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c.stream));
-    CB_CUDA(cudaStreamSynchronize(c.stream));
+    CB_CUDA(stream_wait(c.stream));
     if (c.h_counters[3]) return fail(CB_ERR_CUDA, "cb_intersect: traversal stack overflow");
     return CB_OK;
 }
@@ -928,6 +944,7 @@ int cb_propagate(const CbPhotonBank* bank, cb_geom_t gh, cb_rng_t rh, int32_t nt
                  CbPropagateStats* stats)
 {
     CB_REQUIRE_INIT();
+    CB_SERIALISE();
     int rc = check_bank(bank, "cb_propagate");
     if (rc) return rc;
     Geometry* g = geoms().get(gh);
@@ -1004,6 +1021,17 @@ int cb_propagate(const CbPhotonBank* bank, cb_geom_t gh, cb_rng_t rh, int32_t nt
 
     unsigned long long tot[16] = {0};
     uint32_t launches = 0;
+    // per-class kernel time: an event before and after every launch (no host synchronisation);
+    // class of interval k in cls[k]: 0 traversal, 1 physics, 2 tail
+    std::vector<int> cls;
+    size_t nev = 0;
+    auto stamp = [&]() -> cudaEvent_t {
+        if (nev == c.class_ev.size()) { cudaEvent_t e; cudaEventCreate(&e); c.class_ev.push_back(e); }
+        cudaEvent_t e = c.class_ev[nev++];
+        cudaEventRecord(e, c.stream);
+        return e;
+    };
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> spans;
     uint64_t int0_rays = 0;
     CB_CUDA(cudaEventRecord(c.kev0, c.stream));
     mark("kev0");
@@ -1054,12 +1082,17 @@ int cb_propagate(const CbPhotonBank* bank, cb_geom_t gh, cb_rng_t rh, int32_t nt
                     PropParams PI = P;
                     if (sort_threshold && exact && n_alive >= sort_threshold) PI.hit_slots = c.d_sorted;
                     mark("pre-int");
+                    cudaEvent_t e0 = stamp();
                     k_int<<<iblocks, INT_THREADS, smem_int, c.stream>>>(g->dev, PI, tune);
+                    cudaEvent_t e1 = stamp();
+                    spans.push_back({e0, e1}); cls.push_back(0);
                     mark("int");
                     if (trace) cudaEventRecord(tev[1], c.stream);
                     if (time_it) { CB_CUDA(cudaEventRecord(c.iev1, c.stream)); int0_rays = n_alive; }
                     const unsigned pblocks = (unsigned)std::min<uint64_t>(blocks, (uint64_t)c.sm_count * phys_per_sm);
                     k_phys<<<pblocks, PROP_THREADS, smem_tab, c.stream>>>(g->dev, P);
+                    cudaEvent_t e2 = stamp();
+                    spans.push_back({e1, e2}); cls.push_back(1);
                     mark("phys");
                     if (trace) cudaEventRecord(tev[2], c.stream);
                     CB_CUDA(cudaGetLastError());
@@ -1072,7 +1105,10 @@ int cb_propagate(const CbPhotonBank* bank, cb_geom_t gh, cb_rng_t rh, int32_t nt
                     const unsigned blocks = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((most + per_block - 1) / per_block,
                                                                                              (uint64_t)c.sm_count * tail_per_sm));
                     if (trace) cudaEventRecord(tev[0], c.stream);
+                    cudaEvent_t t0 = stamp();
                     k_tail<<<blocks, TAIL_THREADS, smem_tail, c.stream>>>(g->dev, P);
+                    cudaEvent_t t1 = stamp();
+                    spans.push_back({t0, t1}); cls.push_back(2);
                     mark("tail");
                     CB_CUDA(cudaGetLastError());
                     if (trace) {
@@ -1084,7 +1120,7 @@ int cb_propagate(const CbPhotonBank* bank, cb_geom_t gh, cb_rng_t rh, int32_t nt
 #ifdef CB_TAIL_PROFILE
                     if (!wave && P.queue_in) {
                         // debug build only: when did the tail's photons finish, and after how many steps?
-                        cudaStreamSynchronize(c.stream);
+                        stream_wait(c.stream);
                         std::vector<uint32_t> q(n_alive), st(cap), tm(cap);
                         cudaMemcpy(q.data(), P.queue_in, n_alive * 4, cudaMemcpyDeviceToHost);
                         cudaMemcpy(st.data(), c.d_hit_tri, cap * 4, cudaMemcpyDeviceToHost);
@@ -1120,7 +1156,7 @@ int cb_propagate(const CbPhotonBank* bank, cb_geom_t gh, cb_rng_t rh, int32_t nt
             if (n_alive == 0) break;
             // one read-back per batch: photons queued for the next step (0 once a tail launch has run)
             CB_CUDA(cudaMemcpyAsync(c.h_counters, d_alive + step, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c.stream));
-            CB_CUDA(cudaStreamSynchronize(c.stream));
+            CB_CUDA(stream_wait(c.stream));
             if (trace) {
                 float a = 0, b2 = 0;
                 cudaEventElapsedTime(&a, tev[0], tev[1]); cudaEventElapsedTime(&b2, tev[1], tev[2]);
@@ -1131,15 +1167,15 @@ int cb_propagate(const CbPhotonBank* bank, cb_geom_t gh, cb_rng_t rh, int32_t nt
             exact = true;
         }
         CB_CUDA(cudaMemcpyAsync(c.h_counters, c.d_counters, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c.stream));
-        CB_CUDA(cudaStreamSynchronize(c.stream));
-        for (int i = 1; i < 6; i++) tot[i] += c.h_counters[i];
+        CB_CUDA(stream_wait(c.stream));
+        for (int i = 1; i < 9; i++) tot[i] += c.h_counters[i];
         if (trace && count)
             fprintf(stderr, "[cb trace] ray iterations: max %llu, >100: %llu, >300: %llu, >1000: %llu, total %llu\n",
                     c.h_counters[9], c.h_counters[10], c.h_counters[11], c.h_counters[12], c.h_counters[13]);
     }
     mark("end");
     CB_CUDA(cudaEventRecord(c.kev1, c.stream));
-    CB_CUDA(cudaEventSynchronize(c.kev1));
+    CB_CUDA(event_wait(c.kev1));
     if (timeline) {
         for (size_t i = 1; i < tl_ev.size(); i++) {
             float ms = 0; cudaEventElapsedTime(&ms, tl_ev[i - 1], tl_ev[i]);
@@ -1154,6 +1190,14 @@ int cb_propagate(const CbPhotonBank* bank, cb_geom_t gh, cb_rng_t rh, int32_t nt
         stats->launches = launches;
         cudaEventElapsedTime(&stats->kernel_ms, c.kev0, c.kev1);
         if (int0_rays) { cudaEventElapsedTime(&stats->intersect0_ms, c.iev0, c.iev1); stats->intersect0_rays = int0_rays; }
+        float by_class[3] = {0.f, 0.f, 0.f};
+        for (size_t k = 0; k < spans.size(); k++) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, spans[k].first, spans[k].second) == cudaSuccess) by_class[cls[k]] += ms;
+        }
+        stats->intersect_ms = by_class[0]; stats->physics_ms = by_class[1]; stats->tail_ms = by_class[2];
+        stats->intersect_rays = tot[6]; stats->tail_photons = tot[7]; stats->tail_steps = tot[8];
+        stats->physics_steps = tot[4] - tot[8];
     }
     if (tot[3]) return fail(CB_ERR_CUDA, "cb_propagate: traversal stack overflow");
     return CB_OK;
@@ -1162,19 +1206,21 @@ int cb_propagate(const CbPhotonBank* bank, cb_geom_t gh, cb_rng_t rh, int32_t nt
 int cb_photon_duplicate(const CbPhotonBank* bank, uint64_t nphotons, int32_t ncopies)
 {
     CB_REQUIRE_INIT();
+    CB_SERIALISE();
     int rc = check_bank(bank, "cb_photon_duplicate");
     if (rc) return rc;
     if (ncopies <= 1 || nphotons == 0) return CB_OK;
     if (nphotons * (uint64_t)ncopies > bank->n) return fail(CB_ERR_INVALID, "cb_photon_duplicate: bank too small");
     duplicate_kernel<<<(unsigned)((nphotons + 255) / 256), 256, 0, ctx().stream>>>(*bank, nphotons, ncopies - 1);
     CB_CUDA(cudaGetLastError());
-    CB_CUDA(cudaStreamSynchronize(ctx().stream));
+    CB_CUDA(stream_wait(ctx().stream));
     return CB_OK;
 }
 
 int cb_count_photons(const CbPhotonBank* bank, uint64_t first, uint64_t n, uint32_t flag, uint32_t* count_out)
 {
     CB_REQUIRE_INIT();
+    CB_SERIALISE();
     int rc = check_bank(bank, "cb_count_photons");
     if (rc) return rc;
     return compact<false>(bank, first, n, flag, nullptr, nullptr, nullptr, count_out);
@@ -1183,6 +1229,7 @@ int cb_copy_photons(const CbPhotonBank* src, uint64_t first, uint64_t n, uint32_
                     uint32_t* count_out)
 {
     CB_REQUIRE_INIT();
+    CB_SERIALISE();
     int rc = check_bank(src, "cb_copy_photons");
     if (rc) return rc;
     if ((rc = check_bank(dst, "cb_copy_photons(dst)"))) return rc;
@@ -1192,6 +1239,7 @@ int cb_count_photon_hits(const CbPhotonBank* bank, uint64_t first, uint64_t n, u
                          uint32_t* count_out)
 {
     CB_REQUIRE_INIT();
+    CB_SERIALISE();
     int rc = check_bank(bank, "cb_count_photon_hits");
     if (rc) return rc;
     Geometry* g = geoms().get(gh);
@@ -1202,6 +1250,7 @@ int cb_copy_photon_hits(const CbPhotonBank* src, uint64_t first, uint64_t n, uin
                         const CbPhotonBank* dst, int32_t* d_channels_out, uint32_t* count_out)
 {
     CB_REQUIRE_INIT();
+    CB_SERIALISE();
     int rc = check_bank(src, "cb_copy_photon_hits");
     if (rc) return rc;
     if ((rc = check_bank(dst, "cb_copy_photon_hits(dst)"))) return rc;
@@ -1213,6 +1262,7 @@ int cb_copy_photon_hits(const CbPhotonBank* src, uint64_t first, uint64_t n, uin
 int cb_copy_photon_queue(const CbPhotonBank* src, const uint32_t* d_queue, uint64_t n, const CbPhotonBank* dst)
 {
     CB_REQUIRE_INIT();
+    CB_SERIALISE();
     int rc = check_bank(src, "cb_copy_photon_queue");
     if (rc) return rc;
     if ((rc = check_bank(dst, "cb_copy_photon_queue(dst)"))) return rc;
@@ -1220,7 +1270,7 @@ int cb_copy_photon_queue(const CbPhotonBank* src, const uint32_t* d_queue, uint6
     if (dst->n < n) return fail(CB_ERR_INVALID, "cb_copy_photon_queue: destination too small");
     gather_queue_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx().stream>>>(*src, d_queue, n, *dst);
     CB_CUDA(cudaGetLastError());
-    CB_CUDA(cudaStreamSynchronize(ctx().stream));
+    CB_CUDA(stream_wait(ctx().stream));
     return CB_OK;
 }
 
@@ -1228,6 +1278,7 @@ int cb_copy_photon_queue(const CbPhotonBank* src, const uint32_t* d_queue, uint6
 int cb_daq_create(cb_geom_t gh, int32_t ndaq, cb_daq_t* out)
 {
     CB_REQUIRE_INIT();
+    CB_SERIALISE();
     Geometry* g = geoms().get(gh);
     if (!g || !out) return fail(CB_ERR_INVALID, "cb_daq_create: bad argument");
     if (g->nchannels <= 0 || !g->solid_to_channel)
@@ -1239,20 +1290,28 @@ int cb_daq_create(cb_geom_t gh, int32_t ndaq, cb_daq_t* out)
     if ((e = cudaMalloc(&d->earliest_time, d->count * 4)) || (e = cudaMalloc(&d->earliest_time_int, d->count * 4)) ||
         (e = cudaMalloc(&d->channel_history, d->count * 4)) || (e = cudaMalloc(&d->channel_q_int, d->count * 4)) ||
         (e = cudaMalloc(&d->channel_q, d->count * 4))) {
+        cudaFree(d->earliest_time); cudaFree(d->earliest_time_int); cudaFree(d->channel_history);
+        cudaFree(d->channel_q_int); cudaFree(d->channel_q);
         delete d;
         return cuda_fail(e, "cudaMalloc(daq)");
     }
-    cudaMemset(d->channel_history, 0, d->count * 4);
-    cudaMemset(d->channel_q_int, 0, d->count * 4);
-    cudaMemset(d->channel_q, 0, d->count * 4);
+    if ((e = cudaMemset(d->channel_history, 0, d->count * 4)) || (e = cudaMemset(d->channel_q_int, 0, d->count * 4)) ||
+        (e = cudaMemset(d->channel_q, 0, d->count * 4))) {
+        cudaFree(d->earliest_time); cudaFree(d->earliest_time_int); cudaFree(d->channel_history);
+        cudaFree(d->channel_q_int); cudaFree(d->channel_q);
+        delete d;
+        return cuda_fail(e, "cudaMemset(daq)");
+    }
     *out = daqs().add(d);
     return CB_OK;
 }
 int cb_daq_destroy(cb_daq_t h)
 {
+    CB_REQUIRE_INIT();
+    CB_SERIALISE();
     Daq* d = daqs().take(h);
     if (!d) return fail(CB_ERR_INVALID, "cb_daq_destroy: bad handle");
-    cudaStreamSynchronize(ctx().stream);
+    stream_wait(ctx().stream);
     cudaFree(d->earliest_time); cudaFree(d->earliest_time_int); cudaFree(d->channel_history);
     cudaFree(d->channel_q_int); cudaFree(d->channel_q);
     delete d;
@@ -1260,6 +1319,8 @@ int cb_daq_destroy(cb_daq_t h)
 }
 int cb_daq_begin_acquire(cb_daq_t h)
 {
+    CB_REQUIRE_INIT();
+    CB_SERIALISE();
     Daq* d = daqs().get(h);
     if (!d) return fail(CB_ERR_INVALID, "cb_daq_begin_acquire: bad handle");
     Context& c = ctx();
@@ -1269,13 +1330,14 @@ int cb_daq_begin_acquire(cb_daq_t h)
     CB_CUDA(cudaMemsetAsync(d->channel_q_int, 0, d->count * 4, c.stream));
     CB_CUDA(cudaMemsetAsync(d->channel_q, 0, d->count * 4, c.stream));
     CB_CUDA(cudaMemsetAsync(d->channel_history, 0, d->count * 4, c.stream));
-    CB_CUDA(cudaStreamSynchronize(c.stream));
+    CB_CUDA(stream_wait(c.stream));
     return cb_memset32(d->earliest_time_int, bits, d->count);
 }
 int cb_daq_acquire(cb_daq_t h, const CbPhotonBank* bank, cb_rng_t rh, int32_t nthreads_per_block,
                    int32_t max_blocks, uint64_t start_photon, uint64_t nphotons, float weight)
 {
     CB_REQUIRE_INIT();
+    CB_SERIALISE();
     Daq* d = daqs().get(h);
     RngPool* r = rngs().get(rh);
     if (!d) return fail(CB_ERR_INVALID, "cb_daq_acquire: bad daq handle");
@@ -1318,21 +1380,38 @@ int cb_daq_acquire(cb_daq_t h, const CbPhotonBank* bank, cb_rng_t rh, int32_t nt
             CB_CUDA(cudaGetLastError());
         }
     }
-    CB_CUDA(cudaStreamSynchronize(c.stream));
+    CB_CUDA(stream_wait(c.stream));
     return CB_OK;
 }
 int cb_daq_finalize(cb_daq_t h)
 {
+    CB_REQUIRE_INIT();
+    CB_SERIALISE();
     Daq* d = daqs().get(h);
     if (!d) return fail(CB_ERR_INVALID, "cb_daq_finalize: bad handle");
     Context& c = ctx();
     daq_finalize_kernel<<<(unsigned)((d->count + 255) / 256), 256, 0, c.stream>>>(
         d->count, d->earliest_time_int, d->channel_q_int, d->geom->charge_unit, d->earliest_time, d->channel_q);
     CB_CUDA(cudaGetLastError());
-    CB_CUDA(cudaStreamSynchronize(c.stream));
+    CB_CUDA(stream_wait(c.stream));
     return CB_OK;
 }
 int cb_daq_end_acquire(cb_daq_t h) { return cb_daq_finalize(h); }
+int cb_daq_fold(cb_daq_t dst, cb_daq_t src)
+{
+    CB_REQUIRE_INIT();
+    CB_SERIALISE();
+    Daq* a = daqs().get(dst);
+    Daq* b = daqs().get(src);
+    if (!a || !b || a->count != b->count) return fail(CB_ERR_INVALID, "cb_daq_fold: bad or mismatched handles");
+    Context& c = ctx();
+    daq_fold_into_kernel<<<(unsigned)((a->count + 255) / 256), 256, 0, c.stream>>>(
+        a->count, a->earliest_time_int, b->earliest_time_int, a->channel_q_int, b->channel_q_int, a->channel_history,
+        b->channel_history);
+    CB_CUDA(cudaGetLastError());
+    CB_CUDA(stream_wait(c.stream));
+    return CB_OK;
+}
 int cb_daq_pointers(cb_daq_t h, void** t, void** q, void** flags, void** time_int, void** q_int, uint64_t* count)
 {
     Daq* d = daqs().get(h);

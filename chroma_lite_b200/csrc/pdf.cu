@@ -218,6 +218,7 @@ int cb_pdf_bin_hits(int32_t nchannels, const float* q, const float* t, uint32_t*
                     float tmax, int32_t qbins, float qmin, float qmax, uint32_t* pdf)
 {
     CB_REQUIRE_INIT();
+    CB_SERIALISE();
     if (nchannels < 0 || tbins <= 0 || qbins <= 0 || !q || !t || !hitcount || !pdf)
         return fail(CB_ERR_INVALID, "cb_pdf_bin_hits: bad arguments");
     if (nchannels == 0) return CB_OK;
@@ -225,7 +226,7 @@ int cb_pdf_bin_hits(int32_t nchannels, const float* q, const float* t, uint32_t*
     pdf_bin_hits_kernel<<<blocks_for(nchannels), PDF_THREADS, 0, c.stream>>>(nchannels, q, t, hitcount, tbins, tmin, tmax,
                                                                               qbins, qmin, qmax, pdf);
     CB_CUDA(cudaGetLastError());
-    CB_CUDA(cudaStreamSynchronize(c.stream));
+    CB_CUDA(stream_wait(c.stream));
     return CB_OK;
 }
 
@@ -234,6 +235,7 @@ int cb_pdf_accumulate_moments(int32_t time_only, int32_t nchannels, const float*
                               float* t_mom2, float* q_mom1, float* q_mom2)
 {
     CB_REQUIRE_INIT();
+    CB_SERIALISE();
     if (nchannels < 0 || !mc_time || !mom0 || !t_mom1 || !t_mom2 || (!time_only && (!mc_charge || !q_mom1 || !q_mom2)))
         return fail(CB_ERR_INVALID, "cb_pdf_accumulate_moments: bad arguments");
     if (nchannels == 0) return CB_OK;
@@ -242,7 +244,7 @@ int cb_pdf_accumulate_moments(int32_t time_only, int32_t nchannels, const float*
                                                                              tmax, qmin, qmax, mom0, t_mom1, t_mom2,
                                                                              q_mom1, q_mom2);
     CB_CUDA(cudaGetLastError());
-    CB_CUDA(cudaStreamSynchronize(c.stream));
+    CB_CUDA(stream_wait(c.stream));
     return CB_OK;
 }
 
@@ -253,6 +255,7 @@ int cb_pdf_accumulate_kernel_eval(int32_t time_only, int32_t nchannels, const ui
                                   uint32_t* hitcount, float* time_pdf_values, float* charge_pdf_values)
 {
     CB_REQUIRE_INIT();
+    CB_SERIALISE();
     if (nchannels < 0 || !event_hit || !event_time || !mc_time || !inv_time_bandwidths || !hitcount || !time_pdf_values ||
         (!time_only && (!event_charge || !mc_charge || !inv_charge_bandwidths || !charge_pdf_values)))
         return fail(CB_ERR_INVALID, "cb_pdf_accumulate_kernel_eval: bad arguments");
@@ -262,7 +265,7 @@ int cb_pdf_accumulate_kernel_eval(int32_t time_only, int32_t nchannels, const ui
         time_only, nchannels, event_hit, event_time, event_charge, mc_time, mc_charge, tmin, tmax, qmin, qmax,
         inv_time_bandwidths, inv_charge_bandwidths, hitcount, time_pdf_values, charge_pdf_values);
     CB_CUDA(cudaGetLastError());
-    CB_CUDA(cudaStreamSynchronize(c.stream));
+    CB_CUDA(stream_wait(c.stream));
     return CB_OK;
 }
 
@@ -272,6 +275,7 @@ int cb_pdf_accumulate_eval(int32_t nchannels, int32_t ndaq, int32_t nhit, const 
                            const uint32_t* map_hit_offset_to_channel_id, float* nearest_mc)
 {
     CB_REQUIRE_INIT();
+    CB_SERIALISE();
     if (nchannels < 0 || ndaq <= 0 || nhit < 0 || min_bin_content <= 0 || !event_hit || !event_time || !mc_time ||
         !hitcount || !bincount || (nhit > 0 && (!map_hit_offset_to_channel_id || !nearest_mc)))
         return fail(CB_ERR_INVALID, "cb_pdf_accumulate_eval: bad arguments");
@@ -291,7 +295,7 @@ int cb_pdf_accumulate_eval(int32_t nchannels, int32_t ndaq, int32_t nhit, const 
         nchannels, ndaq, nhit, count_blocks, event_hit, event_time, mc_time, hitcount, bincount, min_twidth, tmin, tmax,
         min_bin_content, map_hit_offset_to_channel_id, nearest_mc, cap);
     CB_CUDA(cudaGetLastError());
-    CB_CUDA(cudaStreamSynchronize(c.stream));
+    CB_CUDA(stream_wait(c.stream));
     return CB_OK;
 }
 

@@ -2,9 +2,10 @@
 #include "host.h"
 #include <string.h>
 #include <stdlib.h>
+#include <time.h>
 #include <algorithm>
 #ifndef CB_L2_WINDOW_MB_DEFAULT
-#define CB_L2_WINDOW_MB_DEFAULT 0.0   /* until measured */
+#define CB_L2_WINDOW_MB_DEFAULT 16.0   /* measured r02: 16 MB -0.15 ms per 2.5 M-photon event, 48 MB the same, 96 MB +0.5 ms */
 #endif
 
 namespace cb {
@@ -28,6 +29,29 @@ int cuda_fail(cudaError_t e, const char* what)
 {
     int code = (e == cudaErrorMemoryAllocation) ? CB_ERR_NOMEM : CB_ERR_CUDA;
     return fail(code, "CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+}
+
+cudaError_t stream_wait(cudaStream_t s)
+{
+    if (!g_ctx.blocking_sync) return cudaStreamSynchronize(s);
+    static thread_local cudaEvent_t ev = nullptr;
+    if (!ev) {
+        cudaError_t e = cudaEventCreateWithFlags(&ev, cudaEventBlockingSync | cudaEventDisableTiming);
+        if (e != cudaSuccess) { ev = nullptr; return e; }
+    }
+    cudaError_t e = cudaEventRecord(ev, s);
+    return e != cudaSuccess ? e : cudaEventSynchronize(ev);
+}
+// timing events are created spinning; in blocking mode wait for the stream position behind them instead
+cudaError_t event_wait(cudaEvent_t e)
+{
+    if (!g_ctx.blocking_sync) return cudaEventSynchronize(e);
+    while (true) {
+        cudaError_t q = cudaEventQuery(e);
+        if (q != cudaErrorNotReady) return q;
+        struct timespec ts = {0, 20000};      // 20 us
+        nanosleep(&ts, nullptr);
+    }
 }
 
 static Registry<Geometry> g_geoms;
@@ -233,7 +257,14 @@ int cb_init(int device)
     // L2 persistence: the carve-out is sized when a geometry's tree prefix is pinned (l2_pin_tree_prefix)
     c.l2_persist_max = (size_t)prop.persistingL2CacheMaxSize;
     c.l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
+    if (const char* e = getenv("CHROMA_B200_SYNC")) c.blocking_sync = strcmp(e, "block") == 0;
     c.device = device;
+    return CB_OK;
+}
+
+int cb_set_blocking_sync(int32_t on)
+{
+    ctx().blocking_sync = on != 0;
     return CB_OK;
 }
 
@@ -242,7 +273,7 @@ int cb_sm_count(void) { return ctx().sm_count; }
 int cb_synchronize(void)
 {
     CB_REQUIRE_INIT();
-    CB_CUDA(cudaStreamSynchronize(ctx().stream));
+    CB_CUDA(stream_wait(ctx().stream));
     CB_CUDA(cudaDeviceSynchronize());
     return CB_OK;
 }
@@ -280,7 +311,7 @@ int cb_memcpy_h2d(void* d, const void* h, uint64_t bytes)
     if (bytes == 0) return CB_OK;
     cudaStream_t s = thread_copy_stream();
     CB_CUDA(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, s));
-    CB_CUDA(cudaStreamSynchronize(s));
+    CB_CUDA(stream_wait(s));
     return CB_OK;
 }
 int cb_memcpy_d2h(void* h, const void* d, uint64_t bytes)
@@ -289,7 +320,7 @@ int cb_memcpy_d2h(void* h, const void* d, uint64_t bytes)
     if (bytes == 0) return CB_OK;
     cudaStream_t s = thread_copy_stream();
     CB_CUDA(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, s));
-    CB_CUDA(cudaStreamSynchronize(s));
+    CB_CUDA(stream_wait(s));
     return CB_OK;
 }
 int cb_memcpy_d2d(void* dst, const void* src, uint64_t bytes)
@@ -298,7 +329,7 @@ int cb_memcpy_d2d(void* dst, const void* src, uint64_t bytes)
     if (bytes == 0) return CB_OK;
     cudaStream_t s = thread_copy_stream();
     CB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, s));
-    CB_CUDA(cudaStreamSynchronize(s));
+    CB_CUDA(stream_wait(s));
     return CB_OK;
 }
 int cb_memset32(void* dptr, uint32_t value, uint64_t count)
@@ -314,7 +345,7 @@ int cb_memset32(void* dptr, uint32_t value, uint64_t count)
         fill32_kernel<<<blocks, 256, 0, s>>>((uint32_t*)dptr, value, count);
         CB_CUDA(cudaGetLastError());
     }
-    CB_CUDA(cudaStreamSynchronize(s));
+    CB_CUDA(stream_wait(s));
     return CB_OK;
 }
 int cb_host_alloc(uint64_t bytes, void** hptr)
@@ -325,6 +356,7 @@ int cb_host_alloc(uint64_t bytes, void** hptr)
 }
 int cb_host_free(void* hptr)
 {
+    CB_REQUIRE_INIT();
     if (!hptr) return CB_OK;
     CB_CUDA(cudaFreeHost(hptr));
     return CB_OK;
@@ -349,7 +381,7 @@ int cb_timer_stop(float* ms)
 {
     CB_REQUIRE_INIT();
     CB_CUDA(cudaEventRecord(ctx().ev1, ctx().stream));
-    CB_CUDA(cudaEventSynchronize(ctx().ev1));
+    CB_CUDA(event_wait(ctx().ev1));
     float t = 0.f;
     CB_CUDA(cudaEventElapsedTime(&t, ctx().ev0, ctx().ev1));
     if (ms) *ms = t;
@@ -370,37 +402,69 @@ int cb_flush_l2(void)
 }
 
 // ---------------------------------------------------------------- RNG pool
-int cb_rng_create(uint64_t n, uint64_t seed, uint64_t offset, cb_rng_t* out)
+int cb_rng_create_streams(uint64_t n, uint64_t seed, uint64_t first_stream, uint64_t offset, cb_rng_t* out)
 {
     CB_REQUIRE_INIT();
+    CB_SERIALISE();
     if (!out) return fail(CB_ERR_INVALID, "cb_rng_create: null out pointer");
     int rc = xw_upload_tables();
     if (rc) return rc;
     RngPool* r = new RngPool();
     r->n = n;
+    r->first_stream = first_stream;
     cudaError_t e = cudaMalloc(&r->states, std::max<uint64_t>(n, 1) * 24);
     if (e != cudaSuccess) { delete r; return cuda_fail(e, "cudaMalloc(rng states)"); }
     if (n) {
         unsigned blocks = (unsigned)((n + 255) / 256);
-        rng_init_kernel<<<blocks, 256, 0, ctx().stream>>>(r->states, n, seed, 0, offset, d_xw_seq, d_xw_off);
+        rng_init_kernel<<<blocks, 256, 0, ctx().stream>>>(r->states, n, seed, first_stream, offset, d_xw_seq, d_xw_off);
         e = cudaGetLastError();
-        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx().stream);
+        if (e == cudaSuccess) e = stream_wait(ctx().stream);
         if (e != cudaSuccess) { cudaFree(r->states); delete r; return cuda_fail(e, "rng_init_kernel"); }
     }
     *out = rngs().add(r);
     return CB_OK;
 }
+int cb_rng_create(uint64_t n, uint64_t seed, uint64_t offset, cb_rng_t* out)
+{
+    return cb_rng_create_streams(n, seed, 0, offset, out);
+}
+int cb_rng_view(cb_rng_t parent, uint64_t first, uint64_t count, cb_rng_t* out)
+{
+    CB_REQUIRE_INIT();
+    CB_SERIALISE();
+    RngPool* p = rngs().get(parent);
+    if (!p || !out) return fail(CB_ERR_INVALID, "cb_rng_view: bad argument");
+    if (first + count > p->n) return fail(CB_ERR_INVALID, "cb_rng_view: window [%llu, %llu) exceeds the pool (%llu)",
+                                          (unsigned long long)first, (unsigned long long)(first + count), (unsigned long long)p->n);
+    // the Box-Muller cache of run_daq_many lives beside the states: allocate it now so that the window sees it
+    if (!p->bm_flag) {
+        CB_CUDA(cudaMalloc(&p->bm_flag, std::max<uint64_t>(p->n, 1) * 4));
+        CB_CUDA(cudaMalloc(&p->bm_extra, std::max<uint64_t>(p->n, 1) * 4));
+        CB_CUDA(cudaMemset(p->bm_flag, 0, std::max<uint64_t>(p->n, 1) * 4));
+        CB_CUDA(cudaMemset(p->bm_extra, 0, std::max<uint64_t>(p->n, 1) * 4));
+    }
+    RngPool* v = new RngPool();
+    v->parent = p->parent ? p->parent : p;
+    v->states = p->states + 6 * first;
+    v->bm_flag = p->bm_flag + first; v->bm_extra = p->bm_extra + first;
+    v->n = count; v->first_stream = p->first_stream + first;
+    *out = rngs().add(v);
+    return CB_OK;
+}
 int cb_rng_destroy(cb_rng_t h)
 {
+    CB_REQUIRE_INIT();
+    CB_SERIALISE();
     RngPool* r = rngs().take(h);
     if (!r) return fail(CB_ERR_INVALID, "cb_rng_destroy: bad handle");
-    cudaStreamSynchronize(ctx().stream);
-    cudaFree(r->states); cudaFree(r->bm_extra); cudaFree(r->bm_flag);
+    stream_wait(ctx().stream);
+    if (!r->parent) { cudaFree(r->states); cudaFree(r->bm_extra); cudaFree(r->bm_flag); }
     delete r;
     return CB_OK;
 }
 int cb_rng_size(cb_rng_t h, uint64_t* n)
 {
+    CB_REQUIRE_INIT();
     RngPool* r = rngs().get(h);
     if (!r) return fail(CB_ERR_INVALID, "cb_rng_size: bad handle");
     *n = r->n;
@@ -408,6 +472,7 @@ int cb_rng_size(cb_rng_t h, uint64_t* n)
 }
 int cb_rng_download(cb_rng_t h, uint64_t first, uint64_t count, uint32_t* out6)
 {
+    CB_REQUIRE_INIT();
     RngPool* r = rngs().get(h);
     if (!r) return fail(CB_ERR_INVALID, "cb_rng_download: bad handle");
     if (first + count > r->n) return fail(CB_ERR_INVALID, "cb_rng_download: range exceeds pool");
@@ -415,13 +480,15 @@ int cb_rng_download(cb_rng_t h, uint64_t first, uint64_t count, uint32_t* out6)
 }
 int cb_rng_fill_uniform(cb_rng_t h, uint64_t n, float low, float high, float* d_out)
 {
+    CB_REQUIRE_INIT();
+    CB_SERIALISE();
     RngPool* r = rngs().get(h);
     if (!r) return fail(CB_ERR_INVALID, "cb_rng_fill_uniform: bad handle");
     if (n > r->n) return fail(CB_ERR_INVALID, "cb_rng_fill_uniform: n exceeds pool");
     if (!n) return CB_OK;
     rng_fill_uniform_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx().stream>>>(r->states, n, low, high, d_out);
     CB_CUDA(cudaGetLastError());
-    CB_CUDA(cudaStreamSynchronize(ctx().stream));
+    CB_CUDA(stream_wait(ctx().stream));
     return CB_OK;
 }
 

@@ -60,6 +60,18 @@ class GPUDaq(object):
         _lib.check(_lib.lib().cb_daq_end_acquire(self.handle))
         return GPUChannels(self.earliest_time_gpu, self.channel_q_gpu, self.channel_history_gpu, self.ndaq, self.stride)
 
+    def fold(self, other):
+        """Merge another GPUDaq's accumulators into this one on the device (MIN time, SUM charge, OR
+        history): per-event acquisitions into run-level accumulators."""
+        _lib.check(_lib.lib().cb_daq_fold(self.handle, other.handle))
+
+    def allreduce(self):
+        """Combine the accumulators of every rank (MIN time, SUM charge, OR history) with one
+        grouped NCCL all-reduce inside the library and convert to the float outputs; needs
+        parallel.init_comm() first, and is end_acquire() on a single rank.  Collective."""
+        _lib.check(_lib.lib().cb_daq_allreduce(self.handle))
+        return GPUChannels(self.earliest_time_gpu, self.channel_q_gpu, self.channel_history_gpu, self.ndaq, self.stride)
+
     def finalize_reduced(self):
         """int accumulators -> float outputs (after a cross-GPU reduction)."""
         _lib.check(_lib.lib().cb_daq_finalize(self.handle))

@@ -29,15 +29,31 @@ class _Context(object):
 
 
 class RNGStates(object):
-    """Pool of XORWOW states; state i == curand_init(seed, i, 0)
-    (get_rng_states, chroma/gpu/tools.py:136-145)."""
+    """Pool of XORWOW states; state i == curand_init(seed, first_stream + i, 0)
+    (get_rng_states, chroma/gpu/tools.py:136-145, where first_stream is always 0).
 
-    def __init__(self, size, seed=1, offset=0):
-        h = C.c_uint64()
-        _lib.check(_lib.lib().cb_rng_create(int(size), int(seed) & 0xFFFFFFFFFFFFFFFF, int(offset), C.byref(h)))
-        self.handle = h.value
+    ``first_stream`` is what makes multi-GPU runs independent of the partition: give every rank
+    the pool of ITS photons (first_stream = global index of its first photon) and hand each
+    event the window of its own photons with ``view()``; stream id == global photon index."""
+
+    def __init__(self, size, seed=1, offset=0, first_stream=0, _view_of=None, _handle=None):
         self.size = int(size)
         self.seed = seed
+        self.first_stream = int(first_stream)
+        self._parent = _view_of              # keeps the owning pool alive
+        if _handle is not None:
+            self.handle = _handle
+            return
+        h = C.c_uint64()
+        _lib.check(_lib.lib().cb_rng_create_streams(self.size, int(seed) & 0xFFFFFFFFFFFFFFFF, self.first_stream,
+                                                    int(offset), C.byref(h)))
+        self.handle = h.value
+
+    def view(self, first, count):
+        """Non-owning window [first, first + count) of this pool."""
+        h = C.c_uint64()
+        _lib.check(_lib.lib().cb_rng_view(self.handle, int(first), int(count), C.byref(h)))
+        return RNGStates(count, seed=self.seed, first_stream=self.first_stream + int(first), _view_of=self, _handle=h.value)
 
     def __len__(self):
         return self.size
@@ -58,9 +74,9 @@ class RNGStates(object):
         self.handle = 0
 
 
-def get_rng_states(size, seed=1):
+def get_rng_states(size, seed=1, first_stream=0):
     "Return `size` number of CUDA random number generator states."
-    return RNGStates(size, seed=seed)
+    return RNGStates(size, seed=seed, first_stream=first_stream)
 
 
 def to_float3(arr):

@@ -18,19 +18,19 @@ def rotate_extrude(x, y, nsteps=64):
     ang = np.linspace(0.0, 2.0 * np.pi, nsteps, endpoint=False)
     # vertex (ring j, profile point i) -> index j*npts + i
     vx = np.outer(np.cos(ang), x)
-    vz = np.outer(np.sin(ang), x)
+    vz = -np.outer(np.sin(ang), x)          # the reference turns the profile about -y (chroma/make.py rotate_extrude)
     vy = np.tile(y, (nsteps, 1))
     vertices = np.stack([vx, vy, vz], axis=-1).reshape(-1, 3)
-    j = np.arange(nsteps)
-    jn = (j + 1) % nsteps
-    i = np.arange(npts - 1)
-    J, I = np.meshgrid(j, i, indexing='ij')
-    JN = jn[J]
-    a = (J * npts + I).ravel()
-    b = (J * npts + I + 1).ravel()
-    c = (JN * npts + I + 1).ravel()
-    d = (JN * npts + I).ravel()
-    triangles = np.concatenate([np.stack([a, b, c], axis=1), np.stack([a, c, d], axis=1)])
+    # Quads between profile points i+1 -> i and angular steps j -> j+1, listed from the top of the
+    # profile down, all steps of a profile segment together; first the triangles (upper, lower,
+    # lower-next) of every quad, then (upper, lower-next, upper-next): the triangle ORDER of the
+    # reference's builder (chroma/make.py mesh_grid), so that triangle ids of a flattened detector
+    # are the reference's.
+    upper, step = np.meshgrid(np.arange(npts - 1, 0, -1), np.arange(nsteps), indexing='ij')
+    nxt = (step + 1) % nsteps
+    hi, lo = (step * npts + upper).ravel(), (step * npts + upper - 1).ravel()
+    hi_next, lo_next = (nxt * npts + upper).ravel(), (nxt * npts + upper - 1).ravel()
+    triangles = np.concatenate([np.stack([hi, lo, lo_next], axis=1), np.stack([hi, lo_next, hi_next], axis=1)])
     return Mesh(vertices, triangles, remove_duplicate_vertices=True)
 
 

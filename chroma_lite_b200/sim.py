@@ -31,7 +31,12 @@ def _peek(iterable):
 
 class Simulation(object):
     def __init__(self, detector, seed=None, cuda_device=None, photon_tracking=False,
-                 nthreads_per_block=512, max_blocks=1024):
+                 nthreads_per_block=512, max_blocks=1024, rng_first_stream=None, rng_size=None):
+        """Same arguments as chroma/sim.py:22-52, plus the multi-GPU extension: with
+        ``rng_first_stream`` (global index of this rank's first photon) the pool holds ``rng_size``
+        states, one per photon this Simulation will ever see, and consecutive batches take
+        consecutive windows of it: RNG stream == global photon index, results do not depend on how a
+        run is partitioned over ranks (parallel.EventPlan)."""
         self.detector = detector
         self.nthreads_per_block = nthreads_per_block
         self.max_blocks = max_blocks
@@ -46,7 +51,17 @@ class Simulation(object):
             self.gpu_geometry = gpu.GPUGeometry(detector)
         # nthreads_per_block*max_blocks is the RNG pool size, part of the replay
         # contract; it no longer dictates a launch shape
-        self.rng_states = gpu.get_rng_states(self.nthreads_per_block * self.max_blocks, seed=self.seed)
+        self.rng_per_photon = rng_first_stream is not None
+        if self.rng_per_photon:
+            self.rng_states = gpu.get_rng_states(int(rng_size), seed=self.seed, first_stream=int(rng_first_stream))
+            self.rng_cursor = 0               # photons that have taken their window so far
+        else:
+            self.rng_states = gpu.get_rng_states(self.nthreads_per_block * self.max_blocks, seed=self.seed)
+        # several ranks per host: pipeline threads wait blocking instead of spinning (parallel.py)
+        import os
+        from . import parallel, _lib
+        if not os.environ.get('CHROMA_B200_SYNC') and parallel.host_threads_should_block():
+            _lib.check(_lib.lib().cb_set_blocking_sync(1))
         self.last_timings = {}
 
     def _upload_batch(self, batch_events):
@@ -109,8 +124,15 @@ class Simulation(object):
         gpu_photons, bounds, upload_s = uploaded if uploaded is not None else self._upload_batch(batch_events)
         t1 = time.perf_counter()
         raw = {'bounds': bounds}
-        raw['tracking'] = gpu_photons.propagate(self.gpu_geometry, self.rng_states,
-                                                nthreads_per_block=self.nthreads_per_block, max_blocks=self.max_blocks,
+        rng, max_blocks = self.rng_states, self.max_blocks
+        if self.rng_per_photon:
+            # this batch's photons take the next window of the pool: one stream per photon, one chunk
+            n = int(bounds[-1])
+            rng = self.rng_states.view(self.rng_cursor, n)
+            self.rng_cursor += n
+            max_blocks = max(max_blocks, -(-n // self.nthreads_per_block))
+        raw['tracking'] = gpu_photons.propagate(self.gpu_geometry, rng,
+                                                nthreads_per_block=self.nthreads_per_block, max_blocks=max_blocks,
                                                 max_steps=max_steps, track=self.photon_tracking)
         t2 = time.perf_counter()
         is_detector = hasattr(self.detector, 'num_channels')
@@ -120,14 +142,21 @@ class Simulation(object):
             raw['hits'] = gpu_photons.get_flat_hits(self.gpu_geometry)
         t3 = time.perf_counter()
         if hasattr(self, 'gpu_daq') and run_daq:
-            # one acquisition per event (chroma/sim.py:141-152)
-            raw['channels'] = []
+            # one acquisition per event (chroma/sim.py:141-152).  run_daq='accumulate' (extension): the
+            # events add to ONE acquisition the caller opened with gpu_daq.begin_acquire() and closes with
+            # end_acquire() / allreduce() -- the run-level per-channel accumulators of a sharded run
+            accumulate = run_daq == 'accumulate'
+            if not accumulate:
+                raw['channels'] = []
             for start, end in zip(bounds[:-1], bounds[1:]):
-                self.gpu_daq.begin_acquire()
-                self.gpu_daq.acquire(gpu_photons, self.rng_states, start_photon=int(start),
+                ev_rng = rng.view(int(start), int(end - start)) if self.rng_per_photon and len(bounds) > 2 else rng
+                if not accumulate:
+                    self.gpu_daq.begin_acquire()
+                self.gpu_daq.acquire(gpu_photons, ev_rng, start_photon=int(start),
                                      nphotons=int(end - start), nthreads_per_block=self.nthreads_per_block,
-                                     max_blocks=self.max_blocks)
-                raw['channels'].append(self.gpu_daq.end_acquire().get())
+                                     max_blocks=max_blocks)
+                if not accumulate:
+                    raw['channels'].append(self.gpu_daq.end_acquire().get())
         t4 = time.perf_counter()
         self.last_timings = {'upload_s': upload_s, 'propagate_s': t2 - t1, 'readback_s': t3 - t2, 'daq_s': t4 - t3,
                              'nphotons': int(bounds[-1]), 'batch_total_s': t4 - t0}

@@ -27,14 +27,15 @@
 extern "C" {
 #endif
 
-#define CB_ABI_VERSION 2
+#define CB_ABI_VERSION 3
 
 typedef enum {
     CB_OK = 0,
     CB_ERR_CUDA = -1,
     CB_ERR_INVALID = -2,
     CB_ERR_NOMEM = -3,
-    CB_ERR_UNSUPPORTED = -4
+    CB_ERR_UNSUPPORTED = -4,
+    CB_ERR_NCCL = -5
 } CbStatus;
 
 typedef uint64_t cb_geom_t;
@@ -158,6 +159,15 @@ typedef struct {
     float    kernel_ms;      /* device time of those kernels (CUDA events) */
     float    intersect0_ms;  /* device time of the first step's traversal kernel (0 if not launched) */
     uint64_t intersect0_rays;/* rays that kernel traced */
+    /* device time per kernel class (CUDA events around every launch on the library stream) and
+     * the work each class did, for the per-kernel rooflines of bench.py */
+    float    intersect_ms;   /* all wavefront traversal launches */
+    float    physics_ms;     /* all wavefront physics launches */
+    float    tail_ms;        /* persistent tail launches */
+    uint64_t intersect_rays; /* rays traced by the wavefront traversal launches */
+    uint64_t physics_steps;  /* photon steps taken by the wavefront physics launches */
+    uint64_t tail_photons;   /* photons handed to the tail */
+    uint64_t tail_steps;     /* photon steps taken by the tail */
 } CbPropagateStats;
 
 #if defined(__GNUC__)
@@ -241,6 +251,14 @@ int cb_native_tree_build_split(const uint32_t* ref_nodes, uint64_t nnodes, uint6
 int cb_rng_create(uint64_t n, uint64_t seed, uint64_t offset, cb_rng_t* out);
 int cb_rng_destroy(cb_rng_t r);
 int cb_rng_size(cb_rng_t r, uint64_t* n);
+/* Same with a stream base: state i == curand_init(seed, first_stream + i, offset).  With
+ * first_stream = the global index of a rank's first photon, stream id == global photon index,
+ * and results do not depend on how the photons are partitioned over GPUs.  The
+ * reference has one device and always starts at stream 0 (chroma/cuda/random.h:60-70). */
+int cb_rng_create_streams(uint64_t n, uint64_t seed, uint64_t first_stream, uint64_t offset, cb_rng_t* out);
+/* Non-owning window [first, first+count) of a pool, usable wherever a pool is (propagate,
+ * acquire): one event's slice of a run-level pool.  Destroy it before its parent. */
+int cb_rng_view(cb_rng_t parent, uint64_t first, uint64_t count, cb_rng_t* out);
 /* test hooks: state words {d, v0..v4} and fill_uniform (chroma/cuda/random.h:72-82) */
 int cb_rng_download(cb_rng_t r, uint64_t first, uint64_t count, uint32_t* out6);
 int cb_rng_fill_uniform(cb_rng_t r, uint64_t n, float low, float high, float* d_out);
@@ -290,6 +308,37 @@ int cb_daq_pointers(cb_daq_t d, void** t, void** q, void** flags,
                     void** time_int, void** q_int, uint64_t* count);
 /* finalise from integer accumulators only (after a cross-GPU reduction) */
 int cb_daq_finalize(cb_daq_t d);
+/* dst <- dst (+) src on the device, channel by channel: MIN of the time words, SUM of the integer
+ * charges, OR of the histories -- what the atomics of run_daq would have produced had src's photons been
+ * acquired into dst (chroma/cuda/daq.cu:73-75).  Folds per-event acquisitions into run-level accumulators. */
+int cb_daq_fold(cb_daq_t dst, cb_daq_t src);
+
+/* ---- multi-GPU: one process per GPU, photon banks partitioned, geometry replicated ------
+ * The reference has no multi-GPU path; what it does with atomics on the per-channel arrays of
+ * ONE device (atomicMin / atomicAdd / atomicOr, chroma/cuda/daq.cu:73-75, 143-145) becomes one
+ * reduction over NVLink once photons are sharded.
+ *   cb_comm_unique_id : rank 0 creates the 128-byte NCCL id; the caller carries it to the other
+ *                       ranks (any side channel: torch.distributed, MPI, a file)
+ *   cb_comm_init      : every rank joins (collective)
+ *   cb_daq_allreduce  : earliest_time_int -> MIN, channel_q_int -> SUM (uint32 wrap-around like
+ *                       atomicAdd), channel_history -> OR (NCCL has no OR: the bits of the history
+ *                       word travel as per-bit counters packed into the SUM buffer), ONE grouped pair
+ *                       of ncclAllReduce on the library stream, the float conversion of
+ *                       cb_daq_finalize fused behind it; no host copy.  Result on every rank.
+ * NCCL is loaded at cb_comm_init time (libnccl.so.2); single-GPU use does not need it. */
+#define CB_COMM_ID_BYTES 128
+int cb_comm_unique_id(void* id_out);
+int cb_comm_init(int32_t nranks, int32_t rank, const void* id);
+int cb_comm_destroy(void);
+int cb_comm_size(int32_t* nranks, int32_t* rank);     /* 1, 0 without a communicator */
+int cb_daq_allreduce(cb_daq_t d);
+/* test hook: the same pack / SUM / MIN / unpack + finalise for n accumulators on ONE device standing in
+ * for n ranks; result in daqs[0] */
+int cb_daq_reduce_local(const cb_daq_t* daqs, int32_t n);
+/* host waits (stream / event synchronisation inside the entry points): 0 = spin (lowest latency,
+ * one busy core per waiting thread), 1 = block (yield the core; for many ranks per host).
+ * Default: CHROMA_B200_SYNC=spin|block, else spin. */
+int cb_set_blocking_sync(int32_t on);
 
 /* ---- host-side mesh preparation (no GPU needed) --------------------------
  * Vertex de-duplication of Geometry.flatten / Mesh.remove_duplicate_vertices

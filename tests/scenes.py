@@ -137,3 +137,26 @@ def wireplane_scene(size=400.0):
 
 def desc_of(geo):
     return make_desc(geo)
+
+
+def ref_tiny_detector():
+    """The reference's demo detector in miniature, built from the reference's own PMT model and
+    optics tables (tests/golden/ref_detector_parts.npz, chroma_lite_b200/demo/refparts.py)."""
+    from chroma_lite_b200.demo import refparts
+    return with_bvh(refparts.tiny())
+
+
+def many_tables_scene(nsteps=16, nangles=14):
+    """More wavelength tables than fit the 48 KB staged into shared memory (the cut must
+    fall on a table boundary): the scintillator scene's media plus a dichroic filter with `nangles`
+    angles (2 x nangles x 188 floats) placed so that it is hit often."""
+    geo = scintillator_scene(nsteps)
+    wl = standard_wavelengths.astype(np.float64)
+    angles = np.linspace(0.0, np.pi / 2, nangles)
+    refl = [np.column_stack([wl, np.clip((wl - 330.0 - 15.0 * a) / 160.0, 0.05, 0.9)]) for a in range(nangles)]
+    tran = [np.column_stack([wl, np.clip(0.97 - r[:, 1], 0, 1)]) for r in refl]
+    for s in geo.solids:
+        for x in s.unique_surfaces:
+            if x is not None and x.name == 'dichroic':
+                x.dichroic_props = DichroicProps(angles, refl, tran)
+    return geo

@@ -216,3 +216,24 @@ def test_wire_planes_vs_reference(gpu_ready, max_steps):
     if max_steps > 1:
         assert (mine.flags & (event.SURFACE_ABSORB | event.REFLECT_SPECULAR | event.REFLECT_DIFFUSE)).astype(bool).mean() > 0.05
     print('identical fraction', frac)
+
+
+def test_table_pool_larger_than_the_shared_memory_stage(gpu_ready):
+    """with more wavelength tables than the 48 KB staged into shared memory the cut must
+    fall on a table boundary (a table straddling it was read past the staged bytes).  A dichroic
+    filter with 14 angles pushes the pool past the cut; checked against the CPU oracle."""
+    from oracle import orc
+    geo = scenes.many_tables_scene(16, nangles=14)
+    desc, keep = scenes.desc_of(geo)
+    assert desc.table_floats > 12288 + 20000          # wavelength tables alone exceed the stage
+    ph = scenes.point_source(40000, seed=21, wl_range=(250.0, 450.0))
+    g = gpu.GPUDetector(geo)
+    rng = gpu.get_rng_states(len(ph), seed=9)
+    gp = gpu.GPUPhotons(ph)
+    gp.propagate(g, rng, nthreads_per_block=256, max_blocks=(len(ph) + 255) // 256, max_steps=30)
+    mine = gp.get()
+    bank, cnt = orc.propagate(desc, ph, orc.rng_init(9, 0, len(ph)), max_steps=30)
+    same = (mine.flags == bank.flags) & (mine.last_hit_triangles == bank.last_hit_triangles)
+    assert same.mean() > 0.97, same.mean()             # fast-math intrinsics vs libm: tolerance-level oracle
+    assert ((mine.flags & event.SURFACE_TRANSMIT) != 0).mean() > 0.05      # the dichroic tables are in use
+    assert abs(((mine.flags & event.SURFACE_TRANSMIT) != 0).mean() - ((bank.flags & event.SURFACE_TRANSMIT) != 0).mean()) < 3e-3

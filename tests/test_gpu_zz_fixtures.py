@@ -53,8 +53,9 @@ def test_engine_replays_reference_kernel_fixture(gpu_ready, name):
 
 
 def test_tree_options_against_the_default_tree(gpu_ready, monkeypatch):
-    """CHROMA_B200_TREE=single (one hierarchy over all leaves) changes the traversal tree only: nearest hits
-    (triangle and distance, ties included) and whole propagations are bit-identical to the default tree.
+    """CHROMA_B200_TREE=solids (solids first, then one subtree per solid: round 1's default) changes the traversal
+    tree only: nearest hits (triangle and distance, ties included) and whole propagations are bit-identical to the
+    default single-level tree.
     CHROMA_B200_LEAF_SPLIT (several tighter leaves per loosely bounded triangle) is NOT exact: the reference's
     float32 triangle test can report a hit several mm away from the triangle for a ray that grazes a sliver, the
     reference finds it because the ray is inside the sliver's big leaf box, a split tree does not look there
@@ -76,7 +77,7 @@ def test_tree_options_against_the_default_tree(gpu_ready, monkeypatch):
     d = np.concatenate([d, aim - o[n:]]).astype(np.float32)
     ph = scenes.point_source(60000, seed=6, wl_range=(300, 600))
     results = []
-    variants = ((None, None), (None, 'single'), ('4,8,8', None), ('16,4,1.5', None), ('8,8,2', 'single'))
+    variants = ((None, None), (None, 'solids'), ('4,8,8', None), ('16,4,1.5', None), ('8,8,2', 'solids'))
     for spec, tree in variants:
         for key, val in (('CHROMA_B200_LEAF_SPLIT', spec), ('CHROMA_B200_TREE', tree)):
             if val is None:

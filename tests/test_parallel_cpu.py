@@ -24,9 +24,36 @@ def test_shard_range_partitions_exactly():
 def test_sum_buffer_roundtrip():
     rng = np.random.default_rng(0)
     q = rng.integers(0, 2 ** 31, 100).astype(np.uint32)
-    h = rng.integers(0, 2 ** 16, 100).astype(np.uint32)
-    q2, h2 = parallel.unpack_sum_buffer(parallel.pack_sum_buffer(q, h), 100)
-    assert np.array_equal(q, q2) and np.array_equal(h, h2)
+    h = rng.integers(0, 2 ** 32, 100).astype(np.uint32)
+    for world in (2, 8, 15, 16, 255, 256):
+        q2, h2 = parallel.unpack_sum_buffer(parallel.pack_sum_buffer(q, h, world), 100, world)
+        assert np.array_equal(q, q2) and np.array_equal(h, h2)
+
+
+def test_or_through_sum_for_every_world_size():
+    """Summing the packed per-bit counters of `world` ranks and unpacking gives the OR of their
+    history words, also when every rank sets every bit (the counters must not spill over)."""
+    rng = np.random.default_rng(1)
+    for world in (2, 3, 8, 15, 16, 40):
+        hs = [rng.integers(0, 2 ** 32, 50).astype(np.uint32) for _ in range(world)]
+        hs[0][:5] = 0xFFFFFFFF
+        for h in hs[1:]:
+            h[:3] = 0xFFFFFFFF                      # all ranks set all bits of channels 0..2
+        total = sum(parallel.pack_history(h, world).astype(np.uint64) for h in hs)
+        assert total.max() < 2 ** 32               # what travels is uint32
+        assert np.array_equal(parallel.unpack_history(total, world), np.bitwise_or.reduce(hs, axis=0))
+
+
+def test_event_plan_streams_do_not_depend_on_the_partition():
+    nev, n = 40, 2500000
+    for world in (1, 2, 4, 8, 3):
+        plans = [parallel.EventPlan(nev, n, r, world) for r in range(world)]
+        assert sum(len(p.events) for p in plans) == nev and sum(p.nphotons for p in plans) == nev * n
+        for p in plans:
+            for e in p.events:
+                first, count = p.window(e)
+                assert count == n and p.first_stream + first == e * n      # stream of photon 0 of event e
+    assert parallel.host_threads_should_block(8, 32) and not parallel.host_threads_should_block(1, 16)
 
 
 WORKER = r'''
@@ -38,13 +65,13 @@ dist.init_process_group('gloo', init_method='tcp://127.0.0.1:%%s' %% os.environ[
 rank, world = dist.get_rank(), dist.get_world_size()
 C = 257
 rng = np.random.default_rng(100 + rank)
-t = rng.integers(1, 2**31 - 1, C); q = rng.integers(0, 2**20, C); h = rng.integers(0, 2**16, C)
+t = rng.integers(1, 2**31 - 1, C); q = rng.integers(0, 2**20, C); h = rng.integers(0, 2**32, C)
 rt, rq, rh = parallel.reduce_channels(torch.from_numpy(t), torch.from_numpy(q), torch.from_numpy(h))
 # expected from all ranks' seeds
 ts, qs, hs = [], [], []
 for r in range(world):
     g = np.random.default_rng(100 + r)
-    ts.append(g.integers(1, 2**31 - 1, C)); qs.append(g.integers(0, 2**20, C)); hs.append(g.integers(0, 2**16, C))
+    ts.append(g.integers(1, 2**31 - 1, C)); qs.append(g.integers(0, 2**20, C)); hs.append(g.integers(0, 2**32, C))
 assert np.array_equal(rt.numpy(), np.min(ts, axis=0))
 assert np.array_equal(rq.numpy(), np.sum(qs, axis=0))
 assert np.array_equal(rh.numpy(), np.bitwise_or.reduce(hs, axis=0))
