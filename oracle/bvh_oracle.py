@@ -20,10 +20,16 @@ def count_unique_in_sorted(a):
     return int((np.ediff1d(a) > 0).sum()) + 1
 
 
-def make_recursive_grid_bvh(vertices, triangles, target_degree=3, leaves=None):
+def make_recursive_grid_bvh(vertices, triangles, target_degree=3, leaves=None, parents=None, concatenate=None,
+                            collapse=None):
     """Returns (world_origin f32[3], world_scale f32, nodes uint32 (N,4), layer_offsets).
-    `leaves` = callable(v, t, origin, scale) -> (leaf_nodes, morton) replaces the C
-    restatement of make_leaves (used to plug in the reference's own kernel)."""
+    The four device kernels of the reference's builder can each be plugged in (the GPU test tier passes
+    the reference's own kernels from oracle/_ref/bvh.cubin through oracle/ref_driver.py); without a hook
+    the C restatement in chroma_oracle.c does the step:
+      leaves(v, t, origin, scale) -> (leaf_nodes, morton)        make_leaves            bvh.cu:148
+      parents(top, first_child, nchild) -> parent nodes          make_parents_detailed  bvh.cu:269
+      concatenate(layers) -> (nodes, bounds)                     copy_and_offset        bvh.cu:364
+      collapse(nodes, bounds) -> nodes                           collapse_child         bvh.cu:530"""
     lib = orc.lib()
     v = np.ascontiguousarray(vertices, dtype=np.float32)
     t = np.ascontiguousarray(triangles, dtype=np.uint32)
@@ -62,20 +68,30 @@ def make_recursive_grid_bvh(vertices, triangles, target_degree=3, leaves=None):
             parent_codes = np.concatenate(pc).astype(np.uint64)
             nchild = np.ediff1d(first_child, to_end=nnodes - first_child[-1]).astype(np.uint32)
         assert (nchild > 0).all() and (nchild <= MAX_CHILD).all()
-        parents = np.zeros((len(first_child), 4), dtype=np.uint32)
-        lib.orc_make_parents(top.ctypes.data_as(C.c_void_p), first_child.ctypes.data_as(C.c_void_p),
-                             nchild.ctypes.data_as(C.c_void_p), C.c_uint64(len(first_child)),
-                             parents.ctypes.data_as(C.c_void_p))
-        layers = [parents] + layers
+        if parents is None:
+            layer = np.zeros((len(first_child), 4), dtype=np.uint32)
+            lib.orc_make_parents(top.ctypes.data_as(C.c_void_p), first_child.ctypes.data_as(C.c_void_p),
+                                 nchild.ctypes.data_as(C.c_void_p), C.c_uint64(len(first_child)),
+                                 layer.ctypes.data_as(C.c_void_p))
+        else:
+            layer = np.ascontiguousarray(parents(top, first_child, nchild), dtype=np.uint32)
+        layers = [layer] + layers
         codes = parent_codes
-    bounds = np.insert(np.cumsum([len(l) for l in layers]), 0, 0)
-    nodes = np.concatenate(layers).astype(np.uint32)
-    for s, e in zip(bounds[:-2], bounds[1:-1]):           # every layer but the leaves
-        w = nodes[s:e, 3]
-        nodes[s:e, 3] = (w & np.uint32(0xF0000000)) | ((w & np.uint32(0x0FFFFFFF)) + np.uint32(e))
-    nodes = np.ascontiguousarray(nodes)
-    for s, e in reversed(list(zip(bounds[:-2], bounds[1:-1]))):
-        lib.orc_collapse_child(nodes.ctypes.data_as(C.c_void_p), C.c_uint64(s), C.c_uint64(e))
+    if concatenate is None:
+        bounds = np.insert(np.cumsum([len(l) for l in layers]), 0, 0)
+        nodes = np.concatenate(layers).astype(np.uint32)
+        for s, e in zip(bounds[:-2], bounds[1:-1]):           # every layer but the leaves
+            w = nodes[s:e, 3]
+            nodes[s:e, 3] = (w & np.uint32(0xF0000000)) | ((w & np.uint32(0x0FFFFFFF)) + np.uint32(e))
+        nodes = np.ascontiguousarray(nodes)
+    else:
+        nodes, bounds = concatenate(layers)
+        nodes = np.ascontiguousarray(nodes, dtype=np.uint32)
+    if collapse is None:
+        for s, e in reversed(list(zip(bounds[:-2], bounds[1:-1]))):
+            lib.orc_collapse_child(nodes.ctypes.data_as(C.c_void_p), C.c_uint64(s), C.c_uint64(e))
+    else:
+        nodes = np.ascontiguousarray(collapse(nodes, bounds), dtype=np.uint32)
     return world_origin, world_scale, nodes, bounds[:-1]
 
 

@@ -495,6 +495,51 @@ def make_leaves(vertices, triangles, world_origin, world_scale):
     return from_dev(nodes), from_dev(codes)
 
 
+def merge_nodes_detailed(nodes, first_child, nchild):
+    """The reference's make_parents_detailed kernel launched as merge_nodes_detailed does
+    (chroma/cuda/bvh.cu:269-308, chroma/gpu/bvh.py:84-112): one parent per (first_child, nchild)."""
+    child = to_dev(np.ascontiguousarray(nodes, dtype=np.uint32))
+    fc = to_dev(np.asarray(first_child).astype(np.int32))
+    nc = to_dev(np.asarray(nchild).astype(np.int32))
+    nparent = len(first_child)
+    parents = to_dev(np.zeros((nparent, 4), dtype=np.uint32))
+    mod = module('bvh.cubin')
+    for first, cnt, blocks in chunk_iterator(nparent, 256, 10000):
+        mod.launch('make_parents_detailed', blocks, 256, C.c_uint(first), C.c_uint(cnt), child, parents, fc, nc)
+    sync()
+    return from_dev(parents)
+
+
+def concatenate_layers(layers):
+    """The reference's copy_and_offset kernel launched as concatenate_layers does
+    (chroma/cuda/bvh.cu:364-384, chroma/gpu/bvh.py:239-267): layers root first into one node array,
+    child ids of every layer but the leaves shifted by the end of that layer."""
+    bounds = np.insert(np.cumsum([len(l) for l in layers]), 0, 0)
+    nodes = to_dev(np.zeros((int(bounds[-1]), 4), dtype=np.uint32))
+    mod = module('bvh.cubin')
+    for start, end, layer in zip(bounds[:-1], bounds[1:], layers):
+        offset = 0 if end == bounds[-1] else int(end)
+        src = to_dev(np.ascontiguousarray(layer, dtype=np.uint32))
+        for first, cnt, blocks in chunk_iterator(int(end - start), 256, 10000):
+            mod.launch('copy_and_offset', blocks, 256, C.c_uint(first), C.c_uint(cnt), C.c_uint(offset), src,
+                       nodes.ptr + 16 * int(start))
+    sync()
+    return from_dev(nodes), bounds
+
+
+def collapse_chains(nodes, layer_bounds):
+    """The reference's collapse_child kernel launched as collapse_chains does
+    (chroma/cuda/bvh.cu:530-543, chroma/gpu/bvh.py:114-130): layers bottom up, leaves excluded."""
+    dev = to_dev(np.ascontiguousarray(nodes, dtype=np.uint32))
+    mod = module('bvh.cubin')
+    bounds = list(zip(layer_bounds[:-1], layer_bounds[1:]))[:-1]
+    bounds.reverse()
+    for start, end in bounds:
+        mod.launch('collapse_child', 120, 256, C.c_uint(int(start)), C.c_uint(int(end)), dev)
+    sync()
+    return from_dev(dev)
+
+
 # ---------------------------------------------------------------- PDF accumulators
 class RefKernelPDF(object):
     """GPUKernelPDF's device side (gpu/pdf.py:44-61, 140-160) on the reference's pdf.cu kernels:

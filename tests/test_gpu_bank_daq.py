@@ -176,12 +176,20 @@ def test_daq_time_and_charge_response(gpu_ready):
 
 
 def test_bvh_build_matches_reference_kernels(gpu_ready):
-    # leaves + Morton codes from the reference's own make_leaves kernel, host grouping
-    # restated from bvh/grid.py: the engine's builder must give the identical tree
-    for geo in (scenes.sphere_scene(16), scenes.tiny_detector(), scenes.scintillator_scene(12)):
+    # The reference's builder with ALL FOUR of its device kernels run from oracle/_ref/bvh.cubin
+    # (make_leaves, make_parents_detailed, copy_and_offset, collapse_child: chroma/cuda/bvh.cu:148, 269,
+    # 364, 530, launched as chroma/gpu/bvh.py:18-130, 239-267 does) and the host grouping of
+    # chroma/bvh/grid.py:11-95 restated in NumPy: the engine's builder must give the identical tree,
+    # node for node.
+    for geo in (scenes.sphere_scene(16), scenes.tiny_detector(), scenes.scintillator_scene(12), scenes.ref_tiny_detector()):
         bvh = make_recursive_grid_bvh(geo.mesh)
-        o, s, nodes, offs = bvh_oracle.make_recursive_grid_bvh(geo.mesh.vertices, geo.mesh.triangles,
-                                                               leaves=ref_driver.make_leaves)
+        o, s, nodes, offs = bvh_oracle.make_recursive_grid_bvh(
+            geo.mesh.vertices, geo.mesh.triangles, leaves=ref_driver.make_leaves, parents=ref_driver.merge_nodes_detailed,
+            concatenate=ref_driver.concatenate_layers, collapse=ref_driver.collapse_chains)
+        # the C restatement of the three small kernels agrees with the reference's kernels too
+        o1, s1, nodes1, offs1 = bvh_oracle.make_recursive_grid_bvh(geo.mesh.vertices, geo.mesh.triangles,
+                                                                   leaves=ref_driver.make_leaves)
+        assert np.array_equal(nodes1, nodes) and list(offs1) == list(offs)
         assert np.array_equal(bvh.world_coords.world_origin, o) and bvh.world_coords.world_scale == s
         mine = bvh.nodes.view(np.uint32).reshape(-1, 4)
         assert list(bvh.layer_offsets) == list(offs)
