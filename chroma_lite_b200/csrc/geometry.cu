@@ -1,7 +1,7 @@
 // geometry.cu -- geometry / detector upload into the engine's native layout and
 // the recursive-grid BVH builder in the reference node format.
 #include "host.h"
-#include <cub/device/device_radix_sort.cuh>
+#include "sort.cuh"
 #include <algorithm>
 #include <string.h>
 #include <math.h>
@@ -650,30 +650,32 @@ extern "C" int cb_bvh_build(const float* vertices, uint64_t nvertices, const uin
     float scale = (float)((double)extent / 65534.0);
 
     Context& c = ctx();
-    float* d_v = nullptr; uint32_t* d_t = nullptr; uint4* d_leaves = nullptr; uint4* d_sorted = nullptr;
+    float* d_v = nullptr; uint32_t* d_t = nullptr; uint4* d_leaves = nullptr;
     unsigned long long *d_codes = nullptr, *d_codes2 = nullptr; uint32_t *d_ids = nullptr, *d_ids2 = nullptr;
-    void* d_tmp = nullptr; size_t tmp_bytes = 0;
+    uint32_t* d_scratch = nullptr;
     auto cleanup = [&]() {
-        cudaFree(d_v); cudaFree(d_t); cudaFree(d_leaves); cudaFree(d_sorted); cudaFree(d_codes);
-        cudaFree(d_codes2); cudaFree(d_ids); cudaFree(d_ids2); cudaFree(d_tmp);
+        cudaFree(d_v); cudaFree(d_t); cudaFree(d_leaves); cudaFree(d_codes);
+        cudaFree(d_codes2); cudaFree(d_ids); cudaFree(d_ids2); cudaFree(d_scratch);
     };
 #define BV(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { cleanup(); return cuda_fail(_e, #call); } } while (0)
     BV(cudaMalloc(&d_v, nvertices * 12)); BV(cudaMalloc(&d_t, ntriangles * 12));
     BV(cudaMalloc(&d_leaves, ntriangles * 16)); BV(cudaMalloc(&d_codes, ntriangles * 8));
     BV(cudaMalloc(&d_codes2, ntriangles * 8)); BV(cudaMalloc(&d_ids, ntriangles * 4)); BV(cudaMalloc(&d_ids2, ntriangles * 4));
+    BV(cudaMalloc(&d_scratch, radix_sort_scratch_words(ntriangles) * 4));
     BV(cudaMemcpyAsync(d_v, vertices, nvertices * 12, cudaMemcpyHostToDevice, c.stream));
     BV(cudaMemcpyAsync(d_t, triangles, ntriangles * 12, cudaMemcpyHostToDevice, c.stream));
     make_leaves_kernel<<<(unsigned)((ntriangles + 255) / 256), 256, 0, c.stream>>>(
         d_v, d_t, ntriangles, make_float3(lo[0], lo[1], lo[2]), scale, d_leaves, d_codes, d_ids);
     BV(cudaGetLastError());
-    // stable LSD radix sort of (morton, triangle id): ties keep ascending triangle order
-    BV(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_codes, d_codes2, d_ids, d_ids2, (int)ntriangles, 0, 48, c.stream));
-    BV(cudaMalloc(&d_tmp, tmp_bytes));
-    BV(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_codes, d_codes2, d_ids, d_ids2, (int)ntriangles, 0, 48, c.stream));
+    // stable LSD radix sort of (morton, triangle id), 6 passes of 8 bits (sort.cuh): ties keep ascending triangle order
+    const bool in_alt = radix_sort_pairs<unsigned long long>(d_codes, d_codes2, d_ids, d_ids2, ntriangles, 48, d_scratch, c.stream);
+    BV(cudaGetLastError());
+    const unsigned long long* sorted_codes = in_alt ? d_codes2 : d_codes;
+    const uint32_t* sorted_ids = in_alt ? d_ids2 : d_ids;
     std::vector<uint64_t> codes(ntriangles);
     std::vector<uint32_t> ids(ntriangles), leaves(ntriangles * 4), sorted(ntriangles * 4);
-    BV(cudaMemcpyAsync(codes.data(), d_codes2, ntriangles * 8, cudaMemcpyDeviceToHost, c.stream));
-    BV(cudaMemcpyAsync(ids.data(), d_ids2, ntriangles * 4, cudaMemcpyDeviceToHost, c.stream));
+    BV(cudaMemcpyAsync(codes.data(), sorted_codes, ntriangles * 8, cudaMemcpyDeviceToHost, c.stream));
+    BV(cudaMemcpyAsync(ids.data(), sorted_ids, ntriangles * 4, cudaMemcpyDeviceToHost, c.stream));
     BV(cudaMemcpyAsync(leaves.data(), d_leaves, ntriangles * 16, cudaMemcpyDeviceToHost, c.stream));
     BV(stream_wait(c.stream));
 #undef BV

@@ -1,7 +1,7 @@
 // kernels.cu -- the hot path: ray intersection, photon propagation, photon-bank
 // utilities and the DAQ, plus their C-ABI entry points.
 #include "host.h"
-#include <cub/device/device_radix_sort.cuh>
+#include "sort.cuh"
 #include <algorithm>
 #include <string.h>
 #include <stdlib.h>
@@ -987,9 +987,7 @@ int cb_propagate(const CbPhotonBank* bank, cb_geom_t gh, cb_rng_t rh, int32_t nt
         c.d_keys[0] = c.d_keys[1] = c.d_sorted = nullptr; c.d_sort_tmp = nullptr;
         CB_CUDA(cudaMalloc(&c.d_keys[0], cap * 4)); CB_CUDA(cudaMalloc(&c.d_keys[1], cap * 4));
         CB_CUDA(cudaMalloc(&c.d_sorted, cap * 4));
-        c.sort_tmp_bytes = 0;
-        CB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, c.sort_tmp_bytes, c.d_keys[0], c.d_keys[1], c.d_queue[0],
-                                                c.d_sorted, (int)cap, 0, 30, c.stream));
+        c.sort_tmp_bytes = radix_sort_scratch_words(cap) * 4;
         CB_CUDA(cudaMalloc(&c.d_sort_tmp, c.sort_tmp_bytes));
         c.scratch_cap = cap;
     }
@@ -1069,10 +1067,14 @@ int cb_propagate(const CbPhotonBank* bank, cb_geom_t gh, cb_rng_t rh, int32_t nt
                         // (the intersect kernel alone walks the sorted order; the physics keeps the queue's)
                         uint32_t* unsorted_vals = c.d_queue[step & 1];     // free until the physics kernel writes it
                         ray_key_kernel<<<(unsigned)((n_alive + 255) / 256), 256, 0, c.stream>>>(g->dev, P, c.d_keys[0], unsorted_vals);
-                        size_t tmp = c.sort_tmp_bytes;
-                        CB_CUDA(cub::DeviceRadixSort::SortPairs(c.d_sort_tmp, tmp, c.d_keys[0], c.d_keys[1], unsorted_vals,
-                                                                c.d_sorted, (int)n_alive, 0, 30, c.stream));
-                        launches += 2;
+                        // 30-bit keys: four 8-bit passes, the result is back in (d_keys[0], unsorted_vals)
+                        int sort_launches = 0;
+                        const bool in_alt = radix_sort_pairs<uint32_t>(c.d_keys[0], c.d_keys[1], unsorted_vals, c.d_sorted, n_alive, 32,
+                                                                       (uint32_t*)c.d_sort_tmp, c.stream, &sort_launches);
+                        if (!in_alt)
+                            CB_CUDA(cudaMemcpyAsync(c.d_sorted, unsorted_vals, n_alive * 4, cudaMemcpyDeviceToDevice, c.stream));
+                        CB_CUDA(cudaGetLastError());
+                        launches += 1 + sort_launches;
                     }
                     const unsigned iblocks = (unsigned)std::min<uint64_t>((n_alive + INT_THREADS - 1) / INT_THREADS,
                                                                           (uint64_t)c.sm_count * int_per_sm);

@@ -22,7 +22,7 @@ constexpr int SCAN_ITEMS = 16;                       // per thread
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 
 // ---- exclusive scan of uint32: tile sums -> scan of the sums -> rescan of each tile with its offset
-__global__ void __launch_bounds__(SCAN_THREADS)
+static __global__ void __launch_bounds__(SCAN_THREADS)
 scan_tile_sums_kernel(const uint32_t* __restrict__ in, uint64_t n, uint32_t* __restrict__ sums)
 {
     __shared__ uint32_t warp_sum[SCAN_THREADS / 32];
@@ -43,7 +43,7 @@ scan_tile_sums_kernel(const uint32_t* __restrict__ in, uint64_t n, uint32_t* __r
 }
 
 // one CTA: exclusive scan of `n` values in place, total -> data[n]
-__global__ void __launch_bounds__(1024)
+static __global__ void __launch_bounds__(1024)
 scan_single_cta_kernel(uint32_t* data, uint32_t n)
 {
     __shared__ uint32_t warp_sums[32];
@@ -80,7 +80,7 @@ scan_single_cta_kernel(uint32_t* data, uint32_t n)
 }
 
 // each tile rescanned in index order: item i of the tile sits at k * SCAN_THREADS + thread
-__global__ void __launch_bounds__(SCAN_THREADS)
+static __global__ void __launch_bounds__(SCAN_THREADS)
 scan_apply_kernel(const uint32_t* __restrict__ in, uint64_t n, const uint32_t* __restrict__ tile_offsets,
                   uint32_t* __restrict__ out)
 {
