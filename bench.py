@@ -359,6 +359,9 @@ def run_ours(args):
     if world > 1:
         parallel.init_comm()              # the library's own NCCL communicator (cb_comm_init)
     timings = {}
+    # the library keeps what it derives from the tree (rank, leaf boxes, its own traversal tree) next to the
+    # detector cache: the first rank of a node builds it, the others read it (CHROMA_B200_TREE_CACHE)
+    os.environ.setdefault('CHROMA_B200_TREE_CACHE', cache_dir())
     # one rank builds the box-local cache, the others wait and load it
     if local == 0:
         det = build_detector(args.workload, timings)

@@ -6,6 +6,11 @@
 #include <string.h>
 #include <math.h>
 #include <thread>
+#include <chrono>
+#include <string>
+#include <fcntl.h>
+#include <unistd.h>
+#include <sys/stat.h>
 
 namespace cb {
 
@@ -99,6 +104,69 @@ static void collect_reference_leaves(const uint32_t* nodes, uint64_t nnodes, uin
     }
 }
 
+// ---------------------------------------------------------------- prepared-tree cache
+// What cb_geometry_create derives from the reference-format tree on the host -- the reference test rank
+// and leaf box of every triangle and the engine's own traversal tree -- costs 5-8 s for the 29k-PMT
+// detector, and with one process per GPU every rank of a node would derive the same thing at the same
+// time with all host threads.  With CHROMA_B200_TREE_CACHE=<dir> the result is kept in a file keyed by a
+// hash of the inputs; the first process to ask builds and writes it (create-exclusive lock file), the
+// others wait for the file and read it (role of chroma/cache.py:209-236 for BVHs, one level further).
+struct PreparedTree {
+    std::vector<uint32_t> rank;       // [ntriangles]
+    std::vector<uint32_t> leafbox;    // [3 * ntriangles]
+    std::vector<Entry> native;        // engine tree (empty: traverse the reference tree)
+};
+
+static uint64_t mix64(uint64_t h, uint64_t v)
+{
+    h ^= v + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+    h *= 0xFF51AFD7ED558CCDull;
+    return h ^ (h >> 32);
+}
+static uint64_t hash_words(uint64_t h, const void* p, uint64_t bytes)
+{
+    const uint64_t* w = static_cast<const uint64_t*>(p);
+    const uint64_t n = bytes / 8;
+    uint64_t a = h, b = ~h, c = h * 3, d2 = h ^ 0x5555555555555555ull;      // four lanes: the loop is memory-bound
+    uint64_t i = 0;
+    for (; i + 4 <= n; i += 4) { a = mix64(a, w[i]); b = mix64(b, w[i + 1]); c = mix64(c, w[i + 2]); d2 = mix64(d2, w[i + 3]); }
+    for (; i < n; i++) a = mix64(a, w[i]);
+    const unsigned char* tail = static_cast<const unsigned char*>(p) + n * 8;
+    uint64_t t = 0;
+    for (uint64_t k = 0; k < bytes % 8; k++) t = (t << 8) | tail[k];
+    return mix64(mix64(mix64(a, b), mix64(c, d2)), t ^ bytes);
+}
+
+static bool read_all(FILE* f, void* p, size_t bytes) { return bytes == 0 || fread(p, 1, bytes, f) == bytes; }
+static bool write_all(FILE* f, const void* p, size_t bytes) { return bytes == 0 || fwrite(p, 1, bytes, f) == bytes; }
+
+static bool prepared_tree_load(const std::string& path, uint64_t key, uint64_t ntriangles, PreparedTree& out)
+{
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) return false;
+    uint64_t head[4] = {0, 0, 0, 0};       // magic, key, ntriangles, native entries
+    bool ok = read_all(f, head, sizeof(head)) && head[0] == 0x43423230305452ull && head[1] == key && head[2] == ntriangles;
+    if (ok) {
+        out.rank.resize(ntriangles); out.leafbox.resize(3 * ntriangles); out.native.resize(head[3]);
+        ok = read_all(f, out.rank.data(), ntriangles * 4) && read_all(f, out.leafbox.data(), ntriangles * 12) &&
+             read_all(f, out.native.data(), head[3] * sizeof(Entry));
+    }
+    fclose(f);
+    return ok;
+}
+
+static void prepared_tree_store(const std::string& path, uint64_t key, uint64_t ntriangles, const PreparedTree& t)
+{
+    const std::string tmp = path + ".tmp" + std::to_string((long long)getpid());
+    FILE* f = fopen(tmp.c_str(), "wb");
+    if (!f) return;
+    const uint64_t head[4] = {0x43423230305452ull, key, ntriangles, (uint64_t)t.native.size()};
+    const bool ok = write_all(f, head, sizeof(head)) && write_all(f, t.rank.data(), ntriangles * 4) &&
+                    write_all(f, t.leafbox.data(), ntriangles * 12) && write_all(f, t.native.data(), t.native.size() * sizeof(Entry));
+    fclose(f);
+    if (ok) rename(tmp.c_str(), path.c_str()); else remove(tmp.c_str());
+}
+
 template <typename T>
 static int upload(T** dst, const T* src, uint64_t count, uint64_t& total)
 {
@@ -146,6 +214,92 @@ static void free_geometry(Geometry* g)
     cudaFree(g->materials); cudaFree(g->surfaces); cudaFree(g->wireframes); cudaFree(g->solid_to_channel);
     cudaFree(g->time_cdf_x); cudaFree(g->time_cdf_y); cudaFree(g->charge_cdf_x); cudaFree(g->charge_cdf_y);
     delete g;
+}
+
+// rank + leaf box per triangle + the engine's traversal tree, computed from the descriptor
+static int prepare_tree_compute(const CbGeometryDesc* d, bool use_reference_tree, PreparedTree& out)
+{
+    reference_test_rank(d->nodes, d->nnodes, d->ntriangles, out.rank);
+    // reference leaf box of every triangle (first leaf entry that names it)
+    out.leafbox.assign(3 * std::max<uint64_t>(d->ntriangles, 1), 0u);
+    {
+        std::vector<uint8_t> seen(d->ntriangles, 0);
+        for (uint64_t i = 0; i < d->nnodes; i++) {
+            const uint32_t w = d->nodes[4 * i + 3];
+            if ((w >> 28) == 0 && w < d->ntriangles && !seen[w]) {
+                seen[w] = 1;
+                for (int a = 0; a < 3; a++) out.leafbox[3ull * w + a] = d->nodes[4 * i + a];
+            }
+        }
+    }
+    out.native.clear();
+    if (use_reference_tree || d->ntriangles == 0) return CB_OK;
+    std::vector<Entry> leaves;
+    collect_reference_leaves(d->nodes, d->nnodes, d->ntriangles, out.rank, leaves);
+    SplitInput split;
+    const bool do_split = split_from_env(split);
+    split.vertices = d->vertices; split.triangles = d->triangles; split.scale = d->world_scale;
+    for (int a = 0; a < 3; a++) split.origin[a] = d->world_origin[a];
+    // One SAH hierarchy over all leaves (default since round 2: -9 % / -19 % traversal iterations on the
+    // 29k-PMT detector, bit-identical hits); CHROMA_B200_TREE=solids builds solids first, then one
+    // subtree per solid (faster to build, the round-1 default)
+    const char* tree_env = getenv("CHROMA_B200_TREE");
+    const bool single_level = !(tree_env && strcmp(tree_env, "solids") == 0);
+    int rc = build_native_tree(leaves, single_level ? nullptr : d->solid_id, out.native, do_split ? &split : nullptr);
+    if (rc != CB_OK) return rc;
+    out.native.resize(out.native.size() + 16, Entry{0, 0, 0, 0});      // the batched sibling fetch may read past the last child
+    return CB_OK;
+}
+
+static int prepare_tree(const CbGeometryDesc* d, PreparedTree& out)
+{
+    const char* tree_env = getenv("CHROMA_B200_TREE");
+    const bool use_reference_tree = tree_env && strcmp(tree_env, "reference") == 0;
+    if (use_reference_tree) {
+        // the traversal kernels fetch at most 8 children per node (the native tree's bound); the reference
+        // format allows 15 (bvh/grid.py caps groups at MAX_CHILD): such a tree cannot be walked as it is
+        for (uint64_t i = 0; i < d->nnodes; i++)
+            if ((d->nodes[4 * i + 3] >> 28) > 8)
+                return fail(CB_ERR_UNSUPPORTED, "CHROMA_B200_TREE=reference: node %llu has %u children, the traversal "
+                            "handles at most 8 (unset CHROMA_B200_TREE to traverse the engine's own tree)",
+                            (unsigned long long)i, d->nodes[4 * i + 3] >> 28);
+    }
+    const char* dir = getenv("CHROMA_B200_TREE_CACHE");
+    if (!dir || !*dir || d->ntriangles < 50000) return prepare_tree_compute(d, use_reference_tree, out);
+
+    // key: everything the result depends on
+    uint64_t key = hash_words(0x6368726f6d61ull, d->nodes, d->nnodes * 16);
+    const char* split_env = getenv("CHROMA_B200_LEAF_SPLIT");
+    const bool by_solid = tree_env && strcmp(tree_env, "solids") == 0;
+    key = mix64(key, d->ntriangles);
+    key = hash_words(key, tree_env ? tree_env : "", tree_env ? strlen(tree_env) : 0);
+    key = hash_words(key, split_env ? split_env : "", split_env ? strlen(split_env) : 0);
+    if (by_solid && d->solid_id) key = hash_words(key, d->solid_id, d->ntriangles * 4);
+    if (split_env && *split_env) {
+        key = hash_words(key, d->vertices, d->nvertices * 12);
+        key = hash_words(key, d->triangles, d->ntriangles * 12);
+    }
+    key = mix64(key, 3);                       // format / builder version
+    char name[64];
+    snprintf(name, sizeof(name), "/tree_%016llx.bin", (unsigned long long)key);
+    mkdir(dir, 0777);
+    const std::string path = std::string(dir) + name, lock = path + ".lock";
+    if (prepared_tree_load(path, key, d->ntriangles, out)) return CB_OK;
+    const int fd = open(lock.c_str(), O_CREAT | O_EXCL | O_WRONLY, 0666);
+    if (fd < 0) {
+        // another process of this node is building it: wait for the file (or for the builder to give up)
+        for (int waited = 0; waited < 6000; waited++) {
+            std::this_thread::sleep_for(std::chrono::milliseconds(100));
+            if (access(path.c_str(), R_OK) == 0 && prepared_tree_load(path, key, d->ntriangles, out)) return CB_OK;
+            if (access(lock.c_str(), F_OK) != 0 && access(path.c_str(), R_OK) != 0) break;
+        }
+        return prepare_tree_compute(d, use_reference_tree, out);
+    }
+    close(fd);
+    const int rc = prepare_tree_compute(d, use_reference_tree, out);
+    if (rc == CB_OK) prepared_tree_store(path, key, d->ntriangles, out);
+    remove(lock.c_str());
+    return rc;
 }
 
 } // namespace cb
@@ -220,25 +374,14 @@ int cb_geometry_create(const CbGeometryDesc* d, cb_geom_t* out)
     }
 #undef UP
 
-    std::vector<uint32_t> rank;
-    reference_test_rank(d->nodes, d->nnodes, d->ntriangles, rank);
+    // host-side preparation (rank, leaf boxes, the engine's tree): from the cache, or computed (and stored)
+    PreparedTree prep;
+    if ((rc = prepare_tree(d, prep)) != CB_OK) { free_geometry(g); return rc; }
     uint32_t* d_rank = nullptr;
     uint32_t* d_leafbox = nullptr;
     uint64_t scratch = 0;
-    if ((rc = upload(&d_rank, rank.data(), d->ntriangles, scratch)) != CB_OK) { free_geometry(g); return rc; }
-    {
-        // reference leaf box of every triangle (first reachable leaf entry)
-        std::vector<uint32_t> leafbox(3 * std::max<uint64_t>(d->ntriangles, 1), 0u);
-        std::vector<uint8_t> seen(d->ntriangles, 0);
-        for (uint64_t i = 0; i < d->nnodes; i++) {
-            const uint32_t w = d->nodes[4 * i + 3];
-            if ((w >> 28) == 0 && w < d->ntriangles && !seen[w]) {
-                seen[w] = 1;
-                leafbox[3ull * w] = d->nodes[4 * i]; leafbox[3ull * w + 1] = d->nodes[4 * i + 1]; leafbox[3ull * w + 2] = d->nodes[4 * i + 2];
-            }
-        }
-        if ((rc = upload(&d_leafbox, leafbox.data(), 3 * d->ntriangles, scratch)) != CB_OK) { cudaFree(d_rank); free_geometry(g); return rc; }
-    }
+    if ((rc = upload(&d_rank, prep.rank.data(), d->ntriangles, scratch)) != CB_OK) { free_geometry(g); return rc; }
+    if ((rc = upload(&d_leafbox, prep.leafbox.data(), 3 * d->ntriangles, scratch)) != CB_OK) { cudaFree(d_rank); free_geometry(g); return rc; }
     {
         cudaError_t e = cudaMalloc((void**)&g->tri64, std::max<uint64_t>(d->ntriangles, 1) * 64);
         if (e != cudaSuccess) { cudaFree(d_rank); cudaFree(d_leafbox); free_geometry(g); return cuda_fail(e, "cudaMalloc(tri64)"); }
@@ -252,37 +395,9 @@ int cb_geometry_create(const CbGeometryDesc* d, cb_geom_t* out)
         cudaFree(d_rank);
         cudaFree(d_leafbox);
     }
-
-    // the engine's own traversal tree over the reference's leaves (bvh_native.cu)
     const uint32_t* root_entry = d->nodes;
-    std::vector<Entry> native;
-    const char* tree_env = getenv("CHROMA_B200_TREE");
-    const bool use_reference_tree = tree_env && strcmp(tree_env, "reference") == 0;
-    if (use_reference_tree) {
-        // the traversal kernels fetch at most 8 children per node (the native tree's bound); the reference
-        // format allows 15 (bvh/grid.py caps groups at MAX_CHILD): such a tree cannot be walked as it is
-        for (uint64_t i = 0; i < d->nnodes; i++)
-            if ((d->nodes[4 * i + 3] >> 28) > 8) {
-                free_geometry(g);
-                return fail(CB_ERR_UNSUPPORTED, "CHROMA_B200_TREE=reference: node %llu has %u children, the traversal "
-                            "handles at most 8 (unset CHROMA_B200_TREE to traverse the engine's own tree)",
-                            (unsigned long long)i, d->nodes[4 * i + 3] >> 28);
-            }
-    }
-    if (!use_reference_tree && d->ntriangles > 0) {
-        std::vector<Entry> leaves;
-        collect_reference_leaves(d->nodes, d->nnodes, d->ntriangles, rank, leaves);
-        SplitInput split;
-        const bool do_split = split_from_env(split);
-        split.vertices = d->vertices; split.triangles = d->triangles; split.scale = d->world_scale;
-        for (int a = 0; a < 3; a++) split.origin[a] = d->world_origin[a];
-        // One SAH hierarchy over all leaves (default since round 2: -9 % / -19 % traversal iterations on the
-        // 29k-PMT detector, bit-identical hits); CHROMA_B200_TREE=solids builds solids first, then one
-        // subtree per solid (faster to build, the round-1 default)
-        const bool single_level = !(tree_env && strcmp(tree_env, "solids") == 0);
-        rc = build_native_tree(leaves, single_level ? nullptr : d->solid_id, native, do_split ? &split : nullptr);
-        if (rc != CB_OK) { free_geometry(g); return rc; }
-        native.resize(native.size() + 16, Entry{0, 0, 0, 0});
+    std::vector<Entry>& native = prep.native;
+    if (!native.empty()) {
         cudaError_t e = cudaMalloc((void**)&g->native_nodes, native.size() * sizeof(Entry));
         if (e != cudaSuccess) { free_geometry(g); return cuda_fail(e, "cudaMalloc(native nodes)"); }
         e = cudaMemcpy(g->native_nodes, native.data(), native.size() * sizeof(Entry), cudaMemcpyHostToDevice);

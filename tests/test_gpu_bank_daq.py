@@ -217,6 +217,40 @@ def test_loader_builds_caches_and_reloads(gpu_ready, tmp_path):
     assert np.array_equal(ends[0].flags, ends[1].flags) and np.array_equal(ends[0].pos, ends[1].pos)
 
 
+def test_prepared_tree_cache_is_shared_and_exact(gpu_ready, tmp_path, monkeypatch):
+    """CHROMA_B200_TREE_CACHE: what cb_geometry_create derives on the host (reference test rank, leaf boxes, the
+    engine's traversal tree) is written once and read back by later creations (other ranks of a node): same
+    hits, same propagation, and a second tree option gets its own file."""
+    import os
+    geo = scenes.ref_tiny_detector()
+    ph = scenes.point_source(30000, seed=4, wl_range=(300, 600))
+
+    def run():
+        g = gpu.GPUDetector(geo)
+        gp = gpu.GPUPhotons(ph)
+        gp.propagate(g, gpu.get_rng_states(len(ph), seed=8), nthreads_per_block=256, max_blocks=(len(ph) + 255) // 256, max_steps=50)
+        tri, dist = gpu.intersect_mesh(g, ph.pos, ph.dir)
+        return gp.get(), tri.get(), dist.get()
+    monkeypatch.delenv('CHROMA_B200_TREE_CACHE', raising=False)
+    base = run()
+    d = tmp_path / 'trees'
+    monkeypatch.setenv('CHROMA_B200_TREE_CACHE', str(d))
+    first = run()
+    files = sorted(os.listdir(str(d)))
+    assert len(files) == 1 and files[0].startswith('tree_') and files[0].endswith('.bin')
+    stamp = os.path.getmtime(str(d / files[0]))
+    second = run()                                  # served from the file
+    assert os.path.getmtime(str(d / files[0])) == stamp and sorted(os.listdir(str(d))) == files
+    for out in (first, second):
+        assert np.array_equal(out[1], base[1]) and np.array_equal(out[2].view(np.uint32), base[2].view(np.uint32))
+        for f in ('pos', 't', 'flags', 'last_hit_triangles'):
+            assert np.array_equal(getattr(out[0], f), getattr(base[0], f)), f
+    monkeypatch.setenv('CHROMA_B200_TREE', 'solids')
+    other = run()
+    assert len(os.listdir(str(d))) == 2             # keyed by the tree option too
+    assert np.array_equal(other[1], base[1])
+
+
 def test_bvh_is_conservative(gpu_ready):
     geo = scenes.tiny_detector()
     bvh = make_recursive_grid_bvh(geo.mesh)
