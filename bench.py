@@ -431,6 +431,8 @@ def run_ours(args):
     list(s.simulate((event.Event(photons_beg=ev) for _ in range(max(4, args.warmup))), **sim_kw))   # warm-up: 3 batches in flight
     nch = s.gpu_geometry.nchannels
     run_daq = gpu.GPUDaq(s.gpu_geometry)            # run-level accumulators
+    run_daq.begin_acquire()
+    run_daq.allreduce()                             # warm-up: the first collective of a communicator sets up its connections
     barrier(world)
     _lib.check(lib.cb_synchronize())
     sampler.resume()
@@ -438,18 +440,33 @@ def run_ours(args):
     run_daq.begin_acquire()
     hit_count = np.zeros(nch, dtype=np.int64)
     d2h = 0
+    gaps, t_prev = [], time.perf_counter()
     for out_ev in s.simulate((event.Event(photons_beg=ev) for _ in range(args.steps)), **sim_kw):
+        gaps.append(time.perf_counter() - t_prev)
         hit_count += out_ev.channels.hit
         fh = out_ev.flat_hits
         d2h = sum(getattr(fh, f).nbytes for f in fields) + fh.channel.nbytes + 3 * 4 * nch
         # run-level: the event's per-channel result folds into the rank's accumulators on the device
         run_daq.fold(s.gpu_daq)
+        t_prev = time.perf_counter()
+    t_loop = time.perf_counter() - t0
     run_channels = run_daq.allreduce().get()        # one NCCL exchange over NVLink + read-back (3 x 4 B x channels)
     _lib.check(lib.cb_synchronize())
     barrier(world)
-    e2e_s = max_over_ranks(time.perf_counter() - t0, world)
+    my_e2e_s = time.perf_counter() - t0
+    e2e_s = max_over_ranks(my_e2e_s, world)
     clocks = sampler.stop() if rank == 0 else None
     e2e = total_photons / e2e_s
+    # every rank's view of its pipeline (where an end-to-end slowdown at large N comes from)
+    mine = {'rank': rank, 'e2e_s': my_e2e_s, 'loop_s': t_loop, 'allreduce_and_readback_s': my_e2e_s - t_loop,
+            'last_batch': dict(s.last_timings), 'yield_gap_ms_median': float(np.median(gaps)) * 1e3,
+            'yield_gap_ms_max': float(np.max(gaps)) * 1e3, 'affinity_cores': len(os.sched_getaffinity(0))}
+    per_rank = [mine]
+    if world > 1:
+        import torch.distributed as dist
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, mine)
+    timings['per_rank'] = per_rank
     timings['e2e_last_batch'] = dict(s.last_timings)
     timings['e2e_s_per_event'] = e2e_s / args.steps
     timings['e2e_hits_per_event'] = int(len(fh))
