@@ -74,19 +74,28 @@ class ClockSampler(object):
          'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
          'clocks_event_reasons.sw_power_cap')
 
-    def __init__(self, index=0):
+    def __init__(self, index=0, pci_bus_id=None, period_s=0.005):
         self.index, self.rows, self.proc, self.nvml = index, [], None, None
         self.sm, self.reasons, self.sm_max = [], set(), None
+        self.period_s = period_s
         self._stop = threading.Event()
         self._on = threading.Event()
+        if os.environ.get('CHROMA_B200_NO_CLOCKS'):
+            self.disabled = True
+            return
+        self.disabled = False
         try:
             import pynvml
             pynvml.nvmlInit()
-            # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES when it is a plain index list
-            vis = os.environ.get('CUDA_VISIBLE_DEVICES', '')
-            ids = [int(x) for x in vis.split(',')] if vis and all(x.strip().isdigit() for x in vis.split(',')) else None
-            phys = ids[index] if ids and index < len(ids) else index
-            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            if pci_bus_id:
+                # NVML orders devices by PCI bus id, CUDA by default "fastest first": identify the GPU by its bus id
+                self.handle = pynvml.nvmlDeviceGetHandleByPciBusId(pci_bus_id.encode() if hasattr(pci_bus_id, 'encode') else pci_bus_id)
+            else:
+                # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES when it is a plain index list
+                vis = os.environ.get('CUDA_VISIBLE_DEVICES', '')
+                ids = [int(x) for x in vis.split(',')] if vis and all(x.strip().isdigit() for x in vis.split(',')) else None
+                phys = ids[index] if ids and index < len(ids) else index
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
             self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
             self.nvml = pynvml
         except Exception:
@@ -94,6 +103,8 @@ class ClockSampler(object):
 
     def start(self):
         """Start the sampling thread (idle until resume())."""
+        if self.disabled:
+            return
         if self.nvml is not None:
             self.thread = threading.Thread(target=self._poll, daemon=True)
             self.thread.start()
@@ -130,7 +141,7 @@ class ClockSampler(object):
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.002)
+            time.sleep(self.period_s)
 
     def _read(self):
         for line in self.proc.stdout:
@@ -139,10 +150,13 @@ class ClockSampler(object):
 
     def stop(self):
         self._stop.set()
+        if self.disabled:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['sampling disabled (CHROMA_B200_NO_CLOCKS)']}
         if self.nvml is not None:
             self.thread.join(timeout=1.0)
             return {'sm_mhz': float(np.median(self.sm)) if self.sm else None, 'sm_max_mhz': self.sm_max,
-                    'reasons': sorted(self.reasons), 'samples': len(self.sm), 'source': 'nvml, 2 ms period, timed regions only'}
+                    'reasons': sorted(self.reasons), 'samples': len(self.sm),
+                    'source': 'nvml, %g ms period, timed regions only' % (self.period_s * 1e3)}
         if self.proc is None:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
         time.sleep(0.15)
@@ -390,7 +404,8 @@ def run_ours(args):
         gp.propagate(g, rng, nthreads_per_block=512, max_blocks=s.max_blocks, max_steps=MAX_STEPS)
         return gp.last_stats
 
-    sampler = ClockSampler(local)
+    pci = C.create_string_buffer(32)
+    sampler = ClockSampler(local, pci_bus_id=pci.value.decode() if lib.cb_device_pci_bus_id(pci, 32) == 0 else None)
     if rank == 0:
         sampler.start()
     for _ in range(args.warmup):
@@ -401,9 +416,11 @@ def run_ours(args):
     acc = dict(kernel_ms=0.0, launches=0, steps=0, nodes_visited=0, tris_tested=0, rays_resolved=0, intersect_ms=0.0,
                physics_ms=0.0, tail_ms=0.0, intersect_rays=0, physics_steps=0, tail_photons=0, tail_steps=0)
     int0_ms, int0_rays, int0_n = 0.0, 0, 0
+    per_event_ms = []
     t0 = time.perf_counter()
     for _ in range(args.steps):
         st = one_step()
+        per_event_ms.append(round(st.kernel_ms, 3))
         for k in acc:
             acc[k] += getattr(st, k)
         if st.intersect0_rays:
@@ -458,7 +475,7 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     e2e = total_photons / e2e_s
     # every rank's view of its pipeline (where an end-to-end slowdown at large N comes from)
-    mine = {'rank': rank, 'e2e_s': my_e2e_s, 'loop_s': t_loop, 'allreduce_and_readback_s': my_e2e_s - t_loop,
+    mine = {'rank': rank, 'device_ms_per_event': per_event_ms, 'pci_bus_id': pci.value.decode(), 'e2e_s': my_e2e_s, 'loop_s': t_loop, 'allreduce_and_readback_s': my_e2e_s - t_loop,
             'last_batch': dict(s.last_timings), 'yield_gap_ms_median': float(np.median(gaps)) * 1e3,
             'yield_gap_ms_max': float(np.max(gaps)) * 1e3, 'affinity_cores': len(os.sched_getaffinity(0))}
     per_rank = [mine]

@@ -81,6 +81,7 @@ SIGNATURES = {
     'cb_last_error': (C.c_char_p, []),
     'cb_synchronize': (C.c_int, []),
     'cb_sm_count': (C.c_int, []),
+    'cb_device_pci_bus_id': (C.c_int, [C.c_char_p, i32]),
     'cb_malloc': (C.c_int, [u64, _P(vp)]),
     'cb_free': (C.c_int, [vp]),
     'cb_memcpy_h2d': (C.c_int, [vp, vp, u64]),

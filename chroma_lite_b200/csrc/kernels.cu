@@ -578,6 +578,158 @@ propagate_tail_kernel(const __grid_constant__ DevGeometry g, const __grid_consta
     }
 }
 
+// Persistent tail, second form: the warp still traverses ONE ray at a time cooperatively (warp_traverse), but
+// it owns up to 32 photons, one per lane, and their physics runs lane-parallel.  In the one-photon-per-warp
+// kernel above every lane executes the same ~1.1 k physics instructions of the same photon, a third of a
+// step's instructions; here those are issued once for up to 32 photons.  A step of the warp is
+//   refill     free lanes claim queue entries (one atomic per attempt for the whole warp)
+//   traverse   for every lane that holds a photon: its ray is read from shared memory by all lanes and
+//              traversed by the warp; the hit goes to the owning lane
+//   physics    each lane advances its own photon; finished photons are stored and their lanes freed
+// The photons live in shared memory between phases ([field][lane] per warp, 22 words per photon), so the
+// traversal's registers are not shared with 20 words of photon state and the kernel keeps its 32 warps per SM.
+constexpr int TAIL_SLOT_WORDS = 22;   // pos dir pol (9) wavelength time weight history last_hit (5) rng (6) index, steps|sf
+template <bool COUNT, bool WIRES>
+__global__ void __launch_bounds__(TAIL_THREADS, CB_TAIL_BLOCKS)
+propagate_tail_lanes_kernel(const __grid_constant__ DevGeometry g, const __grid_constant__ PropParams P)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ unsigned long long mbar;
+    const unsigned long long n_in = *P.n_in;
+    if (n_in > P.tail_at || n_in == 0) return;       // (uniform) still the wavefront kernels' turn, or nothing left
+    constexpr int WARPS = TAIL_THREADS / 32;
+    const unsigned FULL = 0xffffffffu;
+    float* stab = reinterpret_cast<float*>(smem_raw);
+    const uint32_t tab_bytes = g.smem_bytes;
+    const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    unsigned char* after_tables = smem_raw + ((tab_bytes + 127u) & ~127u);
+    uint2* wstack = reinterpret_cast<uint2*>(after_tables) + warp * (CB_WSTACK + CB_WLEAF);
+    uint2* wleaf = wstack + CB_WSTACK;
+    uint32_t* slots = reinterpret_cast<uint32_t*>(after_tables + (size_t)WARPS * (CB_WSTACK + CB_WLEAF) * sizeof(uint2)) +
+                      warp * (TAIL_SLOT_WORDS * 32);
+    uint32_t* mine = slots + lane;                    // field f of this lane's photon: mine[f * 32]
+    stage_tables(stab, g.tables, tab_bytes, &mbar);
+    Tables T = {stab, g.tables, g.smem_floats};
+    TraverseCounters cnt = {0, 0, 0};
+    unsigned long long nsteps_total = 0;
+    bool have = false, exhausted = false;
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(P.counters + 7, n_in);
+    // few photons: spread them over all warps of the grid (a warp traverses its photons' rays one after the
+    // other, so 32 photons in one warp while other warps idle would serialise them)
+    const unsigned long long warps_in_grid = (unsigned long long)gridDim.x * WARPS;
+    const unsigned lanes_cap = (unsigned)min(32ull, (n_in + warps_in_grid - 1) / warps_in_grid);
+    const unsigned may_hold = lanes_cap >= 32u ? FULL : ((1u << lanes_cap) - 1u);
+
+    for (;;) {
+        // ---- refill: the queue is walked twice, photons sitting on a surface first (see the kernel above)
+        for (int attempt = 0; attempt < 4 && !exhausted; attempt++) {
+            const unsigned need = __ballot_sync(FULL, !have) & may_hold;
+            if (!need) break;
+            const int want = __popc(need), leader = __ffs(need) - 1;
+            unsigned long long base = 0;
+            if ((int)lane == leader) base = atomicAdd(P.cursor, (unsigned long long)want);
+            base = __shfl_sync(FULL, base, leader);
+            exhausted = base + want >= 2 * n_in;
+            unsigned long long q = base + __popc(need & lt_mask);
+            if (!have && ((need >> lane) & 1u) && q < 2 * n_in) {
+                const bool first_pass = q < n_in;
+                if (!first_pass) q -= n_in;
+                const uint32_t entry = P.queue_in ? P.queue_in[q] : ((uint32_t)q | QUEUE_ON_SURFACE);
+                const uint32_t k = entry & ~QUEUE_ON_SURFACE;
+                const uint64_t id = P.first + k;
+                if (((entry & QUEUE_ON_SURFACE) != 0) == first_pass) {
+                    const uint32_t hist = P.bank.flags[id] & 0xFFFFu;
+                    if (!(P.step == 0 && (hist & CB_TERMINAL))) {
+                        Photon p;
+                        load_photon(P.bank, id, hist, P.step == 0, p);
+                        const Rng rng = rng_load(P.rng, k);
+                        mine[0 * 32] = __float_as_uint(p.pos.x); mine[1 * 32] = __float_as_uint(p.pos.y); mine[2 * 32] = __float_as_uint(p.pos.z);
+                        mine[3 * 32] = __float_as_uint(p.dir.x); mine[4 * 32] = __float_as_uint(p.dir.y); mine[5 * 32] = __float_as_uint(p.dir.z);
+                        mine[6 * 32] = __float_as_uint(p.pol.x); mine[7 * 32] = __float_as_uint(p.pol.y); mine[8 * 32] = __float_as_uint(p.pol.z);
+                        mine[9 * 32] = __float_as_uint(p.wavelength); mine[10 * 32] = __float_as_uint(p.time);
+                        mine[11 * 32] = __float_as_uint(p.weight); mine[12 * 32] = p.history; mine[13 * 32] = (uint32_t)p.last_hit_triangle;
+                        mine[14 * 32] = rng.d; mine[15 * 32] = rng.v0; mine[16 * 32] = rng.v1; mine[17 * 32] = rng.v2;
+                        mine[18 * 32] = rng.v3; mine[19 * 32] = rng.v4;
+                        mine[20 * 32] = k;
+                        const int sf = (P.step == 0) ? P.scatter_first : 0;
+                        mine[21 * 32] = (uint32_t)P.step | ((uint32_t)(sf + 1) << 16);
+                        have = true;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (!__any_sync(FULL, have)) {
+            if (exhausted) break;
+            continue;
+        }
+        // ---- traversal, one ray at a time, by the whole warp
+        bool nan = false;
+        if (have) {
+            nan = isnan(__uint_as_float(mine[3 * 32]) * __uint_as_float(mine[4 * 32]) * __uint_as_float(mine[5 * 32]) *
+                        __uint_as_float(mine[0 * 32]) * __uint_as_float(mine[1 * 32]) * __uint_as_float(mine[2 * 32]));
+        }
+        unsigned todo = __ballot_sync(FULL, have && !nan);
+        int my_tri = -1;
+        float my_dist = -1.0f;
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const uint32_t* ray = slots + src;
+            const float3 o = f3(__uint_as_float(ray[0 * 32]), __uint_as_float(ray[1 * 32]), __uint_as_float(ray[2 * 32]));
+            const float3 d = f3(__uint_as_float(ray[3 * 32]), __uint_as_float(ray[4 * 32]), __uint_as_float(ray[5 * 32]));
+            const int last = (int)ray[13 * 32];
+            float dist;
+            const int tri = warp_traverse<COUNT>(g, o, d, last, dist, wstack, wleaf, (uint32_t*)(P.counters + 3), &cnt);
+            if ((int)lane == src) { my_tri = tri; my_dist = dist; }
+        }
+        // ---- physics, one photon per lane
+        if (have) {
+            Photon p;
+            p.pos = f3(__uint_as_float(mine[0 * 32]), __uint_as_float(mine[1 * 32]), __uint_as_float(mine[2 * 32]));
+            p.dir = f3(__uint_as_float(mine[3 * 32]), __uint_as_float(mine[4 * 32]), __uint_as_float(mine[5 * 32]));
+            p.pol = f3(__uint_as_float(mine[6 * 32]), __uint_as_float(mine[7 * 32]), __uint_as_float(mine[8 * 32]));
+            p.wavelength = __uint_as_float(mine[9 * 32]); p.time = __uint_as_float(mine[10 * 32]);
+            p.weight = __uint_as_float(mine[11 * 32]); p.history = mine[12 * 32]; p.last_hit_triangle = (int)mine[13 * 32];
+            Rng rng = {mine[14 * 32], mine[15 * 32], mine[16 * 32], mine[17 * 32], mine[18 * 32], mine[19 * 32]};
+            const uint32_t k = mine[20 * 32];
+            const uint32_t packed = mine[21 * 32];
+            const int steps = (int)(packed & 0xFFFFu) + 1, sf = (int)(packed >> 16) - 1;
+            nsteps_total++;
+            bool alive;
+            if (nan) {
+                p.history |= CB_NO_HIT | CB_NAN_ABORT;
+                alive = false;
+            } else {
+                alive = physics_step<WIRES>(g, T, p, rng, my_tri, my_dist, P.use_weights != 0, sf);
+            }
+            if (!alive || steps >= P.max_steps) {
+                rng_store(P.rng, k, rng);
+                store_photon(P.bank, P.first + k, p);
+                have = false;
+            } else {
+                mine[0 * 32] = __float_as_uint(p.pos.x); mine[1 * 32] = __float_as_uint(p.pos.y); mine[2 * 32] = __float_as_uint(p.pos.z);
+                mine[3 * 32] = __float_as_uint(p.dir.x); mine[4 * 32] = __float_as_uint(p.dir.y); mine[5 * 32] = __float_as_uint(p.dir.z);
+                mine[6 * 32] = __float_as_uint(p.pol.x); mine[7 * 32] = __float_as_uint(p.pol.y); mine[8 * 32] = __float_as_uint(p.pol.z);
+                mine[9 * 32] = __float_as_uint(p.wavelength); mine[10 * 32] = __float_as_uint(p.time);
+                mine[11 * 32] = __float_as_uint(p.weight); mine[12 * 32] = p.history; mine[13 * 32] = (uint32_t)p.last_hit_triangle;
+                mine[14 * 32] = rng.d; mine[15 * 32] = rng.v0; mine[16 * 32] = rng.v1; mine[17 * 32] = rng.v2;
+                mine[18 * 32] = rng.v3; mine[19 * 32] = rng.v4;
+                mine[21 * 32] = (uint32_t)steps | (1u << 16);          // scatter_first applies to the first step only
+            }
+        }
+        __syncwarp();
+    }
+    for (int o = 16; o > 0; o >>= 1) nsteps_total += __shfl_down_sync(FULL, nsteps_total, o);
+    if (lane == 0 && nsteps_total) { atomicAdd(P.counters + 4, nsteps_total); atomicAdd(P.counters + 8, nsteps_total); }
+    if (COUNT) {
+        atomicAdd(P.counters + 1, (unsigned long long)cnt.nodes);
+        atomicAdd(P.counters + 2, (unsigned long long)cnt.tris);
+        if (lane == 0) atomicAdd(P.counters + 5, (unsigned long long)cnt.resolved);
+    }
+}
+
 // ---------------------------------------------------------------- bank utilities
 struct BankPtrs { CbPhotonBank b; };
 
@@ -1002,12 +1154,19 @@ int cb_propagate(const CbPhotonBank* bank, cb_geom_t gh, cb_rng_t rh, int32_t nt
 
     auto k_int = count ? step_intersect_kernel<true> : step_intersect_kernel<false>;
     const bool wires = g->dev.nwireplanes > 0;
-    auto k_tail = wires ? (count ? propagate_tail_kernel<true, true> : propagate_tail_kernel<false, true>)
-                        : (count ? propagate_tail_kernel<true, false> : propagate_tail_kernel<false, false>);
+    // CHROMA_B200_TAIL_MODE=warp: one photon per warp, physics executed by all lanes (round 1);
+    // default: 32 photons per warp, physics lane-parallel (propagate_tail_lanes_kernel)
+    const bool tail_lanes = !(getenv("CHROMA_B200_TAIL_MODE") && strcmp(getenv("CHROMA_B200_TAIL_MODE"), "warp") == 0);
+    auto k_tail = tail_lanes
+        ? (wires ? (count ? propagate_tail_lanes_kernel<true, true> : propagate_tail_lanes_kernel<false, true>)
+                 : (count ? propagate_tail_lanes_kernel<true, false> : propagate_tail_lanes_kernel<false, false>))
+        : (wires ? (count ? propagate_tail_kernel<true, true> : propagate_tail_kernel<false, true>)
+                 : (count ? propagate_tail_kernel<true, false> : propagate_tail_kernel<false, false>));
     auto k_phys = wires ? step_physics_kernel<true> : step_physics_kernel<false>;
     const size_t smem_int = stack_smem_bytes();
     const size_t smem_tab = (g->smem_table_bytes + 127u) & ~127u;
-    const size_t smem_tail = smem_tab + (size_t)(TAIL_THREADS / 32) * (CB_WSTACK + CB_WLEAF) * sizeof(uint2);
+    const size_t smem_tail = smem_tab + (size_t)(TAIL_THREADS / 32) * (CB_WSTACK + CB_WLEAF) * sizeof(uint2) +
+                             (tail_lanes ? (size_t)(TAIL_THREADS / 32) * TAIL_SLOT_WORDS * 32 * sizeof(uint32_t) : 0);
     CB_CUDA(cudaFuncSetAttribute(k_int, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_int));
     CB_CUDA(cudaFuncSetAttribute(k_phys, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_tab, 16)));
     CB_CUDA(cudaFuncSetAttribute(k_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tail));
@@ -1102,7 +1261,7 @@ int cb_propagate(const CbPhotonBank* bank, cb_geom_t gh, cb_rng_t rh, int32_t nt
                 }
                 if (tail) {
                     // everything that is left, in one persistent launch; one photon per warp
-                    const uint64_t per_block = TAIL_THREADS / 32;
+                    const uint64_t per_block = TAIL_THREADS / 32;      // warps first; the lanes kernel then fills lanes
                     const uint64_t most = (last || exact) ? n_alive : std::min<uint64_t>(n_alive, tail_threshold);
                     const unsigned blocks = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((most + per_block - 1) / per_block,
                                                                                              (uint64_t)c.sm_count * tail_per_sm));

@@ -291,6 +291,13 @@ int cb_set_blocking_sync(int32_t on)
 }
 
 int cb_sm_count(void) { return ctx().sm_count; }
+int cb_device_pci_bus_id(char* out, int32_t len)
+{
+    CB_REQUIRE_INIT();
+    if (!out || len < 16) return fail(CB_ERR_INVALID, "cb_device_pci_bus_id: buffer too small");
+    CB_CUDA(cudaDeviceGetPCIBusId(out, len, ctx().device));
+    return CB_OK;
+}
 
 int cb_synchronize(void)
 {

@@ -182,6 +182,8 @@ int         cb_abi_version(void);
 const char* cb_last_error(void);
 int         cb_synchronize(void);
 int         cb_sm_count(void);
+/* PCI bus id of the bound device ("0000:1b:00.0"), e.g. to find the same GPU in NVML */
+int         cb_device_pci_bus_id(char* out, int32_t len);
 
 /* replaces pycuda.driver.mem_alloc / memcpy_* / GPUArray.fill */
 int cb_malloc(uint64_t bytes, void** dptr);

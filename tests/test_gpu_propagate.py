@@ -182,12 +182,14 @@ def test_scheduler_invariance(gpu_ready, monkeypatch):
                dict(TAIL='1000000000'),                 # one warp-cooperative persistent launch
                dict(TAIL='20000'),                      # hybrid
                dict(TAIL='20000', SORT='1'),            # + coherence sort
+               dict(TAIL='1000000000', TAIL_MODE='warp'),   # round 1's tail: one photon per warp
+               dict(TAIL='20000', TAIL_MODE='warp'),
                dict(TAIL='0', SPLIT='0'),               # without the end-game ray splitting
                dict(TAIL='20000', SPLIT='0'),
                dict(TAIL='20000', TRAV='lane'),         # first-generation traversal kernels
                dict(TAIL='0', TRAV='lane'))
     for cfg in configs:
-        for k in ('TAIL', 'SORT', 'TRAV', 'SPLIT'):
+        for k in ('TAIL', 'SORT', 'TRAV', 'SPLIT', 'TAIL_MODE'):
             monkeypatch.delenv('CHROMA_B200_' + k, raising=False)
         for k, v in cfg.items():
             monkeypatch.setenv('CHROMA_B200_' + k, v)
