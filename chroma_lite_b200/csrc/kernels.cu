@@ -252,11 +252,11 @@ if (giving) { tv.sp -= CB_PSTRIDE; e = lds64(tv.sp); }
                              *reinterpret_cast<const float4*>(&q[2]));
         } else if (do_exp) {
             PTrav::Nearest nr = {0u, __int_as_float(0x7f800000)};
-            tv.template process4<COUNT>(q, 0, n, nr, sbase, lstack, &cnt);
+            tv.template process4<COUNT>(q, 0, n, nr, sbase, lstack, &cnt, g.nodes, g.tri64);
             if (n > 4) {
 #pragma unroll
                 for (int k = 0; k < 4; k++) q[k] = __ldg(g.nodes + first + min(4u + k, n - 1u));
-                tv.template process4<COUNT>(q, 4, n, nr, sbase, lstack, &cnt);
+                tv.template process4<COUNT>(q, 4, n, nr, sbase, lstack, &cnt, g.nodes, g.tri64);
             }
             tv.expand_end(nr, sbase, lstack);
         }
