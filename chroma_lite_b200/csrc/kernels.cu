@@ -53,6 +53,16 @@ __device__ __forceinline__ void stage_tables(float* smem_dst, const float* gsrc,
 }
 
 // ---------------------------------------------------------------- intersection
+// A ray with a NaN / infinite component or a zero direction cannot be culled: every slab comparison is false,
+// so the traversal would walk the WHOLE tree (139 ms for one such photon in the 37 M-triangle detector, seen as
+// a 26x straggler event at 8 GPUs in round 2).  Such rays are not traced: they report "no hit", and the physics
+// step flags the photon NAN_ABORT by the reference's own rule (propagate.cu:295-299) or NO_HIT.
+__device__ __forceinline__ bool ray_is_traceable(const float3& o, const float3& d)
+{
+    const float s = o.x + o.y + o.z + d.x + d.y + d.z;                 // NaN or inf if any component is
+    return isfinite(s) && isfinite(fabsf(o.x) + fabsf(o.y) + fabsf(o.z)) && (d.x != 0.0f || d.y != 0.0f || d.z != 0.0f);
+}
+
 struct RaySource {           // cb_intersect: free rays, direction normalised like distance_to_mesh
     const float* origins; const float* directions; const int32_t* last_hit;
     int32_t* tri_out; float* dist_out;
@@ -62,7 +72,7 @@ struct RaySource {           // cb_intersect: free rays, direction normalised li
         d = ld3(directions, i);
         d = d / norm(d);
         last = last_hit ? last_hit[i] : -1;
-        return true;
+        return ray_is_traceable(o, d);
     }
     __device__ __forceinline__ void store(unsigned long long i, int tri, float dist) const
     {
@@ -88,6 +98,15 @@ struct RaySource {           // cb_intersect: free rays, direction normalised li
 // (see PTrav), helpers start from the donor's culling limit, and the merge is the
 // same lexicographic minimum, so results are unchanged bit for bit.
 struct Tune { int refill_min; int split; };
+#ifndef CB_TRI_NO_ALLOCATE
+#define CB_TRI_NO_ALLOCATE 0
+#endif
+__device__ __forceinline__ uint4 ldg_no_allocate(const uint4* p)
+{
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
 #ifndef CB_INT_BLOCKS
 #define CB_INT_BLOCKS 5     /* resident CTAs per SM of the traversal kernels: 5 x 128 threads at 96 registers */
 #endif
@@ -168,6 +187,8 @@ __device__ __forceinline__ void persistent_intersect(const DevGeometry& g, const
                         if (src.load(q, o, d, last)) {
                             active = tv.init(g, o, d, last, sbase, lbase);
                             if (!active) src.store(slot, -1, -1.0f);
+                        } else {
+                            src.store(slot, -1, -1.0f);      // skipped (terminal at step 0) or not traceable
                         }
                     }
                 }
@@ -242,10 +263,24 @@ if (giving) { tv.sp -= CB_PSTRIDE; e = lds64(tv.sp); }
         const uint4* blk = do_tri ? reinterpret_cast<const uint4*>(g.tri64) + 4ull * tri : g.nodes + first;
         const uint32_t last_k = do_tri ? 2u : n - 1u;
         uint4 q[4];
+#if CB_TRI_NO_ALLOCATE
+        // triangle records are read once per test and rarely again: they bypass L1 (no_allocate) so that it keeps
+        // the node blocks, which neighbouring rays share.  Both load sequences are issued before either is
+        // consumed, so the warp still waits for memory once per iteration.
+        if (do_tri) {
+#pragma unroll
+            for (int k = 0; k < 3; k++) q[k] = ldg_no_allocate(blk + k);
+        }
+        if (do_exp) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) q[k] = __ldg(blk + min((uint32_t)k, last_k));
+        }
+#else
         if (do_tri || do_exp) {
 #pragma unroll
             for (int k = 0; k < 4; k++) q[k] = __ldg(blk + min((uint32_t)k, last_k));
         }
+#endif
         if (do_tri) {
             if (COUNT) cnt.tris++;
             tv.test_triangle(lbase, tri, *reinterpret_cast<const float4*>(&q[0]), *reinterpret_cast<const float4*>(&q[1]),
@@ -405,7 +440,7 @@ struct PhotonRaySource {     // one propagation step: rays of the photons in the
         d = ld3(P.bank.dir, id);
         if (P.step == 0) d = d / norm(d);
         last = P.bank.last_hit_triangles[id];
-        return true;
+        return ray_is_traceable(o, d);
     }
     __device__ __forceinline__ void store(unsigned long long q, int tri, float dist) const
     {
@@ -550,8 +585,9 @@ propagate_tail_kernel(const __grid_constant__ DevGeometry g, const __grid_consta
                 p.history |= CB_NO_HIT | CB_NAN_ABORT;
                 alive = false;
             } else {
-                float dist;
-                const int tri = warp_traverse<COUNT>(g, p.pos, p.dir, p.last_hit_triangle, dist, wstack, wleaf,
+                float dist = -1.0f;
+                const int tri = !ray_is_traceable(p.pos, p.dir) ? -1 :
+                                warp_traverse<COUNT>(g, p.pos, p.dir, p.last_hit_triangle, dist, wstack, wleaf,
                                                      (uint32_t*)(P.counters + 3), &cnt);
                 alive = physics_step<WIRES>(g, T, p, rng, tri, dist, P.use_weights != 0, sf);
                 sf = 0;
@@ -670,7 +706,10 @@ propagate_tail_lanes_kernel(const __grid_constant__ DevGeometry g, const __grid_
             nan = isnan(__uint_as_float(mine[3 * 32]) * __uint_as_float(mine[4 * 32]) * __uint_as_float(mine[5 * 32]) *
                         __uint_as_float(mine[0 * 32]) * __uint_as_float(mine[1 * 32]) * __uint_as_float(mine[2 * 32]));
         }
-        unsigned todo = __ballot_sync(FULL, have && !nan);
+        const bool traceable = have && !nan &&
+            ray_is_traceable(f3(__uint_as_float(mine[0 * 32]), __uint_as_float(mine[1 * 32]), __uint_as_float(mine[2 * 32])),
+                             f3(__uint_as_float(mine[3 * 32]), __uint_as_float(mine[4 * 32]), __uint_as_float(mine[5 * 32])));
+        unsigned todo = __ballot_sync(FULL, traceable);
         int my_tri = -1;
         float my_dist = -1.0f;
         while (todo) {
