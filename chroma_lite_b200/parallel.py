@@ -163,10 +163,11 @@ def allreduce_daq(gpu_daq):
 
 
 def host_threads_should_block(local_world_size=None, cores=None):
-    """Spin-waiting host threads (the CUDA default) need a core each; with several ranks per host
-    the pipeline threads of all ranks outnumber the cores and starve each other (round 1: 8 ranks
-    on 32 cores, end-to-end 62 % of 8 x one rank).  Block instead when a rank has fewer than 6
-    cores to itself."""
+    """Spin-waiting host threads (the CUDA default) have the lowest latency but need a core each.  Measured
+    in round 2 (profiles/r02_n8_diagnostics_*.log, r02_n2_call4.log): with 4 cores per rank (8 ranks on 32
+    cores, 2 ranks on 8) spinning is still the faster choice (6.7-7.4 ms per event end to end against
+    8.1-8.4 ms with spin-then-block waits); only below 3 cores per rank do the three pipeline threads of a
+    rank starve each other, and the waits then yield the core (cb_set_blocking_sync)."""
     import os
     if local_world_size is None:
         local_world_size = int(os.environ.get('LOCAL_WORLD_SIZE', os.environ.get('WORLD_SIZE', '1')))
@@ -175,4 +176,4 @@ def host_threads_should_block(local_world_size=None, cores=None):
             cores = len(os.sched_getaffinity(0))
         except AttributeError:
             cores = os.cpu_count() or 1
-    return cores / max(local_world_size, 1) < 6
+    return cores / max(local_world_size, 1) < 3

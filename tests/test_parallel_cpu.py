@@ -53,7 +53,8 @@ def test_event_plan_streams_do_not_depend_on_the_partition():
             for e in p.events:
                 first, count = p.window(e)
                 assert count == n and p.first_stream + first == e * n      # stream of photon 0 of event e
-    assert parallel.host_threads_should_block(8, 32) and not parallel.host_threads_should_block(1, 16)
+    assert parallel.host_threads_should_block(8, 16) and not parallel.host_threads_should_block(8, 32)
+    assert not parallel.host_threads_should_block(1, 16)
 
 
 WORKER = r'''
