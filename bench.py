@@ -611,16 +611,20 @@ def strong_scaling(args, det, s0, rank, world, local):
             b.wavelengths[:] = wl[k]
             yield event.Event(photons_beg=b)
 
+    # the geometry on the device is shared with the weak-scaling Simulation; this one has its own pipeline
+    # threads, accumulators and (per pass) a fresh RNG pool with one stream per photon of this rank's share
+    s = sim.Simulation.__new__(sim.Simulation)
+    s.__dict__.update(s0.__dict__)
+    s._pools = None
+    s.seed = 4242
+    s.rng_per_photon = True
+    s.gpu_daq = gpu.GPUDaq(s.gpu_geometry)
+
     def run_once():
-        # the geometry on the device is shared with the weak-scaling Simulation; the RNG pool (one stream per
-        # photon of this rank's share of the run) and the accumulators are fresh
-        s = sim.Simulation.__new__(sim.Simulation)
-        s.__dict__.update(s0.__dict__)
-        s._pools = None                 # its own pipeline threads (Simulation.__del__ shuts them down)
-        s.seed = 4242
-        s.rng_per_photon, s.rng_cursor = True, 0
+        s.rng_states = None             # release the previous pass's pool first
         s.rng_states = gpu.get_rng_states(max(plan.nphotons, 1), seed=s.seed, first_stream=plan.first_stream)
-        s.gpu_daq = gpu.GPUDaq(s.gpu_geometry)
+        s.rng_states.view(0, 1)         # (allocates the pool's Box-Muller side arrays outside the timed region)
+        s.rng_cursor = 0
         barrier(world)
         _lib.check(lib.cb_synchronize())
         t0 = time.perf_counter()
