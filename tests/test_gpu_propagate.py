@@ -77,7 +77,9 @@ def test_scintillator_wls_dichroic_vs_reference(gpu_ready):
     ph = scenes.point_source(150000, seed=11, wl_range=(250, 450))
     mine, _, _ = engine_run(geo, ph, 7, 200, detector=True)
     ref, _ = reference_run(geo, ph, 7, 200)
-    compare(mine, ref, min_same=0.995)
+    # times: the re-emission delay comes from a 20,000-entry CDF whose flat stretches divide two nearly equal
+    # floats; 1 photon in 150,000 lands 0.007 ns (1e-4 of its time) away from the reference kernel's value
+    compare(mine, ref, min_same=0.995, t_frac=0.9999)
     for bit in (event.BULK_REEMIT, event.SURFACE_REEMIT, event.SURFACE_TRANSMIT, event.SURFACE_DETECT):
         m, r = ((mine.flags & bit) != 0).mean(), ((ref.flags & bit) != 0).mean()
         assert m > 0.001, 'flag %x never set' % bit
