@@ -582,102 +582,193 @@ struct BvhResult {
 };
 static BvhResult g_bvh;
 
-static inline void node_union(const uint32_t* child, uint32_t n, uint32_t* lo, uint32_t* hi)
-{
-    for (int a = 0; a < 3; a++) { lo[a] = 0xFFFF; hi[a] = 0; }
-    for (uint32_t i = 0; i < n; i++)
-        for (int a = 0; a < 3; a++) {
-            uint32_t w = child[4 * i + a];
-            lo[a] = std::min(lo[a], w & 0xFFFFu);
-            hi[a] = std::max(hi[a], w >> 16);
-        }
-}
+// ---------------------------------------------------------------- layers on the device
+// The reference builds its layers on the host from arrays it copies back after every kernel
+// (bvh/grid.py:27-95: NumPy ediff1d / argwhere per layer, make_parents_detailed on the GPU, .get()).
+// Here a layer never leaves the device: run boundaries of the (shifted) Morton codes, group ids by a
+// scan, groups cut into runs of at most 15 children, one parent per run; the layers are concatenated
+// root first and single-child chains collapsed, and the finished node array is read back once.
+constexpr uint32_t BVH_MAX_CHILD = 15;
 
-static uint64_t count_unique_sorted(const std::vector<uint64_t>& a)
+__global__ void __launch_bounds__(256)
+count_runs_kernel(const unsigned long long* __restrict__ codes, uint64_t n, int shift, unsigned long long* __restrict__ total)
 {
-    if (a.empty()) return 0;
-    uint64_t n = 1;
-    for (size_t i = 1; i < a.size(); i++) n += (a[i] != a[i - 1]);
-    return n;
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool head = i < n && (i == 0 || (codes[i] >> shift) != (codes[i - 1] >> shift));
+    const unsigned m = __ballot_sync(0xffffffffu, head);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(total, (unsigned long long)__popc(m));
 }
-
-// Host part of the recursive-grid builder (behaviour of bvh/grid.py:11-95 with
-// the layer merge / concatenate / collapse kernels of bvh.cu folded in).
-static void build_layers(std::vector<uint32_t>& leaf_nodes, std::vector<uint64_t>& codes,
-                         int target_degree, BvhResult& out)
+__global__ void __launch_bounds__(256)
+mark_runs_kernel(const unsigned long long* __restrict__ codes, uint64_t n, int shift, uint32_t* __restrict__ flag)
 {
-    const uint32_t MAX_CHILD = 15;
-    std::vector<std::vector<uint32_t>> layers;   // root-first at the end; built leaf-first
-    layers.push_back(std::move(leaf_nodes));
-    while (layers.back().size() / 4 > 1) {
-        const std::vector<uint32_t>& top = layers.back();
-        const uint64_t nnodes = top.size() / 4;
-        uint64_t nunique = count_unique_sorted(codes);
-        while ((double)nnodes / (double)nunique < (double)target_degree && nunique > 1) {
-            for (auto& c : codes) c >>= 1;
-            nunique = count_unique_sorted(codes);
-        }
-        std::vector<uint32_t> first_child;
-        std::vector<uint64_t> parent_codes;
-        for (uint64_t i = 0; i < nnodes; i++) {
-            if (i == 0 || codes[i] != codes[i - 1]) {
-                first_child.push_back((uint32_t)i);
-                parent_codes.push_back(codes[i]);
-            }
-        }
-        // split groups with more than MAX_CHILD children into runs of MAX_CHILD
-        std::vector<uint32_t> fc2;
-        std::vector<uint64_t> pc2;
-        fc2.reserve(first_child.size()); pc2.reserve(first_child.size());
-        for (size_t k = 0; k < first_child.size(); k++) {
-            uint64_t end = (k + 1 < first_child.size()) ? first_child[k + 1] : nnodes;
-            for (uint64_t s = first_child[k]; s < end; s += MAX_CHILD) {
-                fc2.push_back((uint32_t)s);
-                pc2.push_back(parent_codes[k]);
-            }
-        }
-        std::vector<uint32_t> parents(fc2.size() * 4);
-        for (size_t k = 0; k < fc2.size(); k++) {
-            uint64_t end = (k + 1 < fc2.size()) ? fc2[k + 1] : nnodes;
-            uint32_t n = (uint32_t)(end - fc2[k]);
-            uint32_t lo[3], hi[3];
-            node_union(&top[4ull * fc2[k]], n, lo, hi);
-            parents[4 * k + 0] = (hi[0] << 16) | lo[0];
-            parents[4 * k + 1] = (hi[1] << 16) | lo[1];
-            parents[4 * k + 2] = (hi[2] << 16) | lo[2];
-            parents[4 * k + 3] = (n << 28) | fc2[k];
-        }
-        layers.push_back(std::move(parents));
-        codes = std::move(pc2);
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flag[i] = (i == 0 || (codes[i] >> shift) != (codes[i - 1] >> shift)) ? 1u : 0u;
+}
+// start[group] = index of the group's first node (flag marks group heads; gid = exclusive scan of flag)
+__global__ void __launch_bounds__(256)
+group_starts_kernel(const uint32_t* __restrict__ flag, const uint32_t* __restrict__ gid_excl, uint64_t n, uint32_t* __restrict__ start)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && flag[i]) start[gid_excl[i]] = (uint32_t)i;
+}
+// a node heads a parent when it heads its group or sits a multiple of 15 behind the group's head
+__global__ void __launch_bounds__(256)
+mark_parents_kernel(const uint32_t* __restrict__ flag, const uint32_t* __restrict__ gid_excl, const uint32_t* __restrict__ start,
+                    uint64_t n, uint32_t* __restrict__ head)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t g = flag[i] ? gid_excl[i] : gid_excl[i] - 1;       // exclusive scan: a head's own id, else the previous head's
+    head[i] = (flag[i] || ((uint32_t)i - start[g]) % BVH_MAX_CHILD == 0) ? 1u : 0u;
+}
+__global__ void __launch_bounds__(256)
+parent_firsts_kernel(const uint32_t* __restrict__ head, const uint32_t* __restrict__ pid_excl, uint64_t n, uint32_t* __restrict__ first)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && head[i]) first[pid_excl[i]] = (uint32_t)i;
+}
+// parent p bounds children first[p] .. first[p+1]-1 (behaviour of make_parents_detailed, bvh.cu:269-308)
+__global__ void __launch_bounds__(256)
+make_parent_layer_kernel(const uint4* __restrict__ child, const unsigned long long* __restrict__ child_codes, int shift,
+                         const uint32_t* __restrict__ first, uint64_t nparents, uint64_t nchildren, uint4* __restrict__ parent,
+                         unsigned long long* __restrict__ parent_codes)
+{
+    const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= nparents) return;
+    const uint32_t lo_i = first[p], hi_i = (p + 1 < nparents) ? first[p + 1] : (uint32_t)nchildren;
+    uint32_t lo[3] = {0xFFFFu, 0xFFFFu, 0xFFFFu}, hi[3] = {0u, 0u, 0u};
+    for (uint32_t i = lo_i; i < hi_i; i++) {
+        const uint4 c = child[i];
+        const uint32_t w[3] = {c.x, c.y, c.z};
+        for (int a = 0; a < 3; a++) { lo[a] = min(lo[a], w[a] & 0xFFFFu); hi[a] = max(hi[a], w[a] >> 16); }
     }
-    // concatenate root-first; rebase child ids of every non-leaf layer
+    parent[p] = make_uint4(lo[0] | (hi[0] << 16), lo[1] | (hi[1] << 16), lo[2] | (hi[2] << 16), ((hi_i - lo_i) << 28) | lo_i);
+    parent_codes[p] = child_codes[lo_i] >> shift;
+}
+__global__ void __launch_bounds__(256)
+shift_codes_kernel(unsigned long long* codes, uint64_t n, int shift)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) codes[i] >>= shift;
+}
+__global__ void __launch_bounds__(256)
+gather_leaves_kernel(const uint4* __restrict__ leaves, const uint32_t* __restrict__ ids, uint64_t n, uint4* __restrict__ out)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = leaves[ids[i]];
+}
+// layer -> its place in the root-first array, child ids moved by the start of the layer below (copy_and_offset, bvh.cu:364-384)
+__global__ void __launch_bounds__(256)
+place_layer_kernel(const uint4* __restrict__ src, uint64_t n, uint32_t child_offset, uint4* __restrict__ dst)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint4 v = src[i];
+    if (child_offset) v.w = (v.w & 0xF0000000u) | ((v.w & 0x0FFFFFFFu) + child_offset);
+    dst[i] = v;
+}
+// nodes with a single child become that child (collapse_child, bvh.cu:530-543); layers are done bottom up
+__global__ void __launch_bounds__(256)
+collapse_layer_kernel(uint4* nodes, uint64_t start, uint64_t end)
+{
+    const uint64_t i = start + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= end) return;
+    const uint32_t w = nodes[i].w;
+    if ((w >> 28) == 1) nodes[i] = nodes[w & 0x0FFFFFFFu];
+}
+
+struct DeviceLayer { uint4* nodes; uint64_t n; };
+
+// leaves sorted by Morton code (device) -> finished node array on the host, layer offsets
+static int build_layers_device(uint4* d_sorted_leaves, unsigned long long* d_codes, uint64_t ntriangles, int target_degree,
+                               BvhResult& out)
+{
+    Context& c = ctx();
+    cudaStream_t st = c.stream;
+    std::vector<DeviceLayer> layers;                 // leaf first
+    std::vector<void*> owned;
+    uint32_t *d_flag = nullptr, *d_gid = nullptr, *d_start = nullptr, *d_head = nullptr, *d_pid = nullptr, *d_first = nullptr,
+             *d_scan = nullptr;
+    unsigned long long *d_total = nullptr, *d_pcodes = nullptr;
+    uint4* d_final = nullptr;
+    auto cleanup = [&]() {
+        for (void* p : owned) cudaFree(p);
+        cudaFree(d_flag); cudaFree(d_gid); cudaFree(d_start); cudaFree(d_head); cudaFree(d_pid); cudaFree(d_first);
+        cudaFree(d_scan); cudaFree(d_total); cudaFree(d_pcodes); cudaFree(d_codes); cudaFree(d_final);      // both code buffers are ours
+    };
+#define BL(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { cleanup(); return cuda_fail(_e, #call); } } while (0)
+    const uint64_t cap = ntriangles;
+    BL(cudaMalloc(&d_flag, cap * 4)); BL(cudaMalloc(&d_gid, cap * 4)); BL(cudaMalloc(&d_start, (cap + 1) * 4));
+    BL(cudaMalloc(&d_head, cap * 4)); BL(cudaMalloc(&d_pid, cap * 4)); BL(cudaMalloc(&d_first, (cap + 1) * 4));
+    BL(cudaMalloc(&d_scan, exclusive_scan_scratch_words(cap) * 4)); BL(cudaMalloc(&d_total, 8));
+    BL(cudaMalloc(&d_pcodes, cap * 8));
+    auto grid = [](uint64_t n) { return (unsigned)((n + 255) / 256); };
+    auto count_runs = [&](uint64_t n, int shift, uint64_t& runs) -> int {
+        BL(cudaMemsetAsync(d_total, 0, 8, st));
+        count_runs_kernel<<<grid(n), 256, 0, st>>>(d_codes, n, shift, d_total);
+        unsigned long long h = 0;
+        BL(cudaMemcpyAsync(&h, d_total, 8, cudaMemcpyDeviceToHost, st));
+        BL(stream_wait(st));
+        runs = h;
+        return CB_OK;
+    };
+    layers.push_back({d_sorted_leaves, ntriangles});
+    uint64_t n = ntriangles;
+    unsigned long long* codes = d_codes;
+    while (n > 1) {
+        // drop low Morton bits until the mean fan-out reaches the target (bvh/grid.py:41-45)
+        int shift = 0;
+        uint64_t runs = 0;
+        int rc = count_runs(n, 0, runs);
+        if (rc) return rc;
+        while ((double)n / (double)runs < (double)target_degree && runs > 1) {
+            shift++;
+            if ((rc = count_runs(n, shift, runs))) return rc;
+        }
+        mark_runs_kernel<<<grid(n), 256, 0, st>>>(codes, n, shift, d_flag);
+        exclusive_scan(d_flag, d_gid, n, d_scan, st);
+        group_starts_kernel<<<grid(n), 256, 0, st>>>(d_flag, d_gid, n, d_start);
+        mark_parents_kernel<<<grid(n), 256, 0, st>>>(d_flag, d_gid, d_start, n, d_head);
+        exclusive_scan(d_head, d_pid, n, d_scan, st);
+        uint32_t last_pid = 0, last_head = 0;
+        BL(cudaMemcpyAsync(&last_pid, d_pid + (n - 1), 4, cudaMemcpyDeviceToHost, st));
+        BL(cudaMemcpyAsync(&last_head, d_head + (n - 1), 4, cudaMemcpyDeviceToHost, st));
+        BL(stream_wait(st));
+        const uint64_t nparents = (uint64_t)last_pid + last_head;
+        parent_firsts_kernel<<<grid(n), 256, 0, st>>>(d_head, d_pid, n, d_first);
+        uint4* d_parent = nullptr;
+        BL(cudaMalloc(&d_parent, nparents * sizeof(uint4)));
+        owned.push_back(d_parent);
+        make_parent_layer_kernel<<<grid(nparents), 256, 0, st>>>(layers.back().nodes, codes, shift, d_first, nparents, n, d_parent,
+                                                                 d_pcodes);
+        BL(cudaGetLastError());
+        // the parents' codes become the next round's codes (d_codes and d_pcodes swap roles)
+        std::swap(d_codes, d_pcodes);
+        codes = d_codes;
+        layers.push_back({d_parent, nparents});
+        n = nparents;
+    }
+    // root first
     const size_t nl = layers.size();
     std::vector<uint64_t> bounds(nl + 1, 0);
-    for (size_t l = 0; l < nl; l++) bounds[l + 1] = bounds[l] + layers[nl - 1 - l].size() / 4;
-    out.nodes.resize(bounds[nl] * 4);
+    for (size_t l = 0; l < nl; l++) bounds[l + 1] = bounds[l] + layers[nl - 1 - l].n;
+    if (bounds[nl] >= (1ull << 28)) { cleanup(); return fail(CB_ERR_INVALID, "cb_bvh_build: %llu nodes exceed the 28-bit child field", (unsigned long long)bounds[nl]); }
+    BL(cudaMalloc(&d_final, bounds[nl] * sizeof(uint4)));
     for (size_t l = 0; l < nl; l++) {
-        const std::vector<uint32_t>& src = layers[nl - 1 - l];
-        uint32_t* dst = &out.nodes[bounds[l] * 4];
-        memcpy(dst, src.data(), src.size() * 4);
-        if (l + 1 < nl) {
-            uint32_t off = (uint32_t)bounds[l + 1];
-            for (size_t i = 0; i < src.size() / 4; i++) {
-                uint32_t w = dst[4 * i + 3];
-                dst[4 * i + 3] = (w & 0xF0000000u) | ((w & 0x0FFFFFFFu) + off);
-            }
-        }
+        const DeviceLayer& L = layers[nl - 1 - l];
+        const uint32_t child_offset = (l + 1 < nl) ? (uint32_t)bounds[l + 1] : 0u;     // leaves point at triangles
+        place_layer_kernel<<<grid(L.n), 256, 0, st>>>(L.nodes, L.n, child_offset, d_final + bounds[l]);
     }
-    // collapse single-child chains bottom-up (leaf layer excluded)
-    for (size_t l = nl - 1; l-- > 0;) {
-        for (uint64_t i = bounds[l]; i < bounds[l + 1]; i++) {
-            uint32_t w = out.nodes[4 * i + 3];
-            if ((w >> 28) == 1) {
-                uint32_t c = w & 0x0FFFFFFFu;
-                memcpy(&out.nodes[4 * i], &out.nodes[4ull * c], 16);
-            }
-        }
-    }
+    for (size_t l = nl - 1; l-- > 0;)                       // every layer but the leaves, bottom up
+        collapse_layer_kernel<<<grid(bounds[l + 1] - bounds[l]), 256, 0, st>>>(d_final, bounds[l], bounds[l + 1]);
+    BL(cudaGetLastError());
+    out.nodes.resize(bounds[nl] * 4);
+    BL(cudaMemcpyAsync(out.nodes.data(), d_final, bounds[nl] * sizeof(uint4), cudaMemcpyDeviceToHost, st));
+    BL(stream_wait(st));
+#undef BL
     out.layer_offsets.assign(bounds.begin(), bounds.end() - 1);
+    cleanup();
+    return CB_OK;
 }
 
 } // namespace cb
@@ -787,19 +878,23 @@ extern "C" int cb_bvh_build(const float* vertices, uint64_t nvertices, const uin
     BV(cudaGetLastError());
     const unsigned long long* sorted_codes = in_alt ? d_codes2 : d_codes;
     const uint32_t* sorted_ids = in_alt ? d_ids2 : d_ids;
-    std::vector<uint64_t> codes(ntriangles);
-    std::vector<uint32_t> ids(ntriangles), leaves(ntriangles * 4), sorted(ntriangles * 4);
-    BV(cudaMemcpyAsync(codes.data(), sorted_codes, ntriangles * 8, cudaMemcpyDeviceToHost, c.stream));
-    BV(cudaMemcpyAsync(ids.data(), sorted_ids, ntriangles * 4, cudaMemcpyDeviceToHost, c.stream));
-    BV(cudaMemcpyAsync(leaves.data(), d_leaves, ntriangles * 16, cudaMemcpyDeviceToHost, c.stream));
+    // leaves into Morton order, then every layer above them, on the device; one read-back of the finished tree
+    uint4* d_sorted_leaves = nullptr;
+    BV(cudaMalloc(&d_sorted_leaves, ntriangles * 16));
+    gather_leaves_kernel<<<(unsigned)((ntriangles + 255) / 256), 256, 0, c.stream>>>(d_leaves, sorted_ids, ntriangles, d_sorted_leaves);
+    BV(cudaGetLastError());
+    unsigned long long* d_level_codes = nullptr;      // build_layers_device swaps and frees code arrays of its own
+    BV(cudaMalloc(&d_level_codes, ntriangles * 8));
+    BV(cudaMemcpyAsync(d_level_codes, sorted_codes, ntriangles * 8, cudaMemcpyDeviceToDevice, c.stream));
     BV(stream_wait(c.stream));
 #undef BV
     cleanup();
-    for (uint64_t i = 0; i < ntriangles; i++) memcpy(&sorted[4 * i], &leaves[4ull * ids[i]], 16);
-    leaves.clear(); leaves.shrink_to_fit();
-
     g_bvh = BvhResult();
-    build_layers(sorted, codes, target_degree, g_bvh);
+    {
+        const int rc = build_layers_device(d_sorted_leaves, d_level_codes, ntriangles, target_degree, g_bvh);
+        cudaFree(d_sorted_leaves);
+        if (rc != CB_OK) { g_bvh = BvhResult(); return rc; }
+    }
     memcpy(g_bvh.origin, lo, 12);
     g_bvh.scale = scale;
     g_bvh.valid = true;
