@@ -377,8 +377,21 @@ __device__ __forceinline__ void phased_ray_axis(float o, float d, float worigin,
         const float e = 6e-7f * c + 3e-7f * fabsf(b);
         n = off - e; f = off + e;
         sel = (inv >= 0.0f) ? 0x7610u : 0x7632u;   // low half first when the ray runs towards +axis
-    } else {                                       // the reference skips such an axis (intersect.h:120)
-        s = 0.0f; n = -INF; f = INF; sel = 0x7610u;
+    } else {
+        // The ray runs parallel to this axis' planes (d == 0 exactly: 3e-8 of the isotropic directions drawn by
+        // rng_sphere are (0, 0, +-1)).  The reference skips such an axis (intersect.h:120) and therefore enters every
+        // box that lies in the ray's way on the OTHER axes, wherever it is on this one: for a ray along z that is a
+        // slab through the whole detector -- 164 ms for one photon in the 37 M-triangle detector, the straggler event
+        // of the 8-GPU runs of round 2.  A triangle can only be hit if its extent on this axis contains the ray, so
+        // the axis still culls here: with the planes scaled by BIG, "the ray is inside the slab (+- 8 grid quanta,
+        // far more than the triangle test's rounding)" becomes tnear = -huge, tfar = +huge, "outside" becomes
+        // tnear = +huge or tfar = -huge.  Same hits (the triangle test decides), found in microseconds.
+        const float BIG = 1e30f;
+        const float xq = (o - worigin) / wscale;   // where the ray is, in grid quanta
+        s = BIG; sel = 0x7610u;
+        n = -(8388608.0f + xq + 8.0f) * BIG;
+        f = -(8388608.0f + xq - 8.0f) * BIG;
+        (void)INF;
     }
 }
 __device__ __forceinline__ bool hit_box_phased(const PhasedRay& r, uint32_t px, uint32_t py, uint32_t pz, float& tnear)

@@ -149,3 +149,30 @@ def test_untraceable_rays_report_no_hit(gpu_ready):
     good[list(bad)] = False
     assert (tri[list(bad)] == -1).all()
     assert np.array_equal(tri[good], tri0[good]) and np.array_equal(dist[good].view(np.uint32), dist0[good].view(np.uint32))
+
+
+def test_rays_along_an_axis_do_not_walk_the_whole_slab(gpu_ready, monkeypatch):
+    """d == 0 on an axis: the reference skips that axis in its box test (intersect.h:120) and so enters every box in
+    the ray's way on the other axes -- for a photon reflected exactly along z (3e-8 of rng_sphere's directions) a slab
+    through the whole detector: 164 ms for ONE photon in the 29k-PMT detector, the 8-GPU straggler of round 2.  The
+    engine still culls on such an axis (phased_ray_axis); hits are the same (bit-exact test above), the work is not."""
+    monkeypatch.setenv('CHROMA_B200_STATS', '1')
+    geo = scenes.ref_tiny_detector()
+    g = gpu.GPUDetector(geo)
+    n = 4096
+    rng = np.random.default_rng(5)
+    from chroma_lite_b200 import event
+    pos = rng.uniform(-1500, 1500, (n, 3)).astype(np.float32)
+    work = {}
+    for name, d in (('random', None), ('along z', (0.0, 0.0, 1.0)), ('along -x', (-1.0, 0.0, 0.0)), ('in the yz plane', (0.0, 0.6, 0.8))):
+        dirs = scenes.point_source(n, seed=8).dir if d is None else np.tile(np.asarray(d, np.float32), (n, 1))
+        pol = np.cross(dirs, (0.3, 0.5, 0.81))
+        pol /= np.linalg.norm(pol, axis=1)[:, None]
+        ph = event.Photons(pos, dirs, pol.astype(np.float32), np.full(n, 400.0, np.float32))
+        gp = gpu.GPUPhotons(ph)
+        gp.propagate(g, gpu.get_rng_states(n, seed=2), nthreads_per_block=256, max_blocks=16, max_steps=1)
+        st = gp.last_stats
+        work[name] = st.nodes_visited / float(st.steps)
+    print(work)
+    for name in ('along z', 'along -x', 'in the yz plane'):
+        assert work[name] < 2.0 * work['random'], work
