@@ -440,7 +440,7 @@ def run_ours(args):
     # out (Simulation.simulate, batches double-buffered); every event's photons also add to ONE run-level
     # acquisition per rank, and the ranks' run-level accumulators are combined at the end with the
     # library's NCCL all-reduce (cb_daq_allreduce: MIN time, SUM charge, OR history), inside the timed region
-    h2d = sum(getattr(ev, f).nbytes for f in ('pos', 'dir', 'pol', 'wavelengths', 't', 'flags', 'evidx'))
+    h2d = sum(getattr(ev, f).nbytes for f in ('pos', 'dir', 'pol', 'wavelengths', 't', 'flags'))   # evidx of a one-event batch is filled on the device
     sim_kw = dict(keep_hits=False, keep_flat_hits=True, run_daq=True, max_steps=MAX_STEPS, photons_per_batch=n)
     # the event's host arrays live in page-locked memory (gpu.pagelocked_empty, the role of
     # pycuda's pagelocked_empty in the reference): every step uploads them again, host -> device
@@ -464,7 +464,8 @@ def run_ours(args):
         fh = out_ev.flat_hits
         d2h = sum(getattr(fh, f).nbytes for f in fields) + fh.channel.nbytes + 3 * 4 * nch
         # run-level: the event's per-channel result folds into the rank's accumulators on the device
-        run_daq.fold(s.gpu_daq)
+        # (enqueued behind the batch the GPU is working on; the all-reduce below is ordered after it)
+        run_daq.fold(s.gpu_daq, wait=False)
         t_prev = time.perf_counter()
     t_loop = time.perf_counter() - t0
     run_channels = run_daq.allreduce().get()        # one NCCL exchange over NVLink + read-back (3 x 4 B x channels)
@@ -477,7 +478,8 @@ def run_ours(args):
     # every rank's view of its pipeline (where an end-to-end slowdown at large N comes from)
     mine = {'rank': rank, 'device_ms_per_event': per_event_ms, 'pci_bus_id': pci.value.decode(), 'e2e_s': my_e2e_s, 'loop_s': t_loop, 'allreduce_and_readback_s': my_e2e_s - t_loop,
             'last_batch': dict(s.last_timings), 'yield_gap_ms_median': float(np.median(gaps)) * 1e3,
-            'yield_gap_ms_max': float(np.max(gaps)) * 1e3, 'affinity_cores': len(os.sched_getaffinity(0))}
+            'yield_gap_ms_max': float(np.max(gaps)) * 1e3, 'affinity_cores': len(os.sched_getaffinity(0)),
+            'numa_bound': _lib.numa_cores is not None}
     per_rank = [mine]
     if world > 1:
         import torch.distributed as dist

@@ -116,14 +116,21 @@ SIGNATURES = {
     'cb_count_photon_hits': (C.c_int, [_P(CbPhotonBank), u64, u64, u32, u64, _P(u32)]),
     'cb_copy_photon_hits': (C.c_int, [_P(CbPhotonBank), u64, u64, u32, u64, _P(CbPhotonBank), vp, _P(u32)]),
     'cb_copy_photon_queue': (C.c_int, [_P(CbPhotonBank), vp, u64, _P(CbPhotonBank)]),
+    'cb_copy_photon_hits_async': (C.c_int, [_P(CbPhotonBank), u64, u64, u32, u64, vp, vp]),
+    'cb_event_create': (C.c_int, [_P(u64)]),
+    'cb_event_record': (C.c_int, [u64]),
+    'cb_event_wait': (C.c_int, [u64]),
+    'cb_event_destroy': (C.c_int, [u64]),
     'cb_daq_create': (C.c_int, [u64, i32, _P(u64)]),
     'cb_daq_destroy': (C.c_int, [u64]),
     'cb_daq_begin_acquire': (C.c_int, [u64]),
     'cb_daq_acquire': (C.c_int, [u64, _P(CbPhotonBank), u64, i32, i32, u64, u64, f32]),
     'cb_daq_end_acquire': (C.c_int, [u64]),
+    'cb_daq_acquire_async': (C.c_int, [u64, _P(CbPhotonBank), u64, i32, i32, u64, u64, f32, i32, i32]),
     'cb_daq_pointers': (C.c_int, [u64, _P(vp), _P(vp), _P(vp), _P(vp), _P(vp), _P(u64)]),
     'cb_daq_finalize': (C.c_int, [u64]),
     'cb_daq_fold': (C.c_int, [u64, u64]),
+    'cb_daq_fold_async': (C.c_int, [u64, u64]),
     'cb_comm_unique_id': (C.c_int, [vp]),
     'cb_comm_init': (C.c_int, [i32, i32, vp]),
     'cb_comm_destroy': (C.c_int, []),
@@ -140,6 +147,7 @@ SIGNATURES = {
 
 _lib = None
 _device = None
+numa_cores = None        # cores this process was bound to at init() (parallel.bind_to_gpu_numa_node), or None
 
 
 class ChromaB200Error(RuntimeError):
@@ -186,6 +194,13 @@ def init(device=None):
                               'There is no CPU fallback.')
     check(lib.cb_init(int(device)))
     _device = int(device)
+    # several ranks on one host: stay on the cores (and so the memory) next to this rank's GPU
+    if int(os.environ.get('LOCAL_WORLD_SIZE', os.environ.get('WORLD_SIZE', '1')) or 1) > 1 or os.environ.get('CHROMA_B200_NUMA') == '1':
+        from . import parallel
+        buf = C.create_string_buffer(32)
+        if lib.cb_device_pci_bus_id(buf, 32) == 0:
+            global numa_cores
+            numa_cores = parallel.bind_to_gpu_numa_node(buf.value.decode())
     return _device
 
 

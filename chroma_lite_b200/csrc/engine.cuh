@@ -133,6 +133,14 @@ struct TraverseCounters { uint32_t nodes, tris, resolved; };
 // reference (SASS of intersect_triangle in oracle/_ref: cross = fma(a.y,b.z,-(a.z*b.y)),
 // dot = fma(a.z,b.z,fma(a.x,b.x,a.y*b.y)), and u+v contracted to fma(f,dot(s,h),v)),
 // because rays aimed at shared edges/vertices sit right on the +-1e-6 tolerances.
+// The reference's excursions into double are reproduced in float, bit for bit, at a third of the
+// instructions (no F2F / MUFU.RCP64H / 5 DFMA / 6 DSETP per test):
+//   * f = (float)(1.0 / (double)a) is the correctly rounded float reciprocal: rounding a quotient to 53
+//     bits and then to 24 is innocuous when 53 >= 2*24 + 2 (Figueroa), so __frcp_rn(a) is the same float
+//     (checked on 10^8 random floats, and by the full-size parity tests against the reference kernel);
+//   * (double)u < -1e-6 holds for exactly the floats below the float nearest to -1e-6 (which lies above
+//     it), and likewise t > 1e-6 and u > 1.0 + 1e-6 for the floats above the nearest floats (which lie
+//     below): the comparisons against the float-rounded constants select the same floats.
 __device__ __forceinline__ float3 cross_pinned(const float3& a, const float3& b)
 {
     return f3(__fmaf_rn(a.y, b.z, -__fmul_rn(a.z, b.y)), __fmaf_rn(a.z, b.x, -__fmul_rn(a.x, b.z)),
@@ -142,6 +150,9 @@ __device__ __forceinline__ float dot_pinned(const float3& a, const float3& b)
 {
     return __fmaf_rn(a.z, b.z, __fmaf_rn(a.x, b.x, __fmul_rn(a.y, b.y)));
 }
+#ifndef CB_TRI_DOUBLE
+#define CB_TRI_DOUBLE 0      /* 1: the reference's literal mixed-precision expressions (A/B and bisecting aid) */
+#endif
 __device__ __forceinline__ bool hit_triangle(const float3& origin, const float3& direction,
                                              const float3& v0, const float3& v1, const float3& v2,
                                              float& distance)
@@ -151,17 +162,23 @@ __device__ __forceinline__ bool hit_triangle(const float3& origin, const float3&
     const float3 h = cross_pinned(direction, edge2);
     const float a = dot_pinned(edge1, h);
     if (a > -FLT_EPSILON && a < FLT_EPSILON) return false;
+#if CB_TRI_DOUBLE
     const float f = 1.0 / a;
+    const double LO = -1e-6, HI = 1.0 + 1e-6, TMIN = 1e-6;
+#else
+    const float f = __frcp_rn(a);
+    const float LO = -1e-6f, HI = (float)(1.0 + 1e-6), TMIN = 1e-6f;
+#endif
     const float3 s = f3(__fadd_rn(origin.x, -v0.x), __fadd_rn(origin.y, -v0.y), __fadd_rn(origin.z, -v0.z));
     const float sh = dot_pinned(s, h);
     const float u = __fmul_rn(f, sh);
-    if (u < -1e-6 || u > 1.0 + 1e-6) return false;
+    if (u < LO || u > HI) return false;
     const float3 q = cross_pinned(s, edge1);
     const float v = __fmul_rn(f, dot_pinned(direction, q));
     const float upv = __fmaf_rn(f, sh, v);
-    if (v < -1e-6 || upv > 1.0 + 1e-6) return false;
+    if (v < LO || upv > HI) return false;
     const float t = __fmul_rn(f, dot_pinned(edge2, q));
-    if (t > 1e-6 && t < __int_as_float(0x7f800000)) {
+    if (t > TMIN && t < __int_as_float(0x7f800000)) {
         distance = t;
         return true;
     }

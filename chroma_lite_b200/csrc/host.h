@@ -50,6 +50,8 @@ int fail(int code, const char* fmt, ...);
 // cudaEventBlockingSync event so that many ranks / pipeline threads can share few cores
 cudaError_t stream_wait(cudaStream_t s);
 cudaError_t event_wait(cudaEvent_t e);
+// p[0..count) = value on stream s (kernel launch only)
+void fill32_launch(uint32_t* p, uint32_t value, uint64_t count, cudaStream_t s);
 int cuda_fail(cudaError_t e, const char* what);
 
 #define CB_CUDA(call)                                                         \

@@ -866,7 +866,24 @@ tile_scan_kernel(uint32_t* counts, uint32_t ntiles)
     if (threadIdx.x == 0) counts[ntiles] = carry;
 }
 
-template <bool HITS>
+// PACKED: the destination is ONE block holding the ten hit arrays back to back, each as long as the
+// number of hits (words per hit 3,3,3,1,1,1,1,1,1 + channel; the layout GPUPhotons.get_flat_hits reads back in
+// one copy).  The total is only known on the device (tile_offsets[ntiles]), so the array bases are derived
+// here: the host enqueues count, scan and scatter without reading anything back in between.
+__device__ __forceinline__ CbPhotonBank packed_hit_bank(uint32_t* block, uint64_t total, int32_t** channels)
+{
+    const uint64_t m = total ? total : 1;
+    CbPhotonBank d;
+    float* f = reinterpret_cast<float*>(block);
+    d.pos = f; d.dir = f + 3 * m; d.pol = f + 6 * m; d.wavelengths = f + 9 * m; d.t = f + 10 * m;
+    d.last_hit_triangles = reinterpret_cast<int32_t*>(block + 11 * m);
+    d.flags = block + 12 * m; d.weights = f + 13 * m; d.evidx = block + 14 * m;
+    d.n = total;
+    *channels = reinterpret_cast<int32_t*>(block + 15 * m);
+    return d;
+}
+
+template <bool HITS, bool PACKED = false>
 __global__ void __launch_bounds__(256)
 tile_scatter_kernel(CbPhotonBank src, uint64_t first, uint64_t n, uint32_t flag, const uint32_t* solid_map,
                     const int32_t* solid_to_channel, const uint32_t* tile_offsets, CbPhotonBank dst,
@@ -874,6 +891,7 @@ tile_scatter_kernel(CbPhotonBank src, uint64_t first, uint64_t n, uint32_t flag,
 {
     __shared__ uint32_t warp_base[8];
     __shared__ uint32_t running;
+    if (PACKED) dst = packed_hit_bank(reinterpret_cast<uint32_t*>(dst.pos), tile_offsets[gridDim.x], &channels_out);
     if (threadIdx.x == 0) running = tile_offsets[blockIdx.x];
     __syncthreads();
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1459,6 +1477,36 @@ int cb_copy_photon_hits(const CbPhotonBank* src, uint64_t first, uint64_t n, uin
     if (!d_channels_out) return fail(CB_ERR_INVALID, "cb_copy_photon_hits: null channel array");
     return compact<true>(src, first, n, flag, g, dst, d_channels_out, count_out);
 }
+int cb_copy_photon_hits_async(const CbPhotonBank* src, uint64_t first, uint64_t n, uint32_t flag, cb_geom_t gh,
+                              uint32_t* d_block, uint32_t* d_count_out)
+{
+    CB_REQUIRE_INIT();
+    CB_SERIALISE();
+    int rc = check_bank(src, "cb_copy_photon_hits_async");
+    if (rc) return rc;
+    Geometry* g = geoms().get(gh);
+    if (!g || !g->solid_to_channel) return fail(CB_ERR_INVALID, "cb_copy_photon_hits_async: geometry has no detector attached");
+    if (!d_block || !d_count_out) return fail(CB_ERR_INVALID, "cb_copy_photon_hits_async: null output");
+    if (first + n > src->n) return fail(CB_ERR_INVALID, "cb_copy_photon_hits_async: range exceeds the photon bank");
+    Context& c = ctx();
+    if (n == 0) {
+        CB_CUDA(cudaMemsetAsync(d_count_out, 0, 4, c.stream));
+        return CB_OK;
+    }
+    const uint64_t ntiles = (n + TILE - 1) / TILE;
+    if ((rc = ensure_tile_scratch(ntiles))) return rc;
+    CbPhotonBank dst;
+    memset(&dst, 0, sizeof(dst));
+    dst.pos = reinterpret_cast<float*>(d_block);           // the kernel derives the ten array bases from the total
+    tile_count_kernel<true><<<(unsigned)ntiles, 256, 0, c.stream>>>(*src, first, n, flag, g->solid_id, g->solid_to_channel,
+                                                                    c.d_block_counts);
+    tile_scan_kernel<<<1, 1024, 0, c.stream>>>(c.d_block_counts, (uint32_t)ntiles);
+    tile_scatter_kernel<true, true><<<(unsigned)ntiles, 256, 0, c.stream>>>(*src, first, n, flag, g->solid_id, g->solid_to_channel,
+                                                                            c.d_block_counts, dst, nullptr);
+    CB_CUDA(cudaGetLastError());
+    CB_CUDA(cudaMemcpyAsync(d_count_out, c.d_block_counts + ntiles, 4, cudaMemcpyDeviceToDevice, c.stream));
+    return CB_OK;
+}
 int cb_copy_photon_queue(const CbPhotonBank* src, const uint32_t* d_queue, uint64_t n, const CbPhotonBank* dst)
 {
     CB_REQUIRE_INIT();
@@ -1517,12 +1565,9 @@ int cb_daq_destroy(cb_daq_t h)
     delete d;
     return CB_OK;
 }
-int cb_daq_begin_acquire(cb_daq_t h)
+// launch-only pieces of an acquisition (library stream, no host wait); the entry points below add the waits
+static int daq_begin_launch(Daq* d)
 {
-    CB_REQUIRE_INIT();
-    CB_SERIALISE();
-    Daq* d = daqs().get(h);
-    if (!d) return fail(CB_ERR_INVALID, "cb_daq_begin_acquire: bad handle");
     Context& c = ctx();
     const float maxtime = 1e9f;   // gpu/daq.py:56
     uint32_t bits;
@@ -1530,18 +1575,13 @@ int cb_daq_begin_acquire(cb_daq_t h)
     CB_CUDA(cudaMemsetAsync(d->channel_q_int, 0, d->count * 4, c.stream));
     CB_CUDA(cudaMemsetAsync(d->channel_q, 0, d->count * 4, c.stream));
     CB_CUDA(cudaMemsetAsync(d->channel_history, 0, d->count * 4, c.stream));
-    CB_CUDA(stream_wait(c.stream));
-    return cb_memset32(d->earliest_time_int, bits, d->count);
+    fill32_launch(d->earliest_time_int, bits, d->count, c.stream);
+    CB_CUDA(cudaGetLastError());
+    return CB_OK;
 }
-int cb_daq_acquire(cb_daq_t h, const CbPhotonBank* bank, cb_rng_t rh, int32_t nthreads_per_block,
-                   int32_t max_blocks, uint64_t start_photon, uint64_t nphotons, float weight)
+static int daq_acquire_launch(Daq* d, const CbPhotonBank* bank, RngPool* r, int32_t nthreads_per_block, int32_t max_blocks,
+                              uint64_t start_photon, uint64_t nphotons, float weight)
 {
-    CB_REQUIRE_INIT();
-    CB_SERIALISE();
-    Daq* d = daqs().get(h);
-    RngPool* r = rngs().get(rh);
-    if (!d) return fail(CB_ERR_INVALID, "cb_daq_acquire: bad daq handle");
-    if (!r) return fail(CB_ERR_INVALID, "cb_daq_acquire: bad rng handle");
     int rc = check_bank(bank, "cb_daq_acquire");
     if (rc) return rc;
     if (start_photon + nphotons > bank->n) return fail(CB_ERR_INVALID, "cb_daq_acquire: photon range exceeds bank");
@@ -1580,7 +1620,55 @@ int cb_daq_acquire(cb_daq_t h, const CbPhotonBank* bank, cb_rng_t rh, int32_t nt
             CB_CUDA(cudaGetLastError());
         }
     }
-    CB_CUDA(stream_wait(c.stream));
+    return CB_OK;
+}
+static int daq_finalize_launch(Daq* d)
+{
+    Context& c = ctx();
+    daq_finalize_kernel<<<(unsigned)((d->count + 255) / 256), 256, 0, c.stream>>>(
+        d->count, d->earliest_time_int, d->channel_q_int, d->geom->charge_unit, d->earliest_time, d->channel_q);
+    CB_CUDA(cudaGetLastError());
+    return CB_OK;
+}
+int cb_daq_begin_acquire(cb_daq_t h)
+{
+    CB_REQUIRE_INIT();
+    CB_SERIALISE();
+    Daq* d = daqs().get(h);
+    if (!d) return fail(CB_ERR_INVALID, "cb_daq_begin_acquire: bad handle");
+    int rc = daq_begin_launch(d);
+    if (rc) return rc;
+    CB_CUDA(stream_wait(ctx().stream));
+    return CB_OK;
+}
+int cb_daq_acquire(cb_daq_t h, const CbPhotonBank* bank, cb_rng_t rh, int32_t nthreads_per_block,
+                   int32_t max_blocks, uint64_t start_photon, uint64_t nphotons, float weight)
+{
+    CB_REQUIRE_INIT();
+    CB_SERIALISE();
+    Daq* d = daqs().get(h);
+    RngPool* r = rngs().get(rh);
+    if (!d) return fail(CB_ERR_INVALID, "cb_daq_acquire: bad daq handle");
+    if (!r) return fail(CB_ERR_INVALID, "cb_daq_acquire: bad rng handle");
+    int rc = daq_acquire_launch(d, bank, r, nthreads_per_block, max_blocks, start_photon, nphotons, weight);
+    if (rc) return rc;
+    CB_CUDA(stream_wait(ctx().stream));
+    return CB_OK;
+}
+int cb_daq_acquire_async(cb_daq_t h, const CbPhotonBank* bank, cb_rng_t rh, int32_t nthreads_per_block,
+                         int32_t max_blocks, uint64_t start_photon, uint64_t nphotons, float weight,
+                         int32_t begin, int32_t finalize)
+{
+    CB_REQUIRE_INIT();
+    CB_SERIALISE();
+    Daq* d = daqs().get(h);
+    RngPool* r = rngs().get(rh);
+    if (!d) return fail(CB_ERR_INVALID, "cb_daq_acquire_async: bad daq handle");
+    if (!r) return fail(CB_ERR_INVALID, "cb_daq_acquire_async: bad rng handle");
+    int rc = CB_OK;
+    if (begin && (rc = daq_begin_launch(d))) return rc;
+    if ((rc = daq_acquire_launch(d, bank, r, nthreads_per_block, max_blocks, start_photon, nphotons, weight))) return rc;
+    if (finalize && (rc = daq_finalize_launch(d))) return rc;
     return CB_OK;
 }
 int cb_daq_finalize(cb_daq_t h)
@@ -1589,11 +1677,9 @@ int cb_daq_finalize(cb_daq_t h)
     CB_SERIALISE();
     Daq* d = daqs().get(h);
     if (!d) return fail(CB_ERR_INVALID, "cb_daq_finalize: bad handle");
-    Context& c = ctx();
-    daq_finalize_kernel<<<(unsigned)((d->count + 255) / 256), 256, 0, c.stream>>>(
-        d->count, d->earliest_time_int, d->channel_q_int, d->geom->charge_unit, d->earliest_time, d->channel_q);
-    CB_CUDA(cudaGetLastError());
-    CB_CUDA(stream_wait(c.stream));
+    int rc = daq_finalize_launch(d);
+    if (rc) return rc;
+    CB_CUDA(stream_wait(ctx().stream));
     return CB_OK;
 }
 int cb_daq_end_acquire(cb_daq_t h) { return cb_daq_finalize(h); }
@@ -1610,6 +1696,20 @@ int cb_daq_fold(cb_daq_t dst, cb_daq_t src)
         b->channel_history);
     CB_CUDA(cudaGetLastError());
     CB_CUDA(stream_wait(c.stream));
+    return CB_OK;
+}
+int cb_daq_fold_async(cb_daq_t dst, cb_daq_t src)
+{
+    // Enqueue only, and without the library lock: the launch touches nothing but the two accumulators, and a
+    // caller that consumes event k while the pipeline propagates event k+1 must not wait for that call to return.
+    CB_REQUIRE_INIT();
+    Daq* a = daqs().get(dst);
+    Daq* b = daqs().get(src);
+    if (!a || !b || a->count != b->count) return fail(CB_ERR_INVALID, "cb_daq_fold_async: bad or mismatched handles");
+    daq_fold_into_kernel<<<(unsigned)((a->count + 255) / 256), 256, 0, ctx().stream>>>(
+        a->count, a->earliest_time_int, b->earliest_time_int, a->channel_q_int, b->channel_q_int, a->channel_history,
+        b->channel_history);
+    CB_CUDA(cudaGetLastError());
     return CB_OK;
 }
 int cb_daq_pointers(cb_daq_t h, void** t, void** q, void** flags, void** time_int, void** q_int, uint64_t* count)

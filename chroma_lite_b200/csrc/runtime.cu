@@ -235,6 +235,13 @@ __global__ void fill32_kernel(uint32_t* p, uint32_t v, uint64_t n)
     for (; i < n; i += stride) p[i] = v;
 }
 
+void fill32_launch(uint32_t* p, uint32_t value, uint64_t count, cudaStream_t s)
+{
+    if (!count) return;
+    const int blocks = (int)std::min<uint64_t>((count + 255) / 256, (uint64_t)ctx().sm_count * 16);
+    fill32_kernel<<<blocks, 256, 0, s>>>(p, value, count);
+}
+
 } // namespace cb
 
 using namespace cb;
@@ -397,6 +404,49 @@ int cb_mem_info(uint64_t* free_bytes, uint64_t* total_bytes)
     CB_CUDA(cudaMemGetInfo(&f, &t));
     if (free_bytes) *free_bytes = f;
     if (total_bytes) *total_bytes = t;
+    return CB_OK;
+}
+
+// ---------------------------------------------------------------- completion events
+// For callers that enqueue work with the *_async entry points: a marker on the library stream and a host
+// wait for it.  The wait naps between polls (the waiter is off the critical path by construction: it
+// consumes event k while the GPU works on event k+1), so it never occupies a core.
+int cb_event_create(cb_event_t* out)
+{
+    CB_REQUIRE_INIT();
+    if (!out) return fail(CB_ERR_INVALID, "cb_event_create: null out pointer");
+    cudaEvent_t e = nullptr;
+    CB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    *out = (cb_event_t)(uintptr_t)e;
+    return CB_OK;
+}
+int cb_event_record(cb_event_t ev)
+{
+    CB_REQUIRE_INIT();
+    if (!ev) return fail(CB_ERR_INVALID, "cb_event_record: null event");
+    CB_CUDA(cudaEventRecord((cudaEvent_t)(uintptr_t)ev, ctx().stream));
+    return CB_OK;
+}
+int cb_event_wait(cb_event_t ev)
+{
+    CB_REQUIRE_INIT();
+    if (!ev) return fail(CB_ERR_INVALID, "cb_event_wait: null event");
+    const cudaEvent_t e = (cudaEvent_t)(uintptr_t)ev;
+    const double t0 = now_us();
+    for (;;) {
+        const cudaError_t q = cudaEventQuery(e);
+        if (q == cudaSuccess) return CB_OK;
+        if (q != cudaErrorNotReady) return cuda_fail(q, "cudaEventQuery");
+        if (now_us() - t0 > 20.0) {
+            struct timespec ts = {0, 40000};      // 40 us
+            nanosleep(&ts, nullptr);
+        }
+    }
+}
+int cb_event_destroy(cb_event_t ev)
+{
+    CB_REQUIRE_INIT();
+    if (ev) CB_CUDA(cudaEventDestroy((cudaEvent_t)(uintptr_t)ev));
     return CB_OK;
 }
 

@@ -56,14 +56,31 @@ class GPUDaq(object):
         _lib.check(_lib.lib().cb_daq_acquire(self.handle, C.byref(bank), rng_states.handle, int(nthreads_per_block),
                                              int(max_blocks), int(start_photon), int(nphotons), float(weight)))
 
+    def acquire_async(self, gpuphotons, rng_states, nthreads_per_block=64, max_blocks=1024, start_photon=None,
+                      nphotons=None, weight=1.0, begin=True, finalize=True):
+        """begin_acquire + acquire + end_acquire of one acquisition, only enqueued on the library
+        stream (the simulation pipeline's form); returns the GPUChannels, valid once a marker recorded
+        behind this call has been waited for."""
+        start_photon = 0 if start_photon is None else start_photon
+        nphotons = len(gpuphotons.pos) - start_photon if nphotons is None else nphotons
+        bank = gpuphotons._bank()
+        _lib.check(_lib.lib().cb_daq_acquire_async(self.handle, C.byref(bank), rng_states.handle, int(nthreads_per_block),
+                                                   int(max_blocks), int(start_photon), int(nphotons), float(weight),
+                                                   int(bool(begin)), int(bool(finalize))))
+        return GPUChannels(self.earliest_time_gpu, self.channel_q_gpu, self.channel_history_gpu, self.ndaq, self.stride)
+
     def end_acquire(self, nthreads_per_block=64):
         _lib.check(_lib.lib().cb_daq_end_acquire(self.handle))
         return GPUChannels(self.earliest_time_gpu, self.channel_q_gpu, self.channel_history_gpu, self.ndaq, self.stride)
 
-    def fold(self, other):
+    def fold(self, other, wait=True):
         """Merge another GPUDaq's accumulators into this one on the device (MIN time, SUM charge, OR
-        history): per-event acquisitions into run-level accumulators."""
-        _lib.check(_lib.lib().cb_daq_fold(self.handle, other.handle))
+        history): per-event acquisitions into run-level accumulators.  wait=False only enqueues the
+        merge (ordered on the library stream, so a later allreduce() / end_acquire() sees it)."""
+        if wait:
+            _lib.check(_lib.lib().cb_daq_fold(self.handle, other.handle))
+        else:
+            _lib.check(_lib.lib().cb_daq_fold_async(self.handle, other.handle))
 
     def allreduce(self):
         """Combine the accumulators of every rank (MIN time, SUM charge, OR history) with one

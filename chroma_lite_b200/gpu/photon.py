@@ -57,9 +57,10 @@ def _alloc_bank(n):
 
 
 class GPUPhotons(object):
-    def __init__(self, photons, ncopies=1, copy_flags=True, copy_triangles=True, copy_weights=True):
+    def __init__(self, photons, ncopies=1, copy_flags=True, copy_triangles=True, copy_weights=True, evidx_value=None):
         """Load ``photons`` onto the GPU, replicating ``ncopies`` times
-        (chroma/gpu/photon.py:14-116)."""
+        (chroma/gpu/photon.py:14-116).  ``evidx_value`` (extension): every photon belongs to this event
+        of its batch -- the array is filled on the device instead of being uploaded."""
         nphotons = _resolve_nphotons(photons)
         total = nphotons * ncopies
         self.pos = ga.empty(total, ga.vec.float3)
@@ -92,8 +93,11 @@ class GPUPhotons(object):
 
         if nphotons:
             jobs = [(put_vec, self.pos, photons.pos), (put_vec, self.dir, photons.dir), (put_vec, self.pol, photons.pol),
-                    (put, self.wavelengths, photons.wavelengths, np.float32), (put, self.t, photons.t, np.float32),
-                    (put, self.evidx, photons.evidx, np.uint32)]
+                    (put, self.wavelengths, photons.wavelengths, np.float32), (put, self.t, photons.t, np.float32)]
+            if evidx_value is None:
+                jobs.append((put, self.evidx, photons.evidx, np.uint32))
+            else:
+                jobs.append((lambda dest, value: dest[:nphotons].fill(np.uint32(value)), self.evidx, evidx_value))
             if copy_triangles:
                 jobs.append((put, self.last_hit_triangles, photons.last_hit_triangles, np.int32))
             if copy_flags:
@@ -173,6 +177,21 @@ class GPUPhotons(object):
         return event.Photons(vec3(0), vec3(1), vec3(2), part(3, np.float32), part(4, np.float32), part(5, np.int32),
                              part(6, np.uint32), part(7, np.float32), part(8, np.uint32), part(9, np.int32))
 
+    def flat_hits_async(self, gpu_detector, target_flag=(0x1 << 2), start_photon=None, nphotons=None):
+        """get_flat_hits in two halves for the simulation pipeline: this one only ENQUEUES the
+        compaction behind whatever is running on the library stream and returns a PendingHits; its
+        get() -- normally called by another thread while the GPU already works on the next batch --
+        waits for the completion marker and reads the hits back in one copy."""
+        lib = _lib.lib()
+        start_photon = 0 if start_photon is None else start_photon
+        nphotons = self.pos.size - start_photon if nphotons is None else nphotons
+        src = self._bank()
+        block = ga.empty(max(int(nphotons), 1) * 16 + 1, np.uint32)        # ten arrays of H hits + the count H
+        count_ptr = block.ptr + 4 * max(int(nphotons), 1) * 16
+        _lib.check(lib.cb_copy_photon_hits_async(C.byref(src), int(start_photon), int(nphotons), int(target_flag),
+                                                 gpu_detector.handle, block.ptr, count_ptr))
+        return PendingHits(block, count_ptr, self)
+
     def iterate_copies(self):
         for i in range(self.ncopies):
             w = slice(self.true_nphotons * i, self.true_nphotons * (i + 1))
@@ -251,6 +270,55 @@ class GPUPhotons(object):
 
     def __len__(self):
         return self.pos.size
+
+
+class Marker(object):
+    """Completion marker on the library stream (cb_event_*); reusable."""
+    def __init__(self):
+        h = C.c_uint64()
+        _lib.check(_lib.lib().cb_event_create(C.byref(h)))
+        self.handle = h.value
+
+    def record(self):
+        _lib.check(_lib.lib().cb_event_record(self.handle))
+        return self
+
+    def wait(self):
+        _lib.check(_lib.lib().cb_event_wait(self.handle))
+
+    def __del__(self):
+        try:
+            if getattr(self, 'handle', 0) and _lib._lib is not None:
+                _lib._lib.cb_event_destroy(self.handle)
+        except Exception:
+            pass
+        self.handle = 0
+
+
+class PendingHits(object):
+    """Hits being compacted on the device (GPUPhotons.flat_hits_async)."""
+    WORDS = (3, 3, 3, 1, 1, 1, 1, 1, 1, 1)             # 4-byte words per hit: _FIELDS + channel
+
+    def __init__(self, block, count_ptr, source):
+        self.block, self.count_ptr, self.source = block, count_ptr, source      # `source` keeps the bank alive
+
+    def get(self, marker=None):
+        """event.Photons of the hits (with .channel); `marker` must have been recorded behind the
+        compaction (the caller waits on it once for everything the batch enqueued)."""
+        if marker is not None:
+            marker.wait()
+        else:
+            _lib.check(_lib.lib().cb_synchronize())
+        cnt = np.zeros(1, np.uint32)
+        _lib.check(_lib.lib().cb_memcpy_d2h(cnt.ctypes.data, self.count_ptr, 4))
+        n = int(cnt[0])
+        host = self.block[:max(n, 1) * 16].get()
+        self.block = self.source = None
+        offs = np.concatenate([[0], np.cumsum(self.WORDS)]) * max(n, 1)
+        part = lambda i, dt: host[int(offs[i]):int(offs[i]) + n * self.WORDS[i]].view(dt)
+        vec3 = lambda i: part(i, np.float32).reshape((n, 3))
+        return event.Photons(vec3(0), vec3(1), vec3(2), part(3, np.float32), part(4, np.float32), part(5, np.int32),
+                             part(6, np.uint32), part(7, np.float32), part(8, np.uint32), part(9, np.int32))
 
 
 class GPUPhotonsSlice(GPUPhotons):

@@ -79,7 +79,10 @@ class Simulation(object):
                                                    copy_weights=False)
             if batch is None:
                 batch = event.Photons.join(sources)
-        gpu_photons = gpu.GPUPhotons(batch, copy_flags=True, copy_triangles=False, copy_weights=False)
+        # a batch of one event: its evidx is 0 throughout (simulate() has just written that into the host
+        # array too), so the device array is filled in place instead of crossing PCIe
+        gpu_photons = gpu.GPUPhotons(batch, copy_flags=True, copy_triangles=False, copy_weights=False,
+                                     evidx_value=0 if len(sources) == 1 and getattr(batch, 'evidx', None) is not None else None)
         return gpu_photons, bounds, time.perf_counter() - t0
 
     @staticmethod
@@ -114,13 +117,31 @@ class Simulation(object):
             stacked[f] = dest
         return SimpleNamespace(true_nphotons=total, **stacked)
 
+    # events per batch up to which the hit read-back and the DAQ of a batch are only ENQUEUED by the GPU stage
+    # and collected by the host stage (each event of a batch in flight holds its own per-channel arrays)
+    ASYNC_EVENTS_MAX = 8
+
+    def _daq_take(self):
+        """A GPUDaq for one event in flight (a small free list: created on demand, reused)."""
+        free = self.__dict__.setdefault('_daq_free', [])
+        return free.pop() if free else gpu.GPUDaq(self.gpu_geometry)
+
     def _gpu_stage(self, batch_events, uploaded=None, keep_photons_end=False, keep_hits=True, keep_flat_hits=True,
-                   run_daq=False, max_steps=100, verbose=False, **_unused):
+                   run_daq=False, max_steps=100, verbose=False, defer=False, **_unused):
         """Everything of one batch that needs the GPU, in the reference's order (chroma/sim.py:82-152):
         propagate, photons_end / flat-hit read-back, then one DAQ acquisition per event.  Returns the
         raw host arrays; building the Event objects from them (_host_stage) needs no GPU and overlaps
-        with the next batch's GPU stage."""
+        with the next batch's GPU stage.
+
+        defer=True (the pipeline of simulate()): hit compaction and DAQ are enqueued behind the propagate
+        kernels without a host round trip, a completion marker is recorded, and this thread goes straight
+        on to the next batch; _host_stage waits for the marker and reads the results back while the GPU
+        already propagates the next batch (the reference: count kernel, 4-byte read-back, copy kernel, ten
+        read-backs, DAQ kernels, three read-backs, all with the GPU otherwise idle)."""
         t0 = time.perf_counter()
+        if uploaded is not None and hasattr(uploaded, 'result'):
+            uploaded = uploaded.result()
+        t0b = time.perf_counter()
         gpu_photons, bounds, upload_s = uploaded if uploaded is not None else self._upload_batch(batch_events)
         t1 = time.perf_counter()
         raw = {'bounds': bounds}
@@ -136,10 +157,14 @@ class Simulation(object):
                                                 max_steps=max_steps, track=self.photon_tracking)
         t2 = time.perf_counter()
         is_detector = hasattr(self.detector, 'num_channels')
+        defer = defer and len(batch_events) <= self.ASYNC_EVENTS_MAX
         if keep_photons_end:
             raw['photons_end'] = gpu_photons.get()
         if is_detector and (keep_hits or keep_flat_hits):
-            raw['hits'] = gpu_photons.get_flat_hits(self.gpu_geometry)
+            if defer:
+                raw['pending_hits'] = gpu_photons.flat_hits_async(self.gpu_geometry)
+            else:
+                raw['hits'] = gpu_photons.get_flat_hits(self.gpu_geometry)
         t3 = time.perf_counter()
         if hasattr(self, 'gpu_daq') and run_daq:
             # one acquisition per event (chroma/sim.py:141-152).  run_daq='accumulate' (extension): the
@@ -147,21 +172,50 @@ class Simulation(object):
             # end_acquire() / allreduce() -- the run-level per-channel accumulators of a sharded run
             accumulate = run_daq == 'accumulate'
             if not accumulate:
-                raw['channels'] = []
+                raw['pending_channels' if defer else 'channels'] = []
             for start, end in zip(bounds[:-1], bounds[1:]):
                 ev_rng = rng.view(int(start), int(end - start)) if self.rng_per_photon and len(bounds) > 2 else rng
+                kw = dict(start_photon=int(start), nphotons=int(end - start), nthreads_per_block=self.nthreads_per_block,
+                          max_blocks=max_blocks)
+                if defer:
+                    daq = self.gpu_daq if accumulate else self._daq_take()
+                    ch = daq.acquire_async(gpu_photons, ev_rng, begin=not accumulate, finalize=not accumulate, **kw)
+                    if not accumulate:
+                        raw['pending_channels'].append((daq, ch))
+                    continue
                 if not accumulate:
                     self.gpu_daq.begin_acquire()
-                self.gpu_daq.acquire(gpu_photons, ev_rng, start_photon=int(start),
-                                     nphotons=int(end - start), nthreads_per_block=self.nthreads_per_block,
-                                     max_blocks=max_blocks)
+                self.gpu_daq.acquire(gpu_photons, ev_rng, **kw)
                 if not accumulate:
                     raw['channels'].append(self.gpu_daq.end_acquire().get())
+        if defer:
+            markers = self.__dict__.setdefault('_markers_free', [])
+            raw['marker'] = (markers.pop() if markers else gpu.Marker()).record()
+            raw['bank'] = gpu_photons          # in use by the enqueued kernels until the marker has passed
         t4 = time.perf_counter()
-        self.last_timings = {'upload_s': upload_s, 'propagate_s': t2 - t1, 'readback_s': t3 - t2, 'daq_s': t4 - t3,
-                             'nphotons': int(bounds[-1]), 'batch_total_s': t4 - t0}
+        self.last_timings = {'upload_s': upload_s, 'upload_wait_s': t0b - t0, 'propagate_s': t2 - t1, 'readback_s': t3 - t2,
+                             'daq_s': t4 - t3, 'nphotons': int(bounds[-1]), 'batch_total_s': t4 - t0, 'deferred': bool(defer)}
         if verbose:
             print('GPU copy took %0.2f s, propagate %0.2f s' % (t1 - t0, t2 - t1))
+        return raw
+
+    def _collect(self, raw):
+        """Second half of a deferred GPU stage: wait for the batch's marker, read hits and channels back."""
+        marker = raw.pop('marker', None)
+        if marker is None:
+            return raw
+        t0 = time.perf_counter()
+        marker.wait()
+        if 'pending_hits' in raw:
+            raw['hits'] = raw.pop('pending_hits').get(marker)
+        if 'pending_channels' in raw:
+            raw['channels'], raw['daqs'] = [], []
+            for daq, ch in raw.pop('pending_channels'):
+                raw['channels'].append(ch.get())
+                raw['daqs'].append(daq)
+        raw.pop('bank', None)
+        self._markers_free.append(marker)
+        self.last_timings = dict(self.last_timings, collect_s=time.perf_counter() - t0)
         return raw
 
     def _host_stage(self, batch_events, raw, keep_photons_beg=False, keep_photons_end=False, keep_hits=True,
@@ -194,7 +248,14 @@ class Simulation(object):
                     ev.flat_hits = ev_hits
             if 'channels' in raw:
                 ev.channels = raw['channels'][i]
+            if 'daqs' in raw:
+                # the event's per-channel arrays on the device: `gpu_daq` is the one of the event being
+                # yielded (what a caller folds into run-level accumulators), and goes back to the free list
+                # when the consumer comes back for the next event
+                self.gpu_daq = raw['daqs'][i]
             yield ev
+            if 'daqs' in raw:
+                self._daq_free.append(raw['daqs'][i])
 
     def _simulate_batch(self, batch_events, uploaded=None, **kw):
         raw = self._gpu_stage(batch_events, uploaded=uploaded, **kw)
@@ -235,38 +296,46 @@ class Simulation(object):
             if batch:
                 yield batch
 
-        # Three-stage pipeline, one batch per stage: a worker thread uploads batch k+1 on its copy
-        # stream, a second one runs the GPU stage of batch k (propagate, hit read-back, DAQ; the C
-        # calls release the GIL), and this thread turns the raw arrays of batch k-1 into events.
-        # GPU stages run strictly one after the other, so the RNG pool is consumed in the reference's
-        # order (propagate k, DAQ k, propagate k+1, ...).  The reference does upload -> propagate ->
-        # download strictly in sequence (sim.py:79-110).
+        # Pipeline, up to DEPTH batches in flight: a worker thread uploads batches on its copy stream as
+        # soon as they exist, a second one runs their GPU stages strictly one after the other (so the RNG
+        # pool is consumed in the reference's order: propagate k, DAQ k, propagate k+1, ...; the C calls
+        # release the GIL) and only ENQUEUES hit compaction and DAQ behind the propagate kernels, and this
+        # thread waits for a batch's completion marker, reads its results back and turns them into
+        # events -- while the GPU already propagates the next batch.  The reference does upload ->
+        # propagate -> download strictly in sequence (sim.py:79-110).
+        import collections
         it = batches()
-        cur = next(it, None)
-        if cur is None:
-            return
         up_pool, gpu_pool = self._workers()
-        up_pending = up_pool.submit(self._upload_batch, cur)
-        prev = None                               # (batch, future of its raw results)
+        pending = collections.deque()             # (batch, future of its raw results)
+        defer = os.environ.get('CHROMA_B200_DEFER', '1') != '0'      # 0: read every batch back inside its GPU stage
+
+        def submit(batch):
+            up = up_pool.submit(self._upload_batch, batch)
+            pending.append((batch, gpu_pool.submit(self._gpu_stage, batch, up, defer=defer, **kw)))
+
         try:
-            while cur is not None:
-                uploaded = up_pending.result()
-                gpu_pending = gpu_pool.submit(self._gpu_stage, cur, uploaded, **kw)
+            depth = int(os.environ.get('CHROMA_B200_PIPELINE_DEPTH', self.PIPELINE_DEPTH))
+            for _ in range(max(depth, 1)):
                 nxt = next(it, None)
-                up_pending = up_pool.submit(self._upload_batch, nxt) if nxt is not None else None
-                if prev is not None:
-                    yield from self._host_stage(prev[0], prev[1].result(), **kw)
-                prev = (cur, gpu_pending)
-                cur = nxt
-            yield from self._host_stage(prev[0], prev[1].result(), **kw)
+                if nxt is None:
+                    break
+                submit(nxt)
+            while pending:
+                batch, fut = pending.popleft()
+                raw = self._collect(fut.result())
+                nxt = next(it, None)
+                if nxt is not None:
+                    submit(nxt)
+                yield from self._host_stage(batch, raw, **kw)
         finally:
             # a consumer that stops early must not leave work behind that still uses the RNG pool
-            for f in (up_pending, prev[1] if prev else None):
-                if f is not None:
-                    try:
-                        f.result()
-                    except Exception:
-                        pass
+            for _, f in pending:
+                try:
+                    self._collect(f.result())
+                except Exception:
+                    pass
+
+    PIPELINE_DEPTH = 3
 
     # ------------------------------------------------------------------ PDFs / likelihood
     # Upstream Chroma's Simulation.create_pdf / eval_pdf / eval_kernel, which this fork of the

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CB_ABI_VERSION 3
+#define CB_ABI_VERSION 4
 
 typedef enum {
     CB_OK = 0,
@@ -295,6 +295,21 @@ int cb_copy_photon_hits(const CbPhotonBank* src, uint64_t first, uint64_t n,
                         int32_t* d_channels_out, uint32_t* count_out);
 int cb_copy_photon_queue(const CbPhotonBank* src, const uint32_t* d_queue, uint64_t n,
                          const CbPhotonBank* dst);
+/* get_flat_hits without a host round trip (chroma/gpu/photon.py:141-209 reads the hit count back between
+ * its two kernels): count, scan and scatter are only ENQUEUED on the library stream.  d_block receives the ten
+ * hit arrays back to back, each as long as the number of hits H (words per hit: pos 3, dir 3, pol 3,
+ * wavelength, t, last_hit_triangle, flags, weight, evidx, channel = 16; array k starts at word offset[k] * max(H, 1));
+ * it must hold 16 * n words.  H goes to d_count_out (device).  Read both after cb_event_wait on an event
+ * recorded behind this call. */
+int cb_copy_photon_hits_async(const CbPhotonBank* src, uint64_t first, uint64_t n, uint32_t target_flag,
+                              cb_geom_t g, uint32_t* d_block, uint32_t* d_count_out);
+
+/* ---- completion events for the *_async entry points ---------------------- */
+typedef uint64_t cb_event_t;
+int cb_event_create(cb_event_t* out);
+int cb_event_record(cb_event_t e);      /* marks "everything enqueued on the library stream so far" */
+int cb_event_wait(cb_event_t e);        /* host wait; naps between polls, never spins on a core */
+int cb_event_destroy(cb_event_t e);
 
 /* ---- DAQ (chroma/gpu/daq.py:37-101, chroma/cuda/daq.cu) ----------------- */
 int cb_daq_create(cb_geom_t g, int32_t ndaq, cb_daq_t* out);
@@ -304,6 +319,14 @@ int cb_daq_acquire(cb_daq_t d, const CbPhotonBank* bank, cb_rng_t rng,
                    int32_t nthreads_per_block, int32_t max_blocks,
                    uint64_t start_photon, uint64_t nphotons, float weight);
 int cb_daq_end_acquire(cb_daq_t d);
+/* begin_acquire (if `begin`), acquire and the float conversion of end_acquire (if `finalize`) of ONE
+ * acquisition (chroma/gpu/daq.py:53-101), enqueued on the library stream without a host wait: the
+ * simulation pipeline issues it right behind cb_propagate and moves on to the next event; results are
+ * valid after cb_event_wait on an event recorded behind this call. */
+int cb_daq_acquire_async(cb_daq_t d, const CbPhotonBank* bank, cb_rng_t rng,
+                         int32_t nthreads_per_block, int32_t max_blocks,
+                         uint64_t start_photon, uint64_t nphotons, float weight,
+                         int32_t begin, int32_t finalize);
 /* device pointers of earliest_time(float), q(float), flags(u32), and the raw
  * integer accumulators time_int(u32), q_int(u32); each [nchannels*ndaq] */
 int cb_daq_pointers(cb_daq_t d, void** t, void** q, void** flags,
@@ -314,6 +337,8 @@ int cb_daq_finalize(cb_daq_t d);
  * charges, OR of the histories -- what the atomics of run_daq would have produced had src's photons been
  * acquired into dst (chroma/cuda/daq.cu:73-75).  Folds per-event acquisitions into run-level accumulators. */
 int cb_daq_fold(cb_daq_t dst, cb_daq_t src);
+/* the same, enqueued only (ordered on the library stream; no host wait, does not take the library lock) */
+int cb_daq_fold_async(cb_daq_t dst, cb_daq_t src);
 
 /* ---- multi-GPU: one process per GPU, photon banks partitioned, geometry replicated ------
  * The reference has no multi-GPU path; what it does with atomics on the per-channel arrays of

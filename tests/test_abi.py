@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), 'missing export ' + n
     assert set(names) == set(_lib.SIGNATURES), set(names) ^ set(_lib.SIGNATURES)
-    assert lib.cb_abi_version() == 3
+    assert lib.cb_abi_version() == 4
 
 
 def test_struct_layouts_match_header(tmp_path):

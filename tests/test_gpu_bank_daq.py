@@ -284,6 +284,58 @@ def test_simulation_front_end(gpu_ready):
     assert len(single) == 1 and len(single[0].photons_end) == 1000
 
 
+def test_pipeline_defers_collection_without_changing_results(gpu_ready):
+    """simulate() only enqueues hit compaction and DAQ behind the propagate kernels and collects them
+    from the consumer thread while later batches propagate; the events must be exactly those of the
+    synchronous batch-by-batch path (_simulate_batch: the reference's order, chroma/sim.py:54-154),
+    `gpu_daq` must hold the yielded event's arrays (what a caller folds into run-level accumulators),
+    and more events per batch than ASYNC_EVENTS_MAX must take the synchronous read-back."""
+    geo = scenes.tiny_detector()
+    evs = [scenes.point_source(7000 + 300 * k, seed=70 + k, wl_range=(300, 600)) for k in range(7)]
+    kw = dict(keep_photons_end=True, keep_hits=False, keep_flat_hits=True, run_daq=True, max_steps=60)
+    fields = ('pos', 'dir', 'pol', 'wavelengths', 't', 'last_hit_triangles', 'flags', 'weights', 'evidx', 'channel')
+    for per_batch in (1, 15000, 10 ** 9):
+        s_sync = sim.Simulation(geo, seed=21, nthreads_per_block=256, max_blocks=512)
+        ref, batch, n = [], [], 0
+        for k, p in enumerate(evs):                       # the same batching rule as simulate()
+            ev = event.Event(photons_beg=p)
+            p.evidx[:] = len(batch)
+            batch.append(ev)
+            n += len(p)
+            if n >= per_batch or k == len(evs) - 1:
+                ref += list(s_sync._simulate_batch(batch, **kw))
+                batch, n = [], 0
+        s = sim.Simulation(geo, seed=21, nthreads_per_block=256, max_blocks=512)
+        s.ASYNC_EVENTS_MAX = 3                              # the one-batch case (7 events) reads back synchronously
+        run = gpu.GPUDaq(s.gpu_geometry)
+        run.begin_acquire()
+        out, q_sum = [], 0
+        for ev in s.simulate([event.Event(photons_beg=p) for p in evs], photons_per_batch=per_batch, **kw):
+            if s.last_timings.get('deferred'):
+                run.fold(s.gpu_daq, wait=False)
+                q_sum = q_sum + s.gpu_daq.channel_q_int_gpu.get().astype(np.int64)
+            out.append(ev)
+        assert len(out) == len(ref) == 7
+        assert s.last_timings['deferred'] == (per_batch != 10 ** 9)
+        for a, b in zip(ref, out):
+            assert len(b.flat_hits) > 5
+            for f in fields:
+                assert np.array_equal(getattr(a.flat_hits, f), getattr(b.flat_hits, f)), (per_batch, f)
+            assert np.array_equal(a.photons_end.flags, b.photons_end.flags)
+            assert np.array_equal(a.channels.t, b.channels.t) and np.array_equal(a.channels.q, b.channels.q)
+            assert np.array_equal(a.channels.flags, b.channels.flags) and np.array_equal(a.channels.hit, b.channels.hit)
+        if per_batch != 10 ** 9:
+            run.end_acquire()
+            assert np.array_equal(run.channel_q_int_gpu.get().astype(np.int64), q_sum)
+            assert np.array_equal(run.earliest_time_gpu.get(), np.min([e.channels.t for e in out], axis=0))
+    # an event without any hit, and an empty selection, through the deferred path
+    s = sim.Simulation(geo, seed=3, nthreads_per_block=256, max_blocks=512)
+    dark = scenes.point_source(500, seed=1, wl_range=(300, 600))
+    dark.flags[:] = event.SURFACE_ABSORB                    # terminal before the first step: nothing propagates
+    ev = next(s.simulate(dark, keep_flat_hits=True, keep_hits=True, run_daq=True, max_steps=5))
+    assert len(ev.flat_hits) == 0 and ev.hits == {} and not ev.channels.hit.any()
+
+
 def _gpu_view(gp):
     from types import SimpleNamespace
     return SimpleNamespace(pos=gp.pos, dir=gp.dir, pol=gp.pol, wavelengths=gp.wavelengths, t=gp.t,

@@ -96,3 +96,32 @@ def test_reduce_channels_world_size_2_gloo(tmp_path):
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
         assert 'ok' in o
+
+
+def test_numa_binding_reads_the_gpu_node_from_sysfs(tmp_path, monkeypatch):
+    """bind_to_gpu_numa_node: cores of the GPU's node that this process may use; nothing on a host
+    without NUMA information, when the node covers every usable core, or when switched off."""
+    import os
+    from chroma_lite_b200 import parallel
+    have = sorted(os.sched_getaffinity(0))
+    dev = tmp_path / '0000:66:00.0'
+    dev.mkdir()
+    calls = []
+    monkeypatch.setattr(os, 'sched_setaffinity', lambda pid, cpus: calls.append(set(cpus)))
+    (dev / 'numa_node').write_text('-1\n')
+    (dev / 'local_cpulist').write_text('%d\n' % have[0])
+    assert parallel.bind_to_gpu_numa_node('0000:66:00.0', sysfs=str(tmp_path)) is None and not calls
+    (dev / 'numa_node').write_text('1\n')
+    if len(have) > 1:
+        assert parallel.bind_to_gpu_numa_node('0000:66:00.0'.upper(), sysfs=str(tmp_path)) == [have[0]]
+        assert calls == [{have[0]}]
+        assert parallel._cores_before_binding == len(have)
+        assert parallel.host_threads_should_block(local_world_size=1) == (len(have) < 3)
+    (dev / 'local_cpulist').write_text('%d-%d,100000-100003\n' % (have[0], have[-1]))
+    n = len(calls)
+    assert parallel.bind_to_gpu_numa_node('0000:66:00.0', sysfs=str(tmp_path)) is None and len(calls) == n   # covers everything usable
+    monkeypatch.setenv('CHROMA_B200_NUMA', '0')
+    (dev / 'local_cpulist').write_text('%d\n' % have[0])
+    assert parallel.bind_to_gpu_numa_node('0000:66:00.0', sysfs=str(tmp_path)) is None
+    assert parallel.bind_to_gpu_numa_node('0000:99:00.0', sysfs=str(tmp_path)) is None                    # no such device
+    assert parallel._parse_cpulist('0-3,8,10-11') == {0, 1, 2, 3, 8, 10, 11}
