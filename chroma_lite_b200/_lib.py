@@ -89,6 +89,7 @@ SIGNATURES = {
     'cb_memcpy_d2d': (C.c_int, [vp, vp, u64]),
     'cb_memset32': (C.c_int, [vp, u32, u64]),
     'cb_host_alloc': (C.c_int, [u64, _P(vp)]),
+    'cb_host_alloc_flags': (C.c_int, [u64, i32, _P(vp)]),
     'cb_host_free': (C.c_int, [vp]),
     'cb_mem_info': (C.c_int, [_P(u64), _P(u64)]),
     'cb_timer_start': (C.c_int, []),
@@ -110,6 +111,7 @@ SIGNATURES = {
     'cb_rng_fill_uniform': (C.c_int, [u64, u64, f32, f32, vp]),
     'cb_intersect': (C.c_int, [u64, vp, vp, vp, u64, vp, vp]),
     'cb_propagate': (C.c_int, [_P(CbPhotonBank), u64, u64, i32, i32, i32, i32, i32, _P(CbPropagateStats)]),
+    'cb_photon_bank_upload': (C.c_int, [_P(CbPhotonBank), _P(CbPhotonBank), u64, u32]),
     'cb_photon_duplicate': (C.c_int, [_P(CbPhotonBank), u64, i32]),
     'cb_count_photons': (C.c_int, [_P(CbPhotonBank), u64, u64, u32, _P(u32)]),
     'cb_copy_photons': (C.c_int, [_P(CbPhotonBank), u64, u64, u32, _P(CbPhotonBank), _P(u32)]),

@@ -1063,6 +1063,32 @@ static Tune tune_from_env()
     return t;
 }
 
+// cudaFuncSetAttribute + occupancy query of a kernel, done once per (kernel, CTA size, dynamic shared memory):
+// together they cost ~50 us per propagate call, 1 % of a 2.5 M-photon event
+static int kernel_setup(const void* fn, int threads, size_t smem, int* per_sm)
+{
+    struct Key { const void* fn; int threads; size_t smem; int per_sm; };
+    struct Limit { const void* fn; size_t smem; };
+    static std::vector<Key> cache;
+    static std::vector<Limit> limits;          // dynamic shared memory each kernel has been allowed so far (only ever raised)
+    static std::mutex mu;
+    std::lock_guard<std::mutex> l(mu);
+    Limit* lim = nullptr;
+    for (Limit& x : limits) if (x.fn == fn) lim = &x;
+    if (!lim) { limits.push_back({fn, 0}); lim = &limits.back(); }
+    if (smem > lim->smem || lim->smem == 0) {
+        CB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 16)));
+        lim->smem = std::max<size_t>(smem, 16);
+    }
+    for (const Key& k : cache)
+        if (k.fn == fn && k.threads == threads && k.smem == smem) { *per_sm = k.per_sm; return CB_OK; }
+    int n = 0;
+    CB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, threads, smem));
+    cache.push_back({fn, threads, smem, n});
+    *per_sm = n;
+    return CB_OK;
+}
+
 static int ensure_tile_scratch(uint64_t ntiles)
 {
     Context& c = ctx();
@@ -1224,13 +1250,10 @@ int cb_propagate(const CbPhotonBank* bank, cb_geom_t gh, cb_rng_t rh, int32_t nt
     const size_t smem_tab = (g->smem_table_bytes + 127u) & ~127u;
     const size_t smem_tail = smem_tab + (size_t)(TAIL_THREADS / 32) * (CB_WSTACK + CB_WLEAF) * sizeof(uint2) +
                              (tail_lanes ? (size_t)(TAIL_THREADS / 32) * TAIL_SLOT_WORDS * 32 * sizeof(uint32_t) : 0);
-    CB_CUDA(cudaFuncSetAttribute(k_int, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_int));
-    CB_CUDA(cudaFuncSetAttribute(k_phys, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_tab, 16)));
-    CB_CUDA(cudaFuncSetAttribute(k_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tail));
     int phys_per_sm = 0, tail_per_sm = 0, int_per_sm = 0;
-    CB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&int_per_sm, k_int, INT_THREADS, smem_int));
-    CB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&phys_per_sm, k_phys, PROP_THREADS, smem_tab));
-    CB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tail_per_sm, k_tail, TAIL_THREADS, smem_tail));
+    if ((rc = kernel_setup((const void*)k_int, INT_THREADS, smem_int, &int_per_sm))) return rc;
+    if ((rc = kernel_setup((const void*)k_phys, PROP_THREADS, smem_tab, &phys_per_sm))) return rc;
+    if ((rc = kernel_setup((const void*)k_tail, TAIL_THREADS, smem_tail, &tail_per_sm))) return rc;
     if (int_per_sm < 1 || phys_per_sm < 1 || tail_per_sm < 1) return fail(CB_ERR_CUDA, "cb_propagate: kernels do not fit on an SM");
 
     unsigned long long tot[16] = {0};
@@ -1260,10 +1283,11 @@ int cb_propagate(const CbPhotonBank* bank, cb_geom_t gh, cb_rng_t rh, int32_t nt
         P.counters = c.d_counters;
         CB_CUDA(cudaMemsetAsync(c.d_counters, 0, 16 * sizeof(unsigned long long), c.stream));
         CB_CUDA(cudaMemsetAsync(c.d_step_counts, 0, 2 * c.step_slots * sizeof(unsigned long long), c.stream));
-        c.h_counters[15] = cnt;
-        CB_CUDA(cudaMemcpyAsync(d_alive, c.h_counters + 15, sizeof(unsigned long long), cudaMemcpyHostToDevice, c.stream));
+        c.h_counters[17] = cnt;
+        CB_CUDA(cudaMemcpyAsync(d_alive, c.h_counters + 17, sizeof(unsigned long long), cudaMemcpyHostToDevice, c.stream));
         uint64_t n_alive = cnt;            // host's view: exact after every read-back, an upper bound in between
         bool exact = true;
+        bool counters_read = false;        // the call's counters came back with the last alive count
         int step = 0;
         while (step < max_steps && n_alive > 0) {
             const int nb = std::min(batch, max_steps - step);
@@ -1371,28 +1395,34 @@ int cb_propagate(const CbPhotonBank* bank, cb_geom_t gh, cb_rng_t rh, int32_t nt
                 }
                 exact = false;
             }
+            CB_CUDA(cudaEventRecord(c.kev1, c.stream));      // kernel time ends behind the last launch (re-recorded per batch)
             if (n_alive == 0) break;
-            // one read-back per batch: photons queued for the next step (0 once a tail launch has run)
-            CB_CUDA(cudaMemcpyAsync(c.h_counters, d_alive + step, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c.stream));
+            // one read-back per batch: photons queued for the next step (0 once a tail launch has run), and the
+            // chunk's counters, which are final if that count is 0 -- one host round trip instead of two
+            CB_CUDA(cudaMemcpyAsync(c.h_counters + 16, d_alive + step, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c.stream));
+            CB_CUDA(cudaMemcpyAsync(c.h_counters, c.d_counters, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c.stream));
             CB_CUDA(stream_wait(c.stream));
+            counters_read = true;
             if (trace) {
                 float a = 0, b2 = 0;
                 cudaEventElapsedTime(&a, tev[0], tev[1]); cudaEventElapsedTime(&b2, tev[1], tev[2]);
                 fprintf(stderr, "[cb trace] step %d: %llu rays intersect %.3f ms physics %.3f ms -> %llu alive\n",
-                        step - 1, (unsigned long long)n_alive, a, b2, c.h_counters[0]);
+                        step - 1, (unsigned long long)n_alive, a, b2, c.h_counters[16]);
             }
-            n_alive = c.h_counters[0];
+            n_alive = c.h_counters[16];
             exact = true;
+            if (n_alive) counters_read = false;
         }
-        CB_CUDA(cudaMemcpyAsync(c.h_counters, c.d_counters, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c.stream));
-        CB_CUDA(stream_wait(c.stream));
+        if (!counters_read) {
+            CB_CUDA(cudaMemcpyAsync(c.h_counters, c.d_counters, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c.stream));
+            CB_CUDA(stream_wait(c.stream));
+        }
         for (int i = 1; i < 9; i++) tot[i] += c.h_counters[i];
         if (trace && count)
             fprintf(stderr, "[cb trace] ray iterations: max %llu, >100: %llu, >300: %llu, >1000: %llu, total %llu\n",
                     c.h_counters[9], c.h_counters[10], c.h_counters[11], c.h_counters[12], c.h_counters[13]);
     }
     mark("end");
-    CB_CUDA(cudaEventRecord(c.kev1, c.stream));
     CB_CUDA(event_wait(c.kev1));
     if (timeline) {
         for (size_t i = 1; i < tl_ev.size(); i++) {

@@ -69,15 +69,41 @@ class GPUPhotons(object):
         self.wavelengths = ga.empty(total, np.float32)
         self.t = ga.empty(total, np.float32)
         self.last_hit_triangles = ga.empty(total, np.int32)
-        if not copy_triangles:
-            self.last_hit_triangles.fill(-1)
-        self.flags = ga.empty(total, np.uint32) if copy_flags else ga.zeros(total, np.uint32)
+        self.flags = ga.empty(total, np.uint32)
         self.weights = ga.empty(total, np.float32)
-        if not copy_weights:
-            self.weights.fill(1.0)
         # the reference allocates evidx for nphotons only although photon_duplicate
         # writes all copies; allocate the full size
         self.evidx = ga.empty(total, np.uint32)
+
+        wanted = {'pos': True, 'dir': True, 'pol': True, 'wavelengths': True, 't': True, 'evidx': evidx_value is None,
+                  'last_hit_triangles': copy_triangles, 'flags': copy_flags, 'weights': copy_weights}
+        on_host = nphotons > 0 and not any(isinstance(getattr(photons, f, None), ga.DeviceArray) for f, w in wanted.items() if w)
+        if on_host:
+            # host arrays: the whole bank in one library call (copies and default fills on this thread's copy
+            # stream, one wait, the interpreter lock released throughout)
+            host, keep = _lib.CbPhotonBank(), []
+            for f in _FIELDS:
+                if not wanted[f]:
+                    continue
+                if f in ('pos', 'dir', 'pol'):
+                    a = to_float3(np.asarray(getattr(photons, f)))
+                else:
+                    a = np.ascontiguousarray(getattr(photons, f), dtype=getattr(self, f).dtype)
+                if a.nbytes != nphotons * getattr(self, f).dtype.itemsize:
+                    raise ValueError('photon field %s has %d bytes for %d photons' % (f, a.nbytes, nphotons))
+                keep.append(a)
+                setattr(host, f, a.ctypes.data)
+            dst = self._bank(0, nphotons)
+            _lib.check(_lib.lib().cb_photon_bank_upload(C.byref(dst), C.byref(host), int(nphotons),
+                                                        int(evidx_value or 0)))
+            del keep
+        else:
+            if not copy_triangles:
+                self.last_hit_triangles.fill(-1)
+            if not copy_flags:
+                self.flags.fill(0)
+            if not copy_weights:
+                self.weights.fill(1.0)
 
         def put_vec(dest, source):
             if isinstance(source, ga.DeviceArray):
@@ -91,7 +117,7 @@ class GPUPhotons(object):
             else:
                 dest[:nphotons].set(np.asarray(source, dtype=dtype))
 
-        if nphotons:
+        if nphotons and not on_host:
             jobs = [(put_vec, self.pos, photons.pos), (put_vec, self.dir, photons.dir), (put_vec, self.pol, photons.pol),
                     (put, self.wavelengths, photons.wavelengths, np.float32), (put, self.t, photons.t, np.float32)]
             if evidx_value is None:

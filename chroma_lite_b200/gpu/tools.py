@@ -125,12 +125,14 @@ def format_array(name, array):
 import weakref
 
 
-def pagelocked_empty(shape, dtype, **_ignored):
+def pagelocked_empty(shape, dtype, write_combined=False, **_ignored):
+    """Page-locked host array (pycuda.driver.pagelocked_empty).  write_combined=True (pycuda's
+    host_alloc_flags.WRITECOMBINED): for buffers the CPU only writes and the GPU only reads."""
     dtype = np.dtype(dtype)
     shape = (int(shape),) if np.isscalar(shape) else tuple(int(x) for x in shape)
     nbytes = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
     ptr = C.c_void_p()
-    _lib.check(_lib.lib().cb_host_alloc(max(nbytes, 16), C.byref(ptr)))
+    _lib.check(_lib.lib().cb_host_alloc_flags(max(nbytes, 16), int(bool(write_combined)), C.byref(ptr)))
     buf = (C.c_char * max(nbytes, 16)).from_address(ptr.value)
     weakref.finalize(buf, _lib.lib().cb_host_free, C.c_void_p(ptr.value))
     return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape, dtype=np.int64))).reshape(shape)
@@ -142,9 +144,9 @@ def pagelocked_zeros(shape, dtype, **_ignored):
     return a
 
 
-def pagelocked_copy(arr):
+def pagelocked_copy(arr, write_combined=False):
     arr = np.asarray(arr)
-    a = pagelocked_empty(arr.shape, arr.dtype)
+    a = pagelocked_empty(arr.shape, arr.dtype, write_combined=write_combined)
     a[...] = arr
     return a
 
@@ -161,12 +163,12 @@ def mapped_zeros_like(other, **_ignored):
     return pagelocked_zeros(other.shape, other.dtype)
 
 
-def pin_photons(photons):
+def pin_photons(photons, write_combined=False):
     """A copy of an event.Photons whose arrays live in page-locked host memory."""
     from .. import event
     f = ('pos', 'dir', 'pol', 'wavelengths', 't', 'last_hit_triangles', 'flags', 'weights', 'evidx')
     out = event.Photons.__new__(event.Photons)
     for k in f:
-        setattr(out, k, pagelocked_copy(getattr(photons, k)))
+        setattr(out, k, pagelocked_copy(getattr(photons, k), write_combined=write_combined))
     out.channel = np.asarray(getattr(photons, 'channel', np.zeros(len(photons), dtype=np.uint32)))
     return out

@@ -193,6 +193,7 @@ int cb_memcpy_d2h(void* hptr, const void* dptr, uint64_t bytes);
 int cb_memcpy_d2d(void* dst, const void* src, uint64_t bytes);
 int cb_memset32(void* dptr, uint32_t value, uint64_t count);
 int cb_host_alloc(uint64_t bytes, void** hptr);   /* pinned */
+int cb_host_alloc_flags(uint64_t bytes, int32_t write_combined, void** hptr);   /* pinned; optionally write-combined (upload-only buffers) */
 int cb_host_free(void* hptr);
 int cb_mem_info(uint64_t* free_bytes, uint64_t* total_bytes);
 
@@ -283,6 +284,10 @@ int cb_propagate(const CbPhotonBank* bank, cb_geom_t g, cb_rng_t rng,
                  int32_t use_weights, int32_t scatter_first, CbPropagateStats* stats);
 
 /* ---- photon bank utilities (chroma/cuda/propagate.cu:29-251) ------------ */
+/* GPUPhotons.__init__'s uploads (chroma/gpu/photon.py:46-62: nine gpuarray.to_gpu calls) as one call: `host`
+ * holds HOST pointers (page-locked for full speed); a NULL last_hit_triangles / flags / weights / evidx is
+ * filled with the constructor's default instead (-1, 0, 1.0f, evidx_value) by the copy engine. */
+int cb_photon_bank_upload(const CbPhotonBank* dst, const CbPhotonBank* host, uint64_t n, uint32_t evidx_value);
 int cb_photon_duplicate(const CbPhotonBank* bank, uint64_t nphotons, int32_t ncopies);
 int cb_count_photons(const CbPhotonBank* bank, uint64_t first, uint64_t n,
                      uint32_t target_flag, uint32_t* count_out);

@@ -368,6 +368,30 @@ def test_gpu_photons_from_device_arrays(gpu_ready):
     assert np.allclose(reset.weights.get(), 1.0)
 
 
+def test_bank_upload_from_host_arrays_in_one_call(gpu_ready):
+    """GPUPhotons from host arrays goes through cb_photon_bank_upload: what is copied arrives bit for bit
+    (any input dtype / layout, converted like the reference's to_gpu calls), what is not copied gets the
+    constructor's defaults (gpu/photon.py:46-62), for every copy of ncopies."""
+    ph = scenes.point_source(300001, seed=8, wl_range=(300, 600))
+    ph.flags[:] = np.arange(len(ph)) % 5
+    ph.weights[:] = 0.25
+    ph.last_hit_triangles[:] = np.arange(len(ph)) % 11
+    ph.evidx[:] = 9
+    full = gpu.GPUPhotons(ph).get()
+    for f in ('pos', 'dir', 'pol', 'wavelengths', 't', 'last_hit_triangles', 'flags', 'weights', 'evidx'):
+        assert np.array_equal(getattr(full, f), getattr(ph, f)), f
+    odd = event.Photons(np.asfortranarray(ph.pos.astype(np.float64)), ph.dir, ph.pol, ph.wavelengths.astype(np.float64), ph.t,
+                        ph.last_hit_triangles.astype(np.int64), ph.flags, ph.weights, ph.evidx)
+    got = gpu.GPUPhotons(odd, ncopies=2, copy_flags=False, copy_triangles=False, copy_weights=False, evidx_value=3).get()
+    assert len(got) == 2 * len(ph)
+    for half in (slice(0, len(ph)), slice(len(ph), None)):
+        assert np.array_equal(got.pos[half], ph.pos) and np.array_equal(got.wavelengths[half], ph.wavelengths)
+        assert (got.flags[half] == 0).all() and (got.last_hit_triangles[half] == -1).all()
+        assert (got.weights[half] == 1.0).all() and (got.evidx[half] == 3).all()
+    with pytest.raises(ValueError):
+        gpu.GPUPhotons(event.Photons(ph.pos, ph.dir, ph.pol, ph.wavelengths[:-1], ph.t))
+
+
 def test_simulate_accepts_gpu_photons(gpu_ready, monkeypatch):
     """test_gpu_photon_gpu_input.py:87-108: device-resident sources never go through the host join; several
     of them in one batch are stacked on the device (sim.py:170-226) and give the events of the host path."""
