@@ -468,6 +468,8 @@ def run_ours(args):
         run_daq.fold(s.gpu_daq, wait=False)
         t_prev = time.perf_counter()
     t_loop = time.perf_counter() - t0
+    # the pipeline's own record of this region: (stage, start, end) in ms after t0, first and last batches
+    stage_log = [(st, round((a - t0) * 1e3, 2), round((b - t0) * 1e3, 2)) for st, a, b in list(getattr(s, 'batch_log', [])) if a >= t0]
     run_channels = run_daq.allreduce().get()        # one NCCL exchange over NVLink + read-back (3 x 4 B x channels)
     _lib.check(lib.cb_synchronize())
     barrier(world)
@@ -479,7 +481,8 @@ def run_ours(args):
     mine = {'rank': rank, 'device_ms_per_event': per_event_ms, 'pci_bus_id': pci.value.decode(), 'e2e_s': my_e2e_s, 'loop_s': t_loop, 'allreduce_and_readback_s': my_e2e_s - t_loop,
             'last_batch': dict(s.last_timings), 'yield_gap_ms_median': float(np.median(gaps)) * 1e3,
             'yield_gap_ms_max': float(np.max(gaps)) * 1e3, 'affinity_cores': len(os.sched_getaffinity(0)),
-            'numa_bound': _lib.numa_cores is not None}
+            'numa_bound': _lib.numa_cores is not None, 'first_yield_ms': round(gaps[0] * 1e3, 2),
+            'stage_log_head': stage_log[:9], 'stage_log_tail': stage_log[-4:]}
     per_rank = [mine]
     if world > 1:
         import torch.distributed as dist

@@ -107,6 +107,12 @@ __device__ __forceinline__ uint4 ldg_no_allocate(const uint4* p)
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
     return v;
 }
+#ifndef CB_EXP_PIPELINE
+#define CB_EXP_PIPELINE 1   /* loads of children 4..7 issued while children 0..3 are being tested */
+#endif
+#ifndef CB_ROOMY
+#define CB_ROOMY 1          /* cheap expansion when every expanding lane's stack has room for eight entries (PTrav::process4_roomy) */
+#endif
 #ifndef CB_INT_BLOCKS
 #define CB_INT_BLOCKS 5     /* resident CTAs per SM of the traversal kernels: 5 x 128 threads at 96 registers */
 #endif
@@ -260,6 +266,10 @@ if (giving) { tv.sp -= CB_PSTRIDE; e = lds64(tv.sp); }
         const bool do_tri = active && tv.pop_leaf(lbase, tri);
         const bool do_exp = active && !do_tri && tv.lq == lbase && tv.have;
         const uint32_t first = tv.cur & 0x0FFFFFFFu, n = tv.cur >> 28;
+#if CB_ROOMY
+        // room for eight more entries on every expanding lane's shared-memory stack: the cheap form of the expansion
+        const bool all_roomy = __all_sync(FULL, !do_exp || tv.sp + 8u * CB_PSTRIDE <= sbase + CB_PSTACK * CB_PSTRIDE);
+#endif
         const uint4* blk = do_tri ? reinterpret_cast<const uint4*>(g.tri64) + 4ull * tri : g.nodes + first;
         const uint32_t last_k = do_tri ? 2u : n - 1u;
         uint4 q[4];
@@ -286,14 +296,58 @@ if (giving) { tv.sp -= CB_PSTRIDE; e = lds64(tv.sp); }
             tv.test_triangle(lbase, tri, *reinterpret_cast<const float4*>(&q[0]), *reinterpret_cast<const float4*>(&q[1]),
                              *reinterpret_cast<const float4*>(&q[2]));
         } else if (do_exp) {
-            PTrav::Nearest nr = {0u, __int_as_float(0x7f800000)};
-            tv.template process4<COUNT>(q, 0, n, nr, sbase, lstack, &cnt, g.nodes, g.tri64);
-            if (n > 4) {
+#if CB_ROOMY
+            if (all_roomy) {
+                PTrav::Picked pk = {__int_as_float(0x7f800000), 0u};
+                const uint32_t sp0 = tv.sp;
+#if CB_EXP_PIPELINE == 2
+                const bool more = n > 4;
+                tv.template roomy_child<COUNT>(q[0], 0, n, pk, &cnt);
+                if (more) q[0] = __ldg(g.nodes + first + 4u);
+                tv.template roomy_child<COUNT>(q[1], 1, n, pk, &cnt);
+                if (more) q[1] = __ldg(g.nodes + first + min(5u, n - 1u));
+                tv.template roomy_child<COUNT>(q[2], 2, n, pk, &cnt);
+                if (more) q[2] = __ldg(g.nodes + first + min(6u, n - 1u));
+                tv.template roomy_child<COUNT>(q[3], 3, n, pk, &cnt);
+                if (more) {
+                    q[3] = __ldg(g.nodes + first + min(7u, n - 1u));
+                    tv.template process4_roomy<COUNT>(q, 4, n, pk, &cnt);
+                }
+#elif CB_EXP_PIPELINE
+                // children 4..7 sit in the other two sectors of the node's 128-byte line: their loads are issued
+                // as soon as a pair of registers is free, so that the second memory round trip of an expansion
+                // (91 % of them have more than four children) overlaps the tests of children 0..3
+                const bool more = n > 4;
+                tv.template roomy_child<COUNT>(q[0], 0, n, pk, &cnt);
+                tv.template roomy_child<COUNT>(q[1], 1, n, pk, &cnt);
+                if (more) { q[0] = __ldg(g.nodes + first + 4u); q[1] = __ldg(g.nodes + first + min(5u, n - 1u)); }
+                tv.template roomy_child<COUNT>(q[2], 2, n, pk, &cnt);
+                tv.template roomy_child<COUNT>(q[3], 3, n, pk, &cnt);
+                if (more) {
+                    q[2] = __ldg(g.nodes + first + min(6u, n - 1u)); q[3] = __ldg(g.nodes + first + min(7u, n - 1u));
+                    tv.template process4_roomy<COUNT>(q, 4, n, pk, &cnt);
+                }
+#else
+                tv.template process4_roomy<COUNT>(q, 0, n, pk, &cnt);
+                if (n > 4) {
 #pragma unroll
-                for (int k = 0; k < 4; k++) q[k] = __ldg(g.nodes + first + min(4u + k, n - 1u));
-                tv.template process4<COUNT>(q, 4, n, nr, sbase, lstack, &cnt, g.nodes, g.tri64);
+                    for (int k = 0; k < 4; k++) q[k] = __ldg(g.nodes + first + min(4u + k, n - 1u));
+                    tv.template process4_roomy<COUNT>(q, 4, n, pk, &cnt);
+                }
+#endif
+                tv.expand_end_roomy(pk, sp0, sbase, lstack);
+            } else
+#endif
+            {
+                PTrav::Nearest nr = {0u, __int_as_float(0x7f800000)};
+                tv.template process4<COUNT>(q, 0, n, nr, sbase, lstack, &cnt, g.nodes, g.tri64);
+                if (n > 4) {
+#pragma unroll
+                    for (int k = 0; k < 4; k++) q[k] = __ldg(g.nodes + first + min(4u + k, n - 1u));
+                    tv.template process4<COUNT>(q, 4, n, nr, sbase, lstack, &cnt, g.nodes, g.tri64);
+                }
+                tv.expand_end(nr, sbase, lstack);
             }
-            tv.expand_end(nr, sbase, lstack);
         }
         if (active && !do_exp) tv.after_leaves(sbase, lbase, lstack);
     }

@@ -64,6 +64,15 @@ class Simulation(object):
             _lib.check(_lib.lib().cb_set_blocking_sync(1))
         self.last_timings = {}
 
+    def _log(self, stage, t0, t1):
+        """(stage, start, end) of the last pipeline stages, perf_counter seconds: where a run's time went
+        (bench.py prints the first batches of the end-to-end region from it)."""
+        log = self.__dict__.get('batch_log')
+        if log is None:
+            import collections
+            log = self.batch_log = collections.deque(maxlen=256)
+        log.append((stage, t0, t1))
+
     def _upload_batch(self, batch_events):
         """Host -> device for one batch (runs on the prefetch thread while the previous
         batch propagates; copies use the library's copy stream)."""
@@ -83,7 +92,9 @@ class Simulation(object):
         # array too), so the device array is filled in place instead of crossing PCIe
         gpu_photons = gpu.GPUPhotons(batch, copy_flags=True, copy_triangles=False, copy_weights=False,
                                      evidx_value=0 if len(sources) == 1 and getattr(batch, 'evidx', None) is not None else None)
-        return gpu_photons, bounds, time.perf_counter() - t0
+        t1 = time.perf_counter()
+        self._log('upload', t0, t1)
+        return gpu_photons, bounds, t1 - t0
 
     @staticmethod
     def _is_gpu_photon_source(photons, copy_flags=True, copy_triangles=False, copy_weights=False):
@@ -193,6 +204,7 @@ class Simulation(object):
             raw['marker'] = (markers.pop() if markers else gpu.Marker()).record()
             raw['bank'] = gpu_photons          # in use by the enqueued kernels until the marker has passed
         t4 = time.perf_counter()
+        self._log('gpu', t0b, t4)
         self.last_timings = {'upload_s': upload_s, 'upload_wait_s': t0b - t0, 'propagate_s': t2 - t1, 'readback_s': t3 - t2,
                              'daq_s': t4 - t3, 'nphotons': int(bounds[-1]), 'batch_total_s': t4 - t0, 'deferred': bool(defer)}
         if verbose:
@@ -215,7 +227,9 @@ class Simulation(object):
                 raw['daqs'].append(daq)
         raw.pop('bank', None)
         self._markers_free.append(marker)
-        self.last_timings = dict(self.last_timings, collect_s=time.perf_counter() - t0)
+        t1 = time.perf_counter()
+        self._log('collect', t0, t1)
+        self.last_timings = dict(self.last_timings, collect_s=t1 - t0)
         return raw
 
     def _host_stage(self, batch_events, raw, keep_photons_beg=False, keep_photons_end=False, keep_hits=True,
@@ -277,24 +291,31 @@ class Simulation(object):
         kw = dict(keep_photons_beg=keep_photons_beg, keep_photons_end=keep_photons_end, keep_hits=keep_hits,
                   keep_flat_hits=keep_flat_hits, run_daq=run_daq, max_steps=max_steps)
 
+        def set_evidx(ev, index):
+            evidx = getattr(ev.photons_beg, 'evidx', None)
+            if evidx is None:
+                return
+            if isinstance(evidx, ga.DeviceArray):
+                if ev.nphotons:
+                    evidx[:ev.nphotons].fill(np.uint32(index))
+            else:
+                evidx[:ev.nphotons] = np.uint32(index)
+
         def batches():
+            """Lists of events of >= photons_per_batch photons, each event's evidx set to its place in the
+            batch (chroma/sim.py:256-262).  A batch of ONE host-array event is yielded before that write:
+            its upload fills evidx on the device (_upload_batch), so the 4 bytes per photon written on the
+            host here need not delay it -- the caller does the write once the upload is under way (`late`)."""
             nphotons, batch = 0, []
             for ev in iterable:
                 ev.nphotons = len(ev.photons_beg)
-                evidx = getattr(ev.photons_beg, 'evidx', None)
-                if evidx is not None:
-                    if isinstance(evidx, ga.DeviceArray):
-                        if ev.nphotons:
-                            evidx[:ev.nphotons].fill(np.uint32(len(batch)))
-                    else:
-                        evidx[:ev.nphotons] = np.uint32(len(batch))
                 nphotons += ev.nphotons
                 batch.append(ev)
                 if nphotons >= photons_per_batch:
-                    yield batch
+                    yield self._close_batch(batch, set_evidx)
                     nphotons, batch = 0, []
             if batch:
-                yield batch
+                yield self._close_batch(batch, set_evidx)
 
         # Pipeline, up to DEPTH batches in flight: a worker thread uploads batches on its copy stream as
         # soon as they exist, a second one runs their GPU stages strictly one after the other (so the RNG
@@ -309,9 +330,12 @@ class Simulation(object):
         pending = collections.deque()             # (batch, future of its raw results)
         defer = os.environ.get('CHROMA_B200_DEFER', '1') != '0'      # 0: read every batch back inside its GPU stage
 
-        def submit(batch):
+        def submit(item):
+            batch, late = item
             up = up_pool.submit(self._upload_batch, batch)
             pending.append((batch, gpu_pool.submit(self._gpu_stage, batch, up, defer=defer, **kw)))
+            for ev in late:
+                set_evidx(ev, 0)
 
         try:
             depth = int(os.environ.get('CHROMA_B200_PIPELINE_DEPTH', self.PIPELINE_DEPTH))
@@ -336,6 +360,16 @@ class Simulation(object):
                     pass
 
     PIPELINE_DEPTH = 3
+
+    @staticmethod
+    def _close_batch(batch, set_evidx):
+        """(batch, events whose evidx is still to be written on the host)."""
+        single_host_event = len(batch) == 1 and not isinstance(getattr(batch[0].photons_beg, 'evidx', None), ga.DeviceArray)
+        if single_host_event:
+            return batch, list(batch)
+        for i, ev in enumerate(batch):
+            set_evidx(ev, i)
+        return batch, []
 
     # ------------------------------------------------------------------ PDFs / likelihood
     # Upstream Chroma's Simulation.create_pdf / eval_pdf / eval_kernel, which this fork of the
