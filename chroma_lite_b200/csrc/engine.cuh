@@ -429,6 +429,9 @@ __device__ __forceinline__ bool hit_box_phased(const PhasedRay& r, uint32_t px, 
 #ifndef CB_LANE_PREFETCH
 #define CB_LANE_PREFETCH 0
 #endif
+#ifndef CB_LEAF_PREFETCH
+#define CB_LEAF_PREFETCH 0   /* cheap expansion: prefetch the records of queued triangles (1: to L2, 2: to L1) */
+#endif
 struct PTrav {
     // (the ray's origin and direction are only needed by the triangle test and finish():
     //  they live in three extra shared-memory slots behind the leaf queue, not in registers)
@@ -526,28 +529,39 @@ struct PTrav {
     // 44 instructions per child, 20 of them the plane test); the other entries end up in a slightly
     // different order, which changes nothing but the order of visits.
     struct Picked { float t; uint32_t at; };
-    template <bool COUNT>
-    __device__ __forceinline__ void roomy_child(const uint4& nd, uint32_t idx, uint32_t n, Picked& pk, TraverseCounters* cnt)
+    // EXISTS: the caller knows that child idx exists (children 0 and, behind the n > 4 test, 4)
+    template <bool COUNT, bool EXISTS = false>
+    __device__ __forceinline__ void roomy_child(const uint4& nd, uint32_t idx, uint32_t n, Picked& pk, TraverseCounters* cnt,
+                                                const float4* tri_base = nullptr)
     {
         float tmin;
-        const bool ok = hit_box_phased(r, nd.x, nd.y, nd.z, tmin) && !(tmin > limit) && (idx < n);
+        const bool ok = hit_box_phased(r, nd.x, nd.y, nd.z, tmin) && !(tmin > limit) && (EXISTS || idx < n);
         if (COUNT) cnt->nodes += (idx < n);
         const uint32_t w = nd.w;
         const bool is_leaf = ok && w < 0x10000000u;
         const bool is_int = ok && w >= 0x10000000u;
-        if (is_leaf) sts64(lq, w, __float_as_uint(tmin));
-        lq += is_leaf ? CB_PSTRIDE : 0u;
-        if (is_int) sts64(sp, w, __float_as_uint(tmin));
-        const bool better = is_int && tmin < pk.t;
-        pk.t = better ? tmin : pk.t;
-        pk.at = better ? sp : pk.at;
-        sp += is_int ? CB_PSTRIDE : 0u;
+        if (is_leaf) {
+            sts64(lq, w, __float_as_uint(tmin)); lq += CB_PSTRIDE;
+#if CB_LEAF_PREFETCH == 1
+            { const char* rec = reinterpret_cast<const char*>(tri_base + 4ull * w); prefetch_l2(rec); prefetch_l2(rec + 32); }
+#elif CB_LEAF_PREFETCH == 2
+            { const char* rec = reinterpret_cast<const char*>(tri_base + 4ull * w);
+              asm volatile("prefetch.global.L1 [%0];" ::"l"(rec)); asm volatile("prefetch.global.L1 [%0];" ::"l"(rec + 32)); }
+#endif
+        }
+        if (is_int) {
+            sts64(sp, w, __float_as_uint(tmin));
+            if (tmin < pk.t) { pk.t = tmin; pk.at = sp; }
+            sp += CB_PSTRIDE;
+        }
     }
     template <bool COUNT>
-    __device__ __forceinline__ void process4_roomy(const uint4 (&nd)[4], uint32_t i, uint32_t n, Picked& pk, TraverseCounters* cnt)
+    __device__ __forceinline__ void process4_roomy(const uint4 (&nd)[4], uint32_t i, uint32_t n, Picked& pk, TraverseCounters* cnt,
+                                                   const float4* tri_base = nullptr)
     {
+        roomy_child<COUNT, true>(nd[0], i, n, pk, cnt, tri_base);          // i is 0, or 4 behind the caller's n > 4 test
 #pragma unroll
-        for (int k = 0; k < 4; k++) roomy_child<COUNT>(nd[k], i + k, n, pk, cnt);
+        for (int k = 1; k < 4; k++) roomy_child<COUNT>(nd[k], i + k, n, pk, cnt, tri_base);
     }
     __device__ __forceinline__ void expand_end_roomy(const Picked& pk, uint32_t sp0, uint32_t sbase, const uint2* lstack)
     {

@@ -302,37 +302,37 @@ if (giving) { tv.sp -= CB_PSTRIDE; e = lds64(tv.sp); }
                 const uint32_t sp0 = tv.sp;
 #if CB_EXP_PIPELINE == 2
                 const bool more = n > 4;
-                tv.template roomy_child<COUNT>(q[0], 0, n, pk, &cnt);
+                tv.template roomy_child<COUNT, true>(q[0], 0, n, pk, &cnt, g.tri64);
                 if (more) q[0] = __ldg(g.nodes + first + 4u);
-                tv.template roomy_child<COUNT>(q[1], 1, n, pk, &cnt);
+                tv.template roomy_child<COUNT>(q[1], 1, n, pk, &cnt, g.tri64);
                 if (more) q[1] = __ldg(g.nodes + first + min(5u, n - 1u));
-                tv.template roomy_child<COUNT>(q[2], 2, n, pk, &cnt);
+                tv.template roomy_child<COUNT>(q[2], 2, n, pk, &cnt, g.tri64);
                 if (more) q[2] = __ldg(g.nodes + first + min(6u, n - 1u));
-                tv.template roomy_child<COUNT>(q[3], 3, n, pk, &cnt);
+                tv.template roomy_child<COUNT>(q[3], 3, n, pk, &cnt, g.tri64);
                 if (more) {
                     q[3] = __ldg(g.nodes + first + min(7u, n - 1u));
-                    tv.template process4_roomy<COUNT>(q, 4, n, pk, &cnt);
+                    tv.template process4_roomy<COUNT>(q, 4, n, pk, &cnt, g.tri64);
                 }
 #elif CB_EXP_PIPELINE
                 // children 4..7 sit in the other two sectors of the node's 128-byte line: their loads are issued
                 // as soon as a pair of registers is free, so that the second memory round trip of an expansion
                 // (91 % of them have more than four children) overlaps the tests of children 0..3
                 const bool more = n > 4;
-                tv.template roomy_child<COUNT>(q[0], 0, n, pk, &cnt);
-                tv.template roomy_child<COUNT>(q[1], 1, n, pk, &cnt);
+                tv.template roomy_child<COUNT, true>(q[0], 0, n, pk, &cnt, g.tri64);
+                tv.template roomy_child<COUNT>(q[1], 1, n, pk, &cnt, g.tri64);
                 if (more) { q[0] = __ldg(g.nodes + first + 4u); q[1] = __ldg(g.nodes + first + min(5u, n - 1u)); }
-                tv.template roomy_child<COUNT>(q[2], 2, n, pk, &cnt);
-                tv.template roomy_child<COUNT>(q[3], 3, n, pk, &cnt);
+                tv.template roomy_child<COUNT>(q[2], 2, n, pk, &cnt, g.tri64);
+                tv.template roomy_child<COUNT>(q[3], 3, n, pk, &cnt, g.tri64);
                 if (more) {
                     q[2] = __ldg(g.nodes + first + min(6u, n - 1u)); q[3] = __ldg(g.nodes + first + min(7u, n - 1u));
-                    tv.template process4_roomy<COUNT>(q, 4, n, pk, &cnt);
+                    tv.template process4_roomy<COUNT>(q, 4, n, pk, &cnt, g.tri64);
                 }
 #else
-                tv.template process4_roomy<COUNT>(q, 0, n, pk, &cnt);
+                tv.template process4_roomy<COUNT>(q, 0, n, pk, &cnt, g.tri64);
                 if (n > 4) {
 #pragma unroll
                     for (int k = 0; k < 4; k++) q[k] = __ldg(g.nodes + first + min(4u + k, n - 1u));
-                    tv.template process4_roomy<COUNT>(q, 4, n, pk, &cnt);
+                    tv.template process4_roomy<COUNT>(q, 4, n, pk, &cnt, g.tri64);
                 }
 #endif
                 tv.expand_end_roomy(pk, sp0, sbase, lstack);
