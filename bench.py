@@ -468,6 +468,8 @@ def run_ours(args):
         run_daq.fold(s.gpu_daq, wait=False)
         t_prev = time.perf_counter()
     t_loop = time.perf_counter() - t0
+    if getattr(s, 'last_h2d_bytes', None) is not None:
+        h2d = s.last_h2d_bytes            # counted by the upload itself (all-zero flags / times are zeroed on the device, not sent)
     # the pipeline's own record of this region: (stage, start, end) in ms after t0, first and last batches
     stage_log = [(st, round((a - t0) * 1e3, 2), round((b - t0) * 1e3, 2)) for st, a, b in list(getattr(s, 'batch_log', [])) if a >= t0]
     run_channels = run_daq.allreduce().get()        # one NCCL exchange over NVLink + read-back (3 x 4 B x channels)

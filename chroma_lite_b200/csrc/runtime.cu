@@ -419,14 +419,15 @@ int cb_photon_bank_upload(const CbPhotonBank* dst, const CbPhotonBank* host, uin
     if (dst->n < n) return fail(CB_ERR_INVALID, "cb_photon_bank_upload: device bank too small");
     if (!dst->pos || !dst->dir || !dst->pol || !dst->wavelengths || !dst->t || !dst->last_hit_triangles || !dst->flags || !dst->weights)
         return fail(CB_ERR_INVALID, "cb_photon_bank_upload: device bank has null arrays");
-    if (!host->pos || !host->dir || !host->pol || !host->wavelengths || !host->t)
-        return fail(CB_ERR_INVALID, "cb_photon_bank_upload: pos, dir, pol, wavelengths and t are required");
+    if (!host->pos || !host->dir || !host->pol || !host->wavelengths)
+        return fail(CB_ERR_INVALID, "cb_photon_bank_upload: pos, dir, pol and wavelengths are required");
     cudaStream_t s = thread_copy_stream();
     CB_CUDA(cudaMemcpyAsync(dst->pos, host->pos, n * 12, cudaMemcpyHostToDevice, s));
     CB_CUDA(cudaMemcpyAsync(dst->dir, host->dir, n * 12, cudaMemcpyHostToDevice, s));
     CB_CUDA(cudaMemcpyAsync(dst->pol, host->pol, n * 12, cudaMemcpyHostToDevice, s));
     CB_CUDA(cudaMemcpyAsync(dst->wavelengths, host->wavelengths, n * 4, cudaMemcpyHostToDevice, s));
-    CB_CUDA(cudaMemcpyAsync(dst->t, host->t, n * 4, cudaMemcpyHostToDevice, s));
+    if (host->t) CB_CUDA(cudaMemcpyAsync(dst->t, host->t, n * 4, cudaMemcpyHostToDevice, s));
+    else CB_CUDA(cudaMemsetAsync(dst->t, 0, n * 4, s));
     if (host->last_hit_triangles) CB_CUDA(cudaMemcpyAsync(dst->last_hit_triangles, host->last_hit_triangles, n * 4, cudaMemcpyHostToDevice, s));
     else CB_CUDA(cudaMemsetAsync(dst->last_hit_triangles, 0xFF, n * 4, s));                       // -1
     if (host->flags) CB_CUDA(cudaMemcpyAsync(dst->flags, host->flags, n * 4, cudaMemcpyHostToDevice, s));

@@ -94,6 +94,7 @@ class Simulation(object):
                                      evidx_value=0 if len(sources) == 1 and getattr(batch, 'evidx', None) is not None else None)
         t1 = time.perf_counter()
         self._log('upload', t0, t1)
+        self.last_h2d_bytes = getattr(gpu_photons, 'h2d_bytes', None)      # what this batch really sent, when known
         return gpu_photons, bounds, t1 - t0
 
     @staticmethod

@@ -285,8 +285,8 @@ int cb_propagate(const CbPhotonBank* bank, cb_geom_t g, cb_rng_t rng,
 
 /* ---- photon bank utilities (chroma/cuda/propagate.cu:29-251) ------------ */
 /* GPUPhotons.__init__'s uploads (chroma/gpu/photon.py:46-62: nine gpuarray.to_gpu calls) as one call: `host`
- * holds HOST pointers (page-locked for full speed); a NULL last_hit_triangles / flags / weights / evidx is
- * filled with the constructor's default instead (-1, 0, 1.0f, evidx_value) by the copy engine. */
+ * holds HOST pointers (page-locked for full speed); a NULL t / last_hit_triangles / flags / weights / evidx is
+ * filled with the constructor's default instead (0, -1, 0, 1.0f, evidx_value) by the copy engine. */
 int cb_photon_bank_upload(const CbPhotonBank* dst, const CbPhotonBank* host, uint64_t n, uint32_t evidx_value);
 int cb_photon_duplicate(const CbPhotonBank* bank, uint64_t nphotons, int32_t ncopies);
 int cb_count_photons(const CbPhotonBank* bank, uint64_t first, uint64_t n,

@@ -380,6 +380,19 @@ def test_bank_upload_from_host_arrays_in_one_call(gpu_ready):
     full = gpu.GPUPhotons(ph).get()
     for f in ('pos', 'dir', 'pol', 'wavelengths', 't', 'last_hit_triangles', 'flags', 'weights', 'evidx'):
         assert np.array_equal(getattr(full, f), getattr(ph, f)), f
+    # all-zero flags / times are zeroed on the device instead of being sent; anything else is sent
+    ph.flags[:] = 0
+    ph.t[:] = 1.5
+    sent = gpu.GPUPhotons(ph)
+    assert sent.h2d_bytes == len(ph) * (36 + 4 * 5)
+    back = sent.get()
+    assert (back.flags == 0).all() and (back.t == 1.5).all() and np.array_equal(back.last_hit_triangles, ph.last_hit_triangles)
+    ph.t[:] = 0
+    ph.t[7] = -0.0                                         # not the all-zero bit pattern: sent as it is
+    assert gpu.GPUPhotons(ph).h2d_bytes == len(ph) * (36 + 4 * 5)
+    ph.t[7] = 0
+    none = gpu.GPUPhotons(ph)
+    assert none.h2d_bytes == len(ph) * (36 + 4 * 4) and (none.get().t == 0).all()
     odd = event.Photons(np.asfortranarray(ph.pos.astype(np.float64)), ph.dir, ph.pol, ph.wavelengths.astype(np.float64), ph.t,
                         ph.last_hit_triangles.astype(np.int64), ph.flags, ph.weights, ph.evidx)
     got = gpu.GPUPhotons(odd, ncopies=2, copy_flags=False, copy_triangles=False, copy_weights=False, evidx_value=3).get()
