@@ -471,7 +471,7 @@ def run_ours(args):
     if getattr(s, 'last_h2d_bytes', None) is not None:
         h2d = s.last_h2d_bytes            # counted by the upload itself (all-zero flags / times are zeroed on the device, not sent)
     # the pipeline's own record of this region: (stage, start, end) in ms after t0, first and last batches
-    stage_log = [(st, round((a - t0) * 1e3, 2), round((b - t0) * 1e3, 2)) for st, a, b in list(getattr(s, 'batch_log', [])) if a >= t0]
+    stage_log = [(x[0], round((x[1] - t0) * 1e3, 2), round((x[2] - t0) * 1e3, 2)) + tuple(x[3:]) for x in list(getattr(s, 'batch_log', [])) if x[1] >= t0]
     run_channels = run_daq.allreduce().get()        # one NCCL exchange over NVLink + read-back (3 x 4 B x channels)
     _lib.check(lib.cb_synchronize())
     barrier(world)

@@ -64,14 +64,14 @@ class Simulation(object):
             _lib.check(_lib.lib().cb_set_blocking_sync(1))
         self.last_timings = {}
 
-    def _log(self, stage, t0, t1):
+    def _log(self, stage, t0, t1, *extra):
         """(stage, start, end) of the last pipeline stages, perf_counter seconds: where a run's time went
         (bench.py prints the first batches of the end-to-end region from it)."""
         log = self.__dict__.get('batch_log')
         if log is None:
             import collections
             log = self.batch_log = collections.deque(maxlen=256)
-        log.append((stage, t0, t1))
+        log.append((stage, t0, t1) + extra)
 
     def _upload_batch(self, batch_events):
         """Host -> device for one batch (runs on the prefetch thread while the previous
@@ -205,7 +205,8 @@ class Simulation(object):
             raw['marker'] = (markers.pop() if markers else gpu.Marker()).record()
             raw['bank'] = gpu_photons          # in use by the enqueued kernels until the marker has passed
         t4 = time.perf_counter()
-        self._log('gpu', t0b, t4)
+        st = getattr(gpu_photons, 'last_stats', None)
+        self._log('gpu', t0b, t4, round(t2 - t1, 6), round(getattr(st, 'kernel_ms', 0.0), 3), round(getattr(st, 'tail_ms', 0.0), 3))
         self.last_timings = {'upload_s': upload_s, 'upload_wait_s': t0b - t0, 'propagate_s': t2 - t1, 'readback_s': t3 - t2,
                              'daq_s': t4 - t3, 'nphotons': int(bounds[-1]), 'batch_total_s': t4 - t0, 'deferred': bool(defer)}
         if verbose:

@@ -28,9 +28,12 @@ def main():
     steps = int(os.environ.get('STEPS', '20'))
     run_daq = gpu.GPUDaq(s.gpu_geometry)
     run_daq.begin_acquire(); run_daq.allreduce()
-    for name, wc, skip in (('pinned, zeros sent', False, '0'), ('pinned, zeros skipped', False, '1'),
-                           ('write-combined, zeros sent', True, '0'), ('write-combined, zeros skipped', True, '1'),
-                           ('pinned, zeros sent', False, '0'), ('pinned, zeros skipped', False, '1')):
+    variants = (('pinned, zeros sent', False, '0'), ('pinned, zeros skipped', False, '1'),
+                ('write-combined, zeros sent', True, '0'), ('write-combined, zeros skipped', True, '1'),
+                ('pinned, zeros sent', False, '0'), ('pinned, zeros skipped', False, '1'))
+    if os.environ.get('VARIANTS'):
+        variants = variants[:int(os.environ['VARIANTS'])]
+    for name, wc, skip in variants:
         os.environ['CHROMA_B200_SKIP_ZERO'] = skip
         ev = gpu.pin_photons(base, write_combined=wc)
         list(s.simulate((event.Event(photons_beg=ev) for _ in range(5)), **kw))
@@ -45,11 +48,13 @@ def main():
         run_daq.allreduce().get()
         lib.cb_synchronize(); bench.barrier(world)
         dt = bench.max_over_ranks(time.perf_counter() - t0, world)
-        ups = [b - a for st, a, b in s.batch_log if st == 'upload' and a >= t0]
+        ups = [x[2] - x[1] for x in s.batch_log if x[0] == 'upload' and x[1] >= t0]
         up_max = bench.max_over_ranks(float(np.median(ups)), world)
         first = bench.max_over_ranks(gaps[0], world)
         gap = bench.max_over_ranks(float(np.median(gaps)), world)
         if rank == 0:
+            print('   uploads ms:', ' '.join('%.1f' % (u * 1e3) for u in ups), flush=True)
+            print('   gpu stages ms (stage, propagate call, kernels, tail):', ' '.join('%.1f/%.1f/%.1f/%.1f' % ((x[2] - x[1]) * 1e3, x[3] * 1e3, x[4], x[5]) for x in s.batch_log if x[0] == 'gpu' and x[1] >= t0), flush=True)
             print('%-32s e2e %.1f M photons/s  (%.1f ms; first yield %.1f ms, median gap %.2f ms, median upload max over ranks %.2f ms, h2d %d B/photon)'
                   % (name, world * n * steps / dt / 1e6, dt * 1e3, first * 1e3, gap * 1e3, up_max * 1e3, s.last_h2d_bytes // n), flush=True)
     if world > 1:
