@@ -399,7 +399,7 @@ static int ones_buffer(uint64_t n, const float** out)
     if (g_ones_n < n) {
         // the old buffer may still feed a copy in flight on another thread's stream: it is never freed, only outgrown
         float* p = nullptr;
-        const uint64_t cap = std::max<uint64_t>(n, 1u << 20);
+        const uint64_t cap = std::max<uint64_t>(std::max<uint64_t>(n, 2 * g_ones_n), 1u << 20);    // geometric: outgrown buffers stay bounded
         CB_CUDA(cudaMalloc(&p, cap * 4));
         cudaStream_t s = ctx().copy_stream;
         fill32_launch((uint32_t*)p, 0x3F800000u, cap, s);

@@ -336,10 +336,13 @@ class PendingHits(object):
     def __init__(self, block, count_ptr, source):
         self.block, self.count_ptr, self.source = block, count_ptr, source      # `source` keeps the bank alive
 
-    def get(self, marker=None):
-        """event.Photons of the hits (with .channel); `marker` must have been recorded behind the
-        compaction (the caller waits on it once for everything the batch enqueued)."""
-        if marker is not None:
+    def get(self, marker=None, ready=False):
+        """event.Photons of the hits (with .channel).  `marker` must have been recorded behind the
+        compaction; ready=True: the caller has already waited for it (once for everything the batch
+        enqueued); with neither, the whole device is synchronised."""
+        if ready:
+            pass
+        elif marker is not None:
             marker.wait()
         else:
             _lib.check(_lib.lib().cb_synchronize())

@@ -221,7 +221,7 @@ class Simulation(object):
         t0 = time.perf_counter()
         marker.wait()
         if 'pending_hits' in raw:
-            raw['hits'] = raw.pop('pending_hits').get(marker)
+            raw['hits'] = raw.pop('pending_hits').get(marker, ready=True)
         if 'pending_channels' in raw:
             raw['channels'], raw['daqs'] = [], []
             for daq, ch in raw.pop('pending_channels'):
