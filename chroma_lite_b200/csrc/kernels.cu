@@ -1206,9 +1206,8 @@ int cb_intersect(cb_geom_t gh, const float* d_origins, const float* d_directions
     if (int lrc = l2_pin_tree_prefix(g)) return lrc;
     CB_CUDA(cudaMemsetAsync(c.d_counters, 0, 16 * sizeof(unsigned long long), c.stream));
     const size_t smem = stack_smem_bytes();
-    CB_CUDA(cudaFuncSetAttribute(intersect_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    CB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, intersect_kernel<false>, INT_THREADS, smem));
+    if (int src = kernel_setup((const void*)intersect_kernel<false>, INT_THREADS, smem, &per_sm)) return src;
     if (per_sm < 1) per_sm = 1;
     unsigned blocks = (unsigned)std::min<uint64_t>((n + INT_THREADS - 1) / INT_THREADS, (uint64_t)c.sm_count * per_sm);
     RaySource src = {d_origins, d_directions, d_last_hit, d_triangle_out, d_distance_out};
