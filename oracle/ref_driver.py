@@ -419,6 +419,25 @@ def intersect(geom, origins, directions, last_hit=None, block=64):
     return from_dev(tri), from_dev(dist), ms
 
 
+class ResidentRays(object):
+    """Rays and result arrays kept on the device: the reference's intersect_mesh timed launch after launch
+    without the upload in between (bench.py --workload rays --impl reference)."""
+    def __init__(self, origins, directions):
+        self.n = len(origins)
+        self.o = to_dev(np.asarray(origins, dtype=np.float32))
+        self.d = to_dev(np.asarray(directions, dtype=np.float32))
+        self.tri = to_dev(np.full(self.n, -1, dtype=np.int32))
+        self.dist = to_dev(np.zeros(self.n, dtype=np.float32))
+        self.timer = Timer()
+
+    def launch(self, geom, block=64):
+        """One launch over all rays; returns its device time in ms."""
+        self.timer.start()
+        module('ref_wrap.cubin').launch('ref_intersect', self.n // block + 1, block, C.c_int(self.n), self.o, self.d, None,
+                                        geom.gpudata, self.tri, self.dist)
+        return self.timer.stop()
+
+
 def rng_words(n, seed, first_stream=0, offset=0, ndraw=4):
     """(words uint32 (n,ndraw), state6 uint32 (n,6)) straight from curand_init/curand."""
     out = to_dev(np.zeros((n, ndraw), dtype=np.uint32))
