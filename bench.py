@@ -770,11 +770,8 @@ def run_rays(args):
     for _ in range(args.steps):
         lib.cb_flush_l2()
         _lib.check(lib.cb_synchronize())
-        _lib.check(lib.cb_timer_start())
-        tri, dist = gpu.intersect_mesh(g, do, dd)
-        t = _lib.C.c_float()
-        _lib.check(lib.cb_timer_stop(_lib.C.byref(t)))
-        ms.append(t.value)
+        ms.append(timed_call())          # (the result arrays are dropped at once: holding them across steps made the
+                                         #  second step allocate a new pair inside its timed span -- a cudaMalloc of 1-100 ms)
     if os.environ.get('BENCH_DEBUG'):
         log('timed', ' '.join('%.2f' % x for x in ms))
     # e2e: host arrays in (page-locked), triangle + distance back on the host
@@ -789,8 +786,7 @@ def run_rays(args):
                      'd2h_bytes_per_step': int(ht.nbytes + hd.nbytes)},
                 extra={'hit_fraction': float((ht >= 0).mean()), 'ms_steps': [round(x, 3) for x in ms],
                        'ms_per_step_median': float(np.median(ms)),
-                       'note': 'value is the mean over the steps; single steps of 100-200 ms (host stalls between the start event and '
-                               'the launch, seen on some boxes) show up in ms_steps'})
+                       'note': 'value is the mean over the steps; ms_steps lists them'})
     emit(line)
 
 

@@ -4,7 +4,7 @@ from .tools import (create_cuda_context, get_rng_states, chunk_iterator, to_floa
                     mapped_empty, mapped_zeros, mapped_empty_like, mapped_zeros_like, pin_photons)
 from .geometry import GPUGeometry  # noqa: F401
 from .detector import GPUDetector  # noqa: F401
-from .photon import GPUPhotons, GPUPhotonsSlice, PendingHits, Marker  # noqa: F401
+from .photon import GPUPhotons, GPUPhotonsSlice, PendingHits, Marker, reserve_banks  # noqa: F401
 from .daq import GPUDaq, GPUChannels  # noqa: F401
 from .intersect import intersect_mesh  # noqa: F401
 from .pdf import GPUPDF, GPUKernelPDF  # noqa: F401

@@ -57,6 +57,15 @@ def _alloc_bank(n):
                 weights=ga.empty(n, np.float32), evidx=ga.empty(n, np.uint32))
 
 
+def reserve_banks(nphotons, count):
+    """Cache the device blocks of `count` photon banks of `nphotons` photons and of their packed hit blocks
+    (GPUPhotons.flat_hits_async) ahead of time: a pipeline that holds several batches in flight then never
+    allocates while kernels run."""
+    ga.reserve(3 * nphotons, np.float32, 3 * count)   # pos, dir, pol
+    ga.reserve(nphotons, np.float32, 6 * count)       # wavelengths, t, last_hit_triangles, flags, weights, evidx
+    ga.reserve(max(int(nphotons), 1) * 16 + 1, np.uint32, max(2, count - 1))
+
+
 class GPUPhotons(object):
     def __init__(self, photons, ncopies=1, copy_flags=True, copy_triangles=True, copy_weights=True, evidx_value=None):
         """Load ``photons`` onto the GPU, replicating ``ncopies`` times

@@ -66,6 +66,24 @@ class _Pool(object):
         for p in blocks:
             _lib._lib.cb_free(C.c_void_p(p))
 
+    def reserve(self, nbytes, count):
+        """Make sure `count` free blocks of this size are cached: a pipeline allocates them NOW, while
+        nothing is running, instead of meeting a cudaMalloc (which waits for the kernels in flight and can
+        take milliseconds) the first time it happens to hold one block more than ever before."""
+        size = self.bucket(nbytes)
+        made = 0
+        while True:
+            with self.lock:
+                if len(self.free.get(size, ())) >= count or self.cached + size > self.LIMIT:
+                    return made
+            p = C.c_void_p()
+            if _lib.lib().cb_malloc(size, C.byref(p)) != 0:
+                return made
+            with self.lock:
+                self.free.setdefault(size, []).append(p.value)
+                self.cached += size
+            made += 1
+
 
 _pool = _Pool()
 
@@ -135,6 +153,12 @@ def host_result(shape, dtype):
         shape = (int(shape),)
     out = _host_pool.array(tuple(int(x) for x in shape), dtype)
     return out if out is not None else np.empty(shape, dtype=dtype)
+
+
+def reserve(shape, dtype, count):
+    """Pre-populate the device block cache with `count` blocks that fit an array of this shape."""
+    n = int(np.prod(shape, dtype=np.int64)) if not np.isscalar(shape) else int(shape)
+    return _pool.reserve(max(n * np.dtype(dtype).itemsize, 16), int(count))
 
 
 def empty_cache():

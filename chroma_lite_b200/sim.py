@@ -88,6 +88,13 @@ class Simulation(object):
                                                    copy_weights=False)
             if batch is None:
                 batch = event.Photons.join(sources)
+        # the first large batch of a size: cache the device blocks of every batch the pipeline can hold in flight
+        # now, while nothing runs (a cudaMalloc met later waits for the kernels in flight)
+        n = int(bounds[-1])
+        reserve = getattr(gpu, 'reserve_banks', None)
+        if reserve is not None and n >= 200000 and n not in self.__dict__.setdefault('_reserved', set()):
+            self._reserved.add(n)
+            reserve(n, self.PIPELINE_DEPTH + 2)
         # a batch of one event: its evidx is 0 throughout (simulate() has just written that into the host
         # array too), so the device array is filled in place instead of crossing PCIe
         gpu_photons = gpu.GPUPhotons(batch, copy_flags=True, copy_triangles=False, copy_weights=False,
