@@ -143,3 +143,52 @@ def test_loader_uses_and_fills_the_bvh_cache(tmp_path, monkeypatch):
     g6 = demo.tiny()
     g6.bvh = 'kept'
     assert loader.create_geometry_from_obj(g6, cache_dir=d).bvh == 'kept'
+
+
+def test_device_block_cache_reserve_and_reuse(monkeypatch):
+    """gpuarray._Pool: blocks are cached by bucketed size; reserve() pre-populates a bucket (so that a pipeline
+    never meets cudaMalloc while kernels run) and stops at the cache limit; take() hands reserved blocks out."""
+    import ctypes as C
+    from chroma_lite_b200 import gpuarray as ga
+
+    class FakeLib(object):
+        def __init__(self):
+            self.next, self.freed = 0x1000, []
+
+        def cb_malloc(self, size, pptr):
+            pptr._obj.value = self.next
+            self.next += int(size)
+            return 0
+
+        def cb_free(self, p):
+            self.freed.append(p.value)
+            return 0
+
+    fake = FakeLib()
+    monkeypatch.setattr(ga._lib, 'lib', lambda: fake)
+    monkeypatch.setattr(ga._lib, '_lib', fake)
+    pool = ga._Pool()
+    assert pool.bucket(1) == 256 and pool.bucket(300) == 512 and pool.bucket(16 << 20) == 16 << 20
+    assert pool.bucket((16 << 20) + 1) == 18 << 20                      # 2 MiB steps above 16 MiB
+    assert pool.reserve(30000000, 3) == 3 and pool.reserve(30000000, 3) == 0 and pool.reserve(30000000, 5) == 2
+    size = pool.bucket(30000000)
+    assert len(pool.free[size]) == 5 and pool.cached == 5 * size
+    got = [pool.take(size) for _ in range(6)]
+    assert got[5] is None and len(set(got[:5])) == 5 and pool.cached == 0
+    assert pool.give(got[0], size) and pool.take(size) == got[0]
+    pool.LIMIT = 3 * size
+    assert pool.reserve(30000000, 10) == 3                               # the cache limit bounds a reservation
+    pool.release_all()
+    assert len(fake.freed) == 3 and pool.cached == 0
+
+
+def test_bench_warm_up_waits_for_stable_times():
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    series = iter([9.0, 5.0, 4.0, 3.0, 2.5] + [2.0] * 1000)
+    n = bench.warm_until_stable(lambda: next(series), min_calls=10, min_s=0.0, max_s=5.0)
+    assert n == 15                                                      # two consecutive groups of five within 2 %
+    calls = []
+    n = bench.warm_until_stable(lambda: calls.append(1) or float(len(calls)), min_calls=5, min_s=0.0, max_s=0.05)
+    assert n == len(calls) and n >= 10                                   # never stable: stops at max_s
